@@ -1,0 +1,166 @@
+"""Deterministic synthetic checkpoints, inputs and noise (no network, no real checkpoints).
+
+Recipe follows SURVEY.md §8(d): seeded weights stored through fp16 exactly like real RVC
+"small model" files (/root/reference/training_cli.py:41-45), non-zero
+`flow.flows.*.post` (the reference zero-initialises it, modules.py:432-434, which would make
+the flow an identity and hide bugs), `phone ~ N(0,1)`, a smooth voiced f0 contour with
+unvoiced gaps, `pitch` from the reference's mel quantiser
+(/root/reference/pitch_extraction.py:266-267,296-302; lib/audio.py:302-304), and the three noise tensors drawn in the
+reference's call order (models.py:685/801 `randn_like[B,192,T]`, :378 `rand(B,1)`,
+:409 `randn_like[B,L,1]`).
+
+Everything is generated on the CPU with `torch.Generator` so the same seeds give the same
+tensors in the build container and on the GPU box (same image, same torch build).
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+
+from .config import SynthConfig, state_dict_shapes
+
+
+def _fan_in(shape) -> int:
+    n = 1
+    for d in shape[1:]:
+        n *= d
+    return max(n, 1)
+
+
+def make_state_dict(cfg: SynthConfig, seed: int = 0, fp16_roundtrip: bool = True) -> Dict[str, torch.Tensor]:
+    """Random but well-conditioned weights in the reference state_dict layout.
+
+    Weight-normed layers get independent `weight_v` and a `weight_g` that is the row norm of v
+    perturbed by ±10 % so the fold `g*v/||v||` is actually exercised.  Gains are chosen so that
+    activations stay O(1) through the 72 residual convs, LeakyReLU sees both signs and the
+    final tanh is neither saturated nor tiny.
+    """
+    shapes = state_dict_shapes(cfg)
+    sd: Dict[str, torch.Tensor] = {}
+    for key in sorted(shapes):
+        shape = shapes[key]
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFF)
+        if key.endswith("weight_g"):
+            continue  # derived from weight_v below
+        r = torch.randn(shape, generator=g, dtype=torch.float32)
+        if key.endswith(".gamma"):
+            t = 1.0 + 0.1 * r
+        elif key.endswith(".beta"):
+            t = 0.1 * r
+        elif key.endswith(".bias"):
+            t = 0.05 * r
+        elif key == "emb_g.weight":
+            t = r
+        elif key == "enc_p.emb_pitch.weight":
+            t = 0.05 * r
+        elif "emb_rel_" in key:
+            t = r * (shape[-1] ** -0.5)
+        elif key == "dec.m_source.l_linear.weight":
+            t = 0.8 + 0.1 * r
+        elif key.startswith("dec.ups.") and key.endswith("weight_v"):
+            # ConvTranspose1d [C_in, C_out, k]; each output sample sees k/u taps of C_in inputs
+            i = int(key.split(".")[2])
+            taps = max(shape[2] // cfg.upsample_rates[i], 1)
+            t = r * (1.4 / math.sqrt(shape[0] * taps))
+        elif key.startswith("dec.noise_convs."):
+            t = r * (8.0 / math.sqrt(shape[2]))
+        elif key.startswith("dec.resblocks."):
+            t = r * (0.9 / math.sqrt(_fan_in(shape)))
+        elif key == "dec.conv_post.weight":
+            t = r * (0.3 / math.sqrt(_fan_in(shape)))
+        elif key.endswith(".post.weight"):
+            t = r * (0.5 / math.sqrt(_fan_in(shape)))
+        elif key == "enc_p.proj.weight":
+            t = r * (0.45 / math.sqrt(_fan_in(shape)))
+        else:
+            t = r * (1.0 / math.sqrt(_fan_in(shape)))
+        sd[key] = t
+    for key in sorted(shapes):
+        if key.endswith("weight_g"):
+            v = sd[key[:-1] + "v"]
+            gk = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFF)
+            norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(shapes[key])
+            sd[key] = norm * (1.0 + 0.1 * torch.randn(shapes[key], generator=gk))
+    if fp16_roundtrip:
+        sd = {k: v.half().float() for k, v in sd.items()}
+    return sd
+
+
+def coarse_pitch(f0: np.ndarray, f0_min: float = 50.0, f0_max: float = 1100.0, bins: int = 256) -> np.ndarray:
+    """Mel quantiser of /root/reference/pitch_extraction.py:266-267,296-302 (hz_to_mel = 2595 log10(1+f/700),
+    lib/audio.py:302-304; the constant cancels in the ratio)."""
+    mel = lambda f: 1127.0 * np.log(1.0 + np.asarray(f, dtype=np.float64) / 700.0)
+    m_min, m_max = mel(f0_min), mel(f0_max)
+    m = mel(f0)
+    m = (m - m_min) * (bins - 2) / (m_max - m_min) + 1
+    m = np.clip(m, 1, bins - 1)
+    return np.rint(m).astype(np.int64)
+
+
+def make_f0(T: int, frame_rate: float = 100.0, variant: str = "contour", seed: int = 1) -> np.ndarray:
+    """Synthetic f0 [T] in Hz: 220·2^(0.5 sin(2π 0.3 t)) with 0.7 s unvoiced gaps every 5 s."""
+    t = np.arange(T, dtype=np.float64) / frame_rate
+    if variant == "contour":
+        f0 = 220.0 * np.power(2.0, 0.5 * np.sin(2 * np.pi * 0.3 * t))
+    elif variant == "uniform":
+        rng = np.random.default_rng(seed)
+        f0 = rng.uniform(100.0, 400.0, size=T)
+    elif variant == "unvoiced":
+        f0 = np.zeros(T)
+    else:
+        raise ValueError(variant)
+    if variant != "unvoiced":
+        gap = (np.mod(t, 5.0) >= 2.0) & (np.mod(t, 5.0) < 2.7)
+        f0 = np.where(gap, 0.0, f0)
+    return f0.astype(np.float32)
+
+
+def make_inputs(cfg: SynthConfig, B: int, T: int, seed: int = 1, lengths=None, f0_variant: str = "contour"):
+    """(phone[B,T,C_f] f32, lengths[B] i64, pitch[B,T] i64, pitchf[B,T] f32, sid[B] i64) on CPU."""
+    g = torch.Generator().manual_seed(seed)
+    phone = torch.randn(B, T, cfg.feat_dim, generator=g, dtype=torch.float32)
+    f0 = np.stack([np.roll(make_f0(T, variant=f0_variant, seed=seed + b), 37 * b) for b in range(B)])
+    pitchf = torch.from_numpy(f0.astype(np.float32))
+    pitch = torch.from_numpy(coarse_pitch(f0))
+    if lengths is None:
+        lengths = [T] * B
+    lengths = torch.tensor(list(lengths), dtype=torch.int64)
+    sid = torch.zeros(B, dtype=torch.int64)
+    return phone, lengths, pitch, pitchf, sid
+
+
+def draw_noise(cfg: SynthConfig, B: int, T: int, seed: int = 7) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The three RNG draws of one `infer()` in the reference's order and shapes (CPU mt19937).
+
+    Returns (noise_zp[B,192,T], rand_ini[B,1], noise_sine[B,L,1]).  `rand_ini` is zeroed by the
+    reference for the fundamental (models.py:378-381) but still advances the stream.
+    """
+    st = torch.random.get_rng_state()
+    try:
+        torch.manual_seed(seed)
+        nz = torch.randn(B, cfg.inter_channels, T)
+        ri = torch.rand(B, 1)
+        ns = torch.randn(B, T * cfg.upp, 1)
+    finally:
+        torch.random.set_rng_state(st)
+    return nz, ri, ns
+
+
+def to_int16(audio: np.ndarray) -> np.ndarray:
+    """Peak-normalise and truncate exactly like /root/reference/vc_infer_pipeline.py:188-189."""
+    audio = np.asarray(audio)
+    audio_max = np.abs(audio).max() / 0.99
+    return (audio * 32768 / audio_max).astype(np.int16)
+
+
+def snr_db(ref: np.ndarray, est: np.ndarray) -> float:
+    """SDR formula of /root/reference/lib/karafan/compare.py:21-35: 10 log10(Σref² / Σ(ref−est)²)."""
+    ref = np.asarray(ref, dtype=np.float64)
+    est = np.asarray(est, dtype=np.float64)
+    num = np.sum(ref ** 2)
+    den = np.sum((ref - est) ** 2)
+    return float(10.0 * np.log10(num / max(den, 1e-300)))

@@ -1,0 +1,34 @@
+"""Shared helpers for the parity tests: golden fixtures + seeded inputs."""
+from __future__ import annotations
+
+import ast
+import os
+
+import numpy as np
+import torch
+
+from comfy_rvc_b200 import synthetic
+from comfy_rvc_b200.config import NAMED_CONFIGS
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = ["c1_40k_v1", "c2_48k_v2", "c3_32k_v2_ragged", "c4_48k_v2_unvoiced", "c5_48k_v1_5stage", "c6_40k_v1_tiny"]
+
+
+def load_golden(name):
+    """Returns (cfg, state_dict, inputs, noise, golden arrays) for one fixture minted by make_golden.py."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=True)
+    cfg_name, B, T, lengths, f0v, wseed, iseed, nseed, _torch_ver = [str(x) for x in z["meta"]]
+    cfg = NAMED_CONFIGS[cfg_name]
+    B, T = int(B), int(T)
+    lengths = ast.literal_eval(lengths)
+    sd = synthetic.make_state_dict(cfg, seed=int(wseed))
+    inputs = synthetic.make_inputs(cfg, B, T, seed=int(iseed), lengths=lengths, f0_variant=f0v)
+    noise = synthetic.draw_noise(cfg, B, T, seed=int(nseed))
+    return cfg, sd, inputs, noise, z
+
+
+def int16_lsb_diff(ref_f32: np.ndarray, est_f32: np.ndarray) -> int:
+    """max |int16(ref) - int16(est)| with the reference conversion (vc_infer_pipeline.py:188-189)."""
+    a = synthetic.to_int16(ref_f32).astype(np.int32)
+    b = synthetic.to_int16(est_f32).astype(np.int32)
+    return int(np.abs(a - b).max())
