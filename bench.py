@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Headline benchmark: seconds of output audio synthesised per second (RTF^-1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|fp16|bf16]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the reference algorithm's CPU path (oracle port), rank 0 only
+
+A "step" is one `net_g.infer()` of the BASELINE.json workload `configs[1]`: 48k_v2
+(SynthesizerTrnMs768NSFsid), one 60 s segment of synthetic 768-d features + f0 (T = 6000 frames,
+2 880 000 output samples) with seeded random weights, per GPU.  Segments are independent
+(SURVEY.md §8e), so N GPUs run N segments with no collective on the data path: weak scaling,
+value = N * 60 s / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from comfy_rvc_b200 import synthetic  # noqa: E402
+from comfy_rvc_b200.config import NAMED_CONFIGS  # noqa: E402
+
+
+def algorithmic_macs(cfg, T: int) -> dict:
+    """MACs per batch item by component — the formula of SURVEY.md §8(d) (banded rel-pos, 1 MAC = 2 FLOP)."""
+    H, F, Ci = cfg.hidden_channels, cfg.filter_channels, cfg.inter_channels
+    U0 = cfg.upsample_initial_channel
+    R = sum(len(ds) * 2 * k for k, ds in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes)) \
+        if cfg.resblock == "1" else sum(len(ds) * k for k, ds in zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes))
+    pre = T * Ci * U0 * 7
+    ups = noise = res = 0
+    L, C = T, U0
+    for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
+        Cn, Ln = C // 2, L * u
+        ups += L * C * Cn * k
+        noise += Ln * Cn * cfg.noise_conv_geometry(i)[0]
+        res += Ln * Cn * Cn * R
+        L, C = Ln, Cn
+    post = L * C * 7
+    half = Ci // 2
+    flow = cfg.n_flows * T * (half * H + cfg.flow_wn_layers * H * 2 * H * cfg.flow_kernel + 2 * H * 2 * H + H * H + H * half)
+    W = 2 * cfg.window_size + 1
+    enc_lin = T * cfg.feat_dim * H + cfg.n_layers * (4 * T * H * H + 2 * T * H * F * cfg.kernel_size) + T * H * 2 * Ci
+    attn = cfg.n_layers * (2 * T * T * H + 2 * 2 * T * W * (H // cfg.n_heads))
+    return {"conv_pre": pre, "ups": ups, "noise": noise, "resblocks": res, "conv_post": post, "flow": flow,
+            "enc_linear": enc_lin, "attention": attn}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json, sustained)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(cfg, T: int, reps: int, warmup: int, threads: int):
+    """RTF^-1 of the reference algorithm on the host cores (oracle port, fp32 PyTorch CPU)."""
+    from oracle import rvc_oracle
+    torch.set_num_threads(threads)
+    sd = synthetic.make_state_dict(cfg)
+    w = rvc_oracle.fold_weight_norm(sd)
+    phone, lens, pitch, pitchf, sid = synthetic.make_inputs(cfg, 1, T)
+    times = []
+    for i in range(warmup + reps):
+        noise = synthetic.draw_noise(cfg, 1, T, seed=7 + i)
+        t0 = time.perf_counter()
+        rvc_oracle.infer(w, cfg, phone, lens, pitch, pitchf, sid, *noise)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    audio_s = T * cfg.upp / cfg.sr
+    return audio_s / float(np.median(times)), audio_s, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--config", default="48k_v2")
+    ap.add_argument("--seconds", type=float, default=60.0)
+    ap.add_argument("--cpu-frames", type=int, default=300, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    cfg = NAMED_CONFIGS[args.config]
+    T = int(round(args.seconds * 100))
+    audio_s = T * cfg.upp / cfg.sr
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"{args.config} SynthesizerTrnMs{cfg.feat_dim}NSFsid.infer, B=1, T={T} frames ({audio_s:.0f} s segment) per GPU"
+    metric = "seconds of output audio synthesised per second (RTF^-1)"
+
+    # ------------------------------------------------------------------ reference arm (CPU) -------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        # bounded sample: cpu_frames of the same workload per step; cap total wall time to a few minutes
+        rate, sample_s, times = cpu_oracle_rate(cfg, args.cpu_frames, min(steps, 5), min(warm, 1), threads)
+        line = {
+            "impl": "reference", "metric": metric, "value": rate, "unit": "audio-s/s", "n_gpus": args.gpus,
+            "steps": min(steps, 5), "warmup": min(warm, 1), "ms_per_step": float(np.median(times)) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "timed_sample": f"{args.cpu_frames} frames ({sample_s:.1f} s of audio) per step"},
+            "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                             "sample": f"oracle/rvc_oracle.py (fp32 PyTorch CPU restatement of the reference infer), "
+                                       f"{args.cpu_frames} frames = {sample_s:.1f} s audio per step"},
+            "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ product arm (CUDA) --------
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    import comfy_rvc_b200 as rvc
+    from comfy_rvc_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    sd = synthetic.make_state_dict(cfg)
+    cls = rvc.SynthesizerTrnMs256NSFsid if cfg.feat_dim == 256 else rvc.SynthesizerTrnMs768NSFsid
+    net = cls(*cfg.to_positional(), is_half=args.precision != "fp32")
+    del net.enc_q
+    net.load_state_dict({k: v.half() for k, v in sd.items()}, strict=False)
+    net.eval().to(dev).set_precision(args.precision)
+
+    phone, lens, pitch, pitchf, sid = synthetic.make_inputs(cfg, 1, T, seed=1 + rank)
+    host = [t.pin_memory() for t in (phone, lens, pitch, pitchf, sid)]
+    devin = [t.to(dev) for t in host]
+    torch.manual_seed(1234 + rank)
+    lib = _lib.load()
+
+    def step_resident():
+        return net.infer(*devin)[0]          # draws its noise with torch on the device, like the reference
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    lib.rvcb200_profile_enable(net._ctx, 1)
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    cls_ms = (C.c_double * 4)()
+    cls_n = (C.c_int64 * 4)()
+    lib.rvcb200_profile_collect(net._ctx, cls_ms, cls_n)
+    lib.rvcb200_profile_enable(net._ctx, 0)
+    launches = net.last_launches * args.steps
+
+    # end-to-end through the public API with host buffers (pinned H2D of inputs, D2H of the PCM)
+    out_host = torch.empty(1, 1, T * cfg.upp, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        ins = [t.to(dev, non_blocking=True) for t in host]
+        o = net.infer(*ins)[0]
+        out_host.copy_(o, non_blocking=True)
+
+    step_e2e()
+    barrier()
+    f0_, f1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0_.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1_.record()
+    barrier()
+    ms_e2e = f0_.elapsed_time(f1_)
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps * audio_s / (ms / 1e3)
+    e2e_value = world * args.steps * audio_s / (ms_e2e / 1e3)
+    macs = algorithmic_macs(cfg, T)
+    conv_flops = 2.0 * (macs["conv_pre"] + macs["ups"] + macs["resblocks"] + macs["flow"] + macs["enc_linear"])
+    conv_ms_per_launch = cls_ms[0] / max(cls_n[0], 1)
+    conv_launches_per_step = cls_n[0] / args.steps
+    peaks = load_peaks()
+    achieved = conv_flops / conv_launches_per_step / (conv_ms_per_launch * 1e-3) / 1e12
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    line = {
+        "metric": metric, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate"}[args.precision],
+        "data": "synthetic (seeded random-init weights stored as fp16, N(0,1) features, contour f0)",
+        "config": {"workload": workload, "precision": args.precision, "parallelism": f"segments x{world}, no collective",
+                   "l2": "no flush needed: each step streams >1 GB of stage activations (>> 126 MB L2)"},
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": T * cfg.upp * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "conv (dense contraction class: resblocks, ups, conv_pre, flow, enc 1x1/FFN)",
+                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                     "traffic": None, "peak_source": peaks["src"],
+                     "launches_per_step": conv_launches_per_step, "avg_launch_ms": conv_ms_per_launch,
+                     "algorithmic_gflop_per_step": conv_flops / 1e9,
+                     "share_of_step": cls_ms[0] / max(sum(cls_ms), 1e-9)},
+        "time_by_class_ms_per_step": {"conv": cls_ms[0] / args.steps, "attention": cls_ms[1] / args.steps,
+                                      "sine_source": cls_ms[2] / args.steps, "glue": cls_ms[3] / args.steps},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sample_s, _ = cpu_oracle_rate(cfg, args.cpu_frames, 3, 1, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                                "sample": f"oracle/rvc_oracle.py fp32 PyTorch CPU, {args.cpu_frames} frames = {sample_s:.1f} s audio, median of 3"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,5 @@
+"""comfy_rvc_b200 — B200-native (sm_100a) RVC synthesis hot path behind the reference's Python API."""
+from .config import NAMED_CONFIGS, SynthConfig  # noqa: F401
+from .synthesizer import SynthesizerB200, SynthesizerTrnMs256NSFsid, SynthesizerTrnMs768NSFsid  # noqa: F401
+
+__all__ = ["SynthesizerTrnMs256NSFsid", "SynthesizerTrnMs768NSFsid", "SynthesizerB200", "SynthConfig", "NAMED_CONFIGS"]

@@ -1,0 +1,70 @@
+// Shared device/host helpers for the rvcb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rvcb200.h"
+
+namespace rvc {
+
+// Per-launch bookkeeping: launches are counted so bench.py can report gpu_launches.
+struct LaunchCounter {
+  long long n = 0;
+};
+LaunchCounter& launch_counter();
+
+inline int cuda_ok(cudaError_t e, const char* what, char* errbuf, size_t errlen) {
+  if (e == cudaSuccess) return 1;
+  if (errbuf) snprintf(errbuf, errlen, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::); }
+
+// ---- kernels implemented across the .cu files (host launchers) -----------------------------
+typedef rvcb200_conv_desc ConvDesc;
+
+cudaError_t launch_conv_f32(const ConvDesc& d, int B, cudaStream_t st);
+
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, long long rows, int C,
+                             float eps, cudaStream_t st);
+
+cudaError_t launch_attention_f32(const float* qkv, const float* rel_k, const float* rel_v, const int* len, float* out,
+                                 int B, int T, int n_heads, int dk, int window, cudaStream_t st);
+
+size_t sine_scratch_bytes(int B, int T, int upp);
+cudaError_t launch_sine_source(const float* f0, const float* noise, float* har, int B, int T, int upp, int sr,
+                               float lin_w, float lin_b, void* scratch, cudaStream_t st);
+
+// len32[b] = (int) len64[b]
+cudaError_t launch_len_to_i32(const long long* len64, int* len32, int B, int T, cudaStream_t st);
+
+// out[b][j] = bias[j] + sum_i W[j][i] * emb[sid[b]][i]   (all speaker-conditioning 1x1 convs at once)
+cudaError_t launch_cond_gemv(const float* emb_g, const long long* sid, const float* W, const float* bias, float* out,
+                             int B, int gin, int n_out, int n_spk, cudaStream_t st);
+
+// z_p[b][t][c] = (m + exp(logs) * noise[b][c][t] * 0.66666) masked   (models.py:685/801)
+cudaError_t launch_zp_sample(const float* stats, const float* noise_cf, const int* len, float* zp, int B, int T, int C,
+                             cudaStream_t st);
+
+// y[b][t][co] += nb[co] + sum_k har[b][t*s - pad + k] * wn[k][co]   (models.py:552-553)
+cudaError_t launch_noise_conv_add(const float* har, const float* wn, const float* nb, float* y, int B, long long L_har,
+                                  long long L_out, int C, int k, int s, int pad, cudaStream_t st);
+
+// out[b][t] = tanh( sum_{k,ci} lrelu_{slope}(x[b][t+k-3][ci]) * w[k][ci] )   (models.py:561-563)
+cudaError_t launch_conv_post_tanh(const float* x, const float* w, float* out, int B, long long L, int C, int k,
+                                  float slope, cudaStream_t st);
+
+// dst = src * scale, elementwise (row-strided copy): dst[r][c] = src[r][c] for c < C
+cudaError_t launch_copy_rows(const float* src, int lds, float* dst, int ldd, long long rows, int C, cudaStream_t st);
+
+}  // namespace rvc

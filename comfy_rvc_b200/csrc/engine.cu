@@ -1,0 +1,668 @@
+// Context, weight registry, workspace planning and the infer() orchestrator behind the C ABI
+// (include/rvcb200.h).  Mirrors the call order of the reference
+// `SynthesizerTrnMs{256,768}NSFsid.infer` (/root/reference/lib/infer_pack/models.py:682-693,
+// :798-809): emb_g -> enc_p -> prior sample -> reverse flow -> NSF source -> GeneratorNSF.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace rvc;
+
+struct TensorRef {
+  const void* ptr = nullptr;
+  long long numel = 0;
+  int dtype = 0;
+};
+
+struct rvcb200_ctx {
+  rvcb200_config cfg;
+  std::unordered_map<std::string, TensorRef> tensors;
+  std::unordered_map<std::string, float> scalars;
+  bool finalized = false;
+  char err[512];
+  long long last_launches = 0;
+  // derived
+  int upp = 1;
+  int n_cond = 0;  // rows of the stacked conditioning matrix
+  // optional per-class CUDA-event timing of the launches inside infer (bench.py roofline)
+  bool prof = false;
+  std::vector<cudaEvent_t> ev;   // pairs (start, stop)
+  std::vector<int> ev_cls;
+  size_t ev_used = 0;
+  double cls_ms[RVCB200_PROF_CLASSES] = {0};
+  long long cls_n[RVCB200_PROF_CLASSES] = {0};
+};
+
+namespace {
+
+int fail(rvcb200_ctx* c, int code, const char* fmt, const char* a = "", long long b = 0) {
+  if (c) snprintf(c->err, sizeof(c->err), fmt, a, b);
+  return code;
+}
+
+const float* T32(rvcb200_ctx* c, const std::string& name, long long expect, bool* ok) {
+  auto it = c->tensors.find(name);
+  if (it == c->tensors.end()) {
+    if (*ok) snprintf(c->err, sizeof(c->err), "missing tensor '%s'", name.c_str());
+    *ok = false;
+    return nullptr;
+  }
+  if (it->second.dtype != 0 || (expect > 0 && it->second.numel != expect)) {
+    if (*ok)
+      snprintf(c->err, sizeof(c->err), "tensor '%s': numel %lld (expected %lld) dtype %d", name.c_str(),
+               it->second.numel, expect, it->second.dtype);
+    *ok = false;
+    return nullptr;
+  }
+  return reinterpret_cast<const float*>(it->second.ptr);
+}
+
+std::string S(const char* fmt, int a = 0, int b = 0, int c = 0) {
+  char buf[128];
+  snprintf(buf, sizeof(buf), fmt, a, b, c);
+  return std::string(buf);
+}
+
+struct Bump {
+  char* base;
+  size_t off = 0, cap;
+  Bump(void* p, size_t c) : base(reinterpret_cast<char*>(p)), cap(c) {}
+  template <typename T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    T* r = reinterpret_cast<T*>(base ? base + off : nullptr);
+    off += bytes;
+    return r;
+  }
+};
+
+struct UpGeom {
+  int k, u, pad, ntaps, cin, cout;
+  int g_off[16];
+};
+
+UpGeom up_geom(const rvcb200_config& cfg, int i) {
+  UpGeom g;
+  g.k = cfg.up_kernels[i];
+  g.u = cfg.up_rates[i];
+  g.pad = (g.k - g.u) / 2;
+  g.ntaps = (g.k + g.u - 1) / g.u;
+  g.cin = cfg.up_init_channels >> i;
+  g.cout = cfg.up_init_channels >> (i + 1);
+  for (int p = 0; p < 16; ++p) g.g_off[p] = 0;
+  for (int p = 0; p < g.u; ++p) g.g_off[p] = (p + g.pad) / g.u - (g.ntaps - 1);
+  return g;
+}
+
+void noise_geom(const rvcb200_config& cfg, int i, int* k, int* s, int* pad) {
+  if (i + 1 < cfg.n_ups) {
+    int st = 1;
+    for (int j = i + 1; j < cfg.n_ups; ++j) st *= cfg.up_rates[j];
+    *k = 2 * st; *s = st; *pad = st / 2;
+  } else {
+    *k = 1; *s = 1; *pad = 0;
+  }
+}
+
+ConvDesc base_desc() {
+  ConvDesc d;
+  memset(&d, 0, sizeof(d));
+  d.in_slope = 1.f; d.alpha = 1.f; d.out_slope = 1.f; d.div = 1.f;
+  d.ntaps = 1; d.dil = 1; d.G = 1; d.out_stride = 1;
+  return d;
+}
+
+struct Plan {  // workspace carve-up for (B, T)
+  int* len32; int* len_head;
+  float *cond, *x, *xt, *qkv, *att, *ffh, *stats, *zp, *z, *h, *acts, *skip, *har, *pre;
+  void* sine_scratch;
+  float* stage[5];
+  size_t bytes;
+};
+
+Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws) {
+  const rvcb200_config& cf = c->cfg;
+  Plan p;
+  Bump bp(ws, 0);
+  const size_t BT = (size_t)B * T;
+  const int H = cf.hidden_channels, C = cf.inter_channels;
+  p.len32 = bp.take<int>(B);
+  p.len_head = bp.take<int>(B);
+  p.cond = bp.take<float>((size_t)B * c->n_cond);
+  p.x = bp.take<float>(BT * H);
+  p.xt = bp.take<float>(BT * H);
+  p.qkv = bp.take<float>(BT * 3 * H);
+  p.att = bp.take<float>(BT * H);
+  p.ffh = bp.take<float>(BT * cf.filter_channels);
+  p.stats = bp.take<float>(BT * 2 * C);
+  p.zp = bp.take<float>(BT * C);
+  p.z = bp.take<float>(BT * C);
+  p.h = bp.take<float>(BT * H);
+  p.acts = bp.take<float>(BT * H);
+  p.skip = bp.take<float>(BT * H);
+  p.har = bp.take<float>(BT * c->upp);
+  p.sine_scratch = bp.take<char>(sine_scratch_bytes(B, T, c->upp));
+  p.pre = bp.take<float>(BT * cf.up_init_channels);
+  size_t mx = 0;
+  long long L = T;
+  for (int i = 0; i < cf.n_ups; ++i) {
+    L *= cf.up_rates[i];
+    size_t s = (size_t)B * L * (cf.up_init_channels >> (i + 1));
+    if (s > mx) mx = s;
+  }
+  for (int i = 0; i < 5; ++i) p.stage[i] = bp.take<float>(mx);
+  p.bytes = bp.off;
+  return p;
+}
+
+struct TapSet {
+  const rvcb200_tap* taps;
+  int n;
+  cudaStream_t st;
+  cudaError_t emit(const char* name, const void* src, size_t bytes) const {
+    for (int i = 0; i < n; ++i)
+      if (taps[i].name && strcmp(taps[i].name, name) == 0 && taps[i].dst) {
+        size_t nb = bytes < taps[i].bytes ? bytes : taps[i].bytes;
+        return cudaMemcpyAsync(taps[i].dst, src, nb, cudaMemcpyDeviceToDevice, st);
+      }
+    return cudaSuccess;
+  }
+};
+
+#define CK(expr, what)                                                      \
+  do {                                                                      \
+    cudaError_t _e = (expr);                                                \
+    if (_e != cudaSuccess) {                                                \
+      snprintf(ctx->err, sizeof(ctx->err), "%s: %s", what, cudaGetErrorString(_e)); \
+      return RVCB200_ERR_CUDA;                                              \
+    }                                                                       \
+  } while (0)
+
+struct ProfScope {  // records an event pair around one launch when profiling is on
+  rvcb200_ctx* c;
+  cudaStream_t st;
+  bool on;
+  ProfScope(rvcb200_ctx* c_, int cls, cudaStream_t st_) : c(c_), st(st_), on(c_->prof) {
+    if (!on) return;
+    if (c->ev_used + 2 > c->ev.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+      c->ev.push_back(a); c->ev.push_back(b);
+    }
+    c->ev_cls.resize(c->ev.size() / 2);
+    c->ev_cls[c->ev_used / 2] = cls;
+    cudaEventRecord(c->ev[c->ev_used], st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(c->ev[c->ev_used + 1], st);
+    c->ev_used += 2;
+  }
+};
+
+#define CKC(cls, expr, what)                 \
+  do {                                       \
+    ProfScope _ps(ctx, cls, st);             \
+    CK(expr, what);                          \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int32_t rvcb200_abi_version(void) { return RVCB200_ABI_VERSION; }
+
+int rvcb200_create(const rvcb200_config* cfg, rvcb200_ctx** out) {
+  if (!cfg || !out) return RVCB200_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return RVCB200_ERR_NO_DEVICE;
+  rvcb200_ctx* c = new rvcb200_ctx();
+  c->cfg = *cfg;
+  c->err[0] = 0;
+  const rvcb200_config& f = c->cfg;
+  bool ok = f.n_heads > 0 && f.hidden_channels == f.n_heads * 96 && f.inter_channels == f.hidden_channels &&
+            f.inter_channels % 2 == 0 && f.window_size <= 10 && f.n_ups >= 1 && f.n_ups <= RVCB200_MAX_UPS &&
+            f.n_res_kernels >= 1 && f.n_res_kernels <= RVCB200_MAX_RESK && (f.resblock_kind == 1 || f.resblock_kind == 2) &&
+            f.feat_dim % 8 == 0 && f.filter_channels % 64 == 0 && f.enc_kernel % 2 == 1 && f.flow_kernel % 2 == 1 &&
+            f.gin_channels > 0 && f.n_flows % 2 == 0;
+  c->upp = 1;
+  for (int i = 0; ok && i < f.n_ups; ++i) {
+    c->upp *= f.up_rates[i];
+    if (f.up_rates[i] > 16 || f.up_rates[i] < 1 || (f.up_kernels[i] - f.up_rates[i]) % 2 != 0 || f.up_kernels[i] < f.up_rates[i])
+      ok = false;
+    if ((f.up_init_channels >> (i + 1)) % 16 != 0) ok = false;
+  }
+  for (int j = 0; ok && j < f.n_res_kernels; ++j) {
+    if (f.res_kernels[j] % 2 != 1 || f.n_res_dils[j] < 1 || f.n_res_dils[j] > RVCB200_MAX_DIL) ok = false;
+    for (int d = 0; ok && d < f.n_res_dils[j]; ++d)
+      if ((f.res_kernels[j] - 1) * f.res_dils[j][d] > 50) ok = false;
+  }
+  if (!ok) {
+    delete c;
+    return RVCB200_ERR_ARG;
+  }
+  c->n_cond = f.up_init_channels + f.n_flows * f.flow_wn_layers * 2 * f.hidden_channels;
+  *out = c;
+  return RVCB200_OK;
+}
+
+void rvcb200_destroy(rvcb200_ctx* ctx) {
+  if (!ctx) return;
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+  delete ctx;
+}
+
+int rvcb200_profile_enable(rvcb200_ctx* ctx, int32_t on) {
+  if (!ctx) return RVCB200_ERR_ARG;
+  ctx->prof = on != 0;
+  ctx->ev_used = 0;
+  for (int i = 0; i < RVCB200_PROF_CLASSES; ++i) { ctx->cls_ms[i] = 0; ctx->cls_n[i] = 0; }
+  return RVCB200_OK;
+}
+
+int rvcb200_profile_collect(rvcb200_ctx* ctx, double* ms, int64_t* count) {
+  if (!ctx || !ms || !count) return RVCB200_ERR_ARG;
+  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    if (cudaEventSynchronize(ctx->ev[i + 1]) != cudaSuccess) return RVCB200_ERR_CUDA;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) return RVCB200_ERR_CUDA;
+    const int cls = ctx->ev_cls[i / 2];
+    ctx->cls_ms[cls] += t;
+    ctx->cls_n[cls] += 1;
+  }
+  ctx->ev_used = 0;
+  for (int i = 0; i < RVCB200_PROF_CLASSES; ++i) { ms[i] = ctx->cls_ms[i]; count[i] = ctx->cls_n[i]; }
+  return RVCB200_OK;
+}
+
+int rvcb200_set_tensor(rvcb200_ctx* ctx, const char* name, const void* dev_ptr, int64_t numel, int32_t dtype) {
+  if (!ctx || !name || !dev_ptr || numel <= 0) return RVCB200_ERR_ARG;
+  TensorRef t;
+  t.ptr = dev_ptr; t.numel = numel; t.dtype = dtype;
+  ctx->tensors[name] = t;
+  ctx->finalized = false;
+  return RVCB200_OK;
+}
+
+int rvcb200_set_scalar(rvcb200_ctx* ctx, const char* name, float value) {
+  if (!ctx || !name) return RVCB200_ERR_ARG;
+  ctx->scalars[name] = value;
+  return RVCB200_OK;
+}
+
+int rvcb200_finalize(rvcb200_ctx* ctx) {
+  if (!ctx) return RVCB200_ERR_ARG;
+  const rvcb200_config& f = ctx->cfg;
+  const int H = f.hidden_channels, C = f.inter_channels, F = f.filter_channels, half = C / 2;
+  bool ok = true;
+  T32(ctx, "emb_g", (long long)f.n_speakers * f.gin_channels, &ok);
+  T32(ctx, "cond.w", (long long)ctx->n_cond * f.gin_channels, &ok);
+  T32(ctx, "cond.b", ctx->n_cond, &ok);
+  T32(ctx, "enc.emb.w", (long long)f.feat_dim * H, &ok);
+  T32(ctx, "enc.emb.b", H, &ok);
+  T32(ctx, "enc.emb_pitch", 256LL * H, &ok);
+  const int nrel = 2 * f.window_size + 1;
+  for (int l = 0; l < f.n_layers; ++l) {
+    T32(ctx, S("enc.%d.qkv.w", l), (long long)H * 3 * H, &ok);
+    T32(ctx, S("enc.%d.qkv.b", l), 3 * H, &ok);
+    T32(ctx, S("enc.%d.rel_k", l), (long long)nrel * 96, &ok);
+    T32(ctx, S("enc.%d.rel_v", l), (long long)nrel * 96, &ok);
+    T32(ctx, S("enc.%d.o.w", l), (long long)H * H, &ok);
+    T32(ctx, S("enc.%d.o.b", l), H, &ok);
+    T32(ctx, S("enc.%d.ln1.g", l), H, &ok);
+    T32(ctx, S("enc.%d.ln1.b", l), H, &ok);
+    T32(ctx, S("enc.%d.ffn1.w", l), (long long)f.enc_kernel * H * F, &ok);
+    T32(ctx, S("enc.%d.ffn1.b", l), F, &ok);
+    T32(ctx, S("enc.%d.ffn2.w", l), (long long)f.enc_kernel * F * H, &ok);
+    T32(ctx, S("enc.%d.ffn2.b", l), H, &ok);
+    T32(ctx, S("enc.%d.ln2.g", l), H, &ok);
+    T32(ctx, S("enc.%d.ln2.b", l), H, &ok);
+  }
+  T32(ctx, "enc.proj.w", (long long)H * 2 * C, &ok);
+  T32(ctx, "enc.proj.b", 2 * C, &ok);
+  for (int i = 0; i < f.n_flows; ++i) {
+    T32(ctx, S("flow.%d.pre.w", i), (long long)half * H, &ok);
+    T32(ctx, S("flow.%d.pre.b", i), H, &ok);
+    for (int j = 0; j < f.flow_wn_layers; ++j) {
+      T32(ctx, S("flow.%d.in.%d.w", i, j), (long long)f.flow_kernel * H * 2 * H, &ok);
+      T32(ctx, S("flow.%d.in.%d.b", i, j), 2 * H, &ok);
+      if (j < f.flow_wn_layers - 1) {
+        T32(ctx, S("flow.%d.rs.%d.res.w", i, j), (long long)H * H, &ok);
+        T32(ctx, S("flow.%d.rs.%d.res.b", i, j), H, &ok);
+      }
+      T32(ctx, S("flow.%d.rs.%d.skip.w", i, j), (long long)H * H, &ok);
+      T32(ctx, S("flow.%d.rs.%d.skip.b", i, j), H, &ok);
+    }
+    T32(ctx, S("flow.%d.post.w", i), (long long)H * half, &ok);
+    T32(ctx, S("flow.%d.post.b", i), half, &ok);
+  }
+  T32(ctx, "dec.pre.w", 7LL * C * f.up_init_channels, &ok);
+  T32(ctx, "dec.pre.b", f.up_init_channels, &ok);
+  for (int i = 0; i < f.n_ups; ++i) {
+    UpGeom g = up_geom(f, i);
+    T32(ctx, S("dec.ups.%d.w", i), (long long)g.u * g.ntaps * g.cin * g.cout, &ok);
+    T32(ctx, S("dec.ups.%d.b", i), g.cout, &ok);
+    int nk, ns, np;
+    noise_geom(f, i, &nk, &ns, &np);
+    T32(ctx, S("dec.noise.%d.w", i), (long long)nk * g.cout, &ok);
+    T32(ctx, S("dec.noise.%d.b", i), g.cout, &ok);
+    for (int j = 0; j < f.n_res_kernels; ++j) {
+      const int n = i * f.n_res_kernels + j;
+      for (int d = 0; d < f.n_res_dils[j]; ++d) {
+        const long long wn = (long long)f.res_kernels[j] * g.cout * g.cout;
+        if (f.resblock_kind == 1) {
+          T32(ctx, S("dec.rb.%d.c1.%d.w", n, d), wn, &ok);
+          T32(ctx, S("dec.rb.%d.c1.%d.b", n, d), g.cout, &ok);
+          T32(ctx, S("dec.rb.%d.c2.%d.w", n, d), wn, &ok);
+          T32(ctx, S("dec.rb.%d.c2.%d.b", n, d), g.cout, &ok);
+        } else {
+          T32(ctx, S("dec.rb.%d.c.%d.w", n, d), wn, &ok);
+          T32(ctx, S("dec.rb.%d.c.%d.b", n, d), g.cout, &ok);
+        }
+      }
+    }
+  }
+  T32(ctx, "dec.post.w", 7LL * (f.up_init_channels >> f.n_ups), &ok);
+  if (!ctx->scalars.count("dec.src.lin_w") || !ctx->scalars.count("dec.src.lin_b")) {
+    if (ok) snprintf(ctx->err, sizeof(ctx->err), "missing scalar 'dec.src.lin_w/lin_b'");
+    ok = false;
+  }
+  if (!ok) return RVCB200_ERR_MISSING;
+  ctx->finalized = true;
+  return RVCB200_OK;
+}
+
+int64_t rvcb200_workspace_bytes(const rvcb200_ctx* ctx, int32_t B, int32_t T, int32_t precision) {
+  if (!ctx || B <= 0 || T <= 0) return -1;
+  (void)precision;
+  Plan p = make_plan(ctx, B, T, nullptr);
+  return (int64_t)p.bytes + 256;
+}
+
+int64_t rvcb200_last_launch_count(const rvcb200_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+const char* rvcb200_last_error(const rvcb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+
+int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, const int64_t* phone_lengths,
+                  const int64_t* pitch, const float* nsff0, const int64_t* sid, const float* noise_zp,
+                  const float* noise_sine, float* out, float* stats_out, float* zp_out, float* z_out, void* workspace,
+                  int64_t workspace_bytes, int32_t precision, const rvcb200_tap* taps, int32_t n_taps, void* stream) {
+  if (!ctx) return RVCB200_ERR_ARG;
+  if (!ctx->finalized) return fail(ctx, RVCB200_ERR_MISSING, "rvcb200_finalize() has not succeeded%s", "");
+  if (B <= 0 || T <= 0 || !phone || !phone_lengths || !pitch || !nsff0 || !sid || !noise_zp || !noise_sine || !out ||
+      !workspace)
+    return fail(ctx, RVCB200_ERR_ARG, "null or empty argument%s", "");
+  if (precision != RVCB200_PREC_FP32)
+    return fail(ctx, RVCB200_ERR_ARG, "precision %s%lld not built in this library", "", precision);
+  const rvcb200_config& f = ctx->cfg;
+  // 256-byte align the workspace
+  uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
+  const size_t slack = wsp - reinterpret_cast<uintptr_t>(workspace);
+  Plan pl = make_plan(ctx, B, T, reinterpret_cast<void*>(wsp));
+  if ((int64_t)(pl.bytes + slack) > workspace_bytes)
+    return fail(ctx, RVCB200_ERR_WORKSPACE, "workspace too small%s: need %lld bytes", "", (long long)(pl.bytes + 256));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  TapSet tp{taps, n_taps, st};
+  const long long launches0 = launch_counter().n;
+  bool ok = true;
+  auto W = [&](const std::string& n) { return T32(ctx, n, 0, &ok); };
+
+  const int H = f.hidden_channels, C = f.inter_channels, F = f.filter_channels, half = C / 2;
+  const long long BT = (long long)B * T;
+  float* stats = stats_out ? stats_out : pl.stats;
+  float* zp = zp_out ? zp_out : pl.zp;
+  float* z = z_out ? z_out : pl.z;
+
+  CKC(3, launch_len_to_i32(reinterpret_cast<const long long*>(phone_lengths), pl.len32, B, T, st), "len_to_i32");
+  CKC(3, launch_cond_gemv(W("emb_g"), reinterpret_cast<const long long*>(sid), W("cond.w"), W("cond.b"), pl.cond, B,
+                      f.gin_channels, ctx->n_cond, f.n_speakers, st),
+     "cond_gemv");
+
+  // ---------------- TextEncoder (models.py:43-58 / 90-105) -----------------------------------
+  {
+    ConvDesc d = base_desc();
+    d.x = phone; d.x_bstride = (long long)T * f.feat_dim; d.ldx = f.feat_dim; d.L_in = T;
+    d.w = W("enc.emb.w"); d.bias = W("enc.emb.b"); d.Cin = f.feat_dim; d.Cout = H;
+    d.Lj = T; d.y = pl.x; d.y_bstride = (long long)T * H; d.ldy = H;
+    d.gather = W("enc.emb_pitch"); d.gidx = pitch; d.gidx_bstride = T;
+    d.alpha = sqrtf((float)H); d.out_slope = 0.1f; d.mask_post = 1; d.out_len = pl.len32;
+    CKC(0, launch_conv_f32(d, B, st), "enc.emb");
+  }
+  const int kp = (f.enc_kernel - 1) / 2;
+  for (int l = 0; l < f.n_layers; ++l) {
+    {  // q|k|v = conv_{q,k,v}(x)   attentions.py:213-215
+      ConvDesc d = base_desc();
+      d.x = pl.x; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T;
+      d.w = W(S("enc.%d.qkv.w", l)); d.bias = W(S("enc.%d.qkv.b", l)); d.Cin = H; d.Cout = 3 * H;
+      d.Lj = T; d.y = pl.qkv; d.y_bstride = (long long)T * 3 * H; d.ldy = 3 * H;
+      CKC(0, launch_conv_f32(d, B, st), "enc.qkv");
+    }
+    CKC(1, launch_attention_f32(pl.qkv, W(S("enc.%d.rel_k", l)), W(S("enc.%d.rel_v", l)), pl.len32, pl.att, B, T,
+                            f.n_heads, H / f.n_heads, f.window_size, st),
+       "enc.attention");
+    {  // x + conv_o(att)   attentions.py:219,63
+      ConvDesc d = base_desc();
+      d.x = pl.att; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T;
+      d.w = W(S("enc.%d.o.w", l)); d.bias = W(S("enc.%d.o.b", l)); d.Cin = H; d.Cout = H;
+      d.Lj = T; d.y = pl.xt; d.y_bstride = (long long)T * H; d.ldy = H;
+      d.res = pl.x; d.res_bstride = (long long)T * H; d.ldr = H; d.res_mode = 1;
+      CKC(0, launch_conv_f32(d, B, st), "enc.o");
+    }
+    CKC(3, launch_layernorm(pl.xt, W(S("enc.%d.ln1.g", l)), W(S("enc.%d.ln1.b", l)), pl.x, BT, H, 1e-5f, st), "enc.ln1");
+    {  // FFN conv_1 + ReLU   attentions.py:388-392
+      ConvDesc d = base_desc();
+      d.x = pl.x; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T; d.in_len = pl.len32;
+      d.w = W(S("enc.%d.ffn1.w", l)); d.bias = W(S("enc.%d.ffn1.b", l)); d.Cin = H; d.Cout = F;
+      d.ntaps = f.enc_kernel; d.g_off[0] = -kp;
+      d.Lj = T; d.y = pl.ffh; d.y_bstride = (long long)T * F; d.ldy = F; d.relu = 1;
+      CKC(0, launch_conv_f32(d, B, st), "enc.ffn1");
+    }
+    {  // x + conv_2(h*mask)*mask   attentions.py:394-395,67
+      ConvDesc d = base_desc();
+      d.x = pl.ffh; d.x_bstride = (long long)T * F; d.ldx = F; d.L_in = T; d.in_len = pl.len32;
+      d.w = W(S("enc.%d.ffn2.w", l)); d.bias = W(S("enc.%d.ffn2.b", l)); d.Cin = F; d.Cout = H;
+      d.ntaps = f.enc_kernel; d.g_off[0] = -kp;
+      d.Lj = T; d.y = pl.xt; d.y_bstride = (long long)T * H; d.ldy = H;
+      d.mask_pre = 1; d.out_len = pl.len32;
+      d.res = pl.x; d.res_bstride = (long long)T * H; d.ldr = H; d.res_mode = 1;
+      CKC(0, launch_conv_f32(d, B, st), "enc.ffn2");
+    }
+    CKC(3, launch_layernorm(pl.xt, W(S("enc.%d.ln2.g", l)), W(S("enc.%d.ln2.b", l)), pl.x, BT, H, 1e-5f, st), "enc.ln2");
+  }
+  CK(tp.emit("x_enc", pl.x, sizeof(float) * BT * H), "tap");
+  {  // stats = proj(x*mask)*mask   models.py:101-102
+    ConvDesc d = base_desc();
+    d.x = pl.x; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T; d.in_len = pl.len32;
+    d.w = W("enc.proj.w"); d.bias = W("enc.proj.b"); d.Cin = H; d.Cout = 2 * C;
+    d.Lj = T; d.y = stats; d.y_bstride = (long long)T * 2 * C; d.ldy = 2 * C;
+    d.mask_post = 1; d.out_len = pl.len32;
+    CKC(0, launch_conv_f32(d, B, st), "enc.proj");
+  }
+  CK(tp.emit("stats", stats, sizeof(float) * BT * 2 * C), "tap");
+  CKC(3, launch_zp_sample(stats, noise_zp, pl.len32, zp, B, T, C, st), "zp_sample");
+  CK(tp.emit("z_p", zp, sizeof(float) * BT * C), "tap");
+
+  // ---------------- reverse flow (models.py:185-192; modules.py:436-455) ----------------------
+  if (z != zp) CK(cudaMemcpyAsync(z, zp, sizeof(float) * BT * C, cudaMemcpyDeviceToDevice, st), "z copy");
+  {
+    bool flipped = false;
+    for (int i = f.n_flows - 1; i >= 0; --i) {
+      flipped = !flipped;  // the Flip that follows RCL_i in forward order
+      const int in_off = flipped ? half : 0, out_off = half - in_off;
+      {  // h = pre(x0)*mask
+        ConvDesc d = base_desc();
+        d.x = z + in_off; d.x_bstride = (long long)T * C; d.ldx = C; d.L_in = T;
+        d.w = W(S("flow.%d.pre.w", i)); d.bias = W(S("flow.%d.pre.b", i)); d.Cin = half; d.Cout = H;
+        d.Lj = T; d.y = pl.h; d.y_bstride = (long long)T * H; d.ldy = H; d.mask_post = 1; d.out_len = pl.len32;
+        CKC(0, launch_conv_f32(d, B, st), "flow.pre");
+      }
+      for (int j = 0; j < f.flow_wn_layers; ++j) {
+        {  // acts = tanh/sigmoid gate of in_layer(h) + cond   modules.py:192-199
+          ConvDesc d = base_desc();
+          d.x = pl.h; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T;
+          d.w = W(S("flow.%d.in.%d.w", i, j)); d.bias = W(S("flow.%d.in.%d.b", i, j)); d.Cin = H; d.Cout = 2 * H;
+          d.ntaps = f.flow_kernel; d.g_off[0] = -(f.flow_kernel - 1) / 2;
+          d.cond = pl.cond + f.up_init_channels + (i * f.flow_wn_layers + j) * 2 * H; d.cond_bstride = ctx->n_cond;
+          d.gate = 1;
+          d.Lj = T; d.y = pl.acts; d.y_bstride = (long long)T * H; d.ldy = H;
+          CKC(0, launch_conv_f32(d, B, st), "flow.in");
+        }
+        if (j < f.flow_wn_layers - 1) {  // h = (h + res)*mask   modules.py:203-206
+          ConvDesc d = base_desc();
+          d.x = pl.acts; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T;
+          d.w = W(S("flow.%d.rs.%d.res.w", i, j)); d.bias = W(S("flow.%d.rs.%d.res.b", i, j)); d.Cin = H; d.Cout = H;
+          d.Lj = T; d.y = pl.h; d.y_bstride = (long long)T * H; d.ldy = H;
+          d.res = pl.h; d.res_bstride = (long long)T * H; d.ldr = H; d.res_mode = 1;
+          d.mask_post = 1; d.out_len = pl.len32;
+          CKC(0, launch_conv_f32(d, B, st), "flow.res");
+        }
+        {  // output += skip   modules.py:207-208
+          ConvDesc d = base_desc();
+          d.x = pl.acts; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T;
+          d.w = W(S("flow.%d.rs.%d.skip.w", i, j)); d.bias = W(S("flow.%d.rs.%d.skip.b", i, j)); d.Cin = H; d.Cout = H;
+          d.Lj = T; d.y = pl.skip; d.y_bstride = (long long)T * H; d.ldy = H; d.accum = j > 0;
+          CKC(0, launch_conv_f32(d, B, st), "flow.skip");
+        }
+      }
+      {  // x1 = (x1 - post(out*mask)*mask)*mask   modules.py:441,453
+        ConvDesc d = base_desc();
+        d.x = pl.skip; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T; d.in_len = pl.len32;
+        d.w = W(S("flow.%d.post.w", i)); d.bias = W(S("flow.%d.post.b", i)); d.Cin = H; d.Cout = half;
+        d.Lj = T; d.y = z + out_off; d.y_bstride = (long long)T * C; d.ldy = C;
+        d.mask_pre = 1; d.mask_post = 1; d.out_len = pl.len32;
+        d.res = z + out_off; d.res_bstride = (long long)T * C; d.ldr = C; d.res_mode = 2;
+        CKC(0, launch_conv_f32(d, B, st), "flow.post");
+      }
+    }
+  }
+  CK(tp.emit("z", z, sizeof(float) * BT * C), "tap");
+
+  // ---------------- NSF source (models.py:361-411, 455-467) -----------------------------------
+  const long long Lout = (long long)T * ctx->upp;
+  CKC(2, launch_sine_source(nsff0, noise_sine, pl.har, B, T, ctx->upp, f.sr, ctx->scalars["dec.src.lin_w"],
+                        ctx->scalars["dec.src.lin_b"], pl.sine_scratch, st),
+     "sine_source");
+  CK(tp.emit("har_source", pl.har, sizeof(float) * B * Lout), "tap");
+
+  // ---------------- GeneratorNSF (models.py:542-564) -------------------------------------------
+  {
+    ConvDesc d = base_desc();
+    d.x = z; d.x_bstride = (long long)T * C; d.ldx = C; d.L_in = T;
+    d.w = W("dec.pre.w"); d.bias = W("dec.pre.b"); d.Cin = C; d.Cout = f.up_init_channels;
+    d.ntaps = 7; d.g_off[0] = -3;
+    d.cond = pl.cond; d.cond_bstride = ctx->n_cond;
+    d.Lj = T; d.y = pl.pre; d.y_bstride = (long long)T * f.up_init_channels; d.ldy = f.up_init_channels;
+    CKC(0, launch_conv_f32(d, B, st), "dec.conv_pre");
+  }
+  CK(tp.emit("dec.pre", pl.pre, sizeof(float) * BT * f.up_init_channels), "tap");
+  const float* cur = pl.pre;
+  long long Lc = T;
+  int Cc = f.up_init_channels;
+  float* X = pl.stage[0];
+  float* XB = pl.stage[1];
+  float* XT = pl.stage[2];
+  float* ACC = pl.stage[3];
+  float* ACC_next = pl.stage[4];
+  for (int i = 0; i < f.n_ups; ++i) {
+    UpGeom g = up_geom(f, i);
+    const long long Ln = Lc * g.u;
+    {  // x = ups[i](lrelu(x))   models.py:550-551 as g.u phase groups
+      ConvDesc d = base_desc();
+      d.x = cur; d.x_bstride = Lc * Cc; d.ldx = Cc; d.L_in = (int)Lc; d.in_slope = 0.1f;
+      d.w = W(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i)); d.Cin = g.cin; d.Cout = g.cout;
+      d.ntaps = g.ntaps; d.dil = 1; d.G = g.u;
+      for (int p = 0; p < g.u; ++p) d.g_off[p] = g.g_off[p];
+      d.Lj = (int)Lc; d.out_stride = g.u;
+      d.y = X; d.y_bstride = Ln * g.cout; d.ldy = g.cout;
+      CKC(0, launch_conv_f32(d, B, st), "dec.ups");
+    }
+    {
+      int nk, ns, np;
+      noise_geom(f, i, &nk, &ns, &np);
+      CKC(3, launch_noise_conv_add(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X, B, Lout, Ln, g.cout, nk,
+                               ns, np, st),
+         "dec.noise_conv");
+    }
+    CK(tp.emit(S("dec.ups.%d", i).c_str(), X, sizeof(float) * B * Ln * g.cout), "tap");
+    const int Cn = g.cout;
+    for (int j = 0; j < f.n_res_kernels; ++j) {
+      const int n = i * f.n_res_kernels + j;
+      const int k = f.res_kernels[j];
+      const float* src = X;
+      const int nd = f.n_res_dils[j];
+      for (int dd = 0; dd < nd; ++dd) {
+        const bool last = dd == nd - 1;
+        const int dil = f.res_dils[j][dd];
+        ConvDesc o = base_desc();   // the conv that closes the residual pair / step
+        if (f.resblock_kind == 1) {
+          ConvDesc d = base_desc();  // xt = c1(lrelu(x))   modules.py:297-301
+          d.x = src; d.x_bstride = Ln * Cn; d.ldx = Cn; d.L_in = (int)Ln; d.in_slope = 0.1f;
+          d.w = W(S("dec.rb.%d.c1.%d.w", n, dd)); d.bias = W(S("dec.rb.%d.c1.%d.b", n, dd)); d.Cin = Cn; d.Cout = Cn;
+          d.ntaps = k; d.dil = dil; d.g_off[0] = -((k - 1) / 2) * dil;
+          d.Lj = (int)Ln; d.y = XT; d.y_bstride = Ln * Cn; d.ldy = Cn;
+          CKC(0, launch_conv_f32(d, B, st), "dec.rb.c1");
+          o.x = XT; o.dil = 1; o.g_off[0] = -((k - 1) / 2);   // x = c2(lrelu(xt)) + x   modules.py:302-305
+          o.w = W(S("dec.rb.%d.c2.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c2.%d.b", n, dd));
+        } else {                     // ResBlock2: x = c(lrelu(x)) + x   modules.py:347-352
+          o.x = src; o.dil = dil; o.g_off[0] = -((k - 1) / 2) * dil;
+          o.w = W(S("dec.rb.%d.c.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c.%d.b", n, dd));
+        }
+        o.x_bstride = Ln * Cn; o.ldx = Cn; o.L_in = (int)Ln; o.in_slope = 0.1f;
+        o.Cin = Cn; o.Cout = Cn; o.ntaps = k;
+        o.Lj = (int)Ln; o.y_bstride = Ln * Cn; o.ldy = Cn;
+        o.res = src; o.res_bstride = Ln * Cn; o.ldr = Cn; o.res_mode = 1;
+        if (last) {  // xs += resblock(x); x = xs / num_kernels   models.py:554-560
+          o.y = ACC; o.accum = j > 0; o.div = (j == f.n_res_kernels - 1) ? (float)f.n_res_kernels : 1.f;
+        } else {
+          o.y = XB;
+        }
+        CKC(0, launch_conv_f32(o, B, st), "dec.rb.c2");
+        src = XB;
+      }
+    }
+    CK(tp.emit(S("dec.stage.%d", i).c_str(), ACC, sizeof(float) * B * Ln * Cn), "tap");
+    cur = ACC;
+    float* t = ACC; ACC = ACC_next; ACC_next = t;
+    Lc = Ln; Cc = Cn;
+  }
+  CKC(3, launch_conv_post_tanh(cur, W("dec.post.w"), out, B, Lc, Cc, 7, 0.01f, st), "dec.conv_post");
+  if (!ok) return RVCB200_ERR_MISSING;
+  ctx->last_launches = launch_counter().n - launches0;
+  return RVCB200_OK;
+}
+
+// ---------------------------------- op-level entry points --------------------------------------
+int rvcb200_op_conv_f32(const rvcb200_conv_desc* d, int32_t B, void* stream) {
+  if (!d) return RVCB200_ERR_ARG;
+  cudaError_t e = launch_conv_f32(*d, B, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int64_t rvcb200_op_sine_scratch_bytes(int32_t B, int32_t T, int32_t upp) { return (int64_t)sine_scratch_bytes(B, T, upp); }
+
+int rvcb200_op_sine_source(const float* f0, const float* noise, float* har, int32_t B, int32_t T, int32_t upp,
+                           int32_t sr, float lin_w, float lin_b, void* scratch, void* stream) {
+  cudaError_t e = launch_sine_source(f0, noise, har, B, T, upp, sr, lin_w, lin_b, scratch,
+                                     reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : RVCB200_ERR_CUDA;
+}
+
+int rvcb200_op_attention_f32(const float* qkv, const float* rel_k, const float* rel_v, const int32_t* len, float* out,
+                             int32_t B, int32_t T, int32_t n_heads, int32_t dk, int32_t window, void* stream) {
+  cudaError_t e = launch_attention_f32(qkv, rel_k, rel_v, len, out, B, T, n_heads, dk, window,
+                                       reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int rvcb200_op_layernorm(const float* x, const float* gamma, const float* beta, float* y, int64_t rows, int32_t C,
+                         float eps, void* stream) {
+  cudaError_t e = launch_layernorm(x, gamma, beta, y, rows, C, eps, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : RVCB200_ERR_CUDA;
+}
+
+}  // extern "C"

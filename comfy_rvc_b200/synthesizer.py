@@ -1,0 +1,271 @@
+"""Drop-in replacements for the reference synthesizer classes.
+
+`SynthesizerTrnMs256NSFsid` / `SynthesizerTrnMs768NSFsid` keep the reference contract
+(/root/reference/lib/infer_pack/models.py:573-693, :696-809; call sites
+/root/reference/vc_infer_pipeline.py:205-226, :100-101):
+
+    net_g = Cls(*cpt["config"], is_half=config.is_half)     # 18 positional args + is_half
+    del net_g.enc_q
+    net_g.load_state_dict(cpt["weight"], strict=False)      # reference key layout, fp16 tensors
+    net_g.eval().to(device); net_g = net_g.half() | net_g.float()
+    o, x_mask, (z, z_p, m_p, logs_p) = net_g.infer(phone, phone_lengths, pitch, nsff0, sid)
+
+but every FLOP of `infer` runs in librvcb200.so (hand-written sm_100a CUDA behind the C ABI of
+include/rvcb200.h).  There is no PyTorch or CPU fallback: without the extension or without a CUDA
+device `infer` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _lib
+from .config import SynthConfig
+from .weights import pack, validate_state_dict
+
+
+class _IncompatibleKeys:
+    def __init__(self, missing, unexpected):
+        self.missing_keys, self.unexpected_keys = missing, unexpected
+
+    def __repr__(self):
+        return f"<missing={self.missing_keys} unexpected={self.unexpected_keys}>"
+
+
+class SynthesizerB200(nn.Module):
+    """Common implementation; subclasses fix `feat_dim` (TextEncoder256 vs TextEncoder768)."""
+
+    feat_dim = 768
+
+    def __init__(self, *args, is_half: bool = False, **kwargs):
+        super().__init__()
+        self.cfg = SynthConfig.from_positional(args, self.feat_dim)
+        if self.cfg.hidden_channels != 192 or self.cfg.n_heads != 2 or self.cfg.inter_channels != 192:
+            raise ValueError("rvcb200 kernels are built for hidden=inter=192, 2 heads (every shipped RVC config)")
+        self.enc_q = nn.Identity()          # `del net_g.enc_q` (vc_infer_pipeline.py:219) must work
+        self.is_half = bool(is_half)
+        self.precision = "fp32"             # arithmetic of the heavy contractions, see set_precision
+        self._device = torch.device("cuda", 0)
+        self._ref_sd: Optional[Dict[str, torch.Tensor]] = None
+        self._packed: Optional[Dict[str, torch.Tensor]] = None   # device tensors (kept alive for the ctx)
+        self._ctx = None
+        self._ws: Optional[torch.Tensor] = None
+        self.last_launches = 0
+
+    # ---- nn.Module protocol the reference callers use ------------------------------------------
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        missing, unexpected, mismatched = validate_state_dict(self.cfg, state_dict)
+        if mismatched:
+            raise RuntimeError(f"size mismatch for {mismatched[:3]} ...")
+        if missing:
+            # the reference would silently keep random-init values with strict=False; a synthesis
+            # engine with missing weights is never what the caller wants
+            raise RuntimeError(f"missing keys in state_dict: {missing[:5]} ...")
+        if strict and unexpected:
+            raise RuntimeError(f"unexpected keys in state_dict: {unexpected[:5]} ...")
+        self._ref_sd = {k: v.detach().to("cpu") for k, v in state_dict.items() if not k.startswith("enc_q.")}
+        self._release()
+        return _IncompatibleKeys([], unexpected)
+
+    def state_dict(self, *a, **k):
+        return dict(self._ref_sd or {})
+
+    def to(self, device=None, *args, **kwargs):
+        if device is not None and not isinstance(device, torch.dtype):
+            dev = torch.device(device)
+            if dev.type == "cuda":
+                dev = torch.device("cuda", dev.index if dev.index is not None else 0)
+            if dev != self._device:
+                self._device = dev
+                self._release()
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if isinstance(device, int) else 0))
+
+    def half(self):
+        self.is_half = True
+        return self
+
+    def float(self):
+        self.is_half = False
+        return self
+
+    def remove_weight_norm(self):  # models.py:661-664: weight-norm is already folded at load
+        return None
+
+    def set_precision(self, precision: str):
+        if precision not in _lib.PREC:
+            raise ValueError(precision)
+        self.precision = precision
+        return self
+
+    # ---- engine management ----------------------------------------------------------------------
+    def _release(self):
+        if self._ctx is not None:
+            _lib.load().rvcb200_destroy(self._ctx)
+        self._ctx, self._packed, self._ws = None, None, None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _c_config(self) -> _lib.RvcConfig:
+        cfg = self.cfg
+        c = _lib.RvcConfig()
+        c.feat_dim, c.inter_channels, c.hidden_channels = cfg.feat_dim, cfg.inter_channels, cfg.hidden_channels
+        c.filter_channels, c.n_heads, c.n_layers = cfg.filter_channels, cfg.n_heads, cfg.n_layers
+        c.enc_kernel, c.window_size, c.flow_kernel = cfg.kernel_size, cfg.window_size, cfg.flow_kernel
+        c.flow_wn_layers, c.n_flows = cfg.flow_wn_layers, cfg.n_flows
+        c.resblock_kind = 1 if cfg.resblock == "1" else 2
+        c.n_res_kernels = cfg.num_kernels
+        for j, (k, ds) in enumerate(zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes)):
+            c.res_kernels[j] = k
+            c.n_res_dils[j] = len(ds)
+            for d, v in enumerate(ds):
+                c.res_dils[j][d] = v
+        c.n_ups = cfg.num_upsamples
+        for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
+            c.up_rates[i], c.up_kernels[i] = u, k
+        c.up_init_channels, c.gin_channels = cfg.upsample_initial_channel, cfg.gin_channels
+        c.n_speakers = int(self._ref_sd["emb_g.weight"].shape[0])
+        c.sr = cfg.sr
+        return c
+
+    def _materialize(self):
+        if self._ctx is not None:
+            return
+        if self._ref_sd is None:
+            raise RuntimeError("load_state_dict() must be called before infer()")
+        if not torch.cuda.is_available():
+            raise RuntimeError("comfy_rvc_b200 needs a CUDA (sm_100a) device; it has no CPU fallback")
+        lib = _lib.load()
+        packed, scalars = pack(self.cfg, self._ref_sd)
+        with torch.cuda.device(self._device):
+            self._packed = {k: v.to(self._device, dtype=torch.float32).contiguous() for k, v in packed.items()}
+            ctx = C.c_void_p()
+            cc = self._c_config()
+            _lib.check(lib.rvcb200_create(C.byref(cc), C.byref(ctx)), None, "create")
+            self._ctx = ctx
+            for k, t in self._packed.items():
+                _lib.check(lib.rvcb200_set_tensor(ctx, k.encode(), C.c_void_p(t.data_ptr()), t.numel(), 0), ctx, k)
+            for k, v in scalars.items():
+                _lib.check(lib.rvcb200_set_scalar(ctx, k.encode(), C.c_float(v)), ctx, k)
+            _lib.check(lib.rvcb200_finalize(ctx), ctx, "finalize")
+
+    def _workspace(self, B: int, T: int, prec: int) -> torch.Tensor:
+        need = int(_lib.load().rvcb200_workspace_bytes(self._ctx, B, T, prec))
+        if need <= 0:
+            raise RuntimeError("rvcb200_workspace_bytes failed")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self._device)
+        return self._ws
+
+    # ---- the hot path ---------------------------------------------------------------------------
+    def draw_noise(self, B: int, T: int, device=None, dtype=torch.float32):
+        """The reference's three RNG draws, same order and shapes (models.py:685/801, :378, :409), on
+        `device`, so a seeded torch generator yields the stream the reference would consume there."""
+        device = device or self._device
+        L = T * self.cfg.upp
+        nz = torch.randn(B, self.cfg.inter_channels, T, device=device, dtype=dtype)
+        ri = torch.rand(B, 1, device=device)
+        ns = torch.randn(B, L, 1, device=device, dtype=torch.float32)
+        return nz, ri, ns
+
+    @torch.no_grad()
+    def infer(self, phone, phone_lengths, pitch, nsff0, sid, rate=None, noise=None, taps=None):
+        """Same signature/return as the reference `infer` (models.py:682-693 / :798-809).
+
+        `noise=(noise_zp[B,192,T], rand_ini, noise_sine[B,L,1])` injects the RNG draws (parity tests);
+        otherwise they are drawn with torch on the compute device in the reference's order.
+        `taps` (dict name -> None) is filled with intermediate tensors (channels-last) for tests.
+        """
+        if rate:
+            raise NotImplementedError("rate= (tail re-synthesis) is never used by vc_infer_pipeline; not built")
+        self._materialize()
+        lib = _lib.load()
+        dev = self._device
+        cfg = self.cfg
+        B, T, Cf = phone.shape
+        if Cf != cfg.feat_dim:
+            raise ValueError(f"phone has {Cf} features, model expects {cfg.feat_dim}")
+        L = T * cfg.upp
+        with torch.cuda.device(dev):
+            phone_d = phone.to(dev, dtype=torch.float32).contiguous()
+            len_d = phone_lengths.to(dev, dtype=torch.int64).contiguous()
+            pitch_d = pitch.to(dev, dtype=torch.int64).contiguous()
+            f0_d = nsff0.to(dev, dtype=torch.float32).contiguous()
+            sid_d = sid.to(dev, dtype=torch.int64).reshape(-1).contiguous()
+            if sid_d.numel() != B or pitch_d.shape != (B, T) or f0_d.shape != (B, T) or len_d.numel() != B:
+                raise ValueError("inconsistent batch/time dimensions")
+            if noise is None:
+                nz, _ri, ns = self.draw_noise(B, T, dev)
+            else:
+                nz, _ri, ns = noise
+            nz = nz.to(dev, dtype=torch.float32).contiguous()
+            ns = ns.to(dev, dtype=torch.float32).reshape(B, L).contiguous()
+            prec = _lib.PREC[self.precision]
+            ws = self._workspace(B, T, prec)
+            o = torch.empty(B, 1, L, device=dev, dtype=torch.float32)
+            stats = torch.empty(B, T, 2 * cfg.inter_channels, device=dev, dtype=torch.float32)
+            z_p = torch.empty(B, T, cfg.inter_channels, device=dev, dtype=torch.float32)
+            z = torch.empty(B, T, cfg.inter_channels, device=dev, dtype=torch.float32)
+            tap_arr, n_taps, tap_keep = None, 0, {}
+            if taps is not None:
+                shapes = self._tap_shapes(B, T)
+                names = [n for n in taps if n in shapes]
+                tap_arr = (_lib.RvcTap * max(len(names), 1))()
+                for i, n in enumerate(names):
+                    t = torch.zeros(shapes[n], device=dev, dtype=torch.float32)
+                    tap_keep[n] = t
+                    tap_arr[i].name = n.encode()
+                    tap_arr[i].dst = t.data_ptr()
+                    tap_arr[i].bytes = t.numel() * 4
+                n_taps = len(names)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            st = lib.rvcb200_infer(
+                self._ctx, B, T, C.c_void_p(phone_d.data_ptr()), C.c_void_p(len_d.data_ptr()),
+                C.c_void_p(pitch_d.data_ptr()), C.c_void_p(f0_d.data_ptr()), C.c_void_p(sid_d.data_ptr()),
+                C.c_void_p(nz.data_ptr()), C.c_void_p(ns.data_ptr()), C.c_void_p(o.data_ptr()),
+                C.c_void_p(stats.data_ptr()), C.c_void_p(z_p.data_ptr()), C.c_void_p(z.data_ptr()),
+                C.c_void_p(ws.data_ptr()), ws.numel(), prec, tap_arr, n_taps, C.c_void_p(stream))
+            _lib.check(st, self._ctx, "infer")
+            self.last_launches = int(lib.rvcb200_last_launch_count(self._ctx))
+            if taps is not None:
+                taps.update(tap_keep)
+            x_mask = (torch.arange(T, device=dev).unsqueeze(0) < len_d.unsqueeze(1)).unsqueeze(1).to(torch.float32)
+            Ci = cfg.inter_channels
+            m_p = stats[:, :, :Ci].transpose(1, 2)
+            logs_p = stats[:, :, Ci:].transpose(1, 2)
+            return o, x_mask, (z.transpose(1, 2), z_p.transpose(1, 2), m_p, logs_p)
+
+    def _tap_shapes(self, B, T):
+        cfg = self.cfg
+        s = {"x_enc": (B, T, cfg.hidden_channels), "stats": (B, T, 2 * cfg.inter_channels),
+             "z_p": (B, T, cfg.inter_channels), "z": (B, T, cfg.inter_channels), "har_source": (B, T * cfg.upp),
+             "dec.pre": (B, T, cfg.upsample_initial_channel)}
+        Lc = T
+        for i, u in enumerate(cfg.upsample_rates):
+            Lc *= u
+            s[f"dec.ups.{i}"] = (B, Lc, cfg.stage_channels(i))
+            s[f"dec.stage.{i}"] = (B, Lc, cfg.stage_channels(i))
+        return s
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training forward() is out of scope; use infer()")
+
+
+class SynthesizerTrnMs256NSFsid(SynthesizerB200):
+    """v1 models: 256-d HuBERT features (reference models.py:573-693)."""
+    feat_dim = 256
+
+
+class SynthesizerTrnMs768NSFsid(SynthesizerB200):
+    """v2 models: 768-d HuBERT features (reference models.py:696-809)."""
+    feat_dim = 768

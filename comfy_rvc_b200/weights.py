@@ -1,0 +1,175 @@
+"""Checkpoint -> kernel layouts ("weight-norm folded at load").
+
+Input is the reference state_dict `cpt["weight"]` (fp16 on disk, `weight_g`/`weight_v` pairs,
+/root/reference/training_cli.py:41-45; key layout SURVEY.md §8b).  Output is a dict of fp32
+tensors in the layouts the CUDA kernels consume, registered by name with the C ABI:
+
+  conv weights      [G][taps][C_in][C_out]   (C_out contiguous; channels-last implicit GEMM)
+  WN in_layers      output channels interleaved (2c = tanh half c, 2c+1 = sigmoid half c) so the
+                    gate of commons.py:211-218 is applied on register pairs in the epilogue
+  flow pre/post     channel order pre-reversed for the layers that run in "flipped" state, which
+                    removes modules.Flip (modules.py:373-380) from the run time entirely
+  dec.ups           ConvTranspose1d split into `stride` phase groups of ceil(k/stride) taps
+                    (SURVEY.md App. E), tap order = increasing input frame
+  cond.*            dec.cond and all WN cond_layers stacked into one [n_cond][gin] matrix
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from .config import SynthConfig, state_dict_shapes
+
+
+def fold_weight_norm(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """`*.weight_g` + `*.weight_v` -> `*.weight` using the primitive the reference's
+    torch.nn.utils.weight_norm hook calls (bit-exact)."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        if k.endswith("weight_v"):
+            out[k[:-8] + "weight"] = torch._weight_norm(v.float(), sd[k[:-1] + "g"].float(), 0)
+        elif not k.endswith("weight_g"):
+            out[k] = v.float()
+    return out
+
+
+def validate_state_dict(cfg: SynthConfig, sd: Dict[str, torch.Tensor]):
+    """Returns (missing, unexpected, mismatched) against the reference key layout."""
+    want = state_dict_shapes(cfg)
+    missing = [k for k in want if k not in sd]
+    unexpected = [k for k in sd if k not in want and not k.startswith("enc_q.")]
+    mismatched = [(k, tuple(sd[k].shape), want[k]) for k in want if k in sd and tuple(sd[k].shape) != want[k]]
+    return missing, unexpected, mismatched
+
+
+def conv_w(w: torch.Tensor) -> torch.Tensor:
+    """Conv1d weight [C_out, C_in, k] -> [k][C_in][C_out]."""
+    return w.permute(2, 1, 0).contiguous()
+
+
+def up_geometry(k: int, u: int) -> Tuple[int, int, list]:
+    """(pad, ntaps, g_off[p]) — must match `up_geom` in csrc/engine.cu."""
+    pad = (k - u) // 2
+    ntaps = (k + u - 1) // u
+    g_off = [(p + pad) // u - (ntaps - 1) for p in range(u)]
+    return pad, ntaps, g_off
+
+
+def pack_conv_transpose(w: torch.Tensor, u: int) -> torch.Tensor:
+    """ConvTranspose1d weight [C_in, C_out, k] -> [u][ntaps][C_in][C_out].
+
+    out[n = j*u + p] = sum_m x[j + q_p - m] W[:, :, kappa_0 + m*u],  kappa_0 = (p+pad) % u,
+    q_p = (p+pad) // u (models.py:498-511 with padding=(k-u)//2).  Tap t of
+    the packed kernel reads input frame j + g_off[p] + t, i.e. m = ntaps-1-t.
+    """
+    cin, cout, k = w.shape
+    pad, ntaps, _ = up_geometry(k, u)
+    out = torch.zeros(u, ntaps, cin, cout, dtype=w.dtype)
+    for p in range(u):
+        k0 = (p + pad) % u
+        for t in range(ntaps):
+            kap = k0 + (ntaps - 1 - t) * u
+            if kap < k:
+                out[p, t] = w[:, :, kap]
+    return out
+
+
+def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch.Tensor], Dict[str, float]]:
+    """Reference state_dict -> (packed fp32 tensors, scalars)."""
+    w = fold_weight_norm(sd)
+    H, C = cfg.hidden_channels, cfg.inter_channels
+    half = C // 2
+    P: Dict[str, torch.Tensor] = {}
+    S: Dict[str, float] = {}
+    P["emb_g"] = w["emb_g.weight"].contiguous()
+    # ---- TextEncoder ----
+    P["enc.emb.w"] = w["enc_p.emb_phone.weight"].t().contiguous()            # [C_f][H]
+    P["enc.emb.b"] = w["enc_p.emb_phone.bias"].contiguous()
+    P["enc.emb_pitch"] = w["enc_p.emb_pitch.weight"].contiguous()            # [256][H]
+    for l in range(cfg.n_layers):
+        a = f"enc_p.encoder.attn_layers.{l}"
+        P[f"enc.{l}.qkv.w"] = torch.cat([w[f"{a}.conv_{n}.weight"][:, :, 0].t() for n in "qkv"], dim=1).contiguous()
+        P[f"enc.{l}.qkv.b"] = torch.cat([w[f"{a}.conv_{n}.bias"] for n in "qkv"]).contiguous()
+        P[f"enc.{l}.rel_k"] = w[f"{a}.emb_rel_k"][0].contiguous()            # heads_share -> [2w+1][dk]
+        P[f"enc.{l}.rel_v"] = w[f"{a}.emb_rel_v"][0].contiguous()
+        P[f"enc.{l}.o.w"] = w[f"{a}.conv_o.weight"][:, :, 0].t().contiguous()
+        P[f"enc.{l}.o.b"] = w[f"{a}.conv_o.bias"].contiguous()
+        for n, m in (("ln1", "norm_layers_1"), ("ln2", "norm_layers_2")):
+            P[f"enc.{l}.{n}.g"] = w[f"enc_p.encoder.{m}.{l}.gamma"].contiguous()
+            P[f"enc.{l}.{n}.b"] = w[f"enc_p.encoder.{m}.{l}.beta"].contiguous()
+        f = f"enc_p.encoder.ffn_layers.{l}"
+        P[f"enc.{l}.ffn1.w"] = conv_w(w[f"{f}.conv_1.weight"])
+        P[f"enc.{l}.ffn1.b"] = w[f"{f}.conv_1.bias"].contiguous()
+        P[f"enc.{l}.ffn2.w"] = conv_w(w[f"{f}.conv_2.weight"])
+        P[f"enc.{l}.ffn2.b"] = w[f"{f}.conv_2.bias"].contiguous()
+    P["enc.proj.w"] = w["enc_p.proj.weight"][:, :, 0].t().contiguous()       # [H][2C]
+    P["enc.proj.b"] = w["enc_p.proj.bias"].contiguous()
+    # ---- conditioning: dec.cond then (flow i, layer j) blocks, each interleaved like in_layers ----
+    cond_w = [w["dec.cond.weight"][:, :, 0]]
+    cond_b = [w["dec.cond.bias"]]
+    # ---- flow: reversed(flows) = Flip, RCL3, Flip, RCL2, ... (models.py:189-191) ----
+    flipped = False
+    state = {}
+    for i in reversed(range(cfg.n_flows)):
+        flipped = not flipped
+        state[i] = flipped
+    for i in range(cfg.n_flows):
+        p = f"flow.flows.{2 * i}"
+        fl = state[i]
+        pre = w[f"{p}.pre.weight"][:, :, 0]                                   # [H][half] over logical x0
+        post_w = w[f"{p}.post.weight"][:, :, 0]                               # [half][H] -> logical x1
+        post_b = w[f"{p}.post.bias"]
+        if fl:  # physical channel p holds logical channel C-1-p
+            pre = pre.flip(1)
+            post_w = post_w.flip(0)
+            post_b = post_b.flip(0)
+        P[f"flow.{i}.pre.w"] = pre.t().contiguous()                           # [half][H]
+        P[f"flow.{i}.pre.b"] = w[f"{p}.pre.bias"].contiguous()
+        P[f"flow.{i}.post.w"] = post_w.t().contiguous()                       # [H][half]
+        P[f"flow.{i}.post.b"] = post_b.contiguous()
+        cw = w[f"{p}.enc.cond_layer.weight"][:, :, 0]                         # [2H*n][gin]
+        cb = w[f"{p}.enc.cond_layer.bias"]
+        for j in range(cfg.flow_wn_layers):
+            wi = conv_w(w[f"{p}.enc.in_layers.{j}.weight"])                   # [k][H][2H]
+            P[f"flow.{i}.in.{j}.w"] = torch.stack([wi[..., :H], wi[..., H:]], dim=-1).flatten(-2).contiguous()
+            bi = w[f"{p}.enc.in_layers.{j}.bias"]
+            P[f"flow.{i}.in.{j}.b"] = torch.stack([bi[:H], bi[H:]], dim=-1).flatten().contiguous()
+            cwj, cbj = cw[j * 2 * H:(j + 1) * 2 * H], cb[j * 2 * H:(j + 1) * 2 * H]
+            cond_w.append(torch.stack([cwj[:H], cwj[H:]], dim=1).flatten(0, 1))
+            cond_b.append(torch.stack([cbj[:H], cbj[H:]], dim=1).flatten())
+            rs_w = w[f"{p}.enc.res_skip_layers.{j}.weight"][:, :, 0]          # [2H or H][H]
+            rs_b = w[f"{p}.enc.res_skip_layers.{j}.bias"]
+            if j < cfg.flow_wn_layers - 1:
+                P[f"flow.{i}.rs.{j}.res.w"] = rs_w[:H].t().contiguous()
+                P[f"flow.{i}.rs.{j}.res.b"] = rs_b[:H].contiguous()
+                P[f"flow.{i}.rs.{j}.skip.w"] = rs_w[H:].t().contiguous()
+                P[f"flow.{i}.rs.{j}.skip.b"] = rs_b[H:].contiguous()
+            else:
+                P[f"flow.{i}.rs.{j}.skip.w"] = rs_w.t().contiguous()
+                P[f"flow.{i}.rs.{j}.skip.b"] = rs_b.contiguous()
+    P["cond.w"] = torch.cat(cond_w, dim=0).contiguous()
+    P["cond.b"] = torch.cat(cond_b, dim=0).contiguous()
+    # ---- GeneratorNSF ----
+    S["dec.src.lin_w"] = float(w["dec.m_source.l_linear.weight"].reshape(-1)[0])
+    S["dec.src.lin_b"] = float(w["dec.m_source.l_linear.bias"].reshape(-1)[0])
+    P["dec.pre.w"] = conv_w(w["dec.conv_pre.weight"])
+    P["dec.pre.b"] = w["dec.conv_pre.bias"].contiguous()
+    nk = cfg.num_kernels
+    for i, u in enumerate(cfg.upsample_rates):
+        P[f"dec.ups.{i}.w"] = pack_conv_transpose(w[f"dec.ups.{i}.weight"], u).contiguous()
+        P[f"dec.ups.{i}.b"] = w[f"dec.ups.{i}.bias"].contiguous()
+        P[f"dec.noise.{i}.w"] = w[f"dec.noise_convs.{i}.weight"][:, 0, :].t().contiguous()   # [k][C]
+        P[f"dec.noise.{i}.b"] = w[f"dec.noise_convs.{i}.bias"].contiguous()
+        for j in range(nk):
+            n = i * nk + j
+            for d in range(len(cfg.resblock_dilation_sizes[j])):
+                if cfg.resblock == "1":
+                    for src, dst in (("convs1", "c1"), ("convs2", "c2")):
+                        P[f"dec.rb.{n}.{dst}.{d}.w"] = conv_w(w[f"dec.resblocks.{n}.{src}.{d}.weight"])
+                        P[f"dec.rb.{n}.{dst}.{d}.b"] = w[f"dec.resblocks.{n}.{src}.{d}.bias"].contiguous()
+                else:
+                    P[f"dec.rb.{n}.c.{d}.w"] = conv_w(w[f"dec.resblocks.{n}.convs.{d}.weight"])
+                    P[f"dec.rb.{n}.c.{d}.b"] = w[f"dec.resblocks.{n}.convs.{d}.bias"].contiguous()
+    P["dec.post.w"] = w["dec.conv_post.weight"][0].t().contiguous()           # [k][C]
+    return P, S

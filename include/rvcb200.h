@@ -1,0 +1,177 @@
+/*
+ * rvcb200.h — C ABI of the B200-native RVC synthesis hot path.
+ *
+ * The reference has no native code and no FFI; its interface for this path
+ * is the Python call
+ *     net_g.infer(phone, phone_lengths, pitch, nsff0, sid, rate=None)
+ *         -> (o, x_mask, (z, z_p, m_p, logs_p))
+ * (/root/reference/lib/infer_pack/models.py:682-693 and :798-809), reached from
+ * /root/reference/vc_infer_pipeline.py:100-101 after `get_vc` built the module and loaded
+ * `cpt["weight"]` (:198-226).  This header is the thin boundary under the Python drop-in
+ * (`comfy_rvc_b200.SynthesizerTrnMs{256,768}NSFsid`): plain pointers and sizes, device
+ * memory owned by the caller (PyTorch tensors), status codes instead of exceptions, no
+ * allocation inside the hot call.
+ *
+ * Layout convention on the device: activations are channels-last, `[B][rows][C]` fp32 with
+ * the channel index contiguous; `phone` is therefore consumed as given by the reference
+ * (`[B,T,C_f]`), `noise_zp` as drawn by the reference (`[B,192,T]`, torch.randn_like order),
+ * and the waveform `out` is `[B][T*upp]`.
+ */
+#ifndef RVCB200_H
+#define RVCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVCB200_ABI_VERSION 1
+
+/* status codes (0 = ok) */
+#define RVCB200_OK 0
+#define RVCB200_ERR_ARG 1        /* bad argument / unsupported configuration      */
+#define RVCB200_ERR_MISSING 2    /* a required packed tensor was never registered  */
+#define RVCB200_ERR_WORKSPACE 3  /* workspace too small                            */
+#define RVCB200_ERR_CUDA 4       /* a CUDA call or kernel launch failed            */
+#define RVCB200_ERR_NO_DEVICE 5  /* no sm_100 device: there is no CPU fallback     */
+
+/* arithmetic of the heavy contractions */
+#define RVCB200_PREC_FP32 0 /* CUDA-core fp32 FMA everywhere (int16 +-1 LSB parity path)          */
+#define RVCB200_PREC_FP16 1 /* tcgen05 kind::f16 with fp16 operands, fp32 accumulate/residuals     */
+#define RVCB200_PREC_BF16 2 /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate/residuals     */
+
+#define RVCB200_MAX_UPS 8
+#define RVCB200_MAX_RESK 4
+#define RVCB200_MAX_DIL 4
+
+typedef struct rvcb200_ctx rvcb200_ctx;
+
+/* Mirrors the 18-element positional `cpt["config"]` list the reference constructors take
+ * (models.py:573-603 / 696-719; process_ckpt.py:31-137) plus the class choice (feat_dim
+ * 256 = SynthesizerTrnMs256NSFsid, 768 = SynthesizerTrnMs768NSFsid). */
+typedef struct rvcb200_config {
+  int32_t feat_dim;        /* 256 | 768 : TextEncoder256 / TextEncoder768 (models.py:33,80) */
+  int32_t inter_channels;  /* 192 */
+  int32_t hidden_channels; /* 192 */
+  int32_t filter_channels; /* 768 */
+  int32_t n_heads;         /* 2   */
+  int32_t n_layers;        /* 6   */
+  int32_t enc_kernel;      /* 3   (FFN kernel_size) */
+  int32_t window_size;     /* 10  (attentions.py:18) */
+  int32_t flow_kernel;     /* 5   (models.py:654-656) */
+  int32_t flow_wn_layers;  /* 3   */
+  int32_t n_flows;         /* 4   */
+  int32_t resblock_kind;   /* 1 = ResBlock1, 2 = ResBlock2 (models.py:496) */
+  int32_t n_res_kernels;
+  int32_t res_kernels[RVCB200_MAX_RESK];
+  int32_t n_res_dils[RVCB200_MAX_RESK];
+  int32_t res_dils[RVCB200_MAX_RESK][RVCB200_MAX_DIL];
+  int32_t n_ups;
+  int32_t up_rates[RVCB200_MAX_UPS];
+  int32_t up_kernels[RVCB200_MAX_UPS];
+  int32_t up_init_channels; /* 512 */
+  int32_t gin_channels;     /* 256 */
+  int32_t n_speakers;       /* emb_g rows */
+  int32_t sr;               /* 32000 | 40000 | 48000 */
+} rvcb200_config;
+
+/* Optional copy-out of an intermediate (stage-level parity tests).  `name` is one of
+ * "x_enc", "stats", "z_p", "z", "har_source", "dec.pre", "dec.ups.<i>", "dec.stage.<i>".
+ * `dst` is a device buffer of at least `bytes` bytes; data is channels-last fp32. */
+typedef struct rvcb200_tap {
+  const char* name;
+  void* dst;
+  size_t bytes;
+} rvcb200_tap;
+
+/* Replaces: class construction `SynthesizerTrnMs768NSFsid(*cpt["config"], is_half=...)`
+ * (vc_infer_pipeline.py:205-218). */
+int rvcb200_create(const rvcb200_config* cfg, rvcb200_ctx** out);
+void rvcb200_destroy(rvcb200_ctx* ctx);
+
+/* Replaces: `net_g.load_state_dict(cpt["weight"], strict=False)` (vc_infer_pipeline.py:221).
+ * The host folds weight-norm and re-lays-out each tensor (comfy_rvc_b200/weights.py) and
+ * registers the resulting device buffers by name; the library keeps the pointers (the
+ * caller keeps the memory alive).  dtype: 0 = fp32, 1 = fp16, 2 = bf16.  `finalize` resolves
+ * every tensor the configuration needs and fails with RVCB200_ERR_MISSING otherwise. */
+int rvcb200_set_tensor(rvcb200_ctx* ctx, const char* name, const void* dev_ptr, int64_t numel, int32_t dtype);
+/* Host-side scalars of the checkpoint: "dec.src.lin_w", "dec.src.lin_b" (dec.m_source.l_linear, a 1->1
+ * Linear, models.py:452,466). */
+int rvcb200_set_scalar(rvcb200_ctx* ctx, const char* name, float value);
+int rvcb200_finalize(rvcb200_ctx* ctx);
+
+/* Bytes of scratch `rvcb200_infer` needs for a batch of B items of T frames. */
+int64_t rvcb200_workspace_bytes(const rvcb200_ctx* ctx, int32_t B, int32_t T, int32_t precision);
+
+/* Replaces: `net_g.infer(phone, phone_lengths, pitch, nsff0, sid)` (models.py:682-693 /
+ * :798-809).  All pointers are device pointers.  The three RNG draws of the reference are
+ * inputs (as in the reference's ONNX variant, models_onnx.py:634-648): `noise_zp`
+ * [B][inter][T] and `noise_sine` [B][T*upp] as `torch.randn` lays them out; the reference's
+ * `rand_ini` draw is zeroed for the fundamental (models.py:378-381) and needs no buffer.
+ * Outputs: `out` [B][T*upp] fp32 waveform; optional `stats` [B][T][2*inter] (m_p | logs_p),
+ * `z_p` [B][T][inter], `z` [B][T][inter], channels-last (NULL to skip).
+ * Enqueues on `stream` (a cudaStream_t) and returns without synchronising. */
+int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T,
+                  const float* phone, const int64_t* phone_lengths, const int64_t* pitch,
+                  const float* nsff0, const int64_t* sid,
+                  const float* noise_zp, const float* noise_sine,
+                  float* out, float* stats, float* z_p, float* z,
+                  void* workspace, int64_t workspace_bytes, int32_t precision,
+                  const rvcb200_tap* taps, int32_t n_taps, void* stream);
+
+/* Per-class device timing of the launches inside rvcb200_infer (CUDA events on the caller's stream,
+ * accumulated until the next enable): class 0 = dense contractions (conv / 1x1 / transposed conv),
+ * 1 = attention, 2 = NSF sine source, 3 = bandwidth-bound glue (LayerNorm, prior sample, source
+ * injection, conv_post).  `collect` synchronises on the recorded events; ms/count have
+ * RVCB200_PROF_CLASSES entries. */
+#define RVCB200_PROF_CLASSES 4
+int rvcb200_profile_enable(rvcb200_ctx* ctx, int32_t on);
+int rvcb200_profile_collect(rvcb200_ctx* ctx, double* ms, int64_t* count);
+
+/* Number of kernel launches the last `rvcb200_infer` enqueued (bench.py's gpu_launches). */
+int64_t rvcb200_last_launch_count(const rvcb200_ctx* ctx);
+const char* rvcb200_last_error(const rvcb200_ctx* ctx);
+int32_t rvcb200_abi_version(void);
+
+/* ---- op-level entry points (unit tests and micro-benchmarks; same kernels as infer) ---- */
+
+/* Channels-last 1-D convolution / phase-decomposed transposed convolution, fp32 CUDA cores.
+ * y[b][j*out_stride+g][co] = epilogue( bias[co] + sum_{tap,ci} act(x[b][j+g_off[g]+tap*dil][ci]) * w[g][tap][ci][co] ).
+ * Replaces F.conv1d / F.conv_transpose1d call sites of modules.py:295-308, models.py:545-563. */
+typedef struct rvcb200_conv_desc {
+  const float* x; int64_t x_bstride; int32_t ldx; int32_t L_in; const int32_t* in_len; float in_slope;
+  const float* w; const float* bias; int32_t Cin, Cout, ntaps, dil; int32_t G; int32_t g_off[16];
+  int32_t Lj; int32_t out_stride;
+  float* y; int64_t y_bstride; int32_t ldy;
+  const float* cond; int32_t cond_bstride;
+  const float* gather; const int64_t* gidx; int64_t gidx_bstride;
+  float alpha; int32_t gate;
+  int32_t mask_pre, mask_post; const int32_t* out_len;
+  const float* res; int64_t res_bstride; int32_t ldr; int32_t res_mode;
+  float out_slope; int32_t relu;
+  int32_t accum; float div;
+} rvcb200_conv_desc;
+int rvcb200_op_conv_f32(const rvcb200_conv_desc* d, int32_t B, void* stream);
+
+/* NSF harmonic source (SineGen + SourceModuleHnNSF, models.py:361-411,455-467):
+ * f0 [B][T] -> har [B][T*upp]; scratch >= rvcb200_op_sine_scratch_bytes(B,T,upp). */
+int64_t rvcb200_op_sine_scratch_bytes(int32_t B, int32_t T, int32_t upp);
+int rvcb200_op_sine_source(const float* f0, const float* noise, float* har, int32_t B, int32_t T,
+                           int32_t upp, int32_t sr, float lin_w, float lin_b, void* scratch, void* stream);
+
+/* Windowed relative-position multi-head attention (attentions.py:212-270), fp32.
+ * qkv [B][T][3*H] (q|k|v, head h at channels h*dk), out [B][T][H]. */
+int rvcb200_op_attention_f32(const float* qkv, const float* rel_k, const float* rel_v, const int32_t* len,
+                             float* out, int32_t B, int32_t T, int32_t n_heads, int32_t dk, int32_t window,
+                             void* stream);
+
+/* Row LayerNorm over C contiguous channels (modules.py:25-28). */
+int rvcb200_op_layernorm(const float* x, const float* gamma, const float* beta, float* y, int64_t rows,
+                         int32_t C, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVCB200_H */

@@ -1,0 +1,94 @@
+"""CPU: the host-side weight packing (fold, flip absorption, gate interleave, transposed-conv
+phase decomposition, stacked conditioning) is equivalent to the oracle's formulation."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from comfy_rvc_b200 import synthetic, weights
+from comfy_rvc_b200.config import NAMED_CONFIGS
+from oracle import rvc_oracle
+from tests._emulate import conv_cl
+
+
+@pytest.mark.parametrize("k,u", [(24, 12), (20, 10), (16, 10), (16, 8), (4, 2), (16, 6), (16, 4)])
+def test_conv_transpose_phase_decomposition(k, u):
+    g = torch.Generator().manual_seed(k * 100 + u)
+    cin, cout, L = 16, 8, 37
+    w = torch.randn(cin, cout, k, generator=g, dtype=torch.float64)
+    b = torch.randn(cout, generator=g, dtype=torch.float64)
+    x = torch.randn(2, cin, L, generator=g, dtype=torch.float64)
+    ref = F.conv_transpose1d(x, w, b, stride=u, padding=(k - u) // 2)         # [B][cout][L*u]
+    assert ref.shape[-1] == L * u
+    pad, ntaps, g_off = weights.up_geometry(k, u)
+    y = conv_cl(x.transpose(1, 2), weights.pack_conv_transpose(w, u), b, g_off=g_off, out_stride=u)
+    torch.testing.assert_close(y.transpose(1, 2), ref, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("cfg_name", ["48k_v2", "40k"])
+def test_flow_packing_matches_oracle(cfg_name):
+    cfg = NAMED_CONFIGS[cfg_name]
+    sd = {k: v.double() for k, v in synthetic.make_state_dict(cfg).items()}
+    P, S = weights.pack(cfg, sd)
+    P = {k: v.double() for k, v in P.items()}
+    w = {k: v.double() for k, v in rvc_oracle.fold_weight_norm(sd).items()}
+    B, T, H, C = 2, 40, cfg.hidden_channels, cfg.inter_channels
+    half = C // 2
+    g = torch.Generator().manual_seed(3)
+    lens = torch.tensor([T, 29])
+    mask = (torch.arange(T)[None] < lens[:, None]).double()                   # [B][T]
+    z_p = torch.randn(B, C, T, generator=g, dtype=torch.float64) * mask[:, None]
+    sid = torch.tensor([0, 5])
+    gvec = w["emb_g.weight"][sid]                                             # [B][gin]
+    ref = rvc_oracle.flow_reverse(w, cfg, z_p, mask[:, None], gvec.unsqueeze(-1))
+    # --- emulate engine.cu's flow section with the packed tensors ---
+    cond = gvec @ P["cond.w"].t() + P["cond.b"]                               # [B][n_cond]
+    z = z_p.transpose(1, 2).clone()                                           # channels-last
+    m3 = mask[:, :, None]
+    flipped = False
+    for i in reversed(range(cfg.n_flows)):
+        flipped = not flipped
+        in_off = half if flipped else 0
+        out_off = half - in_off
+        h = conv_cl(z[:, :, in_off:in_off + half], P[f"flow.{i}.pre.w"][None, None], P[f"flow.{i}.pre.b"]) * m3
+        skip = None
+        for j in range(cfg.flow_wn_layers):
+            kf = cfg.flow_kernel
+            xin = conv_cl(h, P[f"flow.{i}.in.{j}.w"][None], P[f"flow.{i}.in.{j}.b"], g_off=[-(kf - 1) // 2])
+            off = cfg.upsample_initial_channel + (i * cfg.flow_wn_layers + j) * 2 * H
+            xin = xin + cond[:, None, off:off + 2 * H]
+            acts = torch.tanh(xin[..., 0::2]) * torch.sigmoid(xin[..., 1::2])
+            if j < cfg.flow_wn_layers - 1:
+                h = (h + conv_cl(acts, P[f"flow.{i}.rs.{j}.res.w"][None, None], P[f"flow.{i}.rs.{j}.res.b"])) * m3
+            sk = conv_cl(acts, P[f"flow.{i}.rs.{j}.skip.w"][None, None], P[f"flow.{i}.rs.{j}.skip.b"])
+            skip = sk if skip is None else skip + sk
+        m = conv_cl(skip, P[f"flow.{i}.post.w"][None, None], P[f"flow.{i}.post.b"], in_len=lens) * m3
+        z[:, :, out_off:out_off + half] = (z[:, :, out_off:out_off + half] - m) * m3
+    torch.testing.assert_close(z.transpose(1, 2), ref, rtol=1e-10, atol=1e-10)
+    # dec.cond is the first block of the stacked conditioning matrix
+    ref_c = F.conv1d(gvec.unsqueeze(-1), w["dec.cond.weight"], w["dec.cond.bias"])[:, :, 0]
+    torch.testing.assert_close(cond[:, :cfg.upsample_initial_channel], ref_c, rtol=1e-12, atol=1e-12)
+
+
+def test_encoder_and_decoder_packing_shapes():
+    cfg = NAMED_CONFIGS["48k"]                                                # 5-stage ladder
+    sd = synthetic.make_state_dict(cfg)
+    P, S = weights.pack(cfg, sd)
+    w = rvc_oracle.fold_weight_norm(sd)
+    x = torch.randn(1, 11, 192)
+    # qkv fused 1x1 == three separate convs
+    qkv = conv_cl(x, P["enc.0.qkv.w"][None, None], P["enc.0.qkv.b"])
+    a = "enc_p.encoder.attn_layers.0"
+    for n, name in enumerate("qkv"):
+        ref = F.conv1d(x.transpose(1, 2), w[f"{a}.conv_{name}.weight"], w[f"{a}.conv_{name}.bias"]).transpose(1, 2)
+        torch.testing.assert_close(qkv[..., n * 192:(n + 1) * 192], ref, rtol=1e-5, atol=1e-5)
+    # dilated resblock conv through the generic contract
+    xx = torch.randn(1, 50, 256)
+    k, d = 11, 5
+    ref = F.conv1d(xx.transpose(1, 2), w["dec.resblocks.2.convs1.2.weight"], w["dec.resblocks.2.convs1.2.bias"],
+                   dilation=d, padding=(k * d - d) // 2).transpose(1, 2)
+    y = conv_cl(xx, P["dec.rb.2.c1.2.w"][None], P["dec.rb.2.c1.2.b"], g_off=[-((k - 1) // 2) * d], dil=d)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
+    assert P["dec.post.w"].shape == (7, 16) and P["dec.noise.0.w"].shape == (96, 256)
+    missing, unexpected, mismatched = weights.validate_state_dict(cfg, sd)
+    assert not missing and not unexpected and not mismatched
