@@ -11,7 +11,7 @@
 // outputs interleave.
 //
 // Tiling: time is the GEMM M axis, C_out the N axis, (tap, ci) the K axis.  A CTA of 128
-// threads owns BM x BN outputs (128x64 or 256x32), each thread an 8x8 register tile whose
+// threads owns BM x BN outputs (128x64, 256x32 or 512x16), each thread an 8x8 register tile whose
 // rows are interleaved (row = i*TMT + tm) so that the per-tap shifted reads of the staged
 // input are conflict-free scalar LDS and the weight reads are broadcast LDS.128.  The input
 // rows (BM + halo, 8 channels per chunk) are staged ONCE per channel chunk and reused by
@@ -255,11 +255,12 @@ cudaError_t launch_t(const ConvDesc& d, int B, cudaStream_t st) {
 }  // namespace
 
 cudaError_t launch_conv_f32(const ConvDesc& d, int B, cudaStream_t st) {
-  if (d.Cin % BK != 0 || d.Cout % 32 != 0 || d.ntaps < 1 || (d.ntaps - 1) * d.dil > kMaxHalo || d.G < 1 || d.G > 16 ||
+  if (d.Cin % BK != 0 || d.Cout % 16 != 0 || d.ntaps < 1 || (d.ntaps - 1) * d.dil > kMaxHalo || d.G < 1 || d.G > 16 ||
       d.ldx % 4 != 0 || d.ldy % 2 != 0 || d.Lj <= 0 || B <= 0)
     return cudaErrorInvalidValue;
   if (d.Cout % 64 == 0) return launch_t<64>(d, B, st);
-  return launch_t<32>(d, B, st);
+  if (d.Cout % 32 == 0) return launch_t<32>(d, B, st);
+  return launch_t<16>(d, B, st);   // last stage of the 5-stage v1 ladders (32k, 48k): 32 -> 16 channels
 }
 
 }  // namespace rvc
