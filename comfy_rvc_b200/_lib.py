@@ -48,6 +48,20 @@ class ConvDesc(C.Structure):
     ]
 
 
+class TcConvDesc(C.Structure):
+    _fields_ = [
+        ("x16", C.c_void_p), ("Lp_in", C.c_int32), ("padf", C.c_int32),
+        ("w16", C.c_void_p), ("bias", C.c_void_p),
+        ("Cin", C.c_int32), ("KB", C.c_int32), ("ntaps", C.c_int32), ("dil", C.c_int32), ("G", C.c_int32),
+        ("g_off", C.c_int32 * 16),
+        ("N", C.c_int32), ("Cout_total", C.c_int32), ("tmem_cols", C.c_int32),
+        ("Lj", C.c_int32), ("out_stride", C.c_int32), ("Lp_out", C.c_int32),
+        ("y32", C.c_void_p), ("y16", C.c_void_p), ("res32", C.c_void_p),
+        ("cond", C.c_void_p), ("cond_bstride", C.c_int32),
+        ("accum", C.c_int32), ("div", C.c_float), ("out_slope", C.c_float),
+    ]
+
+
 # every symbol include/rvcb200.h declares: (restype, argtypes)
 SYMBOLS = {
     "rvcb200_abi_version": (C.c_int32, []),
@@ -65,6 +79,7 @@ SYMBOLS = {
     "rvcb200_last_launch_count": (C.c_int64, [C.c_void_p]),
     "rvcb200_last_error": (C.c_char_p, [C.c_void_p]),
     "rvcb200_op_conv_f32": (C.c_int, [C.POINTER(ConvDesc), C.c_int32, C.c_void_p]),
+    "rvcb200_op_conv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_int32, C.c_void_p]),
     "rvcb200_op_sine_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "rvcb200_op_sine_source": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

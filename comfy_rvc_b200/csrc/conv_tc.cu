@@ -1,0 +1,509 @@
+// tcgen05 / TMEM implicit-GEMM 1-D convolution for sm_100a (fp16 or bf16 operands, fp32 accumulate).
+//
+//   D[128 time rows][N = C_out tile] (TMEM, fp32) += sum_{k-block} sum_{tap} A_tap[128][KB] * W_tap[N][KB]^T
+//
+// Data layout ("planar-vector", PV): activations live as [B][C/8][Lp][8] 16-bit (and
+// [B][C/4][Lp][4] fp32 for the residual stream), i.e. one 16-byte vector per (row, channel group),
+// rows contiguous inside a channel-group plane, PADF zero rows in front and >= 96 behind.  This is
+// exactly the tcgen05 no-swizzle K-major canonical layout ((8,m),(8,2)):((16B,128B),(2B,LBO))
+// (cute/atom/mma_traits_sm100.hpp "LayoutType::INTERLEAVE"), with LBO = plane pitch, so
+//   * one bulk copy (cp.async.bulk, UBLKCP) per channel group stages 128+halo rows ONCE per
+//     64-channel k-block and every tap of a dilated kernel is just a descriptor start-address
+//     offset of tap*dil*16 bytes into that slab (no im2col, no re-fetch per tap);
+//   * zero padding at sequence ends is physical (the pad rows are never written);
+//   * the epilogue (thread = TMEM lane = time row) reads residuals and writes outputs as 512-byte
+//     coalesced warp transactions.
+// Weights are pre-packed on the host into the smem image [tap][k-block][8 groups][N][8] so one
+// bulk copy per (k-block, tap) feeds the B operand.
+//
+// Warp roles (192 threads): warp 0 = bulk-copy producer (one lane), warp 1 = TMEM allocator + MMA
+// issuer (one lane), warps 2..5 = epilogue (TMEM lane quadrant = warp_id % 4).
+// Replaces the cuDNN calls behind modules.py:295-308 (ResBlock1), models.py:545-551 (conv_pre, ups).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace rvc {
+namespace {
+
+constexpr int kThreadsTC = 192;
+constexpr int BM = 128;
+constexpr int NB_STAGES = 4;     // weight ring depth
+constexpr int NA_STAGES = 3;     // activation slab ring depth (prefetch distance 2 k-blocks)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, no swizzle: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kThreadsTC) conv_tc_kernel(const TcConvDesc p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z / p.G, g = blockIdx.z % p.G;
+  const int j0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * p.N;                 // first output channel of this n-tile
+  const int halo = (p.ntaps - 1) * p.dil;
+  const int R = (BM + halo + 7) & ~7;              // slab rows
+  const int ngrp = p.KB / 8;                       // 16-byte channel groups per k-block
+  const int nkb = p.Cin / p.KB;
+  const uint32_t a_bytes = (uint32_t)ngrp * R * 16;
+  const uint32_t b_bytes = (uint32_t)p.N * p.KB * 2;
+
+  unsigned char* slabA = smem;                                        // [NA_STAGES][ngrp][R][16]
+  unsigned char* slabB = smem + NA_STAGES * ((a_bytes + 127) & ~127u);  // [NB_STAGES][ngrp][N][16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabB + (size_t)NB_STAGES * ((b_bytes + 127) & ~127u));
+  uint64_t* a_full = bars;                         // [NA_STAGES]
+  uint64_t* a_empty = bars + NA_STAGES;            // [NA_STAGES]
+  uint64_t* b_full = bars + 2 * NA_STAGES;         // [NB_STAGES]
+  uint64_t* b_empty = bars + 2 * NA_STAGES + NB_STAGES;
+  uint64_t* acc_full = bars + 2 * NA_STAGES + 2 * NB_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA_STAGES + 2 * NB_STAGES + 1);
+  const uint32_t a_stride = (a_bytes + 127) & ~127u, b_stride = (b_bytes + 127) & ~127u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NA_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation (power of two >= 32 columns), address lands in smem
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== producer: bulk copies global -> smem ===========================
+    if (lane == 0) {
+      const unsigned char* xa = reinterpret_cast<const unsigned char*>(p.x16) +
+                                ((size_t)b * (p.Cin / 8)) * p.Lp_in * 16 + (size_t)(j0 + p.g_off[g] + p.padf) * 16;
+      const unsigned char* wb = reinterpret_cast<const unsigned char*>(p.w16) +
+                                ((size_t)(g * gridDim.y + blockIdx.y) * p.ntaps * nkb) * b_bytes;
+      auto issue_a = [&](int kb) {   // stage rows [j0+g_off, +R) of the 8-channel groups of k-block kb
+        const int sa = kb % NA_STAGES;
+        mbar_wait(&a_empty[sa], ((kb / NA_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&a_full[sa], a_bytes);
+        for (int c = 0; c < ngrp; ++c)
+          bulk_g2s(slabA + sa * a_stride + (size_t)c * R * 16, xa + (size_t)(kb * ngrp + c) * p.Lp_in * 16, R * 16,
+                   &a_full[sa]);
+      };
+      issue_a(0);
+      if (nkb > 1) issue_a(1);
+      int itb = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        for (int tap = 0; tap < p.ntaps; ++tap, ++itb) {
+          const int sb = itb % NB_STAGES;
+          mbar_wait(&b_empty[sb], ((itb / NB_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&b_full[sb], b_bytes);
+          bulk_g2s(slabB + sb * b_stride, wb + ((size_t)tap * nkb + kb) * b_bytes, b_bytes, &b_full[sb]);
+        }
+        if (kb + 2 < nkb) issue_a(kb + 2);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (single thread) =====================================
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A/B = F16|BF16, K-major both, N>>3 @17, M>>4 @24
+      const uint32_t fmt = BF16 ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t lbo_a = (uint32_t)R * 16, lbo_b = (uint32_t)p.N * 16;
+      const int ksteps = p.KB / 16;
+      int itb = 0;
+      uint32_t accum = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int sa = kb % NA_STAGES;
+        mbar_wait(&a_full[sa], (kb / NA_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(slabA + sa * a_stride);
+        for (int tap = 0; tap < p.ntaps; ++tap, ++itb) {
+          const int sb = itb % NB_STAGES;
+          mbar_wait(&b_full[sb], (itb / NB_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(slabB + sb * b_stride);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ad = make_desc(a_base + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
+            const uint64_t bd = make_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
+            tc_mma_f16(tmem_base, ad, bd, idesc, accum);
+            accum = 1;
+          }
+          tc_commit(&b_empty[sb]);     // frees the weight stage once these MMAs have read it
+        }
+        tc_commit(&a_empty[sa]);       // frees the activation slab
+      }
+      tc_commit(acc_full);             // accumulator complete
+    }
+  } else {
+    // =========================== epilogue: TMEM -> registers -> global ===========================
+    const int q = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int row = j0 + q * 32 + lane;             // time row (within this group's Lj rows)
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const bool row_ok = row < p.Lj;
+    const long long orow = (long long)row * p.out_stride + g + p.padf;      // physical row in the output planes
+    const size_t pitch_o = (size_t)p.Lp_out * 16;                             // bytes per plane (both 16-bit and fp32 PV)
+    unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
+    unsigned char* y16 = p.y16 ? reinterpret_cast<unsigned char*>(p.y16) + (size_t)b * (p.Cout_total / 8) * pitch_o : nullptr;
+    const unsigned char* r32 = p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
+    const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
+    for (int c0 = 0; c0 < p.N; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      if (!row_ok) continue;
+      const int co = n0 + c0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co + i);
+      if (cond) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += __ldg(cond + co + i);
+      }
+      if (r32) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const float4 r = *reinterpret_cast<const float4*>(r32 + (size_t)(co / 4 + k4) * pitch_o + (size_t)orow * 16);
+          v[k4 * 4 + 0] += r.x; v[k4 * 4 + 1] += r.y; v[k4 * 4 + 2] += r.z; v[k4 * 4 + 3] += r.w;
+        }
+      }
+      if (p.accum) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const float4 r = *reinterpret_cast<const float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + (size_t)orow * 16);
+          v[k4 * 4 + 0] += r.x; v[k4 * 4 + 1] += r.y; v[k4 * 4 + 2] += r.z; v[k4 * 4 + 3] += r.w;
+        }
+      }
+      if (p.div != 1.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] / p.div;
+      }
+      if (y32) {
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          *reinterpret_cast<float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + (size_t)orow * 16) =
+              make_float4(v[k4 * 4 + 0], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+      }
+      if (y16) {
+#pragma unroll
+        for (int k8 = 0; k8 < 2; ++k8) {
+          uint4 o;
+          o.x = pack2<BF16>(lrelu(v[k8 * 8 + 0], p.out_slope), lrelu(v[k8 * 8 + 1], p.out_slope));
+          o.y = pack2<BF16>(lrelu(v[k8 * 8 + 2], p.out_slope), lrelu(v[k8 * 8 + 3], p.out_slope));
+          o.z = pack2<BF16>(lrelu(v[k8 * 8 + 4], p.out_slope), lrelu(v[k8 * 8 + 5], p.out_slope));
+          o.w = pack2<BF16>(lrelu(v[k8 * 8 + 6], p.out_slope), lrelu(v[k8 * 8 + 7], p.out_slope));
+          *reinterpret_cast<uint4*>(y16 + (size_t)(co / 8 + k8) * pitch_o + (size_t)orow * 16) = o;
+        }
+      }
+    }
+  }
+  // ------------------------------------ teardown -------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+  }
+}
+
+size_t tc_smem_bytes(const TcConvDesc& d) {
+  const int halo = (d.ntaps - 1) * d.dil;
+  const int R = (BM + halo + 7) & ~7;
+  const size_t a = (((size_t)(d.KB / 8) * R * 16) + 127) & ~(size_t)127;
+  const size_t bb = (((size_t)d.N * d.KB * 2) + 127) & ~(size_t)127;
+  return NA_STAGES * a + NB_STAGES * bb + 8 * (2 * NA_STAGES + 2 * NB_STAGES + 1) + 16 + 128;
+}
+
+// ---- PV-layout glue kernels ----------------------------------------------------------------------
+__global__ void zero_pads_kernel(unsigned char* base, long long planes, int Lp, int padf, long long L) {
+  // zero rows [0, padf) and [padf+L, Lp) of every 16-byte-vector plane
+  const long long tail0 = padf + L;
+  const int npad = padf + (int)(Lp - tail0);
+  const long long total = planes * npad;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long pl = idx / npad;
+    const int r = (int)(idx % npad);
+    const long long row = r < padf ? r : tail0 + (r - padf);
+    *reinterpret_cast<uint4*>(base + (pl * Lp + row) * 16) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+template <bool BF16>
+__global__ void cl_to_pv16_kernel(const float* __restrict__ x, int ldx, long long L, int C, unsigned char* __restrict__ y16,
+                                  int Lp, int padf, float slope) {
+  // x [B][L][ldx] channels-last fp32 -> PV16 [B][C/8][Lp][8]
+  const int b = blockIdx.y;
+  const int ng = C / 8;
+  const long long total = L * ng;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int gch = (int)(idx / L);
+    const long long t = idx % L;
+    const float* src = x + ((long long)b * L + t) * ldx + gch * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
+    uint4 o;
+    o.x = pack2<BF16>(lrelu(a.x, slope), lrelu(a.y, slope));
+    o.y = pack2<BF16>(lrelu(a.z, slope), lrelu(a.w, slope));
+    o.z = pack2<BF16>(lrelu(c.x, slope), lrelu(c.y, slope));
+    o.w = pack2<BF16>(lrelu(c.z, slope), lrelu(c.w, slope));
+    *reinterpret_cast<uint4*>(y16 + (((long long)b * ng + gch) * Lp + padf + t) * 16) = o;
+  }
+}
+
+template <bool BF16>
+__global__ void noise_add_pv_kernel(const float* __restrict__ har, const float* __restrict__ wn, const float* __restrict__ nb,
+                                    unsigned char* __restrict__ x32, unsigned char* __restrict__ x16, long long L_har,
+                                    long long L, int C, int k, int s, int pad, int Lp, int padf, float slope) {
+  // x32 += noise_conv(har);  x16 = cvt(lrelu(x32))   (models.py:552-553 + the lrelu of modules.py:297)
+  extern __shared__ float sw[];  // [k][C] + [C]
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[k * C + i] = nb[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int ng = C / 8;
+  const long long total = L * ng;
+  const float* hb = har + (long long)b * L_har;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int gch = (int)(idx / L);
+    const long long t = idx % L;
+    const int c = gch * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = sw[k * C + c + i];
+    const long long h0 = t * s - pad;
+    for (int kk = 0; kk < k; ++kk) {
+      const long long h = h0 + kk;
+      if (h < 0 || h >= L_har) continue;
+      const float hv = __ldg(hb + h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(hv, sw[kk * C + c + i], acc[i]);
+    }
+    float4* p0 = reinterpret_cast<float4*>(x32 + (((long long)b * (C / 4) + gch * 2) * Lp + padf + t) * 16);
+    float4* p1 = reinterpret_cast<float4*>(x32 + (((long long)b * (C / 4) + gch * 2 + 1) * Lp + padf + t) * 16);
+    float4 a = *p0, d = *p1;
+    a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
+    d.x += acc[4]; d.y += acc[5]; d.z += acc[6]; d.w += acc[7];
+    *p0 = a; *p1 = d;
+    uint4 o;
+    o.x = pack2<BF16>(lrelu(a.x, slope), lrelu(a.y, slope));
+    o.y = pack2<BF16>(lrelu(a.z, slope), lrelu(a.w, slope));
+    o.z = pack2<BF16>(lrelu(d.x, slope), lrelu(d.y, slope));
+    o.w = pack2<BF16>(lrelu(d.z, slope), lrelu(d.w, slope));
+    *reinterpret_cast<uint4*>(x16 + (((long long)b * ng + gch) * Lp + padf + t) * 16) = o;
+  }
+}
+
+__global__ void conv_post_pv_kernel(const unsigned char* __restrict__ x32, const float* __restrict__ w, float* __restrict__ out,
+                                    long long L, int C, int k, int Lp, int padf, float slope) {
+  // out[b][t] = tanh(sum_{kk,c} lrelu(x[c][t+kk-pad]) * w[kk][c]);  x is PV32 with zero pads
+  extern __shared__ float swp[];  // [k][C]
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) swp[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int pad = (k - 1) / 2;
+  const int n4 = C / 4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < L; t += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int g4 = 0; g4 < n4; ++g4) {
+      const unsigned char* pl = x32 + (((long long)b * n4 + g4) * Lp + padf + t - pad) * 16;
+      for (int kk = 0; kk < k; ++kk) {
+        const float4 v = *reinterpret_cast<const float4*>(pl + (long long)kk * 16);
+        const float* wr = swp + kk * C + g4 * 4;
+        acc = fmaf(lrelu(v.x, slope), wr[0], acc);
+        acc = fmaf(lrelu(v.y, slope), wr[1], acc);
+        acc = fmaf(lrelu(v.z, slope), wr[2], acc);
+        acc = fmaf(lrelu(v.w, slope), wr[3], acc);
+      }
+    }
+    out[(long long)b * L + t] = tanhf(acc);
+  }
+}
+
+__global__ void pv32_to_cl_kernel(const unsigned char* __restrict__ x32, float* __restrict__ y, long long L, int C, int Lp, int padf) {
+  // debug/tap helper: PV32 -> channels-last [B][L][C]
+  const int b = blockIdx.y;
+  const int n4 = C / 4;
+  const long long total = L * n4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g4 = (int)(idx / L);
+    const long long t = idx % L;
+    const float4 v = *reinterpret_cast<const float4*>(x32 + (((long long)b * n4 + g4) * Lp + padf + t) * 16);
+    *reinterpret_cast<float4*>(y + ((long long)b * L + t) * C + g4 * 4) = v;
+  }
+}
+
+template <bool BF16>
+__global__ void pv16_to_cl_kernel(const unsigned char* __restrict__ x16, float* __restrict__ y, long long L, int C, int Lp, int padf) {
+  const int b = blockIdx.y;
+  const int n8 = C / 8;
+  const long long total = L * n8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g8 = (int)(idx / L);
+    const long long t = idx % L;
+    const uint4 v = *reinterpret_cast<const uint4*>(x16 + (((long long)b * n8 + g8) * Lp + padf + t) * 16);
+    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+    float* dst = y + ((long long)b * L + t) * C + g8 * 8;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f;
+      if (BF16) f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wds[i]));
+      else f = __half22float2(*reinterpret_cast<const __half2*>(&wds[i]));
+      dst[2 * i] = f.x; dst[2 * i + 1] = f.y;
+    }
+  }
+}
+
+inline unsigned grid_for(long long total, int threads) {
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace
+
+cudaError_t launch_conv_tc(const TcConvDesc& d, int B, bool bf16, cudaStream_t st) {
+  if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.KB % 16 != 0 || d.KB > 64 || d.Cin % d.KB != 0 || d.Cout_total % d.N != 0 ||
+      d.G < 1 || d.G > 16 || d.Lj <= 0 || (d.ntaps - 1) * d.dil > 56 || d.tmem_cols < d.N || (d.accum && !d.y32))
+    return cudaErrorInvalidValue;
+  const size_t smem = tc_smem_bytes(d);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static size_t cfg_h = 0, cfg_b = 0;
+  size_t& cfgd = bf16 ? cfg_b : cfg_h;
+  if (smem > cfgd) {
+    cudaError_t e = bf16 ? cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cfgd = smem;
+  }
+  dim3 grid((d.Lj + BM - 1) / BM, d.Cout_total / d.N, B * d.G);
+  if (bf16) conv_tc_kernel<true><<<grid, kThreadsTC, smem, st>>>(d);
+  else conv_tc_kernel<false><<<grid, kThreadsTC, smem, st>>>(d);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zero_pads(void* base, long long planes, int Lp, int padf, long long L, cudaStream_t st) {
+  const long long total = planes * (Lp - L);
+  zero_pads_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<unsigned char*>(base), planes, Lp, padf, L);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cl_to_pv16(const float* x, int ldx, int B, long long L, int C, void* y16, int Lp, int padf, float slope,
+                              bool bf16, cudaStream_t st) {
+  dim3 grid(grid_for(L * (C / 8), 256), B);
+  if (bf16) cl_to_pv16_kernel<true><<<grid, 256, 0, st>>>(x, ldx, L, C, reinterpret_cast<unsigned char*>(y16), Lp, padf, slope);
+  else cl_to_pv16_kernel<false><<<grid, 256, 0, st>>>(x, ldx, L, C, reinterpret_cast<unsigned char*>(y16), Lp, padf, slope);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, int B,
+                                long long L_har, long long L, int C, int k, int s, int pad, int Lp, int padf, float slope,
+                                bool bf16, cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((size_t)k * C + C);
+  static size_t cfg = 48 * 1024;
+  if (smem > cfg) {
+    cudaError_t e = cudaFuncSetAttribute(noise_add_pv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(noise_add_pv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cfg = smem;
+  }
+  dim3 grid(grid_for(L * (C / 8), 256), B);
+  if (bf16)
+    noise_add_pv_kernel<true><<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32),
+                                                       reinterpret_cast<unsigned char*>(x16), L_har, L, C, k, s, pad, Lp, padf, slope);
+  else
+    noise_add_pv_kernel<false><<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32),
+                                                        reinterpret_cast<unsigned char*>(x16), L_har, L, C, k, s, pad, Lp, padf, slope);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int B, long long L, int C, int k, int Lp,
+                                int padf, float slope, cudaStream_t st) {
+  dim3 grid(grid_for(L, 256), B);
+  conv_post_pv_kernel<<<grid, 256, sizeof(float) * k * C, st>>>(reinterpret_cast<const unsigned char*>(x32), w, out, L, C, k, Lp,
+                                                                padf, slope);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pv_to_cl(const void* src, bool is16, bool bf16, float* y, int B, long long L, int C, int Lp, int padf,
+                            cudaStream_t st) {
+  if (!is16) {
+    dim3 grid(grid_for(L * (C / 4), 256), B);
+    pv32_to_cl_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), y, L, C, Lp, padf);
+  } else {
+    dim3 grid(grid_for(L * (C / 8), 256), B);
+    if (bf16) pv16_to_cl_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), y, L, C, Lp, padf);
+    else pv16_to_cl_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), y, L, C, Lp, padf);
+  }
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+}  // namespace rvc

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_tc.cuh"
 
 using namespace rvc;
 
@@ -60,6 +61,18 @@ const float* T32(rvcb200_ctx* c, const std::string& name, long long expect, bool
     return nullptr;
   }
   return reinterpret_cast<const float*>(it->second.ptr);
+}
+
+const void* T16(rvcb200_ctx* c, const std::string& name, long long expect, int dtype, bool* ok) {
+  auto it = c->tensors.find(name);
+  if (it == c->tensors.end() || it->second.dtype != dtype || (expect > 0 && it->second.numel != expect)) {
+    if (*ok)
+      snprintf(c->err, sizeof(c->err), "missing/mismatched 16-bit tensor '%s' (dtype %d, numel %lld)", name.c_str(), dtype,
+               expect);
+    *ok = false;
+    return nullptr;
+  }
+  return it->second.ptr;
 }
 
 std::string S(const char* fmt, int a = 0, int b = 0, int c = 0) {
@@ -122,10 +135,12 @@ struct Plan {  // workspace carve-up for (B, T)
   float *cond, *x, *xt, *qkv, *att, *ffh, *stats, *zp, *z, *h, *acts, *skip, *har, *pre;
   void* sine_scratch;
   float* stage[5];
+  // tensor-core path: planar-vector buffers
+  void* z16; void* pv16[5]; float* pv32[3];
   size_t bytes;
 };
 
-Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws) {
+Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws, int precision = RVCB200_PREC_FP32) {
   const rvcb200_config& cf = c->cfg;
   Plan p;
   Bump bp(ws, 0);
@@ -155,7 +170,24 @@ Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws) {
     size_t s = (size_t)B * L * (cf.up_init_channels >> (i + 1));
     if (s > mx) mx = s;
   }
-  for (int i = 0; i < 5; ++i) p.stage[i] = bp.take<float>(mx);
+  if (precision == RVCB200_PREC_FP32) {
+    for (int i = 0; i < 5; ++i) p.stage[i] = bp.take<float>(mx);
+    p.z16 = nullptr;
+    for (int i = 0; i < 5; ++i) p.pv16[i] = nullptr;
+    for (int i = 0; i < 3; ++i) p.pv32[i] = nullptr;
+  } else {
+    for (int i = 0; i < 5; ++i) p.stage[i] = nullptr;
+    size_t mxe = (size_t)B * cf.up_init_channels * pv_pitch_rows(T);      // conv_pre output
+    long long Ls = T;
+    for (int i = 0; i < cf.n_ups; ++i) {
+      Ls *= cf.up_rates[i];
+      size_t e = (size_t)B * (cf.up_init_channels >> (i + 1)) * pv_pitch_rows(Ls);
+      if (e > mxe) mxe = e;
+    }
+    p.z16 = bp.take<unsigned short>((size_t)B * C * pv_pitch_rows(T));
+    for (int i = 0; i < 5; ++i) p.pv16[i] = bp.take<unsigned short>(mxe);
+    for (int i = 0; i < 3; ++i) p.pv32[i] = bp.take<float>(mxe);
+  }
   p.bytes = bp.off;
   return p;
 }
@@ -164,6 +196,11 @@ struct TapSet {
   const rvcb200_tap* taps;
   int n;
   cudaStream_t st;
+  const rvcb200_tap* find(const char* name) const {
+    for (int i = 0; i < n; ++i)
+      if (taps[i].name && strcmp(taps[i].name, name) == 0 && taps[i].dst) return &taps[i];
+    return nullptr;
+  }
   cudaError_t emit(const char* name, const void* src, size_t bytes) const {
     for (int i = 0; i < n; ++i)
       if (taps[i].name && strcmp(taps[i].name, name) == 0 && taps[i].dst) {
@@ -380,8 +417,7 @@ int rvcb200_finalize(rvcb200_ctx* ctx) {
 
 int64_t rvcb200_workspace_bytes(const rvcb200_ctx* ctx, int32_t B, int32_t T, int32_t precision) {
   if (!ctx || B <= 0 || T <= 0) return -1;
-  (void)precision;
-  Plan p = make_plan(ctx, B, T, nullptr);
+  Plan p = make_plan(ctx, B, T, nullptr, precision);
   return (int64_t)p.bytes + 256;
 }
 
@@ -397,13 +433,15 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
   if (B <= 0 || T <= 0 || !phone || !phone_lengths || !pitch || !nsff0 || !sid || !noise_zp || !noise_sine || !out ||
       !workspace)
     return fail(ctx, RVCB200_ERR_ARG, "null or empty argument%s", "");
-  if (precision != RVCB200_PREC_FP32)
-    return fail(ctx, RVCB200_ERR_ARG, "precision %s%lld not built in this library", "", precision);
+  if (precision != RVCB200_PREC_FP32 && precision != RVCB200_PREC_FP16 && precision != RVCB200_PREC_BF16)
+    return fail(ctx, RVCB200_ERR_ARG, "unknown precision %s%lld", "", precision);
+  const bool tc = precision != RVCB200_PREC_FP32;
+  const bool bf16 = precision == RVCB200_PREC_BF16;
   const rvcb200_config& f = ctx->cfg;
   // 256-byte align the workspace
   uintptr_t wsp = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255;
   const size_t slack = wsp - reinterpret_cast<uintptr_t>(workspace);
-  Plan pl = make_plan(ctx, B, T, reinterpret_cast<void*>(wsp));
+  Plan pl = make_plan(ctx, B, T, reinterpret_cast<void*>(wsp), precision);
   if ((int64_t)(pl.bytes + slack) > workspace_bytes)
     return fail(ctx, RVCB200_ERR_WORKSPACE, "workspace too small%s: need %lld bytes", "", (long long)(pl.bytes + 256));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -549,6 +587,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
      "sine_source");
   CK(tp.emit("har_source", pl.har, sizeof(float) * B * Lout), "tap");
 
+  if (!tc) {
   // ---------------- GeneratorNSF (models.py:542-564) -------------------------------------------
   {
     ConvDesc d = base_desc();
@@ -631,6 +670,121 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     Lc = Ln; Cc = Cn;
   }
   CKC(3, launch_conv_post_tanh(cur, W("dec.post.w"), out, B, Lc, Cc, 7, 0.01f, st), "dec.conv_post");
+
+  } else {
+    // ------------- GeneratorNSF on tcgen05 (fp16/bf16 operands, fp32 accumulate + residual stream) -----------
+    const int dt = bf16 ? 2 : 1;
+    auto W16 = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, dt, &ok); };
+    auto tmem_cols_for = [](int N) { int c = 32; while (c < N) c <<= 1; return c; };
+    auto tc_base = [&]() {
+      TcConvDesc d;
+      memset(&d, 0, sizeof(d));
+      d.padf = kPadF; d.ntaps = 1; d.dil = 1; d.G = 1; d.out_stride = 1; d.div = 1.f; d.out_slope = 1.f;
+      return d;
+    };
+    const int LpT = pv_pitch_rows(T);
+    // z -> PV16 (conv_pre consumes z*mask; z is already masked)
+    CKC(3, launch_zero_pads(pl.z16, (long long)B * (C / 8), LpT, kPadF, T, st), "zero_pads");
+    CKC(3, launch_cl_to_pv16(z, C, B, T, C, pl.z16, LpT, kPadF, 1.f, bf16, st), "z->pv16");
+    void* IN16 = pl.pv16[0];
+    void* X16 = pl.pv16[1];
+    void* XT16 = pl.pv16[2];
+    void* XB16 = pl.pv16[3];
+    void* N16 = pl.pv16[4];
+    float* X32 = pl.pv32[0];
+    float* XB32 = pl.pv32[1];
+    float* ACC32 = pl.pv32[2];
+    {
+      const int U0 = f.up_init_channels;
+      CKC(3, launch_zero_pads(IN16, (long long)B * (U0 / 8), LpT, kPadF, T, st), "zero_pads");
+      TcConvDesc d = tc_base();
+      d.x16 = pl.z16; d.Lp_in = LpT; d.w16 = W16("dec.pre.w"); d.bias = W("dec.pre.b");
+      d.Cin = C; d.KB = C < 64 ? C : 64; d.ntaps = 7; d.g_off[0] = -3;
+      d.N = U0 < 256 ? U0 : 256; d.Cout_total = U0; d.tmem_cols = tmem_cols_for(d.N);
+      d.Lj = T; d.Lp_out = LpT; d.y16 = IN16; d.out_slope = 0.1f;      // lrelu of models.py:550 folded into the store
+      d.cond = pl.cond; d.cond_bstride = ctx->n_cond;
+      if (!ok) return RVCB200_ERR_MISSING;
+      CKC(0, launch_conv_tc(d, B, bf16, st), "dec.conv_pre(tc)");
+    }
+    long long Lc = T;
+    int Cc = f.up_init_channels;
+    int LpC = LpT;
+    for (int i = 0; i < f.n_ups; ++i) {
+      UpGeom g = up_geom(f, i);
+      const long long Ln = Lc * g.u;
+      const int Cn = g.cout;
+      const int LpN = pv_pitch_rows(Ln);
+      const bool last_stage = i == f.n_ups - 1;
+      CKC(3, launch_zero_pads(X16, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
+      CKC(3, launch_zero_pads(XT16, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
+      CKC(3, launch_zero_pads(XB16, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
+      if (!last_stage) CKC(3, launch_zero_pads(N16, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
+      else CKC(3, launch_zero_pads(ACC32, (long long)B * (Cn / 4), LpN, kPadF, Ln, st), "zero_pads");
+      {  // x = ups[i](lrelu(x)) as g.u phase groups (input already holds lrelu(x) in 16 bit)
+        TcConvDesc d = tc_base();
+        d.x16 = IN16; d.Lp_in = LpC; d.w16 = W16(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i));
+        d.Cin = Cc; d.KB = Cc < 64 ? Cc : 64; d.ntaps = g.ntaps; d.G = g.u;
+        for (int p = 0; p < g.u; ++p) d.g_off[p] = g.g_off[p];
+        d.N = Cn < 256 ? Cn : 256; d.Cout_total = Cn; d.tmem_cols = tmem_cols_for(d.N);
+        d.Lj = (int)Lc; d.out_stride = g.u; d.Lp_out = LpN; d.y32 = X32;
+        if (!ok) return RVCB200_ERR_MISSING;
+        CKC(0, launch_conv_tc(d, B, bf16, st), "dec.ups(tc)");
+      }
+      {
+        int nk, ns, np;
+        noise_geom(f, i, &nk, &ns, &np);
+        CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, B, Lout, Ln, Cn,
+                                   nk, ns, np, LpN, kPadF, 0.1f, bf16, st),
+            "dec.noise_add(pv)");
+      }
+      if (const rvcb200_tap* t = tp.find(S("dec.ups.%d", i).c_str()))
+        CK(launch_pv_to_cl(X32, false, bf16, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");
+      for (int j = 0; j < f.n_res_kernels; ++j) {
+        const int n = i * f.n_res_kernels + j;
+        const int k = f.res_kernels[j];
+        const void* src16 = X16;
+        const float* src32 = X32;
+        const int nd = f.n_res_dils[j];
+        for (int dd = 0; dd < nd; ++dd) {
+          const bool last = dd == nd - 1;
+          const int dil = f.res_dils[j][dd];
+          TcConvDesc o = tc_base();
+          o.Lp_in = LpN; o.Cin = Cn; o.KB = Cn < 64 ? Cn : 64; o.ntaps = k;
+          o.N = Cn < 256 ? Cn : 256; o.Cout_total = Cn; o.tmem_cols = tmem_cols_for(o.N);
+          o.Lj = (int)Ln; o.Lp_out = LpN;
+          if (f.resblock_kind == 1) {
+            TcConvDesc d = o;    // xt = c1(lrelu(x)); only lrelu(xt) is ever consumed -> 16-bit store only
+            d.x16 = src16; d.w16 = W16(S("dec.rb.%d.c1.%d.w", n, dd)); d.bias = W(S("dec.rb.%d.c1.%d.b", n, dd));
+            d.dil = dil; d.g_off[0] = -((k - 1) / 2) * dil;
+            d.y16 = XT16; d.out_slope = 0.1f;
+            if (!ok) return RVCB200_ERR_MISSING;
+            CKC(0, launch_conv_tc(d, B, bf16, st), "dec.rb.c1(tc)");
+            o.x16 = XT16; o.dil = 1; o.g_off[0] = -((k - 1) / 2);
+            o.w16 = W16(S("dec.rb.%d.c2.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c2.%d.b", n, dd));
+          } else {
+            o.x16 = src16; o.dil = dil; o.g_off[0] = -((k - 1) / 2) * dil;
+            o.w16 = W16(S("dec.rb.%d.c.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c.%d.b", n, dd));
+          }
+          o.res32 = src32;
+          if (last) {
+            const bool final_branch = j == f.n_res_kernels - 1;
+            o.y32 = ACC32; o.accum = j > 0; o.div = final_branch ? (float)f.n_res_kernels : 1.f;
+            if (final_branch && !last_stage) { o.y16 = N16; o.out_slope = 0.1f; }
+          } else {
+            o.y32 = XB32; o.y16 = XB16; o.out_slope = 0.1f;
+          }
+          if (!ok) return RVCB200_ERR_MISSING;
+          CKC(0, launch_conv_tc(o, B, bf16, st), "dec.rb.c2(tc)");
+          src16 = XB16; src32 = XB32;
+        }
+      }
+      if (const rvcb200_tap* t = tp.find(S("dec.stage.%d", i).c_str()))
+        CK(launch_pv_to_cl(ACC32, false, bf16, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");
+      void* tmp = IN16; IN16 = N16; N16 = tmp;
+      Lc = Ln; Cc = Cn; LpC = LpN;
+    }
+    CKC(3, launch_conv_post_pv(ACC32, W("dec.post.w"), out, B, Lc, Cc, 7, LpC, kPadF, 0.01f, st), "dec.conv_post(pv)");
+  }
   if (!ok) return RVCB200_ERR_MISSING;
   ctx->last_launches = launch_counter().n - launches0;
   return RVCB200_OK;
@@ -640,6 +794,12 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
 int rvcb200_op_conv_f32(const rvcb200_conv_desc* d, int32_t B, void* stream) {
   if (!d) return RVCB200_ERR_ARG;
   cudaError_t e = launch_conv_f32(*d, B, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, int32_t bf16, void* stream) {
+  if (!d) return RVCB200_ERR_ARG;
+  cudaError_t e = launch_conv_tc(*d, B, bf16 != 0, reinterpret_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 

@@ -24,7 +24,7 @@ from torch import nn
 
 from . import _lib
 from .config import SynthConfig
-from .weights import pack, validate_state_dict
+from .weights import pack, pack_tc, tc_weight_names, validate_state_dict
 
 
 class _IncompatibleKeys:
@@ -53,6 +53,7 @@ class SynthesizerB200(nn.Module):
         self._packed: Optional[Dict[str, torch.Tensor]] = None   # device tensors (kept alive for the ctx)
         self._ctx = None
         self._ws: Optional[torch.Tensor] = None
+        self._tc_done = set()
         self.last_launches = 0
 
     # ---- nn.Module protocol the reference callers use ------------------------------------------
@@ -101,6 +102,8 @@ class SynthesizerB200(nn.Module):
         if precision not in _lib.PREC:
             raise ValueError(precision)
         self.precision = precision
+        if self._ctx is not None:
+            self._ensure_tc()
         return self
 
     # ---- engine management ----------------------------------------------------------------------
@@ -157,6 +160,30 @@ class SynthesizerB200(nn.Module):
             for k, v in scalars.items():
                 _lib.check(lib.rvcb200_set_scalar(ctx, k.encode(), C.c_float(v)), ctx, k)
             _lib.check(lib.rvcb200_finalize(ctx), ctx, "finalize")
+        self._tc_done = set()
+        self._ensure_tc()
+
+    def _ensure_tc(self):
+        """Register the 16-bit tcgen05 weight images for the selected precision (fp16 / bf16)."""
+        if self.precision == "fp32" or self.precision in self._tc_done:
+            return
+        lib = _lib.load()
+        dtype = torch.float16 if self.precision == "fp16" else torch.bfloat16
+        code = _lib.PREC[self.precision]
+        with torch.cuda.device(self._device):
+            for name in tc_weight_names(self.cfg):
+                t = pack_tc(self._packed[name].cpu(), dtype).to(self._device)
+                key = f"{name}.tc"
+                if self.precision == "bf16":
+                    key_store = key + "#bf16"
+                else:
+                    key_store = key + "#fp16"
+                self._packed[key_store] = t
+                _lib.check(lib.rvcb200_set_tensor(self._ctx, key.encode(), C.c_void_p(t.data_ptr()), t.numel(), code),
+                           self._ctx, key)
+            _lib.check(lib.rvcb200_finalize(self._ctx), self._ctx, "finalize")
+        # the engine keeps one `.tc` image per name: switching precision re-registers
+        self._tc_done = {self.precision}
 
     def _workspace(self, B: int, T: int, prec: int) -> torch.Tensor:
         need = int(_lib.load().rvcb200_workspace_bytes(self._ctx, B, T, prec))

@@ -173,3 +173,38 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
                     P[f"dec.rb.{n}.c.{d}.b"] = w[f"dec.resblocks.{n}.convs.{d}.bias"].contiguous()
     P["dec.post.w"] = w["dec.conv_post.weight"][0].t().contiguous()           # [k][C]
     return P, S
+
+
+# ---- tensor-core path: 16-bit smem images of the decoder weights ------------------------------------
+TC_KB_MAX, TC_N_MAX = 64, 256
+
+
+def pack_tc(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[G][taps][C_in][C_out] (or [taps][C_in][C_out]) fp32 -> [G][C_out/N][taps][C_in/KB][KB/8][N][8] 16-bit.
+
+    One (tap, k-block) slice is the exact shared-memory image of the tcgen05 B operand in the
+    no-swizzle K-major canonical layout (csrc/conv_tc.cu): 8-channel groups outermost, then the N
+    output channels, then the 8 contiguous input channels (16 bytes)."""
+    if w.dim() == 3:
+        w = w.unsqueeze(0)
+    G, taps, cin, cout = w.shape
+    KB, N = min(TC_KB_MAX, cin), min(TC_N_MAX, cout)
+    assert cin % KB == 0 and KB % 16 == 0 and cout % N == 0 and N % 16 == 0, (cin, cout)
+    t = w.reshape(G, taps, cin // KB, KB // 8, 8, cout // N, N).permute(0, 5, 1, 2, 3, 6, 4)
+    return t.contiguous().to(dtype)
+
+
+def tc_weight_names(cfg: SynthConfig):
+    """Packed fp32 tensors that also get a 16-bit `.tc` image (the decoder's dense convolutions)."""
+    names = ["dec.pre.w"]
+    nk = cfg.num_kernels
+    for i in range(cfg.num_upsamples):
+        names.append(f"dec.ups.{i}.w")
+        for j in range(nk):
+            n = i * nk + j
+            for d in range(len(cfg.resblock_dilation_sizes[j])):
+                if cfg.resblock == "1":
+                    names += [f"dec.rb.{n}.c1.{d}.w", f"dec.rb.{n}.c2.{d}.w"]
+                else:
+                    names.append(f"dec.rb.{n}.c.{d}.w")
+    return names

@@ -155,6 +155,21 @@ typedef struct rvcb200_conv_desc {
 } rvcb200_conv_desc;
 int rvcb200_op_conv_f32(const rvcb200_conv_desc* d, int32_t B, void* stream);
 
+/* tcgen05/TMEM convolution on "planar-vector" (PV) activations: 16-bit [B][C/8][Lp][8] operands,
+ * fp32 [B][C/4][Lp][4] residual stream, Lp = roundup(L,128)+128 rows per plane, 32 zero rows in front
+ * (csrc/conv_tc.cu).  Weights are the packed smem image [G][C_out/N][taps][C_in/KB][KB/8][N][8]. */
+typedef struct rvcb200_tc_conv_desc {
+  const void* x16; int32_t Lp_in; int32_t padf;
+  const void* w16; const float* bias;
+  int32_t Cin, KB, ntaps, dil, G; int32_t g_off[16];
+  int32_t N, Cout_total, tmem_cols;
+  int32_t Lj, out_stride, Lp_out;
+  float* y32; void* y16; const float* res32;
+  const float* cond; int32_t cond_bstride;
+  int32_t accum; float div; float out_slope;
+} rvcb200_tc_conv_desc;
+int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, int32_t bf16, void* stream);
+
 /* NSF harmonic source (SineGen + SourceModuleHnNSF, models.py:361-411,455-467):
  * f0 [B][T] -> har [B][T*upp]; scratch >= rvcb200_op_sine_scratch_bytes(B,T,upp). */
 int64_t rvcb200_op_sine_scratch_bytes(int32_t B, int32_t T, int32_t upp);

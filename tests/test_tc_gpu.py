@@ -1,0 +1,120 @@
+"""GPU: the tcgen05/TMEM convolution (fp16 / bf16 operands, fp32 accumulate) against an fp64 CPU
+restatement on identically rounded operands, and the tensor-core decode path end to end
+(north_star gate: SNR >= 45 dB against the fp32 reference output)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from comfy_rvc_b200 import _lib, synthetic, weights
+from comfy_rvc_b200.config import NAMED_CONFIGS
+from tests._emulate import conv_cl
+from tests._util import load_golden
+
+pytestmark = pytest.mark.gpu
+PADF = 32
+
+
+def pitch(L):
+    return ((L + 127) // 128) * 128 + 128
+
+
+def to_pv(x, vec, dtype):
+    """[B][L][C] -> planar-vector [B][C/vec][Lp][vec] with zero pads."""
+    B, L, Cc = x.shape
+    out = torch.zeros(B, Cc // vec, pitch(L), vec, dtype=dtype)
+    out[:, :, PADF:PADF + L] = x.reshape(B, L, Cc // vec, vec).permute(0, 2, 1, 3).to(dtype)
+    return out
+
+
+def from_pv(t, L):
+    B, G, Lp, vec = t.shape
+    return t[:, :, PADF:PADF + L].permute(0, 2, 1, 3).reshape(B, L, G * vec)
+
+
+TC_CASES = [
+    # name, B, L, Cin, Cout, ntaps, dil, G
+    ("k1_c64", 1, 256, 64, 64, 1, 1, 1),
+    ("k3_d1_c32", 1, 1000, 32, 32, 3, 1, 1),
+    ("k7_d3_c64", 2, 700, 64, 64, 7, 3, 1),
+    ("k11_d5_c128", 1, 900, 128, 128, 11, 5, 1),
+    ("k11_d1_c256", 1, 300, 256, 256, 11, 1, 1),
+    ("k7_pre_192_512", 1, 200, 192, 512, 7, 1, 1),
+    ("ups12_512_256", 1, 60, 512, 256, 2, 1, 12),
+    ("ups2_64_32", 2, 333, 64, 32, 2, 1, 2),
+    ("k3_c16", 1, 500, 16, 16, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("bf16", [False, True], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tc(case, bf16):
+    name, B, L, Cin, Cout, ntaps, dil, G = case
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    dt = torch.bfloat16 if bf16 else torch.float16
+    g = torch.Generator().manual_seed(len(name) * 131 + Cin + Cout)
+    x = torch.randn(B, L, Cin, generator=g).to(dt).float()                    # operands exactly representable
+    w = (torch.randn(G, ntaps, Cin, Cout, generator=g) / math.sqrt(Cin * ntaps)).to(dt).float()
+    bias = torch.randn(Cout, generator=g)
+    res = torch.randn(B, L * G, Cout, generator=g)
+    if G == 1:
+        g_off = [-((ntaps - 1) // 2) * dil]
+    else:
+        g_off = [(p + G // 2) // G - (ntaps - 1) for p in range(G)]
+    Lo = L * G
+    ref = conv_cl(x.double(), w.double(), bias.double(), g_off=g_off, dil=dil, out_stride=G) + res.double()
+    x16 = to_pv(x, 8, dt).to(dev)
+    r32 = to_pv(res, 4, torch.float32).to(dev)
+    y32 = torch.zeros(B, Cout // 4, pitch(Lo), 4, device=dev)
+    y16 = torch.zeros(B, Cout // 8, pitch(Lo), 8, dtype=dt, device=dev)
+    w16 = weights.pack_tc(w, dt).to(dev)
+    bd = bias.to(dev)
+    d = _lib.TcConvDesc()
+    d.x16, d.Lp_in, d.padf = x16.data_ptr(), pitch(L), PADF
+    d.w16, d.bias = w16.data_ptr(), bd.data_ptr()
+    d.Cin, d.KB, d.ntaps, d.dil, d.G = Cin, min(64, Cin), ntaps, dil, G
+    for i, o in enumerate(g_off):
+        d.g_off[i] = o
+    d.N, d.Cout_total = min(256, Cout), Cout
+    d.tmem_cols = max(32, 1 << (d.N - 1).bit_length())
+    d.Lj, d.out_stride, d.Lp_out = L, G, pitch(Lo)
+    d.y32, d.y16, d.res32 = y32.data_ptr(), y16.data_ptr(), r32.data_ptr()
+    d.accum, d.div, d.out_slope = 0, 1.0, 0.1
+    st = lib.rvcb200_op_conv_tc(C.byref(d), B, int(bf16), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert st == 0, st
+    torch.cuda.synchronize()
+    got = from_pv(y32.cpu(), Lo).double()
+    err = (got - ref).abs().max().item()
+    print(f"conv_tc {name} {'bf16' if bf16 else 'fp16'}: max abs err {err:.3e} (|ref|max {ref.abs().max().item():.2f})")
+    assert err < 1e-3, "tcgen05 conv mismatch"
+    # pads must stay zero and the 16-bit copy is lrelu(out) rounded
+    assert float(y32[:, :, :PADF].abs().max()) == 0.0 and float(y32[:, :, PADF + Lo:].abs().max()) == 0.0
+    want16 = torch.where(ref > 0, ref, ref * 0.1)
+    err16 = (from_pv(y16.cpu().float(), Lo).double() - want16).abs().max().item()
+    assert err16 < (0.08 if bf16 else 0.02)
+
+
+@pytest.mark.parametrize("precision,min_snr", [("fp16", 45.0), ("bf16", 45.0)])
+@pytest.mark.parametrize("name", ["c2_48k_v2", "c1_40k_v1", "c3_32k_v2_ragged", "c5_48k_v1_5stage"])
+def test_infer_tensor_core_path_snr(name, precision, min_snr):
+    from tests.test_parity_gpu import build_net
+    cfg, sd, (phone, lens, pitch_, pitchf, sid), noise, gold = load_golden(name)
+    net = build_net(cfg, sd, precision)
+    taps = {f"dec.stage.{i}": None for i in range(cfg.num_upsamples)}
+    o = net.infer(phone.cuda(), lens.cuda(), pitch_.cuda(), pitchf.cuda(), sid.cuda(), noise=noise, taps=taps)[0]
+    torch.cuda.synchronize()
+    o_np = o[:, 0].cpu().numpy()
+    T = phone.shape[1]
+    worst = 1e9
+    for b in range(o_np.shape[0]):
+        n = int(lens[b]) * cfg.upp
+        if int(lens[b]) < T:
+            n -= 12 * cfg.upp
+        snr = synthetic.snr_db(gold["o_f32"][b, :n], o_np[b, :n])
+        print(f"  {name} {precision} item {b}: SNR {snr:.1f} dB vs reference fp32")
+        worst = min(worst, snr)
+    assert worst >= min_snr
