@@ -59,6 +59,7 @@ class TcConvDesc(C.Structure):
         ("y32", C.c_void_p), ("y16", C.c_void_p), ("res32", C.c_void_p),
         ("cond", C.c_void_p), ("cond_bstride", C.c_int32),
         ("accum", C.c_int32), ("div", C.c_float), ("out_slope", C.c_float),
+        ("in_bf16", C.c_int32), ("out_bf16", C.c_int32),
     ]
 
 
@@ -79,7 +80,7 @@ SYMBOLS = {
     "rvcb200_last_launch_count": (C.c_int64, [C.c_void_p]),
     "rvcb200_last_error": (C.c_char_p, [C.c_void_p]),
     "rvcb200_op_conv_f32": (C.c_int, [C.POINTER(ConvDesc), C.c_int32, C.c_void_p]),
-    "rvcb200_op_conv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_int32, C.c_void_p]),
+    "rvcb200_op_conv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_sine_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "rvcb200_op_sine_source": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

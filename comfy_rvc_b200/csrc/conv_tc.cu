@@ -87,9 +87,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <bool BF16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if (BF16) {
+__device__ __forceinline__ uint32_t pack2(bool bf16, float a, float b) {
+  if (bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
   } else {
@@ -98,7 +97,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   }
 }
 
-template <bool BF16>
 __global__ void __launch_bounds__(kThreadsTC) conv_tc_kernel(const TcConvDesc p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,7 +170,7 @@ __global__ void __launch_bounds__(kThreadsTC) conv_tc_kernel(const TcConvDesc p)
     // =========================== MMA issuer (single thread) =====================================
     if (lane == 0) {
       // instruction descriptor: D=F32, A/B = F16|BF16, K-major both, N>>3 @17, M>>4 @24
-      const uint32_t fmt = BF16 ? 1u : 0u;
+      const uint32_t fmt = p.in_bf16 ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t lbo_a = (uint32_t)R * 16, lbo_b = (uint32_t)p.N * 16;
       const int ksteps = p.KB / 16;
@@ -213,6 +211,7 @@ __global__ void __launch_bounds__(kThreadsTC) conv_tc_kernel(const TcConvDesc p)
     unsigned char* y16 = p.y16 ? reinterpret_cast<unsigned char*>(p.y16) + (size_t)b * (p.Cout_total / 8) * pitch_o : nullptr;
     const unsigned char* r32 = p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
     const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
+    const bool obf = p.out_bf16 != 0;
     for (int c0 = 0; c0 < p.N; c0 += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -252,10 +251,10 @@ __global__ void __launch_bounds__(kThreadsTC) conv_tc_kernel(const TcConvDesc p)
 #pragma unroll
         for (int k8 = 0; k8 < 2; ++k8) {
           uint4 o;
-          o.x = pack2<BF16>(lrelu(v[k8 * 8 + 0], p.out_slope), lrelu(v[k8 * 8 + 1], p.out_slope));
-          o.y = pack2<BF16>(lrelu(v[k8 * 8 + 2], p.out_slope), lrelu(v[k8 * 8 + 3], p.out_slope));
-          o.z = pack2<BF16>(lrelu(v[k8 * 8 + 4], p.out_slope), lrelu(v[k8 * 8 + 5], p.out_slope));
-          o.w = pack2<BF16>(lrelu(v[k8 * 8 + 6], p.out_slope), lrelu(v[k8 * 8 + 7], p.out_slope));
+          o.x = pack2(obf, lrelu(v[k8 * 8 + 0], p.out_slope), lrelu(v[k8 * 8 + 1], p.out_slope));
+          o.y = pack2(obf, lrelu(v[k8 * 8 + 2], p.out_slope), lrelu(v[k8 * 8 + 3], p.out_slope));
+          o.z = pack2(obf, lrelu(v[k8 * 8 + 4], p.out_slope), lrelu(v[k8 * 8 + 5], p.out_slope));
+          o.w = pack2(obf, lrelu(v[k8 * 8 + 6], p.out_slope), lrelu(v[k8 * 8 + 7], p.out_slope));
           *reinterpret_cast<uint4*>(y16 + (size_t)(co / 8 + k8) * pitch_o + (size_t)orow * 16) = o;
         }
       }
@@ -291,9 +290,8 @@ __global__ void zero_pads_kernel(unsigned char* base, long long planes, int Lp, 
   }
 }
 
-template <bool BF16>
 __global__ void cl_to_pv16_kernel(const float* __restrict__ x, int ldx, long long L, int C, unsigned char* __restrict__ y16,
-                                  int Lp, int padf, float slope) {
+                                  int Lp, int padf, float slope, bool BF16) {
   // x [B][L][ldx] channels-last fp32 -> PV16 [B][C/8][Lp][8]
   const int b = blockIdx.y;
   const int ng = C / 8;
@@ -304,18 +302,17 @@ __global__ void cl_to_pv16_kernel(const float* __restrict__ x, int ldx, long lon
     const float* src = x + ((long long)b * L + t) * ldx + gch * 8;
     const float4 a = *reinterpret_cast<const float4*>(src), c = *reinterpret_cast<const float4*>(src + 4);
     uint4 o;
-    o.x = pack2<BF16>(lrelu(a.x, slope), lrelu(a.y, slope));
-    o.y = pack2<BF16>(lrelu(a.z, slope), lrelu(a.w, slope));
-    o.z = pack2<BF16>(lrelu(c.x, slope), lrelu(c.y, slope));
-    o.w = pack2<BF16>(lrelu(c.z, slope), lrelu(c.w, slope));
+    o.x = pack2(BF16, lrelu(a.x, slope), lrelu(a.y, slope));
+    o.y = pack2(BF16, lrelu(a.z, slope), lrelu(a.w, slope));
+    o.z = pack2(BF16, lrelu(c.x, slope), lrelu(c.y, slope));
+    o.w = pack2(BF16, lrelu(c.z, slope), lrelu(c.w, slope));
     *reinterpret_cast<uint4*>(y16 + (((long long)b * ng + gch) * Lp + padf + t) * 16) = o;
   }
 }
 
-template <bool BF16>
 __global__ void noise_add_pv_kernel(const float* __restrict__ har, const float* __restrict__ wn, const float* __restrict__ nb,
                                     unsigned char* __restrict__ x32, unsigned char* __restrict__ x16, long long L_har,
-                                    long long L, int C, int k, int s, int pad, int Lp, int padf, float slope) {
+                                    long long L, int C, int k, int s, int pad, int Lp, int padf, float slope, bool BF16) {
   // x32 += noise_conv(har);  x16 = cvt(lrelu(x32))   (models.py:552-553 + the lrelu of modules.py:297)
   extern __shared__ float sw[];  // [k][C] + [C]
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
@@ -347,10 +344,10 @@ __global__ void noise_add_pv_kernel(const float* __restrict__ har, const float* 
     d.x += acc[4]; d.y += acc[5]; d.z += acc[6]; d.w += acc[7];
     *p0 = a; *p1 = d;
     uint4 o;
-    o.x = pack2<BF16>(lrelu(a.x, slope), lrelu(a.y, slope));
-    o.y = pack2<BF16>(lrelu(a.z, slope), lrelu(a.w, slope));
-    o.z = pack2<BF16>(lrelu(d.x, slope), lrelu(d.y, slope));
-    o.w = pack2<BF16>(lrelu(d.z, slope), lrelu(d.w, slope));
+    o.x = pack2(BF16, lrelu(a.x, slope), lrelu(a.y, slope));
+    o.y = pack2(BF16, lrelu(a.z, slope), lrelu(a.w, slope));
+    o.z = pack2(BF16, lrelu(d.x, slope), lrelu(d.y, slope));
+    o.w = pack2(BF16, lrelu(d.z, slope), lrelu(d.w, slope));
     *reinterpret_cast<uint4*>(x16 + (((long long)b * ng + gch) * Lp + padf + t) * 16) = o;
   }
 }
@@ -394,8 +391,8 @@ __global__ void pv32_to_cl_kernel(const unsigned char* __restrict__ x32, float* 
   }
 }
 
-template <bool BF16>
-__global__ void pv16_to_cl_kernel(const unsigned char* __restrict__ x16, float* __restrict__ y, long long L, int C, int Lp, int padf) {
+__global__ void pv16_to_cl_kernel(const unsigned char* __restrict__ x16, float* __restrict__ y, long long L, int C, int Lp, int padf,
+                                  bool BF16) {
   const int b = blockIdx.y;
   const int n8 = C / 8;
   const long long total = L * n8;
@@ -424,23 +421,20 @@ inline unsigned grid_for(long long total, int threads) {
 
 }  // namespace
 
-cudaError_t launch_conv_tc(const TcConvDesc& d, int B, bool bf16, cudaStream_t st) {
+cudaError_t launch_conv_tc(const TcConvDesc& d, int B, cudaStream_t st) {
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.KB % 16 != 0 || d.KB > 64 || d.Cin % d.KB != 0 || d.Cout_total % d.N != 0 ||
       d.G < 1 || d.G > 16 || d.Lj <= 0 || (d.ntaps - 1) * d.dil > 56 || d.tmem_cols < d.N || (d.accum && !d.y32))
     return cudaErrorInvalidValue;
   const size_t smem = tc_smem_bytes(d);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static size_t cfg_h = 0, cfg_b = 0;
-  size_t& cfgd = bf16 ? cfg_b : cfg_h;
+  static size_t cfgd = 0;
   if (smem > cfgd) {
-    cudaError_t e = bf16 ? cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cfgd = smem;
   }
   dim3 grid((d.Lj + BM - 1) / BM, d.Cout_total / d.N, B * d.G);
-  if (bf16) conv_tc_kernel<true><<<grid, kThreadsTC, smem, st>>>(d);
-  else conv_tc_kernel<false><<<grid, kThreadsTC, smem, st>>>(d);
+  conv_tc_kernel<<<grid, kThreadsTC, smem, st>>>(d);
   launch_counter().n++;
   return cudaGetLastError();
 }
@@ -455,8 +449,7 @@ cudaError_t launch_zero_pads(void* base, long long planes, int Lp, int padf, lon
 cudaError_t launch_cl_to_pv16(const float* x, int ldx, int B, long long L, int C, void* y16, int Lp, int padf, float slope,
                               bool bf16, cudaStream_t st) {
   dim3 grid(grid_for(L * (C / 8), 256), B);
-  if (bf16) cl_to_pv16_kernel<true><<<grid, 256, 0, st>>>(x, ldx, L, C, reinterpret_cast<unsigned char*>(y16), Lp, padf, slope);
-  else cl_to_pv16_kernel<false><<<grid, 256, 0, st>>>(x, ldx, L, C, reinterpret_cast<unsigned char*>(y16), Lp, padf, slope);
+  cl_to_pv16_kernel<<<grid, 256, 0, st>>>(x, ldx, L, C, reinterpret_cast<unsigned char*>(y16), Lp, padf, slope, bf16);
   launch_counter().n++;
   return cudaGetLastError();
 }
@@ -467,18 +460,13 @@ cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* 
   const size_t smem = sizeof(float) * ((size_t)k * C + C);
   static size_t cfg = 48 * 1024;
   if (smem > cfg) {
-    cudaError_t e = cudaFuncSetAttribute(noise_add_pv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(noise_add_pv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(noise_add_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cfg = smem;
   }
   dim3 grid(grid_for(L * (C / 8), 256), B);
-  if (bf16)
-    noise_add_pv_kernel<true><<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32),
-                                                       reinterpret_cast<unsigned char*>(x16), L_har, L, C, k, s, pad, Lp, padf, slope);
-  else
-    noise_add_pv_kernel<false><<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32),
-                                                        reinterpret_cast<unsigned char*>(x16), L_har, L, C, k, s, pad, Lp, padf, slope);
+  noise_add_pv_kernel<<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32),
+                                               reinterpret_cast<unsigned char*>(x16), L_har, L, C, k, s, pad, Lp, padf, slope, bf16);
   launch_counter().n++;
   return cudaGetLastError();
 }
@@ -499,8 +487,7 @@ cudaError_t launch_pv_to_cl(const void* src, bool is16, bool bf16, float* y, int
     pv32_to_cl_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), y, L, C, Lp, padf);
   } else {
     dim3 grid(grid_for(L * (C / 8), 256), B);
-    if (bf16) pv16_to_cl_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), y, L, C, Lp, padf);
-    else pv16_to_cl_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), y, L, C, Lp, padf);
+    pv16_to_cl_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), y, L, C, Lp, padf, bf16);
   }
   launch_counter().n++;
   return cudaGetLastError();

@@ -11,7 +11,7 @@ typedef rvcb200_tc_conv_desc TcConvDesc;
 constexpr int kPadF = 32;                                   // zero rows in front of every PV plane
 inline int pv_pitch_rows(long long L) { return (int)(((L + 127) / 128) * 128 + 128); }   // Lp
 
-cudaError_t launch_conv_tc(const TcConvDesc& d, int B, bool bf16, cudaStream_t st);
+cudaError_t launch_conv_tc(const TcConvDesc& d, int B, cudaStream_t st);
 cudaError_t launch_zero_pads(void* base, long long planes, int Lp, int padf, long long L, cudaStream_t st);
 cudaError_t launch_cl_to_pv16(const float* x, int ldx, int B, long long L, int C, void* y16, int Lp, int padf, float slope,
                               bool bf16, cudaStream_t st);

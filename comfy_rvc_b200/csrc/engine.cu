@@ -469,7 +469,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     d.Lj = T; d.y = pl.x; d.y_bstride = (long long)T * H; d.ldy = H;
     d.gather = W("enc.emb_pitch"); d.gidx = pitch; d.gidx_bstride = T;
     d.alpha = sqrtf((float)H); d.out_slope = 0.1f; d.mask_post = 1; d.out_len = pl.len32;
-    CKC(0, launch_conv_f32(d, B, st), "enc.emb");
+    CKC(6, launch_conv_f32(d, B, st), "enc.emb");
   }
   const int kp = (f.enc_kernel - 1) / 2;
   for (int l = 0; l < f.n_layers; ++l) {
@@ -478,7 +478,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       d.x = pl.x; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T;
       d.w = W(S("enc.%d.qkv.w", l)); d.bias = W(S("enc.%d.qkv.b", l)); d.Cin = H; d.Cout = 3 * H;
       d.Lj = T; d.y = pl.qkv; d.y_bstride = (long long)T * 3 * H; d.ldy = 3 * H;
-      CKC(0, launch_conv_f32(d, B, st), "enc.qkv");
+      CKC(6, launch_conv_f32(d, B, st), "enc.qkv");
     }
     CKC(1, launch_attention_f32(pl.qkv, W(S("enc.%d.rel_k", l)), W(S("enc.%d.rel_v", l)), pl.len32, pl.att, B, T,
                             f.n_heads, H / f.n_heads, f.window_size, st),
@@ -489,7 +489,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       d.w = W(S("enc.%d.o.w", l)); d.bias = W(S("enc.%d.o.b", l)); d.Cin = H; d.Cout = H;
       d.Lj = T; d.y = pl.xt; d.y_bstride = (long long)T * H; d.ldy = H;
       d.res = pl.x; d.res_bstride = (long long)T * H; d.ldr = H; d.res_mode = 1;
-      CKC(0, launch_conv_f32(d, B, st), "enc.o");
+      CKC(6, launch_conv_f32(d, B, st), "enc.o");
     }
     CKC(3, launch_layernorm(pl.xt, W(S("enc.%d.ln1.g", l)), W(S("enc.%d.ln1.b", l)), pl.x, BT, H, 1e-5f, st), "enc.ln1");
     {  // FFN conv_1 + ReLU   attentions.py:388-392
@@ -498,7 +498,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       d.w = W(S("enc.%d.ffn1.w", l)); d.bias = W(S("enc.%d.ffn1.b", l)); d.Cin = H; d.Cout = F;
       d.ntaps = f.enc_kernel; d.g_off[0] = -kp;
       d.Lj = T; d.y = pl.ffh; d.y_bstride = (long long)T * F; d.ldy = F; d.relu = 1;
-      CKC(0, launch_conv_f32(d, B, st), "enc.ffn1");
+      CKC(6, launch_conv_f32(d, B, st), "enc.ffn1");
     }
     {  // x + conv_2(h*mask)*mask   attentions.py:394-395,67
       ConvDesc d = base_desc();
@@ -508,7 +508,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       d.Lj = T; d.y = pl.xt; d.y_bstride = (long long)T * H; d.ldy = H;
       d.mask_pre = 1; d.out_len = pl.len32;
       d.res = pl.x; d.res_bstride = (long long)T * H; d.ldr = H; d.res_mode = 1;
-      CKC(0, launch_conv_f32(d, B, st), "enc.ffn2");
+      CKC(6, launch_conv_f32(d, B, st), "enc.ffn2");
     }
     CKC(3, launch_layernorm(pl.xt, W(S("enc.%d.ln2.g", l)), W(S("enc.%d.ln2.b", l)), pl.x, BT, H, 1e-5f, st), "enc.ln2");
   }
@@ -519,7 +519,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     d.w = W("enc.proj.w"); d.bias = W("enc.proj.b"); d.Cin = H; d.Cout = 2 * C;
     d.Lj = T; d.y = stats; d.y_bstride = (long long)T * 2 * C; d.ldy = 2 * C;
     d.mask_post = 1; d.out_len = pl.len32;
-    CKC(0, launch_conv_f32(d, B, st), "enc.proj");
+    CKC(6, launch_conv_f32(d, B, st), "enc.proj");
   }
   CK(tp.emit("stats", stats, sizeof(float) * BT * 2 * C), "tap");
   CKC(3, launch_zp_sample(stats, noise_zp, pl.len32, zp, B, T, C, st), "zp_sample");
@@ -537,7 +537,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
         d.x = z + in_off; d.x_bstride = (long long)T * C; d.ldx = C; d.L_in = T;
         d.w = W(S("flow.%d.pre.w", i)); d.bias = W(S("flow.%d.pre.b", i)); d.Cin = half; d.Cout = H;
         d.Lj = T; d.y = pl.h; d.y_bstride = (long long)T * H; d.ldy = H; d.mask_post = 1; d.out_len = pl.len32;
-        CKC(0, launch_conv_f32(d, B, st), "flow.pre");
+        CKC(5, launch_conv_f32(d, B, st), "flow.pre");
       }
       for (int j = 0; j < f.flow_wn_layers; ++j) {
         {  // acts = tanh/sigmoid gate of in_layer(h) + cond   modules.py:192-199
@@ -548,7 +548,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
           d.cond = pl.cond + f.up_init_channels + (i * f.flow_wn_layers + j) * 2 * H; d.cond_bstride = ctx->n_cond;
           d.gate = 1;
           d.Lj = T; d.y = pl.acts; d.y_bstride = (long long)T * H; d.ldy = H;
-          CKC(0, launch_conv_f32(d, B, st), "flow.in");
+          CKC(5, launch_conv_f32(d, B, st), "flow.in");
         }
         if (j < f.flow_wn_layers - 1) {  // h = (h + res)*mask   modules.py:203-206
           ConvDesc d = base_desc();
@@ -557,14 +557,14 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
           d.Lj = T; d.y = pl.h; d.y_bstride = (long long)T * H; d.ldy = H;
           d.res = pl.h; d.res_bstride = (long long)T * H; d.ldr = H; d.res_mode = 1;
           d.mask_post = 1; d.out_len = pl.len32;
-          CKC(0, launch_conv_f32(d, B, st), "flow.res");
+          CKC(5, launch_conv_f32(d, B, st), "flow.res");
         }
         {  // output += skip   modules.py:207-208
           ConvDesc d = base_desc();
           d.x = pl.acts; d.x_bstride = (long long)T * H; d.ldx = H; d.L_in = T;
           d.w = W(S("flow.%d.rs.%d.skip.w", i, j)); d.bias = W(S("flow.%d.rs.%d.skip.b", i, j)); d.Cin = H; d.Cout = H;
           d.Lj = T; d.y = pl.skip; d.y_bstride = (long long)T * H; d.ldy = H; d.accum = j > 0;
-          CKC(0, launch_conv_f32(d, B, st), "flow.skip");
+          CKC(5, launch_conv_f32(d, B, st), "flow.skip");
         }
       }
       {  // x1 = (x1 - post(out*mask)*mask)*mask   modules.py:441,453
@@ -574,7 +574,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
         d.Lj = T; d.y = z + out_off; d.y_bstride = (long long)T * C; d.ldy = C;
         d.mask_pre = 1; d.mask_post = 1; d.out_len = pl.len32;
         d.res = z + out_off; d.res_bstride = (long long)T * C; d.ldr = C; d.res_mode = 2;
-        CKC(0, launch_conv_f32(d, B, st), "flow.post");
+        CKC(5, launch_conv_f32(d, B, st), "flow.post");
       }
     }
   }
@@ -596,7 +596,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     d.ntaps = 7; d.g_off[0] = -3;
     d.cond = pl.cond; d.cond_bstride = ctx->n_cond;
     d.Lj = T; d.y = pl.pre; d.y_bstride = (long long)T * f.up_init_channels; d.ldy = f.up_init_channels;
-    CKC(0, launch_conv_f32(d, B, st), "dec.conv_pre");
+    CKC(4, launch_conv_f32(d, B, st), "dec.conv_pre");
   }
   CK(tp.emit("dec.pre", pl.pre, sizeof(float) * BT * f.up_init_channels), "tap");
   const float* cur = pl.pre;
@@ -618,7 +618,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       for (int p = 0; p < g.u; ++p) d.g_off[p] = g.g_off[p];
       d.Lj = (int)Lc; d.out_stride = g.u;
       d.y = X; d.y_bstride = Ln * g.cout; d.ldy = g.cout;
-      CKC(0, launch_conv_f32(d, B, st), "dec.ups");
+      CKC(4, launch_conv_f32(d, B, st), "dec.ups");
     }
     {
       int nk, ns, np;
@@ -673,8 +673,12 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
 
   } else {
     // ------------- GeneratorNSF on tcgen05 (fp16/bf16 operands, fp32 accumulate + residual stream) -----------
+    // Operand formats: resblock convolutions follow `precision`; the ladder on the main signal path
+    // (conv_pre, ups) always runs on fp16 operands -- bf16 there costs ~9 dB of output SNR.
     const int dt = bf16 ? 2 : 1;
     auto W16 = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, dt, &ok); };
+    auto W16h = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, 1, &ok); };
+    const int rb_bf16 = bf16 ? 1 : 0;
     auto tmem_cols_for = [](int N) { int c = 32; while (c < N) c <<= 1; return c; };
     auto tc_base = [&]() {
       TcConvDesc d;
@@ -685,7 +689,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     const int LpT = pv_pitch_rows(T);
     // z -> PV16 (conv_pre consumes z*mask; z is already masked)
     CKC(3, launch_zero_pads(pl.z16, (long long)B * (C / 8), LpT, kPadF, T, st), "zero_pads");
-    CKC(3, launch_cl_to_pv16(z, C, B, T, C, pl.z16, LpT, kPadF, 1.f, bf16, st), "z->pv16");
+    CKC(3, launch_cl_to_pv16(z, C, B, T, C, pl.z16, LpT, kPadF, 1.f, false, st), "z->pv16");
     void* IN16 = pl.pv16[0];
     void* X16 = pl.pv16[1];
     void* XT16 = pl.pv16[2];
@@ -698,13 +702,14 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       const int U0 = f.up_init_channels;
       CKC(3, launch_zero_pads(IN16, (long long)B * (U0 / 8), LpT, kPadF, T, st), "zero_pads");
       TcConvDesc d = tc_base();
-      d.x16 = pl.z16; d.Lp_in = LpT; d.w16 = W16("dec.pre.w"); d.bias = W("dec.pre.b");
+      d.x16 = pl.z16; d.Lp_in = LpT; d.w16 = W16h("dec.pre.w"); d.bias = W("dec.pre.b");
       d.Cin = C; d.KB = C < 64 ? C : 64; d.ntaps = 7; d.g_off[0] = -3;
       d.N = U0 < 256 ? U0 : 256; d.Cout_total = U0; d.tmem_cols = tmem_cols_for(d.N);
       d.Lj = T; d.Lp_out = LpT; d.y16 = IN16; d.out_slope = 0.1f;      // lrelu of models.py:550 folded into the store
       d.cond = pl.cond; d.cond_bstride = ctx->n_cond;
       if (!ok) return RVCB200_ERR_MISSING;
-      CKC(0, launch_conv_tc(d, B, bf16, st), "dec.conv_pre(tc)");
+      d.in_bf16 = 0; d.out_bf16 = 0;
+      CKC(4, launch_conv_tc(d, B, st), "dec.conv_pre(tc)");
     }
     long long Lc = T;
     int Cc = f.up_init_channels;
@@ -722,13 +727,14 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       else CKC(3, launch_zero_pads(ACC32, (long long)B * (Cn / 4), LpN, kPadF, Ln, st), "zero_pads");
       {  // x = ups[i](lrelu(x)) as g.u phase groups (input already holds lrelu(x) in 16 bit)
         TcConvDesc d = tc_base();
-        d.x16 = IN16; d.Lp_in = LpC; d.w16 = W16(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i));
+        d.x16 = IN16; d.Lp_in = LpC; d.w16 = W16h(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i));
         d.Cin = Cc; d.KB = Cc < 64 ? Cc : 64; d.ntaps = g.ntaps; d.G = g.u;
         for (int p = 0; p < g.u; ++p) d.g_off[p] = g.g_off[p];
         d.N = Cn < 256 ? Cn : 256; d.Cout_total = Cn; d.tmem_cols = tmem_cols_for(d.N);
         d.Lj = (int)Lc; d.out_stride = g.u; d.Lp_out = LpN; d.y32 = X32;
         if (!ok) return RVCB200_ERR_MISSING;
-        CKC(0, launch_conv_tc(d, B, bf16, st), "dec.ups(tc)");
+        d.in_bf16 = 0; d.out_bf16 = 0;
+        CKC(4, launch_conv_tc(d, B, st), "dec.ups(tc)");
       }
       {
         int nk, ns, np;
@@ -758,7 +764,8 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
             d.dil = dil; d.g_off[0] = -((k - 1) / 2) * dil;
             d.y16 = XT16; d.out_slope = 0.1f;
             if (!ok) return RVCB200_ERR_MISSING;
-            CKC(0, launch_conv_tc(d, B, bf16, st), "dec.rb.c1(tc)");
+            d.in_bf16 = rb_bf16; d.out_bf16 = rb_bf16;
+            CKC(0, launch_conv_tc(d, B, st), "dec.rb.c1(tc)");
             o.x16 = XT16; o.dil = 1; o.g_off[0] = -((k - 1) / 2);
             o.w16 = W16(S("dec.rb.%d.c2.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c2.%d.b", n, dd));
           } else {
@@ -769,12 +776,14 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
           if (last) {
             const bool final_branch = j == f.n_res_kernels - 1;
             o.y32 = ACC32; o.accum = j > 0; o.div = final_branch ? (float)f.n_res_kernels : 1.f;
+            o.in_bf16 = rb_bf16; o.out_bf16 = 0;       // the next ups consumes fp16
             if (final_branch && !last_stage) { o.y16 = N16; o.out_slope = 0.1f; }
           } else {
+            o.in_bf16 = rb_bf16; o.out_bf16 = rb_bf16;
             o.y32 = XB32; o.y16 = XB16; o.out_slope = 0.1f;
           }
           if (!ok) return RVCB200_ERR_MISSING;
-          CKC(0, launch_conv_tc(o, B, bf16, st), "dec.rb.c2(tc)");
+          CKC(0, launch_conv_tc(o, B, st), "dec.rb.c2(tc)");
           src16 = XB16; src32 = XB32;
         }
       }
@@ -797,9 +806,9 @@ int rvcb200_op_conv_f32(const rvcb200_conv_desc* d, int32_t B, void* stream) {
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 
-int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, int32_t bf16, void* stream) {
+int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream) {
   if (!d) return RVCB200_ERR_ARG;
-  cudaError_t e = launch_conv_tc(*d, B, bf16 != 0, reinterpret_cast<cudaStream_t>(stream));
+  cudaError_t e = launch_conv_tc(*d, B, reinterpret_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 

@@ -122,11 +122,12 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T,
                   const rvcb200_tap* taps, int32_t n_taps, void* stream);
 
 /* Per-class device timing of the launches inside rvcb200_infer (CUDA events on the caller's stream,
- * accumulated until the next enable): class 0 = dense contractions (conv / 1x1 / transposed conv),
- * 1 = attention, 2 = NSF sine source, 3 = bandwidth-bound glue (LayerNorm, prior sample, source
- * injection, conv_post).  `collect` synchronises on the recorded events; ms/count have
+ * accumulated until the next enable): class 0 = decoder resblock convolutions, 1 = attention,
+ * 2 = NSF sine source, 3 = bandwidth-bound glue (LayerNorm, prior sample, source injection, conv_post,
+ * layout conversion), 4 = decoder conv_pre + transposed-conv ladder, 5 = flow contractions,
+ * 6 = text-encoder contractions (emb, qkv, o, FFN, proj), 7 = unused.  `collect` synchronises on the recorded events; ms/count have
  * RVCB200_PROF_CLASSES entries. */
-#define RVCB200_PROF_CLASSES 4
+#define RVCB200_PROF_CLASSES 8
 int rvcb200_profile_enable(rvcb200_ctx* ctx, int32_t on);
 int rvcb200_profile_collect(rvcb200_ctx* ctx, double* ms, int64_t* count);
 
@@ -167,8 +168,9 @@ typedef struct rvcb200_tc_conv_desc {
   float* y32; void* y16; const float* res32;
   const float* cond; int32_t cond_bstride;
   int32_t accum; float div; float out_slope;
+  int32_t in_bf16, out_bf16;   /* operand format of x16/w16 and storage format of y16: 0 = fp16, 1 = bf16 */
 } rvcb200_tc_conv_desc;
-int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, int32_t bf16, void* stream);
+int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 
 /* NSF harmonic source (SineGen + SourceModuleHnNSF, models.py:361-411,455-467):
  * f0 [B][T] -> har [B][T*upp]; scratch >= rvcb200_op_sine_scratch_bytes(B,T,upp). */

@@ -84,7 +84,8 @@ def test_conv_tc(case, bf16):
     d.Lj, d.out_stride, d.Lp_out = L, G, pitch(Lo)
     d.y32, d.y16, d.res32 = y32.data_ptr(), y16.data_ptr(), r32.data_ptr()
     d.accum, d.div, d.out_slope = 0, 1.0, 0.1
-    st = lib.rvcb200_op_conv_tc(C.byref(d), B, int(bf16), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    d.in_bf16 = d.out_bf16 = int(bf16)
+    st = lib.rvcb200_op_conv_tc(C.byref(d), B, C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert st == 0, st
     torch.cuda.synchronize()
     got = from_pv(y32.cpu(), Lo).double()
