@@ -28,10 +28,9 @@
 namespace rvc {
 namespace {
 
-constexpr int kThreadsTC = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreadsTC = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
 constexpr int BM = 128;
-constexpr int NB_STAGES = 4;     // weight ring depth
-constexpr int NA_STAGES = 3;     // activation slab ring depth (prefetch distance 2 k-blocks)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -75,18 +74,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 __device__ __forceinline__ uint32_t pack2(bool bf16, float a, float b) {
   if (bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -97,38 +84,127 @@ __device__ __forceinline__ uint32_t pack2(bool bf16, float a, float b) {
   }
 }
 
-__global__ void __launch_bounds__(kThreadsTC) conv_tc_kernel(const TcConvDesc p) {
+// One epilogue pass over CH accumulator columns of this thread's row: TMEM -> regs, + bias/cond/residual,
+// accumulate, /div, fp32 store, lrelu + 16-bit store.  All loads of the chunk are issued before any use.
+template <int CH>
+__device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t taddr, bool row_ok, int co, size_t pitch_o,
+                                               size_t orow16, unsigned char* y32, unsigned char* y16,
+                                               const unsigned char* r32, const float* cond) {
+  uint32_t r[CH];
+  if (CH == 32) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+        "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16 % CH]),
+          "=r"(r[17 % CH]), "=r"(r[18 % CH]), "=r"(r[19 % CH]), "=r"(r[20 % CH]), "=r"(r[21 % CH]), "=r"(r[22 % CH]),
+          "=r"(r[23 % CH]), "=r"(r[24 % CH]), "=r"(r[25 % CH]), "=r"(r[26 % CH]), "=r"(r[27 % CH]), "=r"(r[28 % CH]),
+          "=r"(r[29 % CH]), "=r"(r[30 % CH]), "=r"(r[31 % CH])
+        : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  }
+  // residual / accumulator loads overlap the TMEM read
+  float4 rr[CH / 4], aa[CH / 4];
+  if (row_ok) {
+    if (r32) {
+#pragma unroll
+      for (int k4 = 0; k4 < CH / 4; ++k4)
+        rr[k4] = *reinterpret_cast<const float4*>(r32 + (size_t)(co / 4 + k4) * pitch_o + orow16);
+    }
+    if (p.accum) {
+#pragma unroll
+      for (int k4 = 0; k4 < CH / 4; ++k4)
+        aa[k4] = *reinterpret_cast<const float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + orow16);
+    }
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (!row_ok) return;
+  float v[CH];
+#pragma unroll
+  for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]) + __ldg(p.bias + co + i);
+  if (cond) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] += __ldg(cond + co + i);
+  }
+  if (r32) {
+#pragma unroll
+    for (int k4 = 0; k4 < CH / 4; ++k4) {
+      v[k4 * 4 + 0] += rr[k4].x; v[k4 * 4 + 1] += rr[k4].y; v[k4 * 4 + 2] += rr[k4].z; v[k4 * 4 + 3] += rr[k4].w;
+    }
+  }
+  if (p.accum) {
+#pragma unroll
+    for (int k4 = 0; k4 < CH / 4; ++k4) {
+      v[k4 * 4 + 0] += aa[k4].x; v[k4 * 4 + 1] += aa[k4].y; v[k4 * 4 + 2] += aa[k4].z; v[k4 * 4 + 3] += aa[k4].w;
+    }
+  }
+  if (p.div != 1.f) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = v[i] / p.div;
+  }
+  if (y32) {
+#pragma unroll
+    for (int k4 = 0; k4 < CH / 4; ++k4)
+      *reinterpret_cast<float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + orow16) =
+          make_float4(v[k4 * 4 + 0], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+  }
+  if (y16) {
+    const bool obf = p.out_bf16 != 0;
+#pragma unroll
+    for (int k8 = 0; k8 < CH / 8; ++k8) {
+      uint4 o;
+      o.x = pack2(obf, lrelu(v[k8 * 8 + 0], p.out_slope), lrelu(v[k8 * 8 + 1], p.out_slope));
+      o.y = pack2(obf, lrelu(v[k8 * 8 + 2], p.out_slope), lrelu(v[k8 * 8 + 3], p.out_slope));
+      o.z = pack2(obf, lrelu(v[k8 * 8 + 4], p.out_slope), lrelu(v[k8 * 8 + 5], p.out_slope));
+      o.w = pack2(obf, lrelu(v[k8 * 8 + 6], p.out_slope), lrelu(v[k8 * 8 + 7], p.out_slope));
+      *reinterpret_cast<uint4*>(y16 + (size_t)(co / 8 + k8) * pitch_o + orow16) = o;
+    }
+  }
+}
+
+// Persistent, warp-specialised: each CTA walks tiles t = blockIdx.x, +gridDim.x, ...; the accumulator is
+// double-buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+__global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_kernel(const TcConvDesc p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z / p.G, g = blockIdx.z % p.G;
-  const int j0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * p.N;                 // first output channel of this n-tile
   const int halo = (p.ntaps - 1) * p.dil;
   const int R = (BM + halo + 7) & ~7;              // slab rows
   const int ngrp = p.KB / 8;                       // 16-byte channel groups per k-block
   const int nkb = p.Cin / p.KB;
   const uint32_t a_bytes = (uint32_t)ngrp * R * 16;
   const uint32_t b_bytes = (uint32_t)p.N * p.KB * 2;
-
-  unsigned char* slabA = smem;                                        // [NA_STAGES][ngrp][R][16]
-  unsigned char* slabB = smem + NA_STAGES * ((a_bytes + 127) & ~127u);  // [NB_STAGES][ngrp][N][16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slabB + (size_t)NB_STAGES * ((b_bytes + 127) & ~127u));
-  uint64_t* a_full = bars;                         // [NA_STAGES]
-  uint64_t* a_empty = bars + NA_STAGES;            // [NA_STAGES]
-  uint64_t* b_full = bars + 2 * NA_STAGES;         // [NB_STAGES]
-  uint64_t* b_empty = bars + 2 * NA_STAGES + NB_STAGES;
-  uint64_t* acc_full = bars + 2 * NA_STAGES + 2 * NB_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NA_STAGES + 2 * NB_STAGES + 1);
+  const int NA = p.na_stages, NB = p.nb_stages;
   const uint32_t a_stride = (a_bytes + 127) & ~127u, b_stride = (b_bytes + 127) & ~127u;
 
+  unsigned char* slabA = smem;                              // [NA][ngrp][R][16]
+  unsigned char* slabB = smem + (size_t)NA * a_stride;      // [NB][ngrp][N][16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabB + (size_t)NB * b_stride);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + NA;
+  uint64_t* b_full = a_empty + NA;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* acc_full = b_empty + NB;     // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int n_mt = (p.Lj + BM - 1) / BM;
+  const int n_nt = p.Cout_total / p.N;
+  const long long total_tiles = (long long)n_mt * n_nt * p.G * p.batch;
+  const int my_tiles = (int)((total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NA_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < NB_STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM allocation (power of two >= 32 columns), address lands in smem
+  if (warp == 1) {  // TMEM: two accumulator buffers of N columns (power of two >= 32 in total)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)p.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -138,126 +214,121 @@ __global__ void __launch_bounds__(kThreadsTC) conv_tc_kernel(const TcConvDesc p)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  auto decode = [&](long long t, int& mt, int& nt, int& g, int& b) {
+    mt = (int)(t % n_mt); t /= n_mt;
+    nt = (int)(t % n_nt); t /= n_nt;
+    g = (int)(t % p.G);
+    b = (int)(t / p.G);
+  };
+
   if (warp == 0) {
     // =========================== producer: bulk copies global -> smem ===========================
     if (lane == 0) {
-      const unsigned char* xa = reinterpret_cast<const unsigned char*>(p.x16) +
-                                ((size_t)b * (p.Cin / 8)) * p.Lp_in * 16 + (size_t)(j0 + p.g_off[g] + p.padf) * 16;
-      const unsigned char* wb = reinterpret_cast<const unsigned char*>(p.w16) +
-                                ((size_t)(g * gridDim.y + blockIdx.y) * p.ntaps * nkb) * b_bytes;
-      auto issue_a = [&](int kb) {   // stage rows [j0+g_off, +R) of the 8-channel groups of k-block kb
-        const int sa = kb % NA_STAGES;
-        mbar_wait(&a_empty[sa], ((kb / NA_STAGES) & 1) ^ 1);
+      const int Q = my_tiles * nkb;                   // flattened (tile, k-block) sequence
+      auto issue_a = [&](int q) {
+        int mt, nt, g, b;
+        decode((long long)blockIdx.x + (long long)(q / nkb) * gridDim.x, mt, nt, g, b);
+        const int kb = q % nkb;
+        const unsigned char* xa = reinterpret_cast<const unsigned char*>(p.x16) +
+                                  ((size_t)b * (p.Cin / 8)) * p.Lp_in * 16 + (size_t)(mt * BM + p.g_off[g] + p.padf) * 16;
+        const int sa = q % NA;
+        mbar_wait(&a_empty[sa], ((q / NA) & 1) ^ 1);
         mbar_expect_tx(&a_full[sa], a_bytes);
         for (int c = 0; c < ngrp; ++c)
           bulk_g2s(slabA + sa * a_stride + (size_t)c * R * 16, xa + (size_t)(kb * ngrp + c) * p.Lp_in * 16, R * 16,
                    &a_full[sa]);
       };
-      issue_a(0);
-      if (nkb > 1) issue_a(1);
+      const int ahead = NA - 1;                       // slabs issued ahead of the one being consumed
+      for (int q = 0; q < ahead && q < Q; ++q) issue_a(q);
       int itb = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int q = 0; q < Q; ++q) {
+        int mt, nt, g, b;
+        decode((long long)blockIdx.x + (long long)(q / nkb) * gridDim.x, mt, nt, g, b);
+        const int kb = q % nkb;
+        const unsigned char* wb = reinterpret_cast<const unsigned char*>(p.w16) +
+                                  ((size_t)(g * n_nt + nt) * p.ntaps * nkb) * b_bytes;
         for (int tap = 0; tap < p.ntaps; ++tap, ++itb) {
-          const int sb = itb % NB_STAGES;
-          mbar_wait(&b_empty[sb], ((itb / NB_STAGES) & 1) ^ 1);
+          const int sb = itb % NB;
+          mbar_wait(&b_empty[sb], ((itb / NB) & 1) ^ 1);
           mbar_expect_tx(&b_full[sb], b_bytes);
           bulk_g2s(slabB + sb * b_stride, wb + ((size_t)tap * nkb + kb) * b_bytes, b_bytes, &b_full[sb]);
         }
-        if (kb + 2 < nkb) issue_a(kb + 2);
+        if (q + ahead < Q) issue_a(q + ahead);
       }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (single thread) =====================================
     if (lane == 0) {
-      // instruction descriptor: D=F32, A/B = F16|BF16, K-major both, N>>3 @17, M>>4 @24
       const uint32_t fmt = p.in_bf16 ? 1u : 0u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t lbo_a = (uint32_t)R * 16, lbo_b = (uint32_t)p.N * 16;
       const int ksteps = p.KB / 16;
-      int itb = 0;
-      uint32_t accum = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int sa = kb % NA_STAGES;
-        mbar_wait(&a_full[sa], (kb / NA_STAGES) & 1);
+      int itb = 0, q = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int buf = t & 1;
+        mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_base = smem_u32(slabA + sa * a_stride);
-        for (int tap = 0; tap < p.ntaps; ++tap, ++itb) {
-          const int sb = itb % NB_STAGES;
-          mbar_wait(&b_full[sb], (itb / NB_STAGES) & 1);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
+        uint32_t accum = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++q) {
+          const int sa = q % NA;
+          mbar_wait(&a_full[sa], (q / NA) & 1);
           tc_fence_after();
-          const uint32_t b_base = smem_u32(slabB + sb * b_stride);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ad = make_desc(a_base + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
-            const uint64_t bd = make_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
-            tc_mma_f16(tmem_base, ad, bd, idesc, accum);
-            accum = 1;
+          const uint32_t a_base = smem_u32(slabA + sa * a_stride);
+          for (int tap = 0; tap < p.ntaps; ++tap, ++itb) {
+            const int sb = itb % NB;
+            mbar_wait(&b_full[sb], (itb / NB) & 1);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(slabB + sb * b_stride);
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t ad = make_desc(a_base + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
+              const uint64_t bd = make_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
+              tc_mma_f16(d_tmem, ad, bd, idesc, accum);
+              accum = 1;
+            }
+            tc_commit(&b_empty[sb]);
           }
-          tc_commit(&b_empty[sb]);     // frees the weight stage once these MMAs have read it
+          tc_commit(&a_empty[sa]);
         }
-        tc_commit(&a_empty[sa]);       // frees the activation slab
+        tc_commit(&acc_full[buf]);
       }
-      tc_commit(acc_full);             // accumulator complete
     }
   } else {
-    // =========================== epilogue: TMEM -> registers -> global ===========================
-    const int q = warp & 3;                         // TMEM lane quadrant this warp may access
-    const int row = j0 + q * 32 + lane;             // time row (within this group's Lj rows)
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const bool row_ok = row < p.Lj;
-    const long long orow = (long long)row * p.out_stride + g + p.padf;      // physical row in the output planes
-    const size_t pitch_o = (size_t)p.Lp_out * 16;                             // bytes per plane (both 16-bit and fp32 PV)
-    unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
-    unsigned char* y16 = p.y16 ? reinterpret_cast<unsigned char*>(p.y16) + (size_t)b * (p.Cout_total / 8) * pitch_o : nullptr;
-    const unsigned char* r32 = p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
-    const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
-    const bool obf = p.out_bf16 != 0;
-    for (int c0 = 0; c0 < p.N; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      if (!row_ok) continue;
-      const int co = n0 + c0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + co + i);
-      if (cond) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += __ldg(cond + co + i);
-      }
-      if (r32) {
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const float4 r = *reinterpret_cast<const float4*>(r32 + (size_t)(co / 4 + k4) * pitch_o + (size_t)orow * 16);
-          v[k4 * 4 + 0] += r.x; v[k4 * 4 + 1] += r.y; v[k4 * 4 + 2] += r.z; v[k4 * 4 + 3] += r.w;
+    // =========================== epilogue: 8 warps, TMEM -> registers -> global ==================
+    const int ew = warp - 2;                        // 0..7
+    const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;                       // which half of the N columns
+    const int wc = p.N >= 32 ? p.N / 2 : p.N;       // columns per warp
+    const bool active = p.N >= 32 || half == 0;
+    const size_t pitch_o = (size_t)p.Lp_out * 16;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int buf = t & 1;
+      int mt, nt, g, b;
+      decode((long long)blockIdx.x + (long long)t * gridDim.x, mt, nt, g, b);
+      mbar_wait(&acc_full[buf], (t >> 1) & 1);
+      tc_fence_after();
+      if (active) {
+        const int row = mt * BM + qd * 32 + lane;
+        const bool row_ok = row < p.Lj;
+        const size_t orow16 = (size_t)((long long)row * p.out_stride + g + p.padf) * 16;
+        unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
+        unsigned char* y16 = p.y16 ? reinterpret_cast<unsigned char*>(p.y16) + (size_t)b * (p.Cout_total / 8) * pitch_o : nullptr;
+        const unsigned char* r32 =
+            p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
+        const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
+        const int c_begin = half * wc;
+        const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * p.N);
+        if (wc % 32 == 0) {
+          for (int c0 = c_begin; c0 < c_begin + wc; c0 += 32)
+            epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16, r32, cond);
+        } else {
+          for (int c0 = c_begin; c0 < c_begin + wc; c0 += 16)
+            epilogue_chunk<16>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16, r32, cond);
         }
       }
-      if (p.accum) {
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const float4 r = *reinterpret_cast<const float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + (size_t)orow * 16);
-          v[k4 * 4 + 0] += r.x; v[k4 * 4 + 1] += r.y; v[k4 * 4 + 2] += r.z; v[k4 * 4 + 3] += r.w;
-        }
-      }
-      if (p.div != 1.f) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = v[i] / p.div;
-      }
-      if (y32) {
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          *reinterpret_cast<float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + (size_t)orow * 16) =
-              make_float4(v[k4 * 4 + 0], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
-      }
-      if (y16) {
-#pragma unroll
-        for (int k8 = 0; k8 < 2; ++k8) {
-          uint4 o;
-          o.x = pack2(obf, lrelu(v[k8 * 8 + 0], p.out_slope), lrelu(v[k8 * 8 + 1], p.out_slope));
-          o.y = pack2(obf, lrelu(v[k8 * 8 + 2], p.out_slope), lrelu(v[k8 * 8 + 3], p.out_slope));
-          o.z = pack2(obf, lrelu(v[k8 * 8 + 4], p.out_slope), lrelu(v[k8 * 8 + 5], p.out_slope));
-          o.w = pack2(obf, lrelu(v[k8 * 8 + 6], p.out_slope), lrelu(v[k8 * 8 + 7], p.out_slope));
-          *reinterpret_cast<uint4*>(y16 + (size_t)(co / 8 + k8) * pitch_o + (size_t)orow * 16) = o;
-        }
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
     }
   }
   // ------------------------------------ teardown -------------------------------------------------
@@ -273,7 +344,7 @@ size_t tc_smem_bytes(const TcConvDesc& d) {
   const int R = (BM + halo + 7) & ~7;
   const size_t a = (((size_t)(d.KB / 8) * R * 16) + 127) & ~(size_t)127;
   const size_t bb = (((size_t)d.N * d.KB * 2) + 127) & ~(size_t)127;
-  return NA_STAGES * a + NB_STAGES * bb + 8 * (2 * NA_STAGES + 2 * NB_STAGES + 1) + 16 + 128;
+  return d.na_stages * a + d.nb_stages * bb + 8 * (2 * d.na_stages + 2 * d.nb_stages + 4) + 16 + 128;
 }
 
 // ---- PV-layout glue kernels ----------------------------------------------------------------------
@@ -421,19 +492,35 @@ inline unsigned grid_for(long long total, int threads) {
 
 }  // namespace
 
-cudaError_t launch_conv_tc(const TcConvDesc& d, int B, cudaStream_t st) {
+cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
+  TcConvDesc d = d_in;
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.KB % 16 != 0 || d.KB > 64 || d.Cin % d.KB != 0 || d.Cout_total % d.N != 0 ||
-      d.G < 1 || d.G > 16 || d.Lj <= 0 || (d.ntaps - 1) * d.dil > 56 || d.tmem_cols < d.N || (d.accum && !d.y32))
+      d.G < 1 || d.G > 16 || d.Lj <= 0 || (d.ntaps - 1) * d.dil > 56 || (d.accum && !d.y32) || B <= 0)
     return cudaErrorInvalidValue;
-  const size_t smem = tc_smem_bytes(d);
+  d.batch = B;
+  int cols = 32;
+  while (cols < 2 * d.N) cols <<= 1;          // two accumulator buffers
+  d.tmem_cols = cols;
+  const int nkb = d.Cin / d.KB;
+  d.na_stages = nkb >= 2 ? 3 : 2;
+  d.nb_stages = 4;
+  size_t smem = tc_smem_bytes(d);
+  while (smem > 200 * 1024 && d.nb_stages > 2) { d.nb_stages--; smem = tc_smem_bytes(d); }
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static size_t cfgd = 0;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
   if (smem > cfgd) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cfgd = smem;
   }
-  dim3 grid((d.Lj + BM - 1) / BM, d.Cout_total / d.N, B * d.G);
+  const long long tiles = (long long)((d.Lj + BM - 1) / BM) * (d.Cout_total / d.N) * d.G * B;
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
   conv_tc_kernel<<<grid, kThreadsTC, smem, st>>>(d);
   launch_counter().n++;
   return cudaGetLastError();
