@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the tcgen05 convolution at the decoder's real shapes (48k_v2, 60 s segment).
+
+    python tools/bench_conv_tc.py [--reps 5] [--only STAGE] [--profile]
+
+For each stage (C, L) x kernel size x epilogue type (c1: 16-bit store only; c2: + fp32 residual read,
+fp32 store) reports device time (CUDA events), TFLOP/s and algorithmic HBM GB/s.  With --profile the
+timed launches are bracketed by cudaProfilerStart/Stop for `ncu --profile-from-start off`.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from comfy_rvc_b200 import _lib, weights  # noqa: E402
+
+PADF = 32
+
+
+def pitch(L):
+    return ((L + 127) // 128) * 128 + 128
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", type=int, default=-1)
+    ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--T", type=int, default=6000)
+    args = ap.parse_args()
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    stages = [(256, args.T * 12), (128, args.T * 120), (64, args.T * 240), (32, args.T * 480)]
+    rows = []
+    for si, (Cc, L) in enumerate(stages):
+        if args.only >= 0 and si != args.only:
+            continue
+        Lp = pitch(L)
+        x16 = torch.zeros(1, Cc // 8, Lp, 8, dtype=torch.float16, device=dev)
+        x16[:, :, PADF:PADF + L].normal_()
+        r32 = torch.randn(1, Cc // 4, Lp, 4, device=dev)
+        y32 = torch.zeros(1, Cc // 4, Lp, 4, device=dev)
+        y16 = torch.zeros(1, Cc // 8, Lp, 8, dtype=torch.float16, device=dev)
+        bias = torch.randn(Cc, device=dev)
+        for k, dil in ((3, 1), (7, 3), (11, 5), (11, 1)):
+            w = weights.pack_tc(torch.randn(1, k, Cc, Cc) / (Cc * k) ** 0.5, torch.float16).to(dev)
+            for kind in ("c1", "c2"):
+                d = _lib.TcConvDesc()
+                d.x16, d.Lp_in, d.padf = x16.data_ptr(), Lp, PADF
+                d.w16, d.bias = w.data_ptr(), bias.data_ptr()
+                d.Cin, d.KB, d.ntaps, d.dil, d.G = Cc, min(64, Cc), k, dil, 1
+                d.g_off[0] = -((k - 1) // 2) * dil
+                d.N, d.Cout_total = min(256, Cc), Cc
+                d.Lj, d.out_stride, d.Lp_out = L, 1, Lp
+                d.y16, d.out_slope, d.div = y16.data_ptr(), 0.1, 1.0
+                if kind == "c2":
+                    d.y32, d.res32 = y32.data_ptr(), r32.data_ptr()
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                for _ in range(2):
+                    assert lib.rvcb200_op_conv_tc(C.byref(d), 1, st) == 0
+                torch.cuda.synchronize()
+                if args.profile:
+                    torch.cuda.profiler.start()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.reps):
+                    lib.rvcb200_op_conv_tc(C.byref(d), 1, st)
+                e1.record()
+                torch.cuda.synchronize()
+                if args.profile:
+                    torch.cuda.profiler.stop()
+                us = e0.elapsed_time(e1) * 1e3 / args.reps
+                flops = 2.0 * L * Cc * Cc * k
+                bytes_ = L * Cc * (2 + 2 + (8 if kind == "c2" else 0))
+                rows.append(dict(stage=si + 1, C=Cc, L=L, k=k, dil=dil, kind=kind, us=round(us, 1),
+                                 tflops=round(flops / us / 1e6, 1), hbm_gbs=round(bytes_ / us / 1e3, 1)))
+                print(json.dumps(rows[-1]), flush=True)
+    return rows
+
+
+if __name__ == "__main__":
+    main()
