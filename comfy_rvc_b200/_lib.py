@@ -60,7 +60,7 @@ class TcConvDesc(C.Structure):
         ("cond", C.c_void_p), ("cond_bstride", C.c_int32),
         ("accum", C.c_int32), ("div", C.c_float), ("out_slope", C.c_float),
         ("in_bf16", C.c_int32), ("out_bf16", C.c_int32),
-        ("batch", C.c_int32), ("na_stages", C.c_int32), ("nb_stages", C.c_int32),
+        ("batch", C.c_int32), ("na_stages", C.c_int32), ("nb_stages", C.c_int32), ("b_stationary", C.c_int32),
     ]
 
 

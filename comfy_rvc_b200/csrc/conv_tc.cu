@@ -239,21 +239,33 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_kernel(const TcConvDesc
                    &a_full[sa]);
       };
       const int ahead = NA - 1;                       // slabs issued ahead of the one being consumed
-      for (int q = 0; q < ahead && q < Q; ++q) issue_a(q);
-      int itb = 0;
-      for (int q = 0; q < Q; ++q) {
-        int mt, nt, g, b;
-        decode((long long)blockIdx.x + (long long)(q / nkb) * gridDim.x, mt, nt, g, b);
-        const int kb = q % nkb;
-        const unsigned char* wb = reinterpret_cast<const unsigned char*>(p.w16) +
-                                  ((size_t)(g * n_nt + nt) * p.ntaps * nkb) * b_bytes;
-        for (int tap = 0; tap < p.ntaps; ++tap, ++itb) {
-          const int sb = itb % NB;
-          mbar_wait(&b_empty[sb], ((itb / NB) & 1) ^ 1);
-          mbar_expect_tx(&b_full[sb], b_bytes);
-          bulk_g2s(slabB + sb * b_stride, wb + ((size_t)tap * nkb + kb) * b_bytes, b_bytes, &b_full[sb]);
+      if (p.b_stationary) {
+        // all (k-block, tap) weight tiles fit in smem: load them once, they serve every tile of this CTA
+        const unsigned char* wb = reinterpret_cast<const unsigned char*>(p.w16);
+        for (int kb = 0; kb < nkb; ++kb)
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int sb = kb * p.ntaps + tap;
+            mbar_expect_tx(&b_full[sb], b_bytes);
+            bulk_g2s(slabB + sb * b_stride, wb + ((size_t)tap * nkb + kb) * b_bytes, b_bytes, &b_full[sb]);
+          }
+        for (int q = 0; q < Q; ++q) issue_a(q);       // issue_a blocks on a_empty: NA slabs in flight
+      } else {
+        for (int q = 0; q < ahead && q < Q; ++q) issue_a(q);
+        int itb = 0;
+        for (int q = 0; q < Q; ++q) {
+          int mt, nt, g, b;
+          decode((long long)blockIdx.x + (long long)(q / nkb) * gridDim.x, mt, nt, g, b);
+          const int kb = q % nkb;
+          const unsigned char* wb = reinterpret_cast<const unsigned char*>(p.w16) +
+                                    ((size_t)(g * n_nt + nt) * p.ntaps * nkb) * b_bytes;
+          for (int tap = 0; tap < p.ntaps; ++tap, ++itb) {
+            const int sb = itb % NB;
+            mbar_wait(&b_empty[sb], ((itb / NB) & 1) ^ 1);
+            mbar_expect_tx(&b_full[sb], b_bytes);
+            bulk_g2s(slabB + sb * b_stride, wb + ((size_t)tap * nkb + kb) * b_bytes, b_bytes, &b_full[sb]);
+          }
+          if (q + ahead < Q) issue_a(q + ahead);
         }
-        if (q + ahead < Q) issue_a(q + ahead);
       }
     }
   } else if (warp == 1) {
@@ -263,6 +275,8 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_kernel(const TcConvDesc
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t lbo_a = (uint32_t)R * 16, lbo_b = (uint32_t)p.N * 16;
       const int ksteps = p.KB / 16;
+      const uint64_t desc_a0 = make_desc(0, lbo_a, 128), desc_b0 = make_desc(0, lbo_b, 128);
+      const bool stat = p.b_stationary != 0;
       int itb = 0, q = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const int buf = t & 1;
@@ -276,17 +290,22 @@ __global__ void __launch_bounds__(kThreadsTC, 1) conv_tc_kernel(const TcConvDesc
           tc_fence_after();
           const uint32_t a_base = smem_u32(slabA + sa * a_stride);
           for (int tap = 0; tap < p.ntaps; ++tap, ++itb) {
-            const int sb = itb % NB;
-            mbar_wait(&b_full[sb], (itb / NB) & 1);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(slabB + sb * b_stride);
+            int sb;
+            if (stat) {
+              sb = kb * p.ntaps + tap;
+              if (t == 0) { mbar_wait(&b_full[sb], 0); tc_fence_after(); }
+            } else {
+              sb = itb % NB;
+              mbar_wait(&b_full[sb], (itb / NB) & 1);
+              tc_fence_after();
+            }
+            const uint64_t ad0 = desc_a0 + (uint64_t)((a_base + (uint32_t)(tap * p.dil) * 16) >> 4);
+            const uint64_t bd0 = desc_b0 + (uint64_t)(smem_u32(slabB + sb * b_stride) >> 4);
             for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t ad = make_desc(a_base + (uint32_t)(tap * p.dil) * 16 + (uint32_t)(2 * ks) * lbo_a, lbo_a, 128);
-              const uint64_t bd = make_desc(b_base + (uint32_t)(2 * ks) * lbo_b, lbo_b, 128);
-              tc_mma_f16(d_tmem, ad, bd, idesc, accum);
+              tc_mma_f16(d_tmem, ad0 + (uint64_t)((2 * ks * lbo_a) >> 4), bd0 + (uint64_t)((2 * ks * lbo_b) >> 4), idesc, accum);
               accum = 1;
             }
-            tc_commit(&b_empty[sb]);
+            if (!stat) tc_commit(&b_empty[sb]);
           }
           tc_commit(&a_empty[sa]);
         }
@@ -502,10 +521,29 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   while (cols < 2 * d.N) cols <<= 1;          // two accumulator buffers
   d.tmem_cols = cols;
   const int nkb = d.Cin / d.KB;
-  d.na_stages = nkb >= 2 ? 3 : 2;
-  d.nb_stages = 4;
+  {
+    // smem policy: weights stationary (loaded once per persistent CTA) when every (k-block, tap) tile
+    // fits beside >= 3 activation slabs; otherwise a weight ring with >= 128 KB in flight.
+    const int halo = (d.ntaps - 1) * d.dil;
+    const int R = (BM + halo + 7) & ~7;
+    const size_t a = (((size_t)(d.KB / 8) * R * 16) + 127) & ~(size_t)127;
+    const size_t bb = (((size_t)d.N * d.KB * 2) + 127) & ~(size_t)127;
+    const size_t budget = 212 * 1024;
+    const int nw = nkb * d.ntaps;
+    const long long tiles_ = (long long)((d.Lj + BM - 1) / BM) * (d.Cout_total / d.N) * d.G * B;
+    d.b_stationary = 0;
+    if (d.G == 1 && d.Cout_total == d.N && nw <= 48 && (size_t)nw * bb + 3 * a <= budget && tiles_ > 2 * 148) {
+      d.b_stationary = 1;
+      d.nb_stages = nw;
+      long long na = (long long)(budget - (size_t)nw * bb) / (long long)a;
+      d.na_stages = (int)(na > 8 ? 8 : na);
+    } else {
+      d.na_stages = nkb >= 2 ? 3 : 2;
+      long long nb = (long long)(budget - (size_t)d.na_stages * a) / (long long)bb;
+      d.nb_stages = (int)(nb > 12 ? 12 : (nb < 2 ? 2 : nb));
+    }
+  }
   size_t smem = tc_smem_bytes(d);
-  while (smem > 200 * 1024 && d.nb_stages > 2) { d.nb_stages--; smem = tc_smem_bytes(d); }
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static size_t cfgd = 0;
   static int num_sms = 0;

@@ -169,7 +169,7 @@ typedef struct rvcb200_tc_conv_desc {
   const float* cond; int32_t cond_bstride;
   int32_t accum; float div; float out_slope;
   int32_t in_bf16, out_bf16;   /* operand format of x16/w16 and storage format of y16: 0 = fp16, 1 = bf16 */
-  int32_t batch, na_stages, nb_stages; /* filled in by the launcher */
+  int32_t batch, na_stages, nb_stages, b_stationary; /* filled in by the launcher */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 

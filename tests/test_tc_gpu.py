@@ -45,6 +45,11 @@ TC_CASES = [
     ("ups12_512_256", 1, 60, 512, 256, 2, 1, 12),
     ("ups2_64_32", 2, 333, 64, 32, 2, 1, 2),
     ("k3_c16", 1, 500, 16, 16, 3, 1, 1),
+    # > 296 tiles: exercises the weights-stationary persistent path (several tiles per CTA)
+    ("k7_d3_c64_long", 1, 60000, 64, 64, 7, 3, 1),
+    ("k11_d5_c32_long", 2, 40000, 32, 32, 11, 5, 1),
+    ("k3_c128_long", 1, 45000, 128, 128, 3, 1, 1),
+    ("k7_c128_ring_long", 1, 45000, 128, 128, 7, 1, 1),
 ]
 
 
