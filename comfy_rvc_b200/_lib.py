@@ -50,16 +50,16 @@ class ConvDesc(C.Structure):
 
 class TcConvDesc(C.Structure):
     _fields_ = [
-        ("x16", C.c_void_p), ("Lp_in", C.c_int32), ("padf", C.c_int32),
+        ("x16", C.c_void_p), ("L_in", C.c_int32), ("padf", C.c_int32),
         ("w16", C.c_void_p), ("bias", C.c_void_p),
-        ("Cin", C.c_int32), ("KB", C.c_int32), ("ntaps", C.c_int32), ("dil", C.c_int32), ("G", C.c_int32),
+        ("Cin", C.c_int32), ("ntaps", C.c_int32), ("dil", C.c_int32), ("G", C.c_int32),
         ("g_off", C.c_int32 * 16),
         ("N", C.c_int32), ("Cout_total", C.c_int32), ("tmem_cols", C.c_int32),
         ("Lj", C.c_int32), ("out_stride", C.c_int32), ("Lp_out", C.c_int32),
         ("y32", C.c_void_p), ("y16", C.c_void_p), ("res32", C.c_void_p),
         ("cond", C.c_void_p), ("cond_bstride", C.c_int32),
         ("accum", C.c_int32), ("div", C.c_float), ("out_slope", C.c_float),
-        ("in_bf16", C.c_int32), ("out_bf16", C.c_int32),
+        ("in_bf16", C.c_int32), ("out_bf16", C.c_int32), ("a_mode", C.c_int32),
         ("batch", C.c_int32), ("na_stages", C.c_int32), ("nb_stages", C.c_int32), ("b_stationary", C.c_int32),
     ]
 

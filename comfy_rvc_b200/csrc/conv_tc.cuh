@@ -13,14 +13,12 @@ inline int pv_pitch_rows(long long L) { return (int)(((L + 127) / 128) * 128 + 1
 
 cudaError_t launch_conv_tc(const TcConvDesc& d, int B, cudaStream_t st);
 cudaError_t launch_zero_pads(void* base, long long planes, int Lp, int padf, long long L, cudaStream_t st);
-cudaError_t launch_cl_to_pv16(const float* x, int ldx, int B, long long L, int C, void* y16, int Lp, int padf, float slope,
-                              bool bf16, cudaStream_t st);
+cudaError_t launch_cl32_to_cl16(const float* x, void* y16, long long numel, float slope, bool bf16, cudaStream_t st);
 cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, int B,
                                 long long L_har, long long L, int C, int k, int s, int pad, int Lp, int padf, float slope,
                                 bool bf16, cudaStream_t st);
 cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int B, long long L, int C, int k, int Lp,
                                 int padf, float slope, cudaStream_t st);
-cudaError_t launch_pv_to_cl(const void* src, bool is16, bool bf16, float* y, int B, long long L, int C, int Lp, int padf,
-                            cudaStream_t st);
+cudaError_t launch_pv32_to_cl(const void* src, float* y, int B, long long L, int C, int Lp, int padf, cudaStream_t st);
 
 }  // namespace rvc

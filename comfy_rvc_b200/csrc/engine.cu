@@ -3,6 +3,7 @@
 // `SynthesizerTrnMs{256,768}NSFsid.infer` (/root/reference/lib/infer_pack/models.py:682-693,
 // :798-809): emb_g -> enc_p -> prior sample -> reverse flow -> NSF source -> GeneratorNSF.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -679,17 +680,18 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     auto W16 = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, dt, &ok); };
     auto W16h = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, 1, &ok); };
     const int rb_bf16 = bf16 ? 1 : 0;
+    static const int tc_a_mode = [] { const char* e = getenv("RVCB200_TC_AMODE"); return e ? atoi(e) : 0; }();
     auto tmem_cols_for = [](int N) { int c = 32; while (c < N) c <<= 1; return c; };
     auto tc_base = [&]() {
       TcConvDesc d;
       memset(&d, 0, sizeof(d));
       d.padf = kPadF; d.ntaps = 1; d.dil = 1; d.G = 1; d.out_stride = 1; d.div = 1.f; d.out_slope = 1.f;
+      d.a_mode = tc_a_mode;
       return d;
     };
     const int LpT = pv_pitch_rows(T);
-    // z -> PV16 (conv_pre consumes z*mask; z is already masked)
-    CKC(3, launch_zero_pads(pl.z16, (long long)B * (C / 8), LpT, kPadF, T, st), "zero_pads");
-    CKC(3, launch_cl_to_pv16(z, C, B, T, C, pl.z16, LpT, kPadF, 1.f, false, st), "z->pv16");
+    // z -> fp16 channels-last (conv_pre consumes z*mask; z is already masked)
+    CKC(3, launch_cl32_to_cl16(z, pl.z16, (long long)BT * C, 1.f, false, st), "z->fp16");
     void* IN16 = pl.pv16[0];
     void* X16 = pl.pv16[1];
     void* XT16 = pl.pv16[2];
@@ -700,10 +702,9 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     float* ACC32 = pl.pv32[2];
     {
       const int U0 = f.up_init_channels;
-      CKC(3, launch_zero_pads(IN16, (long long)B * (U0 / 8), LpT, kPadF, T, st), "zero_pads");
       TcConvDesc d = tc_base();
-      d.x16 = pl.z16; d.Lp_in = LpT; d.w16 = W16h("dec.pre.w"); d.bias = W("dec.pre.b");
-      d.Cin = C; d.KB = C < 64 ? C : 64; d.ntaps = 7; d.g_off[0] = -3;
+      d.x16 = pl.z16; d.L_in = T; d.w16 = W16h("dec.pre.w"); d.bias = W("dec.pre.b");
+      d.Cin = C; d.ntaps = 7; d.g_off[0] = -3;
       d.N = U0 < 256 ? U0 : 256; d.Cout_total = U0; d.tmem_cols = tmem_cols_for(d.N);
       d.Lj = T; d.Lp_out = LpT; d.y16 = IN16; d.out_slope = 0.1f;      // lrelu of models.py:550 folded into the store
       d.cond = pl.cond; d.cond_bstride = ctx->n_cond;
@@ -720,15 +721,11 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       const int Cn = g.cout;
       const int LpN = pv_pitch_rows(Ln);
       const bool last_stage = i == f.n_ups - 1;
-      CKC(3, launch_zero_pads(X16, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
-      CKC(3, launch_zero_pads(XT16, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
-      CKC(3, launch_zero_pads(XB16, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
-      if (!last_stage) CKC(3, launch_zero_pads(N16, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
-      else CKC(3, launch_zero_pads(ACC32, (long long)B * (Cn / 4), LpN, kPadF, Ln, st), "zero_pads");
+      if (last_stage) CKC(3, launch_zero_pads(ACC32, (long long)B * (Cn / 4), LpN, kPadF, Ln, st), "zero_pads");
       {  // x = ups[i](lrelu(x)) as g.u phase groups (input already holds lrelu(x) in 16 bit)
         TcConvDesc d = tc_base();
-        d.x16 = IN16; d.Lp_in = LpC; d.w16 = W16h(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i));
-        d.Cin = Cc; d.KB = Cc < 64 ? Cc : 64; d.ntaps = g.ntaps; d.G = g.u;
+        d.x16 = IN16; d.L_in = (int)Lc; d.w16 = W16h(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i));
+        d.Cin = Cc; d.ntaps = g.ntaps; d.G = g.u;
         for (int p = 0; p < g.u; ++p) d.g_off[p] = g.g_off[p];
         d.N = Cn < 256 ? Cn : 256; d.Cout_total = Cn; d.tmem_cols = tmem_cols_for(d.N);
         d.Lj = (int)Lc; d.out_stride = g.u; d.Lp_out = LpN; d.y32 = X32;
@@ -744,7 +741,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
             "dec.noise_add(pv)");
       }
       if (const rvcb200_tap* t = tp.find(S("dec.ups.%d", i).c_str()))
-        CK(launch_pv_to_cl(X32, false, bf16, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");
+        CK(launch_pv32_to_cl(X32, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");
       for (int j = 0; j < f.n_res_kernels; ++j) {
         const int n = i * f.n_res_kernels + j;
         const int k = f.res_kernels[j];
@@ -755,7 +752,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
           const bool last = dd == nd - 1;
           const int dil = f.res_dils[j][dd];
           TcConvDesc o = tc_base();
-          o.Lp_in = LpN; o.Cin = Cn; o.KB = Cn < 64 ? Cn : 64; o.ntaps = k;
+          o.L_in = (int)Ln; o.Cin = Cn; o.ntaps = k;
           o.N = Cn < 256 ? Cn : 256; o.Cout_total = Cn; o.tmem_cols = tmem_cols_for(o.N);
           o.Lj = (int)Ln; o.Lp_out = LpN;
           if (f.resblock_kind == 1) {
@@ -788,9 +785,9 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
         }
       }
       if (const rvcb200_tap* t = tp.find(S("dec.stage.%d", i).c_str()))
-        CK(launch_pv_to_cl(ACC32, false, bf16, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");
+        CK(launch_pv32_to_cl(ACC32, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");
       void* tmp = IN16; IN16 = N16; N16 = tmp;
-      Lc = Ln; Cc = Cn; LpC = LpN;
+      Lc = Ln; Cc = Cn; LpC = LpN; (void)LpC;
     }
     CKC(3, launch_conv_post_pv(ACC32, W("dec.post.w"), out, B, Lc, Cc, 7, LpC, kPadF, 0.01f, st), "dec.conv_post(pv)");
   }

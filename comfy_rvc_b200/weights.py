@@ -176,21 +176,23 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
 
 
 # ---- tensor-core path: 16-bit smem images of the decoder weights ------------------------------------
-TC_KB_MAX, TC_N_MAX = 64, 256
+TC_KB, TC_N_MAX = 64, 256
 
 
 def pack_tc(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """[G][taps][C_in][C_out] (or [taps][C_in][C_out]) fp32 -> [G][C_out/N][taps][C_in/KB][KB/8][N][8] 16-bit.
+    """[G][taps][C_in][C_out] (or [taps][C_in][C_out]) fp32 -> [G][C_out/N][taps][ceil(C_in/64)][N][64] 16-bit.
 
-    One (tap, k-block) slice is the exact shared-memory image of the tcgen05 B operand in the
-    no-swizzle K-major canonical layout (csrc/conv_tc.cu): 8-channel groups outermost, then the N
-    output channels, then the 8 contiguous input channels (16 bytes)."""
+    One (tap, k-block) slice is an [N][64] K-major matrix (input channels contiguous, zero-padded to
+    64) that TMA loads into SWIZZLE_128B shared memory as the tcgen05 B operand (csrc/conv_tc.cu)."""
     if w.dim() == 3:
         w = w.unsqueeze(0)
     G, taps, cin, cout = w.shape
-    KB, N = min(TC_KB_MAX, cin), min(TC_N_MAX, cout)
-    assert cin % KB == 0 and KB % 16 == 0 and cout % N == 0 and N % 16 == 0, (cin, cout)
-    t = w.reshape(G, taps, cin // KB, KB // 8, 8, cout // N, N).permute(0, 5, 1, 2, 3, 6, 4)
+    N = min(TC_N_MAX, cout)
+    nkb = (cin + TC_KB - 1) // TC_KB
+    assert cout % N == 0 and N % 16 == 0, (cin, cout)
+    if nkb * TC_KB != cin:
+        w = torch.cat([w, w.new_zeros(G, taps, nkb * TC_KB - cin, cout)], dim=2)
+    t = w.reshape(G, taps, nkb, TC_KB, cout // N, N).permute(0, 4, 1, 2, 5, 3)
     return t.contiguous().to(dtype)
 
 

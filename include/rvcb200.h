@@ -156,19 +156,23 @@ typedef struct rvcb200_conv_desc {
 } rvcb200_conv_desc;
 int rvcb200_op_conv_f32(const rvcb200_conv_desc* d, int32_t B, void* stream);
 
-/* tcgen05/TMEM convolution on "planar-vector" (PV) activations: 16-bit [B][C/8][Lp][8] operands,
- * fp32 [B][C/4][Lp][4] residual stream, Lp = roundup(L,128)+128 rows per plane, 32 zero rows in front
- * (csrc/conv_tc.cu).  Weights are the packed smem image [G][C_out/N][taps][C_in/KB][KB/8][N][8]. */
+/* tcgen05/TMEM convolution (csrc/conv_tc.cu).  MMA operands: 16-bit channels-last activations
+ * x16 [B][L_in][Cin] and packed weights w16 [G][C_out/N][taps][ceil(Cin/64)][N][64] (K zero-padded),
+ * both staged by TMA into SWIZZLE_128B shared memory.  fp32 side (residual res32, output y32):
+ * planar-vector [B][C/4][Lp_out][4] with `padf` rows in front; 16-bit output y16: channels-last
+ * [B][Lj*out_stride][Cout_total] holding lrelu_{out_slope}(result).  a_mode 0 = one activation box per
+ * k-block + per-tap descriptor offsets, 1 = one TMA box per (k-block, tap). */
 typedef struct rvcb200_tc_conv_desc {
-  const void* x16; int32_t Lp_in; int32_t padf;
+  const void* x16; int32_t L_in; int32_t padf;
   const void* w16; const float* bias;
-  int32_t Cin, KB, ntaps, dil, G; int32_t g_off[16];
+  int32_t Cin, ntaps, dil, G; int32_t g_off[16];
   int32_t N, Cout_total, tmem_cols;
   int32_t Lj, out_stride, Lp_out;
   float* y32; void* y16; const float* res32;
   const float* cond; int32_t cond_bstride;
   int32_t accum; float div; float out_slope;
   int32_t in_bf16, out_bf16;   /* operand format of x16/w16 and storage format of y16: 0 = fp16, 1 = bf16 */
+  int32_t a_mode;
   int32_t batch, na_stages, nb_stages, b_stationary; /* filled in by the launcher */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);

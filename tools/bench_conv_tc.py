@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--only", type=int, default=-1)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--T", type=int, default=6000)
+    ap.add_argument("--a-mode", type=int, default=0)
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda", 0)
@@ -40,19 +41,19 @@ def main():
         if args.only >= 0 and si != args.only:
             continue
         Lp = pitch(L)
-        x16 = torch.zeros(1, Cc // 8, Lp, 8, dtype=torch.float16, device=dev)
-        x16[:, :, PADF:PADF + L].normal_()
+        x16 = torch.randn(1, L, Cc, dtype=torch.float16, device=dev)
         r32 = torch.randn(1, Cc // 4, Lp, 4, device=dev)
         y32 = torch.zeros(1, Cc // 4, Lp, 4, device=dev)
-        y16 = torch.zeros(1, Cc // 8, Lp, 8, dtype=torch.float16, device=dev)
+        y16 = torch.zeros(1, L, Cc, dtype=torch.float16, device=dev)
         bias = torch.randn(Cc, device=dev)
         for k, dil in ((3, 1), (7, 3), (11, 5), (11, 1)):
             w = weights.pack_tc(torch.randn(1, k, Cc, Cc) / (Cc * k) ** 0.5, torch.float16).to(dev)
             for kind in ("c1", "c2"):
                 d = _lib.TcConvDesc()
-                d.x16, d.Lp_in, d.padf = x16.data_ptr(), Lp, PADF
+                d.x16, d.L_in, d.padf = x16.data_ptr(), L, PADF
                 d.w16, d.bias = w.data_ptr(), bias.data_ptr()
-                d.Cin, d.KB, d.ntaps, d.dil, d.G = Cc, min(64, Cc), k, dil, 1
+                d.Cin, d.ntaps, d.dil, d.G = Cc, k, dil, 1
+                d.a_mode = args.a_mode
                 d.g_off[0] = -((k - 1) // 2) * dil
                 d.N, d.Cout_total = min(256, Cc), Cc
                 d.Lj, d.out_stride, d.Lp_out = L, 1, Lp
@@ -76,7 +77,7 @@ def main():
                 us = e0.elapsed_time(e1) * 1e3 / args.reps
                 flops = 2.0 * L * Cc * Cc * k
                 bytes_ = L * Cc * (2 + 2 + (8 if kind == "c2" else 0))
-                rows.append(dict(stage=si + 1, C=Cc, L=L, k=k, dil=dil, kind=kind, us=round(us, 1),
+                rows.append(dict(a_mode=args.a_mode, stage=si + 1, C=Cc, L=L, k=k, dil=dil, kind=kind, us=round(us, 1),
                                  tflops=round(flops / us / 1e6, 1), hbm_gbs=round(bytes_ / us / 1e3, 1)))
                 print(json.dumps(rows[-1]), flush=True)
     return rows
