@@ -71,18 +71,33 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (elect.sync)
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// descriptors are passed as (lo, hi) 32-bit halves: only the low word (start address) changes per MMA
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
 }
 // K-major SWIZZLE_128B shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B |
@@ -188,9 +203,11 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int halo = (p.ntaps - 1) * p.dil;
-  const int R = p.a_mode == 0 ? ((BM + halo + 7) & ~7) : BM;   // rows per activation box
+  const bool slab = p.a_mode != 1;                             // a_mode 0/2/3: one box per k-block (+ base_offset probes)
+  const int R = slab ? ((BM + halo + 7) & ~7) : BM;            // rows per activation box
   const int nkb = (p.Cin + KBLK - 1) / KBLK;
   const uint32_t a_bytes = (uint32_t)R * 128;
   const uint32_t b_bytes = (uint32_t)p.N * 128;
@@ -253,91 +270,104 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
             tma_load_2d(slabB + (size_t)sb * b_stride, &tmW, 0, w_row(0, 0, tap, kb), &b_full[sb]);
           }
       }
-      int ia = 0, ib = 0;     // running activation / weight ring items
+      int sa = 0, sb = 0;                 // ring slots; phase bits flip on wrap (no div/mod in the loop)
+      uint32_t pa = 1, pb = 1;            // producer waits on "empty" with inverted parity
       for (int t = 0; t < my_tiles; ++t) {
         int mt, nt, g, b;
         decode((long long)blockIdx.x + (long long)t * gridDim.x, mt, nt, g, b);
         const int row0 = mt * BM + p.g_off[g];
+        int wrow = w_row(g, nt, 0, 0);
         for (int kb = 0; kb < nkb; ++kb) {
-          if (p.a_mode == 0) {
-            const int sa = ia % NA;
-            mbar_wait(&a_empty[sa], ((ia / NA) & 1) ^ 1);
+          if (slab) {
+            mbar_wait(&a_empty[sa], pa);
             mbar_expect_tx(&a_full[sa], a_bytes);
             tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0, b, &a_full[sa]);
-            ++ia;
+            if (++sa == NA) { sa = 0; pa ^= 1; }
           }
           for (int tap = 0; tap < p.ntaps; ++tap) {
-            if (p.a_mode != 0) {
-              const int sa = ia % NA;
-              mbar_wait(&a_empty[sa], ((ia / NA) & 1) ^ 1);
+            if (!slab) {
+              mbar_wait(&a_empty[sa], pa);
               mbar_expect_tx(&a_full[sa], a_bytes);
               tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0 + tap * p.dil, b, &a_full[sa]);
-              ++ia;
+              if (++sa == NA) { sa = 0; pa ^= 1; }
             }
             if (!stat) {
-              const int sb = ib % NB;
-              mbar_wait(&b_empty[sb], ((ib / NB) & 1) ^ 1);
+              mbar_wait(&b_empty[sb], pb);
               mbar_expect_tx(&b_full[sb], b_bytes);
-              tma_load_2d(slabB + (size_t)sb * b_stride, &tmW, 0, w_row(g, nt, tap, kb), &b_full[sb]);
-              ++ib;
+              tma_load_2d(slabB + (size_t)sb * b_stride, &tmW, 0, wrow + (tap * nkb + kb) * p.N, &b_full[sb]);
+              if (++sb == NB) { sb = 0; pb ^= 1; }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (single thread) =====================================
-    if (lane == 0) {
-      const uint32_t fmt = p.in_bf16 ? 1u : 0u;
-      // instruction descriptor: D=F32 @4, A/B format @7/@10, K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int ia = 0, ib = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int buf = t & 1;
-        mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
-        uint32_t accum = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
-          int sa = 0;
-          if (p.a_mode == 0) {
-            sa = ia % NA;
-            mbar_wait(&a_full[sa], (ia / NA) & 1);
+    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues ==========
+    // (keeping the loop uniform lets the compiler hold descriptors in uniform registers; a per-thread
+    //  `if (lane == 0)` loop spent ~20 SASS instructions / ~270 cycles per UTCHMMA on R2UR traffic.)
+    const uint32_t fmt = p.in_bf16 ? 1u : 0u;
+    // instruction descriptor: D=F32 @4, A/B format @7/@10, K-major both, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint64_t dproto = make_desc_sw128(0, 0);
+    const uint32_t d_hi0 = (uint32_t)(dproto >> 32), d_lo0 = (uint32_t)dproto;
+    const uint32_t slabA_u = smem_u32(slabA), slabB_u = smem_u32(slabB);
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int buf = t & 1;
+      mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
+      uint32_t accum = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (slab) {
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+        }
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          uint32_t a_lo, a_hi = d_hi0;
+          if (slab) {
+            const uint32_t shift = (uint32_t)(tap * p.dil);
+            const uint32_t bo = p.a_mode == 0 ? (shift & 7u) : (p.a_mode == 2 ? 0u : ((8u - (shift & 7u)) & 7u));
+            a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride + shift * 128u) >> 4);
+            a_hi = d_hi0 | (bo << 17);                        // base_offset lives at bits [49,52)
+          } else {
+            mbar_wait(&a_full[sa], pa);
+            tc_fence_after();
+            a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
+          }
+          int wb_slot;
+          if (stat) {
+            wb_slot = kb * p.ntaps + tap;
+            if (t == 0) { mbar_wait(&b_full[wb_slot], 0); tc_fence_after(); }
+          } else {
+            wb_slot = sb;
+            mbar_wait(&b_full[sb], pb);
             tc_fence_after();
           }
-          for (int tap = 0; tap < p.ntaps; ++tap) {
-            uint64_t ad;
-            if (p.a_mode == 0) {
-              const uint32_t shift = (uint32_t)(tap * p.dil);
-              ad = make_desc_sw128(smem_u32(slabA + (size_t)sa * a_stride) + shift * 128u, shift & 7u);
-            } else {
-              sa = ia % NA;
-              mbar_wait(&a_full[sa], (ia / NA) & 1);
-              tc_fence_after();
-              ad = make_desc_sw128(smem_u32(slabA + (size_t)sa * a_stride), 0);
-            }
-            int sb;
-            if (stat) {
-              sb = kb * p.ntaps + tap;
-              if (t == 0) { mbar_wait(&b_full[sb], 0); tc_fence_after(); }
-            } else {
-              sb = ib % NB;
-              mbar_wait(&b_full[sb], (ib / NB) & 1);
-              tc_fence_after();
-            }
-            const uint64_t bd = make_desc_sw128(smem_u32(slabB + (size_t)sb * b_stride), 0);
+          const uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)wb_slot * b_stride) >> 4);
+          if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < KBLK / 16; ++ks) {   // +32 B per K=16 step inside the 128-byte swizzled row
-              tc_mma_f16(d_tmem, ad + (uint64_t)(2 * ks), bd + (uint64_t)(2 * ks), idesc, accum);
+              tc_mma_f16(d_tmem, a_lo + 2u * ks, a_hi, b_lo + 2u * ks, d_hi0, idesc, accum);
               accum = 1;
             }
-            if (!stat) { tc_commit(&b_empty[sb]); ++ib; }
-            if (p.a_mode != 0) { tc_commit(&a_empty[sa]); ++ia; }
+            if (!stat) tc_commit(&b_empty[sb]);
+            if (!slab) tc_commit(&a_empty[sa]);
           }
-          if (p.a_mode == 0) { tc_commit(&a_empty[sa]); ++ia; }
+          __syncwarp();
+          accum = 1;
+          if (!stat) { if (++sb == NB) { sb = 0; pb ^= 1; } }
+          if (!slab) { if (++sa == NA) { sa = 0; pa ^= 1; } }
         }
-        tc_commit(&acc_full[buf]);
+        if (slab) {
+          if (elect_one()) tc_commit(&a_empty[sa]);
+          __syncwarp();
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+        }
       }
+      if (elect_one()) tc_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     // =========================== epilogue: 8 warps, TMEM -> registers -> global ==================
@@ -390,7 +420,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
 
 size_t tc_smem_bytes(const TcConvDesc& d) {
   const int halo = (d.ntaps - 1) * d.dil;
-  const int R = d.a_mode == 0 ? ((BM + halo + 7) & ~7) : BM;
+  const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
   const size_t a = (((size_t)R * 128) + 1023) & ~(size_t)1023;
   const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
   return 1024 + d.na_stages * a + d.nb_stages * bb + 8 * (2 * d.na_stages + 2 * d.nb_stages + 4) + 16 + 128;
@@ -549,12 +579,12 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   {
     // smem policy: weights stationary (loaded once per persistent CTA) when every (k-block, tap) tile
     // fits beside >= 3 activation boxes; otherwise a weight ring.
-    const int R = d.a_mode == 0 ? ((BM + halo + 7) & ~7) : BM;
+    const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
     const size_t a = (((size_t)R * 128) + 1023) & ~(size_t)1023;
     const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
     const size_t budget = 208 * 1024;
     const int nw = nkb * d.ntaps;
-    const int na_max = d.a_mode == 0 ? 6 : 10;
+    const int na_max = d.a_mode != 1 ? 6 : 10;
     d.b_stationary = 0;
     if (d.G == 1 && n_nt == 1 && nw <= 48 && (size_t)nw * bb + 3 * a <= budget && tiles > 2 * 148) {
       d.b_stationary = 1;
@@ -562,7 +592,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
       long long na = (long long)(budget - (size_t)nw * bb) / (long long)a;
       d.na_stages = (int)(na > na_max ? na_max : na);
     } else {
-      d.na_stages = d.a_mode == 0 ? (nkb >= 2 ? 3 : 2) : 4;
+      d.na_stages = d.a_mode != 1 ? (nkb >= 2 ? 3 : 2) : 4;
       long long nb = (long long)(budget - (size_t)d.na_stages * a) / (long long)bb;
       d.nb_stages = (int)(nb > 10 ? 10 : (nb < 2 ? 2 : nb));
     }
@@ -574,7 +604,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   CUtensorMap tmA, tmW;
   const CUtensorMapDataType dt = d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
-    const int R = d.a_mode == 0 ? ((BM + halo + 7) & ~7) : BM;
+    const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
     cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)d.L_in, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.Cin * 2 * (cuuint64_t)d.L_in};
     cuuint32_t box[3] = {(cuuint32_t)KBLK, (cuuint32_t)R, 1};
