@@ -12,8 +12,9 @@
 // before 0 / after L-1 and channels >= C are zero-filled by the hardware (conv zero padding and the
 // K padding of the 32- and 16-channel stages come for free).
 //   a_mode 0: ONE TMA box of 128+halo rows per 64-channel k-block; each tap of the (dilated) kernel is
-//             a descriptor whose start address is advanced by tap*dil rows (x128 B) with the
-//             descriptor's base_offset field carrying the swizzle phase ((rows) & 7).
+//             a descriptor whose start address is advanced by tap*dil rows (x128 B).  The hardware
+//             applies the 128B swizzle on absolute smem address bits, so base_offset stays 0 (measured:
+//             base_offset = rows&7 or -rows&7 both give wrong results, 0 is bit-correct).
 //   a_mode 1: one TMA box of 128 rows per (k-block, tap) at row coordinate j0 + off + tap*dil.
 // Weights: 16-bit [G][C_out/N][taps][k-blocks][N][64] (K zero-padded to 64), TMA box (64, N); kept
 // resident in smem for the whole persistent CTA when all (k-block, tap) tiles fit, else a ring.
@@ -313,6 +314,10 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
     const uint32_t slabA_u = smem_u32(slabA), slabB_u = smem_u32(slabB);
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
+    if (stat) {   // resident weights: wait once for all (k-block, tap) tiles
+      for (int i = 0; i < nkb * p.ntaps; ++i) mbar_wait(&b_full[i], 0);
+      tc_fence_after();
+    }
     for (int t = 0; t < my_tiles; ++t) {
       const int buf = t & 1;
       mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
@@ -320,17 +325,36 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
       uint32_t accum = 0;
       for (int kb = 0; kb < nkb; ++kb) {
+        const int kleft = p.Cin - kb * KBLK;
+        const int ksteps = kleft >= KBLK ? KBLK / 16 : (kleft + 15) / 16;     // skip the zero-padded K of narrow stages
         if (slab) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
         }
+        if (slab && stat) {
+          // fast path: nothing to wait for inside the k-block -> one elected lane issues every tap back to back
+          if (elect_one()) {
+            const uint32_t a0 = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
+            const uint32_t b0 = d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4);
+            const uint32_t a_step = (uint32_t)(p.dil * 128) >> 4, b_step = b_stride >> 4;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              const uint32_t a_lo = a0 + (uint32_t)tap * a_step, b_lo = b0 + (uint32_t)tap * b_step;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                tc_mma_f16(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum);
+                accum = 1;
+              }
+            }
+            tc_commit(&a_empty[sa]);
+          }
+          __syncwarp();
+          accum = 1;
+          if (++sa == NA) { sa = 0; pa ^= 1; }
+          continue;
+        }
         for (int tap = 0; tap < p.ntaps; ++tap) {
-          uint32_t a_lo, a_hi = d_hi0;
+          uint32_t a_lo;
           if (slab) {
-            const uint32_t shift = (uint32_t)(tap * p.dil);
-            const uint32_t bo = p.a_mode == 0 ? (shift & 7u) : (p.a_mode == 2 ? 0u : ((8u - (shift & 7u)) & 7u));
-            a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride + shift * 128u) >> 4);
-            a_hi = d_hi0 | (bo << 17);                        // base_offset lives at bits [49,52)
+            a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride + (uint32_t)(tap * p.dil) * 128u) >> 4);
           } else {
             mbar_wait(&a_full[sa], pa);
             tc_fence_after();
@@ -339,7 +363,6 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           int wb_slot;
           if (stat) {
             wb_slot = kb * p.ntaps + tap;
-            if (t == 0) { mbar_wait(&b_full[wb_slot], 0); tc_fence_after(); }
           } else {
             wb_slot = sb;
             mbar_wait(&b_full[sb], pb);
@@ -347,9 +370,8 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           }
           const uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)wb_slot * b_stride) >> 4);
           if (elect_one()) {
-#pragma unroll
-            for (int ks = 0; ks < KBLK / 16; ++ks) {   // +32 B per K=16 step inside the 128-byte swizzled row
-              tc_mma_f16(d_tmem, a_lo + 2u * ks, a_hi, b_lo + 2u * ks, d_hi0, idesc, accum);
+            for (int ks = 0; ks < ksteps; ++ks) {   // +32 B per K=16 step inside the 128-byte swizzled row
+              tc_mma_f16(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum);
               accum = 1;
             }
             if (!stat) tc_commit(&b_empty[sb]);

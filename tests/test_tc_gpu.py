@@ -53,7 +53,7 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("a_mode", [1, 0, 2, 3], ids=["pertap", "slab_bo_shift", "slab_bo_zero", "slab_bo_neg"])
+@pytest.mark.parametrize("a_mode", [0, 1], ids=["slab", "pertap"])
 @pytest.mark.parametrize("bf16", [False, True], ids=["fp16", "bf16"])
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_conv_tc(case, bf16, a_mode):
@@ -97,8 +97,6 @@ def test_conv_tc(case, bf16, a_mode):
     got = from_pv(y32.cpu(), Lo).double()
     err = (got - ref).abs().max().item()
     print(f"conv_tc {name} {'bf16' if bf16 else 'fp16'} a_mode={a_mode}: max abs err {err:.3e} (|ref|max {ref.abs().max().item():.2f})")
-    if a_mode != 1:
-        return          # probes of the descriptor base_offset semantics: report only
     assert err < 1e-3, "tcgen05 conv mismatch"
     # pads must stay zero and the 16-bit copy is lrelu(out) rounded
     assert float(y32[:, :, :PADF].abs().max()) == 0.0 and float(y32[:, :, PADF + Lo:].abs().max()) == 0.0
