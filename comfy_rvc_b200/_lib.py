@@ -61,6 +61,12 @@ class TcConvDesc(C.Structure):
         ("accum", C.c_int32), ("div", C.c_float), ("out_slope", C.c_float),
         ("in_bf16", C.c_int32), ("out_bf16", C.c_int32), ("a_mode", C.c_int32),
         ("batch", C.c_int32), ("na_stages", C.c_int32), ("nb_stages", C.c_int32), ("b_stationary", C.c_int32),
+        ("generic", C.c_int32), ("ldx16", C.c_int32), ("f32_cl", C.c_int32),
+        ("ldy32", C.c_int32), ("ldr32", C.c_int32), ("ldy16", C.c_int32),
+        ("gather", C.c_void_p), ("gidx", C.c_void_p), ("gidx_bstride", C.c_int64),
+        ("alpha", C.c_float), ("pre_slope", C.c_float), ("relu", C.c_int32), ("gate", C.c_int32),
+        ("res_mode", C.c_int32), ("mask_pre", C.c_int32), ("mask_post", C.c_int32), ("mask16", C.c_int32),
+        ("out_len", C.c_void_p),
     ]
 
 

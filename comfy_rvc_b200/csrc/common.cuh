@@ -36,7 +36,7 @@ typedef rvcb200_conv_desc ConvDesc;
 cudaError_t launch_conv_f32(const ConvDesc& d, int B, cudaStream_t st);
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, long long rows, int C,
-                             float eps, cudaStream_t st);
+                             float eps, cudaStream_t st, void* y16 = nullptr, const int* len = nullptr, int T = 0);
 
 cudaError_t launch_attention_f32(const float* qkv, const float* rel_k, const float* rel_v, const int* len, float* out,
                                  int B, int T, int n_heads, int dk, int window, cudaStream_t st);
@@ -54,7 +54,7 @@ cudaError_t launch_cond_gemv(const float* emb_g, const long long* sid, const flo
 
 // z_p[b][t][c] = (m + exp(logs) * noise[b][c][t] * 0.66666) masked   (models.py:685/801)
 cudaError_t launch_zp_sample(const float* stats, const float* noise_cf, const int* len, float* zp, int B, int T, int C,
-                             cudaStream_t st);
+                             cudaStream_t st, float* z = nullptr, void* z16 = nullptr);
 
 // y[b][t][co] += nb[co] + sum_k har[b][t*s - pad + k] * wn[k][co]   (models.py:552-553)
 cudaError_t launch_noise_conv_add(const float* har, const float* wn, const float* nb, float* y, int B, long long L_har,

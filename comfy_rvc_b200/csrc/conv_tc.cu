@@ -200,6 +200,120 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t tad
   }
 }
 
+// Generic epilogue (text encoder / flow): channels-last or PV fp32 I/O, embedding gather, scale, gate,
+// masks, residual modes.  One pass over 16 accumulator columns of this thread's row.
+__device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t taddr, bool row_ok, bool valid, int b,
+                                                   long long orow, int co) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (!row_ok) return;
+  const long long Lout = (long long)p.Lj * p.out_stride;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __ldg(p.bias + co + i);
+  if (p.cond) {
+    const float* cond = p.cond + (size_t)b * p.cond_bstride;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(cond + co + i);
+  }
+  if (p.gather) {
+    const long long gi = p.gidx[(long long)b * p.gidx_bstride + orow];
+    const float* gr = p.gather + gi * p.Cout_total + co;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __ldg(gr + i);
+  }
+  if (p.alpha != 1.f) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+  }
+  int nout = 16, oc = co;
+  if (p.gate) {   // commons.py:211-218 on interleaved (tanh, sigmoid) pairs
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = tanhf(v[2 * i]) * sigmoidf_(v[2 * i + 1]);
+    nout = 8; oc = co >> 1;
+  }
+  if (p.pre_slope != 1.f) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.pre_slope);
+  }
+  if (p.mask_pre && !valid) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  }
+  // fp32 side: channels-last rows (ldy32 / ldr32) or planar-vector planes
+  const size_t pitch_o = (size_t)p.Lp_out * 16;
+  const int ctot = p.gate ? p.Cout_total / 2 : p.Cout_total;
+  auto f32_ptr = [&](const float* base, int ld, int c) -> const float* {
+    if (p.f32_cl) return base + ((size_t)b * Lout + orow) * ld + c;
+    return reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(base) + (size_t)b * (ctot / 4) * pitch_o +
+                                          (size_t)(c / 4) * pitch_o + (size_t)(orow + p.padf) * 16);
+  };
+  const size_t cstep = p.f32_cl ? 4 : pitch_o / 4;   // floats between consecutive 4-channel groups
+  if (p.res32) {
+    const float* rp = f32_ptr(p.res32, p.ldr32, oc);
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4)
+      if (k4 * 4 < nout) {
+        const float4 q = *reinterpret_cast<const float4*>(rp + k4 * cstep);
+        if (p.res_mode == 2) {
+          v[k4 * 4 + 0] = q.x - v[k4 * 4 + 0]; v[k4 * 4 + 1] = q.y - v[k4 * 4 + 1];
+          v[k4 * 4 + 2] = q.z - v[k4 * 4 + 2]; v[k4 * 4 + 3] = q.w - v[k4 * 4 + 3];
+        } else {
+          v[k4 * 4 + 0] += q.x; v[k4 * 4 + 1] += q.y; v[k4 * 4 + 2] += q.z; v[k4 * 4 + 3] += q.w;
+        }
+      }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  float* yp = p.y32 ? const_cast<float*>(f32_ptr(p.y32, p.ldy32, oc)) : nullptr;
+  if (p.accum) {
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4)
+      if (k4 * 4 < nout) {
+        const float4 q = *reinterpret_cast<const float4*>(yp + k4 * cstep);
+        v[k4 * 4 + 0] += q.x; v[k4 * 4 + 1] += q.y; v[k4 * 4 + 2] += q.z; v[k4 * 4 + 3] += q.w;
+      }
+  }
+  if (p.div != 1.f) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] / p.div;
+  }
+  if (p.mask_post && !valid) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+  }
+  if (yp) {
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4)
+      if (k4 * 4 < nout)
+        *reinterpret_cast<float4*>(yp + k4 * cstep) = make_float4(v[k4 * 4 + 0], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+  }
+  if (p.y16) {
+    const bool obf = p.out_bf16 != 0;
+    const int ld16 = p.ldy16 ? p.ldy16 : ctot;
+    unsigned char* y16row = reinterpret_cast<unsigned char*>(p.y16) + (((size_t)b * Lout + orow) * ld16 + oc) * 2;
+    const bool z16 = p.mask16 && !valid;
+#pragma unroll
+    for (int k8 = 0; k8 < 2; ++k8)
+      if (k8 * 8 < nout) {
+        uint4 o;
+        o.x = pack2(obf, lrelu(v[k8 * 8 + 0], p.out_slope), lrelu(v[k8 * 8 + 1], p.out_slope));
+        o.y = pack2(obf, lrelu(v[k8 * 8 + 2], p.out_slope), lrelu(v[k8 * 8 + 3], p.out_slope));
+        o.z = pack2(obf, lrelu(v[k8 * 8 + 4], p.out_slope), lrelu(v[k8 * 8 + 5], p.out_slope));
+        o.w = pack2(obf, lrelu(v[k8 * 8 + 6], p.out_slope), lrelu(v[k8 * 8 + 7], p.out_slope));
+        if (z16) o = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(y16row + k8 * 16) = o;
+      }
+  }
+}
+
 __global__ void __launch_bounds__(kThreadsTC, 1)
 conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
   extern __shared__ unsigned char smem_raw[];
@@ -396,8 +510,9 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
     const int ew = warp - 2;                        // 0..7
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
     const int half = ew >> 2;                       // which half of the N columns
-    const int wc = p.N >= 32 ? p.N / 2 : p.N;       // columns per warp
-    const bool active = p.N >= 32 || half == 0;
+    const bool split = p.N >= 32 && (p.N / 2) % 16 == 0;
+    const int wc = split ? p.N / 2 : p.N;           // columns per warp
+    const bool active = split || half == 0;
     const size_t pitch_o = (size_t)p.Lp_out * 16;
     const long long Lout = (long long)p.Lj * p.out_stride;
     for (int t = 0; t < my_tiles; ++t) {
@@ -419,7 +534,11 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
         const int c_begin = half * wc;
         const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * p.N);
-        if (wc % 32 == 0) {
+        if (p.generic) {
+          const bool valid = p.out_len ? (orow < p.out_len[b]) : true;
+          for (int c0 = c_begin; c0 < c_begin + wc; c0 += 16)
+            epilogue_generic16(p, tbase + (uint32_t)c0, row_ok, valid, b, orow, nt * p.N + c0);
+        } else if (wc % 32 == 0) {
           for (int c0 = c_begin; c0 < c_begin + wc; c0 += 32)
             epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond);
         } else {
@@ -628,7 +747,8 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   {
     const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
     cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)d.L_in, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)d.Cin * 2 * (cuuint64_t)d.L_in};
+    const cuuint64_t ldx = (cuuint64_t)(d.generic && d.ldx16 ? d.ldx16 : d.Cin);
+    cuuint64_t strides[2] = {ldx * 2, ldx * 2 * (cuuint64_t)d.L_in};
     cuuint32_t box[3] = {(cuuint32_t)KBLK, (cuuint32_t)R, 1};
     cuuint32_t es[3] = {1, 1, 1};
     if (enc(&tmA, dt, 3, const_cast<void*>(d.x16), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

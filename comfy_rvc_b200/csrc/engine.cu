@@ -138,6 +138,7 @@ struct Plan {  // workspace carve-up for (B, T)
   float* stage[5];
   // tensor-core path: planar-vector buffers
   void* z16; void* pv16[5]; float* pv32[3];
+  void *phone16, *x16, *att16, *ffh16, *h16, *acts16, *skip16;   // fp16 MMA operands of enc_p / flow
   size_t bytes;
 };
 
@@ -186,6 +187,13 @@ Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws, int precision = RVC
       if (e > mxe) mxe = e;
     }
     p.z16 = bp.take<unsigned short>((size_t)B * C * pv_pitch_rows(T));
+    p.phone16 = bp.take<unsigned short>(BT * cf.feat_dim);
+    p.x16 = bp.take<unsigned short>(BT * H);
+    p.att16 = bp.take<unsigned short>(BT * H);
+    p.ffh16 = bp.take<unsigned short>(BT * cf.filter_channels);
+    p.h16 = bp.take<unsigned short>(BT * H);
+    p.acts16 = bp.take<unsigned short>(BT * H);
+    p.skip16 = bp.take<unsigned short>(BT * H);
     for (int i = 0; i < 5; ++i) p.pv16[i] = bp.take<unsigned short>(mxe);
     for (int i = 0; i < 3; ++i) p.pv32[i] = bp.take<float>(mxe);
   }
@@ -462,6 +470,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
                       f.gin_channels, ctx->n_cond, f.n_speakers, st),
      "cond_gemv");
 
+  if (!tc) {
   // ---------------- TextEncoder (models.py:43-58 / 90-105) -----------------------------------
   {
     ConvDesc d = base_desc();
@@ -581,6 +590,120 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
   }
   CK(tp.emit("z", z, sizeof(float) * BT * C), "tap");
 
+
+  } else {
+    // ====== TextEncoder + reverse flow with every contraction on tcgen05 (fp16 operands, fp32 epilogues) ======
+    auto W16h = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, 1, &ok); };
+    auto n_for = [](int cout) { for (int n = 256; n >= 16; n -= 16) if (cout % n == 0) return n; return 16; };
+    auto gen = [&](const void* x16, int Cin, const std::string& wname, const std::string& bname, int Cout) {
+      TcConvDesc d;
+      memset(&d, 0, sizeof(d));
+      d.padf = kPadF; d.ntaps = 1; d.dil = 1; d.G = 1; d.out_stride = 1; d.div = 1.f; d.out_slope = 1.f;
+      d.generic = 1; d.f32_cl = 1; d.alpha = 1.f; d.pre_slope = 1.f;
+      d.x16 = x16; d.L_in = T; d.Cin = Cin; d.w16 = W16h(wname); d.bias = W(bname);
+      d.N = n_for(Cout); d.Cout_total = Cout; d.Lj = T; d.Lp_out = pv_pitch_rows(T);
+      d.out_len = pl.len32;
+      return d;
+    };
+#define TCG(cls, d, what)                         \
+  do {                                            \
+    if (!ok) return RVCB200_ERR_MISSING;          \
+    CKC(cls, launch_conv_tc(d, B, st), what);     \
+  } while (0)
+    CKC(3, launch_cl32_to_cl16(phone, pl.phone16, (long long)BT * f.feat_dim, 1.f, false, st), "phone->fp16");
+    {  // x = lrelu((emb_phone(phone) + emb_pitch[pitch]) * sqrt(H)) * mask   models.py:92-100
+      TcConvDesc d = gen(pl.phone16, f.feat_dim, "enc.emb.w", "enc.emb.b", H);
+      d.gather = W("enc.emb_pitch"); d.gidx = pitch; d.gidx_bstride = T;
+      d.alpha = sqrtf((float)H); d.pre_slope = 0.1f; d.mask_post = 1; d.mask16 = 1;
+      d.y32 = pl.x; d.ldy32 = H; d.y16 = pl.x16;
+      TCG(6, d, "enc.emb(tc)");
+    }
+    const int kp = (f.enc_kernel - 1) / 2;
+    for (int l = 0; l < f.n_layers; ++l) {
+      {  // q|k|v (fp32, consumed by the banded attention kernel)
+        TcConvDesc d = gen(pl.x16, H, S("enc.%d.qkv.w", l), S("enc.%d.qkv.b", l), 3 * H);
+        d.y32 = pl.qkv; d.ldy32 = 3 * H;
+        TCG(6, d, "enc.qkv(tc)");
+      }
+      CKC(1, launch_attention_f32(pl.qkv, W(S("enc.%d.rel_k", l)), W(S("enc.%d.rel_v", l)), pl.len32, pl.att, B, T,
+                                  f.n_heads, H / f.n_heads, f.window_size, st),
+          "enc.attention");
+      CKC(3, launch_cl32_to_cl16(pl.att, pl.att16, (long long)BT * H, 1.f, false, st), "att->fp16");
+      {  // x + conv_o(att)
+        TcConvDesc d = gen(pl.att16, H, S("enc.%d.o.w", l), S("enc.%d.o.b", l), H);
+        d.res32 = pl.x; d.ldr32 = H; d.res_mode = 1; d.y32 = pl.xt; d.ldy32 = H;
+        TCG(6, d, "enc.o(tc)");
+      }
+      CKC(3, launch_layernorm(pl.xt, W(S("enc.%d.ln1.g", l)), W(S("enc.%d.ln1.b", l)), pl.x, BT, H, 1e-5f, st, pl.x16,
+                              pl.len32, T),
+          "enc.ln1");
+      {  // FFN conv_1 + ReLU; the fp16 copy is masked (it feeds conv_2(h * mask))
+        TcConvDesc d = gen(pl.x16, H, S("enc.%d.ffn1.w", l), S("enc.%d.ffn1.b", l), F);
+        d.ntaps = f.enc_kernel; d.g_off[0] = -kp; d.relu = 1; d.mask16 = 1; d.y16 = pl.ffh16;
+        TCG(6, d, "enc.ffn1(tc)");
+      }
+      {  // x + conv_2(h*mask)*mask
+        TcConvDesc d = gen(pl.ffh16, F, S("enc.%d.ffn2.w", l), S("enc.%d.ffn2.b", l), H);
+        d.ntaps = f.enc_kernel; d.g_off[0] = -kp; d.mask_pre = 1;
+        d.res32 = pl.x; d.ldr32 = H; d.res_mode = 1; d.y32 = pl.xt; d.ldy32 = H;
+        TCG(6, d, "enc.ffn2(tc)");
+      }
+      CKC(3, launch_layernorm(pl.xt, W(S("enc.%d.ln2.g", l)), W(S("enc.%d.ln2.b", l)), pl.x, BT, H, 1e-5f, st, pl.x16,
+                              pl.len32, T),
+          "enc.ln2");
+    }
+    CK(tp.emit("x_enc", pl.x, sizeof(float) * BT * H), "tap");
+    {  // stats = proj(x*mask)*mask
+      TcConvDesc d = gen(pl.x16, H, "enc.proj.w", "enc.proj.b", 2 * C);
+      d.mask_post = 1; d.y32 = stats; d.ldy32 = 2 * C;
+      TCG(6, d, "enc.proj(tc)");
+    }
+    CK(tp.emit("stats", stats, sizeof(float) * BT * 2 * C), "tap");
+    CKC(3, launch_zp_sample(stats, noise_zp, pl.len32, zp, B, T, C, st, z != zp ? z : nullptr, pl.z16), "zp_sample");
+    CK(tp.emit("z_p", zp, sizeof(float) * BT * C), "tap");
+    {
+      bool flipped = false;
+      const unsigned short* z16 = reinterpret_cast<const unsigned short*>(pl.z16);
+      for (int i = f.n_flows - 1; i >= 0; --i) {
+        flipped = !flipped;
+        const int in_off = flipped ? half : 0, out_off = half - in_off;
+        {  // h = pre(x0)*mask
+          TcConvDesc d = gen(z16 + in_off, half, S("flow.%d.pre.w", i), S("flow.%d.pre.b", i), H);
+          d.ldx16 = C; d.mask_post = 1; d.y32 = pl.h; d.ldy32 = H; d.y16 = pl.h16;
+          TCG(5, d, "flow.pre(tc)");
+        }
+        for (int j = 0; j < f.flow_wn_layers; ++j) {
+          {  // acts = gate(in_layer(h) + cond)
+            TcConvDesc d = gen(pl.h16, H, S("flow.%d.in.%d.w", i, j), S("flow.%d.in.%d.b", i, j), 2 * H);
+            d.ntaps = f.flow_kernel; d.g_off[0] = -(f.flow_kernel - 1) / 2;
+            d.cond = pl.cond + f.up_init_channels + (i * f.flow_wn_layers + j) * 2 * H; d.cond_bstride = ctx->n_cond;
+            d.gate = 1; d.y16 = pl.acts16;
+            TCG(5, d, "flow.in(tc)");
+          }
+          if (j < f.flow_wn_layers - 1) {  // h = (h + res)*mask
+            TcConvDesc d = gen(pl.acts16, H, S("flow.%d.rs.%d.res.w", i, j), S("flow.%d.rs.%d.res.b", i, j), H);
+            d.res32 = pl.h; d.ldr32 = H; d.res_mode = 1; d.mask_post = 1; d.y32 = pl.h; d.ldy32 = H; d.y16 = pl.h16;
+            TCG(5, d, "flow.res(tc)");
+          }
+          {  // output += skip; the last layer also emits the masked fp16 copy that feeds `post`
+            TcConvDesc d = gen(pl.acts16, H, S("flow.%d.rs.%d.skip.w", i, j), S("flow.%d.rs.%d.skip.b", i, j), H);
+            d.y32 = pl.skip; d.ldy32 = H; d.accum = j > 0;
+            if (j == f.flow_wn_layers - 1) { d.y16 = pl.skip16; d.mask16 = 1; }
+            TCG(5, d, "flow.skip(tc)");
+          }
+        }
+        {  // x1 = (x1 - post(out*mask)*mask)*mask, fp32 in place + fp16 copy into the z operand
+          TcConvDesc d = gen(pl.skip16, H, S("flow.%d.post.w", i), S("flow.%d.post.b", i), half);
+          d.mask_pre = 1; d.mask_post = 1;
+          d.res32 = z + out_off; d.ldr32 = C; d.res_mode = 2; d.y32 = z + out_off; d.ldy32 = C;
+          d.y16 = const_cast<unsigned short*>(z16) + out_off; d.ldy16 = C;
+          TCG(5, d, "flow.post(tc)");
+        }
+      }
+    }
+    CK(tp.emit("z", z, sizeof(float) * BT * C), "tap");
+#undef TCG
+  }
   // ---------------- NSF source (models.py:361-411, 455-467) -----------------------------------
   const long long Lout = (long long)T * ctx->upp;
   CKC(2, launch_sine_source(nsff0, noise_sine, pl.har, B, T, ctx->upp, f.sr, ctx->scalars["dec.src.lin_w"],
@@ -690,8 +813,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       return d;
     };
     const int LpT = pv_pitch_rows(T);
-    // z -> fp16 channels-last (conv_pre consumes z*mask; z is already masked)
-    CKC(3, launch_cl32_to_cl16(z, pl.z16, (long long)BT * C, 1.f, false, st), "z->fp16");
+    // pl.z16 already holds z (fp16, masked) from the flow's `post` epilogues
     void* IN16 = pl.pv16[0];
     void* X16 = pl.pv16[1];
     void* XT16 = pl.pv16[2];

@@ -1,4 +1,6 @@
 // Bandwidth-bound glue kernels of the synthesis path (channels-last fp32).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace rvc {
@@ -13,7 +15,7 @@ namespace {
 // ---- LayerNorm over contiguous channels: one warp per row (modules.py:25-28) ---------------
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* __restrict__ y, long long rows, int C,
-                                 float eps) {
+                                 float eps, __half* __restrict__ y16, const int* __restrict__ len, int T) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -32,7 +34,14 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   const float rstd = rsqrtf(q / (float)C + eps);
   float* yr = y + row * C;
   n = 0;
-  for (int c = lane; c < C; c += 32) { yr[c] = (v[n] - mean) * rstd * gamma[c] + beta[c]; ++n; }
+  // optional fp16 copy (the MMA operand of the next contraction), zeroed for rows >= len (x * x_mask)
+  const bool keep = !len || (int)(row % T) < len[row / T];
+  for (int c = lane; c < C; c += 32) {
+    const float o = (v[n] - mean) * rstd * gamma[c] + beta[c];
+    yr[c] = o;
+    if (y16) y16[row * C + c] = __float2half_rn(keep ? o : 0.f);
+    ++n;
+  }
 }
 
 __global__ void len_to_i32_kernel(const long long* len64, int* len32, int B, int T) {
@@ -65,7 +74,8 @@ __global__ void cond_gemv_kernel(const float* __restrict__ emb_g, const long lon
 
 // ---- prior sample: z_p = (m + exp(logs)*eps*0.66666)*mask, noise read channels-first --------
 __global__ void zp_sample_kernel(const float* __restrict__ stats, const float* __restrict__ noise,
-                                 const int* __restrict__ len, float* __restrict__ zp, int T, int C) {
+                                 const int* __restrict__ len, float* __restrict__ zp, int T, int C,
+                                 float* __restrict__ z, __half* __restrict__ z16) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -83,7 +93,11 @@ __global__ void zp_sample_kernel(const float* __restrict__ stats, const float* _
       const float* sr = stats + ((long long)b * T + t) * (2 * C);
       float m = sr[c], lg = sr[C + c];
       float v = m + expf(lg) * tile[tx][r] * 0.66666f;
-      zp[((long long)b * T + t) * C + c] = (t < L) ? v : 0.f;
+      const float o = (t < L) ? v : 0.f;
+      const long long oi = ((long long)b * T + t) * C + c;
+      zp[oi] = o;
+      if (z) z[oi] = o;
+      if (z16) z16[oi] = __float2half_rn(o);
     }
   }
 }
@@ -175,10 +189,11 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, int lds, float* 
 }  // namespace
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, long long rows, int C,
-                             float eps, cudaStream_t st) {
+                             float eps, cudaStream_t st, void* y16, const int* len, int T) {
   if (C > 256 || rows <= 0) return cudaErrorInvalidValue;
   const int wpb = 8;
-  layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, gamma, beta, y, rows, C, eps);
+  layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, gamma, beta, y, rows, C, eps,
+                                                                            reinterpret_cast<__half*>(y16), len, T > 0 ? T : 1);
   launch_counter().n++;
   return cudaGetLastError();
 }
@@ -198,9 +213,9 @@ cudaError_t launch_cond_gemv(const float* emb_g, const long long* sid, const flo
 }
 
 cudaError_t launch_zp_sample(const float* stats, const float* noise_cf, const int* len, float* zp, int B, int T, int C,
-                             cudaStream_t st) {
+                             cudaStream_t st, float* z, void* z16) {
   dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-  zp_sample_kernel<<<grid, dim3(32, 8), 0, st>>>(stats, noise_cf, len, zp, T, C);
+  zp_sample_kernel<<<grid, dim3(32, 8), 0, st>>>(stats, noise_cf, len, zp, T, C, z, reinterpret_cast<__half*>(z16));
   launch_counter().n++;
   return cudaGetLastError();
 }

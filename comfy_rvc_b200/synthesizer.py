@@ -173,8 +173,8 @@ class SynthesizerB200(nn.Module):
         lib = _lib.load()
         with torch.cuda.device(self._device):
             for name in tc_weight_names(self.cfg):
-                ladder = name.startswith("dec.pre") or name.startswith("dec.ups")
-                prec = "fp16" if ladder else self.precision
+                resblock = name.startswith("dec.rb.")
+                prec = self.precision if resblock else "fp16"      # ladder, text encoder and flow: always fp16
                 dtype = torch.float16 if prec == "fp16" else torch.bfloat16
                 t = pack_tc(self._packed[name].cpu(), dtype).to(self._device)
                 key = f"{name}.tc"

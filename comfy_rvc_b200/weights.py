@@ -179,15 +179,25 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
 TC_KB, TC_N_MAX = 64, 256
 
 
+def tc_n_for(cout: int) -> int:
+    """MMA N tile: the largest multiple of 16 <= 256 dividing C_out (same rule as csrc/engine.cu)."""
+    for n in range(TC_N_MAX, 15, -16):
+        if cout % n == 0:
+            return n
+    raise ValueError(cout)
+
+
 def pack_tc(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """[G][taps][C_in][C_out] (or [taps][C_in][C_out]) fp32 -> [G][C_out/N][taps][ceil(C_in/64)][N][64] 16-bit.
 
     One (tap, k-block) slice is an [N][64] K-major matrix (input channels contiguous, zero-padded to
     64) that TMA loads into SWIZZLE_128B shared memory as the tcgen05 B operand (csrc/conv_tc.cu)."""
-    if w.dim() == 3:
+    if w.dim() == 2:
+        w = w[None, None]
+    elif w.dim() == 3:
         w = w.unsqueeze(0)
     G, taps, cin, cout = w.shape
-    N = min(TC_N_MAX, cout)
+    N = tc_n_for(cout)
     nkb = (cin + TC_KB - 1) // TC_KB
     assert cout % N == 0 and N % 16 == 0, (cin, cout)
     if nkb * TC_KB != cin:
@@ -198,7 +208,15 @@ def pack_tc(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 
 def tc_weight_names(cfg: SynthConfig):
     """Packed fp32 tensors that also get a 16-bit `.tc` image (the decoder's dense convolutions)."""
-    names = ["dec.pre.w"]
+    names = ["dec.pre.w", "enc.emb.w", "enc.proj.w"]
+    for l in range(cfg.n_layers):
+        names += [f"enc.{l}.qkv.w", f"enc.{l}.o.w", f"enc.{l}.ffn1.w", f"enc.{l}.ffn2.w"]
+    for i in range(cfg.n_flows):
+        names += [f"flow.{i}.pre.w", f"flow.{i}.post.w"]
+        for j in range(cfg.flow_wn_layers):
+            names += [f"flow.{i}.in.{j}.w", f"flow.{i}.rs.{j}.skip.w"]
+            if j < cfg.flow_wn_layers - 1:
+                names.append(f"flow.{i}.rs.{j}.res.w")
     nk = cfg.num_kernels
     for i in range(cfg.num_upsamples):
         names.append(f"dec.ups.{i}.w")

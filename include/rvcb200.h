@@ -174,6 +174,17 @@ typedef struct rvcb200_tc_conv_desc {
   int32_t in_bf16, out_bf16;   /* operand format of x16/w16 and storage format of y16: 0 = fp16, 1 = bf16 */
   int32_t a_mode;
   int32_t batch, na_stages, nb_stages, b_stationary; /* filled in by the launcher */
+  /* ---- generic epilogue (text encoder / flow); all zero = the lean decoder epilogue ---- */
+  int32_t generic;             /* 1: use the fields below */
+  int32_t ldx16;               /* row stride (elements) of x16 when it is a channel slice (0 = Cin) */
+  int32_t f32_cl;              /* 1: y32 / res32 are channels-last with row strides ldy32 / ldr32 (floats) */
+  int32_t ldy32, ldr32, ldy16; /* ldy16: row stride (elements) of y16 (0 = Cout_total, or Cout_total/2 with gate) */
+  const float* gather; const int64_t* gidx; int64_t gidx_bstride;  /* += gather[gidx[b][row]][co] */
+  float alpha;                 /* scale after bias/cond/gather */
+  float pre_slope;             /* leaky slope applied to the value itself (1 = none) */
+  int32_t relu, gate;          /* gate: interleaved (tanh, sigmoid) column pairs -> C_out/2 outputs */
+  int32_t res_mode;            /* 1: v + res, 2: res - v */
+  int32_t mask_pre, mask_post, mask16; const int32_t* out_len;    /* rows >= out_len[b] -> 0 */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 

@@ -111,9 +111,15 @@ def test_infer_tensor_core_path_snr(name, precision, min_snr):
     from tests.test_parity_gpu import build_net
     cfg, sd, (phone, lens, pitch_, pitchf, sid), noise, gold = load_golden(name)
     net = build_net(cfg, sd, precision)
-    taps = {f"dec.stage.{i}": None for i in range(cfg.num_upsamples)}
-    o = net.infer(phone.cuda(), lens.cuda(), pitch_.cuda(), pitchf.cuda(), sid.cuda(), noise=noise, taps=taps)[0]
+    taps = {n: None for n in ["x_enc", "stats", "z_p", "z"] + [f"dec.stage.{i}" for i in range(cfg.num_upsamples)]}
+    o, _, (z, z_p, m_p, logs_p) = net.infer(phone.cuda(), lens.cuda(), pitch_.cuda(), pitchf.cuda(), sid.cuda(),
+                                            noise=noise, taps=taps)
     torch.cuda.synchronize()
+    for key, got in (("m_p", m_p), ("logs_p", logs_p), ("z_p", z_p), ("z", z)):
+        ref = gold[key]
+        rel = np.abs(got.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-9)
+        print(f"  {name} {precision} {key}: max rel err {rel:.2e}")
+        assert rel < 3e-2, key
     o_np = o[:, 0].cpu().numpy()
     T = phone.shape[1]
     worst = 1e9
