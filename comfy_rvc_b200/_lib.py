@@ -93,6 +93,8 @@ SYMBOLS = {
                                          C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "rvcb200_op_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "rvcb200_op_attention_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "rvcb200_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                        C.c_float, C.c_void_p]),
 }

@@ -1,0 +1,480 @@
+// Windowed relative-position self-attention on tcgen05 / TMEM (fp16 operands, fp32 softmax + accumulate).
+//
+// Restates /root/reference/lib/infer_pack/attentions.py:222-270 in the banded form of SURVEY.md App. D:
+//     S[i][j] = q~_i . k_j + [|j-i| <= w] q~_i . Ek[j-i+w]        (q~ = q / sqrt(dk), folded into the q weights)
+//     P = softmax_j(S) over keys j < len;   O_i = sum_j P[i][j] v_j + sum_{|j-i|<=w} P[i][j] Ev[j-i+w]
+//
+// One CTA = 128 queries of one (batch, head).  All four contractions run on the tensor core:
+//     R  = Q Ek^T           [128 x 32]   once          (the 21 relative-key logits of every query)
+//     S  = Q K^T            [128 x 64]   per key tile, twice (pass 1: row max, pass 2: probabilities)
+//     O += P V              [128 x 96]   per key tile (pass 2)
+//     O += Pband Ev         [128 x 96]   once          (Pband[i][r] = P[i][i+r-w], gathered by the softmax warps)
+// Two passes over the keys avoid rescaling the TMEM accumulator (the extra Q K^T costs 37 % more MMA work on
+// a kernel that is bound by the exp/TMEM traffic of the softmax warps anyway).
+//
+// Operands (all K-major, TMA + SWIZZLE_128B): qk16 [B][T][512] = q(h0|h1) k(h0|h1), 128 channels per head
+// (96 + zero pad); vt16 [B*heads][128][Tp] = V transposed (keys contiguous); ek16 [32][128]; evt16 [128][64].
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax (thread = query row = TMEM lane).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace rvc {
+namespace {
+
+constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 3, MAXREL = 21;
+constexpr int kThreadsAtt = 192;
+// TMEM columns
+constexpr uint32_t TM_S = 0, TM_O = 64, TM_R = 160, TM_COLS = 256;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = s_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma3(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(s_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(s_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ bool elect1() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc) : "memory");
+}
+// SWIZZLE_128B K-major descriptor halves: lo = start>>4 | LBO(1)<<16 ; hi = SBO(1024>>4) | version 1<<14 | SW128 (2)<<29
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t idesc_f16(int N) {   // D=F32, A=B=F16, K-major, M=128
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct AttSmem {                        // 1024-byte aligned tiles, all [rows][128 B] swizzled
+  unsigned char q[2][BQ * 128];         // 2 k-blocks of 64 channels
+  unsigned char k[NSTG][2][BKV * 128];
+  unsigned char v[NSTG][DKP * 128];     // V^T tile: 128 d-rows x 64 keys
+  unsigned char p[BQ * 128];            // probabilities, 64 keys per row
+  unsigned char pband[BQ * 128];        // P[i][i+r-w], r < 21 (columns >= 21 stay zero)
+  unsigned char ek[2][32 * 128];
+  unsigned char evt[DKP * 128];
+  float rtab[BQ * 24];                  // relative-key logits per query row (dynamic indexing)
+  uint64_t bars[32];
+  uint32_t tmem_slot;
+};
+
+struct AttArgs {
+  const int* len;
+  __half* out;          // [B][T][H]
+  int T, n_heads, window, H;
+};
+
+__global__ void __launch_bounds__(kThreadsAtt, 1)
+attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmEk,
+                    const __grid_constant__ CUtensorMap tmEv) {
+  extern __shared__ unsigned char smem_raw[];
+  AttSmem& sm = *reinterpret_cast<AttSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  const int L = min(a.len ? a.len[b] : a.T, a.T);
+  const int nrel = 2 * a.window + 1;
+
+  if (q0 >= L) {   // padding-only query tile: zeros (uniform early exit, nothing allocated yet)
+    for (int idx = threadIdx.x; idx < BQ * (DKV / 8); idx += kThreadsAtt) {
+      const int i = idx / (DKV / 8), c = idx % (DKV / 8);
+      if (q0 + i < a.T)
+        *reinterpret_cast<uint4*>(a.out + ((size_t)b * a.T + q0 + i) * a.H + h * DKV + c * 8) = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+  const int ntiles = (L + BKV - 1) / BKV;
+
+  uint64_t* q_full = &sm.bars[0];
+  uint64_t* k_full = &sm.bars[1];        // [NSTG]
+  uint64_t* k_empty = &sm.bars[4];       // [NSTG]
+  uint64_t* v_full = &sm.bars[7];        // [NSTG]
+  uint64_t* v_empty = &sm.bars[10];      // [NSTG]
+  uint64_t* r_full = &sm.bars[13];
+  uint64_t* s_full = &sm.bars[14];
+  uint64_t* s_empty = &sm.bars[15];      // 4 softmax warps
+  uint64_t* p_full = &sm.bars[16];       // 4 softmax warps
+  uint64_t* p_empty = &sm.bars[17];
+  uint64_t* pb_full = &sm.bars[18];      // 4 softmax warps
+  uint64_t* o_full = &sm.bars[19];
+
+  if (threadIdx.x == 0) {
+    bar_init(q_full, 1);
+    for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); bar_init(&v_full[i], 1); bar_init(&v_empty[i], 1); }
+    bar_init(r_full, 1); bar_init(s_full, 1); bar_init(s_empty, 4); bar_init(p_full, 4); bar_init(p_empty, 1);
+    bar_init(pb_full, 4); bar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&sm.tmem_slot)), "r"(TM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // zero the Pband tile (generic proxy) before anybody can use it
+  for (int idx = threadIdx.x; idx < BQ * 8; idx += kThreadsAtt) reinterpret_cast<uint4*>(sm.pband)[idx] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = sm.tmem_slot;
+
+  if (warp == 0) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0) {
+      bar_expect(q_full, 2 * BQ * 128 + 2 * 32 * 128 + DKP * 128);
+      for (int kb = 0; kb < 2; ++kb) tma3(sm.q[kb], &tmQ, h * DKP + kb * 64, q0, b, q_full);
+      for (int kb = 0; kb < 2; ++kb) tma2(sm.ek[kb], &tmEk, kb * 64, 0, q_full);
+      tma2(sm.evt, &tmEv, 0, 0, q_full);
+      int ks = 0, vs = 0;
+      uint32_t kp = 1, vp = 1;
+      for (int pass = 0; pass < 2; ++pass)
+        for (int t = 0; t < ntiles; ++t) {
+          const int j0 = t * BKV;
+          bar_wait(&k_empty[ks], kp);
+          bar_expect(&k_full[ks], 2 * BKV * 128);
+          for (int kb = 0; kb < 2; ++kb) tma3(sm.k[ks][kb], &tmK, a.n_heads * DKP + h * DKP + kb * 64, j0, b, &k_full[ks]);
+          if (++ks == NSTG) { ks = 0; kp ^= 1; }
+          if (pass == 1) {
+            bar_wait(&v_empty[vs], vp);
+            bar_expect(&v_full[vs], DKP * 128);
+            tma3(sm.v[vs], &tmV, j0, 0, b * a.n_heads + h, &v_full[vs]);
+            if (++vs == NSTG) { vs = 0; vp ^= 1; }
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ======================================= MMA issuer =========================================
+    const uint32_t id_s = idesc_f16(BKV), id_o = idesc_f16(DKV), id_r = idesc_f16(32);
+    const uint32_t q_lo0 = desc_lo(s_u32(sm.q[0])), q_lo1 = desc_lo(s_u32(sm.q[1]));
+    bar_wait(q_full, 0);
+    fence_after();
+    if (elect1()) {   // R = Q Ek^T : K = 96 = 4 + 2 MMAs
+      uint32_t acc = 0;
+      for (int ks = 0; ks < 6; ++ks) {
+        const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
+        const uint32_t b_lo = desc_lo(s_u32(sm.ek[ks >> 2])) + 2u * (ks & 3);
+        mma_f16(tmem + TM_R, a_lo, b_lo, kDescHi, id_r, acc);
+        acc = 1;
+      }
+      commit(r_full);
+    }
+    __syncwarp();
+    int ks_ = 0, vs_ = 0;
+    uint32_t kp = 0, vp = 0, sp = 1, pp = 0;
+    uint32_t o_acc = 0;
+    int it = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int t = 0; t < ntiles; ++t, ++it) {
+        bar_wait(&k_full[ks_], kp);
+        bar_wait(s_empty, sp);            // softmax has read the previous S tile out of TMEM
+        sp ^= 1;
+        fence_after();
+        if (elect1()) {
+          uint32_t acc = 0;
+          for (int ks = 0; ks < 6; ++ks) {
+            const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
+            const uint32_t b_lo = desc_lo(s_u32(sm.k[ks_][ks >> 2])) + 2u * (ks & 3);
+            mma_f16(tmem + TM_S, a_lo, b_lo, kDescHi, id_s, acc);
+            acc = 1;
+          }
+          commit(s_full);
+          commit(&k_empty[ks_]);
+        }
+        __syncwarp();
+        if (++ks_ == NSTG) { ks_ = 0; kp ^= 1; }
+        if (pass == 1) {
+          bar_wait(p_full, pp);           // probabilities of this tile are in smem
+          pp ^= 1;
+          bar_wait(&v_full[vs_], vp);
+          fence_after();
+          if (elect1()) {
+            const uint32_t p_lo = desc_lo(s_u32(sm.p)), v_lo = desc_lo(s_u32(sm.v[vs_]));
+            for (int ks = 0; ks < BKV / 16; ++ks) {
+              mma_f16(tmem + TM_O, p_lo + 2u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
+              o_acc = 1;
+            }
+            commit(p_empty);
+            commit(&v_empty[vs_]);
+          }
+          __syncwarp();
+          o_acc = 1;
+          if (++vs_ == NSTG) { vs_ = 0; vp ^= 1; }
+        }
+      }
+    // O += Pband Ev  (K = 32: two MMAs)
+    bar_wait(pb_full, 0);
+    fence_after();
+    if (elect1()) {
+      const uint32_t p_lo = desc_lo(s_u32(sm.pband)), e_lo = desc_lo(s_u32(sm.evt));
+      for (int ks = 0; ks < 2; ++ks) mma_f16(tmem + TM_O, p_lo + 2u * ks, e_lo + 2u * ks, kDescHi, id_o, 1u);
+      commit(o_full);
+    }
+    __syncwarp();
+  } else {
+    // ======================================= softmax warps ======================================
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;                     // TMEM lane = query row in the tile
+    const int qi = q0 + row;
+    const uint32_t lane_base = ((uint32_t)(qd * 32) << 16);
+    // relative-key logits of this row -> smem (dynamic indexing by key offset)
+    bar_wait(r_full, 0);
+    fence_after();
+    {
+      float rv[32];
+      tmem_ld32(tmem + lane_base + TM_R, rv);
+#pragma unroll
+      for (int r = 0; r < 24; ++r) sm.rtab[row * 24 + r] = rv[r];
+    }
+    float mx = -INFINITY, lsum = 0.f;
+    uint32_t sfp = 0, pep = 1;
+    const bool band_any_lo = true;
+    (void)band_any_lo;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int t = 0; t < ntiles; ++t) {
+        const int j0 = t * BKV;
+        bar_wait(s_full, sfp);
+        sfp ^= 1;
+        fence_after();
+        float s[BKV];
+        tmem_ld32(tmem + lane_base + TM_S, s);
+        tmem_ld32(tmem + lane_base + TM_S + 32, s + 32);
+        fence_before();
+        __syncwarp();
+        if (lane == 0) bar_arrive(s_empty);             // S is in registers: the next Q K^T may overwrite TMEM
+        const bool band = j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window;
+        if (band) {
+#pragma unroll
+          for (int c = 0; c < BKV; ++c) {
+            const int r = j0 + c - qi + a.window;
+            if ((unsigned)r < (unsigned)nrel) s[c] += sm.rtab[row * 24 + r];
+          }
+        }
+        if (j0 + BKV > L) {
+#pragma unroll
+          for (int c = 0; c < BKV; ++c)
+            if (j0 + c >= L) s[c] = -INFINITY;
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int c = 0; c < BKV; ++c) mx = fmaxf(mx, s[c]);
+        } else {
+          // probabilities (fp16) -> swizzled K-major smem tile; also harvest the band for the Ev term
+          uint32_t pk[BKV / 2];
+#pragma unroll
+          for (int c = 0; c < BKV; c += 2) {
+            const float p0 = __expf(s[c] - mx), p1 = __expf(s[c + 1] - mx);
+            lsum += p0 + p1;
+            __half2 hp = __floats2half2_rn(p0, p1);
+            pk[c / 2] = *reinterpret_cast<uint32_t*>(&hp);
+          }
+          if (band) {
+#pragma unroll
+            for (int c = 0; c < BKV; ++c) {
+              const int r = j0 + c - qi + a.window;
+              if ((unsigned)r < (unsigned)nrel) {
+                const uint32_t w = pk[c / 2];
+                const unsigned short hv = (c & 1) ? (unsigned short)(w >> 16) : (unsigned short)(w & 0xffffu);
+                *reinterpret_cast<unsigned short*>(sm.pband + row * 128 + (((r >> 3) ^ (row & 7)) << 4) + (r & 7) * 2) = hv;
+              }
+            }
+          }
+          bar_wait(p_empty, pep);                       // the previous P V MMA has finished reading sm.p
+          pep ^= 1;
+#pragma unroll
+          for (int cc = 0; cc < BKV / 8; ++cc)
+            *reinterpret_cast<uint4*>(sm.p + row * 128 + ((cc ^ (row & 7)) << 4)) =
+                make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) bar_arrive(p_full);
+        }
+      }
+    // band tile complete -> final MMA, then normalise and store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) bar_arrive(pb_full);
+    bar_wait(o_full, 0);
+    fence_after();
+    const bool valid = qi < L;
+    const float inv = valid ? 1.f / lsum : 0.f;
+    __half* orow = a.out + ((size_t)b * a.T + qi) * a.H + h * DKV;
+#pragma unroll
+    for (int c0 = 0; c0 < DKV; c0 += 32) {
+      float o[32];
+      tmem_ld32(tmem + lane_base + TM_O + c0, o);
+      if (qi < a.T) {
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+          uint4 w;
+          __half2 h0 = __floats2half2_rn(o[c8 * 8 + 0] * inv, o[c8 * 8 + 1] * inv);
+          __half2 h1 = __floats2half2_rn(o[c8 * 8 + 2] * inv, o[c8 * 8 + 3] * inv);
+          __half2 h2 = __floats2half2_rn(o[c8 * 8 + 4] * inv, o[c8 * 8 + 5] * inv);
+          __half2 h3 = __floats2half2_rn(o[c8 * 8 + 6] * inv, o[c8 * 8 + 7] * inv);
+          w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+          w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(orow + c0 + c8 * 8) = w;
+        }
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS));
+  }
+}
+
+// V part of the fused q|k|v projection -> V^T per (batch, head): vt[b*heads+h][d][t], keys contiguous
+__global__ void transpose_v_kernel(const __half* __restrict__ qkv16, __half* __restrict__ vt, int T, int Tp, int ld, int voff,
+                                   int n_heads) {
+  __shared__ __half tile[32][34];
+  const int bh = blockIdx.z, b = bh / n_heads, h = bh % n_heads;
+  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r;
+    tile[r][tx] = t < T ? qkv16[((size_t)b * T + t) * ld + voff + h * DKP + d0 + tx] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + tx;
+    if (t < Tp) vt[((size_t)bh * DKP + d0 + r) * Tp + t] = tile[tx][r];
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn att_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+bool make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+              const cuuint32_t* box) {
+  cuuint32_t es[3] = {1, 1, 1};
+  return att_encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// qkv16: [B][T][3*heads*128] fp16 (q | k | v, 128 channels per head, q pre-scaled); vt: scratch [B*heads][128][Tp];
+// ek16 [32][128], evt16 [128][64]; out: [B][T][heads*96] fp16.
+cudaError_t launch_attention_tc(const void* qkv16, void* vt, const void* ek16, const void* evt16, const int* len, void* out,
+                                int B, int T, int n_heads, int dk, int window, cudaStream_t st) {
+  if (dk != DKV || 2 * window + 1 > MAXREL || B <= 0 || T <= 0 || n_heads < 1) return cudaErrorInvalidValue;
+  if (!att_encode_tiled()) return cudaErrorNotSupported;
+  const int ld = 3 * n_heads * DKP;
+  const int Tp = (T + 7) & ~7;
+  {
+    dim3 grid((Tp + 31) / 32, DKP / 32, B * n_heads);
+    transpose_v_kernel<<<grid, dim3(32, 8), 0, st>>>(reinterpret_cast<const __half*>(qkv16), reinterpret_cast<__half*>(vt), T, Tp,
+                                                     ld, 2 * n_heads * DKP, n_heads);
+    launch_counter().n++;
+  }
+  CUtensorMap tmQ, tmK, tmV, tmEk, tmEv;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)(2 * n_heads * DKP), (cuuint64_t)T, (cuuint64_t)B};   // only the q|k columns are visible
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)T};
+    cuuint32_t boxq[3] = {64, BQ, 1}, boxk[3] = {64, BKV, 1};
+    if (!make_map(&tmQ, qkv16, 3, dims, strides, boxq) || !make_map(&tmK, qkv16, 3, dims, strides, boxk)) return cudaErrorInvalidValue;
+    cuuint64_t vd[3] = {(cuuint64_t)T, (cuuint64_t)DKP, (cuuint64_t)(B * n_heads)};          // keys >= T read as zero
+    cuuint64_t vs[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)Tp * 2 * DKP};
+    cuuint32_t boxv[3] = {BKV, DKP, 1};
+    if (!make_map(&tmV, vt, 3, vd, vs, boxv)) return cudaErrorInvalidValue;
+    cuuint64_t ekd[2] = {DKP, 32}, eks[1] = {DKP * 2};
+    cuuint32_t boxek[2] = {64, 32};
+    if (!make_map(&tmEk, ek16, 2, ekd, eks, boxek)) return cudaErrorInvalidValue;
+    cuuint64_t evd[2] = {64, DKP}, evs[1] = {64 * 2};
+    cuuint32_t boxev[2] = {64, DKP};
+    if (!make_map(&tmEv, evt16, 2, evd, evs, boxev)) return cudaErrorInvalidValue;
+  }
+  const size_t smem = sizeof(AttSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  AttArgs a;
+  a.len = len; a.out = reinterpret_cast<__half*>(out); a.T = T; a.n_heads = n_heads; a.window = window; a.H = n_heads * DKV;
+  dim3 grid((T + BQ - 1) / BQ, n_heads, B);
+  attention_tc_kernel<<<grid, kThreadsAtt, smem, st>>>(a, tmQ, tmK, tmV, tmEk, tmEv);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+}  // namespace rvc

@@ -21,4 +21,8 @@ cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int
                                 int padf, float slope, cudaStream_t st);
 cudaError_t launch_pv32_to_cl(const void* src, float* y, int B, long long L, int C, int Lp, int padf, cudaStream_t st);
 
+// tcgen05 flash attention with banded relative-position terms (attention_tc.cu)
+cudaError_t launch_attention_tc(const void* qkv16, void* vt, const void* ek16, const void* evt16, const int* len, void* out,
+                                int B, int T, int n_heads, int dk, int window, cudaStream_t st);
+
 }  // namespace rvc

@@ -139,6 +139,7 @@ struct Plan {  // workspace carve-up for (B, T)
   // tensor-core path: planar-vector buffers
   void* z16; void* pv16[5]; float* pv32[3];
   void *phone16, *x16, *att16, *ffh16, *h16, *acts16, *skip16;   // fp16 MMA operands of enc_p / flow
+  void *qkv16, *vt16;                                            // padded q|k|v and V^T for the tcgen05 attention
   size_t bytes;
 };
 
@@ -194,6 +195,8 @@ Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws, int precision = RVC
     p.h16 = bp.take<unsigned short>(BT * H);
     p.acts16 = bp.take<unsigned short>(BT * H);
     p.skip16 = bp.take<unsigned short>(BT * H);
+    p.qkv16 = bp.take<unsigned short>(BT * 3 * cf.n_heads * 128);
+    p.vt16 = bp.take<unsigned short>((size_t)B * cf.n_heads * 128 * ((T + 7) & ~7));
     for (int i = 0; i < 5; ++i) p.pv16[i] = bp.take<unsigned short>(mxe);
     for (int i = 0; i < 3; ++i) p.pv32[i] = bp.take<float>(mxe);
   }
@@ -594,6 +597,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
   } else {
     // ====== TextEncoder + reverse flow with every contraction on tcgen05 (fp16 operands, fp32 epilogues) ======
     auto W16h = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, 1, &ok); };
+    static const bool tc_attention = [] { const char* e = getenv("RVCB200_TC_ATTENTION"); return e ? atoi(e) != 0 : true; }();
     auto n_for = [](int cout) { for (int n = 256; n >= 16; n -= 16) if (cout % n == 0) return n; return 16; };
     auto gen = [&](const void* x16, int Cin, const std::string& wname, const std::string& bname, int Cout) {
       TcConvDesc d;
@@ -620,15 +624,28 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     }
     const int kp = (f.enc_kernel - 1) / 2;
     for (int l = 0; l < f.n_layers; ++l) {
-      {  // q|k|v (fp32, consumed by the banded attention kernel)
-        TcConvDesc d = gen(pl.x16, H, S("enc.%d.qkv.w", l), S("enc.%d.qkv.b", l), 3 * H);
-        d.y32 = pl.qkv; d.ldy32 = 3 * H;
-        TCG(6, d, "enc.qkv(tc)");
+      if (tc_attention) {
+        {  // q|k|v, 128 channels per head (96 + zero pad), q pre-scaled by 1/sqrt(dk): fp16 operands of the attention
+          TcConvDesc d = gen(pl.x16, H, S("enc.%d.qkvp.w", l), S("enc.%d.qkvp.b", l), 3 * f.n_heads * 128);
+          d.y16 = pl.qkv16;
+          TCG(6, d, "enc.qkv(tc)");
+        }
+        if (!ok) return RVCB200_ERR_MISSING;
+        CKC(1, launch_attention_tc(pl.qkv16, pl.vt16, T16(ctx, S("enc.%d.ek16", l), 32 * 128, 1, &ok),
+                                   T16(ctx, S("enc.%d.evt16", l), 128 * 64, 1, &ok), pl.len32, pl.att16, B, T, f.n_heads,
+                                   H / f.n_heads, f.window_size, st),
+            "enc.attention(tc)");
+      } else {
+        {  // q|k|v (fp32, consumed by the CUDA-core banded attention kernel)
+          TcConvDesc d = gen(pl.x16, H, S("enc.%d.qkv.w", l), S("enc.%d.qkv.b", l), 3 * H);
+          d.y32 = pl.qkv; d.ldy32 = 3 * H;
+          TCG(6, d, "enc.qkv(tc)");
+        }
+        CKC(1, launch_attention_f32(pl.qkv, W(S("enc.%d.rel_k", l)), W(S("enc.%d.rel_v", l)), pl.len32, pl.att, B, T,
+                                    f.n_heads, H / f.n_heads, f.window_size, st),
+            "enc.attention");
+        CKC(3, launch_cl32_to_cl16(pl.att, pl.att16, (long long)BT * H, 1.f, false, st), "att->fp16");
       }
-      CKC(1, launch_attention_f32(pl.qkv, W(S("enc.%d.rel_k", l)), W(S("enc.%d.rel_v", l)), pl.len32, pl.att, B, T,
-                                  f.n_heads, H / f.n_heads, f.window_size, st),
-          "enc.attention");
-      CKC(3, launch_cl32_to_cl16(pl.att, pl.att16, (long long)BT * H, 1.f, false, st), "att->fp16");
       {  // x + conv_o(att)
         TcConvDesc d = gen(pl.att16, H, S("enc.%d.o.w", l), S("enc.%d.o.b", l), H);
         d.res32 = pl.x; d.ldr32 = H; d.res_mode = 1; d.y32 = pl.xt; d.ldy32 = H;
@@ -944,6 +961,13 @@ int rvcb200_op_attention_f32(const float* qkv, const float* rel_k, const float* 
                              int32_t B, int32_t T, int32_t n_heads, int32_t dk, int32_t window, void* stream) {
   cudaError_t e = launch_attention_f32(qkv, rel_k, rel_v, len, out, B, T, n_heads, dk, window,
                                        reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int rvcb200_op_attention_tc(const void* qkv16, void* vt, const void* ek16, const void* evt16, const int32_t* len, void* out,
+                            int32_t B, int32_t T, int32_t n_heads, int32_t dk, int32_t window, void* stream) {
+  cudaError_t e = launch_attention_tc(qkv16, vt, ek16, evt16, len, out, B, T, n_heads, dk, window,
+                                      reinterpret_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 

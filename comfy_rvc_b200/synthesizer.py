@@ -181,6 +181,12 @@ class SynthesizerB200(nn.Module):
                 self._packed[f"{key}#{self.precision}"] = t          # keep alive; the engine holds the pointer
                 _lib.check(lib.rvcb200_set_tensor(self._ctx, key.encode(), C.c_void_p(t.data_ptr()), t.numel(),
                                                   _lib.PREC[prec]), self._ctx, key)
+            for l in range(self.cfg.n_layers):          # fp16 relative-position tables of the tcgen05 attention
+                for nm in (f"enc.{l}.ek16", f"enc.{l}.evt16"):
+                    t = self._packed[nm].to(torch.float16).contiguous()
+                    self._packed[nm + "#h"] = t
+                    _lib.check(lib.rvcb200_set_tensor(self._ctx, nm.encode(), C.c_void_p(t.data_ptr()), t.numel(), 1),
+                               self._ctx, nm)
             _lib.check(lib.rvcb200_finalize(self._ctx), self._ctx, "finalize")
         self._tc_done = {self.precision}      # one `.tc` image per name: switching precision re-registers
 

@@ -15,6 +15,7 @@ tensors in the layouts the CUDA kernels consume, registered by name with the C A
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Tuple
 
 import torch
@@ -91,6 +92,28 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
         a = f"enc_p.encoder.attn_layers.{l}"
         P[f"enc.{l}.qkv.w"] = torch.cat([w[f"{a}.conv_{n}.weight"][:, :, 0].t() for n in "qkv"], dim=1).contiguous()
         P[f"enc.{l}.qkv.b"] = torch.cat([w[f"{a}.conv_{n}.bias"] for n in "qkv"]).contiguous()
+        # tensor-core attention operands: q|k|v with 128 channels per head (96 + zero pad), q pre-scaled by
+        # 1/sqrt(dk) (attentions.py:229); relative tables as K-major fp16 matrices
+        nh, dk = cfg.n_heads, H // cfg.n_heads
+        wp = torch.zeros(H, 3 * nh * 128)
+        bp = torch.zeros(3 * nh * 128)
+        for pi, n in enumerate("qkv"):
+            wn = w[f"{a}.conv_{n}.weight"][:, :, 0].t()                       # [H_in][H_out]
+            bn = w[f"{a}.conv_{n}.bias"]
+            sc = 1.0 / math.sqrt(dk) if n == "q" else 1.0
+            for h in range(nh):
+                c0 = (pi * nh + h) * 128
+                wp[:, c0:c0 + dk] = wn[:, h * dk:(h + 1) * dk] * sc
+                bp[c0:c0 + dk] = bn[h * dk:(h + 1) * dk] * sc
+        P[f"enc.{l}.qkvp.w"] = wp.contiguous()
+        P[f"enc.{l}.qkvp.b"] = bp.contiguous()
+        nrel = 2 * cfg.window_size + 1
+        ek = torch.zeros(32, 128)
+        ek[:nrel, :dk] = w[f"{a}.emb_rel_k"][0]
+        evt = torch.zeros(128, 64)
+        evt[:dk, :nrel] = w[f"{a}.emb_rel_v"][0].t()
+        P[f"enc.{l}.ek16"] = ek
+        P[f"enc.{l}.evt16"] = evt
         P[f"enc.{l}.rel_k"] = w[f"{a}.emb_rel_k"][0].contiguous()            # heads_share -> [2w+1][dk]
         P[f"enc.{l}.rel_v"] = w[f"{a}.emb_rel_v"][0].contiguous()
         P[f"enc.{l}.o.w"] = w[f"{a}.conv_o.weight"][:, :, 0].t().contiguous()
@@ -210,7 +233,7 @@ def tc_weight_names(cfg: SynthConfig):
     """Packed fp32 tensors that also get a 16-bit `.tc` image (the decoder's dense convolutions)."""
     names = ["dec.pre.w", "enc.emb.w", "enc.proj.w"]
     for l in range(cfg.n_layers):
-        names += [f"enc.{l}.qkv.w", f"enc.{l}.o.w", f"enc.{l}.ffn1.w", f"enc.{l}.ffn2.w"]
+        names += [f"enc.{l}.qkv.w", f"enc.{l}.qkvp.w", f"enc.{l}.o.w", f"enc.{l}.ffn1.w", f"enc.{l}.ffn2.w"]
     for i in range(cfg.n_flows):
         names += [f"flow.{i}.pre.w", f"flow.{i}.post.w"]
         for j in range(cfg.flow_wn_layers):

@@ -105,6 +105,39 @@ def test_conv_tc(case, bf16, a_mode):
     assert err16 < (0.08 if bf16 else 0.02)
 
 
+@pytest.mark.parametrize("T,lens", [(7, [7]), (64, [64, 33]), (300, [300, 211]), (1000, [1000]), (2500, [2500, 1999])])
+def test_attention_tc(T, lens):
+    """tcgen05 attention vs the fp64 banded restatement on fp16-rounded operands."""
+    from tests.test_ops_gpu import _attention_ref
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(T + 5)
+    B, nh, dk = len(lens), 2, 96
+    qkv = (torch.randn(B, T, 3 * nh * dk, generator=g)).half().float()        # q|k|v, head-major, unpadded
+    rel_k = (torch.randn(21, dk, generator=g) * 0.1).half().float()
+    rel_v = (torch.randn(21, dk, generator=g) * 0.1).half().float()
+    ref = _attention_ref(qkv, rel_k, rel_v, lens, nh, 10)                      # divides q by sqrt(dk) itself
+    # padded fp16 operand: [q h0|q h1|k h0|k h1|v h0|v h1] x 128, q pre-scaled
+    qp = torch.zeros(B, T, 3 * nh * 128)
+    for pi in range(3):
+        for h in range(nh):
+            src = qkv[..., (pi * nh + h) * dk:(pi * nh + h + 1) * dk]
+            qp[..., (pi * nh + h) * 128:(pi * nh + h) * 128 + dk] = src / math.sqrt(dk) if pi == 0 else src
+    ek = torch.zeros(32, 128); ek[:21, :dk] = rel_k
+    evt = torch.zeros(128, 64); evt[:dk, :21] = rel_v.t()
+    qd, ekd, evd = qp.half().to(dev), ek.half().to(dev), evt.half().to(dev)
+    vt = torch.zeros(B * nh * 128 * ((T + 7) // 8 * 8), dtype=torch.float16, device=dev)
+    ld = torch.tensor(lens, dtype=torch.int32, device=dev)
+    out = torch.full((B, T, nh * dk), float("nan"), dtype=torch.float16, device=dev)
+    st = lib.rvcb200_op_attention_tc(qd.data_ptr(), vt.data_ptr(), ekd.data_ptr(), evd.data_ptr(), ld.data_ptr(), out.data_ptr(),
+                                     B, T, nh, dk, 10, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert st == 0, st
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs().max().item()
+    print(f"attention_tc T={T}: max abs err {err:.3e} (|ref|max {ref.abs().max().item():.2f})")
+    assert err < 2e-2        # fp16 q (pre-scaled), fp16 probabilities, fp16 output
+
+
 @pytest.mark.parametrize("precision,min_snr", [("fp16", 45.0), ("bf16", 45.0)])
 @pytest.mark.parametrize("name", ["c2_48k_v2", "c1_40k_v1", "c3_32k_v2_ragged", "c5_48k_v1_5stage"])
 def test_infer_tensor_core_path_snr(name, precision, min_snr):
