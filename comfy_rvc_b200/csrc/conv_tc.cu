@@ -22,8 +22,8 @@
 // every warp-level load/store is one 512 B transaction).
 //
 // Persistent, warp-specialised (320 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator
-// + MMA issuer (one lane), warps 2..9 = epilogue.  Two accumulator buffers in TMEM so the epilogue of
-// tile i overlaps the loads and MMAs of tile i+1.
+// + MMA issuer (one lane), warps 2..9 = two epilogue groups, each owning one of the two TMEM accumulator
+// buffers (tile t is drained by group t & 1 while the MMAs of tile t+1 run).
 // Replaces the cuDNN calls behind modules.py:295-308 (ResBlock1), models.py:545-551 (conv_pre, ups).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -314,6 +314,7 @@ __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t
   }
 }
 
+template <bool GENERIC>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
   extern __shared__ unsigned char smem_raw[];
@@ -349,7 +350,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps / 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -506,25 +507,34 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       __syncwarp();
     }
   } else {
-    // =========================== epilogue: 8 warps, TMEM -> registers -> global ==================
-    const int ew = warp - 2;                        // 0..7
+    // ============== epilogue: two groups of 4 warps, group e owns accumulator buffer e ===============
+    // (tile t is drained by group t & 1, so consecutive tiles' epilogues overlap and each warp pays the
+    //  per-tile fixed cost -- barrier wait, index math, bias -- only every other tile)
+    const int eg = (warp - 2) >> 2;                 // epilogue group = accumulator buffer
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                       // which half of the N columns
-    const bool split = p.N >= 32 && (p.N / 2) % 16 == 0;
-    const int wc = split ? p.N / 2 : p.N;           // columns per warp
-    const bool active = split || half == 0;
     const size_t pitch_o = (size_t)p.Lp_out * 16;
     const long long Lout = (long long)p.Lj * p.out_stride;
-    for (int t = 0; t < my_tiles; ++t) {
-      const int buf = t & 1;
-      int mt, nt, g, b;
-      decode((long long)blockIdx.x + (long long)t * gridDim.x, mt, nt, g, b);
-      mbar_wait(&acc_full[buf], (t >> 1) & 1);
+    const bool simple = n_nt == 1 && p.G == 1;      // resblock convs: tile -> (batch, m-tile) with one division
+    const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(eg * p.N);
+    for (int t = eg; t < my_tiles; t += 2) {
+      int mt, nt = 0, g = 0, b = 0;
+      const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
+      if (simple) {
+        if (p.batch == 1) mt = (int)tile;
+        else { b = (int)(tile / (unsigned)n_mt); mt = (int)(tile - (unsigned)b * (unsigned)n_mt); }
+      } else {
+        decode((long long)tile, mt, nt, g, b);
+      }
+      const int row = mt * BM + qd * 32 + lane;
+      const bool row_ok = row < p.Lj;
+      const long long orow = (long long)row * p.out_stride + g;
+      mbar_wait(&acc_full[eg], (t >> 1) & 1);
       tc_fence_after();
-      if (active) {
-        const int row = mt * BM + qd * 32 + lane;
-        const bool row_ok = row < p.Lj;
-        const long long orow = (long long)row * p.out_stride + g;
+      if (GENERIC) {
+        const bool valid = p.out_len ? (orow < p.out_len[b]) : true;
+        for (int c0 = 0; c0 < p.N; c0 += 16)
+          epilogue_generic16(p, tbase + (uint32_t)c0, row_ok, valid, b, orow, nt * p.N + c0);
+      } else {
         const size_t orow16 = (size_t)(orow + p.padf) * 16;
         unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
         unsigned char* y16row = p.y16 ? reinterpret_cast<unsigned char*>(p.y16) + ((size_t)b * Lout + orow) * p.Cout_total * 2
@@ -532,23 +542,17 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         const unsigned char* r32 =
             p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
         const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
-        const int c_begin = half * wc;
-        const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(buf * p.N);
-        if (p.generic) {
-          const bool valid = p.out_len ? (orow < p.out_len[b]) : true;
-          for (int c0 = c_begin; c0 < c_begin + wc; c0 += 16)
-            epilogue_generic16(p, tbase + (uint32_t)c0, row_ok, valid, b, orow, nt * p.N + c0);
-        } else if (wc % 32 == 0) {
-          for (int c0 = c_begin; c0 < c_begin + wc; c0 += 32)
+        if (p.N % 32 == 0) {
+          for (int c0 = 0; c0 < p.N; c0 += 32)
             epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond);
         } else {
-          for (int c0 = c_begin; c0 < c_begin + wc; c0 += 16)
+          for (int c0 = 0; c0 < p.N; c0 += 16)
             epilogue_chunk<16>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[eg])) : "memory");
     }
   }
   // ------------------------------------ teardown -------------------------------------------------
@@ -770,12 +774,14 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
   if (smem > cfgd) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cfgd = smem;
   }
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
-  conv_tc_kernel<<<grid, kThreadsTC, smem, st>>>(d, tmA, tmW);
+  if (d.generic) conv_tc_kernel<true><<<grid, kThreadsTC, smem, st>>>(d, tmA, tmW);
+  else conv_tc_kernel<false><<<grid, kThreadsTC, smem, st>>>(d, tmA, tmW);
   launch_counter().n++;
   return cudaGetLastError();
 }
