@@ -100,6 +100,29 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_lo, uint3
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
       "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
 }
+// Same, executed by every lane of a converged warp but issued only where `leader` is set: the operands
+// are computed in warp-uniform control flow so they can live in uniform registers.
+__device__ __forceinline__ void tc_mma_f16_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t acc, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(leader) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pred(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(leader) : "memory");
+}
 // K-major SWIZZLE_128B shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B |
 // version 1 [46,48) | base_offset [49,52) | layout_type SWIZZLE_128B = 2 [61,64)
@@ -447,19 +470,21 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           tc_fence_after();
         }
         if (slab && stat) {
-          // fast path: nothing to wait for inside the k-block -> one elected lane issues every tap back to back
-          if (elect_one()) {
-            const uint32_t a0 = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
-            const uint32_t b0 = d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4);
+          // fast path: nothing to wait for inside the k-block -> every tap is issued back to back.  The loop
+          // is warp-uniform (descriptors stay in uniform registers); only the MMA itself is predicated.
+          {
+            const uint32_t leader = elect_one() ? 1u : 0u;
+            uint32_t a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
+            uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4);
             const uint32_t a_step = (uint32_t)(p.dil * 128) >> 4, b_step = b_stride >> 4;
             for (int tap = 0; tap < p.ntaps; ++tap) {
-              const uint32_t a_lo = a0 + (uint32_t)tap * a_step, b_lo = b0 + (uint32_t)tap * b_step;
               for (int ks = 0; ks < ksteps; ++ks) {
-                tc_mma_f16(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum);
+                tc_mma_f16_pred(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum, leader);
                 accum = 1;
               }
+              a_lo += a_step; b_lo += b_step;
             }
-            tc_commit(&a_empty[sa]);
+            tc_commit_pred(&a_empty[sa], leader);
           }
           __syncwarp();
           accum = 1;
