@@ -66,7 +66,7 @@ class TcConvDesc(C.Structure):
         ("gather", C.c_void_p), ("gidx", C.c_void_p), ("gidx_bstride", C.c_int64),
         ("alpha", C.c_float), ("pre_slope", C.c_float), ("relu", C.c_int32), ("gate", C.c_int32),
         ("res_mode", C.c_int32), ("mask_pre", C.c_int32), ("mask_post", C.c_int32), ("mask16", C.c_int32),
-        ("out_len", C.c_void_p),
+        ("out_len", C.c_void_p), ("dbg_alt", C.c_int32),
     ]
 
 

@@ -36,7 +36,7 @@ namespace rvc {
 namespace {
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreadsTC = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
+constexpr int kThreadsTC = 96 + 32 * kEpiWarps;   // producer warp + 2 MMA warps + epilogue warps
 constexpr int BM = 128;
 constexpr int KBLK = 64;                          // channels per k-block = one 128-byte swizzled row
 
@@ -440,8 +440,9 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues ==========
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: warp w-1 issues the tiles t = w-1 (mod 2) into accumulator w-1 =====
+    // (a single issuing warp is instruction-latency-bound at ~10 SASS instrs per UTCHMMA on the narrow stages)
     // (keeping the loop uniform lets the compiler hold descriptors in uniform registers; a per-thread
     //  `if (lane == 0)` loop spent ~20 SASS instructions / ~270 cycles per UTCHMMA on R2UR traffic.)
     const uint32_t fmt = p.in_bf16 ? 1u : 0u;
@@ -450,14 +451,24 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
     const uint64_t dproto = make_desc_sw128(0, 0);
     const uint32_t d_hi0 = (uint32_t)(dproto >> 32), d_lo0 = (uint32_t)dproto;
     const uint32_t slabA_u = smem_u32(slabA), slabB_u = smem_u32(slabB);
+    const uint32_t d_hi_u = __shfl_sync(0xffffffffu, d_hi0, 0), idesc_u = __shfl_sync(0xffffffffu, idesc, 0);
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
+    const int mw = warp - 1;                                // which MMA warp: owns accumulator buffer mw
+    // ring positions advance over BOTH warps' tiles: skip the other warp's activation boxes / weight stages
+    const int a_per_tile = slab ? nkb : nkb * p.ntaps;
+    const int b_per_tile = stat ? 0 : nkb * p.ntaps;
+    auto skip_tile = [&]() {
+      for (int i = 0; i < a_per_tile; ++i) { if (++sa == NA) { sa = 0; pa ^= 1; } }
+      for (int i = 0; i < b_per_tile; ++i) { if (++sb == NB) { sb = 0; pb ^= 1; } }
+    };
     if (stat) {   // resident weights: wait once for all (k-block, tap) tiles
       for (int i = 0; i < nkb * p.ntaps; ++i) mbar_wait(&b_full[i], 0);
       tc_fence_after();
     }
-    for (int t = 0; t < my_tiles; ++t) {
-      const int buf = t & 1;
+    if (mw == 1 && my_tiles > 0) skip_tile();               // tile 0 belongs to warp 0
+    for (int t = mw; t < my_tiles; t += 2) {
+      const int buf = mw;
       mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
@@ -474,12 +485,15 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           // is warp-uniform (descriptors stay in uniform registers); only the MMA itself is predicated.
           {
             const uint32_t leader = elect_one() ? 1u : 0u;
-            uint32_t a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
-            uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4);
+            // __shfl_sync(.., 0) marks the bases as warp-uniform for the compiler: everything derived from
+            // them stays in uniform registers, so no R2UR chain sits between consecutive UTCHMMAs
+            uint32_t a_lo = __shfl_sync(0xffffffffu, d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4), 0);
+            uint32_t b_lo = __shfl_sync(0xffffffffu, d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4), 0);
+            const uint32_t dt = __shfl_sync(0xffffffffu, d_tmem, 0);
             const uint32_t a_step = (uint32_t)(p.dil * 128) >> 4, b_step = b_stride >> 4;
             for (int tap = 0; tap < p.ntaps; ++tap) {
               for (int ks = 0; ks < ksteps; ++ks) {
-                tc_mma_f16_pred(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum, leader);
+                tc_mma_f16_pred(dt, a_lo + 2u * ks, d_hi_u, b_lo + 2u * ks, d_hi_u, idesc_u, accum, leader);
                 accum = 1;
               }
               a_lo += a_step; b_lo += b_step;
@@ -530,12 +544,13 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       }
       if (elect_one()) tc_commit(&acc_full[buf]);
       __syncwarp();
+      if (t + 1 < my_tiles) skip_tile();                    // the other warp's tile
     }
   } else {
     // ============== epilogue: two groups of 4 warps, group e owns accumulator buffer e ===============
     // (tile t is drained by group t & 1, so consecutive tiles' epilogues overlap and each warp pays the
     //  per-tile fixed cost -- barrier wait, index math, bias -- only every other tile)
-    const int eg = (warp - 2) >> 2;                 // epilogue group = accumulator buffer
+    const int eg = (warp - 3) >> 2;                 // epilogue group = accumulator buffer
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
     const size_t pitch_o = (size_t)p.Lp_out * 16;
     const long long Lout = (long long)p.Lj * p.out_stride;

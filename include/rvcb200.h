@@ -185,6 +185,7 @@ typedef struct rvcb200_tc_conv_desc {
   int32_t relu, gate;          /* gate: interleaved (tanh, sigmoid) column pairs -> C_out/2 outputs */
   int32_t res_mode;            /* 1: v + res, 2: res - v */
   int32_t mask_pre, mask_post, mask16; const int32_t* out_len;    /* rows >= out_len[b] -> 0 */
+  int32_t dbg_alt;             /* timing experiment only (wrong results): alternate accumulator regions */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--T", type=int, default=6000)
     ap.add_argument("--a-mode", type=int, default=0)
+    ap.add_argument("--dbg-alt", type=int, default=0)
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda", 0)
@@ -54,6 +55,7 @@ def main():
                 d.w16, d.bias = w.data_ptr(), bias.data_ptr()
                 d.Cin, d.ntaps, d.dil, d.G = Cc, k, dil, 1
                 d.a_mode = args.a_mode
+                d.dbg_alt = args.dbg_alt
                 d.g_off[0] = -((k - 1) // 2) * dil
                 d.N, d.Cout_total = min(256, Cc), Cc
                 d.Lj, d.out_stride, d.Lp_out = L, 1, Lp
