@@ -2,4 +2,6 @@
 from .config import NAMED_CONFIGS, SynthConfig  # noqa: F401
 from .synthesizer import SynthesizerB200, SynthesizerTrnMs256NSFsid, SynthesizerTrnMs768NSFsid  # noqa: F401
 
-__all__ = ["SynthesizerTrnMs256NSFsid", "SynthesizerTrnMs768NSFsid", "SynthesizerB200", "SynthConfig", "NAMED_CONFIGS"]
+from .pipeline import VC, FeatureExtractor, PipelineConfig, get_vc  # noqa: F401
+
+__all__ = ["VC", "FeatureExtractor", "PipelineConfig", "get_vc", "SynthesizerTrnMs256NSFsid", "SynthesizerTrnMs768NSFsid", "SynthesizerB200", "SynthConfig", "NAMED_CONFIGS"]

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librvcb200.so")
+LIB_PATH = os.environ.get("RVCB200_LIB") or os.path.join(HERE, "librvcb200.so")   # env override: kernel A/B experiments
 
 MAX_UPS, MAX_RESK, MAX_DIL = 8, 4, 4
 PREC = {"fp32": 0, "fp16": 1, "bf16": 2}
@@ -97,6 +97,10 @@ SYMBOLS = {
                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "rvcb200_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                        C.c_float, C.c_void_p]),
+    "rvcb200_op_prepare_feats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
+    "rvcb200_op_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+    "rvcb200_op_to_int16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

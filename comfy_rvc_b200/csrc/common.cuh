@@ -67,4 +67,10 @@ cudaError_t launch_conv_post_tanh(const float* x, const float* w, float* out, in
 // dst = src * scale, elementwise (row-strided copy): dst[r][c] = src[r][c] for c < C
 cudaError_t launch_copy_rows(const float* src, int lds, float* dst, int ldd, long long rows, int C, cudaStream_t st);
 
+// ---- segmented-driver pre/post steps (pipeline_kernels.cu) ----
+cudaError_t launch_prepare_feats(const void* f, const void* f0, int dtype, const float* pitchf, float* out, int F, int T, int C,
+                                 float protect, int use_protect, cudaStream_t st);
+cudaError_t launch_absmax(const float* x, long long n, float* out, int reset, cudaStream_t st);
+cudaError_t launch_to_int16(const float* x, long long n, const float* absmax, short* out, cudaStream_t st);
+
 }  // namespace rvc

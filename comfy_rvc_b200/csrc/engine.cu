@@ -977,4 +977,21 @@ int rvcb200_op_layernorm(const float* x, const float* gamma, const float* beta, 
   return e == cudaSuccess ? RVCB200_OK : RVCB200_ERR_CUDA;
 }
 
+int rvcb200_op_prepare_feats(const void* feats, const void* feats0, int32_t dtype, const float* pitchf, float* out, int32_t F,
+                             int32_t T, int32_t C, float protect, int32_t use_protect, void* stream) {
+  cudaError_t e = launch_prepare_feats(feats, feats0, dtype, pitchf, out, F, T, C, protect, use_protect,
+                                       reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int rvcb200_op_absmax(const float* x, int64_t n, float* out, int32_t reset, void* stream) {
+  cudaError_t e = launch_absmax(x, n, out, reset, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t* out, void* stream) {
+  cudaError_t e = launch_to_int16(x, n, absmax, out, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
 }  // extern "C"

@@ -47,7 +47,9 @@ class SynthesizerB200(nn.Module):
             raise ValueError("rvcb200 kernels are built for hidden=inter=192, 2 heads (every shipped RVC config)")
         self.enc_q = nn.Identity()          # `del net_g.enc_q` (vc_infer_pipeline.py:219) must work
         self.is_half = bool(is_half)
-        self.precision = "fp32"             # arithmetic of the heavy contractions, see set_precision
+        # arithmetic of the heavy contractions: `is_half` / `.half()` select the tensor-core path with fp16 operands
+        # (the reference's own GPU dtype), `.float()` the fp32 CUDA-core path; set_precision("bf16") is the third option
+        self.precision = "fp16" if self.is_half else "fp32"
         self._device = torch.device("cuda", 0)
         self._ref_sd: Optional[Dict[str, torch.Tensor]] = None
         self._packed: Optional[Dict[str, torch.Tensor]] = None   # device tensors (kept alive for the ctx)
@@ -89,11 +91,11 @@ class SynthesizerB200(nn.Module):
 
     def half(self):
         self.is_half = True
-        return self
+        return self.set_precision("fp16") if self.precision == "fp32" else self
 
     def float(self):
         self.is_half = False
-        return self
+        return self.set_precision("fp32")
 
     def remove_weight_norm(self):  # models.py:661-664: weight-norm is already folded at load
         return None

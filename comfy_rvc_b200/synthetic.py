@@ -164,3 +164,61 @@ def snr_db(ref: np.ndarray, est: np.ndarray) -> float:
     num = np.sum(ref ** 2)
     den = np.sum((ref - est) ** 2)
     return float(10.0 * np.log10(num / max(den, 1e-300)))
+
+
+# ---------------------------------------------------------------------------------------------
+# Pipeline-level synthetic stand-ins (VC.pipeline / VC.vc, /root/reference/vc_infer_pipeline.py:25-196).
+# HuBERT, the f0 estimators and faiss sit upstream of the synthesis path and are not
+# available offline; these deterministic doubles have the same call signatures and output shapes.
+# ---------------------------------------------------------------------------------------------
+def make_song(seconds: float, seed: int = 0, sr: int = 16000) -> np.ndarray:
+    """Band-limited noise with a slow amplitude modulation so that quiet points exist (float64, 16 kHz)."""
+    n = int(round(seconds * sr))
+    rng = np.random.default_rng(seed)
+    white = rng.standard_normal(n + 15)
+    x = np.convolve(white, np.ones(16) / 16.0, mode="valid")[:n]
+    t = np.arange(n, dtype=np.float64) / sr
+    am = 0.05 + 0.95 * np.sin(2 * np.pi * 0.37 * t + 0.3 * seed) ** 2
+    return 0.4 * x * am
+
+
+def pipeline_f0(x, **_unused) -> np.ndarray:
+    """Synthetic f0 "method" with the reference's estimator signature (pitch_extraction.py:252-268 passes
+    x=, f0_up_key=, f0_min=, ... as keywords): one value per 160-sample hop of the padded audio."""
+    n = int(np.asarray(x).shape[0]) // 160
+    t = np.arange(n, dtype=np.float64) / 100.0
+    f0 = 180.0 * np.power(2.0, 0.6 * np.sin(2 * np.pi * 0.45 * t))
+    gap = np.mod(t, 1.7) < 0.4
+    return np.where(gap, 0.0, f0)
+
+
+class FakeHubert:
+    """Deterministic stand-in for `HubertModelWithFinalProj.extract_features`
+    (/root/reference/lib/infer_pack/loaders.py:43-61): 20 ms hop, receptive field 400 samples, so
+    `source[1, n]` → `[1, (n - 400)//320 + 1, C_f]`; values are N(0,1) seeded by n."""
+
+    def __init__(self, feat_dim: int, seed: int = 100):
+        self.feat_dim, self.seed = feat_dim, seed
+
+    def extract_features(self, version=None, source=None, padding_mask=None, output_layer=None, **_):
+        n = int(source.shape[-1])
+        frames = (n - 400) // 320 + 1
+        g = torch.Generator().manual_seed(self.seed + n)
+        feats = torch.randn(1, frames, self.feat_dim, generator=g, dtype=torch.float32)
+        return feats.to(device=source.device, dtype=source.dtype)
+
+
+class FakeIndex:
+    """Brute-force stand-in for a faiss `IndexFlatL2` over `big_npy` (vc_infer_pipeline.py:60-74 only calls
+    `.search(npy, k=1)`; squared-L2 scores like faiss)."""
+
+    def __init__(self, feat_dim: int, n: int = 48, seed: int = 5):
+        g = torch.Generator().manual_seed(seed)
+        self.big_npy = torch.randn(n, feat_dim, generator=g, dtype=torch.float32).numpy()
+
+    def search(self, npy: np.ndarray, k: int = 1):
+        a = np.asarray(npy, dtype=np.float64)
+        b = self.big_npy.astype(np.float64)
+        d = (a * a).sum(1, keepdims=True) - 2.0 * a @ b.T + (b * b).sum(1)[None, :]
+        ix = np.argsort(d, axis=1, kind="stable")[:, :k]
+        return np.take_along_axis(d, ix, axis=1).astype(np.float32), ix.astype(np.int64)

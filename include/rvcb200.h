@@ -211,6 +211,23 @@ int rvcb200_op_attention_tc(const void* qkv16, void* vt, const void* ek16, const
 int rvcb200_op_layernorm(const float* x, const float* gamma, const float* beta, float* y, int64_t rows,
                          int32_t C, float eps, void* stream);
 
+/* ---- segmented-driver pre/post steps (csrc/pipeline_kernels.cu); replace the torch/numpy glue of VC.vc and the
+ * tail of VC.pipeline so a whole song is converted without a host round trip per segment. ---- */
+
+/* out[T][C] fp32 = x2 nearest interpolation of feats[F][C] (dtype 0 = fp32, 1 = fp16), optionally blended with
+ * feats0 by the "protect" weight p = (pitchf[t] < 1 ? protect : 1): out = f*p + f0*(1-p)
+ * (/root/reference/vc_infer_pipeline.py:77-95; T <= 2F). */
+int rvcb200_op_prepare_feats(const void* feats, const void* feats0, int32_t dtype, const float* pitchf, float* out, int32_t F,
+                             int32_t T, int32_t C, float protect, int32_t use_protect, void* stream);
+
+/* *out = max(*out, max|x[0..n)|) on the device (reset != 0 zeroes *out first); x 16-byte aligned
+ * (vc_infer_pipeline.py:188 `np.abs(audio_opt).max()`). */
+int rvcb200_op_absmax(const float* x, int64_t n, float* out, int32_t reset, void* stream);
+
+/* out[i] = (int16) trunc(x[i] * 32768 / (*absmax / 0.99)) in float32 arithmetic (vc_infer_pipeline.py:188-189,
+ * NumPy >= 2 promotion). */
+int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,3 +32,21 @@ def int16_lsb_diff(ref_f32: np.ndarray, est_f32: np.ndarray) -> int:
     a = synthetic.to_int16(ref_f32).astype(np.int32)
     b = synthetic.to_int16(est_f32).astype(np.int32)
     return int(np.abs(a - b).max())
+
+
+PIPELINE_CASES = ["p1_40k_v1_4seg", "p2_32k_v2_protect_index", "p3_48k_v2_single"]
+
+
+def load_pipeline_golden(name):
+    """Fixture minted by tests/golden/make_pipeline_golden.py → dict of everything needed to replay it."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=True)
+    cfg_name, secs, tiers, protect, index_rate, f0_up_key, aseed, rseed = [str(x) for x in z["meta"][:8]]
+    cfg = NAMED_CONFIGS[cfg_name]
+    index_rate = float(index_rate)
+    case = dict(cfg=cfg, sd=synthetic.make_state_dict(cfg, seed=0), tiers=ast.literal_eval(tiers), protect=float(protect),
+                index_rate=index_rate, f0_up_key=int(f0_up_key), rseed=int(rseed),
+                audio=synthetic.make_song(float(secs), seed=int(aseed)), version="v1" if cfg.feat_dim == 256 else "v2",
+                hubert=synthetic.FakeHubert(cfg.feat_dim), gold=z)
+    idx = synthetic.FakeIndex(cfg.feat_dim, seed=5)
+    case["file_index"] = (idx, idx.big_npy) if index_rate > 0 else ""
+    return case

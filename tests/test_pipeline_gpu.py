@@ -1,0 +1,152 @@
+"""GPU: the segmented conversion driver (`comfy_rvc_b200.VC.vc` / `.pipeline`, through the C ABI) against the
+reference-minted pipeline fixtures and the pipeline oracle.
+
+Gates (BASELINE.json north_star): fp32 path — int16 song within ±1 LSB of the reference's own `VC.pipeline`
+output; tensor-core path — SNR ≥ 45 dB (formula of lib/karafan/compare.py:21-35)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from comfy_rvc_b200 import _lib, synthetic
+from comfy_rvc_b200 import pipeline as pl
+from oracle import pipeline_oracle, rvc_oracle
+from tests._util import PIPELINE_CASES, load_pipeline_golden
+from tests.test_parity_gpu import build_net
+
+pytestmark = pytest.mark.gpu
+
+
+def run_product(case, precision="fp32", noise="reference"):
+    cfg = case["cfg"]
+    net = build_net(cfg, case["sd"], precision)
+    vc = pl.VC(cfg.sr, pl.PipelineConfig(*case["tiers"], is_half=False, device="cuda:0"), noise=noise)
+    vc.f0_method_dict["synthetic"] = synthetic.pipeline_f0
+    torch.manual_seed(case["rseed"])             # the reference drew from the global CPU RNG, segment by segment
+    times = [0, 0, 0]
+    out = vc.pipeline(case["hubert"], net, 0, case["audio"].copy(), times, case["f0_up_key"], "synthetic", "median",
+                      case["file_index"], case["index_rate"], 1, 3, cfg.sr, 0, 1.0, case["version"], case["protect"], 160,
+                      False, False, None, 50, 1100)
+    return out, vc, net
+
+
+@pytest.mark.parametrize("name", PIPELINE_CASES)
+def test_pipeline_matches_reference_golden_fp32(name):
+    case = load_pipeline_golden(name)
+    out, vc, net = run_product(case)
+    gold = case["gold"]
+    assert out.dtype == np.int16 and out.shape == gold["out_i16"].shape
+    assert len(vc.last_plan["segments"]) == len(gold["seg_audio_len"])
+    assert [s.n_samples for s in vc.last_plan["segments"]] == list(gold["seg_audio_len"])
+    d = np.abs(out.astype(np.int32) - gold["out_i16"].astype(np.int32))
+    print(f"{name}: int16 max diff {d.max()} LSB, {np.mean(d > 0) * 100:.2f}% samples differ, launches/segment {net.last_launches}")
+    assert d.max() <= 1
+    assert np.abs(out).max() == 32440            # peak maps to trunc(0.99 * 32768)
+
+
+@pytest.mark.parametrize("precision,name", [("fp16", "p1_40k_v1_4seg"), ("bf16", "p2_32k_v2_protect_index")])
+def test_pipeline_tensor_path_snr(precision, name):
+    case = load_pipeline_golden(name)
+    out, _, _ = run_product(case, precision)
+    snr = synthetic.snr_db(case["gold"]["out_i16"].astype(np.float64), out.astype(np.float64))
+    print(f"{name} {precision}: song SNR {snr:.1f} dB")
+    assert snr >= 45.0
+
+
+def test_device_noise_is_sharding_independent_and_seeded():
+    case = load_pipeline_golden("p1_40k_v1_4seg")
+    a, _, _ = run_product(case, noise="device")
+    b, _, _ = run_product(case, noise="device")
+    assert np.array_equal(a, b)                  # per-segment generators: deterministic, independent of call order
+
+
+def test_vc_single_segment_matches_oracle():
+    """`VC.vc` (numpy in → float32 numpy out, like vc_infer_pipeline.py:25-114) on one segment with protect + index."""
+    case = load_pipeline_golden("p2_32k_v2_protect_index")
+    cfg = case["cfg"]
+    net = build_net(cfg, case["sd"])
+    vc = pl.VC(cfg.sr, pl.PipelineConfig(*case["tiers"], is_half=False, device="cuda:0"))
+    n = 16000 * 2 + 320
+    audio0 = synthetic.make_song(3.0, seed=9)[:n]
+    f0 = synthetic.pipeline_f0(x=np.zeros(n))
+    coarse, f0 = pipeline_oracle.f0_post(f0, 2)
+    pitch = torch.from_numpy(coarse.astype(np.int64)).unsqueeze(0)
+    pitchf = torch.from_numpy(f0.astype(np.float32)).unsqueeze(0)
+    T = min(n // 160, 2 * pl.hubert_frames(n))
+    noise = synthetic.draw_noise(cfg, 1, T, seed=21)
+    idx, big = case["file_index"]
+    # product: noise injected through the reference-order global RNG
+    vc.noise_mode = "reference"
+    torch.manual_seed(21)
+    orig = net.infer
+    net.infer = lambda *a, **k: orig(*a, noise=noise, **k)
+    got = vc.vc(case["hubert"], net, torch.zeros(1, dtype=torch.int64, device="cuda:0"), audio0, pitch.cuda(), pitchf.cuda(),
+                [0, 0, 0], idx, big, 0.75, "v2", 0.33)
+    c = pipeline_oracle.Constants(*case["tiers"], tgt_sr=cfg.sr)
+    w = rvc_oracle.fold_weight_norm(case["sd"])
+    want = pipeline_oracle.vc_segment(
+        lambda feats, pl_, p, pf, s: rvc_oracle.infer(w, cfg, feats, pl_, p, pf, s, *noise)[0][0, 0].numpy(),
+        case["hubert"], cfg, audio0, pitch, pitchf, torch.zeros(1, dtype=torch.int64), c, idx, big, 0.75, "v2", 0.33)
+    assert got.dtype == np.float32 and got.shape == want.shape == (T * cfg.upp,)
+    assert np.abs(synthetic.to_int16(got).astype(np.int32) - synthetic.to_int16(want).astype(np.int32)).max() <= 1
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("use_protect", [0, 1])
+def test_prepare_feats_bit_exact(dtype, use_protect):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    Fr, Cf, T = 57, 768, 113
+    f = torch.randn(1, Fr, Cf, generator=g).to(dtype)
+    f0 = torch.randn(1, Fr, Cf, generator=g).to(dtype)
+    pitchf = torch.from_numpy(synthetic.pipeline_f0(x=np.zeros(160 * T)).astype(np.float32)).unsqueeze(0)
+    pitchf[0, 5] = 0.5                      # 0 < f0 < 1: the second assignment (protect) wins, vc_infer_pipeline.py:91-92
+    protect = 0.33
+    # reference arithmetic (vc_infer_pipeline.py:77-95) on the CPU in the same dtypes
+    a = F.interpolate(f.float().permute(0, 2, 1), scale_factor=2).permute(0, 2, 1)[:, :T]
+    if use_protect:
+        b = F.interpolate(f0.float().permute(0, 2, 1), scale_factor=2).permute(0, 2, 1)[:, :T]
+        pff = pitchf.clone()
+        pff[pitchf > 0] = 1
+        pff[pitchf < 1] = protect
+        pff = pff.unsqueeze(-1)
+        a = a * pff + b * (1 - pff)
+    out = torch.empty(1, T, Cf, device="cuda")
+    fd, f0d, pd = f.cuda(), f0.cuda(), pitchf.cuda()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.rvcb200_op_prepare_feats(C.c_void_p(fd.data_ptr()), C.c_void_p(f0d.data_ptr()), 0 if dtype == torch.float32 else 1,
+                                        C.c_void_p(pd.data_ptr()), C.c_void_p(out.data_ptr()), Fr, T, Cf, protect, use_protect,
+                                        st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), a)
+    assert lib.rvcb200_op_prepare_feats(C.c_void_p(fd.data_ptr()), None, 0, None, C.c_void_p(out.data_ptr()), Fr, 2 * Fr + 1, Cf,
+                                        protect, 0, st) == 1          # T > 2F is a bad argument, not a crash
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 1000003, 5_000_000])
+def test_absmax_and_int16_bit_exact(n):
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) * 0.3).astype(np.float32)
+    if n > 10:
+        x[n // 3] = -1.7                        # the peak is negative
+    xd = torch.from_numpy(x).cuda()
+    peak = torch.full((1,), 123.0, device="cuda")
+    out = torch.empty(n, dtype=torch.int16, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.rvcb200_op_absmax(C.c_void_p(xd.data_ptr()), n, C.c_void_p(peak.data_ptr()), 1, st) == 0
+    torch.cuda.synchronize()
+    want_peak = np.abs(x).max() if n else np.float32(0)
+    assert peak.item() == float(want_peak)
+    if n == 0:
+        return
+    assert lib.rvcb200_op_to_int16(C.c_void_p(xd.data_ptr()), n, C.c_void_p(peak.data_ptr()), C.c_void_p(out.data_ptr()), st) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), synthetic.to_int16(x))      # vc_infer_pipeline.py:188-189 in numpy
+    # running max without reset keeps the larger value
+    small = torch.full((8,), 0.25, device="cuda")
+    assert lib.rvcb200_op_absmax(C.c_void_p(small.data_ptr()), 8, C.c_void_p(peak.data_ptr()), 0, st) == 0
+    torch.cuda.synchronize()
+    assert peak.item() == float(want_peak)

@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--T", type=int, default=6000)
     ap.add_argument("--a-mode", type=int, default=0)
     ap.add_argument("--dbg-alt", type=int, default=0)
+    ap.add_argument("--stages", default="", help="comma list of stage indices (0-3) to keep")
+    ap.add_argument("--ks", default="", help="comma list of kernel sizes to keep (default all)")
     args = ap.parse_args()
     lib = _lib.load()
     dev = torch.device("cuda", 0)
@@ -41,13 +43,18 @@ def main():
     for si, (Cc, L) in enumerate(stages):
         if args.only >= 0 and si != args.only:
             continue
+        if args.stages and si not in {int(v) for v in args.stages.split(",")}:
+            continue
         Lp = pitch(L)
         x16 = torch.randn(1, L, Cc, dtype=torch.float16, device=dev)
         r32 = torch.randn(1, Cc // 4, Lp, 4, device=dev)
         y32 = torch.zeros(1, Cc // 4, Lp, 4, device=dev)
         y16 = torch.zeros(1, L, Cc, dtype=torch.float16, device=dev)
         bias = torch.randn(Cc, device=dev)
+        keep = {int(v) for v in args.ks.split(",")} if args.ks else None
         for k, dil in ((3, 1), (7, 3), (11, 5), (11, 1)):
+            if keep is not None and (k not in keep or (k == 11 and dil == 1)):
+                continue
             w = weights.pack_tc(torch.randn(1, k, Cc, Cc) / (Cc * k) ** 0.5, torch.float16).to(dev)
             for kind in ("c1", "c2"):
                 d = _lib.TcConvDesc()
