@@ -129,7 +129,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp16", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "fp16", "bf16"],
+                    help="bf16 (default; BASELINE north_star's tensor path, SNR >= 45 dB gate), fp16 (the reference's own GPU "
+                         "dtype, same speed, ~61 dB) or fp32 (CUDA-core path, +-1 LSB gate)")
     ap.add_argument("--config", default="48k_v2")
     ap.add_argument("--seconds", type=float, default=60.0)
     ap.add_argument("--cpu-frames", type=int, default=300, help="frames of the bounded CPU-baseline sample")
@@ -262,7 +264,7 @@ def main():
     line = {
         "metric": metric, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate"}[args.precision],
+        "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands (resblocks) / f16 operands (ladder, encoder, flow), f32 accumulate"}[args.precision],
         "data": "synthetic (seeded random-init weights stored as fp16, N(0,1) features, contour f0)",
         "config": {"workload": workload, "precision": args.precision, "parallelism": f"segments x{world}, no collective",
                    "l2": "no flush needed: each step streams >1 GB of stage activations (>> 126 MB L2)"},

@@ -31,197 +31,17 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "tc_ptx.cuh"
 
 namespace rvc {
 namespace {
 
 constexpr int kEpiWarps = 8;
-constexpr int kThreadsTC = 96 + 32 * kEpiWarps;   // producer warp + 2 MMA warps + epilogue warps
+constexpr int kThreadsTC = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
 constexpr int BM = 128;
 constexpr int KBLK = 64;                          // channels per k-block = one 128-byte swizzled row
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ bool elect_one() {   // one lane of a converged warp (elect.sync)
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// descriptors are passed as (lo, hi) 32-bit halves: only the low word (start address) changes per MMA
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                           uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc) : "memory");
-}
-// Same, executed by every lane of a converged warp but issued only where `leader` is set: the operands
-// are computed in warp-uniform control flow so they can live in uniform registers.
-__device__ __forceinline__ void tc_mma_f16_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                                uint32_t idesc, uint32_t acc, uint32_t leader) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "setp.ne.b32 q, %7, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc), "r"(leader) : "memory");
-}
-__device__ __forceinline__ void tc_commit_pred(uint64_t* bar, uint32_t leader) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(leader) : "memory");
-}
-// K-major SWIZZLE_128B shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B |
-// version 1 [46,48) | base_offset [49,52) | layout_type SWIZZLE_128B = 2 [61,64)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t base_offset) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         ((uint64_t)(base_offset & 7u) << 49) | (2ull << 61);
-}
-
-__device__ __forceinline__ uint32_t pack2(bool bf16, float a, float b) {
-  if (bf16) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  } else {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-}
-
-// One epilogue pass over CH accumulator columns of this thread's row: TMEM -> regs, + bias/cond/residual,
-// accumulate, /div, fp32 PV store, lrelu + 16-bit channels-last store.  Loads are issued before use.
-template <int CH>
-__device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t taddr, bool row_ok, int co, size_t pitch_o,
-                                               size_t orow16, unsigned char* y32, unsigned char* y16row,
-                                               const unsigned char* r32, const float* cond) {
-  uint32_t r[CH];
-  if (CH == 32) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
-        "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16 % CH]),
-          "=r"(r[17 % CH]), "=r"(r[18 % CH]), "=r"(r[19 % CH]), "=r"(r[20 % CH]), "=r"(r[21 % CH]), "=r"(r[22 % CH]),
-          "=r"(r[23 % CH]), "=r"(r[24 % CH]), "=r"(r[25 % CH]), "=r"(r[26 % CH]), "=r"(r[27 % CH]), "=r"(r[28 % CH]),
-          "=r"(r[29 % CH]), "=r"(r[30 % CH]), "=r"(r[31 % CH])
-        : "r"(taddr));
-  } else {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-  }
-  float4 rr[CH / 4], aa[CH / 4];
-  if (row_ok) {
-    if (r32) {
-#pragma unroll
-      for (int k4 = 0; k4 < CH / 4; ++k4)
-        rr[k4] = *reinterpret_cast<const float4*>(r32 + (size_t)(co / 4 + k4) * pitch_o + orow16);
-    }
-    if (p.accum) {
-#pragma unroll
-      for (int k4 = 0; k4 < CH / 4; ++k4)
-        aa[k4] = *reinterpret_cast<const float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + orow16);
-    }
-  }
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  if (!row_ok) return;
-  float v[CH];
-#pragma unroll
-  for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]) + __ldg(p.bias + co + i);
-  if (cond) {
-#pragma unroll
-    for (int i = 0; i < CH; ++i) v[i] += __ldg(cond + co + i);
-  }
-  if (r32) {
-#pragma unroll
-    for (int k4 = 0; k4 < CH / 4; ++k4) {
-      v[k4 * 4 + 0] += rr[k4].x; v[k4 * 4 + 1] += rr[k4].y; v[k4 * 4 + 2] += rr[k4].z; v[k4 * 4 + 3] += rr[k4].w;
-    }
-  }
-  if (p.accum) {
-#pragma unroll
-    for (int k4 = 0; k4 < CH / 4; ++k4) {
-      v[k4 * 4 + 0] += aa[k4].x; v[k4 * 4 + 1] += aa[k4].y; v[k4 * 4 + 2] += aa[k4].z; v[k4 * 4 + 3] += aa[k4].w;
-    }
-  }
-  if (p.div != 1.f) {
-#pragma unroll
-    for (int i = 0; i < CH; ++i) v[i] = v[i] / p.div;
-  }
-  if (y32) {
-#pragma unroll
-    for (int k4 = 0; k4 < CH / 4; ++k4)
-      *reinterpret_cast<float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + orow16) =
-          make_float4(v[k4 * 4 + 0], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
-  }
-  if (y16row) {
-    const bool obf = p.out_bf16 != 0;
-#pragma unroll
-    for (int k8 = 0; k8 < CH / 8; ++k8) {
-      uint4 o;
-      o.x = pack2(obf, lrelu(v[k8 * 8 + 0], p.out_slope), lrelu(v[k8 * 8 + 1], p.out_slope));
-      o.y = pack2(obf, lrelu(v[k8 * 8 + 2], p.out_slope), lrelu(v[k8 * 8 + 3], p.out_slope));
-      o.z = pack2(obf, lrelu(v[k8 * 8 + 4], p.out_slope), lrelu(v[k8 * 8 + 5], p.out_slope));
-      o.w = pack2(obf, lrelu(v[k8 * 8 + 6], p.out_slope), lrelu(v[k8 * 8 + 7], p.out_slope));
-      *reinterpret_cast<uint4*>(y16row + (size_t)(co + k8 * 8) * 2) = o;
-    }
-  }
-}
+using namespace tc;
 
 // Generic epilogue (text encoder / flow): channels-last or PV fp32 I/O, embedding gather, scale, gate,
 // masks, residual modes.  One pass over 16 accumulator columns of this thread's row.
@@ -440,9 +260,8 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===================== MMA issuers: warp w-1 issues the tiles t = w-1 (mod 2) into accumulator w-1 =====
-    // (a single issuing warp is instruction-latency-bound at ~10 SASS instrs per UTCHMMA on the narrow stages)
+  } else if (warp == 1) {
+    // ===================== MMA issuer: warp-uniform control flow, one elected lane issues ==========
     // (keeping the loop uniform lets the compiler hold descriptors in uniform registers; a per-thread
     //  `if (lane == 0)` loop spent ~20 SASS instructions / ~270 cycles per UTCHMMA on R2UR traffic.)
     const uint32_t fmt = p.in_bf16 ? 1u : 0u;
@@ -451,24 +270,14 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
     const uint64_t dproto = make_desc_sw128(0, 0);
     const uint32_t d_hi0 = (uint32_t)(dproto >> 32), d_lo0 = (uint32_t)dproto;
     const uint32_t slabA_u = smem_u32(slabA), slabB_u = smem_u32(slabB);
-    const uint32_t d_hi_u = __shfl_sync(0xffffffffu, d_hi0, 0), idesc_u = __shfl_sync(0xffffffffu, idesc, 0);
     int sa = 0, sb = 0;
     uint32_t pa = 0, pb = 0;
-    const int mw = warp - 1;                                // which MMA warp: owns accumulator buffer mw
-    // ring positions advance over BOTH warps' tiles: skip the other warp's activation boxes / weight stages
-    const int a_per_tile = slab ? nkb : nkb * p.ntaps;
-    const int b_per_tile = stat ? 0 : nkb * p.ntaps;
-    auto skip_tile = [&]() {
-      for (int i = 0; i < a_per_tile; ++i) { if (++sa == NA) { sa = 0; pa ^= 1; } }
-      for (int i = 0; i < b_per_tile; ++i) { if (++sb == NB) { sb = 0; pb ^= 1; } }
-    };
     if (stat) {   // resident weights: wait once for all (k-block, tap) tiles
       for (int i = 0; i < nkb * p.ntaps; ++i) mbar_wait(&b_full[i], 0);
       tc_fence_after();
     }
-    if (mw == 1 && my_tiles > 0) skip_tile();               // tile 0 belongs to warp 0
-    for (int t = mw; t < my_tiles; t += 2) {
-      const int buf = mw;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int buf = t & 1;
       mbar_wait(&acc_empty[buf], ((t >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
@@ -485,15 +294,12 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           // is warp-uniform (descriptors stay in uniform registers); only the MMA itself is predicated.
           {
             const uint32_t leader = elect_one() ? 1u : 0u;
-            // __shfl_sync(.., 0) marks the bases as warp-uniform for the compiler: everything derived from
-            // them stays in uniform registers, so no R2UR chain sits between consecutive UTCHMMAs
-            uint32_t a_lo = __shfl_sync(0xffffffffu, d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4), 0);
-            uint32_t b_lo = __shfl_sync(0xffffffffu, d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4), 0);
-            const uint32_t dt = __shfl_sync(0xffffffffu, d_tmem, 0);
+            uint32_t a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
+            uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4);
             const uint32_t a_step = (uint32_t)(p.dil * 128) >> 4, b_step = b_stride >> 4;
             for (int tap = 0; tap < p.ntaps; ++tap) {
               for (int ks = 0; ks < ksteps; ++ks) {
-                tc_mma_f16_pred(dt, a_lo + 2u * ks, d_hi_u, b_lo + 2u * ks, d_hi_u, idesc_u, accum, leader);
+                tc_mma_f16_pred(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum, leader);
                 accum = 1;
               }
               a_lo += a_step; b_lo += b_step;
@@ -544,13 +350,12 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       }
       if (elect_one()) tc_commit(&acc_full[buf]);
       __syncwarp();
-      if (t + 1 < my_tiles) skip_tile();                    // the other warp's tile
     }
   } else {
     // ============== epilogue: two groups of 4 warps, group e owns accumulator buffer e ===============
     // (tile t is drained by group t & 1, so consecutive tiles' epilogues overlap and each warp pays the
     //  per-tile fixed cost -- barrier wait, index math, bias -- only every other tile)
-    const int eg = (warp - 3) >> 2;                 // epilogue group = accumulator buffer
+    const int eg = (warp - 2) >> 2;                 // epilogue group = accumulator buffer
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
     const size_t pitch_o = (size_t)p.Lp_out * 16;
     const long long Lout = (long long)p.Lj * p.out_stride;
@@ -655,46 +460,67 @@ __global__ void cl32_to_cl16_kernel(const float* __restrict__ x, unsigned char* 
   }
 }
 
+// x32 (PV fp32) += noise_conv(har);  x16 (channels-last 16 bit) = cvt(lrelu(x32))
+// (models.py:552-553 + the lrelu of modules.py:297).  HBM-bound: 4 B read + 4 B write + 2 B write per element.
+// One thread owns CPT consecutive channels of one time row: CPT/4 plane accesses (each coalesced across the warp)
+// and one contiguous CPT*2-byte piece of the 16-bit row (whole 32-byte sectors, no partial-sector writes).
+template <int CPT>
 __global__ void noise_add_pv_kernel(const float* __restrict__ har, const float* __restrict__ wn, const float* __restrict__ nb,
                                     unsigned char* __restrict__ x32, unsigned char* __restrict__ x16, long long L_har,
                                     long long L, int C, int k, int s, int pad, int Lp, int padf, float slope, bool BF16) {
-  // x32 (PV fp32) += noise_conv(har);  x16 (channels-last 16 bit) = cvt(lrelu(x32))
-  // (models.py:552-553 + the lrelu of modules.py:297)
   extern __shared__ float sw[];  // [k][C] + [C]
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) sw[k * C + i] = nb[i];
   __syncthreads();
   const int b = blockIdx.y;
-  const int ng = C / 8;
+  const int ng = C / CPT;
   const long long total = L * ng;
   const float* hb = har + (long long)b * L_har;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int gch = (int)(idx / L);
-    const long long t = idx % L;
-    const int c = gch * 8;
-    float acc[8];
+    const long long t = idx - (long long)gch * L;
+    const int c = gch * CPT;
+    float4 xv[CPT / 4];
+    unsigned char* px = x32 + (((long long)b * (C / 4) + c / 4) * Lp + padf + t) * 16;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = sw[k * C + c + i];
+    for (int q = 0; q < CPT / 4; ++q) xv[q] = *reinterpret_cast<const float4*>(px + (long long)q * Lp * 16);
+    float acc[CPT];
+#pragma unroll
+    for (int q = 0; q < CPT / 4; ++q) {
+      const float4 bq = *reinterpret_cast<const float4*>(sw + k * C + c + q * 4);
+      acc[q * 4 + 0] = bq.x; acc[q * 4 + 1] = bq.y; acc[q * 4 + 2] = bq.z; acc[q * 4 + 3] = bq.w;
+    }
     const long long h0 = t * s - pad;
     for (int kk = 0; kk < k; ++kk) {
       const long long h = h0 + kk;
       if (h < 0 || h >= L_har) continue;
       const float hv = __ldg(hb + h);
+      const float* wr = sw + kk * C + c;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(hv, sw[kk * C + c + i], acc[i]);
+      for (int q = 0; q < CPT / 4; ++q) {
+        const float4 wq = *reinterpret_cast<const float4*>(wr + q * 4);
+        acc[q * 4 + 0] = fmaf(hv, wq.x, acc[q * 4 + 0]);
+        acc[q * 4 + 1] = fmaf(hv, wq.y, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(hv, wq.z, acc[q * 4 + 2]);
+        acc[q * 4 + 3] = fmaf(hv, wq.w, acc[q * 4 + 3]);
+      }
     }
-    float4* p0 = reinterpret_cast<float4*>(x32 + (((long long)b * (C / 4) + gch * 2) * Lp + padf + t) * 16);
-    float4* p1 = reinterpret_cast<float4*>(x32 + (((long long)b * (C / 4) + gch * 2 + 1) * Lp + padf + t) * 16);
-    float4 a = *p0, d = *p1;
-    a.x += acc[0]; a.y += acc[1]; a.z += acc[2]; a.w += acc[3];
-    d.x += acc[4]; d.y += acc[5]; d.z += acc[6]; d.w += acc[7];
-    *p0 = a; *p1 = d;
-    uint4 o;
-    o.x = pack2(BF16, lrelu(a.x, slope), lrelu(a.y, slope));
-    o.y = pack2(BF16, lrelu(a.z, slope), lrelu(a.w, slope));
-    o.z = pack2(BF16, lrelu(d.x, slope), lrelu(d.y, slope));
-    o.w = pack2(BF16, lrelu(d.z, slope), lrelu(d.w, slope));
-    *reinterpret_cast<uint4*>(x16 + (((long long)b * L + t) * C + c) * 2) = o;
+#pragma unroll
+    for (int q = 0; q < CPT / 4; ++q) {
+      xv[q].x += acc[q * 4 + 0]; xv[q].y += acc[q * 4 + 1]; xv[q].z += acc[q * 4 + 2]; xv[q].w += acc[q * 4 + 3];
+      *reinterpret_cast<float4*>(px + (long long)q * Lp * 16) = xv[q];
+    }
+    unsigned char* p16 = x16 + (((long long)b * L + t) * C + c) * 2;
+#pragma unroll
+    for (int q = 0; q < CPT / 8; ++q) {
+      const float4 a = xv[2 * q], d = xv[2 * q + 1];
+      uint4 o;
+      o.x = pack2(BF16, lrelu(a.x, slope), lrelu(a.y, slope));
+      o.y = pack2(BF16, lrelu(a.z, slope), lrelu(a.w, slope));
+      o.z = pack2(BF16, lrelu(d.x, slope), lrelu(d.y, slope));
+      o.w = pack2(BF16, lrelu(d.z, slope), lrelu(d.w, slope));
+      *reinterpret_cast<uint4*>(p16 + q * 16) = o;
+    }
   }
 }
 
@@ -844,15 +670,19 @@ cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* 
                                 long long L_har, long long L, int C, int k, int s, int pad, int Lp, int padf, float slope,
                                 bool bf16, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)k * C + C);
-  static size_t cfg = 48 * 1024;
-  if (smem > cfg) {
-    cudaError_t e = cudaFuncSetAttribute(noise_add_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  const int cpt = C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8);
+  auto kern = cpt == 32 ? noise_add_pv_kernel<32> : (cpt == 16 ? noise_add_pv_kernel<16> : noise_add_pv_kernel<8>);
+  static size_t cfg[3] = {48 * 1024, 48 * 1024, 48 * 1024};
+  size_t& c = cfg[cpt == 32 ? 0 : (cpt == 16 ? 1 : 2)];
+  if (smem > c) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cfg = smem;
+    c = smem;
   }
-  dim3 grid(grid_for(L * (C / 8), 256), B);
-  noise_add_pv_kernel<<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32),
-                                               reinterpret_cast<unsigned char*>(x16), L_har, L, C, k, s, pad, Lp, padf, slope, bf16);
+  dim3 grid(grid_for(L * (C / cpt), 256), B);
+  kern<<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32), reinterpret_cast<unsigned char*>(x16), L_har, L,
+                                C, k, s, pad, Lp, padf, slope, bf16);
   launch_counter().n++;
   return cudaGetLastError();
 }

@@ -12,6 +12,9 @@ constexpr int kPadF = 32;                                   // zero rows in fron
 inline int pv_pitch_rows(long long L) { return (int)(((L + 127) / 128) * 128 + 128); }   // Lp
 
 cudaError_t launch_conv_tc(const TcConvDesc& d, int B, cudaStream_t st);
+// Compile-time specialised resblock convolution (rbconv_tc.cu); cudaErrorNotSupported if the shape is not covered.
+bool rbconv_tc_supported(const TcConvDesc& d);
+cudaError_t launch_rbconv_tc(const TcConvDesc& d, int B, cudaStream_t st);
 cudaError_t launch_zero_pads(void* base, long long planes, int Lp, int padf, long long L, cudaStream_t st);
 cudaError_t launch_cl32_to_cl16(const float* x, void* y16, long long numel, float slope, bool bf16, cudaStream_t st);
 cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, int B,

@@ -821,6 +821,13 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     auto W16h = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, 1, &ok); };
     const int rb_bf16 = bf16 ? 1 : 0;
     static const int tc_a_mode = [] { const char* e = getenv("RVCB200_TC_AMODE"); return e ? atoi(e) : 0; }();
+    // resblock convs run on the compile-time specialised kernel (rbconv_tc.cu) when it covers the shape;
+    // RVCB200_RBCONV=0 forces the generic kernel (A/B measurements)
+    static const int use_rb = [] { const char* e = getenv("RVCB200_RBCONV"); return e ? atoi(e) : 1; }();
+    auto launch_rb = [&](const TcConvDesc& d) -> cudaError_t {
+      if (use_rb && rbconv_tc_supported(d)) return launch_rbconv_tc(d, B, st);
+      return launch_conv_tc(d, B, st);
+    };
     auto tmem_cols_for = [](int N) { int c = 32; while (c < N) c <<= 1; return c; };
     auto tc_base = [&]() {
       TcConvDesc d;
@@ -901,7 +908,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
             d.y16 = XT16; d.out_slope = 0.1f;
             if (!ok) return RVCB200_ERR_MISSING;
             d.in_bf16 = rb_bf16; d.out_bf16 = rb_bf16;
-            CKC(0, launch_conv_tc(d, B, st), "dec.rb.c1(tc)");
+            CKC(0, launch_rb(d), "dec.rb.c1(tc)");
             o.x16 = XT16; o.dil = 1; o.g_off[0] = -((k - 1) / 2);
             o.w16 = W16(S("dec.rb.%d.c2.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c2.%d.b", n, dd));
           } else {
@@ -919,7 +926,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
             o.y32 = XB32; o.y16 = XB16; o.out_slope = 0.1f;
           }
           if (!ok) return RVCB200_ERR_MISSING;
-          CKC(0, launch_conv_tc(o, B, st), "dec.rb.c2(tc)");
+          CKC(0, launch_rb(o), "dec.rb.c2(tc)");
           src16 = XB16; src32 = XB32;
         }
       }
@@ -946,6 +953,12 @@ int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream) {
   if (!d) return RVCB200_ERR_ARG;
   cudaError_t e = launch_conv_tc(*d, B, reinterpret_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int rvcb200_op_rbconv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream) {
+  if (!d) return RVCB200_ERR_ARG;
+  cudaError_t e = launch_rbconv_tc(*d, B, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : ((e == cudaErrorInvalidValue || e == cudaErrorNotSupported) ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 
 int64_t rvcb200_op_sine_scratch_bytes(int32_t B, int32_t T, int32_t upp) { return (int64_t)sine_scratch_bytes(B, T, upp); }

@@ -1,0 +1,410 @@
+// Compile-time specialised tcgen05 convolution for the decoder's ResBlock convs (C_in = C_out = C, zero "same"
+// padding, kernel NTAPS, dilation DIL) -- the 72 launches that are >70 % of a synthesis step.
+//
+// Why a second kernel next to conv_tc.cu: the ncu source view of the generic kernel on the narrow stages
+// (profiles/r1_ncu_conv_tc_v5.md) shows the tensor pipe 3-10 % busy, DRAM 23-50 % busy and the single MMA-issuing
+// warp executing ~256 SASS instructions per 128-row tile for 6 MMAs (runtime loop bounds, ring arithmetic, R2UR
+// traffic): the kernel is bound by per-tile instruction overhead of the issuing warp.  Here
+//   * every loop bound, descriptor offset and smem address is a compile-time constant (C, NTAPS, DIL, MSUB),
+//   * one "tile" is MSUB x 128 time rows: one activation slab (MSUB*128 + halo rows per 64-channel k-block, loaded
+//     by <= 3 TMA boxes) feeds MSUB accumulators, so barrier round trips, ring updates and -- when the weights do
+//     not fit in shared memory (C = 128, k = 7/11; C = 256) -- the weight stream are amortised over MSUB x more work,
+//   * the epilogue software-pipelines the fp32 residual loads one 32-column chunk ahead of the TMEM reads,
+//   * the bias lives in shared memory.
+// Layouts, epilogue semantics and the weight packing are those of conv_tc.cu (see its header).
+#include "tc_ptx.cuh"
+
+namespace rvc {
+namespace {
+
+using namespace tc;
+
+constexpr int kRbThreads = 64 + 32 * 8;   // TMA producer warp, MMA warp, 8 epilogue warps (2 groups of 4)
+
+template <int C, int NTAPS, int DIL, int MSUB>
+struct RbCfg {
+  static constexpr int NKB = (C + 63) / 64;                // 64-channel k-blocks (one 128-byte swizzled row each)
+  static constexpr int KS = C >= 64 ? 4 : C / 16;          // K=16 MMA steps per k-block (zero-padded K is skipped)
+  static constexpr int TILE_M = MSUB * 128;
+  static constexpr int HALO = (NTAPS - 1) * DIL;
+  static constexpr int GOFF = -((NTAPS - 1) / 2) * DIL;    // "same" padding
+  static constexpr int R = TILE_M + HALO;                  // activation rows one tile needs
+  static constexpr int NBOX = (R + 255) / 256;             // TMA boxes are <= 256 rows
+  static constexpr int RB = (((R + NBOX - 1) / NBOX) + 7) & ~7;
+  static constexpr uint32_t A_BYTES = (uint32_t)NBOX * RB * 128;
+  static constexpr uint32_t W_BYTES = (uint32_t)C * 128;   // one (k-block, tap) weight tile [C][64] 16-bit
+  static constexpr int NW = NKB * NTAPS;
+  static constexpr bool STAT = (size_t)NW * W_BYTES <= 96 * 1024;   // weights resident for the whole CTA
+  static constexpr int NB = STAT ? NW : (C >= 256 ? 3 : 6);
+  static constexpr int SMEM_BUDGET = 218 * 1024;
+  static constexpr int NA_FIT = (int)((SMEM_BUDGET - (size_t)NB * W_BYTES) / A_BYTES);
+  static constexpr int NA = NA_FIT > 6 ? 6 : NA_FIT;
+  static constexpr int TMEM_COLS = 2 * MSUB * C;           // two accumulator buffers of MSUB sub-tiles
+  static constexpr int NCH = MSUB * (C / 32);              // 32-column epilogue chunks per tile and warp
+  static constexpr size_t SMEM = 1024 + (size_t)NA * A_BYTES + (size_t)NB * W_BYTES + C * sizeof(float) +
+                                 8 * (2 * NA + 2 * NB + 4) + 64;
+  static_assert(C % 32 == 0 && C <= 256, "C");
+  static_assert(NA >= 2, "activation ring too small");
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+  static_assert(RB <= 256 && A_BYTES % 1024 == 0 && W_BYTES % 1024 == 0, "box");
+};
+
+template <int C, int NTAPS, int DIL, int MSUB>
+__global__ void __launch_bounds__(kRbThreads, 1)
+rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
+  using K = RbCfg<C, NTAPS, DIL, MSUB>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                                       // [NA][SLAB_ROWS][128 B] swizzled
+  unsigned char* sW = sA + (size_t)K::NA * K::A_BYTES;            // [NB][C][128 B] swizzled
+  float* sbias = reinterpret_cast<float*>(sW + (size_t)K::NB * K::W_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + C);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + K::NA;
+  uint64_t* b_full = a_empty + K::NA;
+  uint64_t* b_empty = b_full + K::NB;
+  uint64_t* acc_full = b_empty + K::NB;     // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const unsigned n_mt = (unsigned)((p.Lj + K::TILE_M - 1) / K::TILE_M);
+  const unsigned total_tiles = n_mt * (unsigned)p.batch;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < K::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < K::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)K::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < C; i += kRbThreads) sbias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== producer: TMA global -> swizzled smem ============================
+    if (lane == 0) {
+      if (K::STAT) {
+#pragma unroll 1
+        for (int i = 0; i < K::NW; ++i) {            // slot i = kb * NTAPS + tap; packed row = (tap * NKB + kb) * C
+          const int kb = i / NTAPS, tap = i - kb * NTAPS;
+          mbar_expect_tx(&b_full[i], K::W_BYTES);
+          tma_load_2d(sW + (size_t)i * K::W_BYTES, &tmW, 0, (tap * K::NKB + kb) * C, &b_full[i]);
+        }
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 1, pb = 1;                       // producer waits on "empty" with inverted parity
+#pragma unroll 1
+      for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const unsigned b = tile / n_mt, mt = tile - b * n_mt;
+        const int row0 = (int)mt * K::TILE_M + K::GOFF;
+#pragma unroll 1
+        for (int kb = 0; kb < K::NKB; ++kb) {
+          mbar_wait(&a_empty[sa], pa);
+          mbar_expect_tx(&a_full[sa], K::A_BYTES);
+#pragma unroll
+          for (int j = 0; j < K::NBOX; ++j)
+            tma_load_3d(sA + (size_t)sa * K::A_BYTES + (size_t)j * K::RB * 128, &tmA, kb * 64, row0 + j * K::RB, (int)b,
+                        &a_full[sa]);
+          if (++sa == K::NA) { sa = 0; pa ^= 1; }
+          if (!K::STAT) {
+#pragma unroll 1
+            for (int tap = 0; tap < NTAPS; ++tap) {
+              mbar_wait(&b_empty[sb], pb);
+              mbar_expect_tx(&b_full[sb], K::W_BYTES);
+              tma_load_2d(sW + (size_t)sb * K::W_BYTES, &tmW, 0, (tap * K::NKB + kb) * C, &b_full[sb]);
+              if (++sb == K::NB) { sb = 0; pb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============ MMA issuer: warp-uniform control flow, fully unrolled per k-block, one elected lane issues ========
+    // (everything the MMAs consume is warp-uniform -- kernel parameters, loop counters and values broadcast with
+    //  __shfl_sync(.., 0) -- so descriptors live in uniform registers: SASS is UMOV/UIADD3 + UTCHMMA per MMA)
+    {
+      const uint32_t leader = elect_one() ? 1u : 0u;
+      const uint32_t fmt = p.in_bf16 ? 1u : 0u;
+      // instruction descriptor: D=F32 @4, A/B format @7/@10, K-major both, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t dproto = make_desc_sw128(0, 0);
+      const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo0 = (uint32_t)dproto;
+      const uint32_t sA_d = __shfl_sync(0xffffffffu, d_lo0 + (smem_u32(sA) >> 4), 0);
+      const uint32_t sW_d = __shfl_sync(0xffffffffu, d_lo0 + (smem_u32(sW) >> 4), 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      if (K::STAT) {
+#pragma unroll 1
+        for (int i = 0; i < K::NW; ++i) mbar_wait(&b_full[i], 0);
+        tc_fence_after();
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t it = 0;
+#pragma unroll 1
+      for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t buf = it & 1u;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1u) ^ 1u);       // the epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + buf * (uint32_t)(MSUB * C);
+#pragma unroll
+        for (int kb = 0; kb < K::NKB; ++kb) {
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_d = sA_d + (uint32_t)sa * (K::A_BYTES >> 4);
+#pragma unroll
+          for (int tap = 0; tap < NTAPS; ++tap) {
+            uint32_t b_d;
+            if (K::STAT) {
+              b_d = sW_d + (uint32_t)(kb * NTAPS + tap) * (K::W_BYTES >> 4);
+            } else {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              b_d = sW_d + (uint32_t)sb * (K::W_BYTES >> 4);
+            }
+#pragma unroll
+            for (int ms = 0; ms < MSUB; ++ms) {
+#pragma unroll
+              for (int ks = 0; ks < K::KS; ++ks) {
+                // activation rows of sub-tile ms shifted by tap*DIL: +128 B per row inside the swizzled slab
+                // (base_offset stays 0, see conv_tc.cu); +32 B per K=16 step inside the 128-byte row
+                tc_mma_f16_pred(d_tmem + (uint32_t)(ms * C), a_d + (uint32_t)(((ms * 128 + tap * DIL) * 128 + ks * 32) >> 4),
+                                d_hi, b_d + (uint32_t)((ks * 32) >> 4), d_hi, idesc, (kb | tap | ks) != 0 ? 1u : 0u, leader);
+              }
+            }
+            if (!K::STAT) {
+              tc_commit_pred(&b_empty[sb], leader);
+              if (++sb == K::NB) { sb = 0; pb ^= 1; }
+            }
+          }
+          tc_commit_pred(&a_empty[sa], leader);
+          if (++sa == K::NA) { sa = 0; pa ^= 1; }
+        }
+        tc_commit_pred(&acc_full[buf], leader);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============== epilogue: two groups of 4 warps, group e drains accumulator buffer e ==================
+    const int eg = (warp - 2) >> 2;
+    const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
+    const size_t pitch_o = (size_t)p.Lp_out * 16;   // bytes per planar-vector plane
+    const bool obf = p.out_bf16 != 0;
+    const float slope = p.out_slope;
+    const float inv_div = p.div;                    // divide (not multiply by reciprocal): matches the fp32 path
+    uint32_t it = (uint32_t)eg;
+#pragma unroll 1
+    for (unsigned tile = blockIdx.x + (unsigned)eg * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+      const unsigned b = tile / n_mt, mt = tile - b * n_mt;
+      const int row_base = (int)mt * K::TILE_M + qd * 32 + lane;
+      const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(eg * MSUB * C);
+      unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (C / 4) * pitch_o : nullptr;
+      const unsigned char* r32 = p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (C / 4) * pitch_o : nullptr;
+      unsigned char* y16 = p.y16 ? reinterpret_cast<unsigned char*>(p.y16) + (size_t)b * (size_t)p.Lj * C * 2 : nullptr;
+      const bool do_acc = p.accum != 0;
+
+      float4 rr[2][8];
+      auto load_res = [&](int ci, float4* dst) {
+        const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
+        const int row = row_base + ms * 128;
+        if (r32 != nullptr && row < p.Lj) {
+          const unsigned char* q = r32 + (size_t)(c0 / 4) * pitch_o + (size_t)(row + p.padf) * 16;
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) dst[k4] = *reinterpret_cast<const float4*>(q + (size_t)k4 * pitch_o);
+        }
+      };
+      load_res(0, rr[0]);                            // residual of the first chunk is in flight before the MMAs finish
+      mbar_wait(&acc_full[eg], (it >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < K::NCH; ++ci) {
+        const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
+        const int row = row_base + ms * 128;
+        const bool row_ok = row < p.Lj;
+        if (ci + 1 < K::NCH) load_res(ci + 1, rr[(ci + 1) & 1]);
+        uint32_t r[32];
+        const uint32_t taddr = tbase + (uint32_t)(ms * C + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+            "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row_ok) {
+          const size_t orow16 = (size_t)(row + p.padf) * 16;
+          float v[32];
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) {
+            const float4 bq = *reinterpret_cast<const float4*>(sbias + c0 + k4 * 4);
+            v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
+            v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
+            v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
+            v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
+          }
+          if (r32 != nullptr) {
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 rq = rr[ci & 1][k4];
+              v[k4 * 4 + 0] += rq.x; v[k4 * 4 + 1] += rq.y; v[k4 * 4 + 2] += rq.z; v[k4 * 4 + 3] += rq.w;
+            }
+          }
+          if (do_acc) {
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 aq = *reinterpret_cast<const float4*>(y32 + (size_t)(c0 / 4 + k4) * pitch_o + orow16);
+              v[k4 * 4 + 0] += aq.x; v[k4 * 4 + 1] += aq.y; v[k4 * 4 + 2] += aq.z; v[k4 * 4 + 3] += aq.w;
+            }
+          }
+          if (inv_div != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
+          }
+          if (y32 != nullptr) {
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4)
+              *reinterpret_cast<float4*>(y32 + (size_t)(c0 / 4 + k4) * pitch_o + orow16) =
+                  make_float4(v[k4 * 4 + 0], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
+          }
+          if (y16 != nullptr) {
+            unsigned char* yr = y16 + ((size_t)row * C + c0) * 2;
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              uint4 o;
+              o.x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
+              o.y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
+              o.z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
+              o.w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
+              *reinterpret_cast<uint4*>(yr + k8 * 16) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[eg])) : "memory");
+    }
+  }
+  // ------------------------------------ teardown -------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K::TMEM_COLS));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn rb_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int C, int NTAPS, int DIL, int MSUB>
+cudaError_t launch_one(const TcConvDesc& d, int B, cudaStream_t st) {
+  using K = RbCfg<C, NTAPS, DIL, MSUB>;
+  EncodeTiledFn enc = rb_encode_tiled();
+  if (!enc) return cudaErrorNotSupported;
+  CUtensorMap tmA, tmW;
+  const CUtensorMapDataType dt = d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint32_t es[3] = {1, 1, 1};
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)d.L_in, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * (cuuint64_t)d.L_in};
+    cuuint32_t box[3] = {64, (cuuint32_t)K::RB, 1};
+    if (enc(&tmA, dt, 3, const_cast<void*>(d.x16), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    cuuint64_t wdims[2] = {64, (cuuint64_t)NTAPS * K::NKB * C};
+    cuuint64_t wstrides[1] = {128};
+    cuuint32_t wbox[2] = {64, (cuuint32_t)C};
+    if (enc(&tmW, dt, 2, const_cast<void*>(d.w16), wdims, wstrides, wbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rbconv_tc_kernel<C, NTAPS, DIL, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)K::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  TcConvDesc p = d;
+  p.batch = B;
+  const long long tiles = (long long)((d.Lj + K::TILE_M - 1) / K::TILE_M) * B;
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
+  rbconv_tc_kernel<C, NTAPS, DIL, MSUB><<<grid, kRbThreads, K::SMEM, st>>>(p, tmA, tmW);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+template <int C, int MSUB>
+cudaError_t launch_c(const TcConvDesc& d, int B, cudaStream_t st) {
+  switch (d.ntaps * 16 + d.dil) {
+    case 3 * 16 + 1: return launch_one<C, 3, 1, MSUB>(d, B, st);
+    case 3 * 16 + 3: return launch_one<C, 3, 3, MSUB>(d, B, st);
+    case 3 * 16 + 5: return launch_one<C, 3, 5, MSUB>(d, B, st);
+    case 7 * 16 + 1: return launch_one<C, 7, 1, MSUB>(d, B, st);
+    case 7 * 16 + 3: return launch_one<C, 7, 3, MSUB>(d, B, st);
+    case 7 * 16 + 5: return launch_one<C, 7, 5, MSUB>(d, B, st);
+    case 11 * 16 + 1: return launch_one<C, 11, 1, MSUB>(d, B, st);
+    case 11 * 16 + 3: return launch_one<C, 11, 3, MSUB>(d, B, st);
+    case 11 * 16 + 5: return launch_one<C, 11, 5, MSUB>(d, B, st);
+    default: return cudaErrorNotSupported;
+  }
+}
+
+}  // namespace
+
+bool rbconv_tc_supported(const TcConvDesc& d) {
+  if (d.generic || d.G != 1 || d.out_stride != 1 || d.cond != nullptr || d.a_mode != 0) return false;
+  if (d.Cin != d.Cout_total || d.N != d.Cin || d.L_in != d.Lj) return false;
+  if (!(d.Cin == 32 || d.Cin == 64 || d.Cin == 128 || d.Cin == 256)) return false;
+  if (!(d.ntaps == 3 || d.ntaps == 7 || d.ntaps == 11) || !(d.dil == 1 || d.dil == 3 || d.dil == 5)) return false;
+  if (d.g_off[0] != -((d.ntaps - 1) / 2) * d.dil) return false;
+  if ((d.accum && !d.y32) || !d.x16 || !d.w16 || !d.bias) return false;
+  return true;
+}
+
+// Resblock convolution on the specialised kernel; cudaErrorNotSupported when the shape is not covered
+// (the caller falls back to launch_conv_tc).
+cudaError_t launch_rbconv_tc(const TcConvDesc& d, int B, cudaStream_t st) {
+  if (!rbconv_tc_supported(d) || B <= 0) return cudaErrorNotSupported;
+  switch (d.Cin) {
+    case 32: return launch_c<32, 4>(d, B, st);
+    case 64: return launch_c<64, 2>(d, B, st);
+    case 128: return launch_c<128, 2>(d, B, st);
+    case 256: return launch_c<256, 1>(d, B, st);
+    default: return cudaErrorNotSupported;
+  }
+}
+
+}  // namespace rvc

@@ -189,6 +189,11 @@ typedef struct rvcb200_tc_conv_desc {
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 
+/* Same contract, compile-time specialised kernel for the decoder ResBlock shapes (csrc/rbconv_tc.cu): Cin = Cout = N in
+ * {32, 64, 128, 256}, ntaps in {3, 7, 11}, dil in {1, 3, 5}, "same" padding, G = 1, no cond, lean epilogue.  Returns
+ * RVCB200_ERR_ARG for any other shape (the engine then uses rvcb200_op_conv_tc's kernel). */
+int rvcb200_op_rbconv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
+
 /* NSF harmonic source (SineGen + SourceModuleHnNSF, models.py:361-411,455-467):
  * f0 [B][T] -> har [B][T*upp]; scratch >= rvcb200_op_sine_scratch_bytes(B,T,upp). */
 int64_t rvcb200_op_sine_scratch_bytes(int32_t B, int32_t T, int32_t upp);

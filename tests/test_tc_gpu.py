@@ -105,6 +105,91 @@ def test_conv_tc(case, bf16, a_mode):
     assert err16 < (0.08 if bf16 else 0.02)
 
 
+RB_CASES = [
+    # name, B, L, C, ntaps, dil  (every C of the specialised kernel; stationary and streamed weights; ragged last tiles)
+    ("rb_c32_k3_d1", 1, 1000, 32, 3, 1),
+    ("rb_c32_k11_d5_long", 2, 70001, 32, 11, 5),
+    ("rb_c32_k7_d3", 1, 513, 32, 7, 3),
+    ("rb_c64_k3_d5", 1, 300, 64, 3, 5),
+    ("rb_c64_k7_d3_long", 1, 60000, 64, 7, 3),
+    ("rb_c64_k11_d1_long", 2, 38000, 64, 11, 1),
+    ("rb_c128_k3_d1_long", 1, 45000, 128, 3, 1),
+    ("rb_c128_k7_d1_ring_long", 1, 45000, 128, 7, 1),
+    ("rb_c128_k11_d5_ring", 2, 5000, 128, 11, 5),
+    ("rb_c256_k3_d3", 1, 300, 256, 3, 3),
+    ("rb_c256_k11_d5_long", 1, 24000, 256, 11, 5),
+    ("rb_c256_k7_d1", 3, 700, 256, 7, 1),
+]
+
+
+@pytest.mark.parametrize("kind", ["c1", "c2", "c2_accum_div"])
+@pytest.mark.parametrize("bf16", [False, True], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("case", RB_CASES, ids=[c[0] for c in RB_CASES])
+def test_rbconv_tc(case, bf16, kind):
+    """Specialised resblock kernel vs the fp64 restatement, and bit-identical to the generic tcgen05 kernel."""
+    name, B, L, Cc, ntaps, dil = case
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    dt = torch.bfloat16 if bf16 else torch.float16
+    g = torch.Generator().manual_seed(len(name) * 7 + Cc + ntaps)
+    x = torch.randn(B, L, Cc, generator=g).to(dt).float()
+    w = (torch.randn(1, ntaps, Cc, Cc, generator=g) / math.sqrt(Cc * ntaps)).to(dt).float()
+    bias = torch.randn(Cc, generator=g)
+    res = torch.randn(B, L, Cc, generator=g)
+    acc0 = torch.randn(B, L, Cc, generator=g)
+    g_off = [-((ntaps - 1) // 2) * dil]
+    ref = conv_cl(x.double(), w.double(), bias.double(), g_off=g_off, dil=dil, out_stride=1)
+    if kind != "c1":
+        ref = ref + res.double()
+    if kind == "c2_accum_div":
+        ref = (ref + acc0.double()) / 3.0
+    x16 = x.to(dt).to(dev).contiguous()
+    r32 = to_pv(res, 4, torch.float32).to(dev)
+    w16 = weights.pack_tc(w, dt).to(dev)
+    bd = bias.to(dev)
+    outs = []
+    for fn in (lib.rvcb200_op_rbconv_tc, lib.rvcb200_op_conv_tc):
+        y32 = to_pv(acc0, 4, torch.float32).to(dev) if kind == "c2_accum_div" else torch.zeros(B, Cc // 4, pitch(L), 4, device=dev)
+        y16 = torch.zeros(B, L, Cc, dtype=dt, device=dev)
+        d = _lib.TcConvDesc()
+        d.x16, d.L_in, d.padf = x16.data_ptr(), L, PADF
+        d.w16, d.bias = w16.data_ptr(), bd.data_ptr()
+        d.Cin, d.ntaps, d.dil, d.G = Cc, ntaps, dil, 1
+        d.g_off[0] = g_off[0]
+        d.N, d.Cout_total = Cc, Cc
+        d.Lj, d.out_stride, d.Lp_out = L, 1, pitch(L)
+        d.y16, d.out_slope, d.div = y16.data_ptr(), 0.1, 1.0
+        if kind != "c1":
+            d.y32, d.res32 = y32.data_ptr(), r32.data_ptr()
+        if kind == "c2_accum_div":
+            d.accum, d.div = 1, 3.0
+        d.in_bf16 = d.out_bf16 = int(bf16)
+        st = fn(C.byref(d), B, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert st == 0, st
+        torch.cuda.synchronize()
+        outs.append((y32.cpu(), y16.cpu()))
+    (y32, y16), (g32, g16) = outs
+    want16 = torch.where(ref > 0, ref, ref * 0.1)
+    err16 = (y16.float().double() - want16).abs().max().item()
+    assert err16 < (0.08 if bf16 else 0.02), err16
+    if kind != "c1":
+        got = from_pv(y32, L).double()
+        err = (got - ref).abs().max().item()
+        print(f"rbconv {name} {kind} {'bf16' if bf16 else 'fp16'}: max abs err {err:.3e}")
+        assert err < 1e-3
+        assert float(y32[:, :, :PADF].abs().max()) == 0.0 and float(y32[:, :, PADF + L:].abs().max()) == 0.0
+        assert torch.equal(y32, g32)          # same MMA order, same epilogue arithmetic as the generic kernel
+    assert torch.equal(y16.view(torch.int16), g16.view(torch.int16))
+
+
+def test_rbconv_rejects_other_shapes():
+    d = _lib.TcConvDesc()
+    d.Cin = d.Cout_total = d.N = 16
+    d.ntaps, d.dil, d.G, d.out_stride, d.L_in, d.Lj = 3, 1, 1, 1, 100, 100
+    d.g_off[0] = -1
+    assert _lib.load().rvcb200_op_rbconv_tc(C.byref(d), 1, None) == 1
+
+
 @pytest.mark.parametrize("T,lens", [(7, [7]), (64, [64, 33]), (300, [300, 211]), (1000, [1000]), (2500, [2500, 1999])])
 def test_attention_tc(T, lens):
     """tcgen05 attention vs the fp64 banded restatement on fp16-rounded operands."""

@@ -33,10 +33,12 @@ def main():
     ap.add_argument("--T", type=int, default=6000)
     ap.add_argument("--a-mode", type=int, default=0)
     ap.add_argument("--dbg-alt", type=int, default=0)
+    ap.add_argument("--rb", type=int, default=1, help="1: specialised resblock kernel (rbconv_tc.cu), 0: generic conv_tc")
     ap.add_argument("--stages", default="", help="comma list of stage indices (0-3) to keep")
     ap.add_argument("--ks", default="", help="comma list of kernel sizes to keep (default all)")
     args = ap.parse_args()
     lib = _lib.load()
+    conv_fn = lib.rvcb200_op_rbconv_tc if args.rb else lib.rvcb200_op_conv_tc
     dev = torch.device("cuda", 0)
     stages = [(256, args.T * 12), (128, args.T * 120), (64, args.T * 240), (32, args.T * 480)]
     rows = []
@@ -71,14 +73,14 @@ def main():
                     d.y32, d.res32 = y32.data_ptr(), r32.data_ptr()
                 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
                 for _ in range(2):
-                    assert lib.rvcb200_op_conv_tc(C.byref(d), 1, st) == 0
+                    assert conv_fn(C.byref(d), 1, st) == 0
                 torch.cuda.synchronize()
                 if args.profile:
                     torch.cuda.profiler.start()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(args.reps):
-                    lib.rvcb200_op_conv_tc(C.byref(d), 1, st)
+                    conv_fn(C.byref(d), 1, st)
                 e1.record()
                 torch.cuda.synchronize()
                 if args.profile:
@@ -86,7 +88,7 @@ def main():
                 us = e0.elapsed_time(e1) * 1e3 / args.reps
                 flops = 2.0 * L * Cc * Cc * k
                 bytes_ = L * Cc * (2 + 2 + (8 if kind == "c2" else 0))
-                rows.append(dict(a_mode=args.a_mode, stage=si + 1, C=Cc, L=L, k=k, dil=dil, kind=kind, us=round(us, 1),
+                rows.append(dict(rb=args.rb, a_mode=args.a_mode, stage=si + 1, C=Cc, L=L, k=k, dil=dil, kind=kind, us=round(us, 1),
                                  tflops=round(flops / us / 1e6, 1), hbm_gbs=round(bytes_ / us / 1e3, 1)))
                 print(json.dumps(rows[-1]), flush=True)
     return rows
