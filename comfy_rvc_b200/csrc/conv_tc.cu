@@ -209,11 +209,15 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Tile order: phase g fastest, then the N tile, then the M tile.  The G phases (and N tiles) of one M tile run on
+  // neighbouring CTAs at the same time, so the activation slab is read from HBM once (L2 hits for the rest) and the
+  // row-interleaved outputs of a transposed conv (row = t*G + g: 16-byte pieces of the same 32-byte sectors / 128-byte
+  // lines written by different phases) merge in L2 instead of being evicted half-written.
   auto decode = [&](long long t, int& mt, int& nt, int& g, int& b) {
-    mt = (int)(t % n_mt); t /= n_mt;
+    g = (int)(t % p.G); t /= p.G;
     nt = (int)(t % n_nt); t /= n_nt;
-    g = (int)(t % p.G);
-    b = (int)(t / p.G);
+    mt = (int)(t % n_mt);
+    b = (int)(t / n_mt);
   };
   // weight row coordinate of tile (g, nt), tap, k-block in the [..][N][64] table
   auto w_row = [&](int g, int nt, int tap, int kb) { return (((g * n_nt + nt) * p.ntaps + tap) * nkb + kb) * p.N; };

@@ -598,7 +598,9 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     // ====== TextEncoder + reverse flow with every contraction on tcgen05 (fp16 operands, fp32 epilogues) ======
     auto W16h = [&](const std::string& n) { return T16(ctx, n + ".tc", 0, 1, &ok); };
     static const bool tc_attention = [] { const char* e = getenv("RVCB200_TC_ATTENTION"); return e ? atoi(e) != 0 : true; }();
-    auto n_for = [](int cout) { for (int n = 256; n >= 16; n -= 16) if (cout % n == 0) return n; return 16; };
+    // N tile of the encoder/flow contractions: capped at 64 columns (weights.py tc_n_max_for_name): with only T/128
+    // M tiles per launch, narrow N tiles occupy 3-12x more SMs and each CTA pulls 3-4x fewer weight bytes from L2
+    auto n_for = [](int cout) { for (int n = 64; n >= 16; n -= 16) if (cout % n == 0) return n; return 16; };
     auto gen = [&](const void* x16, int Cin, const std::string& wname, const std::string& bname, int Cout) {
       TcConvDesc d;
       memset(&d, 0, sizeof(d));

@@ -24,7 +24,7 @@ from torch import nn
 
 from . import _lib
 from .config import SynthConfig
-from .weights import pack, pack_tc, tc_weight_names, validate_state_dict
+from .weights import pack, pack_tc, tc_n_max_for_name, tc_weight_names, validate_state_dict
 
 
 class _IncompatibleKeys:
@@ -178,7 +178,7 @@ class SynthesizerB200(nn.Module):
                 resblock = name.startswith("dec.rb.")
                 prec = self.precision if resblock else "fp16"      # ladder, text encoder and flow: always fp16
                 dtype = torch.float16 if prec == "fp16" else torch.bfloat16
-                t = pack_tc(self._packed[name].cpu(), dtype).to(self._device)
+                t = pack_tc(self._packed[name].cpu(), dtype, tc_n_max_for_name(name)).to(self._device)
                 key = f"{name}.tc"
                 self._packed[f"{key}#{self.precision}"] = t          # keep alive; the engine holds the pointer
                 _lib.check(lib.rvcb200_set_tensor(self._ctx, key.encode(), C.c_void_p(t.data_ptr()), t.numel(),

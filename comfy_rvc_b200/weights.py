@@ -202,15 +202,25 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
 TC_KB, TC_N_MAX = 64, 256
 
 
-def tc_n_for(cout: int) -> int:
-    """MMA N tile: the largest multiple of 16 <= 256 dividing C_out (same rule as csrc/engine.cu)."""
-    for n in range(TC_N_MAX, 15, -16):
+TC_N_MAX_SMALL_M = 64   # text encoder / flow: few 128-row tiles per launch (T/128), so split C_out over more CTAs
+
+
+def tc_n_max_for_name(name: str) -> int:
+    """N-tile cap per packed tensor (same rule as csrc/engine.cu): the decoder's long time axis fills the GPU with
+    M tiles and wants wide N; the text encoder and flow have T/128 (~47) M tiles per launch, so C_out is split into
+    64-column tiles to occupy 3-12x more SMs and to cut the weight bytes each CTA has to pull from L2."""
+    return TC_N_MAX if name.startswith("dec.") else TC_N_MAX_SMALL_M
+
+
+def tc_n_for(cout: int, n_max: int = TC_N_MAX) -> int:
+    """MMA N tile: the largest multiple of 16 <= n_max dividing C_out (same rule as csrc/engine.cu)."""
+    for n in range(n_max, 15, -16):
         if cout % n == 0:
             return n
     raise ValueError(cout)
 
 
-def pack_tc(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+def pack_tc(w: torch.Tensor, dtype: torch.dtype, n_max: int = TC_N_MAX) -> torch.Tensor:
     """[G][taps][C_in][C_out] (or [taps][C_in][C_out]) fp32 -> [G][C_out/N][taps][ceil(C_in/64)][N][64] 16-bit.
 
     One (tap, k-block) slice is an [N][64] K-major matrix (input channels contiguous, zero-padded to
@@ -220,7 +230,7 @@ def pack_tc(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     elif w.dim() == 3:
         w = w.unsqueeze(0)
     G, taps, cin, cout = w.shape
-    N = tc_n_for(cout)
+    N = tc_n_for(cout, n_max)
     nkb = (cin + TC_KB - 1) // TC_KB
     assert cout % N == 0 and N % 16 == 0, (cin, cout)
     if nkb * TC_KB != cin:
