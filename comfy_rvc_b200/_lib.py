@@ -67,6 +67,7 @@ class TcConvDesc(C.Structure):
         ("alpha", C.c_float), ("pre_slope", C.c_float), ("relu", C.c_int32), ("gate", C.c_int32),
         ("res_mode", C.c_int32), ("mask_pre", C.c_int32), ("mask_post", C.c_int32), ("mask16", C.c_int32),
         ("out_len", C.c_void_p), ("dbg_alt", C.c_int32),
+        ("res16", C.c_void_p), ("res_neg_scale", C.c_float), ("a_fp16", C.c_int32), ("acc_f16", C.c_int32),
     ]
 
 

@@ -385,18 +385,21 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           epilogue_generic16(p, tbase + (uint32_t)c0, row_ok, valid, b, orow, nt * p.N + c0);
       } else {
         const size_t orow16 = (size_t)(orow + p.padf) * 16;
-        unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
+        unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (p.Cout_total / (p.acc_f16 ? 8 : 4)) * pitch_o
+                                    : nullptr;
         unsigned char* y16row = p.y16 ? reinterpret_cast<unsigned char*>(p.y16) + ((size_t)b * Lout + orow) * p.Cout_total * 2
                                       : nullptr;
         const unsigned char* r32 =
             p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (p.Cout_total / 4) * pitch_o : nullptr;
         const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
+        const unsigned char* r16row =
+            p.res16 ? reinterpret_cast<const unsigned char*>(p.res16) + ((size_t)b * Lout + orow) * p.Cout_total * 2 : nullptr;
         if (p.N % 32 == 0) {
           for (int c0 = 0; c0 < p.N; c0 += 32)
-            epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond);
+            epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row);
         } else {
           for (int c0 = 0; c0 < p.N; c0 += 16)
-            epilogue_chunk<16>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond);
+            epilogue_chunk<16>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row);
         }
       }
       tc_fence_before();
@@ -470,7 +473,8 @@ __global__ void cl32_to_cl16_kernel(const float* __restrict__ x, unsigned char* 
 // and one contiguous CPT*2-byte piece of the 16-bit row (whole 32-byte sectors, no partial-sector writes).
 template <int CPT>
 __global__ void noise_add_pv_kernel(const float* __restrict__ har, const float* __restrict__ wn, const float* __restrict__ nb,
-                                    unsigned char* __restrict__ x32, unsigned char* __restrict__ x16, long long L_har,
+                                    unsigned char* __restrict__ x32, unsigned char* __restrict__ x16,
+                                    unsigned char* __restrict__ xr16, int write32, long long L_har,
                                     long long L, int C, int k, int s, int pad, int Lp, int padf, float slope, bool BF16) {
   extern __shared__ float sw[];  // [k][C] + [C]
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
@@ -512,7 +516,18 @@ __global__ void noise_add_pv_kernel(const float* __restrict__ har, const float* 
 #pragma unroll
     for (int q = 0; q < CPT / 4; ++q) {
       xv[q].x += acc[q * 4 + 0]; xv[q].y += acc[q * 4 + 1]; xv[q].z += acc[q * 4 + 2]; xv[q].w += acc[q * 4 + 3];
-      *reinterpret_cast<float4*>(px + (long long)q * Lp * 16) = xv[q];
+      if (write32) *reinterpret_cast<float4*>(px + (long long)q * Lp * 16) = xv[q];
+    }
+    if (xr16 != nullptr) {   // raw fp16 copy: the residual stream the resblocks add
+      unsigned char* pr = xr16 + (((long long)b * L + t) * C + c) * 2;
+#pragma unroll
+      for (int q = 0; q < CPT / 8; ++q) {
+        const float4 a = xv[2 * q], d = xv[2 * q + 1];
+        uint4 o;
+        o.x = pack2(false, a.x, a.y); o.y = pack2(false, a.z, a.w);
+        o.z = pack2(false, d.x, d.y); o.w = pack2(false, d.z, d.w);
+        *reinterpret_cast<uint4*>(pr + q * 16) = o;
+      }
     }
     unsigned char* p16 = x16 + (((long long)b * L + t) * C + c) * 2;
 #pragma unroll
@@ -554,6 +569,57 @@ __global__ void conv_post_pv_kernel(const unsigned char* __restrict__ x32, const
   }
 }
 
+__device__ __forceinline__ void unpack8(const uint4& w, float* f) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// out[b][t] = tanh(sum_{kk,c} lrelu(x[c][t+kk-pad]) * w[kk][c]);  x is planar-vector fp16 [B][C/8][Lp][8] with zero pads.
+// One thread per output sample; each plane row (16 B) is loaded once and feeds the k outputs it contributes to through
+// a register window, so L1 traffic is 1x the tensor instead of k x.
+template <int KT>
+__global__ void conv_post_pv16_kernel(const unsigned char* __restrict__ x16, const float* __restrict__ w, float* __restrict__ out,
+                                      long long L, int C, int Lp, int padf, float slope) {
+  extern __shared__ float swp[];  // [KT][C]
+  for (int i = threadIdx.x; i < KT * C; i += blockDim.x) swp[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  constexpr int pad = (KT - 1) / 2;
+  const int n8 = C / 8;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < L; t += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int g8 = 0; g8 < n8; ++g8) {
+      const unsigned char* pl = x16 + (((long long)b * n8 + g8) * Lp + padf + t - pad) * 16;
+#pragma unroll
+      for (int kk = 0; kk < KT; ++kk) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(pl + (long long)kk * 16), f);
+        const float* wr = swp + kk * C + g8 * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(lrelu(f[i], slope), wr[i], acc);
+      }
+    }
+    out[(long long)b * L + t] = tanhf(acc);
+  }
+}
+
+__global__ void pv16_to_cl_kernel(const unsigned char* __restrict__ x16, float* __restrict__ y, long long L, int C, int Lp, int padf) {
+  // debug/tap helper: planar-vector fp16 -> fp32 channels-last [B][L][C]
+  const int b = blockIdx.y;
+  const int n8 = C / 8;
+  const long long total = L * n8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int g8 = (int)(idx / L);
+    const long long t = idx % L;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x16 + (((long long)b * n8 + g8) * Lp + padf + t) * 16), f);
+    float* o = y + ((long long)b * L + t) * C + g8 * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
 __global__ void pv32_to_cl_kernel(const unsigned char* __restrict__ x32, float* __restrict__ y, long long L, int C, int Lp, int padf) {
   // debug/tap helper: PV32 -> channels-last [B][L][C]
   const int b = blockIdx.y;
@@ -579,7 +645,8 @@ inline unsigned grid_for(long long total, int threads) {
 cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   TcConvDesc d = d_in;
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.Cin % 8 != 0 || d.Cout_total % d.N != 0 || d.G < 1 || d.G > 16 ||
-      d.Lj <= 0 || d.L_in <= 0 || (d.ntaps - 1) * d.dil > 120 || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16)
+      d.Lj <= 0 || d.L_in <= 0 || (d.ntaps - 1) * d.dil > 120 || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
+      d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)))
     return cudaErrorInvalidValue;
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return cudaErrorNotSupported;
@@ -670,9 +737,9 @@ cudaError_t launch_cl32_to_cl16(const float* x, void* y16, long long numel, floa
   return cudaGetLastError();
 }
 
-cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, int B,
-                                long long L_har, long long L, int C, int k, int s, int pad, int Lp, int padf, float slope,
-                                bool bf16, cudaStream_t st) {
+cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, void* xr16,
+                                bool write32, int B, long long L_har, long long L, int C, int k, int s, int pad, int Lp,
+                                int padf, float slope, bool bf16, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)k * C + C);
   if (C % 8 != 0) return cudaErrorInvalidValue;
   const int cpt = C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8);
@@ -685,8 +752,9 @@ cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* 
     c = smem;
   }
   dim3 grid(grid_for(L * (C / cpt), 256), B);
-  kern<<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32), reinterpret_cast<unsigned char*>(x16), L_har, L,
-                                C, k, s, pad, Lp, padf, slope, bf16);
+  kern<<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32), reinterpret_cast<unsigned char*>(x16),
+                                reinterpret_cast<unsigned char*>(xr16), write32 ? 1 : 0, L_har, L, C, k, s, pad, Lp, padf, slope,
+                                bf16);
   launch_counter().n++;
   return cudaGetLastError();
 }
@@ -696,6 +764,23 @@ cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int
   dim3 grid(grid_for(L, 256), B);
   conv_post_pv_kernel<<<grid, 256, sizeof(float) * k * C, st>>>(reinterpret_cast<const unsigned char*>(x32), w, out, L, C, k, Lp,
                                                                 padf, slope);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_post_pv16(const void* x16, const float* w, float* out, int B, long long L, int C, int k, int Lp,
+                                  int padf, float slope, cudaStream_t st) {
+  if (k != 7 || C % 8) return cudaErrorInvalidValue;
+  dim3 grid(grid_for(L, 256), B);
+  conv_post_pv16_kernel<7><<<grid, 256, sizeof(float) * k * C, st>>>(reinterpret_cast<const unsigned char*>(x16), w, out, L, C, Lp,
+                                                                    padf, slope);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pv16_to_cl(const void* src, float* y, int B, long long L, int C, int Lp, int padf, cudaStream_t st) {
+  dim3 grid(grid_for(L * (C / 8), 256), B);
+  pv16_to_cl_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(src), y, L, C, Lp, padf);
   launch_counter().n++;
   return cudaGetLastError();
 }

@@ -137,7 +137,7 @@ struct Plan {  // workspace carve-up for (B, T)
   void* sine_scratch;
   float* stage[5];
   // tensor-core path: planar-vector buffers
-  void* z16; void* pv16[5]; float* pv32[3];
+  void* z16; void* pv16[5]; float* pv32[2];
   void *phone16, *x16, *att16, *ffh16, *h16, *acts16, *skip16;   // fp16 MMA operands of enc_p / flow
   void *qkv16, *vt16;                                            // padded q|k|v and V^T for the tcgen05 attention
   size_t bytes;
@@ -177,7 +177,7 @@ Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws, int precision = RVC
     for (int i = 0; i < 5; ++i) p.stage[i] = bp.take<float>(mx);
     p.z16 = nullptr;
     for (int i = 0; i < 5; ++i) p.pv16[i] = nullptr;
-    for (int i = 0; i < 3; ++i) p.pv32[i] = nullptr;
+    for (int i = 0; i < 2; ++i) p.pv32[i] = nullptr;
   } else {
     for (int i = 0; i < 5; ++i) p.stage[i] = nullptr;
     size_t mxe = (size_t)B * cf.up_init_channels * pv_pitch_rows(T);      // conv_pre output
@@ -198,7 +198,7 @@ Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws, int precision = RVC
     p.qkv16 = bp.take<unsigned short>(BT * 3 * cf.n_heads * 128);
     p.vt16 = bp.take<unsigned short>((size_t)B * cf.n_heads * 128 * ((T + 7) & ~7));
     for (int i = 0; i < 5; ++i) p.pv16[i] = bp.take<unsigned short>(mxe);
-    for (int i = 0; i < 3; ++i) p.pv32[i] = bp.take<float>(mxe);
+    for (int i = 0; i < 2; ++i) p.pv32[i] = bp.take<float>(mxe);
   }
   p.bytes = bp.off;
   return p;
@@ -845,9 +845,15 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     void* XT16 = pl.pv16[2];
     void* XB16 = pl.pv16[3];
     void* N16 = pl.pv16[4];
+    // The activation stream between convolutions lives in HBM ONCE, as fp16 lrelu_{0.1}(x), channels-last: it is the MMA
+    // operand of the next convolution as it is, and the residual x is recovered from it in the pair-closing epilogue
+    // (x = r > 0 ? r : 10 r -- the same relative precision as an fp16 copy of x itself; tools/emulate_precision.py: -2 dB
+    // in fp16 mode, -0.2 dB in bf16 mode against an fp32 stream).  A pair moves 10 bytes per element instead of 16.
+    // bf16 mode keeps the stream in fp16 (a bf16 stream costs 5 dB): convs1 (stream x weights) run on fp16 operands,
+    // convs2 (h x weights, h never leaves the pair) on bf16 operands -- tcgen05 kind::f16 rejects mixed A/B formats.
+    // The branch sum xs lives in planar-vector fp16 [B][C/8][Lp][8] (only epilogues touch it: 512 B per warp access).
     float* X32 = pl.pv32[0];
-    float* XB32 = pl.pv32[1];
-    float* ACC32 = pl.pv32[2];
+    float* ACC32 = pl.pv32[1];
     {
       const int U0 = f.up_init_channels;
       TcConvDesc d = tc_base();
@@ -869,7 +875,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       const int Cn = g.cout;
       const int LpN = pv_pitch_rows(Ln);
       const bool last_stage = i == f.n_ups - 1;
-      if (last_stage) CKC(3, launch_zero_pads(ACC32, (long long)B * (Cn / 4), LpN, kPadF, Ln, st), "zero_pads");
+      if (last_stage) CKC(3, launch_zero_pads(ACC32, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
       {  // x = ups[i](lrelu(x)) as g.u phase groups (input already holds lrelu(x) in 16 bit)
         TcConvDesc d = tc_base();
         d.x16 = IN16; d.L_in = (int)Lc; d.w16 = W16h(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i));
@@ -884,8 +890,9 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       {
         int nk, ns, np;
         noise_geom(f, i, &nk, &ns, &np);
-        CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, B, Lout, Ln, Cn,
-                                   nk, ns, np, LpN, kPadF, 0.1f, bf16, st),
+        const bool want_tap = tp.find(S("dec.ups.%d", i).c_str()) != nullptr;
+        CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, nullptr, want_tap, B,
+                                   Lout, Ln, Cn, nk, ns, np, LpN, kPadF, 0.1f, false, st),
             "dec.noise_add(pv)");
       }
       if (const rvcb200_tap* t = tp.find(S("dec.ups.%d", i).c_str()))
@@ -894,50 +901,50 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
         const int n = i * f.n_res_kernels + j;
         const int k = f.res_kernels[j];
         const void* src16 = X16;
-        const float* src32 = X32;
         const int nd = f.n_res_dils[j];
         for (int dd = 0; dd < nd; ++dd) {
           const bool last = dd == nd - 1;
           const int dil = f.res_dils[j][dd];
           TcConvDesc o = tc_base();
+          const int c2_bf16 = f.resblock_kind == 1 ? rb_bf16 : 0;
           o.L_in = (int)Ln; o.Cin = Cn; o.ntaps = k;
           o.N = Cn < 256 ? Cn : 256; o.Cout_total = Cn; o.tmem_cols = tmem_cols_for(o.N);
           o.Lj = (int)Ln; o.Lp_out = LpN;
           if (f.resblock_kind == 1) {
             TcConvDesc d = o;    // xt = c1(lrelu(x)); only lrelu(xt) is ever consumed -> 16-bit store only
-            d.x16 = src16; d.w16 = W16(S("dec.rb.%d.c1.%d.w", n, dd)); d.bias = W(S("dec.rb.%d.c1.%d.b", n, dd));
+            d.x16 = src16; d.w16 = W16h(S("dec.rb.%d.c1.%d.w", n, dd)); d.bias = W(S("dec.rb.%d.c1.%d.b", n, dd));
             d.dil = dil; d.g_off[0] = -((k - 1) / 2) * dil;
             d.y16 = XT16; d.out_slope = 0.1f;
             if (!ok) return RVCB200_ERR_MISSING;
-            d.in_bf16 = rb_bf16; d.out_bf16 = rb_bf16;
+            d.in_bf16 = 0; d.out_bf16 = rb_bf16;
             CKC(0, launch_rb(d), "dec.rb.c1(tc)");
             o.x16 = XT16; o.dil = 1; o.g_off[0] = -((k - 1) / 2);
             o.w16 = W16(S("dec.rb.%d.c2.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c2.%d.b", n, dd));
           } else {
             o.x16 = src16; o.dil = dil; o.g_off[0] = -((k - 1) / 2) * dil;
-            o.w16 = W16(S("dec.rb.%d.c.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c.%d.b", n, dd));
+            o.w16 = W16h(S("dec.rb.%d.c.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c.%d.b", n, dd));
           }
-          o.res32 = src32;
+          o.res16 = src16; o.res_neg_scale = 10.f;
           if (last) {
             const bool final_branch = j == f.n_res_kernels - 1;
-            o.y32 = ACC32; o.accum = j > 0; o.div = final_branch ? (float)f.n_res_kernels : 1.f;
-            o.in_bf16 = rb_bf16; o.out_bf16 = 0;       // the next ups consumes fp16
+            o.y32 = ACC32; o.acc_f16 = 1; o.accum = j > 0; o.div = final_branch ? (float)f.n_res_kernels : 1.f;
+            o.in_bf16 = c2_bf16; o.out_bf16 = 0;       // the next ups consumes fp16
             if (final_branch && !last_stage) { o.y16 = N16; o.out_slope = 0.1f; }
           } else {
-            o.in_bf16 = rb_bf16; o.out_bf16 = rb_bf16;
-            o.y32 = XB32; o.y16 = XB16; o.out_slope = 0.1f;
+            o.in_bf16 = c2_bf16; o.out_bf16 = 0;
+            o.y16 = XB16; o.out_slope = 0.1f;
           }
           if (!ok) return RVCB200_ERR_MISSING;
           CKC(0, launch_rb(o), "dec.rb.c2(tc)");
-          src16 = XB16; src32 = XB32;
+          src16 = XB16;
         }
       }
       if (const rvcb200_tap* t = tp.find(S("dec.stage.%d", i).c_str()))
-        CK(launch_pv32_to_cl(ACC32, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");
+        CK(launch_pv16_to_cl(ACC32, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");
       void* tmp = IN16; IN16 = N16; N16 = tmp;
       Lc = Ln; Cc = Cn; LpC = LpN; (void)LpC;
     }
-    CKC(3, launch_conv_post_pv(ACC32, W("dec.post.w"), out, B, Lc, Cc, 7, LpC, kPadF, 0.01f, st), "dec.conv_post(pv)");
+    CKC(3, launch_conv_post_pv16(ACC32, W("dec.post.w"), out, B, Lc, Cc, 7, LpC, kPadF, 0.01f, st), "dec.conv_post(pv16)");
   }
   if (!ok) return RVCB200_ERR_MISSING;
   ctx->last_launches = launch_counter().n - launches0;

@@ -20,29 +20,68 @@ namespace {
 using namespace tc;
 
 constexpr int kRbThreads = 64 + 32 * 8;   // TMA producer warp, MMA warp, 8 epilogue warps (2 groups of 4)
+constexpr int kEpiBox = 2048;             // one epilogue staging box: 32 rows x 32 channels x 16 bit, SWIZZLE_64B
+
+// Shared-memory plan of one instantiation (plain constexpr functions so that MSUB can be chosen by "does it fit").
+struct RbPlan {
+  int nkb, ks, tile_m, halo, r, nbox, rb, a_bytes, w_bytes, nw, out_slots, epi_bytes, budget, stat, nb, na_fit;
+};
+constexpr RbPlan rb_plan(int C, int NTAPS, int DIL, int MSUB) {
+  RbPlan q{};
+  q.nkb = (C + 63) / 64;
+  q.ks = C >= 64 ? 4 : C / 16;
+  q.tile_m = MSUB * 128;
+  q.halo = (NTAPS - 1) * DIL;
+  q.r = q.tile_m + q.halo;
+  q.nbox = (q.r + 255) / 256;
+  q.rb = (((q.r + q.nbox - 1) / q.nbox) + 7) & ~7;
+  q.a_bytes = q.nbox * q.rb * 128;
+  q.w_bytes = C * 128;
+  q.nw = q.nkb * NTAPS;
+  // epilogue staging (C <= 128): per warp 2 residual boxes + out_slots output boxes
+  q.out_slots = C == 128 ? 1 : 2;
+  q.epi_bytes = C <= 128 ? 8 * (2 + q.out_slots) * kEpiBox : 0;
+  q.budget = 218 * 1024 - q.epi_bytes;
+  q.stat = (q.nw * q.w_bytes <= 96 * 1024 && (q.budget - q.nw * q.w_bytes) / q.a_bytes >= 2) ? 1 : 0;
+  q.nb = q.stat ? q.nw : (C >= 256 ? 3 : (C == 128 ? 4 : 6));
+  q.na_fit = (q.budget - q.nb * q.w_bytes) / q.a_bytes;
+  return q;
+}
+constexpr bool rb_fits(int C, int NTAPS, int DIL, int MSUB) {
+  return rb_plan(C, NTAPS, DIL, MSUB).na_fit >= 2 && 2 * MSUB * C <= 512;
+}
+// largest MSUB <= the preferred one whose rings fit beside the epilogue staging
+constexpr int rb_msub(int C, int NTAPS, int DIL) {
+  int m = C == 32 ? 4 : (C == 256 ? 1 : 2);
+  while (m > 1 && !rb_fits(C, NTAPS, DIL, m)) m >>= 1;
+  return m;
+}
 
 template <int C, int NTAPS, int DIL, int MSUB>
 struct RbCfg {
-  static constexpr int NKB = (C + 63) / 64;                // 64-channel k-blocks (one 128-byte swizzled row each)
-  static constexpr int KS = C >= 64 ? 4 : C / 16;          // K=16 MMA steps per k-block (zero-padded K is skipped)
-  static constexpr int TILE_M = MSUB * 128;
-  static constexpr int HALO = (NTAPS - 1) * DIL;
+  static constexpr RbPlan P = rb_plan(C, NTAPS, DIL, MSUB);
+  static constexpr int NKB = P.nkb;                        // 64-channel k-blocks (one 128-byte swizzled row each)
+  static constexpr int KS = P.ks;                          // K=16 MMA steps per k-block (zero-padded K is skipped)
+  static constexpr int TILE_M = P.tile_m;
+  static constexpr int HALO = P.halo;
   static constexpr int GOFF = -((NTAPS - 1) / 2) * DIL;    // "same" padding
-  static constexpr int R = TILE_M + HALO;                  // activation rows one tile needs
-  static constexpr int NBOX = (R + 255) / 256;             // TMA boxes are <= 256 rows
-  static constexpr int RB = (((R + NBOX - 1) / NBOX) + 7) & ~7;
-  static constexpr uint32_t A_BYTES = (uint32_t)NBOX * RB * 128;
-  static constexpr uint32_t W_BYTES = (uint32_t)C * 128;   // one (k-block, tap) weight tile [C][64] 16-bit
-  static constexpr int NW = NKB * NTAPS;
-  static constexpr bool STAT = (size_t)NW * W_BYTES <= 96 * 1024;   // weights resident for the whole CTA
-  static constexpr int NB = STAT ? NW : (C >= 256 ? 3 : 6);
-  static constexpr int SMEM_BUDGET = 218 * 1024;
-  static constexpr int NA_FIT = (int)((SMEM_BUDGET - (size_t)NB * W_BYTES) / A_BYTES);
-  static constexpr int NA = NA_FIT > 6 ? 6 : NA_FIT;
+  static constexpr int NBOX = P.nbox;                      // TMA boxes are <= 256 rows
+  static constexpr int RB = P.rb;
+  static constexpr uint32_t A_BYTES = (uint32_t)P.a_bytes;
+  static constexpr uint32_t W_BYTES = (uint32_t)P.w_bytes; // one (k-block, tap) weight tile [C][64] 16-bit
+  static constexpr int NW = P.nw;
+  static constexpr bool STAT = P.stat != 0;                // weights resident for the whole CTA
+  static constexpr int NB = P.nb;
+  static constexpr int NA = P.na_fit > 6 ? 6 : P.na_fit;
+  static constexpr bool EPI_TMA = C <= 128;                // 16-bit epilogue I/O staged in smem and moved by TMA
+  static constexpr int OUT_SLOTS = P.out_slots;
+  static constexpr int EPI_WARP_BYTES = (2 + OUT_SLOTS) * kEpiBox;
+  static constexpr int EPI_BYTES = P.epi_bytes;
   static constexpr int TMEM_COLS = 2 * MSUB * C;           // two accumulator buffers of MSUB sub-tiles
   static constexpr int NCH = MSUB * (C / 32);              // 32-column epilogue chunks per tile and warp
-  static constexpr size_t SMEM = 1024 + (size_t)NA * A_BYTES + (size_t)NB * W_BYTES + C * sizeof(float) +
-                                 8 * (2 * NA + 2 * NB + 4) + 64;
+  static constexpr int NBAR = 2 * NA + 2 * NB + 4 + 16;    // + 8 warps x 2 residual-box barriers
+  static constexpr size_t SMEM = 1024 + (size_t)NA * A_BYTES + (size_t)NB * W_BYTES + EPI_BYTES + C * sizeof(float) +
+                                 8 * NBAR + 64;
   static_assert(C % 32 == 0 && C <= 256, "C");
   static_assert(NA >= 2, "activation ring too small");
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
@@ -52,13 +91,15 @@ struct RbCfg {
 
 template <int C, int NTAPS, int DIL, int MSUB>
 __global__ void __launch_bounds__(kRbThreads, 1)
-rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
+rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmY) {
   using K = RbCfg<C, NTAPS, DIL, MSUB>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                                       // [NA][SLAB_ROWS][128 B] swizzled
   unsigned char* sW = sA + (size_t)K::NA * K::A_BYTES;            // [NB][C][128 B] swizzled
-  float* sbias = reinterpret_cast<float*>(sW + (size_t)K::NB * K::W_BYTES);
+  unsigned char* sE = sW + (size_t)K::NB * K::W_BYTES;            // [8 warps][2 residual + OUT_SLOTS output boxes][2 KB]
+  float* sbias = reinterpret_cast<float*>(sE + K::EPI_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + C);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + K::NA;
@@ -66,7 +107,8 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
   uint64_t* b_empty = b_full + K::NB;
   uint64_t* acc_full = b_empty + K::NB;     // [2]
   uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* res_full = acc_empty + 2;       // [8 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -77,6 +119,7 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
     for (int i = 0; i < K::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < K::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 16; ++i) mbar_init(&res_full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -198,34 +241,90 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
     }
   } else {
     // ============== epilogue: two groups of 4 warps, group e drains accumulator buffer e ==================
+    // 16-bit I/O (C <= 128): thread = TMEM lane = time row, so direct global accesses would be 16-byte pieces 2*C bytes
+    // apart -- 32 L2 requests per warp instruction; measured ~0.37 requests/clk/SM whatever the byte count, the limit
+    // of every epilogue-heavy shape (profiles/r1_conv_shapes_v8_*.jsonl).  Instead each warp moves [32 rows][32 channels]
+    // boxes with TMA: the residual box lands in a SWIZZLE_64B staging slot (2 slots, loaded one chunk ahead), the
+    // 16-bit output box is written to a staging slot by the lanes (conflict-free under the swizzle) and stored by one
+    // lane; fp32 planar accumulators (branch sum) keep the direct path: their warp accesses are 512 B contiguous.
     const int eg = (warp - 2) >> 2;
+    const int ew = warp - 2;
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
     const size_t pitch_o = (size_t)p.Lp_out * 16;   // bytes per planar-vector plane
     const bool obf = p.out_bf16 != 0;
     const float slope = p.out_slope;
     const float inv_div = p.div;                    // divide (not multiply by reciprocal): matches the fp32 path
+    const float neg_scale = p.res_neg_scale == 0.f ? 1.f : p.res_neg_scale;
+    const bool has_r16 = p.res16 != nullptr;
+    const bool has_y16 = p.y16 != nullptr;
+    unsigned char* my_stage = sE + (size_t)ew * K::EPI_WARP_BYTES;      // [2 residual][OUT_SLOTS output] boxes
+    uint64_t* my_res_full = res_full + ew * 2;
+    // byte offset of this lane's 16-byte piece j inside a SWIZZLE_64B box: row = lane (64 B), piece ^= (row >> 1) & 3
+    const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = ((uint32_t)lane >> 1) & 3u;
+    uint32_t rcnt = 0;                              // residual boxes consumed so far (slot = rcnt & 1)
+    uint32_t ocnt = 0;                              // output boxes stored so far
     uint32_t it = (uint32_t)eg;
 #pragma unroll 1
     for (unsigned tile = blockIdx.x + (unsigned)eg * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
       const unsigned b = tile / n_mt, mt = tile - b * n_mt;
-      const int row_base = (int)mt * K::TILE_M + qd * 32 + lane;
+      const int wrow0 = (int)mt * K::TILE_M + qd * 32;            // first row of this warp's 32-row group (sub-tile 0)
+      const int row_base = wrow0 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(eg * MSUB * C);
-      unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (C / 4) * pitch_o : nullptr;
+      const bool acc16 = p.acc_f16 != 0;            // branch sum in planar-vector fp16 [C/8][Lp][8]
+      unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (C / (acc16 ? 8 : 4)) * pitch_o : nullptr;
       const unsigned char* r32 = p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (C / 4) * pitch_o : nullptr;
-      unsigned char* y16 = p.y16 ? reinterpret_cast<unsigned char*>(p.y16) + (size_t)b * (size_t)p.Lj * C * 2 : nullptr;
+      unsigned char* y16 = has_y16 ? reinterpret_cast<unsigned char*>(p.y16) + (size_t)b * (size_t)p.Lj * C * 2 : nullptr;
+      const unsigned char* r16 = has_r16 ? reinterpret_cast<const unsigned char*>(p.res16) + (size_t)b * (size_t)p.Lj * C * 2 : nullptr;
       const bool do_acc = p.accum != 0;
 
-      float4 rr[2][8];
-      auto load_res = [&](int ci, float4* dst) {
+      // ---- residual fetch: TMA boxes (C <= 128) or direct prefetch ring of raw 16-byte words ----
+      uint4 rq[16];   // direct paths: fp32 planar = 8 words per chunk x 2 slots; fp16 channels-last = 4 words x 4 slots
+      auto issue_box = [&](int ci, uint32_t cnt) {     // one lane: residual box of chunk ci -> staging slot cnt & 1
+        const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
+        uint64_t* bar = &my_res_full[cnt & 1u];
+        mbar_expect_tx(bar, kEpiBox);
+        tma_load_3d(my_stage + (cnt & 1u) * kEpiBox, &tmR, c0, wrow0 + ms * 128, (int)b, bar);
+      };
+      auto load_res = [&](int ci) {
         const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
         const int row = row_base + ms * 128;
-        if (r32 != nullptr && row < p.Lj) {
-          const unsigned char* q = r32 + (size_t)(c0 / 4) * pitch_o + (size_t)(row + p.padf) * 16;
+        if (row < p.Lj) {
+          if (has_r16) {
+            const uint4* q = reinterpret_cast<const uint4*>(r16 + ((size_t)row * C + c0) * 2);
 #pragma unroll
-          for (int k4 = 0; k4 < 8; ++k4) dst[k4] = *reinterpret_cast<const float4*>(q + (size_t)k4 * pitch_o);
+            for (int k = 0; k < 4; ++k) rq[(ci & 3) * 4 + k] = ld_nc_u4(q + k);
+          } else if (r32 != nullptr) {
+            const unsigned char* q = r32 + (size_t)(c0 / 4) * pitch_o + (size_t)(row + p.padf) * 16;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) rq[(ci & 1) * 8 + k4] = *reinterpret_cast<const uint4*>(q + (size_t)k4 * pitch_o);
+          }
         }
       };
-      load_res(0, rr[0]);                            // residual of the first chunk is in flight before the MMAs finish
+      // fp16 branch-sum prefetch (one chunk ahead), only beside the TMA residual path (rq is free there)
+      const bool acc_pf = K::EPI_TMA && acc16 && do_acc && y32 != nullptr && r32 == nullptr;
+      auto load_acc = [&](int ci) {
+        const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
+        const int row = row_base + ms * 128;
+        if (row < p.Lj) {
+          const unsigned char* q = y32 + (size_t)(c0 / 8) * pitch_o + (size_t)(row + p.padf) * 16;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rq[8 + (ci & 1) * 4 + k] = *reinterpret_cast<const uint4*>(q + (size_t)k * pitch_o);
+        }
+      };
+      if (acc_pf) load_acc(0);
+      // the first residuals are in flight before the MMAs of this tile finish
+      if (K::EPI_TMA && has_r16) {
+        if (lane == 0) {
+          issue_box(0, rcnt);
+          if (1 < K::NCH) issue_box(1, rcnt + 1);
+        }
+      } else {
+        load_res(0);
+        if (has_r16) {
+          if (1 < K::NCH) load_res(1);
+          if (2 < K::NCH) load_res(2);
+        }
+      }
       mbar_wait(&acc_full[eg], (it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
@@ -233,7 +332,14 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
         const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
         const int row = row_base + ms * 128;
         const bool row_ok = row < p.Lj;
-        if (ci + 1 < K::NCH) load_res(ci + 1, rr[(ci + 1) & 1]);
+        if (!(K::EPI_TMA && has_r16)) {
+          if (has_r16) {
+            if (ci + 3 < K::NCH) load_res(ci + 3);
+          } else {
+            if (ci + 1 < K::NCH) load_res(ci + 1);
+          }
+        }
+        if (acc_pf && ci + 1 < K::NCH) load_acc(ci + 1);
         uint32_t r[32];
         const uint32_t taddr = tbase + (uint32_t)(ms * C + c0);
         asm volatile(
@@ -245,52 +351,105 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row_ok) {
-          const size_t orow16 = (size_t)(row + p.padf) * 16;
-          float v[32];
+        float v[32];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 bq = *reinterpret_cast<const float4*>(sbias + c0 + k4 * 4);
+          v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
+          v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
+          v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
+          v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
+        }
+        if (K::EPI_TMA && has_r16) {
+          // residual box of this chunk: wait, read this lane's row, hand the slot back, refill it two chunks ahead
+          const unsigned char* box = my_stage + (rcnt & 1u) * kEpiBox + sw_row;
+          mbar_wait(&my_res_full[rcnt & 1u], (rcnt >> 1) & 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint4 w = *reinterpret_cast<const uint4*>(box + ((((uint32_t)k) ^ sw_x) << 4));
+            add_res8(v + k * 8, w, neg_scale);
+          }
+          __syncwarp();
+          if (lane == 0 && ci + 2 < K::NCH) issue_box(ci + 2, rcnt + 2);
+          ++rcnt;
+        } else if (has_r16) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) add_res8(v + k * 8, rq[(ci & 3) * 4 + k], neg_scale);
+        } else if (r32 != nullptr) {
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
-            const float4 bq = *reinterpret_cast<const float4*>(sbias + c0 + k4 * 4);
-            v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
-            v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
-            v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
-            v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
+            const uint4 w = rq[(ci & 1) * 8 + k4];
+            v[k4 * 4 + 0] += __uint_as_float(w.x); v[k4 * 4 + 1] += __uint_as_float(w.y);
+            v[k4 * 4 + 2] += __uint_as_float(w.z); v[k4 * 4 + 3] += __uint_as_float(w.w);
           }
-          if (r32 != nullptr) {
-#pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) {
-              const float4 rq = rr[ci & 1][k4];
-              v[k4 * 4 + 0] += rq.x; v[k4 * 4 + 1] += rq.y; v[k4 * 4 + 2] += rq.z; v[k4 * 4 + 3] += rq.w;
-            }
-          }
+        }
+        if (y32 != nullptr && row_ok) {
+          const size_t orow16 = (size_t)(row + p.padf) * 16;
           if (do_acc) {
+            if (acc16) {
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) {
-              const float4 aq = *reinterpret_cast<const float4*>(y32 + (size_t)(c0 / 4 + k4) * pitch_o + orow16);
-              v[k4 * 4 + 0] += aq.x; v[k4 * 4 + 1] += aq.y; v[k4 * 4 + 2] += aq.z; v[k4 * 4 + 3] += aq.w;
+              for (int k = 0; k < 4; ++k) {
+                const uint4 w = acc_pf ? rq[8 + (ci & 1) * 4 + k]
+                                       : *reinterpret_cast<const uint4*>(y32 + (size_t)(c0 / 8 + k) * pitch_o + orow16);
+                add_res8(v + k * 8, w, 1.f);
+              }
+            } else {
+#pragma unroll
+              for (int k4 = 0; k4 < 8; ++k4) {
+                const float4 aq = *reinterpret_cast<const float4*>(y32 + (size_t)(c0 / 4 + k4) * pitch_o + orow16);
+                v[k4 * 4 + 0] += aq.x; v[k4 * 4 + 1] += aq.y; v[k4 * 4 + 2] += aq.z; v[k4 * 4 + 3] += aq.w;
+              }
             }
           }
           if (inv_div != 1.f) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
           }
-          if (y32 != nullptr) {
+          if (acc16) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint4 o;
+              o.x = pack2(false, v[k * 8 + 0], v[k * 8 + 1]); o.y = pack2(false, v[k * 8 + 2], v[k * 8 + 3]);
+              o.z = pack2(false, v[k * 8 + 4], v[k * 8 + 5]); o.w = pack2(false, v[k * 8 + 6], v[k * 8 + 7]);
+              *reinterpret_cast<uint4*>(y32 + (size_t)(c0 / 8 + k) * pitch_o + orow16) = o;
+            }
+          } else {
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4)
               *reinterpret_cast<float4*>(y32 + (size_t)(c0 / 4 + k4) * pitch_o + orow16) =
                   make_float4(v[k4 * 4 + 0], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
           }
-          if (y16 != nullptr) {
+        } else if (inv_div != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
+        }
+        if (has_y16) {
+          uint4 o[4];
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) {
+            o[k8].x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
+            o[k8].y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
+            o[k8].z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
+            o[k8].w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
+          }
+          if (K::EPI_TMA) {
+            // stage the [32 rows][32 channels] box, then one lane stores it (rows >= L are clipped by the tensor map)
+            unsigned char* box = my_stage + (2 + (ocnt % K::OUT_SLOTS)) * kEpiBox;
+            if (lane == 0) bulk_wait_read<K::OUT_SLOTS - 1>();        // the store that last used this slot has read it
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(box + sw_row + ((((uint32_t)k) ^ sw_x) << 4)) = o[k];
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmY, box, c0, wrow0 + ms * 128, (int)b);
+              bulk_commit();
+            }
+            ++ocnt;
+          } else if (row_ok) {
             unsigned char* yr = y16 + ((size_t)row * C + c0) * 2;
 #pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
-              uint4 o;
-              o.x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
-              o.y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
-              o.z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
-              o.w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
-              *reinterpret_cast<uint4*>(yr + k8 * 16) = o;
-            }
+            for (int k8 = 0; k8 < 4; ++k8) *reinterpret_cast<uint4*>(yr + k8 * 16) = o[k8];
           }
         }
       }
@@ -298,6 +457,7 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[eg])) : "memory");
     }
+    if (K::EPI_TMA && lane == 0) bulk_wait_all();     // staged stores complete before the CTA's smem goes away
   }
   // ------------------------------------ teardown -------------------------------------------------
   tc_fence_before();
@@ -327,7 +487,7 @@ cudaError_t launch_one(const TcConvDesc& d, int B, cudaStream_t st) {
   using K = RbCfg<C, NTAPS, DIL, MSUB>;
   EncodeTiledFn enc = rb_encode_tiled();
   if (!enc) return cudaErrorNotSupported;
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmR, tmY;
   const CUtensorMapDataType dt = d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   cuuint32_t es[3] = {1, 1, 1};
   {
@@ -343,6 +503,24 @@ cudaError_t launch_one(const TcConvDesc& d, int B, cudaStream_t st) {
     if (enc(&tmW, dt, 2, const_cast<void*>(d.w16), wdims, wstrides, wbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
+    // epilogue boxes: [32 rows][32 channels] of the 16-bit channels-last residual / output, SWIZZLE_64B staging
+    tmR = tmA;
+    tmY = tmA;
+    if (K::EPI_TMA) {
+      cuuint64_t odims[3] = {(cuuint64_t)C, (cuuint64_t)d.Lj, (cuuint64_t)B};
+      cuuint64_t ostrides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * (cuuint64_t)d.Lj};
+      cuuint32_t obox[3] = {32, 32, 1};
+      if (d.res16 &&
+          enc(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d.res16), odims, ostrides, obox, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+      if (d.y16 &&
+          enc(&tmY, d.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, d.y16, odims, ostrides,
+              obox, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    }
   }
   static bool configured = false;
   if (!configured) {
@@ -361,23 +539,23 @@ cudaError_t launch_one(const TcConvDesc& d, int B, cudaStream_t st) {
   p.batch = B;
   const long long tiles = (long long)((d.Lj + K::TILE_M - 1) / K::TILE_M) * B;
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
-  rbconv_tc_kernel<C, NTAPS, DIL, MSUB><<<grid, kRbThreads, K::SMEM, st>>>(p, tmA, tmW);
+  rbconv_tc_kernel<C, NTAPS, DIL, MSUB><<<grid, kRbThreads, K::SMEM, st>>>(p, tmA, tmW, tmR, tmY);
   launch_counter().n++;
   return cudaGetLastError();
 }
 
-template <int C, int MSUB>
+template <int C>
 cudaError_t launch_c(const TcConvDesc& d, int B, cudaStream_t st) {
   switch (d.ntaps * 16 + d.dil) {
-    case 3 * 16 + 1: return launch_one<C, 3, 1, MSUB>(d, B, st);
-    case 3 * 16 + 3: return launch_one<C, 3, 3, MSUB>(d, B, st);
-    case 3 * 16 + 5: return launch_one<C, 3, 5, MSUB>(d, B, st);
-    case 7 * 16 + 1: return launch_one<C, 7, 1, MSUB>(d, B, st);
-    case 7 * 16 + 3: return launch_one<C, 7, 3, MSUB>(d, B, st);
-    case 7 * 16 + 5: return launch_one<C, 7, 5, MSUB>(d, B, st);
-    case 11 * 16 + 1: return launch_one<C, 11, 1, MSUB>(d, B, st);
-    case 11 * 16 + 3: return launch_one<C, 11, 3, MSUB>(d, B, st);
-    case 11 * 16 + 5: return launch_one<C, 11, 5, MSUB>(d, B, st);
+    case 3 * 16 + 1: return launch_one<C, 3, 1, rb_msub(C, 3, 1)>(d, B, st);
+    case 3 * 16 + 3: return launch_one<C, 3, 3, rb_msub(C, 3, 3)>(d, B, st);
+    case 3 * 16 + 5: return launch_one<C, 3, 5, rb_msub(C, 3, 5)>(d, B, st);
+    case 7 * 16 + 1: return launch_one<C, 7, 1, rb_msub(C, 7, 1)>(d, B, st);
+    case 7 * 16 + 3: return launch_one<C, 7, 3, rb_msub(C, 7, 3)>(d, B, st);
+    case 7 * 16 + 5: return launch_one<C, 7, 5, rb_msub(C, 7, 5)>(d, B, st);
+    case 11 * 16 + 1: return launch_one<C, 11, 1, rb_msub(C, 11, 1)>(d, B, st);
+    case 11 * 16 + 3: return launch_one<C, 11, 3, rb_msub(C, 11, 3)>(d, B, st);
+    case 11 * 16 + 5: return launch_one<C, 11, 5, rb_msub(C, 11, 5)>(d, B, st);
     default: return cudaErrorNotSupported;
   }
 }
@@ -390,7 +568,7 @@ bool rbconv_tc_supported(const TcConvDesc& d) {
   if (!(d.Cin == 32 || d.Cin == 64 || d.Cin == 128 || d.Cin == 256)) return false;
   if (!(d.ntaps == 3 || d.ntaps == 7 || d.ntaps == 11) || !(d.dil == 1 || d.dil == 3 || d.dil == 5)) return false;
   if (d.g_off[0] != -((d.ntaps - 1) / 2) * d.dil) return false;
-  if ((d.accum && !d.y32) || !d.x16 || !d.w16 || !d.bias) return false;
+  if ((d.accum && !d.y32) || !d.x16 || !d.w16 || !d.bias || (d.res16 && d.res32) || d.a_fp16) return false;
   return true;
 }
 
@@ -399,10 +577,10 @@ bool rbconv_tc_supported(const TcConvDesc& d) {
 cudaError_t launch_rbconv_tc(const TcConvDesc& d, int B, cudaStream_t st) {
   if (!rbconv_tc_supported(d) || B <= 0) return cudaErrorNotSupported;
   switch (d.Cin) {
-    case 32: return launch_c<32, 4>(d, B, st);
-    case 64: return launch_c<64, 2>(d, B, st);
-    case 128: return launch_c<128, 2>(d, B, st);
-    case 256: return launch_c<256, 1>(d, B, st);
+    case 32: return launch_c<32>(d, B, st);
+    case 64: return launch_c<64>(d, B, st);
+    case 128: return launch_c<128>(d, B, st);
+    case 256: return launch_c<256>(d, B, st);
     default: return cudaErrorNotSupported;
   }
 }

@@ -102,6 +102,35 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t bas
          ((uint64_t)(base_offset & 7u) << 49) | (2ull << 61);
 }
 
+// 16-byte read-only global load that does not allocate in L1 (streamed residuals)
+__device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// v[0..8) += x where the 8 fp16 values of `w` hold r = lrelu(x): x = r > 0 ? r : r * neg_scale (neg_scale = 1: plain add)
+__device__ __forceinline__ void add_res8(float* v, const uint4& w, float neg_scale) {
+  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+  const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z));
+  const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+  const float r[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] += r[i] > 0.f ? r[i] : r[i] * neg_scale;
+}
+
+// ---- bulk-tensor (TMA) stores from shared memory ----
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack2(bool bf16, float a, float b) {
   if (bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -117,7 +146,8 @@ __device__ __forceinline__ uint32_t pack2(bool bf16, float a, float b) {
 template <int CH>
 __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t taddr, bool row_ok, int co, size_t pitch_o,
                                                size_t orow16, unsigned char* y32, unsigned char* y16row,
-                                               const unsigned char* r32, const float* cond) {
+                                               const unsigned char* r32, const float* cond,
+                                               const unsigned char* r16row = nullptr) {
   uint32_t r[CH];
   if (CH == 32) {
     asm volatile(
@@ -137,16 +167,34 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t tad
         : "r"(taddr));
   }
   float4 rr[CH / 4], aa[CH / 4];
+  uint4 rh[CH / 8];
   if (row_ok) {
+    if (r16row) {
+#pragma unroll
+      for (int k8 = 0; k8 < CH / 8; ++k8) rh[k8] = *reinterpret_cast<const uint4*>(r16row + (size_t)(co + k8 * 8) * 2);
+    }
     if (r32) {
 #pragma unroll
       for (int k4 = 0; k4 < CH / 4; ++k4)
         rr[k4] = *reinterpret_cast<const float4*>(r32 + (size_t)(co / 4 + k4) * pitch_o + orow16);
     }
     if (p.accum) {
+      if (p.acc_f16) {   // planar-vector fp16: 8 channels per 16-byte row
 #pragma unroll
-      for (int k4 = 0; k4 < CH / 4; ++k4)
-        aa[k4] = *reinterpret_cast<const float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + orow16);
+        for (int k8 = 0; k8 < CH / 8; ++k8) {
+          const uint4 w = *reinterpret_cast<const uint4*>(y32 + (size_t)(co / 8 + k8) * pitch_o + orow16);
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+          const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z));
+          const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+          aa[2 * k8] = make_float4(f0.x, f0.y, f1.x, f1.y);
+          aa[2 * k8 + 1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+        }
+      } else {
+#pragma unroll
+        for (int k4 = 0; k4 < CH / 4; ++k4)
+          aa[k4] = *reinterpret_cast<const float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + orow16);
+      }
     }
   }
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -164,6 +212,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t tad
       v[k4 * 4 + 0] += rr[k4].x; v[k4 * 4 + 1] += rr[k4].y; v[k4 * 4 + 2] += rr[k4].z; v[k4 * 4 + 3] += rr[k4].w;
     }
   }
+  if (r16row) {
+    const float ns = p.res_neg_scale == 0.f ? 1.f : p.res_neg_scale;
+#pragma unroll
+    for (int k8 = 0; k8 < CH / 8; ++k8) add_res8(v + k8 * 8, rh[k8], ns);
+  }
   if (p.accum) {
 #pragma unroll
     for (int k4 = 0; k4 < CH / 4; ++k4) {
@@ -174,7 +227,15 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t tad
 #pragma unroll
     for (int i = 0; i < CH; ++i) v[i] = v[i] / p.div;
   }
-  if (y32) {
+  if (y32 && p.acc_f16) {
+#pragma unroll
+    for (int k8 = 0; k8 < CH / 8; ++k8) {
+      uint4 o;
+      o.x = pack2(false, v[k8 * 8 + 0], v[k8 * 8 + 1]); o.y = pack2(false, v[k8 * 8 + 2], v[k8 * 8 + 3]);
+      o.z = pack2(false, v[k8 * 8 + 4], v[k8 * 8 + 5]); o.w = pack2(false, v[k8 * 8 + 6], v[k8 * 8 + 7]);
+      *reinterpret_cast<uint4*>(y32 + (size_t)(co / 8 + k8) * pitch_o + orow16) = o;
+    }
+  } else if (y32) {
 #pragma unroll
     for (int k4 = 0; k4 < CH / 4; ++k4)
       *reinterpret_cast<float4*>(y32 + (size_t)(co / 4 + k4) * pitch_o + orow16) =

@@ -168,15 +168,17 @@ class SynthesizerB200(nn.Module):
     def _ensure_tc(self):
         """Register the 16-bit tcgen05 weight images for the selected precision.
 
-        Resblock convolutions use `precision` (fp16 | bf16) operands; conv_pre and the transposed-conv
-        ladder sit on the main signal path and always use fp16 operands (bf16 there costs ~9 dB SNR)."""
+        The pair-closing resblock convolutions (`convs2`, half of the decoder FLOPs) use `precision` (fp16 | bf16)
+        operands.  Everything that reads the fp16 activation stream -- `convs1`, conv_pre, the transposed-conv
+        ladder, text encoder, flow -- uses fp16 operands: a bf16 stream costs ~5-9 dB of output SNR and tcgen05
+        kind::f16 rejects mixed fp16 x bf16 operands (measured: illegal instruction)."""
         if self.precision == "fp32" or self.precision in self._tc_done:
             return
         lib = _lib.load()
         with torch.cuda.device(self._device):
             for name in tc_weight_names(self.cfg):
-                resblock = name.startswith("dec.rb.")
-                prec = self.precision if resblock else "fp16"      # ladder, text encoder and flow: always fp16
+                closing = name.startswith("dec.rb.") and ".c2." in name
+                prec = self.precision if closing else "fp16"
                 dtype = torch.float16 if prec == "fp16" else torch.bfloat16
                 t = pack_tc(self._packed[name].cpu(), dtype, tc_n_max_for_name(name)).to(self._device)
                 key = f"{name}.tc"

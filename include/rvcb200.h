@@ -186,6 +186,14 @@ typedef struct rvcb200_tc_conv_desc {
   int32_t res_mode;            /* 1: v + res, 2: res - v */
   int32_t mask_pre, mask_post, mask16; const int32_t* out_len;    /* rows >= out_len[b] -> 0 */
   int32_t dbg_alt;             /* timing experiment only (wrong results): alternate accumulator regions */
+  /* ---- fp16 activation stream of the decoder (lean epilogue) ---- */
+  const void* res16;           /* residual, fp16 channels-last [B][Lj*out_stride][Cout_total] (exclusive with res32) */
+  float res_neg_scale;         /* v += (r > 0 ? r : r * res_neg_scale); 0 or 1 = plain add.  The decoder keeps ONE fp16 copy
+                                * of the stream, lrelu_{0.1}(x) -- the MMA operand of the next convolution -- and recovers the
+                                * residual x from it with res_neg_scale = 10 (same relative precision as storing x itself) */
+  int32_t a_fp16;              /* reserved, must be 0 (fp16 x bf16 mixed-format MMA: tcgen05 kind::f16 raises an illegal
+                                * instruction on sm_100a) */
+  int32_t acc_f16;             /* 1: y32 (output and `accum` input) is planar-vector fp16 [B][Cout/8][Lp_out][8] */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--dbg-alt", type=int, default=0)
     ap.add_argument("--rb", type=int, default=1, help="1: specialised resblock kernel (rbconv_tc.cu), 0: generic conv_tc")
     ap.add_argument("--stages", default="", help="comma list of stage indices (0-3) to keep")
+    ap.add_argument("--kinds", default="c1,c2,c2s,c2a", help="c1: 16-bit store only; c2: + fp32 planar residual in/out; "
+                    "c2s: + residual from the fp16 lrelu-domain stream; c2a: stream residual, planar fp16 branch-sum accumulate, no 16-bit store")
     ap.add_argument("--ks", default="", help="comma list of kernel sizes to keep (default all)")
     args = ap.parse_args()
     lib = _lib.load()
@@ -52,13 +54,14 @@ def main():
         r32 = torch.randn(1, Cc // 4, Lp, 4, device=dev)
         y32 = torch.zeros(1, Cc // 4, Lp, 4, device=dev)
         y16 = torch.zeros(1, L, Cc, dtype=torch.float16, device=dev)
+        r16 = torch.randn(1, L, Cc, dtype=torch.float16, device=dev)
         bias = torch.randn(Cc, device=dev)
         keep = {int(v) for v in args.ks.split(",")} if args.ks else None
         for k, dil in ((3, 1), (7, 3), (11, 5), (11, 1)):
             if keep is not None and (k not in keep or (k == 11 and dil == 1)):
                 continue
             w = weights.pack_tc(torch.randn(1, k, Cc, Cc) / (Cc * k) ** 0.5, torch.float16).to(dev)
-            for kind in ("c1", "c2"):
+            for kind in args.kinds.split(","):
                 d = _lib.TcConvDesc()
                 d.x16, d.L_in, d.padf = x16.data_ptr(), L, PADF
                 d.w16, d.bias = w.data_ptr(), bias.data_ptr()
@@ -71,6 +74,10 @@ def main():
                 d.y16, d.out_slope, d.div = y16.data_ptr(), 0.1, 1.0
                 if kind == "c2":
                     d.y32, d.res32 = y32.data_ptr(), r32.data_ptr()
+                elif kind == "c2s":      # residual recovered from the fp16 lrelu-domain stream, one 16-bit store
+                    d.res16, d.res_neg_scale = r16.data_ptr(), 10.0
+                elif kind == "c2a":      # last pair of a resblock: stream residual + fp32 planar branch accumulate
+                    d.res16, d.res_neg_scale, d.y32, d.accum, d.y16, d.acc_f16 = r16.data_ptr(), 10.0, y32.data_ptr(), 1, None, 1
                 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
                 for _ in range(2):
                     assert conv_fn(C.byref(d), 1, st) == 0
@@ -87,7 +94,7 @@ def main():
                     torch.cuda.profiler.stop()
                 us = e0.elapsed_time(e1) * 1e3 / args.reps
                 flops = 2.0 * L * Cc * Cc * k
-                bytes_ = L * Cc * (2 + 2 + (8 if kind == "c2" else 0))
+                bytes_ = L * Cc * (2 + 2 + {"c1": 0, "c2": 8, "c2s": 2, "c2a": 4}[kind])
                 rows.append(dict(rb=args.rb, a_mode=args.a_mode, stage=si + 1, C=Cc, L=L, k=k, dil=dil, kind=kind, us=round(us, 1),
                                  tflops=round(flops / us / 1e6, 1), hbm_gbs=round(bytes_ / us / 1e3, 1)))
                 print(json.dumps(rows[-1]), flush=True)
