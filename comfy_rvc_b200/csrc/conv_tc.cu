@@ -467,78 +467,66 @@ __global__ void cl32_to_cl16_kernel(const float* __restrict__ x, unsigned char* 
   }
 }
 
-// x32 (PV fp32) += noise_conv(har);  x16 (channels-last 16 bit) = cvt(lrelu(x32))
-// (models.py:552-553 + the lrelu of modules.py:297).  HBM-bound: 4 B read + 4 B write + 2 B write per element.
-// One thread owns CPT consecutive channels of one time row: CPT/4 plane accesses (each coalesced across the warp)
-// and one contiguous CPT*2-byte piece of the 16-bit row (whole 32-byte sectors, no partial-sector writes).
-template <int CPT>
-__global__ void noise_add_pv_kernel(const float* __restrict__ har, const float* __restrict__ wn, const float* __restrict__ nb,
-                                    unsigned char* __restrict__ x32, unsigned char* __restrict__ x16,
-                                    unsigned char* __restrict__ xr16, int write32, long long L_har,
-                                    long long L, int C, int k, int s, int pad, int Lp, int padf, float slope, bool BF16) {
-  extern __shared__ float sw[];  // [k][C] + [C]
+// x = x32 (planar-vector fp32, the transposed conv's output) + noise_conv(har);  x16 (channels-last 16 bit) =
+// cvt(lrelu(x))   (models.py:552-553 + the lrelu of modules.py:297).  HBM-bound: 4 B read + 2 B write per element.
+// A block owns tiles of TR time rows x all C channels: planar reads are coalesced along time (thread = row), the
+// 16-bit rows are assembled in shared memory (16-byte pieces XOR-swizzled by row) and leave as one contiguous
+// TR*C*2-byte copy -- a direct store from the thread = row mapping is 32 L2 requests of 8 bytes per warp instruction.
+__global__ void __launch_bounds__(256)
+noise_add_tile_kernel(const float* __restrict__ har, const float* __restrict__ wn, const float* __restrict__ nb,
+                      unsigned char* __restrict__ x32, unsigned char* __restrict__ x16, int write32, long long L_har,
+                      long long L, int C, int k, int s, int pad, int Lp, int padf, float slope, bool BF16, int TR) {
+  extern __shared__ __align__(16) unsigned char nsm[];
+  const int hs = s + 1;                                            // padded har row: (r, j) -> r*hs + j, conflict-free
+  const int n_hrows = TR + (k + s - 1) / s;                        // rows of s samples the tile's taps touch
+  float* sw = reinterpret_cast<float*>(nsm);                       // [k][C] + [C]
+  float* sh = sw + (size_t)k * C + C;                              // [n_hrows][hs]
+  unsigned char* tile = reinterpret_cast<unsigned char*>(sh + (((size_t)n_hrows * hs + 3) & ~(size_t)3));   // [TR][C] 16 bit
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) sw[k * C + i] = nb[i];
-  __syncthreads();
   const int b = blockIdx.y;
-  const int ng = C / CPT;
-  const long long total = L * ng;
   const float* hb = har + (long long)b * L_har;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int gch = (int)(idx / L);
-    const long long t = idx - (long long)gch * L;
-    const int c = gch * CPT;
-    float4 xv[CPT / 4];
-    unsigned char* px = x32 + (((long long)b * (C / 4) + c / 4) * Lp + padf + t) * 16;
-#pragma unroll
-    for (int q = 0; q < CPT / 4; ++q) xv[q] = *reinterpret_cast<const float4*>(px + (long long)q * Lp * 16);
-    float acc[CPT];
-#pragma unroll
-    for (int q = 0; q < CPT / 4; ++q) {
-      const float4 bq = *reinterpret_cast<const float4*>(sw + k * C + c + q * 4);
-      acc[q * 4 + 0] = bq.x; acc[q * 4 + 1] = bq.y; acc[q * 4 + 2] = bq.z; acc[q * 4 + 3] = bq.w;
+  const int n4 = C / 4, pieces = C / 8;
+  const int pmask = pieces >= 8 ? 7 : pieces - 1;
+  const long long n_tiles = (L + TR - 1) / TR;
+  for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const long long t0 = tl * TR;
+    __syncthreads();                                               // previous tile fully copied out; weights visible
+    const long long h0 = t0 * s - pad;
+    for (int i = threadIdx.x; i < n_hrows * s; i += blockDim.x) {
+      const long long h = h0 + i;
+      sh[(i / s) * hs + (i % s)] = (h >= 0 && h < L_har) ? __ldg(hb + h) : 0.f;
     }
-    const long long h0 = t * s - pad;
-    for (int kk = 0; kk < k; ++kk) {
-      const long long h = h0 + kk;
-      if (h < 0 || h >= L_har) continue;
-      const float hv = __ldg(hb + h);
-      const float* wr = sw + kk * C + c;
-#pragma unroll
-      for (int q = 0; q < CPT / 4; ++q) {
-        const float4 wq = *reinterpret_cast<const float4*>(wr + q * 4);
-        acc[q * 4 + 0] = fmaf(hv, wq.x, acc[q * 4 + 0]);
-        acc[q * 4 + 1] = fmaf(hv, wq.y, acc[q * 4 + 1]);
-        acc[q * 4 + 2] = fmaf(hv, wq.z, acc[q * 4 + 2]);
-        acc[q * 4 + 3] = fmaf(hv, wq.w, acc[q * 4 + 3]);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TR * n4; idx += blockDim.x) {
+      const int r = idx % TR, g4 = idx / TR;
+      const long long t = t0 + r;
+      if (t >= L) continue;
+      unsigned char* px = x32 + (((long long)b * n4 + g4) * Lp + padf + t) * 16;
+      float4 xv = *reinterpret_cast<const float4*>(px);
+      const float4 bq = *reinterpret_cast<const float4*>(sw + k * C + g4 * 4);
+      float a0 = bq.x, a1 = bq.y, a2 = bq.z, a3 = bq.w;
+      const float* hp = sh + r * hs;                               // tap kk -> har row r + kk / s, column kk % s
+      for (int kk = 0, j = 0; kk < k; ++kk) {
+        const float hv = hp[j];
+        const float4 wq = *reinterpret_cast<const float4*>(sw + kk * C + g4 * 4);
+        a0 = fmaf(hv, wq.x, a0); a1 = fmaf(hv, wq.y, a1); a2 = fmaf(hv, wq.z, a2); a3 = fmaf(hv, wq.w, a3);
+        if (++j == s) { j = 0; hp += hs; }
       }
+      xv.x += a0; xv.y += a1; xv.z += a2; xv.w += a3;
+      if (write32) *reinterpret_cast<float4*>(px) = xv;
+      uint2 o;
+      o.x = pack2(BF16, lrelu(xv.x, slope), lrelu(xv.y, slope));
+      o.y = pack2(BF16, lrelu(xv.z, slope), lrelu(xv.w, slope));
+      const int piece = (g4 >> 1) ^ (r & pmask);
+      *reinterpret_cast<uint2*>(tile + ((size_t)r * pieces + piece) * 16 + (g4 & 1) * 8) = o;
     }
-#pragma unroll
-    for (int q = 0; q < CPT / 4; ++q) {
-      xv[q].x += acc[q * 4 + 0]; xv[q].y += acc[q * 4 + 1]; xv[q].z += acc[q * 4 + 2]; xv[q].w += acc[q * 4 + 3];
-      if (write32) *reinterpret_cast<float4*>(px + (long long)q * Lp * 16) = xv[q];
-    }
-    if (xr16 != nullptr) {   // raw fp16 copy: the residual stream the resblocks add
-      unsigned char* pr = xr16 + (((long long)b * L + t) * C + c) * 2;
-#pragma unroll
-      for (int q = 0; q < CPT / 8; ++q) {
-        const float4 a = xv[2 * q], d = xv[2 * q + 1];
-        uint4 o;
-        o.x = pack2(false, a.x, a.y); o.y = pack2(false, a.z, a.w);
-        o.z = pack2(false, d.x, d.y); o.w = pack2(false, d.z, d.w);
-        *reinterpret_cast<uint4*>(pr + q * 16) = o;
-      }
-    }
-    unsigned char* p16 = x16 + (((long long)b * L + t) * C + c) * 2;
-#pragma unroll
-    for (int q = 0; q < CPT / 8; ++q) {
-      const float4 a = xv[2 * q], d = xv[2 * q + 1];
-      uint4 o;
-      o.x = pack2(BF16, lrelu(a.x, slope), lrelu(a.y, slope));
-      o.y = pack2(BF16, lrelu(a.z, slope), lrelu(a.w, slope));
-      o.z = pack2(BF16, lrelu(d.x, slope), lrelu(d.y, slope));
-      o.w = pack2(BF16, lrelu(d.z, slope), lrelu(d.w, slope));
-      *reinterpret_cast<uint4*>(p16 + q * 16) = o;
+    __syncthreads();
+    const long long rows_here = (L - t0) < TR ? (L - t0) : TR;
+    uint4* dst = reinterpret_cast<uint4*>(x16 + (((long long)b * L + t0) * C) * 2);
+    for (int i = threadIdx.x; i < (int)rows_here * pieces; i += blockDim.x) {
+      const int r = i / pieces, pc = i - r * pieces;
+      dst[i] = *reinterpret_cast<const uint4*>(tile + ((size_t)r * pieces + (pc ^ (r & pmask))) * 16);
     }
   }
 }
@@ -737,24 +725,30 @@ cudaError_t launch_cl32_to_cl16(const float* x, void* y16, long long numel, floa
   return cudaGetLastError();
 }
 
-cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, void* xr16,
-                                bool write32, int B, long long L_har, long long L, int C, int k, int s, int pad, int Lp,
-                                int padf, float slope, bool bf16, cudaStream_t st) {
-  const size_t smem = sizeof(float) * ((size_t)k * C + C);
-  if (C % 8 != 0) return cudaErrorInvalidValue;
-  const int cpt = C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : 8);
-  auto kern = cpt == 32 ? noise_add_pv_kernel<32> : (cpt == 16 ? noise_add_pv_kernel<16> : noise_add_pv_kernel<8>);
-  static size_t cfg[3] = {48 * 1024, 48 * 1024, 48 * 1024};
-  size_t& c = cfg[cpt == 32 ? 0 : (cpt == 16 ? 1 : 2)];
-  if (smem > c) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, bool write32, int B,
+                                long long L_har, long long L, int C, int k, int s, int pad, int Lp, int padf, float slope,
+                                bool bf16, cudaStream_t st) {
+  if (C % 8 != 0 || C / 8 > 64 || ((C / 8) & (C / 8 - 1)) != 0 || s < 1 || k < 1) return cudaErrorInvalidValue;
+  // tile rows: as many as fit beside the taps in ~100 KB (two blocks per SM), at most 128
+  int TR = 128;
+  auto smem_for = [&](int tr) {
+    const size_t nh = (size_t)(tr + (k + s - 1) / s) * (s + 1);
+    return sizeof(float) * ((size_t)k * C + C + ((nh + 3) & ~(size_t)3)) + (size_t)tr * C * 2;
+  };
+  while (TR > 8 && smem_for(TR) > 100 * 1024) TR >>= 1;
+  const size_t smem = smem_for(TR);
+  static size_t cfgd = 48 * 1024;
+  if (smem > cfgd) {
+    cudaError_t e = cudaFuncSetAttribute(noise_add_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    c = smem;
+    cfgd = smem;
   }
-  dim3 grid(grid_for(L * (C / cpt), 256), B);
-  kern<<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32), reinterpret_cast<unsigned char*>(x16),
-                                reinterpret_cast<unsigned char*>(xr16), write32 ? 1 : 0, L_har, L, C, k, s, pad, Lp, padf, slope,
-                                bf16);
+  const long long n_tiles = (L + TR - 1) / TR;
+  const long long per = smem > 56 * 1024 ? 2 : 4;                  // resident blocks per SM
+  dim3 grid((unsigned)(n_tiles < 148 * per ? n_tiles : 148 * per), B);
+  noise_add_tile_kernel<<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32),
+                                                reinterpret_cast<unsigned char*>(x16), write32 ? 1 : 0, L_har, L, C, k, s, pad, Lp,
+                                                padf, slope, bf16, TR);
   launch_counter().n++;
   return cudaGetLastError();
 }

@@ -17,11 +17,11 @@ bool rbconv_tc_supported(const TcConvDesc& d);
 cudaError_t launch_rbconv_tc(const TcConvDesc& d, int B, cudaStream_t st);
 cudaError_t launch_zero_pads(void* base, long long planes, int Lp, int padf, long long L, cudaStream_t st);
 cudaError_t launch_cl32_to_cl16(const float* x, void* y16, long long numel, float slope, bool bf16, cudaStream_t st);
-// x = x32 (PV fp32, ups output) + noise_conv(har): x16 = lrelu(x) in the MMA operand format, xr16 = raw fp16 (residual
-// stream, may be null), x32 written back only when write32 (stage taps)
-cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, void* xr16,
-                                bool write32, int B, long long L_har, long long L, int C, int k, int s, int pad, int Lp,
-                                int padf, float slope, bool bf16, cudaStream_t st);
+// x = x32 (PV fp32, ups output) + noise_conv(har): x16 = lrelu(x) as 16-bit channels-last (the activation stream);
+// x32 is written back only when write32 (stage taps)
+cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, bool write32, int B,
+                                long long L_har, long long L, int C, int k, int s, int pad, int Lp, int padf, float slope,
+                                bool bf16, cudaStream_t st);
 cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int B, long long L, int C, int k, int Lp,
                                 int padf, float slope, cudaStream_t st);
 // same, x planar-vector fp16 [B][C/8][Lp][8] (k = 7)

@@ -891,7 +891,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
         int nk, ns, np;
         noise_geom(f, i, &nk, &ns, &np);
         const bool want_tap = tp.find(S("dec.ups.%d", i).c_str()) != nullptr;
-        CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, nullptr, want_tap, B,
+        CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, want_tap, B,
                                    Lout, Ln, Cn, nk, ns, np, LpN, kPadF, 0.1f, false, st),
             "dec.noise_add(pv)");
       }

@@ -246,7 +246,9 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
     // of every epilogue-heavy shape (profiles/r1_conv_shapes_v8_*.jsonl).  Instead each warp moves [32 rows][32 channels]
     // boxes with TMA: the residual box lands in a SWIZZLE_64B staging slot (2 slots, loaded one chunk ahead), the
     // 16-bit output box is written to a staging slot by the lanes (conflict-free under the swizzle) and stored by one
-    // lane; fp32 planar accumulators (branch sum) keep the direct path: their warp accesses are 512 B contiguous.
+    // lane.  The fp16 planar branch sum keeps the direct path: its warp accesses are 512 B contiguous.
+    // The chunk loop is unrolled by two only (slot indices stay compile-time): the fully unrolled version was 240 KB of
+    // SASS and 39 % of all warp stalls were instruction fetches (ncu source view, profiles/r1_ncu_rbconv_v8.md).
     const int eg = (warp - 2) >> 2;
     const int ew = warp - 2;
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
@@ -257,201 +259,161 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
     const float neg_scale = p.res_neg_scale == 0.f ? 1.f : p.res_neg_scale;
     const bool has_r16 = p.res16 != nullptr;
     const bool has_y16 = p.y16 != nullptr;
+    const bool has_acc = p.y32 != nullptr;          // planar-vector fp16 branch sum [C/8][Lp][8]
+    const bool do_acc = has_acc && p.accum != 0;
     unsigned char* my_stage = sE + (size_t)ew * K::EPI_WARP_BYTES;      // [2 residual][OUT_SLOTS output] boxes
     uint64_t* my_res_full = res_full + ew * 2;
     // byte offset of this lane's 16-byte piece j inside a SWIZZLE_64B box: row = lane (64 B), piece ^= (row >> 1) & 3
     const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = ((uint32_t)lane >> 1) & 3u;
-    uint32_t rcnt = 0;                              // residual boxes consumed so far (slot = rcnt & 1)
+    uint32_t rpar = 0;                              // phase parity of the two residual slots (both flip once per pair)
     uint32_t ocnt = 0;                              // output boxes stored so far
     uint32_t it = (uint32_t)eg;
+    constexpr int CPS = C / 32;                     // chunks per 128-row sub-tile (power of two)
 #pragma unroll 1
     for (unsigned tile = blockIdx.x + (unsigned)eg * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
       const unsigned b = tile / n_mt, mt = tile - b * n_mt;
       const int wrow0 = (int)mt * K::TILE_M + qd * 32;            // first row of this warp's 32-row group (sub-tile 0)
       const int row_base = wrow0 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(eg * MSUB * C);
-      const bool acc16 = p.acc_f16 != 0;            // branch sum in planar-vector fp16 [C/8][Lp][8]
-      unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (C / (acc16 ? 8 : 4)) * pitch_o : nullptr;
-      const unsigned char* r32 = p.res32 ? reinterpret_cast<const unsigned char*>(p.res32) + (size_t)b * (C / 4) * pitch_o : nullptr;
+      unsigned char* acc = has_acc ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (C / 8) * pitch_o : nullptr;
       unsigned char* y16 = has_y16 ? reinterpret_cast<unsigned char*>(p.y16) + (size_t)b * (size_t)p.Lj * C * 2 : nullptr;
       const unsigned char* r16 = has_r16 ? reinterpret_cast<const unsigned char*>(p.res16) + (size_t)b * (size_t)p.Lj * C * 2 : nullptr;
-      const bool do_acc = p.accum != 0;
 
-      // ---- residual fetch: TMA boxes (C <= 128) or direct prefetch ring of raw 16-byte words ----
-      uint4 rq[16];   // direct paths: fp32 planar = 8 words per chunk x 2 slots; fp16 channels-last = 4 words x 4 slots
-      auto issue_box = [&](int ci, uint32_t cnt) {     // one lane: residual box of chunk ci -> staging slot cnt & 1
-        const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
-        uint64_t* bar = &my_res_full[cnt & 1u];
+      uint4 rq[16];   // [0,8): direct residual, 2 slots x 4 words (C = 256); [8,16): branch-sum prefetch, 2 slots x 4 words
+      auto issue_box = [&](int ci, int slot) {       // one lane: residual box of chunk ci -> staging slot
+        const int ms = ci / CPS, c0 = (ci - ms * CPS) * 32;
+        uint64_t* bar = &my_res_full[slot];
         mbar_expect_tx(bar, kEpiBox);
-        tma_load_3d(my_stage + (cnt & 1u) * kEpiBox, &tmR, c0, wrow0 + ms * 128, (int)b, bar);
+        tma_load_3d(my_stage + slot * kEpiBox, &tmR, c0, wrow0 + ms * 128, (int)b, bar);
       };
-      auto load_res = [&](int ci) {
-        const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
+      auto load_res = [&](int ci, int slot) {        // direct path (C = 256): this lane's 64 bytes of the residual row
+        const int ms = ci / CPS, c0 = (ci - ms * CPS) * 32;
         const int row = row_base + ms * 128;
         if (row < p.Lj) {
-          if (has_r16) {
-            const uint4* q = reinterpret_cast<const uint4*>(r16 + ((size_t)row * C + c0) * 2);
+          const uint4* q = reinterpret_cast<const uint4*>(r16 + ((size_t)row * C + c0) * 2);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rq[(ci & 3) * 4 + k] = ld_nc_u4(q + k);
-          } else if (r32 != nullptr) {
-            const unsigned char* q = r32 + (size_t)(c0 / 4) * pitch_o + (size_t)(row + p.padf) * 16;
-#pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) rq[(ci & 1) * 8 + k4] = *reinterpret_cast<const uint4*>(q + (size_t)k4 * pitch_o);
-          }
+          for (int k = 0; k < 4; ++k) rq[slot * 4 + k] = ld_nc_u4(q + k);
         }
       };
-      // fp16 branch-sum prefetch (one chunk ahead), only beside the TMA residual path (rq is free there)
-      const bool acc_pf = K::EPI_TMA && acc16 && do_acc && y32 != nullptr && r32 == nullptr;
-      auto load_acc = [&](int ci) {
-        const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
+      auto load_acc = [&](int ci, int slot) {
+        const int ms = ci / CPS, c0 = (ci - ms * CPS) * 32;
         const int row = row_base + ms * 128;
         if (row < p.Lj) {
-          const unsigned char* q = y32 + (size_t)(c0 / 8) * pitch_o + (size_t)(row + p.padf) * 16;
+          const unsigned char* q = acc + (size_t)(c0 / 8) * pitch_o + (size_t)(row + p.padf) * 16;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) rq[8 + (ci & 1) * 4 + k] = *reinterpret_cast<const uint4*>(q + (size_t)k * pitch_o);
+          for (int k = 0; k < 4; ++k) rq[8 + slot * 4 + k] = *reinterpret_cast<const uint4*>(q + (size_t)k * pitch_o);
         }
       };
-      if (acc_pf) load_acc(0);
-      // the first residuals are in flight before the MMAs of this tile finish
-      if (K::EPI_TMA && has_r16) {
-        if (lane == 0) {
-          issue_box(0, rcnt);
-          if (1 < K::NCH) issue_box(1, rcnt + 1);
-        }
-      } else {
-        load_res(0);
-        if (has_r16) {
-          if (1 < K::NCH) load_res(1);
-          if (2 < K::NCH) load_res(2);
+      // the first residual / branch-sum words are in flight before the MMAs of this tile finish
+      if (has_r16) {
+        if (K::EPI_TMA) {
+          if (lane == 0) { issue_box(0, 0); issue_box(1, 1); }
+        } else {
+          load_res(0, 0);
         }
       }
+      if (do_acc) load_acc(0, 0);
       mbar_wait(&acc_full[eg], (it >> 1) & 1u);
       tc_fence_after();
+#pragma unroll 1
+      for (int cp = 0; cp < K::NCH; cp += 2) {
 #pragma unroll
-      for (int ci = 0; ci < K::NCH; ++ci) {
-        const int ms = ci / (C / 32), c0 = (ci - ms * (C / 32)) * 32;
-        const int row = row_base + ms * 128;
-        const bool row_ok = row < p.Lj;
-        if (!(K::EPI_TMA && has_r16)) {
-          if (has_r16) {
-            if (ci + 3 < K::NCH) load_res(ci + 3);
-          } else {
-            if (ci + 1 < K::NCH) load_res(ci + 1);
-          }
-        }
-        if (acc_pf && ci + 1 < K::NCH) load_acc(ci + 1);
-        uint32_t r[32];
-        const uint32_t taddr = tbase + (uint32_t)(ms * C + c0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
-            "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float v[32];
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 bq = *reinterpret_cast<const float4*>(sbias + c0 + k4 * 4);
-          v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
-          v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
-          v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
-          v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
-        }
-        if (K::EPI_TMA && has_r16) {
-          // residual box of this chunk: wait, read this lane's row, hand the slot back, refill it two chunks ahead
-          const unsigned char* box = my_stage + (rcnt & 1u) * kEpiBox + sw_row;
-          mbar_wait(&my_res_full[rcnt & 1u], (rcnt >> 1) & 1u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint4 w = *reinterpret_cast<const uint4*>(box + ((((uint32_t)k) ^ sw_x) << 4));
-            add_res8(v + k * 8, w, neg_scale);
-          }
-          __syncwarp();
-          if (lane == 0 && ci + 2 < K::NCH) issue_box(ci + 2, rcnt + 2);
-          ++rcnt;
-        } else if (has_r16) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) add_res8(v + k * 8, rq[(ci & 3) * 4 + k], neg_scale);
-        } else if (r32 != nullptr) {
+        for (int u = 0; u < 2; ++u) {
+          const int ci = cp + u;
+          const int ms = ci / CPS, c0 = (ci - ms * CPS) * 32;
+          const int row = row_base + ms * 128;
+          const bool row_ok = row < p.Lj;
+          if (!K::EPI_TMA && has_r16 && ci + 1 < K::NCH) load_res(ci + 1, u ^ 1);
+          if (do_acc && ci + 1 < K::NCH) load_acc(ci + 1, u ^ 1);
+          uint32_t r[32];
+          const uint32_t taddr = tbase + (uint32_t)(ms * C + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+              "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float v[32];
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
-            const uint4 w = rq[(ci & 1) * 8 + k4];
-            v[k4 * 4 + 0] += __uint_as_float(w.x); v[k4 * 4 + 1] += __uint_as_float(w.y);
-            v[k4 * 4 + 2] += __uint_as_float(w.z); v[k4 * 4 + 3] += __uint_as_float(w.w);
+            const float4 bq = *reinterpret_cast<const float4*>(sbias + c0 + k4 * 4);
+            v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
+            v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
+            v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
+            v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
           }
-        }
-        if (y32 != nullptr && row_ok) {
-          const size_t orow16 = (size_t)(row + p.padf) * 16;
-          if (do_acc) {
-            if (acc16) {
+          if (has_r16) {
+            if (K::EPI_TMA) {
+              // residual box of this chunk: wait, read this lane's row, hand the slot back, refill it two chunks ahead
+              const unsigned char* box = my_stage + u * kEpiBox + sw_row;
+              mbar_wait(&my_res_full[u], rpar);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint4 w = acc_pf ? rq[8 + (ci & 1) * 4 + k]
-                                       : *reinterpret_cast<const uint4*>(y32 + (size_t)(c0 / 8 + k) * pitch_o + orow16);
-                add_res8(v + k * 8, w, 1.f);
-              }
+              for (int k = 0; k < 4; ++k)
+                add_res8(v + k * 8, *reinterpret_cast<const uint4*>(box + ((((uint32_t)k) ^ sw_x) << 4)), neg_scale);
+              __syncwarp();
+              if (lane == 0 && ci + 2 < K::NCH) issue_box(ci + 2, u);
             } else {
 #pragma unroll
-              for (int k4 = 0; k4 < 8; ++k4) {
-                const float4 aq = *reinterpret_cast<const float4*>(y32 + (size_t)(c0 / 4 + k4) * pitch_o + orow16);
-                v[k4 * 4 + 0] += aq.x; v[k4 * 4 + 1] += aq.y; v[k4 * 4 + 2] += aq.z; v[k4 * 4 + 3] += aq.w;
-              }
+              for (int k = 0; k < 4; ++k) add_res8(v + k * 8, rq[u * 4 + k], neg_scale);
             }
           }
-          if (inv_div != 1.f) {
+          if (has_acc) {
+            if (do_acc) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) add_res8(v + k * 8, rq[8 + u * 4 + k], 1.f);
+            }
+            if (inv_div != 1.f) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
+            }
+            if (row_ok) {
+              unsigned char* q = acc + (size_t)(c0 / 8) * pitch_o + (size_t)(row + p.padf) * 16;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                uint4 o;
+                o.x = pack2(false, v[k * 8 + 0], v[k * 8 + 1]); o.y = pack2(false, v[k * 8 + 2], v[k * 8 + 3]);
+                o.z = pack2(false, v[k * 8 + 4], v[k * 8 + 5]); o.w = pack2(false, v[k * 8 + 6], v[k * 8 + 7]);
+                *reinterpret_cast<uint4*>(q + (size_t)k * pitch_o) = o;
+              }
+            }
+          } else if (inv_div != 1.f) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
           }
-          if (acc16) {
+          if (has_y16) {
+            uint4 o[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint4 o;
-              o.x = pack2(false, v[k * 8 + 0], v[k * 8 + 1]); o.y = pack2(false, v[k * 8 + 2], v[k * 8 + 3]);
-              o.z = pack2(false, v[k * 8 + 4], v[k * 8 + 5]); o.w = pack2(false, v[k * 8 + 6], v[k * 8 + 7]);
-              *reinterpret_cast<uint4*>(y32 + (size_t)(c0 / 8 + k) * pitch_o + orow16) = o;
+            for (int k8 = 0; k8 < 4; ++k8) {
+              o[k8].x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
+              o[k8].y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
+              o[k8].z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
+              o[k8].w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
             }
-          } else {
+            if (K::EPI_TMA) {
+              // stage the [32 rows][32 channels] box, then one lane stores it (rows >= L are clipped by the tensor map)
+              unsigned char* box = my_stage + (2 + (ocnt % K::OUT_SLOTS)) * kEpiBox;
+              if (lane == 0) bulk_wait_read<K::OUT_SLOTS - 1>();      // the store that last used this slot has read it
+              __syncwarp();
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4)
-              *reinterpret_cast<float4*>(y32 + (size_t)(c0 / 4 + k4) * pitch_o + orow16) =
-                  make_float4(v[k4 * 4 + 0], v[k4 * 4 + 1], v[k4 * 4 + 2], v[k4 * 4 + 3]);
-          }
-        } else if (inv_div != 1.f) {
+              for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(box + sw_row + ((((uint32_t)k) ^ sw_x) << 4)) = o[k];
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmY, box, c0, wrow0 + ms * 128, (int)b);
+                bulk_commit();
+              }
+              ++ocnt;
+            } else if (row_ok) {
+              unsigned char* yr = y16 + ((size_t)row * C + c0) * 2;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
-        }
-        if (has_y16) {
-          uint4 o[4];
-#pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) {
-            o[k8].x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
-            o[k8].y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
-            o[k8].z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
-            o[k8].w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
-          }
-          if (K::EPI_TMA) {
-            // stage the [32 rows][32 channels] box, then one lane stores it (rows >= L are clipped by the tensor map)
-            unsigned char* box = my_stage + (2 + (ocnt % K::OUT_SLOTS)) * kEpiBox;
-            if (lane == 0) bulk_wait_read<K::OUT_SLOTS - 1>();        // the store that last used this slot has read it
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(box + sw_row + ((((uint32_t)k) ^ sw_x) << 4)) = o[k];
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_3d(&tmY, box, c0, wrow0 + ms * 128, (int)b);
-              bulk_commit();
+              for (int k8 = 0; k8 < 4; ++k8) *reinterpret_cast<uint4*>(yr + k8 * 16) = o[k8];
             }
-            ++ocnt;
-          } else if (row_ok) {
-            unsigned char* yr = y16 + ((size_t)row * C + c0) * 2;
-#pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) *reinterpret_cast<uint4*>(yr + k8 * 16) = o[k8];
           }
         }
+        if (K::EPI_TMA && has_r16) rpar ^= 1u;
       }
       tc_fence_before();
       __syncwarp();
@@ -568,7 +530,8 @@ bool rbconv_tc_supported(const TcConvDesc& d) {
   if (!(d.Cin == 32 || d.Cin == 64 || d.Cin == 128 || d.Cin == 256)) return false;
   if (!(d.ntaps == 3 || d.ntaps == 7 || d.ntaps == 11) || !(d.dil == 1 || d.dil == 3 || d.dil == 5)) return false;
   if (d.g_off[0] != -((d.ntaps - 1) / 2) * d.dil) return false;
-  if ((d.accum && !d.y32) || !d.x16 || !d.w16 || !d.bias || (d.res16 && d.res32) || d.a_fp16) return false;
+  if ((d.accum && !d.y32) || !d.x16 || !d.w16 || !d.bias || d.a_fp16) return false;
+  if (d.res32 || (d.y32 && !d.acc_f16)) return false;      // fp32 planar residual / output: generic kernel only
   return true;
 }
 

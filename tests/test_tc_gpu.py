@@ -180,10 +180,13 @@ def test_rbconv_tc(case, bf16, kind):
             d.accum, d.div = 1, 3.0
         d.in_bf16 = d.out_bf16 = int(bf16)
         st = fn(C.byref(d), B, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if fn is lib.rvcb200_op_rbconv_tc and kind in ("c2", "c2_accum_div", "c2_s16_accum_div"):
+            assert st == 1, st            # fp32 planar residual / output: the specialised kernel declines, generic only
+            continue
         assert st == 0, st
         torch.cuda.synchronize()
         outs.append((y32.cpu(), y16.cpu()))
-    (y32, y16), (g32, g16) = outs
+    (y32, y16), (g32, g16) = outs[0], outs[-1]
     want16 = torch.where(ref > 0, ref, ref * 0.1)
     err16 = (y16.float().double() - want16).abs().max().item()
     assert err16 < (0.08 if bf16 else 0.02), err16

@@ -35,7 +35,7 @@ def main():
     ap.add_argument("--dbg-alt", type=int, default=0)
     ap.add_argument("--rb", type=int, default=1, help="1: specialised resblock kernel (rbconv_tc.cu), 0: generic conv_tc")
     ap.add_argument("--stages", default="", help="comma list of stage indices (0-3) to keep")
-    ap.add_argument("--kinds", default="c1,c2,c2s,c2a", help="c1: 16-bit store only; c2: + fp32 planar residual in/out; "
+    ap.add_argument("--kinds", default="c1,c2s,c2a", help="c1: 16-bit store only; c2: + fp32 planar residual in/out; "
                     "c2s: + residual from the fp16 lrelu-domain stream; c2a: stream residual, planar fp16 branch-sum accumulate, no 16-bit store")
     ap.add_argument("--ks", default="", help="comma list of kernel sizes to keep (default all)")
     args = ap.parse_args()
