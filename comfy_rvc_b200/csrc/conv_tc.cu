@@ -498,28 +498,44 @@ noise_add_tile_kernel(const float* __restrict__ har, const float* __restrict__ w
       sh[(i / s) * hs + (i % s)] = (h >= 0 && h < L_har) ? __ldg(hb + h) : 0.f;
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < TR * n4; idx += blockDim.x) {
-      const int r = idx % TR, g4 = idx / TR;
-      const long long t = t0 + r;
-      if (t >= L) continue;
-      unsigned char* px = x32 + (((long long)b * n4 + g4) * Lp + padf + t) * 16;
-      float4 xv = *reinterpret_cast<const float4*>(px);
+    // one item = 4 rows (TR/4 apart: each of the 4 planar loads is coalesced across the warp) x 4 channels: the 4 loads
+    // are in flight together and every weight vector read from shared memory feeds 16 FMAs
+    const int RQ = TR / 4;
+    for (int idx = threadIdx.x; idx < RQ * n4; idx += blockDim.x) {
+      const int rq = idx % RQ, g4 = idx / RQ;
+      unsigned char* px0 = x32 + (((long long)b * n4 + g4) * Lp + padf + t0 + rq) * 16;
+      float4 xv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        xv[j] = (t0 + rq + j * RQ < L) ? *reinterpret_cast<const float4*>(px0 + (long long)j * RQ * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 bq = *reinterpret_cast<const float4*>(sw + k * C + g4 * 4);
-      float a0 = bq.x, a1 = bq.y, a2 = bq.z, a3 = bq.w;
-      const float* hp = sh + r * hs;                               // tap kk -> har row r + kk / s, column kk % s
+      float a[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j][0] = bq.x; a[j][1] = bq.y; a[j][2] = bq.z; a[j][3] = bq.w; }
+      const float* hp = sh + rq * hs;                              // tap kk -> har row r + kk / s, column kk % s
+      const int hstep = RQ * hs;
       for (int kk = 0, j = 0; kk < k; ++kk) {
-        const float hv = hp[j];
         const float4 wq = *reinterpret_cast<const float4*>(sw + kk * C + g4 * 4);
-        a0 = fmaf(hv, wq.x, a0); a1 = fmaf(hv, wq.y, a1); a2 = fmaf(hv, wq.z, a2); a3 = fmaf(hv, wq.w, a3);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float hv = hp[q * hstep + j];
+          a[q][0] = fmaf(hv, wq.x, a[q][0]); a[q][1] = fmaf(hv, wq.y, a[q][1]);
+          a[q][2] = fmaf(hv, wq.z, a[q][2]); a[q][3] = fmaf(hv, wq.w, a[q][3]);
+        }
         if (++j == s) { j = 0; hp += hs; }
       }
-      xv.x += a0; xv.y += a1; xv.z += a2; xv.w += a3;
-      if (write32) *reinterpret_cast<float4*>(px) = xv;
-      uint2 o;
-      o.x = pack2(BF16, lrelu(xv.x, slope), lrelu(xv.y, slope));
-      o.y = pack2(BF16, lrelu(xv.z, slope), lrelu(xv.w, slope));
-      const int piece = (g4 >> 1) ^ (r & pmask);
-      *reinterpret_cast<uint2*>(tile + ((size_t)r * pieces + piece) * 16 + (g4 & 1) * 8) = o;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = rq + q * RQ;
+        if (t0 + r >= L) continue;
+        xv[q].x += a[q][0]; xv[q].y += a[q][1]; xv[q].z += a[q][2]; xv[q].w += a[q][3];
+        if (write32) *reinterpret_cast<float4*>(px0 + (long long)q * RQ * 16) = xv[q];
+        uint2 o;
+        o.x = pack2(BF16, lrelu(xv[q].x, slope), lrelu(xv[q].y, slope));
+        o.y = pack2(BF16, lrelu(xv[q].z, slope), lrelu(xv[q].w, slope));
+        const int piece = (g4 >> 1) ^ (r & pmask);
+        *reinterpret_cast<uint2*>(tile + ((size_t)r * pieces + piece) * 16 + (g4 & 1) * 8) = o;
+      }
     }
     __syncthreads();
     const long long rows_here = (L - t0) < TR ? (L - t0) : TR;
