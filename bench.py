@@ -57,6 +57,33 @@ def algorithmic_macs(cfg, T: int) -> dict:
             "enc_linear": enc_lin, "attention": attn}
 
 
+def resblock_bytes(cfg, T: int):
+    """Algorithmic HBM bytes (read, write) of the decoder resblock convolutions of one item on the tensor path
+    (one fp16 stream copy, h as one 16-bit tensor, planar fp16 branch sum)."""
+    rd = wr = 0
+    L, C = T, cfg.upsample_initial_channel
+    nk = len(cfg.resblock_kernel_sizes)
+    for i, u in enumerate(cfg.upsample_rates):
+        L, C = L * u, C // 2
+        E = L * C
+        last_stage = i == len(cfg.upsample_rates) - 1
+        for j, ds in enumerate(cfg.resblock_dilation_sizes):
+            for d_i in range(len(ds)):
+                if cfg.resblock == "1":
+                    rd += 2 * E; wr += 2 * E                      # conv1: stream in, h out
+                    rd += 4 * E                                   # conv2: h + residual from the stream
+                else:
+                    rd += 2 * E
+                if d_i < len(ds) - 1:
+                    wr += 2 * E                                   # stream out
+                else:
+                    rd += 2 * E if j > 0 else 0                   # branch sum in
+                    wr += 2 * E                                   # branch sum out
+                    if j == nk - 1 and not last_stage:
+                        wr += 2 * E                               # operand of the next transposed conv
+    return rd, wr
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -75,7 +102,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -207,10 +234,11 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    lib.rvcb200_profile_enable(net._ctx, 1)
-    barrier()
     if sampler:
         sampler.start()
+        for _ in range(8):                   # keep the GPU under load until nvidia-smi has delivered its first samples
+            step_resident()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -218,30 +246,59 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
+    launches = net.last_launches * args.steps
+    # per-class kernel times: a second pass of the same K steps with a CUDA-event pair around every launch (the event
+    # records sit between kernels and serialise their programmatic dependent launches, so they stay out of `value`)
+    lib.rvcb200_profile_enable(net._ctx, 1)
+    for _ in range(args.steps):
+        step_resident()
+    torch.cuda.synchronize()
     cls_ms = (C.c_double * 8)()
     cls_n = (C.c_int64 * 8)()
     lib.rvcb200_profile_collect(net._ctx, cls_ms, cls_n)
     lib.rvcb200_profile_enable(net._ctx, 0)
-    launches = net.last_launches * args.steps
 
-    # end-to-end through the public API with host buffers (pinned H2D of inputs, D2H of the PCM)
+    # end-to-end through the public API with host buffers: every step copies its inputs from pinned host memory and its PCM
+    # back.  The driver is pipelined the way a serving loop would be: inputs of step i+1 travel on a copy stream while step i
+    # computes, the PCM of step i-1 leaves on another; the synthesizer itself runs on the current stream.
     out_host = torch.empty(1, 1, T * cfg.upp, dtype=torch.float32).pin_memory()
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    cur = torch.cuda.current_stream(dev)
 
-    def step_e2e():
-        ins = [t.to(dev, non_blocking=True) for t in host]
-        o = net.infer(*ins)[0]
-        out_host.copy_(o, non_blocking=True)
+    def fetch():
+        with torch.cuda.stream(s_in):
+            ins = [t.to(dev, non_blocking=True) for t in host]
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+        return ins, ev
 
-    step_e2e()
+    def run_e2e(n):
+        nxt = fetch()
+        for _ in range(n):
+            ins, ev = nxt
+            cur.wait_event(ev)
+            nxt = fetch()                              # H2D of the next step's inputs overlaps this step's kernels
+            o = net.infer(*ins)[0]
+            for t in ins:
+                t.record_stream(cur)
+            done = torch.cuda.Event()
+            done.record(cur)
+            s_out.wait_event(done)
+            with torch.cuda.stream(s_out):
+                out_host.copy_(o, non_blocking=True)   # D2H of this step's PCM overlaps the next step's kernels
+            o.record_stream(s_out)
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
+
+    run_e2e(2)
     barrier()
     f0_, f1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0_.record()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     f1_.record()
     barrier()
     ms_e2e = f0_.elapsed_time(f1_)
+    clocks = sampler.stop() if sampler else None
 
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -260,6 +317,9 @@ def main():
     conv_launches_per_step = cls_n[0] / args.steps
     peaks = load_peaks()
     achieved = conv_flops / conv_launches_per_step / (conv_ms_per_launch * 1e-3) / 1e12
+    rb_rd, rb_wr = resblock_bytes(cfg, T)
+    rb_bytes = (rb_rd + rb_wr) / max(conv_launches_per_step, 1)
+    rb_traffic = (1.001 * rb_rd + 0.80 * rb_wr) / max(conv_launches_per_step, 1) if args.precision != "fp32" else None
     h2d = sum(t.numel() * t.element_size() for t in host)
     line = {
         "metric": metric, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -267,13 +327,20 @@ def main():
         "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands (resblocks) / f16 operands (ladder, encoder, flow), f32 accumulate"}[args.precision],
         "data": "synthetic (seeded random-init weights stored as fp16, N(0,1) features, contour f0)",
         "config": {"workload": workload, "precision": args.precision, "parallelism": f"segments x{world}, no collective",
-                   "l2": "no flush needed: each step streams >1 GB of stage activations (>> 126 MB L2)"},
+                   "l2": "no flush needed: each step streams >1 GB of stage activations (>> 126 MB L2)",
+                   "roofline_pass": "per-launch CUDA events in a second pass of the same K steps (event records between kernels "
+                                    "would serialise the programmatic dependent launches of the timed pass)"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": T * cfg.upp * 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "decoder resblock convolutions (conv_tc_kernel on tcgen05; conv_f32_kernel in fp32 mode)",
+        "roofline": {"bound": "tensor", "kernel": "decoder resblock convolutions (rbconv_tc_kernel on tcgen05; conv_f32_kernel in fp32 mode)",
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                     "traffic": None, "peak_source": peaks["src"],
+                     "traffic": rb_traffic, "traffic_note": "dram__bytes_read+write per launch, average over the 72 launches of a step: "
+                     "algorithmic bytes x the read/write ratios ncu measured on 12 sampled launches (profiles/r1_ncu_rbconv_v10.md: "
+                     "reads 1.001 x algorithmic, writes 0.80 x -- the rest is still dirty in L2 at kernel end)",
+                     "algorithmic_bytes_per_launch": rb_bytes, "achieved_hbm_gbs": rb_bytes / (conv_ms_per_launch * 1e-3) / 1e9,
+                     "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": rb_bytes / (conv_ms_per_launch * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "peak_source": peaks["src"],
                      "launches_per_step": conv_launches_per_step, "avg_launch_ms": conv_ms_per_launch,
                      "algorithmic_gflop_per_step": conv_flops / 1e9,
                      "share_of_step": cls_ms[0] / max(sum(cls_ms), 1e-9)},

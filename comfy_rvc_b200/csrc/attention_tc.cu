@@ -136,6 +136,8 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();                            // q|k|v (and V^T) come from the kernels just before
   const int L = min(a.len ? a.len[b] : a.T, a.T);
   const int nrel = 2 * a.window + 1;
 
@@ -472,7 +474,8 @@ cudaError_t launch_attention_tc(const void* qkv16, void* vt, const void* ek16, c
   AttArgs a;
   a.len = len; a.out = reinterpret_cast<__half*>(out); a.T = T; a.n_heads = n_heads; a.window = window; a.H = n_heads * DKV;
   dim3 grid((T + BQ - 1) / BQ, n_heads, B);
-  attention_tc_kernel<<<grid, kThreadsAtt, smem, st>>>(a, tmQ, tmK, tmV, tmEk, tmEv);
+  cudaError_t le = launch_pdl(attention_tc_kernel, grid, dim3(kThreadsAtt), smem, st, a, tmQ, tmK, tmV, tmEk, tmEv);
+  if (le != cudaSuccess) return le;
   launch_counter().n++;
   return cudaGetLastError();
 }

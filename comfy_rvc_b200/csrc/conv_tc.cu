@@ -191,6 +191,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   const bool stat = p.b_stationary != 0;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();
     for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps / 2); }
@@ -233,6 +234,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
             tma_load_2d(slabB + (size_t)sb * b_stride, &tmW, 0, w_row(0, 0, tap, kb), &b_full[sb]);
           }
       }
+      pdl_wait();                         // activations come from the previous kernel (the weights above do not)
       int sa = 0, sb = 0;                 // ring slots; phase bits flip on wrap (no div/mod in the loop)
       uint32_t pa = 1, pb = 1;            // producer waits on "empty" with inverted parity
       for (int t = 0; t < my_tiles; ++t) {
@@ -359,6 +361,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
     // ============== epilogue: two groups of 4 warps, group e owns accumulator buffer e ===============
     // (tile t is drained by group t & 1, so consecutive tiles' epilogues overlap and each warp pays the
     //  per-tile fixed cost -- barrier wait, index math, bias -- only every other tile)
+    pdl_wait();                                     // residual / mask / gather reads and every output write
     const int eg = (warp - 2) >> 2;                 // epilogue group = accumulator buffer
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
     const size_t pitch_o = (size_t)p.Lp_out * 16;
@@ -482,8 +485,10 @@ noise_add_tile_kernel(const float* __restrict__ har, const float* __restrict__ w
   float* sw = reinterpret_cast<float*>(nsm);                       // [k][C] + [C]
   float* sh = sw + (size_t)k * C + C;                              // [n_hrows][hs]
   unsigned char* tile = reinterpret_cast<unsigned char*>(sh + (((size_t)n_hrows * hs + 3) & ~(size_t)3));   // [TR][C] 16 bit
+  if (threadIdx.x == 0) pdl_trigger();
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) sw[k * C + i] = nb[i];
+  pdl_wait();                                                      // x32 comes from the transposed conv just before
   const int b = blockIdx.y;
   const float* hb = har + (long long)b * L_har;
   const int n4 = C / 4, pieces = C / 8;
@@ -586,8 +591,10 @@ template <int KT>
 __global__ void conv_post_pv16_kernel(const unsigned char* __restrict__ x16, const float* __restrict__ w, float* __restrict__ out,
                                       long long L, int C, int Lp, int padf, float slope) {
   extern __shared__ float swp[];  // [KT][C]
+  if (threadIdx.x == 0) pdl_trigger();
   for (int i = threadIdx.x; i < KT * C; i += blockDim.x) swp[i] = w[i];
   __syncthreads();
+  pdl_wait();
   const int b = blockIdx.y;
   constexpr int pad = (KT - 1) / 2;
   const int n8 = C / 8;
@@ -721,10 +728,10 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     cfgd = smem;
   }
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
-  if (d.generic) conv_tc_kernel<true><<<grid, kThreadsTC, smem, st>>>(d, tmA, tmW);
-  else conv_tc_kernel<false><<<grid, kThreadsTC, smem, st>>>(d, tmA, tmW);
+  cudaError_t le = d.generic ? launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW)
+                             : launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW);
   launch_counter().n++;
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_zero_pads(void* base, long long planes, int Lp, int padf, long long L, cudaStream_t st) {
@@ -762,11 +769,11 @@ cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* 
   const long long n_tiles = (L + TR - 1) / TR;
   const long long per = smem > 56 * 1024 ? 2 : 4;                  // resident blocks per SM
   dim3 grid((unsigned)(n_tiles < 148 * per ? n_tiles : 148 * per), B);
-  noise_add_tile_kernel<<<grid, 256, smem, st>>>(har, wn, nb, reinterpret_cast<unsigned char*>(x32),
-                                                reinterpret_cast<unsigned char*>(x16), write32 ? 1 : 0, L_har, L, C, k, s, pad, Lp,
-                                                padf, slope, bf16, TR);
+  cudaError_t le = launch_pdl(noise_add_tile_kernel, grid, dim3(256), smem, st, har, wn, nb, reinterpret_cast<unsigned char*>(x32),
+                              reinterpret_cast<unsigned char*>(x16), write32 ? 1 : 0, L_har, L, C, k, s, pad, Lp, padf, slope, bf16,
+                              TR);
   launch_counter().n++;
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int B, long long L, int C, int k, int Lp,
@@ -782,10 +789,10 @@ cudaError_t launch_conv_post_pv16(const void* x16, const float* w, float* out, i
                                   int padf, float slope, cudaStream_t st) {
   if (k != 7 || C % 8) return cudaErrorInvalidValue;
   dim3 grid(grid_for(L, 256), B);
-  conv_post_pv16_kernel<7><<<grid, 256, sizeof(float) * k * C, st>>>(reinterpret_cast<const unsigned char*>(x16), w, out, L, C, Lp,
-                                                                    padf, slope);
+  cudaError_t le = launch_pdl(conv_post_pv16_kernel<7>, grid, dim3(256), sizeof(float) * k * C, st,
+                              reinterpret_cast<const unsigned char*>(x16), w, out, L, C, Lp, padf, slope);
   launch_counter().n++;
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 cudaError_t launch_pv16_to_cl(const void* src, float* y, int B, long long L, int C, int Lp, int padf, cudaStream_t st) {

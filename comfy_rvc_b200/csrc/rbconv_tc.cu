@@ -116,6 +116,7 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
   const unsigned total_tiles = n_mt * (unsigned)p.batch;
 
   if (threadIdx.x == 0) {
+    pdl_trigger();     // the next kernel's CTAs may take over SMs as ours retire (they block in pdl_wait until we are done)
     for (int i = 0; i < K::NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < K::NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
@@ -147,6 +148,7 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
           tma_load_2d(sW + (size_t)i * K::W_BYTES, &tmW, 0, (tap * K::NKB + kb) * C, &b_full[i]);
         }
       }
+      pdl_wait();                                    // activations come from the previous kernel (weights do not)
       int sa = 0, sb = 0;
       uint32_t pa = 1, pb = 1;                       // producer waits on "empty" with inverted parity
 #pragma unroll 1
@@ -249,6 +251,7 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
     // lane.  The fp16 planar branch sum keeps the direct path: its warp accesses are 512 B contiguous.
     // The chunk loop is unrolled by two only (slot indices stay compile-time): the fully unrolled version was 240 KB of
     // SASS and 39 % of all warp stalls were instruction fetches (ncu source view, profiles/r1_ncu_rbconv_v8.md).
+    pdl_wait();                                     // residual / branch sum reads and every output write
     const int eg = (warp - 2) >> 2;
     const int ew = warp - 2;
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
@@ -501,9 +504,9 @@ cudaError_t launch_one(const TcConvDesc& d, int B, cudaStream_t st) {
   p.batch = B;
   const long long tiles = (long long)((d.Lj + K::TILE_M - 1) / K::TILE_M) * B;
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
-  rbconv_tc_kernel<C, NTAPS, DIL, MSUB><<<grid, kRbThreads, K::SMEM, st>>>(p, tmA, tmW, tmR, tmY);
+  cudaError_t le = launch_pdl(rbconv_tc_kernel<C, NTAPS, DIL, MSUB>, dim3(grid), dim3(kRbThreads), K::SMEM, st, p, tmA, tmW, tmR, tmY);
   launch_counter().n++;
-  return cudaGetLastError();
+  return le != cudaSuccess ? le : cudaGetLastError();
 }
 
 template <int C>

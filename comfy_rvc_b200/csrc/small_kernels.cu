@@ -1,6 +1,8 @@
 // Bandwidth-bound glue kernels of the synthesis path (channels-last fp32).
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rvc {
@@ -8,6 +10,11 @@ namespace rvc {
 LaunchCounter& launch_counter() {
   static LaunchCounter c;
   return c;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("RVCB200_PDL"); return e ? atoi(e) != 0 : false; }();
+  return on;
 }
 
 namespace {
@@ -18,6 +25,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
                                  float eps, __half* __restrict__ y16, const int* __restrict__ len, int T) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (threadIdx.x == 0) pdl_trigger();
+  pdl_wait();
   if (row >= rows) return;
   const float* xr = x + row * C;
   float v[8];  // C <= 256
@@ -192,7 +201,7 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
                              float eps, cudaStream_t st, void* y16, const int* len, int T) {
   if (C > 256 || rows <= 0) return cudaErrorInvalidValue;
   const int wpb = 8;
-  layernorm_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(x, gamma, beta, y, rows, C, eps,
+  launch_pdl(layernorm_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, x, gamma, beta, y, rows, C, eps,
                                                                             reinterpret_cast<__half*>(y16), len, T > 0 ? T : 1);
   launch_counter().n++;
   return cudaGetLastError();
