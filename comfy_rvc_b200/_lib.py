@@ -22,7 +22,7 @@ class RvcConfig(C.Structure):
         ("n_res_kernels", C.c_int32), ("res_kernels", C.c_int32 * MAX_RESK), ("n_res_dils", C.c_int32 * MAX_RESK),
         ("res_dils", (C.c_int32 * MAX_DIL) * MAX_RESK), ("n_ups", C.c_int32), ("up_rates", C.c_int32 * MAX_UPS),
         ("up_kernels", C.c_int32 * MAX_UPS), ("up_init_channels", C.c_int32), ("gin_channels", C.c_int32),
-        ("n_speakers", C.c_int32), ("sr", C.c_int32),
+        ("n_speakers", C.c_int32), ("sr", C.c_int32), ("no_f0", C.c_int32),
     ]
 
 

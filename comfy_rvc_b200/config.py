@@ -39,9 +39,10 @@ class SynthConfig:
     flow_kernel: int = 5         # models.py:654-656 / 770-772: ResidualCouplingBlock(inter, hidden, 5, 1, 3)
     flow_wn_layers: int = 3
     n_flows: int = 4
+    f0: bool = True              # False: the `_nono` classes (no pitch embedding, plain `Generator`, models.py:244-317, 812-1021)
 
     @staticmethod
-    def from_positional(args: Sequence, feat_dim: int) -> "SynthConfig":
+    def from_positional(args: Sequence, feat_dim: int, f0: bool = True) -> "SynthConfig":
         if len(args) != 18:
             raise ValueError(f"expected the 18-element reference config list, got {len(args)}")
         a = list(args)
@@ -56,7 +57,7 @@ class SynthConfig:
             resblock_dilation_sizes=tuple(tuple(int(d) for d in ds) for ds in a[11]),
             upsample_rates=tuple(int(u) for u in a[12]), upsample_initial_channel=int(a[13]),
             upsample_kernel_sizes=tuple(int(k) for k in a[14]), spk_embed_dim=int(a[15]),
-            gin_channels=int(a[16]), sr=int(sr), feat_dim=int(feat_dim),
+            gin_channels=int(a[16]), sr=int(sr), feat_dim=int(feat_dim), f0=bool(f0),
         )
 
     def to_positional(self) -> list:
@@ -123,6 +124,12 @@ NAMED_CONFIGS: Dict[str, SynthConfig] = {
 }
 
 
+def nono(cfg: SynthConfig) -> SynthConfig:
+    """The no-f0 variant of a configuration (`SynthesizerTrnMs{256,768}NSFsid_nono`)."""
+    from dataclasses import replace
+    return replace(cfg, f0=False)
+
+
 def state_dict_shapes(cfg: SynthConfig) -> Dict[str, Tuple[int, ...]]:
     """Key -> shape of the reference `cpt["weight"]` state_dict (enc_q removed).
 
@@ -139,7 +146,8 @@ def state_dict_shapes(cfg: SynthConfig) -> Dict[str, Tuple[int, ...]]:
     # enc_p (models.py:33-41 / 80-88)
     s["enc_p.emb_phone.weight"] = (H, cfg.feat_dim)
     s["enc_p.emb_phone.bias"] = (H,)
-    s["enc_p.emb_pitch.weight"] = (256, H)
+    if cfg.f0:
+        s["enc_p.emb_pitch.weight"] = (256, H)
     for l in range(cfg.n_layers):
         a = f"enc_p.encoder.attn_layers.{l}"
         s[f"{a}.emb_rel_k"] = (1, W, dk)
@@ -177,8 +185,9 @@ def state_dict_shapes(cfg: SynthConfig) -> Dict[str, Tuple[int, ...]]:
         s[f"{p}.post.weight"] = (half, H, 1)
         s[f"{p}.post.bias"] = (half,)
     # dec (models.py:470-540)
-    s["dec.m_source.l_linear.weight"] = (1, 1)
-    s["dec.m_source.l_linear.bias"] = (1,)
+    if cfg.f0:
+        s["dec.m_source.l_linear.weight"] = (1, 1)
+        s["dec.m_source.l_linear.bias"] = (1,)
     U0 = cfg.upsample_initial_channel
     s["dec.conv_pre.weight"] = (U0, C, 7)
     s["dec.conv_pre.bias"] = (U0,)
@@ -187,9 +196,10 @@ def state_dict_shapes(cfg: SynthConfig) -> Dict[str, Tuple[int, ...]]:
         s[f"dec.ups.{i}.bias"] = (cout,)
         s[f"dec.ups.{i}.weight_g"] = (cin, 1, 1)
         s[f"dec.ups.{i}.weight_v"] = (cin, cout, k)
-        nk, _, _ = cfg.noise_conv_geometry(i)
-        s[f"dec.noise_convs.{i}.weight"] = (cout, 1, nk)
-        s[f"dec.noise_convs.{i}.bias"] = (cout,)
+        if cfg.f0:
+            nk, _, _ = cfg.noise_conv_geometry(i)
+            s[f"dec.noise_convs.{i}.weight"] = (cout, 1, nk)
+            s[f"dec.noise_convs.{i}.bias"] = (cout,)
         for j, (k_r, ds) in enumerate(zip(cfg.resblock_kernel_sizes, cfg.resblock_dilation_sizes)):
             r = f"dec.resblocks.{i * cfg.num_kernels + j}"
             if cfg.resblock == "1":

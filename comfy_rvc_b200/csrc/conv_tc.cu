@@ -487,7 +487,7 @@ noise_add_tile_kernel(const float* __restrict__ har, const float* __restrict__ w
   unsigned char* tile = reinterpret_cast<unsigned char*>(sh + (((size_t)n_hrows * hs + 3) & ~(size_t)3));   // [TR][C] 16 bit
   if (threadIdx.x == 0) pdl_trigger();
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[k * C + i] = nb[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[k * C + i] = nb ? nb[i] : 0.f;   // k = 0, nb = null: plain conversion
   pdl_wait();                                                      // x32 comes from the transposed conv just before
   const int b = blockIdx.y;
   const float* hb = har + (long long)b * L_har;
@@ -498,10 +498,11 @@ noise_add_tile_kernel(const float* __restrict__ har, const float* __restrict__ w
     const long long t0 = tl * TR;
     __syncthreads();                                               // previous tile fully copied out; weights visible
     const long long h0 = t0 * s - pad;
-    for (int i = threadIdx.x; i < n_hrows * s; i += blockDim.x) {
-      const long long h = h0 + i;
-      sh[(i / s) * hs + (i % s)] = (h >= 0 && h < L_har) ? __ldg(hb + h) : 0.f;
-    }
+    if (k > 0)
+      for (int i = threadIdx.x; i < n_hrows * s; i += blockDim.x) {
+        const long long h = h0 + i;
+        sh[(i / s) * hs + (i % s)] = (h >= 0 && h < L_har) ? __ldg(hb + h) : 0.f;
+      }
     __syncthreads();
     // one item = 4 rows (TR/4 apart: each of the 4 planar loads is coalesced across the warp) x 4 channels: the 4 loads
     // are in flight together and every weight vector read from shared memory feeds 16 FMAs
@@ -751,7 +752,9 @@ cudaError_t launch_cl32_to_cl16(const float* x, void* y16, long long numel, floa
 cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, bool write32, int B,
                                 long long L_har, long long L, int C, int k, int s, int pad, int Lp, int padf, float slope,
                                 bool bf16, cudaStream_t st) {
-  if (C % 8 != 0 || C / 8 > 64 || ((C / 8) & (C / 8 - 1)) != 0 || s < 1 || k < 1) return cudaErrorInvalidValue;
+  if (C % 8 != 0 || C / 8 > 64 || ((C / 8) & (C / 8 - 1)) != 0 || s < 1 || k < 0 ||
+      (k > 0 && (!har || !wn || !nb)))
+    return cudaErrorInvalidValue;
   // tile rows: as many as fit beside the taps in ~100 KB (two blocks per SM), at most 128
   int TR = 128;
   auto smem_for = [&](int tr) {

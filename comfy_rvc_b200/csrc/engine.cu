@@ -355,7 +355,8 @@ int rvcb200_finalize(rvcb200_ctx* ctx) {
   T32(ctx, "cond.b", ctx->n_cond, &ok);
   T32(ctx, "enc.emb.w", (long long)f.feat_dim * H, &ok);
   T32(ctx, "enc.emb.b", H, &ok);
-  T32(ctx, "enc.emb_pitch", 256LL * H, &ok);
+  const bool f0 = f.no_f0 == 0;
+  if (f0) T32(ctx, "enc.emb_pitch", 256LL * H, &ok);
   const int nrel = 2 * f.window_size + 1;
   for (int l = 0; l < f.n_layers; ++l) {
     T32(ctx, S("enc.%d.qkv.w", l), (long long)H * 3 * H, &ok);
@@ -399,8 +400,10 @@ int rvcb200_finalize(rvcb200_ctx* ctx) {
     T32(ctx, S("dec.ups.%d.b", i), g.cout, &ok);
     int nk, ns, np;
     noise_geom(f, i, &nk, &ns, &np);
-    T32(ctx, S("dec.noise.%d.w", i), (long long)nk * g.cout, &ok);
-    T32(ctx, S("dec.noise.%d.b", i), g.cout, &ok);
+    if (f0) {
+      T32(ctx, S("dec.noise.%d.w", i), (long long)nk * g.cout, &ok);
+      T32(ctx, S("dec.noise.%d.b", i), g.cout, &ok);
+    }
     for (int j = 0; j < f.n_res_kernels; ++j) {
       const int n = i * f.n_res_kernels + j;
       for (int d = 0; d < f.n_res_dils[j]; ++d) {
@@ -418,7 +421,7 @@ int rvcb200_finalize(rvcb200_ctx* ctx) {
     }
   }
   T32(ctx, "dec.post.w", 7LL * (f.up_init_channels >> f.n_ups), &ok);
-  if (!ctx->scalars.count("dec.src.lin_w") || !ctx->scalars.count("dec.src.lin_b")) {
+  if (f0 && (!ctx->scalars.count("dec.src.lin_w") || !ctx->scalars.count("dec.src.lin_b"))) {
     if (ok) snprintf(ctx->err, sizeof(ctx->err), "missing scalar 'dec.src.lin_w/lin_b'");
     ok = false;
   }
@@ -442,8 +445,9 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
                   int64_t workspace_bytes, int32_t precision, const rvcb200_tap* taps, int32_t n_taps, void* stream) {
   if (!ctx) return RVCB200_ERR_ARG;
   if (!ctx->finalized) return fail(ctx, RVCB200_ERR_MISSING, "rvcb200_finalize() has not succeeded%s", "");
-  if (B <= 0 || T <= 0 || !phone || !phone_lengths || !pitch || !nsff0 || !sid || !noise_zp || !noise_sine || !out ||
-      !workspace)
+  const bool f0 = ctx->cfg.no_f0 == 0;
+  if (B <= 0 || T <= 0 || !phone || !phone_lengths || !sid || !noise_zp || !out || !workspace ||
+      (f0 && (!pitch || !nsff0 || !noise_sine)))
     return fail(ctx, RVCB200_ERR_ARG, "null or empty argument%s", "");
   if (precision != RVCB200_PREC_FP32 && precision != RVCB200_PREC_FP16 && precision != RVCB200_PREC_BF16)
     return fail(ctx, RVCB200_ERR_ARG, "unknown precision %s%lld", "", precision);
@@ -480,7 +484,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     d.x = phone; d.x_bstride = (long long)T * f.feat_dim; d.ldx = f.feat_dim; d.L_in = T;
     d.w = W("enc.emb.w"); d.bias = W("enc.emb.b"); d.Cin = f.feat_dim; d.Cout = H;
     d.Lj = T; d.y = pl.x; d.y_bstride = (long long)T * H; d.ldy = H;
-    d.gather = W("enc.emb_pitch"); d.gidx = pitch; d.gidx_bstride = T;
+    if (f0) { d.gather = W("enc.emb_pitch"); d.gidx = pitch; d.gidx_bstride = T; }
     d.alpha = sqrtf((float)H); d.out_slope = 0.1f; d.mask_post = 1; d.out_len = pl.len32;
     CKC(6, launch_conv_f32(d, B, st), "enc.emb");
   }
@@ -619,7 +623,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     CKC(3, launch_cl32_to_cl16(phone, pl.phone16, (long long)BT * f.feat_dim, 1.f, false, st), "phone->fp16");
     {  // x = lrelu((emb_phone(phone) + emb_pitch[pitch]) * sqrt(H)) * mask   models.py:92-100
       TcConvDesc d = gen(pl.phone16, f.feat_dim, "enc.emb.w", "enc.emb.b", H);
-      d.gather = W("enc.emb_pitch"); d.gidx = pitch; d.gidx_bstride = T;
+      if (f0) { d.gather = W("enc.emb_pitch"); d.gidx = pitch; d.gidx_bstride = T; }
       d.alpha = sqrtf((float)H); d.pre_slope = 0.1f; d.mask_post = 1; d.mask16 = 1;
       d.y32 = pl.x; d.ldy32 = H; d.y16 = pl.x16;
       TCG(6, d, "enc.emb(tc)");
@@ -725,10 +729,12 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
   }
   // ---------------- NSF source (models.py:361-411, 455-467) -----------------------------------
   const long long Lout = (long long)T * ctx->upp;
-  CKC(2, launch_sine_source(nsff0, noise_sine, pl.har, B, T, ctx->upp, f.sr, ctx->scalars["dec.src.lin_w"],
-                        ctx->scalars["dec.src.lin_b"], pl.sine_scratch, st),
-     "sine_source");
-  CK(tp.emit("har_source", pl.har, sizeof(float) * B * Lout), "tap");
+  if (f0) {
+    CKC(2, launch_sine_source(nsff0, noise_sine, pl.har, B, T, ctx->upp, f.sr, ctx->scalars["dec.src.lin_w"],
+                              ctx->scalars["dec.src.lin_b"], pl.sine_scratch, st),
+        "sine_source");
+    CK(tp.emit("har_source", pl.har, sizeof(float) * B * Lout), "tap");
+  }
 
   if (!tc) {
   // ---------------- GeneratorNSF (models.py:542-564) -------------------------------------------
@@ -763,7 +769,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       d.y = X; d.y_bstride = Ln * g.cout; d.ldy = g.cout;
       CKC(4, launch_conv_f32(d, B, st), "dec.ups");
     }
-    {
+    if (f0) {
       int nk, ns, np;
       noise_geom(f, i, &nk, &ns, &np);
       CKC(3, launch_noise_conv_add(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X, B, Lout, Ln, g.cout, nk,
@@ -891,9 +897,14 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
         int nk, ns, np;
         noise_geom(f, i, &nk, &ns, &np);
         const bool want_tap = tp.find(S("dec.ups.%d", i).c_str()) != nullptr;
-        CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, want_tap, B,
-                                   Lout, Ln, Cn, nk, ns, np, LpN, kPadF, 0.1f, false, st),
-            "dec.noise_add(pv)");
+        if (f0)
+          CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, want_tap, B,
+                                     Lout, Ln, Cn, nk, ns, np, LpN, kPadF, 0.1f, false, st),
+              "dec.noise_add(pv)");
+        else    // plain Generator (models.py:298-300): no source injection, only the fp32 planar -> fp16 stream conversion
+          CKC(3, launch_noise_add_pv(nullptr, nullptr, nullptr, X32, X16, false, B, Lout, Ln, Cn, 0, 1, 0, LpN, kPadF, 0.1f,
+                                     false, st),
+              "dec.to_stream(pv)");
       }
       if (const rvcb200_tap* t = tp.find(S("dec.ups.%d", i).c_str()))
         CK(launch_pv32_to_cl(X32, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");

@@ -250,12 +250,16 @@ class VC(FeatureExtractor):
         cfg = net_g.cfg
         dev = staged["dev"]
         if self.noise_mode == "reference":
-            nz = torch.randn(1, cfg.inter_channels, T)          # models.py:685/801
+            nz = torch.randn(1, cfg.inter_channels, T)          # models.py:685/801 (:908 for the no-f0 classes)
+            if not cfg.f0:
+                return (nz,)
             ri = torch.rand(1, 1)                               # models.py:378
             ns = torch.randn(1, T * cfg.upp, 1)                 # models.py:409
             return nz, ri, ns
         g = torch.Generator(device=dev).manual_seed(self.seed * 1000003 + i)
         nz = torch.randn(1, cfg.inter_channels, T, device=dev, generator=g)
+        if not cfg.f0:
+            return (nz,)
         ri = torch.rand(1, 1, device=dev, generator=g)
         ns = torch.randn(1, T * cfg.upp, 1, device=dev, generator=g)
         return nz, ri, ns
@@ -287,12 +291,11 @@ class VC(FeatureExtractor):
         feats = feats.contiguous()
         F_, Cf = int(feats.shape[1]), int(feats.shape[2])
         p_len = min(n_samples // self.window, 2 * F_)                                          # :83
-        if not use_f0:
-            raise NotImplementedError("the no-f0 (`_nono`) synthesizers are not built yet (SURVEY.md §8f rank 2)")
-        pitch = pitch[:, :p_len].contiguous()                                                  # :86-87
-        pitchf = pitchf[:, :p_len].contiguous()
-        if pitch.shape[1] < p_len:
-            raise ValueError(f"pitch has {pitch.shape[1]} frames, segment needs {p_len}")
+        if use_f0:
+            pitch = pitch[:, :p_len].contiguous()                                              # :86-87
+            pitchf = pitchf[:, :p_len].contiguous()
+            if pitch.shape[1] < p_len:
+                raise ValueError(f"pitch has {pitch.shape[1]} frames, segment needs {p_len}")
         phone = torch.empty(1, p_len, Cf, device=dev, dtype=torch.float32)
         use_protect = 1 if feats0 is not None else 0
         f0p = feats0.contiguous() if feats0 is not None else feats
@@ -301,11 +304,14 @@ class VC(FeatureExtractor):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.rvcb200_op_prepare_feats(                                               # :77-95 in one kernel
             C.c_void_p(feats.data_ptr()), C.c_void_p(f0p.data_ptr()), 0 if feats.dtype == torch.float32 else 1,
-            C.c_void_p(pitchf.data_ptr()), C.c_void_p(phone.data_ptr()), F_, p_len, Cf, float(protect), use_protect,
+            C.c_void_p(pitchf.data_ptr() if use_f0 else None), C.c_void_p(phone.data_ptr()), F_, p_len, Cf, float(protect),
+            use_protect,
             C.c_void_p(stream)), None, "prepare_feats")
         p_len_t = torch.full((1,), p_len, device=dev, dtype=torch.int64)                       # :96 (no H2D copy)
         kw = {"noise": noise} if noise is not None else {}
-        return net_g.infer(phone, p_len_t, pitch, pitchf, sid, **kw)[0][0, 0]                  # :97-105
+        if use_f0:
+            return net_g.infer(phone, p_len_t, pitch, pitchf, sid, **kw)[0][0, 0]              # :97-101
+        return net_g.infer(phone, p_len_t, sid, **kw)[0][0, 0]                                 # :102-105
 
     def vc(self, model, net_g, sid, audio0, pitch, pitchf, times, index, big_npy, index_rate, version, protect):
         """Same contract as the reference `VC.vc` (vc_infer_pipeline.py:25-114): numpy in, float32 numpy PCM out."""
@@ -357,8 +363,6 @@ class VC(FeatureExtractor):
             raise NotImplementedError("rms_mix_rate < 1 (change_rms, lib/model_utils.py:39, needs librosa) is outside this path")
         if resample_sr >= 16000 and tgt_sr != resample_sr:
             raise NotImplementedError("resample_sr (librosa.resample, vc_infer_pipeline.py:185-186) is outside this path")
-        if not if_f0:
-            raise NotImplementedError("the no-f0 (`_nono`) synthesizers are not built yet (SURVEY.md §8f rank 2)")
         dist, rank, world = self._dist()
         t0 = time.time()
         index, big_npy = self.load_index(file_index)
@@ -371,11 +375,15 @@ class VC(FeatureExtractor):
                                       dtype="float32")
             except Exception:  # noqa: BLE001
                 traceback.print_exc()
-        pitch, pitchf = self.get_f0(audio_pad, f0_up_key, f0_method, merge_type, filter_radius, crepe_hop_length,
-                                    f0_autotune, rmvpe_onnx, inp_f0, f0_min, f0_max)          # :155-157
-        p_len = min(pitch.shape[0], pitchf.shape[0])                                           # :158-162
-        pitch = pitch[:p_len].astype(np.int64)
-        pitchf = pitchf[:p_len].astype(np.float32)
+        pitch = pitchf = None
+        if if_f0 == 1:                                                                         # :153-162
+            pitch, pitchf = self.get_f0(audio_pad, f0_up_key, f0_method, merge_type, filter_radius, crepe_hop_length,
+                                        f0_autotune, rmvpe_onnx, inp_f0, f0_min, f0_max)
+            p_len = min(pitch.shape[0], pitchf.shape[0])
+            pitch = pitch[:p_len].astype(np.int64)
+            pitchf = pitchf[:p_len].astype(np.float32)
+        if (pitch is None) != (not getattr(getattr(net_g, "cfg", None), "f0", True)):
+            raise ValueError("if_f0 does not match the synthesizer class (f0 vs `_nono`)")
         lengths = [s.n_samples for s in segs]
         assignment = assign_segments(lengths, world)
         mine = assignment[rank]
@@ -430,8 +438,8 @@ class VC(FeatureExtractor):
                 "dev": dev,
                 "audio": audio_h.to(dev, non_blocking=True),                                   # the whole song, once
                 "sid": torch.as_tensor(sid).reshape(1).to(dev).long(),                         # :151
-                "pitch": torch.from_numpy(pitch).to(dev).unsqueeze(0),
-                "pitchf": torch.from_numpy(pitchf).to(dev).unsqueeze(0),
+                "pitch": torch.from_numpy(pitch).to(dev).unsqueeze(0) if pitch is not None else None,
+                "pitchf": torch.from_numpy(pitchf).to(dev).unsqueeze(0) if pitchf is not None else None,
             }
 
     def _convert(self, staged, model, net_g, s: Segment, T_formula: int, index, big_npy, index_rate, version, protect, noise):
@@ -439,7 +447,8 @@ class VC(FeatureExtractor):
         dev = staged["dev"]
         with torch.cuda.device(dev):
             o = self._vc_device(model, net_g, staged["sid"], staged["audio"][s.start:s.end], s.n_samples,
-                                staged["pitch"][:, s.f0_start:s.f0_end], staged["pitchf"][:, s.f0_start:s.f0_end],
+                                staged["pitch"][:, s.f0_start:s.f0_end] if staged["pitch"] is not None else None,
+                                staged["pitchf"][:, s.f0_start:s.f0_end] if staged["pitchf"] is not None else None,
                                 index, big_npy, index_rate, version, protect, noise=noise)
             if self.noise_mode == "reference" and o.shape[0] != T_formula * net_g.cfg.upp:
                 raise RuntimeError("HuBERT front end does not follow the 400/320 frame formula; reference-order noise "
@@ -477,16 +486,18 @@ class VC(FeatureExtractor):
 def get_vc(model_path, file_index=None, config=None, device=None):
     """Reference `get_vc` (vc_infer_pipeline.py:198-249) on the B200 classes: checkpoint → {vc, cpt, net_g, ...}."""
     import os
-    from .synthesizer import SynthesizerTrnMs256NSFsid, SynthesizerTrnMs768NSFsid
+    from .synthesizer import (SynthesizerTrnMs256NSFsid, SynthesizerTrnMs768NSFsid, SynthesizerTrnMs256NSFsid_nono,
+                              SynthesizerTrnMs768NSFsid_nono)
     config = config or PipelineConfig()
     cpt = torch.load(model_path, map_location="cpu")
     tgt_sr = cpt["config"][-1]
     cpt["config"][-3] = cpt["weight"]["emb_g.weight"].shape[0]       # n_spk
     if_f0 = cpt.get("f0", 1)
     version = cpt.get("version", "v1")
-    if if_f0 != 1:
-        raise NotImplementedError("the no-f0 (`_nono`) synthesizers are not built yet (SURVEY.md §8f rank 2)")
-    cls = SynthesizerTrnMs256NSFsid if version == "v1" else SynthesizerTrnMs768NSFsid
+    if if_f0 == 1:                                                     # the 4-way dispatch of vc_infer_pipeline.py:205-218
+        cls = SynthesizerTrnMs256NSFsid if version == "v1" else SynthesizerTrnMs768NSFsid
+    else:
+        cls = SynthesizerTrnMs256NSFsid_nono if version == "v1" else SynthesizerTrnMs768NSFsid_nono
     net_g = cls(*cpt["config"], is_half=config.is_half)
     del net_g.enc_q
     net_g.load_state_dict(cpt["weight"], strict=False)

@@ -39,10 +39,11 @@ class SynthesizerB200(nn.Module):
     """Common implementation; subclasses fix `feat_dim` (TextEncoder256 vs TextEncoder768)."""
 
     feat_dim = 768
+    f0 = True            # False: the `_nono` classes
 
     def __init__(self, *args, is_half: bool = False, **kwargs):
         super().__init__()
-        self.cfg = SynthConfig.from_positional(args, self.feat_dim)
+        self.cfg = SynthConfig.from_positional(args, self.feat_dim, self.f0)
         if self.cfg.hidden_channels != 192 or self.cfg.n_heads != 2 or self.cfg.inter_channels != 192:
             raise ValueError("rvcb200 kernels are built for hidden=inter=192, 2 heads (every shipped RVC config)")
         self.enc_q = nn.Identity()          # `del net_g.enc_q` (vc_infer_pipeline.py:219) must work
@@ -140,6 +141,7 @@ class SynthesizerB200(nn.Module):
         c.up_init_channels, c.gin_channels = cfg.upsample_initial_channel, cfg.gin_channels
         c.n_speakers = int(self._ref_sd["emb_g.weight"].shape[0])
         c.sr = cfg.sr
+        c.no_f0 = 0 if cfg.f0 else 1
         return c
 
     def _materialize(self):
@@ -215,13 +217,21 @@ class SynthesizerB200(nn.Module):
         return nz, ri, ns
 
     @torch.no_grad()
-    def infer(self, phone, phone_lengths, pitch, nsff0, sid, rate=None, noise=None, taps=None):
-        """Same signature/return as the reference `infer` (models.py:682-693 / :798-809).
+    def infer(self, phone, phone_lengths, *rest, rate=None, noise=None, taps=None):
+        """Same signature/return as the reference `infer`: `(phone, phone_lengths, pitch, nsff0, sid, rate=None)`
+        for the f0 classes (models.py:682-693 / :798-809), `(phone, phone_lengths, sid, rate=None)` for the `_nono`
+        classes (models.py:905-915 / :1011-1021).
 
         `noise=(noise_zp[B,192,T], rand_ini, noise_sine[B,L,1])` injects the RNG draws (parity tests);
         otherwise they are drawn with torch on the compute device in the reference's order.
         `taps` (dict name -> None) is filled with intermediate tensors (channels-last) for tests.
         """
+        n_pos = 3 if self.f0 else 1
+        if len(rest) == n_pos + 1 and rate is None:      # `rate` passed positionally, like the reference allows
+            rest, rate = rest[:n_pos], rest[n_pos]
+        if len(rest) != n_pos:
+            raise TypeError(f"infer() takes {'(phone, phone_lengths, pitch, nsff0, sid)' if self.f0 else '(phone, phone_lengths, sid)'}")
+        pitch, nsff0, sid = rest if self.f0 else (None, None, rest[0])
         if rate:
             raise NotImplementedError("rate= (tail re-synthesis) is never used by vc_infer_pipeline; not built")
         self._materialize()
@@ -235,17 +245,24 @@ class SynthesizerB200(nn.Module):
         with torch.cuda.device(dev):
             phone_d = phone.to(dev, dtype=torch.float32).contiguous()
             len_d = phone_lengths.to(dev, dtype=torch.int64).contiguous()
-            pitch_d = pitch.to(dev, dtype=torch.int64).contiguous()
-            f0_d = nsff0.to(dev, dtype=torch.float32).contiguous()
             sid_d = sid.to(dev, dtype=torch.int64).reshape(-1).contiguous()
-            if sid_d.numel() != B or pitch_d.shape != (B, T) or f0_d.shape != (B, T) or len_d.numel() != B:
+            if sid_d.numel() != B or len_d.numel() != B:
                 raise ValueError("inconsistent batch/time dimensions")
-            if noise is None:
-                nz, _ri, ns = self.draw_noise(B, T, dev)
-            else:
-                nz, _ri, ns = noise
+            if self.f0:
+                pitch_d = pitch.to(dev, dtype=torch.int64).contiguous()
+                f0_d = nsff0.to(dev, dtype=torch.float32).contiguous()
+                if pitch_d.shape != (B, T) or f0_d.shape != (B, T):
+                    raise ValueError("inconsistent batch/time dimensions")
+                if noise is None:
+                    nz, _ri, ns = self.draw_noise(B, T, dev)
+                else:
+                    nz, _ri, ns = noise
+                ns = ns.to(dev, dtype=torch.float32).reshape(B, L).contiguous()
+                pitch_p, f0_p, ns_p = pitch_d.data_ptr(), f0_d.data_ptr(), ns.data_ptr()
+            else:                                    # one RNG draw only (models.py:908)
+                nz = noise[0] if noise is not None else torch.randn(B, cfg.inter_channels, T, device=dev)
+                pitch_p = f0_p = ns_p = None
             nz = nz.to(dev, dtype=torch.float32).contiguous()
-            ns = ns.to(dev, dtype=torch.float32).reshape(B, L).contiguous()
             prec = _lib.PREC[self.precision]
             ws = self._workspace(B, T, prec)
             o = torch.empty(B, 1, L, device=dev, dtype=torch.float32)
@@ -267,8 +284,8 @@ class SynthesizerB200(nn.Module):
             stream = torch.cuda.current_stream(dev).cuda_stream
             st = lib.rvcb200_infer(
                 self._ctx, B, T, C.c_void_p(phone_d.data_ptr()), C.c_void_p(len_d.data_ptr()),
-                C.c_void_p(pitch_d.data_ptr()), C.c_void_p(f0_d.data_ptr()), C.c_void_p(sid_d.data_ptr()),
-                C.c_void_p(nz.data_ptr()), C.c_void_p(ns.data_ptr()), C.c_void_p(o.data_ptr()),
+                C.c_void_p(pitch_p), C.c_void_p(f0_p), C.c_void_p(sid_d.data_ptr()),
+                C.c_void_p(nz.data_ptr()), C.c_void_p(ns_p), C.c_void_p(o.data_ptr()),
                 C.c_void_p(stats.data_ptr()), C.c_void_p(z_p.data_ptr()), C.c_void_p(z.data_ptr()),
                 C.c_void_p(ws.data_ptr()), ws.numel(), prec, tap_arr, n_taps, C.c_void_p(stream))
             _lib.check(st, self._ctx, "infer")
@@ -305,3 +322,15 @@ class SynthesizerTrnMs256NSFsid(SynthesizerB200):
 class SynthesizerTrnMs768NSFsid(SynthesizerB200):
     """v2 models: 768-d HuBERT features (reference models.py:696-809)."""
     feat_dim = 768
+
+
+class SynthesizerTrnMs256NSFsid_nono(SynthesizerB200):
+    """v1 models trained without pitch guidance (reference models.py:812-915): `infer(phone, phone_lengths, sid)`."""
+    feat_dim = 256
+    f0 = False
+
+
+class SynthesizerTrnMs768NSFsid_nono(SynthesizerB200):
+    """v2 models trained without pitch guidance (reference models.py:918-1021)."""
+    feat_dim = 768
+    f0 = False

@@ -87,7 +87,8 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
     # ---- TextEncoder ----
     P["enc.emb.w"] = w["enc_p.emb_phone.weight"].t().contiguous()            # [C_f][H]
     P["enc.emb.b"] = w["enc_p.emb_phone.bias"].contiguous()
-    P["enc.emb_pitch"] = w["enc_p.emb_pitch.weight"].contiguous()            # [256][H]
+    if cfg.f0:
+        P["enc.emb_pitch"] = w["enc_p.emb_pitch.weight"].contiguous()        # [256][H]
     for l in range(cfg.n_layers):
         a = f"enc_p.encoder.attn_layers.{l}"
         P[f"enc.{l}.qkv.w"] = torch.cat([w[f"{a}.conv_{n}.weight"][:, :, 0].t() for n in "qkv"], dim=1).contiguous()
@@ -174,16 +175,18 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
     P["cond.w"] = torch.cat(cond_w, dim=0).contiguous()
     P["cond.b"] = torch.cat(cond_b, dim=0).contiguous()
     # ---- GeneratorNSF ----
-    S["dec.src.lin_w"] = float(w["dec.m_source.l_linear.weight"].reshape(-1)[0])
-    S["dec.src.lin_b"] = float(w["dec.m_source.l_linear.bias"].reshape(-1)[0])
+    if cfg.f0:
+        S["dec.src.lin_w"] = float(w["dec.m_source.l_linear.weight"].reshape(-1)[0])
+        S["dec.src.lin_b"] = float(w["dec.m_source.l_linear.bias"].reshape(-1)[0])
     P["dec.pre.w"] = conv_w(w["dec.conv_pre.weight"])
     P["dec.pre.b"] = w["dec.conv_pre.bias"].contiguous()
     nk = cfg.num_kernels
     for i, u in enumerate(cfg.upsample_rates):
         P[f"dec.ups.{i}.w"] = pack_conv_transpose(w[f"dec.ups.{i}.weight"], u).contiguous()
         P[f"dec.ups.{i}.b"] = w[f"dec.ups.{i}.bias"].contiguous()
-        P[f"dec.noise.{i}.w"] = w[f"dec.noise_convs.{i}.weight"][:, 0, :].t().contiguous()   # [k][C]
-        P[f"dec.noise.{i}.b"] = w[f"dec.noise_convs.{i}.bias"].contiguous()
+        if cfg.f0:
+            P[f"dec.noise.{i}.w"] = w[f"dec.noise_convs.{i}.weight"][:, 0, :].t().contiguous()   # [k][C]
+            P[f"dec.noise.{i}.b"] = w[f"dec.noise_convs.{i}.bias"].contiguous()
         for j in range(nk):
             n = i * nk + j
             for d in range(len(cfg.resblock_dilation_sizes[j])):

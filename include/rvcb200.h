@@ -75,6 +75,8 @@ typedef struct rvcb200_config {
   int32_t gin_channels;     /* 256 */
   int32_t n_speakers;       /* emb_g rows */
   int32_t sr;               /* 32000 | 40000 | 48000 */
+  int32_t no_f0;            /* 0: NSF synthesizers with pitch (models.py:573-809); 1: the `_nono` classes (models.py:812-1021):
+                             * no pitch embedding, plain `Generator` decoder (models.py:244-317) without harmonic source */
 } rvcb200_config;
 
 /* Optional copy-out of an intermediate (stage-level parity tests).  `name` is one of
@@ -112,6 +114,8 @@ int64_t rvcb200_workspace_bytes(const rvcb200_ctx* ctx, int32_t B, int32_t T, in
  * `rand_ini` draw is zeroed for the fundamental (models.py:378-381) and needs no buffer.
  * Outputs: `out` [B][T*upp] fp32 waveform; optional `stats` [B][T][2*inter] (m_p | logs_p),
  * `z_p` [B][T][inter], `z` [B][T][inter], channels-last (NULL to skip).
+ * With cfg.no_f0 (`net_g.infer(phone, phone_lengths, sid)`, models.py:905-915) pitch, nsff0 and noise_sine are
+ * ignored and may be NULL.
  * Enqueues on `stream` (a cudaStream_t) and returns without synchronising. */
 int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T,
                   const float* phone, const int64_t* phone_lengths, const int64_t* pitch,

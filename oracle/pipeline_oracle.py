@@ -103,7 +103,8 @@ def vc_segment(infer_fn, hubert, cfg, audio0: np.ndarray, pitch, pitchf, sid, c:
     feats = torch.from_numpy(audio0).float().view(1, -1)                                   # :39-47
     feats = hubert.extract_features(version=version, source=feats, padding_mask=torch.zeros_like(feats, dtype=torch.bool),
                                     output_layer=9 if version == "v1" else 12)             # :48-55
-    feats0 = feats.clone() if protect < 0.5 else None                                     # :57-58
+    use_f0 = pitch is not None and pitchf is not None
+    feats0 = feats.clone() if (protect < 0.5 and use_f0) else None                         # :57-58
     if index is not None and big_npy is not None and index_rate > 0:                       # :59-75
         npy = feats[0].numpy()
         score, ix = index.search(npy, k=1)
@@ -115,8 +116,9 @@ def vc_segment(infer_fn, hubert, cfg, audio0: np.ndarray, pitch, pitchf, sid, c:
     if feats0 is not None:
         feats0 = F.interpolate(feats0.permute(0, 2, 1), scale_factor=2).permute(0, 2, 1)   # :78-81
     p_len = min(audio0.shape[0] // c.window, feats.shape[1])                               # :83
-    pitch, pitchf = pitch[:, :p_len], pitchf[:, :p_len]                                    # :86-87
-    if protect < 0.5:                                                                      # :89-95
+    if use_f0:
+        pitch, pitchf = pitch[:, :p_len], pitchf[:, :p_len]                                # :85-87
+    if use_f0 and protect < 0.5:                                                           # :89-95
         pitchff = pitchf.clone()
         pitchff[pitchf > 0] = 1
         pitchff[pitchf < 1] = protect
@@ -134,7 +136,7 @@ def to_int16(audio_opt: np.ndarray) -> np.ndarray:
 
 def pipeline(sd_folded, cfg, hubert, audio: np.ndarray, c: Constants, f0_fn, f0_up_key=0, sid: int = 0, file_index="",
              index_rate: float = 0.0, version: str = "v2", protect: float = 0.5, f0_min=50, f0_max=1100,
-             noise_fn=None, return_parts: bool = False):
+             noise_fn=None, return_parts: bool = False, if_f0: int = 1):
     """`VC.pipeline`, vc_infer_pipeline.py:116-196 with rms_mix_rate = 1 and no resampling.
 
     `noise_fn(i, T)` returns the three RNG draws of segment i; default: the global torch CPU RNG in the
@@ -144,14 +146,19 @@ def pipeline(sd_folded, cfg, hubert, audio: np.ndarray, c: Constants, f0_fn, f0_
     opt_ts = split_points(audio, c)                                                        # :123-135
     audio_pad = np.pad(audio, (c.t_pad, c.t_pad), mode="reflect")                          # :141
     sid_t = torch.tensor(sid).unsqueeze(0).long()                                          # :151
-    coarse, f0 = f0_post(f0_fn(x=audio_pad, f0_up_key=f0_up_key, f0_min=f0_min, f0_max=f0_max), f0_up_key, f0_min, f0_max)
-    p_len = min(coarse.shape[0], f0.shape[0])                                              # :158-162
-    pitch = torch.from_numpy(coarse[:p_len].astype(np.int64)).unsqueeze(0)
-    pitchf = torch.from_numpy(f0[:p_len].astype(np.float32)).unsqueeze(0)
+    pitch = pitchf = None                                                                  # :152
+    if if_f0:                                                                              # :153-162
+        coarse, f0 = f0_post(f0_fn(x=audio_pad, f0_up_key=f0_up_key, f0_min=f0_min, f0_max=f0_max), f0_up_key, f0_min, f0_max)
+        p_len = min(coarse.shape[0], f0.shape[0])
+        pitch = torch.from_numpy(coarse[:p_len].astype(np.int64)).unsqueeze(0)
+        pitchf = torch.from_numpy(f0[:p_len].astype(np.float32)).unsqueeze(0)
 
     def infer_fn_factory(i):
         def infer_fn(feats, p_len_t, pitch_s, pitchf_s, sid_s):
             T = int(feats.shape[1])
+            if not if_f0:                                                                  # :102-105, one RNG draw (models.py:908)
+                nz = noise_fn(i, T)[0] if noise_fn is not None else torch.randn(1, cfg.inter_channels, T)
+                return rvc_oracle.infer_nono(sd_folded, cfg, feats, p_len_t, sid_s, nz)[0][0, 0].float().numpy()
             if noise_fn is not None:
                 nz, ri, ns = noise_fn(i, T)
             else:
@@ -165,8 +172,8 @@ def pipeline(sd_folded, cfg, hubert, audio: np.ndarray, c: Constants, f0_fn, f0_
     parts = []
     for i, (start, end) in enumerate(segments(audio.shape[0], opt_ts, c)):                 # :167-180
         a = audio_pad[start:end]
-        ps = pitch[:, start // c.window: (end // c.window if end is not None else None)]
-        pfs = pitchf[:, start // c.window: (end // c.window if end is not None else None)]
+        ps = pitch[:, start // c.window: (end // c.window if end is not None else None)] if if_f0 else None
+        pfs = pitchf[:, start // c.window: (end // c.window if end is not None else None)] if if_f0 else None
         out = vc_segment(infer_fn_factory(i), hubert, cfg, a, ps, pfs, sid_t, c, index, big_npy, index_rate, version, protect)
         parts.append(out[c.t_pad_tgt: -c.t_pad_tgt])
     audio_opt = np.concatenate(parts)                                                      # :182

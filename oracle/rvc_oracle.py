@@ -210,14 +210,17 @@ def _resblock(w, pfx, x, ks, dils, kind):
 
 
 def generator_nsf(w, cfg, x, har_source, g, taps: Optional[dict] = None):
+    """GeneratorNSF.forward (models.py:542-564); with har_source=None the plain `Generator.forward`
+    (models.py:293-311) of the no-f0 synthesizers: the same ladder without the noise_convs injection."""
     x = F.conv1d(x, w["dec.conv_pre.weight"], w["dec.conv_pre.bias"], padding=3)
     x = x + F.conv1d(g, w["dec.cond.weight"], w["dec.cond.bias"])
     nk = cfg.num_kernels
     for i, (u, k) in enumerate(zip(cfg.upsample_rates, cfg.upsample_kernel_sizes)):
         x = F.leaky_relu(x, LRELU_SLOPE)
         x = F.conv_transpose1d(x, w[f"dec.ups.{i}.weight"], w[f"dec.ups.{i}.bias"], stride=u, padding=(k - u) // 2)
-        kn, sn, pn = cfg.noise_conv_geometry(i)
-        x = x + F.conv1d(har_source, w[f"dec.noise_convs.{i}.weight"], w[f"dec.noise_convs.{i}.bias"], stride=sn, padding=pn)
+        if har_source is not None:
+            kn, sn, pn = cfg.noise_conv_geometry(i)
+            x = x + F.conv1d(har_source, w[f"dec.noise_convs.{i}.weight"], w[f"dec.noise_convs.{i}.bias"], stride=sn, padding=pn)
         if taps is not None:
             taps[f"dec.ups_plus_noise.{i}"] = x
         xs = None
@@ -259,4 +262,23 @@ def infer(sd_folded, cfg, phone, phone_lengths, pitch, nsff0, sid, noise_zp, ran
     if taps is not None:
         taps.update({"m_p": m_p, "logs_p": logs_p, "z_p": z_p, "z": z, "har_source": har})
     o = generator_nsf(w, cfg, z * x_mask, har, g, taps)
+    return o, x_mask, (z, z_p, m_p, logs_p)
+
+
+@torch.no_grad()
+def infer_nono(sd_folded, cfg, phone, phone_lengths, sid, noise_zp, rate=None, taps: Optional[dict] = None):
+    """`SynthesizerTrnMs{256,768}NSFsid_nono.infer` (models.py:905-915 / :1011-1021): no pitch embedding in the
+    text encoder (`enc_p(phone, None, lengths)`, models.py:50-53), plain `Generator` decoder, one RNG draw."""
+    w = sd_folded
+    g = F.embedding(sid, w["emb_g.weight"]).unsqueeze(-1)
+    m_p, logs_p, x_mask = text_encoder(w, cfg, phone.float(), None, phone_lengths)
+    z_p = (m_p + torch.exp(logs_p) * noise_zp * 0.66666) * x_mask
+    if rate:
+        head = int(z_p.shape[2] * rate)
+        z_p = z_p[:, :, -head:]
+        x_mask = x_mask[:, :, -head:]
+    z = flow_reverse(w, cfg, z_p, x_mask, g)
+    if taps is not None:
+        taps.update({"m_p": m_p, "logs_p": logs_p, "z_p": z_p, "z": z})
+    o = generator_nsf(w, cfg, z * x_mask, None, g, taps)
     return o, x_mask, (z, z_p, m_p, logs_p)

@@ -8,23 +8,48 @@ import numpy as np
 import torch
 
 from comfy_rvc_b200 import synthetic
-from comfy_rvc_b200.config import NAMED_CONFIGS
+from comfy_rvc_b200.config import NAMED_CONFIGS, nono
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-GOLDEN_CASES = ["c1_40k_v1", "c2_48k_v2", "c3_32k_v2_ragged", "c4_48k_v2_unvoiced", "c5_48k_v1_5stage", "c6_40k_v1_tiny"]
+GOLDEN_CASES = ["c1_40k_v1", "c2_48k_v2", "c3_32k_v2_ragged", "c4_48k_v2_unvoiced", "c5_48k_v1_5stage", "c6_40k_v1_tiny",
+                "c7_40k_v1_nono", "c8_48k_v2_nono_ragged"]
 
 
 def load_golden(name):
     """Returns (cfg, state_dict, inputs, noise, golden arrays) for one fixture minted by make_golden.py."""
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=True)
     cfg_name, B, T, lengths, f0v, wseed, iseed, nseed, _torch_ver = [str(x) for x in z["meta"]]
-    cfg = NAMED_CONFIGS[cfg_name]
+    cfg = NAMED_CONFIGS[cfg_name.split(":")[0]]
+    if cfg_name.endswith(":nono"):                 # the no-f0 classes (models.py:812-1021)
+        cfg = nono(cfg)
     B, T = int(B), int(T)
     lengths = ast.literal_eval(lengths)
     sd = synthetic.make_state_dict(cfg, seed=int(wseed))
     inputs = synthetic.make_inputs(cfg, B, T, seed=int(iseed), lengths=lengths, f0_variant=f0v)
     noise = synthetic.draw_noise(cfg, B, T, seed=int(nseed))
     return cfg, sd, inputs, noise, z
+
+
+def oracle_infer(cfg, w, inputs, noise, taps=None):
+    """The oracle call matching the synthesizer class: `infer` (f0) or `infer_nono` (models.py:905-915)."""
+    from oracle import rvc_oracle
+    phone, lens, pitch, pitchf, sid = inputs
+    if cfg.f0:
+        return rvc_oracle.infer(w, cfg, phone, lens, pitch, pitchf, sid, *noise, taps=taps)
+    return rvc_oracle.infer_nono(w, cfg, phone, lens, sid, noise[0], taps=taps)
+
+
+def net_infer(net, cfg, inputs, noise=None, taps=None, device="cuda"):
+    """`net.infer` with the reference's positional signature for the class (5 tensors with f0, 3 without)."""
+    phone, lens, pitch, pitchf, sid = [t.to(device) for t in inputs]
+    kw = {}
+    if noise is not None:
+        kw["noise"] = noise if cfg.f0 else noise[:1]
+    if taps is not None:
+        kw["taps"] = taps
+    if cfg.f0:
+        return net.infer(phone, lens, pitch, pitchf, sid, **kw)
+    return net.infer(phone, lens, sid, **kw)
 
 
 def int16_lsb_diff(ref_f32: np.ndarray, est_f32: np.ndarray) -> int:

@@ -26,7 +26,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from comfy_rvc_b200.config import NAMED_CONFIGS, state_dict_shapes  # noqa: E402
+from comfy_rvc_b200.config import NAMED_CONFIGS, nono, state_dict_shapes  # noqa: E402
 from comfy_rvc_b200 import synthetic  # noqa: E402
 
 CASES = [
@@ -37,6 +37,9 @@ CASES = [
     ("c4_48k_v2_unvoiced", "48k_v2", 1, 64, None, "unvoiced", 0, 3, 9),
     ("c5_48k_v1_5stage", "48k", 1, 48, None,     "contour",  0, 4, 10),
     ("c6_40k_v1_tiny", "40k", 1, 7, None,        "contour",  0, 5, 11),   # T < window+1
+    # no-f0 synthesizers (SynthesizerTrnMs{256,768}NSFsid_nono, models.py:812-1021): config name suffixed ":nono"
+    ("c7_40k_v1_nono", "40k:nono", 1, 110, None, "contour",  0, 6, 12),
+    ("c8_48k_v2_nono_ragged", "48k_v2:nono", 2, 80, [80, 57], "contour", 0, 7, 13),
 ]
 
 
@@ -49,8 +52,12 @@ def import_reference():
 
 
 def build_reference_model(ref_models, cfg, sd):
-    cls = ref_models.SynthesizerTrnMs256NSFsid if cfg.feat_dim == 256 else ref_models.SynthesizerTrnMs768NSFsid
-    net = cls(*cfg.to_positional(), is_half=False)
+    if cfg.f0:
+        cls = ref_models.SynthesizerTrnMs256NSFsid if cfg.feat_dim == 256 else ref_models.SynthesizerTrnMs768NSFsid
+        net = cls(*cfg.to_positional(), is_half=False)
+    else:
+        cls = ref_models.SynthesizerTrnMs256NSFsid_nono if cfg.feat_dim == 256 else ref_models.SynthesizerTrnMs768NSFsid_nono
+        net = cls(*cfg.to_positional())
     del net.enc_q                                   # vc_infer_pipeline.py:219
     ref_keys = {k: tuple(v.shape) for k, v in net.state_dict().items()}
     ours = state_dict_shapes(cfg)
@@ -68,7 +75,9 @@ def main():
     torch.set_num_threads(1)        # pin: 1 vs 8 threads already moves 1 LSB
     ref_models = import_reference()
     for name, cfg_name, B, T, lengths, f0v, wseed, iseed, nseed in CASES:
-        cfg = NAMED_CONFIGS[cfg_name]
+        cfg = NAMED_CONFIGS[cfg_name.split(":")[0]]
+        if cfg_name.endswith(":nono"):
+            cfg = nono(cfg)
         sd = synthetic.make_state_dict(cfg, seed=wseed)
         net = build_reference_model(ref_models, cfg, sd)
         phone, lens, pitch, pitchf, sid = synthetic.make_inputs(cfg, B, T, seed=iseed, lengths=lengths, f0_variant=f0v)
@@ -78,12 +87,15 @@ def main():
             pass
         torch.manual_seed(nseed)
         with torch.no_grad():
-            o, x_mask, (z, z_p, m_p, logs_p) = net.infer(phone, lens, pitch, pitchf, sid)
+            if cfg.f0:
+                o, x_mask, (z, z_p, m_p, logs_p) = net.infer(phone, lens, pitch, pitchf, sid)
+            else:
+                o, x_mask, (z, z_p, m_p, logs_p) = net.infer(phone, lens, sid)
         # har_source on its own, same RNG position as inside infer: replay the stream
         torch.manual_seed(nseed)
         _ = torch.randn(B, cfg.inter_channels, T)
         with torch.no_grad():
-            har, _, _ = net.dec.m_source(pitchf, net.dec.upp)
+            har = net.dec.m_source(pitchf, net.dec.upp)[0] if cfg.f0 else torch.zeros(B, T * cfg.upp, 1)
         o_np = o[:, 0].numpy()
         out = {
             "o_f32": o_np.astype(np.float32),

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     import ctypes as C
-    assert C.sizeof(_lib.RvcConfig) == 4 * (12 + 1 + 4 + 4 + 16 + 1 + 8 + 8 + 4)
+    assert C.sizeof(_lib.RvcConfig) == 4 * (12 + 1 + 4 + 4 + 16 + 1 + 8 + 8 + 4 + 1)
     assert C.sizeof(_lib.RvcTap) == 24
 
 
@@ -43,6 +43,15 @@ def test_reference_constructor_and_state_dict_contract():
         res = net.load_state_dict(sd, strict=False)
         assert not res.missing_keys
         assert net.eval().to("cuda:0").half().float() is net
+        # the no-f0 classes (models.py:812-1021): same constructor list, state_dict without pitch / source tensors
+        from comfy_rvc_b200.config import nono
+        shapes0 = state_dict_shapes(nono(cfg))
+        assert set(shapes) - set(shapes0) == ({"enc_p.emb_pitch.weight", "dec.m_source.l_linear.weight", "dec.m_source.l_linear.bias"}
+                                              | {f"dec.noise_convs.{i}.{n}" for i in range(cfg.num_upsamples) for n in ("weight", "bias")})
+        cls0 = rvc.SynthesizerTrnMs256NSFsid_nono if cfg.feat_dim == 256 else rvc.SynthesizerTrnMs768NSFsid_nono
+        net0 = cls0(*cfg.to_positional(), is_half=True)
+        del net0.enc_q
+        assert not net0.load_state_dict({k: torch.zeros(s, dtype=torch.float16) for k, s in shapes0.items()}, strict=False).missing_keys
         bad = dict(sd)
         bad.pop("dec.conv_post.weight")
         with pytest.raises(RuntimeError):

@@ -11,13 +11,16 @@ import comfy_rvc_b200 as rvc
 from comfy_rvc_b200 import synthetic
 from comfy_rvc_b200.config import NAMED_CONFIGS
 from oracle import rvc_oracle
-from tests._util import GOLDEN_CASES, int16_lsb_diff, load_golden
+from tests._util import GOLDEN_CASES, int16_lsb_diff, load_golden, net_infer, oracle_infer
 
 pytestmark = pytest.mark.gpu
 
 
 def build_net(cfg, sd, precision="fp32"):
-    cls = rvc.SynthesizerTrnMs256NSFsid if cfg.feat_dim == 256 else rvc.SynthesizerTrnMs768NSFsid
+    if cfg.f0:
+        cls = rvc.SynthesizerTrnMs256NSFsid if cfg.feat_dim == 256 else rvc.SynthesizerTrnMs768NSFsid
+    else:
+        cls = rvc.SynthesizerTrnMs256NSFsid_nono if cfg.feat_dim == 256 else rvc.SynthesizerTrnMs768NSFsid_nono
     net = cls(*cfg.to_positional(), is_half=False)
     del net.enc_q
     net.load_state_dict({k: v.half() for k, v in sd.items()}, strict=False)   # checkpoints are fp16 on disk
@@ -47,17 +50,17 @@ def test_infer_matches_golden_fp32(name):
     tap_names = ["x_enc", "stats", "z_p", "z", "har_source", "dec.pre"] + \
                 [f"dec.ups.{i}" for i in range(cfg.num_upsamples)] + [f"dec.stage.{i}" for i in range(cfg.num_upsamples)]
     taps = {n: None for n in tap_names}
-    o, x_mask, (z, z_p, m_p, logs_p) = net.infer(phone.cuda(), lens.cuda(), pitch.cuda(), pitchf.cuda(), sid.cuda(),
-                                                 noise=noise, taps=taps)
+    o, x_mask, (z, z_p, m_p, logs_p) = net_infer(net, cfg, (phone, lens, pitch, pitchf, sid), noise, taps)
     torch.cuda.synchronize()
     assert net.last_launches > 0
     # oracle with stage taps (CPU) for a readable per-stage report
     w = rvc_oracle.fold_weight_norm(sd)
     ref_taps = {}
-    rvc_oracle.infer(w, cfg, phone, lens, pitch, pitchf, sid, *noise, taps=ref_taps)
+    oracle_infer(cfg, w, (phone, lens, pitch, pitchf, sid), noise, taps=ref_taps)
     ref_taps["stats"] = torch.cat([ref_taps["m_p"], ref_taps["logs_p"]], dim=1)
     for i in range(cfg.num_upsamples):
-        ref_taps[f"dec.ups.{i}"] = ref_taps[f"dec.ups_plus_noise.{i}"]
+        if f"dec.ups_plus_noise.{i}" in ref_taps:
+            ref_taps[f"dec.ups.{i}"] = ref_taps[f"dec.ups_plus_noise.{i}"]
     names = [n for n in tap_names if n in ref_taps]
     T = phone.shape[1]
     valid_only = bool((lens < T).any())

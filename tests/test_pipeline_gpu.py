@@ -55,6 +55,34 @@ def test_pipeline_tensor_path_snr(precision, name):
     assert snr >= 45.0
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_pipeline_no_f0_classes_match_oracle(precision):
+    """`if_f0 = 0` (vc_infer_pipeline.py:152-153, :102-105): the `_nono` synthesizers through the whole song-level driver,
+    against the pipeline oracle fed the same global RNG stream."""
+    from comfy_rvc_b200.config import nono
+    case = load_pipeline_golden("p1_40k_v1_4seg")
+    cfg = nono(case["cfg"])
+    sd = synthetic.make_state_dict(cfg, seed=3)
+    net = build_net(cfg, sd, precision)
+    vc = pl.VC(cfg.sr, pl.PipelineConfig(*case["tiers"], is_half=False, device="cuda:0"), noise="reference")
+    torch.manual_seed(17)
+    out = vc.pipeline(case["hubert"], net, 0, case["audio"].copy(), [0, 0, 0], 0, "synthetic", "median", "", 0.0, 0, 3, cfg.sr,
+                      0, 1.0, case["version"], 0.33, 160, False, False, None, 50, 1100)
+    torch.manual_seed(17)
+    c = pipeline_oracle.Constants(*case["tiers"], tgt_sr=cfg.sr)
+    want = pipeline_oracle.pipeline(rvc_oracle.fold_weight_norm(sd), cfg, case["hubert"], case["audio"].copy(), c, None,
+                                    version=case["version"], protect=0.33, if_f0=0)
+    assert out.dtype == np.int16 and out.shape == want.shape
+    if precision == "fp32":
+        d = np.abs(out.astype(np.int32) - want.astype(np.int32)).max()
+        print(f"no-f0 pipeline: int16 max diff {d} LSB over {len(vc.last_plan['segments'])} segments")
+        assert d <= 1
+    else:
+        snr = synthetic.snr_db(want.astype(np.float64), out.astype(np.float64))
+        print(f"no-f0 pipeline {precision}: song SNR {snr:.1f} dB")
+        assert snr >= 45.0
+
+
 def test_device_noise_is_sharding_independent_and_seeded():
     case = load_pipeline_golden("p1_40k_v1_4seg")
     a, _, _ = run_product(case, noise="device")

@@ -242,14 +242,15 @@ def test_attention_tc(T, lens):
 
 
 @pytest.mark.parametrize("precision,min_snr", [("fp16", 45.0), ("bf16", 45.0)])
-@pytest.mark.parametrize("name", ["c2_48k_v2", "c1_40k_v1", "c3_32k_v2_ragged", "c5_48k_v1_5stage"])
+@pytest.mark.parametrize("name", ["c2_48k_v2", "c1_40k_v1", "c3_32k_v2_ragged", "c5_48k_v1_5stage", "c7_40k_v1_nono",
+                                  "c8_48k_v2_nono_ragged"])
 def test_infer_tensor_core_path_snr(name, precision, min_snr):
     from tests.test_parity_gpu import build_net
+    from tests._util import net_infer
     cfg, sd, (phone, lens, pitch_, pitchf, sid), noise, gold = load_golden(name)
     net = build_net(cfg, sd, precision)
     taps = {n: None for n in ["x_enc", "stats", "z_p", "z"] + [f"dec.stage.{i}" for i in range(cfg.num_upsamples)]}
-    o, _, (z, z_p, m_p, logs_p) = net.infer(phone.cuda(), lens.cuda(), pitch_.cuda(), pitchf.cuda(), sid.cuda(),
-                                            noise=noise, taps=taps)
+    o, _, (z, z_p, m_p, logs_p) = net_infer(net, cfg, (phone, lens, pitch_, pitchf, sid), noise, taps)
     torch.cuda.synchronize()
     for key, got in (("m_p", m_p), ("logs_p", logs_p), ("z_p", z_p), ("z", z)):
         ref = gold[key]
