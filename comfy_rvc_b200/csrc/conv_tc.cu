@@ -159,7 +159,8 @@ __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t
 
 template <bool GENERIC>
 __global__ void __launch_bounds__(kThreadsTC, 1)
-conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW) {
+conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmY) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
@@ -183,6 +184,8 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   uint64_t* acc_full = b_empty + NB;     // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  // 16-bit output staging (tma_out): [8 warps][2 slots][32 rows x 64 B], SWIZZLE_64B
+  unsigned char* sE = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
 
   const int n_mt = (p.Lj + BM - 1) / BM;
   const int n_nt = p.Cout_total / p.N;
@@ -368,6 +371,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
     const long long Lout = (long long)p.Lj * p.out_stride;
     const bool simple = n_nt == 1 && p.G == 1;      // resblock convs: tile -> (batch, m-tile) with one division
     const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(eg * p.N);
+    uint32_t ocnt = 0;                              // staged output boxes so far (tma_out)
     for (int t = eg; t < my_tiles; t += 2) {
       int mt, nt = 0, g = 0, b = 0;
       const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
@@ -397,18 +401,43 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
         const unsigned char* r16row =
             p.res16 ? reinterpret_cast<const unsigned char*>(p.res16) + ((size_t)b * Lout + orow) * p.Cout_total * 2 : nullptr;
-        if (p.N % 32 == 0) {
+        const float* har_b = p.noise_har ? p.noise_har + (long long)b * p.noise_L : nullptr;
+        const long long h0 = orow * p.noise_s - p.noise_pad;
+        if (p.tma_out) {
+          // the thread = row mapping makes a direct 16-bit store 32 L2 requests per instruction (phase-interleaved rows
+          // on top): stage [32 rows][32 channels] boxes (SWIZZLE_64B) and let TMA write them; the tensor map views the
+          // output as [B][Lj][G][C], so a box is one phase of 32 consecutive input rows
+          unsigned char* my_stage = sE + (size_t)(warp - 2) * (2 * 2048);
+          const uint32_t sw_x = ((uint32_t)lane >> 1) & 3u;
+          for (int c0 = 0; c0 < p.N; c0 += 32) {
+            unsigned char* box = my_stage + (ocnt & 1u) * 2048;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+            epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row,
+                               har_b, h0, box + lane * 64, sw_x);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmY, box, nt * p.N + c0, g, mt * BM + qd * 32, b);
+              bulk_commit();
+            }
+            ++ocnt;
+          }
+        } else if (p.N % 32 == 0) {
           for (int c0 = 0; c0 < p.N; c0 += 32)
-            epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row);
+            epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row,
+                               har_b, h0);
         } else {
           for (int c0 = 0; c0 < p.N; c0 += 16)
-            epilogue_chunk<16>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row);
+            epilogue_chunk<16>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row,
+                               har_b, h0);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[eg])) : "memory");
     }
+    if (p.tma_out && lane == 0) bulk_wait_all();    // staged stores complete before the CTA's smem goes away
   }
   // ------------------------------------ teardown -------------------------------------------------
   tc_fence_before();
@@ -418,12 +447,15 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   }
 }
 
+constexpr size_t kStageBytes = 8 * 2 * 2048 + 1024;   // tma_out staging (+ alignment slack)
+
 size_t tc_smem_bytes(const TcConvDesc& d) {
   const int halo = (d.ntaps - 1) * d.dil;
   const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
   const size_t a = (((size_t)R * 128) + 1023) & ~(size_t)1023;
   const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
-  return 1024 + d.na_stages * a + d.nb_stages * bb + 8 * (2 * d.na_stages + 2 * d.nb_stages + 4) + 16 + 128;
+  return 1024 + d.na_stages * a + d.nb_stages * bb + 8 * (2 * d.na_stages + 2 * d.nb_stages + 4) + 16 + 128 +
+         (d.tma_out ? kStageBytes : 0);
 }
 
 // ---- driver entry point for tensor-map encoding (no link-time dependency on libcuda) --------------
@@ -658,7 +690,8 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   TcConvDesc d = d_in;
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.Cin % 8 != 0 || d.Cout_total % d.N != 0 || d.G < 1 || d.G > 16 ||
       d.Lj <= 0 || d.L_in <= 0 || (d.ntaps - 1) * d.dil > 120 || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
-      d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)))
+      d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)) ||
+      (d.noise_har && (d.generic || !d.noise_w || !d.noise_b || d.noise_k < 1 || d.noise_s < 1)))
     return cudaErrorInvalidValue;
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return cudaErrorNotSupported;
@@ -676,7 +709,9 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
     const size_t a = (((size_t)R * 128) + 1023) & ~(size_t)1023;
     const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
-    const size_t budget = 208 * 1024;
+    // lean epilogue with a 16-bit output in whole 32-column chunks: staged + TMA-stored (see the kernel)
+    d.tma_out = (!d.generic && d.y16 && d.N % 32 == 0) ? 1 : 0;
+    const size_t budget = 208 * 1024 - (d.tma_out ? kStageBytes : 0);
     const int nw = nkb * d.ntaps;
     const int na_max = d.a_mode != 1 ? 6 : 10;
     d.b_stationary = 0;
@@ -695,7 +730,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
 
   // tensor maps: activations (C, L_in, B) box (64, R, 1); weights (64, rows) box (64, N); SWIZZLE_128B
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmY;
   const CUtensorMapDataType dt = d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
     const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
@@ -715,6 +750,18 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
+  tmY = tmA;
+  if (d.tma_out) {   // output viewed as [B][Lj][G][Cout_total] 16-bit; box = 32 channels x 1 phase x 32 rows
+    cuuint64_t odims[4] = {(cuuint64_t)d.Cout_total, (cuuint64_t)d.out_stride, (cuuint64_t)d.Lj, (cuuint64_t)B};
+    cuuint64_t ostr[3] = {(cuuint64_t)d.Cout_total * 2, (cuuint64_t)d.Cout_total * 2 * d.out_stride,
+                          (cuuint64_t)d.Cout_total * 2 * d.out_stride * (cuuint64_t)d.Lj};
+    cuuint32_t obox[4] = {32, 1, 32, 1};
+    cuuint32_t oes[4] = {1, 1, 1, 1};
+    if (enc(&tmY, d.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d.y16, odims, ostr, obox, oes,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
   static size_t cfgd = 0;
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -729,8 +776,8 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     cfgd = smem;
   }
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
-  cudaError_t le = d.generic ? launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW)
-                             : launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW);
+  cudaError_t le = d.generic ? launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW, tmY)
+                             : launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW, tmY);
   launch_counter().n++;
   return le != cudaSuccess ? le : cudaGetLastError();
 }

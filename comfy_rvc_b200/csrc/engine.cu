@@ -882,27 +882,42 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       const int LpN = pv_pitch_rows(Ln);
       const bool last_stage = i == f.n_ups - 1;
       if (last_stage) CKC(3, launch_zero_pads(ACC32, (long long)B * (Cn / 8), LpN, kPadF, Ln, st), "zero_pads");
+      int nk, ns, np;
+      noise_geom(f, i, &nk, &ns, &np);
+      const bool want_tap = tp.find(S("dec.ups.%d", i).c_str()) != nullptr;
+      // Source injection fused into the transposed conv's epilogue when its kernel is short (every stage but the first:
+      // k = 2 * prod(later rates) <= 16): the stage's first stream tensor is written directly, the fp32 planar
+      // intermediate (4 B/elem written + read) and one launch disappear.  Kept apart for long kernels (k = 80 on the
+      // first, smallest stage: 2560 FMAs per row chunk would sit on the epilogue warps) and when a test taps x.
+      static const int fuse_max_k = [] { const char* e = getenv("RVCB200_FUSE_NOISE_K"); return e ? atoi(e) : 16; }();
+      const bool fuse = !want_tap && (!f0 || nk <= fuse_max_k);
       {  // x = ups[i](lrelu(x)) as g.u phase groups (input already holds lrelu(x) in 16 bit)
         TcConvDesc d = tc_base();
         d.x16 = IN16; d.L_in = (int)Lc; d.w16 = W16h(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i));
         d.Cin = Cc; d.ntaps = g.ntaps; d.G = g.u;
         for (int p = 0; p < g.u; ++p) d.g_off[p] = g.g_off[p];
         d.N = Cn < 256 ? Cn : 256; d.Cout_total = Cn; d.tmem_cols = tmem_cols_for(d.N);
-        d.Lj = (int)Lc; d.out_stride = g.u; d.Lp_out = LpN; d.y32 = X32;
+        d.Lj = (int)Lc; d.out_stride = g.u; d.Lp_out = LpN;
+        if (fuse) {
+          d.y16 = X16; d.out_slope = 0.1f;
+          if (f0) {
+            d.noise_har = pl.har; d.noise_w = W(S("dec.noise.%d.w", i)); d.noise_b = W(S("dec.noise.%d.b", i));
+            d.noise_k = nk; d.noise_s = ns; d.noise_pad = np; d.noise_L = Lout;
+          }
+        } else {
+          d.y32 = X32;
+        }
         if (!ok) return RVCB200_ERR_MISSING;
         d.in_bf16 = 0; d.out_bf16 = 0;
         CKC(4, launch_conv_tc(d, B, st), "dec.ups(tc)");
       }
-      {
-        int nk, ns, np;
-        noise_geom(f, i, &nk, &ns, &np);
-        const bool want_tap = tp.find(S("dec.ups.%d", i).c_str()) != nullptr;
+      if (!fuse) {
         if (f0)
           CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, want_tap, B,
                                      Lout, Ln, Cn, nk, ns, np, LpN, kPadF, 0.1f, false, st),
               "dec.noise_add(pv)");
         else    // plain Generator (models.py:298-300): no source injection, only the fp32 planar -> fp16 stream conversion
-          CKC(3, launch_noise_add_pv(nullptr, nullptr, nullptr, X32, X16, false, B, Lout, Ln, Cn, 0, 1, 0, LpN, kPadF, 0.1f,
+          CKC(3, launch_noise_add_pv(nullptr, nullptr, nullptr, X32, X16, want_tap, B, Lout, Ln, Cn, 0, 1, 0, LpN, kPadF, 0.1f,
                                      false, st),
               "dec.to_stream(pv)");
       }

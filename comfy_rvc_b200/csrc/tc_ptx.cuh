@@ -125,6 +125,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -147,7 +151,8 @@ template <int CH>
 __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t taddr, bool row_ok, int co, size_t pitch_o,
                                                size_t orow16, unsigned char* y32, unsigned char* y16row,
                                                const unsigned char* r32, const float* cond,
-                                               const unsigned char* r16row = nullptr) {
+                                               const unsigned char* r16row = nullptr, const float* har_b = nullptr,
+                                               long long h0 = 0, unsigned char* stage_row = nullptr, uint32_t sw_x = 0) {
   uint32_t r[CH];
   if (CH == 32) {
     asm volatile(
@@ -206,6 +211,21 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t tad
 #pragma unroll
     for (int i = 0; i < CH; ++i) v[i] += __ldg(cond + co + i);
   }
+  if (har_b) {   // source injection: + noise_conv(har)[row][co..]; weights are warp-uniform (broadcast loads)
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] += __ldg(p.noise_b + co + i);
+    for (int kk = 0; kk < p.noise_k; ++kk) {
+      const long long h = h0 + kk;
+      const float hv = (h >= 0 && h < p.noise_L) ? __ldg(har_b + h) : 0.f;
+      const float4* wq = reinterpret_cast<const float4*>(p.noise_w + (size_t)kk * p.Cout_total + co);
+#pragma unroll
+      for (int k4 = 0; k4 < CH / 4; ++k4) {
+        const float4 w4 = __ldg(wq + k4);
+        v[k4 * 4 + 0] = fmaf(hv, w4.x, v[k4 * 4 + 0]); v[k4 * 4 + 1] = fmaf(hv, w4.y, v[k4 * 4 + 1]);
+        v[k4 * 4 + 2] = fmaf(hv, w4.z, v[k4 * 4 + 2]); v[k4 * 4 + 3] = fmaf(hv, w4.w, v[k4 * 4 + 3]);
+      }
+    }
+  }
   if (r32) {
 #pragma unroll
     for (int k4 = 0; k4 < CH / 4; ++k4) {
@@ -250,7 +270,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t tad
       o.y = pack2(obf, lrelu(v[k8 * 8 + 2], p.out_slope), lrelu(v[k8 * 8 + 3], p.out_slope));
       o.z = pack2(obf, lrelu(v[k8 * 8 + 4], p.out_slope), lrelu(v[k8 * 8 + 5], p.out_slope));
       o.w = pack2(obf, lrelu(v[k8 * 8 + 6], p.out_slope), lrelu(v[k8 * 8 + 7], p.out_slope));
-      *reinterpret_cast<uint4*>(y16row + (size_t)(co + k8 * 8) * 2) = o;
+      if (stage_row)   // this lane's row of a SWIZZLE_64B staging box (the caller stores the box with TMA)
+        *reinterpret_cast<uint4*>(stage_row + ((((uint32_t)k8) ^ sw_x) << 4)) = o;
+      else
+        *reinterpret_cast<uint4*>(y16row + (size_t)(co + k8 * 8) * 2) = o;
     }
   }
 }

@@ -268,3 +268,20 @@ def test_infer_tensor_core_path_snr(name, precision, min_snr):
         print(f"  {name} {precision} item {b}: SNR {snr:.1f} dB vs reference fp32")
         worst = min(worst, snr)
     assert worst >= min_snr
+
+
+@pytest.mark.parametrize("name", ["c2_48k_v2", "c5_48k_v1_5stage", "c8_48k_v2_nono_ragged"])
+def test_fused_source_injection_equals_separate_kernel(name):
+    """Stages whose noise_conv kernel is short get it fused into the transposed conv's epilogue (engine.cu); tapping
+    `dec.ups.i` forces the separate fp32-planar + noise_add path.  Same arithmetic up to fp32 summation order."""
+    from tests.test_parity_gpu import build_net
+    from tests._util import net_infer
+    cfg, sd, inputs, noise, gold = load_golden(name)
+    net = build_net(cfg, sd, "fp16")
+    fused = net_infer(net, cfg, inputs, noise)[0]
+    taps = {f"dec.ups.{i}": None for i in range(cfg.num_upsamples)}
+    separate = net_infer(net, cfg, inputs, noise, taps)[0]
+    torch.cuda.synchronize()
+    snr = synthetic.snr_db(separate.cpu().numpy(), fused.cpu().numpy())
+    print(f"{name}: fused vs separate source injection: {snr:.1f} dB")
+    assert snr >= 65.0
