@@ -68,8 +68,6 @@ class TcConvDesc(C.Structure):
         ("res_mode", C.c_int32), ("mask_pre", C.c_int32), ("mask_post", C.c_int32), ("mask16", C.c_int32),
         ("out_len", C.c_void_p), ("dbg_alt", C.c_int32),
         ("res16", C.c_void_p), ("res_neg_scale", C.c_float), ("a_fp16", C.c_int32), ("acc_f16", C.c_int32),
-        ("noise_har", C.c_void_p), ("noise_w", C.c_void_p), ("noise_b", C.c_void_p),
-        ("noise_k", C.c_int32), ("noise_s", C.c_int32), ("noise_pad", C.c_int32), ("noise_L", C.c_int64),
         ("tma_out", C.c_int32),
     ]
 

@@ -401,8 +401,6 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
         const unsigned char* r16row =
             p.res16 ? reinterpret_cast<const unsigned char*>(p.res16) + ((size_t)b * Lout + orow) * p.Cout_total * 2 : nullptr;
-        const float* har_b = p.noise_har ? p.noise_har + (long long)b * p.noise_L : nullptr;
-        const long long h0 = orow * p.noise_s - p.noise_pad;
         if (p.tma_out) {
           // the thread = row mapping makes a direct 16-bit store 32 L2 requests per instruction (phase-interleaved rows
           // on top): stage [32 rows][32 channels] boxes (SWIZZLE_64B) and let TMA write them; the tensor map views the
@@ -414,7 +412,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
             if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
             epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row,
-                               har_b, h0, box + lane * 64, sw_x);
+                               box + lane * 64, sw_x);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -425,12 +423,10 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           }
         } else if (p.N % 32 == 0) {
           for (int c0 = 0; c0 < p.N; c0 += 32)
-            epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row,
-                               har_b, h0);
+            epilogue_chunk<32>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row);
         } else {
           for (int c0 = 0; c0 < p.N; c0 += 16)
-            epilogue_chunk<16>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row,
-                               har_b, h0);
+            epilogue_chunk<16>(p, tbase + (uint32_t)c0, row_ok, nt * p.N + c0, pitch_o, orow16, y32, y16row, r32, cond, r16row);
         }
       }
       tc_fence_before();
@@ -500,6 +496,12 @@ __global__ void cl32_to_cl16_kernel(const float* __restrict__ x, unsigned char* 
     o.w = pack2(BF16, lrelu(c.z, slope), lrelu(c.w, slope));
     *reinterpret_cast<uint4*>(y16 + idx * 16) = o;
   }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& w, float* f) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 
 // x = x32 (planar-vector fp32, the transposed conv's output) + noise_conv(har);  x16 (channels-last 16 bit) =
@@ -585,6 +587,83 @@ noise_add_tile_kernel(const float* __restrict__ har, const float* __restrict__ w
   }
 }
 
+// In-place source injection on the 16-bit stream (models.py:552-553 + the lrelu of modules.py:297):
+//   x16[b][t][c] <- cvt( lrelu( x16[b][t][c] + nb[c] + sum_k har[b][t*s - pad + k] * wn[k][c] ) )
+// x16 arrives as the transposed conv's RAW fp16 output (out_slope 1) and leaves as the stage's first stream tensor.
+// Both sides are channels-last, so a thread owns one 16-byte piece (8 channels) of a row and every warp access is
+// contiguous; 2 B read + 2 B written per element.  Tiles of TR rows per block; taps, bias and the harmonic-source
+// segment of the tile sit in shared memory; one item = 4 rows (TR/4 apart) x 8 channels so that the 4 loads are in
+// flight together and every weight vector feeds 32 FMAs.
+__global__ void __launch_bounds__(256)
+noise_add16_kernel(const float* __restrict__ har, const float* __restrict__ wn, const float* __restrict__ nb,
+                   unsigned char* __restrict__ x16, long long L_har, long long L, int C, int k, int s, int pad, float slope,
+                   int TR) {
+  extern __shared__ __align__(16) unsigned char nsm[];
+  const int hs = s + 1;
+  const int n_hrows = TR + (k + s - 1) / s;
+  float* sw = reinterpret_cast<float*>(nsm);                       // [k][C] + [C]
+  float* sh = sw + (size_t)k * C + C;                              // [n_hrows][hs]
+  if (threadIdx.x == 0) pdl_trigger();
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[k * C + i] = nb[i];
+  pdl_wait();
+  const int b = blockIdx.y;
+  const float* hb = har + (long long)b * L_har;
+  const int pieces = C / 8, RQ = TR / 4;
+  const long long n_tiles = (L + TR - 1) / TR;
+  for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const long long t0 = tl * TR;
+    __syncthreads();
+    const long long h0 = t0 * s - pad;
+    for (int i = threadIdx.x; i < n_hrows * s; i += blockDim.x) {
+      const long long h = h0 + i;
+      sh[(i / s) * hs + (i % s)] = (h >= 0 && h < L_har) ? __ldg(hb + h) : 0.f;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < RQ * pieces; idx += blockDim.x) {
+      const int pc = idx % pieces, rq = idx / pieces;
+      uint4* px0 = reinterpret_cast<uint4*>(x16 + (((long long)b * L + t0 + rq) * C + pc * 8) * 2);
+      const long long rstep = (long long)RQ * pieces;              // uint4 elements between the item's rows
+      uint4 xv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] = (t0 + rq + j * RQ < L) ? px0[j * rstep] : make_uint4(0, 0, 0, 0);
+      float a[4][8];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(sw + k * C + pc * 8), b1 = *reinterpret_cast<const float4*>(sw + k * C + pc * 8 + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          a[j][0] = b0.x; a[j][1] = b0.y; a[j][2] = b0.z; a[j][3] = b0.w; a[j][4] = b1.x; a[j][5] = b1.y; a[j][6] = b1.z; a[j][7] = b1.w;
+        }
+      }
+      const float* hp = sh + rq * hs;
+      const int hstep = RQ * hs;
+      for (int kk = 0, j = 0; kk < k; ++kk) {
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + kk * C + pc * 8), w1 = *reinterpret_cast<const float4*>(sw + kk * C + pc * 8 + 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float hv = hp[q * hstep + j];
+          a[q][0] = fmaf(hv, w0.x, a[q][0]); a[q][1] = fmaf(hv, w0.y, a[q][1]); a[q][2] = fmaf(hv, w0.z, a[q][2]);
+          a[q][3] = fmaf(hv, w0.w, a[q][3]); a[q][4] = fmaf(hv, w1.x, a[q][4]); a[q][5] = fmaf(hv, w1.y, a[q][5]);
+          a[q][6] = fmaf(hv, w1.z, a[q][6]); a[q][7] = fmaf(hv, w1.w, a[q][7]);
+        }
+        if (++j == s) { j = 0; hp += hs; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (t0 + rq + q * RQ >= L) continue;
+        float f[8];
+        unpack8(xv[q], f);
+        uint4 o;
+        o.x = pack2(false, lrelu(f[0] + a[q][0], slope), lrelu(f[1] + a[q][1], slope));
+        o.y = pack2(false, lrelu(f[2] + a[q][2], slope), lrelu(f[3] + a[q][3], slope));
+        o.z = pack2(false, lrelu(f[4] + a[q][4], slope), lrelu(f[5] + a[q][5], slope));
+        o.w = pack2(false, lrelu(f[6] + a[q][6], slope), lrelu(f[7] + a[q][7], slope));
+        px0[q * rstep] = o;
+      }
+    }
+  }
+}
+
 __global__ void conv_post_pv_kernel(const unsigned char* __restrict__ x32, const float* __restrict__ w, float* __restrict__ out,
                                     long long L, int C, int k, int Lp, int padf, float slope) {
   // out[b][t] = tanh(sum_{kk,c} lrelu(x[c][t+kk-pad]) * w[kk][c]);  x is PV32 with zero pads
@@ -611,11 +690,6 @@ __global__ void conv_post_pv_kernel(const unsigned char* __restrict__ x32, const
   }
 }
 
-__device__ __forceinline__ void unpack8(const uint4& w, float* f) {
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
-  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
 
 // out[b][t] = tanh(sum_{kk,c} lrelu(x[c][t+kk-pad]) * w[kk][c]);  x is planar-vector fp16 [B][C/8][Lp][8] with zero pads.
 // One thread per output sample; each plane row (16 B) is loaded once and feeds the k outputs it contributes to through
@@ -690,8 +764,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   TcConvDesc d = d_in;
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.Cin % 8 != 0 || d.Cout_total % d.N != 0 || d.G < 1 || d.G > 16 ||
       d.Lj <= 0 || d.L_in <= 0 || (d.ntaps - 1) * d.dil > 120 || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
-      d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)) ||
-      (d.noise_har && (d.generic || !d.noise_w || !d.noise_b || d.noise_k < 1 || d.noise_s < 1)))
+      d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)))
     return cudaErrorInvalidValue;
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return cudaErrorNotSupported;
@@ -822,6 +895,28 @@ cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* 
   cudaError_t le = launch_pdl(noise_add_tile_kernel, grid, dim3(256), smem, st, har, wn, nb, reinterpret_cast<unsigned char*>(x32),
                               reinterpret_cast<unsigned char*>(x16), write32 ? 1 : 0, L_har, L, C, k, s, pad, Lp, padf, slope, bf16,
                               TR);
+  launch_counter().n++;
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+cudaError_t launch_noise_add16(const float* har, const float* wn, const float* nb, void* x16, int B, long long L_har,
+                               long long L, int C, int k, int s, int pad, float slope, cudaStream_t st) {
+  if (C % 8 != 0 || s < 1 || k < 1 || !har || !wn || !nb || !x16) return cudaErrorInvalidValue;
+  int TR = 128;
+  auto smem_for = [&](int tr) { return sizeof(float) * ((size_t)k * C + C + (size_t)(tr + (k + s - 1) / s) * (s + 1)); };
+  while (TR > 8 && smem_for(TR) > 100 * 1024) TR >>= 1;
+  const size_t smem = smem_for(TR);
+  static size_t cfgd = 48 * 1024;
+  if (smem > cfgd) {
+    cudaError_t e = cudaFuncSetAttribute(noise_add16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cfgd = smem;
+  }
+  const long long n_tiles = (L + TR - 1) / TR;
+  const long long per = smem > 56 * 1024 ? 2 : 8;
+  dim3 grid((unsigned)(n_tiles < 148 * per ? n_tiles : 148 * per), B);
+  cudaError_t le = launch_pdl(noise_add16_kernel, grid, dim3(256), smem, st, har, wn, nb, reinterpret_cast<unsigned char*>(x16), L_har,
+                              L, C, k, s, pad, slope, TR);
   launch_counter().n++;
   return le != cudaSuccess ? le : cudaGetLastError();
 }

@@ -22,6 +22,9 @@ cudaError_t launch_cl32_to_cl16(const float* x, void* y16, long long numel, floa
 cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* nb, void* x32, void* x16, bool write32, int B,
                                 long long L_har, long long L, int C, int k, int s, int pad, int Lp, int padf, float slope,
                                 bool bf16, cudaStream_t st);
+// in place on the 16-bit stream: x16 <- lrelu(x16 + noise_conv(har)), x16 holding the transposed conv's raw fp16 output
+cudaError_t launch_noise_add16(const float* har, const float* wn, const float* nb, void* x16, int B, long long L_har,
+                               long long L, int C, int k, int s, int pad, float slope, cudaStream_t st);
 cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int B, long long L, int C, int k, int Lp,
                                 int padf, float slope, cudaStream_t st);
 // same, x planar-vector fp16 [B][C/8][Lp][8] (k = 7)

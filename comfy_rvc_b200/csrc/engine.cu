@@ -113,6 +113,13 @@ UpGeom up_geom(const rvcb200_config& cfg, int i) {
   return g;
 }
 
+// Stage i's transposed conv as one ordinary 3-tap convolution C_in -> u*C_out = C_in on the specialised resblock kernel
+// (weights.py ups_is_dense / pack_conv_transpose_dense): all phases side by side in N, output rows contiguous.
+bool ups_dense(const rvcb200_config& cfg, int i) {
+  const int u = cfg.up_rates[i], k = cfg.up_kernels[i], cin = cfg.up_init_channels >> i;
+  return u == 2 && k == 2 * u && (cin == 32 || cin == 64 || cin == 128 || cin == 256);
+}
+
 void noise_geom(const rvcb200_config& cfg, int i, int* k, int* s, int* pad) {
   if (i + 1 < cfg.n_ups) {
     int st = 1;
@@ -885,41 +892,49 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       int nk, ns, np;
       noise_geom(f, i, &nk, &ns, &np);
       const bool want_tap = tp.find(S("dec.ups.%d", i).c_str()) != nullptr;
-      // Source injection fused into the transposed conv's epilogue when its kernel is short (every stage but the first:
-      // k = 2 * prod(later rates) <= 16): the stage's first stream tensor is written directly, the fp32 planar
-      // intermediate (4 B/elem written + read) and one launch disappear.  Kept apart for long kernels (k = 80 on the
-      // first, smallest stage: 2560 FMAs per row chunk would sit on the epilogue warps) and when a test taps x.
-      static const int fuse_max_k = [] { const char* e = getenv("RVCB200_FUSE_NOISE_K"); return e ? atoi(e) : 16; }();
-      const bool fuse = !want_tap && (!f0 || nk <= fuse_max_k);
-      {  // x = ups[i](lrelu(x)) as g.u phase groups (input already holds lrelu(x) in 16 bit)
+      // x = ups[i](lrelu(x)) [+ noise_convs[i](har)]   (models.py:550-553; the input already holds lrelu(x) in 16 bit).
+      // Default: the transposed conv writes its RAW result as fp16 straight into the stream buffer (2 B/elem) and the
+      // source injection runs in place on it (2 + 2 B/elem) -- 6 B/elem per stage instead of the 10 of an fp32 planar
+      // intermediate.  Stages with stride 2 run as ONE dense 3-tap convolution on the resblock kernel (ups_dense);
+      // the others as phase groups on the generic kernel.  (Injecting the source inside the conv epilogue was measured
+      // slower: 2-8 taps x 32 channels of FMAs per row chunk on the 8 epilogue warps, profiles/r1_ups_modes.jsonl.)
+      // When a test taps x, the fp32 planar path of the first version is used.
+      static const int dense_ok = [] { const char* e = getenv("RVCB200_UPS_DENSE"); return e ? atoi(e) : 1; }();
+      const float first_slope = f0 ? 1.f : 0.1f;      // with f0 the lrelu is applied by the injection kernel
+      if (!want_tap && dense_ok && ups_dense(f, i)) {
+        TcConvDesc d = tc_base();
+        d.x16 = IN16; d.L_in = (int)Lc; d.w16 = W16h(S("dec.ups.%d.w3", i)); d.bias = W(S("dec.ups.%d.b3", i));
+        d.Cin = Cc; d.ntaps = 3; d.dil = 1; d.g_off[0] = -1;
+        d.N = Cc; d.Cout_total = Cc; d.tmem_cols = tmem_cols_for(d.N);
+        d.Lj = (int)Lc; d.Lp_out = pv_pitch_rows(Lc); d.y16 = X16; d.out_slope = first_slope;   // [Lc][u*Cn] == [Ln][Cn]
+        if (!ok) return RVCB200_ERR_MISSING;
+        CKC(4, launch_rb(d), "dec.ups(dense)");
+      } else {
         TcConvDesc d = tc_base();
         d.x16 = IN16; d.L_in = (int)Lc; d.w16 = W16h(S("dec.ups.%d.w", i)); d.bias = W(S("dec.ups.%d.b", i));
         d.Cin = Cc; d.ntaps = g.ntaps; d.G = g.u;
         for (int p = 0; p < g.u; ++p) d.g_off[p] = g.g_off[p];
         d.N = Cn < 256 ? Cn : 256; d.Cout_total = Cn; d.tmem_cols = tmem_cols_for(d.N);
         d.Lj = (int)Lc; d.out_stride = g.u; d.Lp_out = LpN;
-        if (fuse) {
-          d.y16 = X16; d.out_slope = 0.1f;
-          if (f0) {
-            d.noise_har = pl.har; d.noise_w = W(S("dec.noise.%d.w", i)); d.noise_b = W(S("dec.noise.%d.b", i));
-            d.noise_k = nk; d.noise_s = ns; d.noise_pad = np; d.noise_L = Lout;
-          }
-        } else {
-          d.y32 = X32;
-        }
+        if (want_tap) d.y32 = X32;
+        else { d.y16 = X16; d.out_slope = first_slope; }
         if (!ok) return RVCB200_ERR_MISSING;
         d.in_bf16 = 0; d.out_bf16 = 0;
         CKC(4, launch_conv_tc(d, B, st), "dec.ups(tc)");
       }
-      if (!fuse) {
+      if (want_tap) {
         if (f0)
-          CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, want_tap, B,
+          CKC(3, launch_noise_add_pv(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X32, X16, true, B,
                                      Lout, Ln, Cn, nk, ns, np, LpN, kPadF, 0.1f, false, st),
               "dec.noise_add(pv)");
-        else    // plain Generator (models.py:298-300): no source injection, only the fp32 planar -> fp16 stream conversion
-          CKC(3, launch_noise_add_pv(nullptr, nullptr, nullptr, X32, X16, want_tap, B, Lout, Ln, Cn, 0, 1, 0, LpN, kPadF, 0.1f,
+        else    // plain Generator (models.py:298-300): only the fp32 planar -> fp16 stream conversion
+          CKC(3, launch_noise_add_pv(nullptr, nullptr, nullptr, X32, X16, true, B, Lout, Ln, Cn, 0, 1, 0, LpN, kPadF, 0.1f,
                                      false, st),
               "dec.to_stream(pv)");
+      } else if (f0) {
+        CKC(3, launch_noise_add16(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X16, B, Lout, Ln, Cn, nk, ns,
+                                  np, 0.1f, st),
+            "dec.noise_add16");
       }
       if (const rvcb200_tap* t = tp.find(S("dec.ups.%d", i).c_str()))
         CK(launch_pv32_to_cl(X32, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");

@@ -534,7 +534,7 @@ bool rbconv_tc_supported(const TcConvDesc& d) {
   if (!(d.ntaps == 3 || d.ntaps == 7 || d.ntaps == 11) || !(d.dil == 1 || d.dil == 3 || d.dil == 5)) return false;
   if (d.g_off[0] != -((d.ntaps - 1) / 2) * d.dil) return false;
   if ((d.accum && !d.y32) || !d.x16 || !d.w16 || !d.bias || d.a_fp16) return false;
-  if (d.res32 || (d.y32 && !d.acc_f16) || d.noise_har) return false;      // fp32 planar residual / output: generic kernel only
+  if (d.res32 || (d.y32 && !d.acc_f16)) return false;      // fp32 planar residual / output: generic kernel only
   return true;
 }
 

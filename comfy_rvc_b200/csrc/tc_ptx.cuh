@@ -151,8 +151,8 @@ template <int CH>
 __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t taddr, bool row_ok, int co, size_t pitch_o,
                                                size_t orow16, unsigned char* y32, unsigned char* y16row,
                                                const unsigned char* r32, const float* cond,
-                                               const unsigned char* r16row = nullptr, const float* har_b = nullptr,
-                                               long long h0 = 0, unsigned char* stage_row = nullptr, uint32_t sw_x = 0) {
+                                               const unsigned char* r16row = nullptr, unsigned char* stage_row = nullptr,
+                                               uint32_t sw_x = 0) {
   uint32_t r[CH];
   if (CH == 32) {
     asm volatile(
@@ -210,21 +210,6 @@ __device__ __forceinline__ void epilogue_chunk(const TcConvDesc& p, uint32_t tad
   if (cond) {
 #pragma unroll
     for (int i = 0; i < CH; ++i) v[i] += __ldg(cond + co + i);
-  }
-  if (har_b) {   // source injection: + noise_conv(har)[row][co..]; weights are warp-uniform (broadcast loads)
-#pragma unroll
-    for (int i = 0; i < CH; ++i) v[i] += __ldg(p.noise_b + co + i);
-    for (int kk = 0; kk < p.noise_k; ++kk) {
-      const long long h = h0 + kk;
-      const float hv = (h >= 0 && h < p.noise_L) ? __ldg(har_b + h) : 0.f;
-      const float4* wq = reinterpret_cast<const float4*>(p.noise_w + (size_t)kk * p.Cout_total + co);
-#pragma unroll
-      for (int k4 = 0; k4 < CH / 4; ++k4) {
-        const float4 w4 = __ldg(wq + k4);
-        v[k4 * 4 + 0] = fmaf(hv, w4.x, v[k4 * 4 + 0]); v[k4 * 4 + 1] = fmaf(hv, w4.y, v[k4 * 4 + 1]);
-        v[k4 * 4 + 2] = fmaf(hv, w4.z, v[k4 * 4 + 2]); v[k4 * 4 + 3] = fmaf(hv, w4.w, v[k4 * 4 + 3]);
-      }
-    }
   }
   if (r32) {
 #pragma unroll

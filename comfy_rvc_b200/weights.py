@@ -76,6 +76,30 @@ def pack_conv_transpose(w: torch.Tensor, u: int) -> torch.Tensor:
     return out
 
 
+def ups_is_dense(cfg: SynthConfig, i: int) -> bool:
+    """Stage i's transposed conv can run as ONE ordinary 3-tap convolution C_in -> u*C_out = C_in (all phases side by
+    side in N) on the specialised resblock kernel: k = 2u (two taps per phase) and u = 2 (channels halve, so u*C_out =
+    C_in).  Same rule as `ups_dense` in csrc/engine.cu."""
+    u, k = cfg.upsample_rates[i], cfg.upsample_kernel_sizes[i]
+    cin = cfg.upsample_initial_channel >> i
+    return u == 2 and k == 2 * u and cin in (32, 64, 128, 256)
+
+
+def pack_conv_transpose_dense(w: torch.Tensor, u: int) -> torch.Tensor:
+    """ConvTranspose1d weight [C_in, C_out, k = 2u] -> ordinary conv weight [3 taps][C_in][u*C_out]: output row j of
+    the dense conv holds the u phases j*u .. j*u+u-1 side by side (= the channels-last tensor [L*u][C_out] itself);
+    tap tau reads input frame j - 1 + tau, taps a phase does not use are zero."""
+    cin, cout, k = w.shape
+    pad, ntaps, g_off = up_geometry(k, u)
+    assert ntaps == 2 and all(-1 <= o <= 0 for o in g_off)
+    ph = pack_conv_transpose(w, u)                      # [u][2][C_in][C_out]
+    out = torch.zeros(3, cin, u * cout, dtype=w.dtype)
+    for p in range(u):
+        for t in range(ntaps):
+            out[g_off[p] + t + 1, :, p * cout:(p + 1) * cout] = ph[p, t]
+    return out
+
+
 def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch.Tensor], Dict[str, float]]:
     """Reference state_dict -> (packed fp32 tensors, scalars)."""
     w = fold_weight_norm(sd)
@@ -184,6 +208,9 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
     for i, u in enumerate(cfg.upsample_rates):
         P[f"dec.ups.{i}.w"] = pack_conv_transpose(w[f"dec.ups.{i}.weight"], u).contiguous()
         P[f"dec.ups.{i}.b"] = w[f"dec.ups.{i}.bias"].contiguous()
+        if ups_is_dense(cfg, i):
+            P[f"dec.ups.{i}.w3"] = pack_conv_transpose_dense(w[f"dec.ups.{i}.weight"], u).contiguous()
+            P[f"dec.ups.{i}.b3"] = w[f"dec.ups.{i}.bias"].repeat(u).contiguous()
         if cfg.f0:
             P[f"dec.noise.{i}.w"] = w[f"dec.noise_convs.{i}.weight"][:, 0, :].t().contiguous()   # [k][C]
             P[f"dec.noise.{i}.b"] = w[f"dec.noise_convs.{i}.bias"].contiguous()
@@ -256,6 +283,8 @@ def tc_weight_names(cfg: SynthConfig):
     nk = cfg.num_kernels
     for i in range(cfg.num_upsamples):
         names.append(f"dec.ups.{i}.w")
+        if ups_is_dense(cfg, i):
+            names.append(f"dec.ups.{i}.w3")
         for j in range(nk):
             n = i * nk + j
             for d in range(len(cfg.resblock_dilation_sizes[j])):

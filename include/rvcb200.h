@@ -198,11 +198,6 @@ typedef struct rvcb200_tc_conv_desc {
   int32_t a_fp16;              /* reserved, must be 0 (fp16 x bf16 mixed-format MMA: tcgen05 kind::f16 raises an illegal
                                 * instruction on sm_100a) */
   int32_t acc_f16;             /* 1: y32 (output and `accum` input) is planar-vector fp16 [B][Cout/8][Lp_out][8] */
-  /* ---- fused source injection of the NSF decoder (generic kernel, lean epilogue; models.py:552-553):
-   * v[row][c] += noise_b[c] + sum_{k < noise_k} noise_har[b][row * noise_s - noise_pad + k] * noise_w[k][c]
-   * with row the OUTPUT row (t * out_stride + g); taps outside [0, noise_L) contribute zero ---- */
-  const float* noise_har; const float* noise_w; const float* noise_b;
-  int32_t noise_k, noise_s, noise_pad; int64_t noise_L;
   int32_t tma_out;             /* filled in by the launcher: y16 leaves through swizzled staging boxes + TMA stores */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);

@@ -92,3 +92,23 @@ def test_encoder_and_decoder_packing_shapes():
     assert P["dec.post.w"].shape == (7, 16) and P["dec.noise.0.w"].shape == (96, 256)
     missing, unexpected, mismatched = weights.validate_state_dict(cfg, sd)
     assert not missing and not unexpected and not mismatched
+
+
+def test_dense_transposed_conv_packing_matches_torch():
+    """Stride-2 transposed convs run as ONE ordinary 3-tap conv C_in -> 2*C_out with the phases side by side
+    (weights.pack_conv_transpose_dense): check against F.conv_transpose1d (models.py:498-511 geometry)."""
+    import torch.nn.functional as F
+    from comfy_rvc_b200 import weights
+    g = torch.Generator().manual_seed(3)
+    cin, cout, u, k, L = 8, 4, 2, 4, 11
+    w = torch.randn(cin, cout, k, generator=g)
+    x = torch.randn(2, cin, L, generator=g)
+    ref = F.conv_transpose1d(x, w, stride=u, padding=(k - u) // 2)
+    w3 = weights.pack_conv_transpose_dense(w, u)
+    xp = F.pad(x, (1, 1)).transpose(1, 2)
+    out = sum(xp[:, tau:tau + L] @ w3[tau] for tau in range(3))
+    out = out.reshape(2, L * u, cout).transpose(1, 2)
+    assert torch.allclose(out, ref, atol=1e-6)
+    from comfy_rvc_b200.config import NAMED_CONFIGS
+    assert [weights.ups_is_dense(NAMED_CONFIGS["48k_v2"], i) for i in range(4)] == [False, False, True, True]
+    assert [weights.ups_is_dense(NAMED_CONFIGS["48k"], i) for i in range(5)] == [False, False, True, True, True]

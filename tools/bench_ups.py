@@ -68,9 +68,6 @@ def main():
                     d.y32 = y32.data_ptr()
                 else:
                     d.y16 = y16.data_ptr()
-                if mode == "fused":
-                    d.noise_har, d.noise_w, d.noise_b = har.data_ptr(), wn.data_ptr(), nb.data_ptr()
-                    d.noise_k, d.noise_s, d.noise_pad, d.noise_L = nk, ns, npad, L_har
                 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
                 for _ in range(2):
                     assert lib.rvcb200_op_conv_tc(C.byref(d), 1, st) == 0

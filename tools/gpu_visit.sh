@@ -12,10 +12,10 @@ tail -4 gpurun_out/pytest_gpu.log
 timeout 300 python tools/bench_conv_tc.py --reps 5 --rb 1 > gpurun_out/shapes_rb1.jsonl 2> gpurun_out/shapes_rb1.err
 timeout 300 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_bf16.json 2> gpurun_out/bench_bf16.err
 timeout 300 python bench.py --precision fp16 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_fp16.json 2> gpurun_out/bench_fp16.err
-RVCB200_PDL=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_bf16_nopdl.json 2> gpurun_out/bench_bf16_nopdl.err
+RVCB200_UPS_DENSE=0 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_bf16_nodense.json 2> gpurun_out/bench_bf16_nodense.err
 python - <<'P'
 import json
-for n in ("bench_bf16", "bench_fp16", "bench_bf16_nopdl"):
+for n in ("bench_bf16", "bench_fp16", "bench_bf16_nodense"):
     try:
         d = json.load(open(f"gpurun_out/{n}.json"))
         print(n, round(d["value"]), "RT  e2e", round(d["e2e"]["value"]), "ms", round(d["ms_per_step"], 3), d["time_by_class_ms_per_step"], d["clocks"])
