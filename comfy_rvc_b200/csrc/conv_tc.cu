@@ -692,8 +692,9 @@ __global__ void conv_post_pv_kernel(const unsigned char* __restrict__ x32, const
 
 
 // out[b][t] = tanh(sum_{kk,c} lrelu(x[c][t+kk-pad]) * w[kk][c]);  x is planar-vector fp16 [B][C/8][Lp][8] with zero pads.
-// One thread per output sample; each plane row (16 B) is loaded once and feeds the k outputs it contributes to through
-// a register window, so L1 traffic is 1x the tensor instead of k x.
+// Instruction-bound (convert + lrelu + FMA per loaded element), so a thread produces 4 consecutive samples from a
+// sliding window of KT+3 rows: every 16-byte row piece is loaded, converted and rectified once for the (up to) 4
+// outputs it feeds instead of once per output.
 template <int KT>
 __global__ void conv_post_pv16_kernel(const unsigned char* __restrict__ x16, const float* __restrict__ w, float* __restrict__ out,
                                       long long L, int C, int Lp, int padf, float slope) {
@@ -704,21 +705,38 @@ __global__ void conv_post_pv16_kernel(const unsigned char* __restrict__ x16, con
   pdl_wait();
   const int b = blockIdx.y;
   constexpr int pad = (KT - 1) / 2;
+  constexpr int NO = 4;
   const int n8 = C / 8;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < L; t += (long long)gridDim.x * blockDim.x) {
-    float acc = 0.f;
+  const long long nq = (L + NO - 1) / NO;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    const long long t0 = q * NO;
+    float acc[NO] = {0.f, 0.f, 0.f, 0.f};
     for (int g8 = 0; g8 < n8; ++g8) {
-      const unsigned char* pl = x16 + (((long long)b * n8 + g8) * Lp + padf + t - pad) * 16;
+      const unsigned char* pl = x16 + (((long long)b * n8 + g8) * Lp + padf + t0 - pad) * 16;
+      const float* wg = swp + g8 * 8;
 #pragma unroll
-      for (int kk = 0; kk < KT; ++kk) {
+      for (int r = 0; r < KT + NO - 1; ++r) {
         float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(pl + (long long)kk * 16), f);
-        const float* wr = swp + kk * C + g8 * 8;
+        unpack8(*reinterpret_cast<const uint4*>(pl + (long long)r * 16), f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fmaf(lrelu(f[i], slope), wr[i], acc);
+        for (int i = 0; i < 8; ++i) f[i] = lrelu(f[i], slope);
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+          const int kk = r - o;
+          if (kk >= 0 && kk < KT) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wg + kk * C), w1 = *reinterpret_cast<const float4*>(wg + kk * C + 4);
+            acc[o] = fmaf(f[0], w0.x, acc[o]); acc[o] = fmaf(f[1], w0.y, acc[o]); acc[o] = fmaf(f[2], w0.z, acc[o]);
+            acc[o] = fmaf(f[3], w0.w, acc[o]); acc[o] = fmaf(f[4], w1.x, acc[o]); acc[o] = fmaf(f[5], w1.y, acc[o]);
+            acc[o] = fmaf(f[6], w1.z, acc[o]); acc[o] = fmaf(f[7], w1.w, acc[o]);
+          }
+        }
       }
     }
-    out[(long long)b * L + t] = tanhf(acc);
+    if (t0 + NO <= L) {
+      *reinterpret_cast<float4*>(out + (long long)b * L + t0) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+    } else {
+      for (int o = 0; o < NO && t0 + o < L; ++o) out[(long long)b * L + t0 + o] = tanhf(acc[o]);
+    }
   }
 }
 
@@ -902,7 +920,9 @@ cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* 
 cudaError_t launch_noise_add16(const float* har, const float* wn, const float* nb, void* x16, int B, long long L_har,
                                long long L, int C, int k, int s, int pad, float slope, cudaStream_t st) {
   if (C % 8 != 0 || s < 1 || k < 1 || !har || !wn || !nb || !x16) return cudaErrorInvalidValue;
-  int TR = 128;
+  // tile rows: ~32 KB of stream per tile (two block-wide barriers per tile), shrunk until taps + source segment fit
+  int TR = 512;
+  while (TR > 32 && (long long)TR * C > 16384) TR >>= 1;
   auto smem_for = [&](int tr) { return sizeof(float) * ((size_t)k * C + C + (size_t)(tr + (k + s - 1) / s) * (s + 1)); };
   while (TR > 8 && smem_for(TR) > 100 * 1024) TR >>= 1;
   const size_t smem = smem_for(TR);
@@ -913,7 +933,7 @@ cudaError_t launch_noise_add16(const float* har, const float* wn, const float* n
     cfgd = smem;
   }
   const long long n_tiles = (L + TR - 1) / TR;
-  const long long per = smem > 56 * 1024 ? 2 : 8;
+  const long long per = smem > 56 * 1024 ? 2 : (smem > 24 * 1024 ? 4 : 8);
   dim3 grid((unsigned)(n_tiles < 148 * per ? n_tiles : 148 * per), B);
   cudaError_t le = launch_pdl(noise_add16_kernel, grid, dim3(256), smem, st, har, wn, nb, reinterpret_cast<unsigned char*>(x16), L_har,
                               L, C, k, s, pad, slope, TR);
@@ -932,8 +952,8 @@ cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int
 
 cudaError_t launch_conv_post_pv16(const void* x16, const float* w, float* out, int B, long long L, int C, int k, int Lp,
                                   int padf, float slope, cudaStream_t st) {
-  if (k != 7 || C % 8) return cudaErrorInvalidValue;
-  dim3 grid(grid_for(L, 256), B);
+  if (k != 7 || C % 8 || L % 4) return cudaErrorInvalidValue;     // L = T * upp, upp a multiple of 4 in every configuration
+  dim3 grid(grid_for((L + 3) / 4, 256), B);
   cudaError_t le = launch_pdl(conv_post_pv16_kernel<7>, grid, dim3(256), sizeof(float) * k * C, st,
                               reinterpret_cast<const unsigned char*>(x16), w, out, L, C, Lp, padf, slope);
   launch_counter().n++;
