@@ -78,14 +78,18 @@ def split_points(audio: np.ndarray, window: int, t_query: int, t_center: int, t_
     audio_pad = np.pad(audio, (window // 2, window // 2), mode="reflect")
     opt_ts: List[int] = []
     if audio_pad.shape[0] > t_max:
-        # sliding |sum| over `window` samples: cumulative-sum form of the reference's 160 shifted adds would round
-        # differently, so keep the reference's accumulation order (float64, 160 passes, host-side, once per song)
-        audio_sum = np.zeros_like(audio)
-        for i in range(window):
-            audio_sum += audio_pad[i: i - window]
-        for t in range(t_center, audio.shape[0], t_center):
-            seg = np.abs(audio_sum[t - t_query: t + t_query])
-            opt_ts.append(t - t_query + int(np.where(seg == seg.min())[0][0]))
+        # sliding |sum| over `window` samples: a cumulative-sum form of the reference's 160 shifted adds would round
+        # differently, so keep the reference's accumulation order (float64, one add per shift) -- but only over the
+        # 2*t_query samples around each centre that are ever looked at (each element's sum is independent of the others,
+        # so this is bit-identical to summing the whole song: 3x less host work for a 10 min song)
+        n = audio.shape[0]
+        for t in range(t_center, n, t_center):
+            lo, hi = t - t_query, min(t + t_query, n)
+            seg = np.zeros(hi - lo, dtype=audio.dtype)
+            for i in range(window):
+                seg += audio_pad[lo + i: hi + i]
+            seg = np.abs(seg)
+            opt_ts.append(lo + int(np.where(seg == seg.min())[0][0]))
     return opt_ts
 
 
