@@ -91,6 +91,7 @@ SYMBOLS = {
     "rvcb200_op_conv_f32": (C.c_int, [C.POINTER(ConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_conv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_rbconv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
+    "rvcb200_op_rbpair_tc": (C.c_int, [C.POINTER(TcConvDesc), C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_sine_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "rvcb200_op_sine_source": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),

@@ -15,6 +15,9 @@ cudaError_t launch_conv_tc(const TcConvDesc& d, int B, cudaStream_t st);
 // Compile-time specialised resblock convolution (rbconv_tc.cu); cudaErrorNotSupported if the shape is not covered.
 bool rbconv_tc_supported(const TcConvDesc& d);
 cudaError_t launch_rbconv_tc(const TcConvDesc& d, int B, cudaStream_t st);
+// Fused ResBlock1 pair (rbpair_tc.cu): conv1 -> lrelu -> conv2 + residual in one kernel, h only in shared memory.
+bool rbpair_tc_supported(const TcConvDesc& d1, const TcConvDesc& d2);
+cudaError_t launch_rbpair_tc(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st);
 cudaError_t launch_zero_pads(void* base, long long planes, int Lp, int padf, long long L, cudaStream_t st);
 cudaError_t launch_cl32_to_cl16(const float* x, void* y16, long long numel, float slope, bool bf16, cudaStream_t st);
 // x = x32 (PV fp32, ups output) + noise_conv(har): x16 = lrelu(x) as 16-bit channels-last (the activation stream);

@@ -839,6 +839,9 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     // resblock convs run on the compile-time specialised kernel (rbconv_tc.cu) when it covers the shape;
     // RVCB200_RBCONV=0 forces the generic kernel (A/B measurements)
     static const int use_rb = [] { const char* e = getenv("RVCB200_RBCONV"); return e ? atoi(e) : 1; }();
+    // ResBlock1 pairs the fused kernel covers (C <= 64, k <= 7) run as one launch; RVCB200_FUSE_PAIRS=0: two launches
+    // (read per call so that a test can compare both forms in one process)
+    const int fuse_pairs = [] { const char* e = getenv("RVCB200_FUSE_PAIRS"); return e ? atoi(e) : 1; }();
     auto launch_rb = [&](const TcConvDesc& d) -> cudaError_t {
       if (use_rb && rbconv_tc_supported(d)) return launch_rbconv_tc(d, B, st);
       return launch_conv_tc(d, B, st);
@@ -951,33 +954,45 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
           o.L_in = (int)Ln; o.Cin = Cn; o.ntaps = k;
           o.N = Cn < 256 ? Cn : 256; o.Cout_total = Cn; o.tmem_cols = tmem_cols_for(o.N);
           o.Lj = (int)Ln; o.Lp_out = LpN;
+          // stream buffers: X16 (the stage input, shared by the three branches) stays intact; XT16 / XB16 alternate.
+          // A convolution reads a halo of its input, so its 16-bit output never aliases it; only the pair-closing conv of
+          // the two-launch form may update the stream in place (its input is h, the stream is a row-aligned residual).
+          void* const hbuf = src16 == XT16 ? XB16 : XT16;                    // h = lrelu(c1(.)) of the two-launch form
+          void* const ynew = src16 == XB16 ? XT16 : XB16;                    // output that aliases neither src16 nor X16
+          TcConvDesc d = o;    // xt = c1(lrelu(x)); only lrelu(xt) is ever consumed -> 16-bit store only
           if (f.resblock_kind == 1) {
-            TcConvDesc d = o;    // xt = c1(lrelu(x)); only lrelu(xt) is ever consumed -> 16-bit store only
             d.x16 = src16; d.w16 = W16h(S("dec.rb.%d.c1.%d.w", n, dd)); d.bias = W(S("dec.rb.%d.c1.%d.b", n, dd));
             d.dil = dil; d.g_off[0] = -((k - 1) / 2) * dil;
-            d.y16 = XT16; d.out_slope = 0.1f;
+            d.y16 = hbuf; d.out_slope = 0.1f;
             if (!ok) return RVCB200_ERR_MISSING;
             d.in_bf16 = 0; d.out_bf16 = rb_bf16;
-            CKC(0, launch_rb(d), "dec.rb.c1(tc)");
-            o.x16 = XT16; o.dil = 1; o.g_off[0] = -((k - 1) / 2);
+            o.x16 = hbuf; o.dil = 1; o.g_off[0] = -((k - 1) / 2);
             o.w16 = W16(S("dec.rb.%d.c2.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c2.%d.b", n, dd));
           } else {
             o.x16 = src16; o.dil = dil; o.g_off[0] = -((k - 1) / 2) * dil;
             o.w16 = W16h(S("dec.rb.%d.c.%d.w", n, dd)); o.bias = W(S("dec.rb.%d.c.%d.b", n, dd));
           }
           o.res16 = src16; o.res_neg_scale = 10.f;
+          o.in_bf16 = c2_bf16; o.out_bf16 = 0;           // the stream (and what the next ups consumes) is fp16
           if (last) {
             const bool final_branch = j == f.n_res_kernels - 1;
             o.y32 = ACC32; o.acc_f16 = 1; o.accum = j > 0; o.div = final_branch ? (float)f.n_res_kernels : 1.f;
-            o.in_bf16 = c2_bf16; o.out_bf16 = 0;       // the next ups consumes fp16
             if (final_branch && !last_stage) { o.y16 = N16; o.out_slope = 0.1f; }
           } else {
-            o.in_bf16 = c2_bf16; o.out_bf16 = 0;
-            o.y16 = XB16; o.out_slope = 0.1f;
+            o.y16 = ynew; o.out_slope = 0.1f;
           }
           if (!ok) return RVCB200_ERR_MISSING;
-          CKC(0, launch_rb(o), "dec.rb.c2(tc)");
-          src16 = XB16;
+          if (f.resblock_kind == 1 && fuse_pairs && rbpair_tc_supported(d, o)) {
+            // one kernel per pair, h stays in shared memory (rbpair_tc.cu): 4 B/element of HBM traffic instead of 10
+            CKC(0, launch_rbpair_tc(d, o, B, st), "dec.rb.pair(tc)");
+          } else {
+            if (f.resblock_kind == 1) {
+              CKC(0, launch_rb(d), "dec.rb.c1(tc)");
+              if (!last && src16 != X16) o.y16 = const_cast<void*>(src16);   // in place: the third buffer holds h
+            }
+            CKC(0, launch_rb(o), "dec.rb.c2(tc)");
+          }
+          src16 = o.y16;
         }
       }
       if (const rvcb200_tap* t = tp.find(S("dec.stage.%d", i).c_str()))
@@ -1008,6 +1023,12 @@ int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream) {
 int rvcb200_op_rbconv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream) {
   if (!d) return RVCB200_ERR_ARG;
   cudaError_t e = launch_rbconv_tc(*d, B, reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : ((e == cudaErrorInvalidValue || e == cudaErrorNotSupported) ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int rvcb200_op_rbpair_tc(const rvcb200_tc_conv_desc* d1, const rvcb200_tc_conv_desc* d2, int32_t B, void* stream) {
+  if (!d1 || !d2) return RVCB200_ERR_ARG;
+  cudaError_t e = launch_rbpair_tc(*d1, *d2, B, reinterpret_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? RVCB200_OK : ((e == cudaErrorInvalidValue || e == cudaErrorNotSupported) ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 

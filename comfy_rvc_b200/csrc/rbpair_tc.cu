@@ -1,0 +1,565 @@
+// Fused ResBlock1 pair on tcgen05:  x' = x + conv2(lrelu(conv1(lrelu(x))))   (modules.py:295-308, one (c1, c2) pair)
+// in ONE kernel, with h = lrelu(conv1(.)) living only in shared memory.
+//
+// Why: on the narrow decoder stages (C = 64 / 32, L = 1.44 M / 2.88 M rows per 60 s segment) the two launches of a
+// pair are bound by the bytes they move through HBM -- conv1 reads the stream and writes h (4 B/element), conv2 reads
+// h and the residual and writes the stream (6 B/element); profiles/r1_conv_shapes_v10.jsonl: 4.7-5.9 TB/s on every
+// k = 3 shape.  Fused, a pair reads the stream once and writes it once: 4 B/element instead of 10 (6 instead of 12
+// for the branch-closing pair, which also carries the planar fp16 branch sum).
+//
+// Tiling: one tile = TILE_M = MSUB x 128 rows of h.  conv1 reads an activation slab of TILE_M + (k-1) DIL rows (one
+// TMA slab, tap = descriptor row offset, as in rbconv_tc.cu) and accumulates MSUB sub-tiles in TMEM; the first
+// epilogue group adds the bias, applies lrelu, rounds to the operand format of conv2 and writes h straight into a
+// SWIZZLE_128B K-major shared-memory tile (the layout TMA would have produced), zeroing rows outside [0, L) -- the
+// zero padding conv2 sees.  conv2 (dilation 1) reads that tile with tap = row offset; its last k-1 output rows would
+// need h rows of the next tile, so a tile yields OUT_ROWS = TILE_M - (k-1) valid output rows and tiles advance by
+// OUT_ROWS (0.8-4.7 % of the MMA work is recomputed instead of exchanging halos between CTAs).  The second epilogue
+// group takes the residual from the activation slab that is still in shared memory (x = r > 0 ? r : 10 r, the
+// lrelu-domain stream of DESIGN.md §3), so the residual costs no second global read.
+//
+// Pipeline per CTA (persistent, 1 CTA/SM): TMA producer warp (3-slot slab ring), one MMA warp issuing
+// conv1(i+1) before conv2(i) so the tensor pipe works while epilogue 1 turns accumulator i into h, two accumulator
+// buffers per convolution in TMEM (4 x MSUB x C columns), 4 + 4 epilogue warps.
+// Arithmetic is that of two rbconv_tc launches (same MMA order, same rounding points): the op-level test compares
+// the outputs bit for bit.
+#include "tc_ptx.cuh"
+
+namespace rvc {
+namespace {
+
+using namespace tc;
+
+constexpr int kPairThreads = 64 + 32 * 8;   // TMA producer warp, MMA warp, 4 h-epilogue warps, 4 output-epilogue warps
+constexpr int kPairBox = 2048;              // one output staging box: 32 rows x 32 channels x 16 bit, SWIZZLE_64B
+constexpr int kPairNA = 3;                  // slab ring: conv1(i+2) is loading while epilogue 2 still reads slab i
+
+struct PairPlan {
+  int tile_m, out_rows, halo, r, nbox, rb, a_bytes, h_rows, h_bytes, w_bytes, epi_bytes, nbar, smem;
+};
+constexpr PairPlan pair_plan(int C, int NTAPS, int DIL, int MSUB) {
+  PairPlan q{};
+  q.tile_m = MSUB * 128;
+  q.out_rows = q.tile_m - (NTAPS - 1);
+  q.halo = (NTAPS - 1) * DIL;
+  q.r = q.tile_m + q.halo;
+  q.nbox = (q.r + 255) / 256;
+  q.rb = (((q.r + q.nbox - 1) / q.nbox) + 7) & ~7;
+  q.a_bytes = q.nbox * q.rb * 128;
+  q.h_rows = (q.tile_m + NTAPS - 1 + 7) & ~7;
+  q.h_bytes = q.h_rows * 128;
+  q.w_bytes = C * 128;
+  q.epi_bytes = 4 * 2 * kPairBox;
+  q.nbar = 2 * kPairNA + 1 + 8 + 2;
+  q.smem = 1024 + kPairNA * q.a_bytes + q.h_bytes + 2 * NTAPS * q.w_bytes + q.epi_bytes + 2 * C * 4 + 8 * q.nbar + 64;
+  return q;
+}
+constexpr bool pair_fits(int C, int NTAPS, int DIL, int MSUB) {
+  return pair_plan(C, NTAPS, DIL, MSUB).smem <= 227 * 1024 && 4 * MSUB * C <= 512;
+}
+constexpr int pair_msub(int C, int NTAPS, int DIL) { return pair_fits(C, NTAPS, DIL, 2) ? 2 : 1; }
+
+struct PairParams {
+  const float* bias1;
+  const float* bias2;
+  int L, batch;
+  int fmt1, fmt2;              // MMA operand formats of conv1 / conv2 (0 = fp16, 1 = bf16); h is stored in fmt2
+  float h_slope;               // lrelu slope between the convolutions
+  void* y32;                   // planar-vector fp16 branch sum [B][C/8][Lp_out][8] (or null)
+  void* y16;                   // 16-bit channels-last output lrelu_{out_slope}(x') (or null)
+  int Lp_out, padf, accum, out_bf16;
+  float div, out_slope, res_neg_scale;
+};
+
+template <int C, int NTAPS, int DIL, int MSUB>
+struct PairCfg {
+  static constexpr PairPlan P = pair_plan(C, NTAPS, DIL, MSUB);
+  static constexpr int KS = C / 16;                        // K=16 MMA steps (C <= 64: one 128-byte swizzled row)
+  static constexpr int OUT_ROWS = P.out_rows;
+  static constexpr int P2 = (NTAPS - 1) / 2;               // "same" padding of conv2 (dilation 1)
+  static constexpr int P1 = ((NTAPS - 1) / 2) * DIL;       // ... of conv1
+  static constexpr int NBOX = P.nbox;
+  static constexpr int RB = P.rb;
+  static constexpr uint32_t A_BYTES = (uint32_t)P.a_bytes;
+  static constexpr uint32_t H_BYTES = (uint32_t)P.h_bytes;
+  static constexpr uint32_t W_BYTES = (uint32_t)P.w_bytes;
+  static constexpr int EPI_BYTES = P.epi_bytes;
+  static constexpr int ACC_COLS = MSUB * C;                // one accumulator buffer
+  static constexpr int TMEM_COLS = 4 * ACC_COLS;           // conv1 x 2, conv2 x 2
+  static constexpr size_t SMEM = (size_t)P.smem;
+  static constexpr int TAIL_ROWS = 32 - (NTAPS - 1);       // valid rows of a tile's last 32-row output box
+  static_assert(C == 32 || C == 64, "C");
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+  static_assert(RB <= 256 && A_BYTES % 1024 == 0 && H_BYTES % 1024 == 0 && W_BYTES % 1024 == 0, "box");
+  static_assert(NTAPS - 1 < 32, "tail box");
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int C, int NTAPS, int DIL, int MSUB>
+__global__ void __launch_bounds__(kPairThreads, 1)
+rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
+                 const __grid_constant__ CUtensorMap tmYt) {
+  using K = PairCfg<C, NTAPS, DIL, MSUB>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                                       // [NA][slab rows][128 B] swizzled (TMA)
+  unsigned char* sH = sA + (size_t)kPairNA * K::A_BYTES;          // [H_ROWS][128 B] swizzled (written by epilogue 1)
+  unsigned char* sW1 = sH + K::H_BYTES;                           // [NTAPS][C][128 B] swizzled
+  unsigned char* sW2 = sW1 + (size_t)NTAPS * K::W_BYTES;
+  unsigned char* sE = sW2 + (size_t)NTAPS * K::W_BYTES;           // [4 warps][2 output boxes][2 KB]
+  float* sbias1 = reinterpret_cast<float*>(sE + K::EPI_BYTES);
+  float* sbias2 = sbias1 + C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias2 + C);
+  uint64_t* a_full = bars;                  // [NA]
+  uint64_t* a_empty = a_full + kPairNA;     // [NA]  conv1 MMAs done (1) + the 4 output-epilogue warps (residual reads)
+  uint64_t* w_full = a_empty + kPairNA;     // [1]
+  uint64_t* acc1_full = w_full + 1;         // [2]
+  uint64_t* acc1_empty = acc1_full + 2;     // [2]
+  uint64_t* acc2_full = acc1_empty + 2;     // [2]
+  uint64_t* acc2_empty = acc2_full + 2;     // [2]
+  uint64_t* h_full = acc2_empty + 2;        // [1]  epilogue 1 has written h (4 warps)
+  uint64_t* h_empty = h_full + 1;           // [1]  conv2 MMAs have read h
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const unsigned n_mt = (unsigned)((p.L + K::OUT_ROWS - 1) / K::OUT_ROWS);
+  const unsigned total_tiles = n_mt * (unsigned)p.batch;
+
+  if (threadIdx.x == 0) {
+    pdl_trigger();
+    for (int i = 0; i < kPairNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 5); }
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 4);
+      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 4);
+    }
+    mbar_init(h_full, 4);
+    mbar_init(h_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)K::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < C; i += kPairThreads) { sbias1[i] = p.bias1[i]; sbias2[i] = p.bias2[i]; }
+  // rows [TILE_M, H_ROWS) of the h tile are only ever read for output rows that are discarded; keep them finite
+  for (int i = threadIdx.x; i < (int)(K::H_BYTES / 16); i += kPairThreads)
+    reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== producer: TMA global -> swizzled smem ============================
+    if (lane == 0) {
+      mbar_expect_tx(w_full, 2u * NTAPS * K::W_BYTES);
+#pragma unroll 1
+      for (int tap = 0; tap < NTAPS; ++tap) {
+        tma_load_2d(sW1 + (size_t)tap * K::W_BYTES, &tmW1, 0, tap * C, w_full);
+        tma_load_2d(sW2 + (size_t)tap * K::W_BYTES, &tmW2, 0, tap * C, w_full);
+      }
+      pdl_wait();                                    // the stream comes from the previous kernel (weights do not)
+      int sa = 0;
+      uint32_t pa = 1;
+#pragma unroll 1
+      for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const unsigned b = tile / n_mt, mt = tile - b * n_mt;
+        const int row0 = (int)mt * K::OUT_ROWS - K::P2 - K::P1;
+        mbar_wait(&a_empty[sa], pa);
+        mbar_expect_tx(&a_full[sa], K::A_BYTES);
+#pragma unroll
+        for (int j = 0; j < K::NBOX; ++j)
+          tma_load_3d(sA + (size_t)sa * K::A_BYTES + (size_t)j * K::RB * 128, &tmA, 0, row0 + j * K::RB, (int)b, &a_full[sa]);
+        if (++sa == kPairNA) { sa = 0; pa ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (warp-uniform, one elected lane): conv1(0), conv1(1), conv2(0), conv1(2), conv2(1), ... =====
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    // instruction descriptor: D=F32 @4, A/B format @7/@10, K-major both, N>>3 @17, M>>4 @24
+    const uint32_t f1 = p.fmt1 ? 1u : 0u, f2 = p.fmt2 ? 1u : 0u;
+    const uint32_t idesc1 = (1u << 4) | (f1 << 7) | (f1 << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (f2 << 7) | (f2 << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t dproto = make_desc_sw128(0, 0);
+    const uint32_t d_hi = (uint32_t)(dproto >> 32), d_lo0 = (uint32_t)dproto;
+    const uint32_t sA_d = __shfl_sync(0xffffffffu, d_lo0 + (smem_u32(sA) >> 4), 0);
+    const uint32_t sH_d = __shfl_sync(0xffffffffu, d_lo0 + (smem_u32(sH) >> 4), 0);
+    const uint32_t sW1_d = __shfl_sync(0xffffffffu, d_lo0 + (smem_u32(sW1) >> 4), 0);
+    const uint32_t sW2_d = __shfl_sync(0xffffffffu, d_lo0 + (smem_u32(sW2) >> 4), 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    mbar_wait(w_full, 0);
+    tc_fence_after();
+    auto conv2 = [&](uint32_t j) {                   // h of my j-th tile is in sH
+      const uint32_t buf = j & 1u;
+      mbar_wait(h_full, j & 1u);
+      mbar_wait(&acc2_empty[buf], ((j >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + (uint32_t)(2 * K::ACC_COLS) + buf * (uint32_t)K::ACC_COLS;
+#pragma unroll
+      for (int tap = 0; tap < NTAPS; ++tap) {
+        const uint32_t b_d = sW2_d + (uint32_t)tap * (K::W_BYTES >> 4);
+#pragma unroll
+        for (int ms = 0; ms < MSUB; ++ms) {
+#pragma unroll
+          for (int ks = 0; ks < K::KS; ++ks)
+            tc_mma_f16_pred(d_tmem + (uint32_t)(ms * C), sH_d + (uint32_t)(((ms * 128 + tap) * 128 + ks * 32) >> 4), d_hi,
+                            b_d + (uint32_t)((ks * 32) >> 4), d_hi, idesc2, (tap | ks) != 0 ? 1u : 0u, leader);
+        }
+      }
+      tc_commit_pred(h_empty, leader);
+      tc_commit_pred(&acc2_full[buf], leader);
+    };
+    int sa = 0;
+    uint32_t pa = 0;
+    uint32_t it = 0;
+#pragma unroll 1
+    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      mbar_wait(&acc1_empty[buf], ((it >> 1) & 1u) ^ 1u);
+      mbar_wait(&a_full[sa], pa);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + buf * (uint32_t)K::ACC_COLS;
+      const uint32_t a_d = sA_d + (uint32_t)sa * (K::A_BYTES >> 4);
+#pragma unroll
+      for (int tap = 0; tap < NTAPS; ++tap) {
+        const uint32_t b_d = sW1_d + (uint32_t)tap * (K::W_BYTES >> 4);
+#pragma unroll
+        for (int ms = 0; ms < MSUB; ++ms) {
+#pragma unroll
+          for (int ks = 0; ks < K::KS; ++ks)
+            tc_mma_f16_pred(d_tmem + (uint32_t)(ms * C), a_d + (uint32_t)(((ms * 128 + tap * DIL) * 128 + ks * 32) >> 4), d_hi,
+                            b_d + (uint32_t)((ks * 32) >> 4), d_hi, idesc1, (tap | ks) != 0 ? 1u : 0u, leader);
+        }
+      }
+      tc_commit_pred(&a_empty[sa], leader);
+      tc_commit_pred(&acc1_full[buf], leader);
+      if (++sa == kPairNA) { sa = 0; pa ^= 1; }
+      if (it > 0) conv2(it - 1);
+      __syncwarp();
+    }
+    if (it > 0) conv2(it - 1);
+    __syncwarp();
+  } else if (warp < 6) {
+    // ============ epilogue 1: conv1 accumulator -> h = lrelu(. + b1) in the operand format of conv2 -> sH ============
+    const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
+    const bool hbf = p.fmt2 != 0;
+    const float hs = p.h_slope;
+    uint32_t j = 0;
+#pragma unroll 1
+    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const unsigned b = tile / n_mt, mt = tile - b * n_mt;
+      (void)b;
+      const int th0 = (int)mt * K::OUT_ROWS - K::P2 + qd * 32 + lane;     // time index of this lane's h row (sub-tile 0)
+      const uint32_t buf = j & 1u;
+      mbar_wait(&acc1_full[buf], (j >> 1) & 1u);
+      mbar_wait(h_empty, (j & 1u) ^ 1u);             // conv2 of the previous tile has consumed sH
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * (uint32_t)K::ACC_COLS;
+#pragma unroll 1
+      for (int ms = 0; ms < MSUB; ++ms) {
+        const int hrow = ms * 128 + qd * 32 + lane;
+        const int th = th0 + ms * 128;
+        const bool ok = th >= 0 && th < p.L;         // conv2 pads h with zeros outside [0, L)
+        unsigned char* hp = sH + (size_t)hrow * 128;
+        const uint32_t sx = (uint32_t)hrow & 7u;
+#pragma unroll
+        for (int cc = 0; cc < C / 32; ++cc) {
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)(ms * C + cc * 32), r);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(sbias1 + cc * 32 + k * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(sbias1 + cc * 32 + k * 8 + 4);
+            v[0] = __uint_as_float(r[k * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[k * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(r[k * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[k * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(r[k * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[k * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(r[k * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[k * 8 + 7]) + b1.w;
+            uint4 o;
+            o.x = pack2(hbf, lrelu(v[0], hs), lrelu(v[1], hs)); o.y = pack2(hbf, lrelu(v[2], hs), lrelu(v[3], hs));
+            o.z = pack2(hbf, lrelu(v[4], hs), lrelu(v[5], hs)); o.w = pack2(hbf, lrelu(v[6], hs), lrelu(v[7], hs));
+            if (!ok) o = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(hp + ((((uint32_t)(cc * 4 + k)) ^ sx) << 4)) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();                           // generic-proxy writes of sH -> visible to the MMA (async proxy)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&acc1_empty[buf]); mbar_arrive(h_full); }
+    }
+  } else {
+    // ===== epilogue 2: conv2 accumulator + b2 + residual (from the slab) -> branch sum / 16-bit stream (TMA boxes) =====
+    pdl_wait();
+    const int ew = warp - 6;
+    const int qd = warp & 3;
+    const size_t pitch_o = (size_t)p.Lp_out * 16;   // bytes per planar-vector plane
+    const bool obf = p.out_bf16 != 0;
+    const float slope = p.out_slope;
+    const float inv_div = p.div;                    // divide (not multiply by reciprocal): matches the fp32 path
+    const float neg_scale = p.res_neg_scale == 0.f ? 1.f : p.res_neg_scale;
+    const bool has_y16 = p.y16 != nullptr;
+    const bool has_acc = p.y32 != nullptr;
+    const bool do_acc = has_acc && p.accum != 0;
+    unsigned char* my_stage = sE + (size_t)ew * 2 * kPairBox;
+    const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = ((uint32_t)lane >> 1) & 3u;   // SWIZZLE_64B staging box
+    uint32_t ocnt = 0;
+    uint32_t j = 0;
+    int sa = 0;
+    uint32_t pa = 0;
+#pragma unroll 1
+    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const unsigned b = tile / n_mt, mt = tile - b * n_mt;
+      const int o0 = (int)mt * K::OUT_ROWS;
+      const int wj0 = qd * 32;                                    // first in-tile row of this warp's group (sub-tile 0)
+      const uint32_t buf = j & 1u;
+      unsigned char* acc = has_acc ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (C / 8) * pitch_o : nullptr;
+      const unsigned char* slab = sA + (size_t)sa * K::A_BYTES;
+      constexpr int CPS = C / 32;                                 // 32-column chunks per 128-row sub-tile
+      constexpr int NCH = MSUB * CPS;
+      uint4 aq[2][4];                                             // branch-sum words, fetched one chunk ahead
+      auto load_acc = [&](int ci, int slot) {
+        const int ms = ci / CPS, c0 = (ci - ms * CPS) * 32;
+        const int jl = ms * 128 + wj0 + lane;
+        if (jl < K::OUT_ROWS && o0 + jl < p.L) {
+          const unsigned char* q = acc + (size_t)(c0 / 8) * pitch_o + (size_t)(o0 + jl + p.padf) * 16;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) aq[slot][k] = *reinterpret_cast<const uint4*>(q + (size_t)k * pitch_o);
+        }
+      };
+      if (do_acc) load_acc(0, 0);
+      mbar_wait(&acc2_full[buf], (j >> 1) & 1u);
+      mbar_wait(&a_full[sa], pa);                                 // (long complete: orders the slab reads after the TMA writes)
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(2 * K::ACC_COLS) + buf * (uint32_t)K::ACC_COLS;
+#pragma unroll
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int ms = ci / CPS, cc = ci - ms * CPS, c0 = cc * 32;
+        const int jl = ms * 128 + wj0 + lane;                     // in-tile output row of this lane
+        const int row = o0 + jl;
+        const bool row_ok = jl < K::OUT_ROWS && row < p.L;
+        const int srow = jl + K::P2 + K::P1;                      // the same time step inside the activation slab
+        const unsigned char* rp = slab + (size_t)srow * 128;
+        const uint32_t rx = (uint32_t)srow & 7u;
+        if (do_acc && ci + 1 < NCH) load_acc(ci + 1, (ci + 1) & 1);
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)(ms * C + c0), r);
+        float v[32];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 bq = *reinterpret_cast<const float4*>(sbias2 + c0 + k4 * 4);
+          v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
+          v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
+          v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
+          v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          add_res8(v + k * 8, *reinterpret_cast<const uint4*>(rp + ((((uint32_t)(cc * 4 + k)) ^ rx) << 4)), neg_scale);
+        if (has_acc) {
+          if (do_acc && row_ok) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) add_res8(v + k * 8, aq[ci & 1][k], 1.f);
+          }
+          if (inv_div != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
+          }
+          if (row_ok) {
+            unsigned char* q = acc + (size_t)(c0 / 8) * pitch_o + (size_t)(row + p.padf) * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint4 o;
+              o.x = pack2(false, v[k * 8 + 0], v[k * 8 + 1]); o.y = pack2(false, v[k * 8 + 2], v[k * 8 + 3]);
+              o.z = pack2(false, v[k * 8 + 4], v[k * 8 + 5]); o.w = pack2(false, v[k * 8 + 6], v[k * 8 + 7]);
+              *reinterpret_cast<uint4*>(q + (size_t)k * pitch_o) = o;
+            }
+          }
+        } else if (inv_div != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
+        }
+        if (has_y16) {
+          uint4 o[4];
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) {
+            o[k8].x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
+            o[k8].y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
+            o[k8].z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
+            o[k8].w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
+          }
+          // stage the [32 rows][32 channels] box, then one lane stores it (rows >= L are clipped by the tensor map;
+          // the tile's last box holds only TAIL_ROWS valid rows and goes through the shorter tensor-map box)
+          unsigned char* box = my_stage + (ocnt & 1u) * kPairBox;
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(box + sw_row + ((((uint32_t)k) ^ sw_x) << 4)) = o[k];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const bool tail = ms == MSUB - 1 && qd == 3;
+            tma_store_3d(tail ? &tmYt : &tmY, box, c0, o0 + ms * 128 + wj0, (int)b);
+            bulk_commit();
+          }
+          ++ocnt;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&acc2_empty[buf]); mbar_arrive(&a_empty[sa]); }
+      if (++sa == kPairNA) { sa = 0; pa ^= 1; }
+    }
+    if (lane == 0) bulk_wait_all();                 // staged stores complete before the CTA's smem goes away
+  }
+  // ------------------------------------ teardown -------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)K::TMEM_COLS));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn pair_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int C, int NTAPS, int DIL, int MSUB>
+cudaError_t launch_pair_one(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st) {
+  using K = PairCfg<C, NTAPS, DIL, MSUB>;
+  EncodeTiledFn enc = pair_encode_tiled();
+  if (!enc) return cudaErrorNotSupported;
+  CUtensorMap tmA, tmW1, tmW2, tmY, tmYt;
+  const CUtensorMapDataType dt1 = d1.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType dt2 = d2.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  cuuint32_t es[3] = {1, 1, 1};
+  const int L = d1.Lj;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * (cuuint64_t)L};
+    cuuint32_t box[3] = {64, (cuuint32_t)K::RB, 1};
+    if (enc(&tmA, dt1, 3, const_cast<void*>(d1.x16), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    cuuint64_t wdims[2] = {64, (cuuint64_t)NTAPS * C};
+    cuuint64_t wstrides[1] = {128};
+    cuuint32_t wbox[2] = {64, (cuuint32_t)C};
+    if (enc(&tmW1, dt1, 2, const_cast<void*>(d1.w16), wdims, wstrides, wbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    if (enc(&tmW2, dt2, 2, const_cast<void*>(d2.w16), wdims, wstrides, wbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    tmY = tmA;
+    tmYt = tmA;
+    if (d2.y16) {
+      const CUtensorMapDataType dto = d2.out_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+      cuuint32_t obox[3] = {32, 32, 1};
+      cuuint32_t tbox[3] = {32, (cuuint32_t)K::TAIL_ROWS, 1};
+      if (enc(&tmY, dto, 3, d2.y16, dims, strides, obox, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+      if (enc(&tmYt, dto, 3, d2.y16, dims, strides, tbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    }
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(rbpair_tc_kernel<C, NTAPS, DIL, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)K::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  PairParams p{};
+  p.bias1 = d1.bias; p.bias2 = d2.bias;
+  p.L = L; p.batch = B;
+  p.fmt1 = d1.in_bf16; p.fmt2 = d2.in_bf16;
+  p.h_slope = d1.out_slope;
+  p.y32 = d2.y32; p.y16 = d2.y16;
+  p.Lp_out = d2.Lp_out; p.padf = d2.padf; p.accum = d2.accum; p.out_bf16 = d2.out_bf16;
+  p.div = d2.div; p.out_slope = d2.out_slope; p.res_neg_scale = d2.res_neg_scale;
+  const long long tiles = (long long)((L + K::OUT_ROWS - 1) / K::OUT_ROWS) * B;
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
+  cudaError_t le = launch_pdl(rbpair_tc_kernel<C, NTAPS, DIL, MSUB>, dim3(grid), dim3(kPairThreads), K::SMEM, st, p, tmA, tmW1,
+                              tmW2, tmY, tmYt);
+  launch_counter().n++;
+  return le != cudaSuccess ? le : cudaGetLastError();
+}
+
+template <int C, int NTAPS>
+cudaError_t launch_pair_d(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st) {
+  switch (d1.dil) {
+    case 1: return launch_pair_one<C, NTAPS, 1, pair_msub(C, NTAPS, 1)>(d1, d2, B, st);
+    case 3: return launch_pair_one<C, NTAPS, 3, pair_msub(C, NTAPS, 3)>(d1, d2, B, st);
+    case 5: return launch_pair_one<C, NTAPS, 5, pair_msub(C, NTAPS, 5)>(d1, d2, B, st);
+    default: return cudaErrorNotSupported;
+  }
+}
+
+}  // namespace
+
+// The fused kernel covers a (conv1, conv2) pair when both are resblock shapes of rbconv_tc.cu with C in {32, 64},
+// k in {3, 7} (both weight sets resident in shared memory), conv2 has dilation 1 and consumes conv1's 16-bit output,
+// the residual is the pair's own input stream, and the output does not alias it (tiles read a halo of the input).
+bool rbpair_tc_supported(const TcConvDesc& d1, const TcConvDesc& d2) {
+  if (!rbconv_tc_supported(d1) || !rbconv_tc_supported(d2)) return false;
+  if (!(d1.Cin == 32 || d1.Cin == 64) || d2.Cin != d1.Cin) return false;
+  if (!(d1.ntaps == 3 || d1.ntaps == 7) || d2.ntaps != d1.ntaps || d2.dil != 1) return false;
+  if (d1.Lj != d2.Lj || d1.L_in != d2.L_in) return false;
+  if (!d1.y16 || d1.y32 || d1.res16 || d1.accum || d1.div != 1.f) return false;      // conv1: 16-bit store of lrelu(.) only
+  if (d2.x16 != d1.y16 || d1.out_bf16 != d2.in_bf16) return false;                   // conv2 consumes h
+  if (!d2.res16 || d2.res16 != d1.x16) return false;                                 // residual = the pair's input stream
+  if (d2.y16 == d1.x16) return false;                                                // no in-place update (halo reads)
+  if (!d2.y16 && !d2.y32) return false;
+  return true;
+}
+
+cudaError_t launch_rbpair_tc(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st) {
+  if (!rbpair_tc_supported(d1, d2) || B <= 0) return cudaErrorNotSupported;
+  if (d1.Cin == 32) return d1.ntaps == 3 ? launch_pair_d<32, 3>(d1, d2, B, st) : launch_pair_d<32, 7>(d1, d2, B, st);
+  return d1.ntaps == 3 ? launch_pair_d<64, 3>(d1, d2, B, st) : launch_pair_d<64, 7>(d1, d2, B, st);
+}
+
+}  // namespace rvc

@@ -207,6 +207,12 @@ int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
  * RVCB200_ERR_ARG for any other shape (the engine then uses rvcb200_op_conv_tc's kernel). */
 int rvcb200_op_rbconv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 
+/* One ResBlock1 pair x' = x + c2(lrelu(c1(lrelu(x)))) (/root/reference/lib/infer_pack/modules.py:295-308) as ONE kernel
+ * (csrc/rbpair_tc.cu): d1 / d2 are the descriptors the two rvcb200_op_rbconv_tc launches would take (d2->x16 == d1->y16,
+ * d2->res16 == d1->x16, d2->y16 != d1->x16); h = lrelu(c1) stays in shared memory, so d1->y16 is NOT written.  Results
+ * are bit-identical to the two launches.  Covers Cin in {32, 64}, ntaps in {3, 7}; RVCB200_ERR_ARG otherwise. */
+int rvcb200_op_rbpair_tc(const rvcb200_tc_conv_desc* d1, const rvcb200_tc_conv_desc* d2, int32_t B, void* stream);
+
 /* NSF harmonic source (SineGen + SourceModuleHnNSF, models.py:361-411,455-467):
  * f0 [B][T] -> har [B][T*upp]; scratch >= rvcb200_op_sine_scratch_bytes(B,T,upp). */
 int64_t rvcb200_op_sine_scratch_bytes(int32_t B, int32_t T, int32_t upp);

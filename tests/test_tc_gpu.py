@@ -200,6 +200,118 @@ def test_rbconv_tc(case, bf16, kind):
     assert torch.equal(y16.view(torch.int16), g16.view(torch.int16))
 
 
+PAIR_CASES = [
+    # name, B, L, C, ntaps, dil   (every (C, k) the fused kernel covers; ragged last tiles; several tiles per CTA; batch)
+    ("pair_c32_k3_d1", 1, 1000, 32, 3, 1),
+    ("pair_c32_k3_d5_long", 2, 70001, 32, 3, 5),
+    ("pair_c32_k7_d3", 1, 513, 32, 7, 3),
+    ("pair_c32_k7_d5_long", 1, 90000, 32, 7, 5),
+    ("pair_c64_k3_d3", 1, 300, 64, 3, 3),
+    ("pair_c64_k3_d1_long", 2, 50001, 64, 3, 1),
+    ("pair_c64_k7_d1", 3, 254, 64, 7, 1),
+    ("pair_c64_k7_d5_long", 1, 60000, 64, 7, 5),
+    ("pair_c64_k3_d5_tiny", 1, 5, 64, 3, 5),
+]
+
+
+def _pair_descs(x16, h16, y16, xs, w1, w2, b1, b2, L, Cc, ntaps, dil, kind, bf16):
+    d1, d2 = _lib.TcConvDesc(), _lib.TcConvDesc()
+    for d, dl in ((d1, dil), (d2, 1)):
+        d.L_in, d.padf, d.Cin, d.ntaps, d.dil, d.G = L, PADF, Cc, ntaps, dl, 1
+        d.g_off[0] = -((ntaps - 1) // 2) * dl
+        d.N, d.Cout_total, d.Lj, d.out_stride, d.Lp_out = Cc, Cc, L, 1, pitch(L)
+        d.div, d.out_slope = 1.0, 0.1
+    d1.x16, d1.w16, d1.bias, d1.y16 = x16.data_ptr(), w1.data_ptr(), b1.data_ptr(), h16.data_ptr()
+    d1.in_bf16, d1.out_bf16 = 0, int(bf16)
+    d2.x16, d2.w16, d2.bias = h16.data_ptr(), w2.data_ptr(), b2.data_ptr()
+    d2.in_bf16, d2.out_bf16 = int(bf16), 0
+    d2.res16, d2.res_neg_scale = x16.data_ptr(), 10.0
+    if kind in ("s", "af"):
+        d2.y16 = y16.data_ptr()
+    if kind in ("a", "af"):
+        d2.y32, d2.acc_f16, d2.accum, d2.div = xs.data_ptr(), 1, 1, 3.0
+    return d1, d2
+
+
+@pytest.mark.parametrize("kind", ["s", "a", "af"])
+@pytest.mark.parametrize("bf16", [False, True], ids=["fp16", "bf16"])
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
+def test_rbpair_tc(case, bf16, kind):
+    """Fused ResBlock1 pair (rbpair_tc.cu) is bit-identical to the two rbconv_tc launches it replaces, and both match
+    the fp64 restatement.  kind s: 16-bit stream out; a: planar fp16 branch sum (accumulate, /3); af: both."""
+    name, B, L, Cc, ntaps, dil = case
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    dt2 = torch.bfloat16 if bf16 else torch.float16
+    g = torch.Generator().manual_seed(len(name) * 11 + Cc + ntaps + dil)
+    x = torch.randn(B, L, Cc, generator=g)
+    stream = torch.where(x > 0, x, x * 0.1).half()                        # lrelu-domain stream: the MMA operand
+    w1 = (torch.randn(1, ntaps, Cc, Cc, generator=g) / math.sqrt(Cc * ntaps)).half().float()
+    w2 = (torch.randn(1, ntaps, Cc, Cc, generator=g) / math.sqrt(Cc * ntaps)).to(dt2).float()
+    b1, b2 = torch.randn(Cc, generator=g), torch.randn(Cc, generator=g)
+    acc0 = torch.randn(B, L, Cc, generator=g).half().float()
+    x16 = stream.to(dev).contiguous()
+    w1d, w2d = weights.pack_tc(w1, torch.float16).to(dev), weights.pack_tc(w2, dt2).to(dev)
+    b1d, b2d = b1.to(dev), b2.to(dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for fused in (True, False):
+        h16 = torch.full((B, L, Cc), float("nan"), dtype=dt2, device=dev)
+        y16 = torch.zeros(B, L, Cc, dtype=torch.float16, device=dev)
+        xs = to_pv(acc0, 8, torch.float16).to(dev)
+        d1, d2 = _pair_descs(x16, h16, y16, xs, w1d, w2d, b1d, b2d, L, Cc, ntaps, dil, kind, bf16)
+        if fused:
+            assert lib.rvcb200_op_rbpair_tc(C.byref(d1), C.byref(d2), B, st) == 0
+        else:
+            assert lib.rvcb200_op_rbconv_tc(C.byref(d1), B, st) == 0
+            assert lib.rvcb200_op_rbconv_tc(C.byref(d2), B, st) == 0
+        torch.cuda.synchronize()
+        outs.append((y16.cpu(), xs.cpu(), h16.cpu()))
+    (fy, fxs, fh), (uy, uxs, uh) = outs
+    assert bool(torch.isnan(fh.float()).all())                             # the fused kernel never writes h
+    # fp64 restatement on the two-launch form's own h (its rounding point), then fused == two-launch bit for bit
+    xr = torch.where(stream > 0, stream.float(), stream.float() * 10.0).double()
+    ref = conv_cl(uh.float().double(), w2.double(), b2.double(), g_off=[-((ntaps - 1) // 2)], dil=1, out_stride=1) + xr
+    if kind in ("a", "af"):
+        ref = (ref + acc0.double()) / 3.0
+        got = from_pv(fxs.float(), L).double()
+        assert (got - ref).abs().max().item() < 6e-3
+        assert torch.equal(fxs.view(torch.int16), uxs.view(torch.int16))
+        assert float(fxs[:, :, :PADF].abs().max()) == 0.0 and float(fxs[:, :, PADF + L:].abs().max()) == 0.0
+    if kind in ("s", "af"):
+        want16 = torch.where(ref > 0, ref, ref * 0.1)
+        assert (fy.float().double() - want16).abs().max().item() < 0.02
+        assert torch.equal(fy.view(torch.int16), uy.view(torch.int16))
+
+
+def test_rbpair_rejects_uncovered_pairs():
+    lib = _lib.load()
+    z = torch.zeros(8, dtype=torch.float16)
+    for Cc, ntaps, alias in ((128, 3, False), (64, 11, False), (64, 3, True)):
+        L = 100
+        d1, d2 = _pair_descs(z, z[1:], z[2:], z[3:], z, z, z, z, L, Cc, ntaps, 1, "s", False)
+        if alias:
+            d2.y16 = d1.x16                                                # in-place update: tiles read a halo of x
+        assert lib.rvcb200_op_rbpair_tc(C.byref(d1), C.byref(d2), 1, None) == 1
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", ["c2_48k_v2", "c3_32k_v2_ragged", "c5_48k_v1_5stage", "c7_40k_v1_nono"])
+def test_infer_fused_pairs_equals_two_launch_form(name, precision, monkeypatch):
+    """End to end: RVCB200_FUSE_PAIRS=1 (default) and =0 give the same waveform bit for bit."""
+    from tests.test_parity_gpu import build_net
+    from tests._util import net_infer
+    cfg, sd, inputs, noise, gold = load_golden(name)
+    net = build_net(cfg, sd, precision)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("RVCB200_FUSE_PAIRS", flag)
+        outs.append((net_infer(net, cfg, inputs, noise)[0].cpu(), net.last_launches))
+    torch.cuda.synchronize()
+    assert outs[0][1] < outs[1][1], "the fused form must launch fewer kernels"
+    assert torch.equal(outs[0][0], outs[1][0])
+
+
 def test_rbconv_rejects_other_shapes():
     d = _lib.TcConvDesc()
     d.Cin = d.Cout_total = d.N = 16

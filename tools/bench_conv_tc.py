@@ -25,6 +25,71 @@ def pitch(L):
     return ((L + 127) // 128) * 128 + 128
 
 
+def bench_pairs(args, lib):
+    """One ResBlock1 pair x' = x + c2(lrelu(c1(lrelu(x)))) at the decoder's stage-3/4 shapes: one fused launch vs two."""
+    dev = torch.device("cuda", 0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rows = []
+    for si, (Cc, L) in ((3, (64, args.T * 240)), (4, (32, args.T * 480))):
+        if args.stages and (si - 1) not in {int(v) for v in args.stages.split(",")}:
+            continue
+        Lp = pitch(L)
+        x16 = torch.randn(1, L, Cc, dtype=torch.float16, device=dev)
+        h16 = torch.zeros(1, L, Cc, dtype=torch.float16, device=dev)
+        y16 = torch.zeros(1, L, Cc, dtype=torch.float16, device=dev)
+        xs = torch.zeros(1, Cc // 8, Lp, 8, dtype=torch.float16, device=dev)
+        bias = torch.randn(Cc, device=dev)
+        keep = {int(v) for v in args.ks.split(",")} if args.ks else None
+        for k, dil in ((3, 1), (3, 5), (7, 1), (7, 5)):
+            if keep is not None and k not in keep:
+                continue
+            w = weights.pack_tc(torch.randn(1, k, Cc, Cc) / (Cc * k) ** 0.5, torch.float16).to(dev)
+            for kind in ("s", "a"):
+                d1, d2 = _lib.TcConvDesc(), _lib.TcConvDesc()
+                for d, dl in ((d1, dil), (d2, 1)):
+                    d.L_in, d.padf, d.Cin, d.ntaps, d.dil, d.G = L, PADF, Cc, k, dl, 1
+                    d.g_off[0] = -((k - 1) // 2) * dl
+                    d.N, d.Cout_total, d.Lj, d.out_stride, d.Lp_out = Cc, Cc, L, 1, Lp
+                    d.div, d.out_slope, d.w16, d.bias = 1.0, 0.1, w.data_ptr(), bias.data_ptr()
+                d1.x16, d1.y16 = x16.data_ptr(), h16.data_ptr()
+                d2.x16, d2.res16, d2.res_neg_scale = h16.data_ptr(), x16.data_ptr(), 10.0
+                if kind == "s":
+                    d2.y16 = y16.data_ptr()
+                else:
+                    d2.y32, d2.acc_f16, d2.accum = xs.data_ptr(), 1, 1
+
+                def fused():
+                    return lib.rvcb200_op_rbpair_tc(C.byref(d1), C.byref(d2), 1, st)
+
+                def two():
+                    return lib.rvcb200_op_rbconv_tc(C.byref(d1), 1, st) | lib.rvcb200_op_rbconv_tc(C.byref(d2), 1, st)
+
+                res = {}
+                for nm, fn in (("fused", fused), ("two", two)):
+                    for _ in range(2):
+                        assert fn() == 0
+                    torch.cuda.synchronize()
+                    if args.profile and nm == "fused":
+                        torch.cuda.profiler.start()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(args.reps):
+                        fn()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if args.profile and nm == "fused":
+                        torch.cuda.profiler.stop()
+                    res[nm] = e0.elapsed_time(e1) * 1e3 / args.reps
+                flops = 2 * 2.0 * L * Cc * Cc * k
+                b_f = L * Cc * (4 if kind == "s" else 6)
+                b_t = L * Cc * (10 if kind == "s" else 12)
+                rows.append(dict(pair=1, stage=si, C=Cc, L=L, k=k, dil=dil, kind=kind, fused_us=round(res["fused"], 1),
+                                 two_us=round(res["two"], 1), fused_tflops=round(flops / res["fused"] / 1e6, 1),
+                                 fused_hbm_gbs=round(b_f / res["fused"] / 1e3, 1), two_hbm_gbs=round(b_t / res["two"] / 1e3, 1)))
+                print(json.dumps(rows[-1]), flush=True)
+    return rows
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=5)
@@ -38,8 +103,11 @@ def main():
     ap.add_argument("--kinds", default="c1,c2s,c2a", help="c1: 16-bit store only; c2: + fp32 planar residual in/out; "
                     "c2s: + residual from the fp16 lrelu-domain stream; c2a: stream residual, planar fp16 branch-sum accumulate, no 16-bit store")
     ap.add_argument("--ks", default="", help="comma list of kernel sizes to keep (default all)")
+    ap.add_argument("--pair", action="store_true", help="fused ResBlock pair (rbpair_tc.cu) against its two-launch form")
     args = ap.parse_args()
     lib = _lib.load()
+    if args.pair:
+        return bench_pairs(args, lib)
     conv_fn = lib.rvcb200_op_rbconv_tc if args.rb else lib.rvcb200_op_conv_tc
     dev = torch.device("cuda", 0)
     stages = [(256, args.T * 12), (128, args.T * 120), (64, args.T * 240), (32, args.T * 480)]
