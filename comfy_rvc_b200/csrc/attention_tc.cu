@@ -132,7 +132,8 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmEk,
                     const __grid_constant__ CUtensorMap tmEv) {
   extern __shared__ unsigned char smem_raw[];
-  AttSmem& sm = *reinterpret_cast<AttSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned by pointer arithmetic on the __shared__ array: keeps the shared address space (LDS/STS, not generic LD/ST)
+  AttSmem& sm = *reinterpret_cast<AttSmem*>(smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;

@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmY) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned with pointer arithmetic on the __shared__ array (not through an integer cast): the compiler keeps the
+  // shared address space and emits LDS/STS instead of generic LD/ST for every access derived from it
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   const int halo = (p.ntaps - 1) * p.dil;
@@ -185,7 +187,8 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   uint64_t* acc_empty = acc_full + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   // 16-bit output staging (tma_out): [8 warps][2 slots][32 rows x 64 B], SWIZZLE_64B
-  unsigned char* sE = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sE = reinterpret_cast<unsigned char*>(tmem_slot + 4);
+  sE += (1024u - (smem_u32(sE) & 1023u)) & 1023u;
 
   const int n_mt = (p.Lj + BM - 1) / BM;
   const int n_nt = p.Cout_total / p.N;

@@ -95,7 +95,9 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmY) {
   using K = RbCfg<C, NTAPS, DIL, MSUB>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned with pointer arithmetic on the __shared__ array (not through an integer cast): the compiler keeps the
+  // shared address space and emits LDS/STS instead of generic LD/ST for every access derived from it
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;                                       // [NA][SLAB_ROWS][128 B] swizzled
   unsigned char* sW = sA + (size_t)K::NA * K::A_BYTES;            // [NB][C][128 B] swizzled
   unsigned char* sE = sW + (size_t)K::NB * K::W_BYTES;            // [8 warps][2 residual + OUT_SLOTS output boxes][2 KB]

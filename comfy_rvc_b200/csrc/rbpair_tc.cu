@@ -17,12 +17,17 @@
 // group takes the residual from the activation slab that is still in shared memory (x = r > 0 ? r : 10 r, the
 // lrelu-domain stream of DESIGN.md §3), so the residual costs no second global read.
 //
-// Pipeline per CTA (persistent, 1 CTA/SM): TMA producer warp (3-slot slab ring), one MMA warp issuing
-// conv1(i+1) before conv2(i) so the tensor pipe works while epilogue 1 turns accumulator i into h, two accumulator
-// buffers per convolution in TMEM (4 x MSUB x C columns), 4 + 4 epilogue warps.
+// Pipeline per CTA (persistent, 1 CTA/SM): TMA producer warp (NA-slot slab ring), one MMA warp issuing conv1 LA tiles
+// ahead of conv2 (conv1(i+LA) before conv2(i)) so the tensor pipe works while epilogue 1 turns accumulator i into h,
+// LA+1 conv1 accumulators and 2 conv2 accumulators in TMEM, NH h tiles, 4 + 4 epilogue warps.  A slab slot is released
+// only when epilogue 2 has read the residual from it, i.e. a whole conv1 -> h -> conv2 -> epilogue chain after it was
+// loaded: with the 3 slots of the first version the HBM latency of the next slab load sat on the critical path
+// (profiles/r1_pair_shapes_v1.jsonl: 2.6 TB/s, 490 TFLOP/s on C = 64, k = 3), hence small tiles and deep rings.
 // Arithmetic is that of two rbconv_tc launches (same MMA order, same rounding points): the op-level test compares
 // the outputs bit for bit.
 #include "tc_ptx.cuh"
+
+#include <cstdlib>
 
 namespace rvc {
 namespace {
@@ -31,14 +36,25 @@ using namespace tc;
 
 constexpr int kPairThreads = 64 + 32 * 8;   // TMA producer warp, MMA warp, 4 h-epilogue warps, 4 output-epilogue warps
 constexpr int kPairBox = 2048;              // one output staging box: 32 rows x 32 channels x 16 bit, SWIZZLE_64B
-constexpr int kPairNA = 3;                  // slab ring: conv1(i+2) is loading while epilogue 2 still reads slab i
+constexpr int kPairSmemMax = 227 * 1024;
+
+// Pipeline shape of one instantiation: rows per tile, h tiles, conv1 look-ahead, output staging slots per warp.
+struct PairSel { int msub, nh, la, out_slots; };
+constexpr PairSel pair_sel(int C, int NTAPS, int variant) {
+  if (C == 64) {
+    if (NTAPS == 3) return variant == 0 ? PairSel{1, 2, 2, 2} : PairSel{1, 3, 2, 2};
+    return PairSel{1, 1, 1, 1};                                              // k = 7: 112 KB of weights
+  }
+  if (NTAPS == 3) return variant == 0 ? PairSel{2, 1, 1, 2} : PairSel{2, 2, 1, 1};
+  return variant == 0 ? PairSel{1, 2, 2, 2} : PairSel{1, 3, 2, 2};
+}
 
 struct PairPlan {
-  int tile_m, out_rows, halo, r, nbox, rb, a_bytes, h_rows, h_bytes, w_bytes, epi_bytes, nbar, smem;
+  int tile_m, out_rows, halo, r, nbox, rb, a_bytes, h_rows, h_bytes, w_bytes, epi_bytes, nb1, fixed, na, nbar, smem;
 };
-constexpr PairPlan pair_plan(int C, int NTAPS, int DIL, int MSUB) {
+constexpr PairPlan pair_plan(int C, int NTAPS, int DIL, PairSel s) {
   PairPlan q{};
-  q.tile_m = MSUB * 128;
+  q.tile_m = s.msub * 128;
   q.out_rows = q.tile_m - (NTAPS - 1);
   q.halo = (NTAPS - 1) * DIL;
   q.r = q.tile_m + q.halo;
@@ -48,15 +64,15 @@ constexpr PairPlan pair_plan(int C, int NTAPS, int DIL, int MSUB) {
   q.h_rows = (q.tile_m + NTAPS - 1 + 7) & ~7;
   q.h_bytes = q.h_rows * 128;
   q.w_bytes = C * 128;
-  q.epi_bytes = 4 * 2 * kPairBox;
-  q.nbar = 2 * kPairNA + 1 + 8 + 2;
-  q.smem = 1024 + kPairNA * q.a_bytes + q.h_bytes + 2 * NTAPS * q.w_bytes + q.epi_bytes + 2 * C * 4 + 8 * q.nbar + 64;
+  q.epi_bytes = 4 * s.out_slots * s.msub * (C / 32) * kPairBox;      // [4 warps][sets][boxes of a tile][2 KB]
+  q.nb1 = s.la + 1;
+  q.fixed = 1024 + s.nh * q.h_bytes + 2 * NTAPS * q.w_bytes + q.epi_bytes + 2 * C * 4 + 8 * (2 * 6 + 1 + 2 * q.nb1 + 4 + 2 * s.nh) + 64;
+  q.na = (kPairSmemMax - q.fixed) / q.a_bytes;
+  if (q.na > 6) q.na = 6;
+  q.nbar = 2 * q.na + 1 + 2 * q.nb1 + 4 + 2 * s.nh;
+  q.smem = q.fixed + q.na * q.a_bytes;
   return q;
 }
-constexpr bool pair_fits(int C, int NTAPS, int DIL, int MSUB) {
-  return pair_plan(C, NTAPS, DIL, MSUB).smem <= 227 * 1024 && 4 * MSUB * C <= 512;
-}
-constexpr int pair_msub(int C, int NTAPS, int DIL) { return pair_fits(C, NTAPS, DIL, 2) ? 2 : 1; }
 
 struct PairParams {
   const float* bias1;
@@ -70,9 +86,16 @@ struct PairParams {
   float div, out_slope, res_neg_scale;
 };
 
-template <int C, int NTAPS, int DIL, int MSUB>
+template <int C, int NTAPS, int DIL, int VAR>
 struct PairCfg {
-  static constexpr PairPlan P = pair_plan(C, NTAPS, DIL, MSUB);
+  static constexpr PairSel S = pair_sel(C, NTAPS, VAR);
+  static constexpr PairPlan P = pair_plan(C, NTAPS, DIL, S);
+  static constexpr int MSUB = S.msub;
+  static constexpr int NH = S.nh;                          // h tiles
+  static constexpr int LA = S.la;                          // conv1 runs LA tiles ahead of conv2
+  static constexpr int NB1 = P.nb1;                        // conv1 accumulator buffers
+  static constexpr int NA = P.na;                          // slab ring
+  static constexpr int OUT_SLOTS = S.out_slots;
   static constexpr int KS = C / 16;                        // K=16 MMA steps (C <= 64: one 128-byte swizzled row)
   static constexpr int OUT_ROWS = P.out_rows;
   static constexpr int P2 = (NTAPS - 1) / 2;               // "same" padding of conv2 (dilation 1)
@@ -84,21 +107,32 @@ struct PairCfg {
   static constexpr uint32_t W_BYTES = (uint32_t)P.w_bytes;
   static constexpr int EPI_BYTES = P.epi_bytes;
   static constexpr int ACC_COLS = MSUB * C;                // one accumulator buffer
-  static constexpr int TMEM_COLS = 4 * ACC_COLS;           // conv1 x 2, conv2 x 2
+  static constexpr int ACC_USED = (NB1 + 2) * ACC_COLS;    // conv1 x NB1, conv2 x 2
+  static constexpr int TMEM_COLS = ACC_USED <= 32 ? 32 : ACC_USED <= 64 ? 64 : ACC_USED <= 128 ? 128 : ACC_USED <= 256 ? 256 : 512;
   static constexpr size_t SMEM = (size_t)P.smem;
   static constexpr int TAIL_ROWS = 32 - (NTAPS - 1);       // valid rows of a tile's last 32-row output box
+  static constexpr int CPS = C / 32;                       // 32-column epilogue chunks per 128-row sub-tile
+  static constexpr int NCH = MSUB * CPS;                   // ... per tile and warp
+  static constexpr int GCH = NCH >= 2 ? 2 : 1;             // chunks whose TMEM loads are issued together
   static_assert(C == 32 || C == 64, "C");
-  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS >= 32, "TMEM columns");
-  static_assert(SMEM <= 227 * 1024, "shared memory");
+  static_assert(ACC_USED <= 512, "TMEM columns");
+  static_assert(NA >= LA + 2, "slab ring too small for the conv1 look-ahead");
+  static_assert(SMEM <= (size_t)kPairSmemMax, "shared memory");
   static_assert(RB <= 256 && A_BYTES % 1024 == 0 && H_BYTES % 1024 == 0 && W_BYTES % 1024 == 0, "box");
-  static_assert(NTAPS - 1 < 32, "tail box");
+  static_assert(NTAPS - 1 < 32 && NCH % GCH == 0 && NCH <= 2, "tail box / chunk groups / epilogue registers");
 };
+
+struct Ring { uint32_t i, ph; };
+template <int N>
+__device__ __forceinline__ void ring_next(Ring& r) {
+  if (++r.i == (uint32_t)N) { r.i = 0; r.ph ^= 1u; }
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
       "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -107,35 +141,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int C, int NTAPS, int DIL, int MSUB>
+template <int C, int NTAPS, int DIL, int VAR>
 __global__ void __launch_bounds__(kPairThreads, 1)
 rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
                  const __grid_constant__ CUtensorMap tmYt) {
-  using K = PairCfg<C, NTAPS, DIL, MSUB>;
+  using K = PairCfg<C, NTAPS, DIL, VAR>;
+  constexpr int MSUB = K::MSUB, NA = K::NA, NH = K::NH, LA = K::LA, NB1 = K::NB1;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // aligned with pointer arithmetic on the __shared__ array (not through an integer cast): the compiler keeps the
+  // shared address space and emits LDS/STS instead of generic LD/ST for every access derived from it
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* sA = smem;                                       // [NA][slab rows][128 B] swizzled (TMA)
-  unsigned char* sH = sA + (size_t)kPairNA * K::A_BYTES;          // [H_ROWS][128 B] swizzled (written by epilogue 1)
-  unsigned char* sW1 = sH + K::H_BYTES;                           // [NTAPS][C][128 B] swizzled
+  unsigned char* sH = sA + (size_t)NA * K::A_BYTES;               // [NH][H_ROWS][128 B] swizzled (written by epilogue 1)
+  unsigned char* sW1 = sH + (size_t)NH * K::H_BYTES;              // [NTAPS][C][128 B] swizzled
   unsigned char* sW2 = sW1 + (size_t)NTAPS * K::W_BYTES;
-  unsigned char* sE = sW2 + (size_t)NTAPS * K::W_BYTES;           // [4 warps][2 output boxes][2 KB]
+  unsigned char* sE = sW2 + (size_t)NTAPS * K::W_BYTES;           // [4 warps][OUT_SLOTS sets][NCH output boxes][2 KB]
   float* sbias1 = reinterpret_cast<float*>(sE + K::EPI_BYTES);
   float* sbias2 = sbias1 + C;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias2 + C);
   uint64_t* a_full = bars;                  // [NA]
-  uint64_t* a_empty = a_full + kPairNA;     // [NA]  conv1 MMAs done (1) + the 4 output-epilogue warps (residual reads)
-  uint64_t* w_full = a_empty + kPairNA;     // [1]
-  uint64_t* acc1_full = w_full + 1;         // [2]
-  uint64_t* acc1_empty = acc1_full + 2;     // [2]
-  uint64_t* acc2_full = acc1_empty + 2;     // [2]
+  uint64_t* a_empty = a_full + NA;          // [NA]  conv1 MMAs done (1) + the 4 output-epilogue warps (residual reads)
+  uint64_t* w_full = a_empty + NA;          // [1]
+  uint64_t* acc1_full = w_full + 1;         // [NB1]
+  uint64_t* acc1_empty = acc1_full + NB1;   // [NB1]
+  uint64_t* acc2_full = acc1_empty + NB1;   // [2]
   uint64_t* acc2_empty = acc2_full + 2;     // [2]
-  uint64_t* h_full = acc2_empty + 2;        // [1]  epilogue 1 has written h (4 warps)
-  uint64_t* h_empty = h_full + 1;           // [1]  conv2 MMAs have read h
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + 1);
+  uint64_t* h_full = acc2_empty + 2;        // [NH]  epilogue 1 has written h (4 warps)
+  uint64_t* h_empty = h_full + NH;          // [NH]  conv2 MMAs have read h
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_empty + NH);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,14 +181,11 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
 
   if (threadIdx.x == 0) {
     pdl_trigger();
-    for (int i = 0; i < kPairNA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 5); }
+    for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 5); }
     mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 4);
-      mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 4);
-    }
-    mbar_init(h_full, 4);
-    mbar_init(h_empty, 1);
+    for (int i = 0; i < NB1; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&acc1_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 4); }
+    for (int i = 0; i < NH; ++i) { mbar_init(&h_full[i], 4); mbar_init(&h_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -164,8 +198,8 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = threadIdx.x; i < C; i += kPairThreads) { sbias1[i] = p.bias1[i]; sbias2[i] = p.bias2[i]; }
-  // rows [TILE_M, H_ROWS) of the h tile are only ever read for output rows that are discarded; keep them finite
-  for (int i = threadIdx.x; i < (int)(K::H_BYTES / 16); i += kPairThreads)
+  // rows [TILE_M, H_ROWS) of an h tile are only ever read for output rows that are discarded; keep them finite
+  for (int i = threadIdx.x; i < (int)((size_t)NH * K::H_BYTES / 16); i += kPairThreads)
     reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
@@ -183,22 +217,22 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
         tma_load_2d(sW2 + (size_t)tap * K::W_BYTES, &tmW2, 0, tap * C, w_full);
       }
       pdl_wait();                                    // the stream comes from the previous kernel (weights do not)
-      int sa = 0;
-      uint32_t pa = 1;
+      Ring ra{0u, 0u};
 #pragma unroll 1
       for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const unsigned b = tile / n_mt, mt = tile - b * n_mt;
         const int row0 = (int)mt * K::OUT_ROWS - K::P2 - K::P1;
-        mbar_wait(&a_empty[sa], pa);
-        mbar_expect_tx(&a_full[sa], K::A_BYTES);
+        mbar_wait(&a_empty[ra.i], ra.ph ^ 1u);
+        mbar_expect_tx(&a_full[ra.i], K::A_BYTES);
 #pragma unroll
         for (int j = 0; j < K::NBOX; ++j)
-          tma_load_3d(sA + (size_t)sa * K::A_BYTES + (size_t)j * K::RB * 128, &tmA, 0, row0 + j * K::RB, (int)b, &a_full[sa]);
-        if (++sa == kPairNA) { sa = 0; pa ^= 1; }
+          tma_load_3d(sA + (size_t)ra.i * K::A_BYTES + (size_t)j * K::RB * 128, &tmA, 0, row0 + j * K::RB, (int)b,
+                      &a_full[ra.i]);
+        ring_next<NA>(ra);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (warp-uniform, one elected lane): conv1(0), conv1(1), conv2(0), conv1(2), conv2(1), ... =====
+    // ===== MMA issuer (warp-uniform, one elected lane): conv1(i + LA) is issued before conv2(i) =====
     const uint32_t leader = elect_one() ? 1u : 0u;
     // instruction descriptor: D=F32 @4, A/B format @7/@10, K-major both, N>>3 @17, M>>4 @24
     const uint32_t f1 = p.fmt1 ? 1u : 0u, f2 = p.fmt2 ? 1u : 0u;
@@ -211,94 +245,104 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
     const uint32_t sW1_d = __shfl_sync(0xffffffffu, d_lo0 + (smem_u32(sW1) >> 4), 0);
     const uint32_t sW2_d = __shfl_sync(0xffffffffu, d_lo0 + (smem_u32(sW2) >> 4), 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t n_my = __shfl_sync(0xffffffffu, (total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x, 0);
     mbar_wait(w_full, 0);
     tc_fence_after();
-    auto conv2 = [&](uint32_t j) {                   // h of my j-th tile is in sH
-      const uint32_t buf = j & 1u;
-      mbar_wait(h_full, j & 1u);
-      mbar_wait(&acc2_empty[buf], ((j >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_u + (uint32_t)(2 * K::ACC_COLS) + buf * (uint32_t)K::ACC_COLS;
-#pragma unroll
-      for (int tap = 0; tap < NTAPS; ++tap) {
-        const uint32_t b_d = sW2_d + (uint32_t)tap * (K::W_BYTES >> 4);
-#pragma unroll
-        for (int ms = 0; ms < MSUB; ++ms) {
-#pragma unroll
-          for (int ks = 0; ks < K::KS; ++ks)
-            tc_mma_f16_pred(d_tmem + (uint32_t)(ms * C), sH_d + (uint32_t)(((ms * 128 + tap) * 128 + ks * 32) >> 4), d_hi,
-                            b_d + (uint32_t)((ks * 32) >> 4), d_hi, idesc2, (tap | ks) != 0 ? 1u : 0u, leader);
-        }
-      }
-      tc_commit_pred(h_empty, leader);
-      tc_commit_pred(&acc2_full[buf], leader);
-    };
-    int sa = 0;
-    uint32_t pa = 0;
-    uint32_t it = 0;
+    Ring ra{0u, 0u}, r1{0u, 0u}, rh{0u, 0u}, r2{0u, 0u};
 #pragma unroll 1
-    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const uint32_t buf = it & 1u;
-      mbar_wait(&acc1_empty[buf], ((it >> 1) & 1u) ^ 1u);
-      mbar_wait(&a_full[sa], pa);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_u + buf * (uint32_t)K::ACC_COLS;
-      const uint32_t a_d = sA_d + (uint32_t)sa * (K::A_BYTES >> 4);
+    for (uint32_t it = 0; it < n_my + (uint32_t)LA; ++it) {
+      if (it < n_my) {                                // conv1 of my tile `it`
+        mbar_wait(&acc1_empty[r1.i], r1.ph ^ 1u);
+        mbar_wait(&a_full[ra.i], ra.ph);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + r1.i * (uint32_t)K::ACC_COLS;
+        const uint32_t a_d = sA_d + ra.i * (K::A_BYTES >> 4);
 #pragma unroll
-      for (int tap = 0; tap < NTAPS; ++tap) {
-        const uint32_t b_d = sW1_d + (uint32_t)tap * (K::W_BYTES >> 4);
+        for (int tap = 0; tap < NTAPS; ++tap) {
+          const uint32_t b_d = sW1_d + (uint32_t)tap * (K::W_BYTES >> 4);
 #pragma unroll
-        for (int ms = 0; ms < MSUB; ++ms) {
+          for (int ms = 0; ms < MSUB; ++ms) {
 #pragma unroll
-          for (int ks = 0; ks < K::KS; ++ks)
-            tc_mma_f16_pred(d_tmem + (uint32_t)(ms * C), a_d + (uint32_t)(((ms * 128 + tap * DIL) * 128 + ks * 32) >> 4), d_hi,
-                            b_d + (uint32_t)((ks * 32) >> 4), d_hi, idesc1, (tap | ks) != 0 ? 1u : 0u, leader);
+            for (int ks = 0; ks < K::KS; ++ks)
+              tc_mma_f16_pred(d_tmem + (uint32_t)(ms * C), a_d + (uint32_t)(((ms * 128 + tap * DIL) * 128 + ks * 32) >> 4), d_hi,
+                              b_d + (uint32_t)((ks * 32) >> 4), d_hi, idesc1, (tap | ks) != 0 ? 1u : 0u, leader);
+          }
         }
+        tc_commit_pred(&a_empty[ra.i], leader);
+        tc_commit_pred(&acc1_full[r1.i], leader);
+        ring_next<NA>(ra);
+        ring_next<NB1>(r1);
       }
-      tc_commit_pred(&a_empty[sa], leader);
-      tc_commit_pred(&acc1_full[buf], leader);
-      if (++sa == kPairNA) { sa = 0; pa ^= 1; }
-      if (it > 0) conv2(it - 1);
+      if (it >= (uint32_t)LA) {                       // conv2 of my tile `it - LA`: its h is in sH[rh.i]
+        mbar_wait(&h_full[rh.i], rh.ph);
+        mbar_wait(&acc2_empty[r2.i], r2.ph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_u + ((uint32_t)NB1 + r2.i) * (uint32_t)K::ACC_COLS;
+        const uint32_t h_d = sH_d + rh.i * (K::H_BYTES >> 4);
+#pragma unroll
+        for (int tap = 0; tap < NTAPS; ++tap) {
+          const uint32_t b_d = sW2_d + (uint32_t)tap * (K::W_BYTES >> 4);
+#pragma unroll
+          for (int ms = 0; ms < MSUB; ++ms) {
+#pragma unroll
+            for (int ks = 0; ks < K::KS; ++ks)
+              tc_mma_f16_pred(d_tmem + (uint32_t)(ms * C), h_d + (uint32_t)(((ms * 128 + tap) * 128 + ks * 32) >> 4), d_hi,
+                              b_d + (uint32_t)((ks * 32) >> 4), d_hi, idesc2, (tap | ks) != 0 ? 1u : 0u, leader);
+          }
+        }
+        tc_commit_pred(&h_empty[rh.i], leader);
+        tc_commit_pred(&acc2_full[r2.i], leader);
+        ring_next<NH>(rh);
+        ring_next<2>(r2);
+      }
       __syncwarp();
     }
-    if (it > 0) conv2(it - 1);
-    __syncwarp();
   } else if (warp < 6) {
     // ============ epilogue 1: conv1 accumulator -> h = lrelu(. + b1) in the operand format of conv2 -> sH ============
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
     const bool hbf = p.fmt2 != 0;
     const float hs = p.h_slope;
-    uint32_t j = 0;
+    Ring r1{0u, 0u}, rh{0u, 0u};
 #pragma unroll 1
-    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
-      const unsigned b = tile / n_mt, mt = tile - b * n_mt;
-      (void)b;
+    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const unsigned mt = tile % n_mt;
       const int th0 = (int)mt * K::OUT_ROWS - K::P2 + qd * 32 + lane;     // time index of this lane's h row (sub-tile 0)
-      const uint32_t buf = j & 1u;
-      mbar_wait(&acc1_full[buf], (j >> 1) & 1u);
-      mbar_wait(h_empty, (j & 1u) ^ 1u);             // conv2 of the previous tile has consumed sH
+      mbar_wait(&acc1_full[r1.i], r1.ph);
+      mbar_wait(&h_empty[rh.i], rh.ph ^ 1u);         // conv2 of the tile that last used this h tile has consumed it
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * (uint32_t)K::ACC_COLS;
-#pragma unroll 1
-      for (int ms = 0; ms < MSUB; ++ms) {
-        const int hrow = ms * 128 + qd * 32 + lane;
-        const int th = th0 + ms * 128;
-        const bool ok = th >= 0 && th < p.L;         // conv2 pads h with zeros outside [0, L)
-        unsigned char* hp = sH + (size_t)hrow * 128;
-        const uint32_t sx = (uint32_t)hrow & 7u;
+      const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + r1.i * (uint32_t)K::ACC_COLS;
+      unsigned char* hbuf = sH + (size_t)rh.i * K::H_BYTES;
 #pragma unroll
-        for (int cc = 0; cc < C / 32; ++cc) {
-          uint32_t r[32];
-          tmem_ld32(tbase + (uint32_t)(ms * C + cc * 32), r);
+      for (int g0 = 0; g0 < K::NCH; g0 += K::GCH) {
+        uint32_t r[K::GCH][32];
+#pragma unroll
+        for (int u = 0; u < K::GCH; ++u) {
+          const int ci = g0 + u, ms = ci / K::CPS, cc = ci - ms * K::CPS;
+          tmem_ld32_issue(tbase + (uint32_t)(ms * C + cc * 32), r[u]);
+        }
+        tmem_ld_wait();
+        if (g0 + K::GCH >= K::NCH) {                  // the accumulator is in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc1_empty[r1.i]);
+        }
+#pragma unroll
+        for (int u = 0; u < K::GCH; ++u) {
+          const int ci = g0 + u, ms = ci / K::CPS, cc = ci - ms * K::CPS;
+          const int hrow = ms * 128 + qd * 32 + lane;
+          const int th = th0 + ms * 128;
+          const bool ok = th >= 0 && th < p.L;       // conv2 pads h with zeros outside [0, L)
+          unsigned char* hp = hbuf + (size_t)hrow * 128;
+          const uint32_t sx = (uint32_t)hrow & 7u;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             float v[8];
             const float4 b0 = *reinterpret_cast<const float4*>(sbias1 + cc * 32 + k * 8);
             const float4 b1 = *reinterpret_cast<const float4*>(sbias1 + cc * 32 + k * 8 + 4);
-            v[0] = __uint_as_float(r[k * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[k * 8 + 1]) + b0.y;
-            v[2] = __uint_as_float(r[k * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[k * 8 + 3]) + b0.w;
-            v[4] = __uint_as_float(r[k * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[k * 8 + 5]) + b1.y;
-            v[6] = __uint_as_float(r[k * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[k * 8 + 7]) + b1.w;
+            v[0] = __uint_as_float(r[u][k * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[u][k * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(r[u][k * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[u][k * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(r[u][k * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[u][k * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(r[u][k * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[u][k * 8 + 7]) + b1.w;
             uint4 o;
             o.x = pack2(hbf, lrelu(v[0], hs), lrelu(v[1], hs)); o.y = pack2(hbf, lrelu(v[2], hs), lrelu(v[3], hs));
             o.z = pack2(hbf, lrelu(v[4], hs), lrelu(v[5], hs)); o.w = pack2(hbf, lrelu(v[6], hs), lrelu(v[7], hs));
@@ -307,13 +351,18 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
           }
         }
       }
-      tc_fence_before();
       fence_proxy_async();                           // generic-proxy writes of sH -> visible to the MMA (async proxy)
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&acc1_empty[buf]); mbar_arrive(h_full); }
+      if (lane == 0) mbar_arrive(&h_full[rh.i]);
+      ring_next<NB1>(r1);
+      ring_next<NH>(rh);
     }
   } else {
     // ===== epilogue 2: conv2 accumulator + b2 + residual (from the slab) -> branch sum / 16-bit stream (TMA boxes) =====
+    // The warps of this group are the busiest of the CTA (profiles/r1_ncu_rbpair_v2.md: 94 % of their samples are not
+    // barrier waits), so the branch-sum words (global loads) are in registers BEFORE the accumulator barrier is waited
+    // for, the accumulator is handed back as soon as it is in registers, and the tile's output boxes share one proxy
+    // fence and one bulk group.
     pdl_wait();
     const int ew = warp - 6;
     const int qd = warp & 3;
@@ -325,65 +374,76 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
     const bool has_y16 = p.y16 != nullptr;
     const bool has_acc = p.y32 != nullptr;
     const bool do_acc = has_acc && p.accum != 0;
-    unsigned char* my_stage = sE + (size_t)ew * 2 * kPairBox;
+    unsigned char* my_stage = sE + (size_t)ew * K::OUT_SLOTS * K::NCH * kPairBox;   // [OUT_SLOTS sets][NCH boxes]
     const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = ((uint32_t)lane >> 1) & 3u;   // SWIZZLE_64B staging box
-    uint32_t ocnt = 0;
-    uint32_t j = 0;
-    int sa = 0;
-    uint32_t pa = 0;
+    uint32_t oset = 0;
+    Ring r2{0u, 0u}, ra{0u, 0u};
 #pragma unroll 1
-    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const unsigned b = tile / n_mt, mt = tile - b * n_mt;
       const int o0 = (int)mt * K::OUT_ROWS;
       const int wj0 = qd * 32;                                    // first in-tile row of this warp's group (sub-tile 0)
-      const uint32_t buf = j & 1u;
       unsigned char* acc = has_acc ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (C / 8) * pitch_o : nullptr;
-      const unsigned char* slab = sA + (size_t)sa * K::A_BYTES;
-      constexpr int CPS = C / 32;                                 // 32-column chunks per 128-row sub-tile
-      constexpr int NCH = MSUB * CPS;
-      uint4 aq[2][4];                                             // branch-sum words, fetched one chunk ahead
-      auto load_acc = [&](int ci, int slot) {
-        const int ms = ci / CPS, c0 = (ci - ms * CPS) * 32;
-        const int jl = ms * 128 + wj0 + lane;
-        if (jl < K::OUT_ROWS && o0 + jl < p.L) {
-          const unsigned char* q = acc + (size_t)(c0 / 8) * pitch_o + (size_t)(o0 + jl + p.padf) * 16;
+      const unsigned char* slab = sA + (size_t)ra.i * K::A_BYTES;
+      uint4 aq[K::NCH][4];                                        // branch-sum words of this lane's rows
+      if (do_acc) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) aq[slot][k] = *reinterpret_cast<const uint4*>(q + (size_t)k * pitch_o);
+        for (int ci = 0; ci < K::NCH; ++ci) {
+          const int ms = ci / K::CPS, c0 = (ci - ms * K::CPS) * 32;
+          const int jl = ms * 128 + wj0 + lane;
+          if (jl < K::OUT_ROWS && o0 + jl < p.L) {
+            const unsigned char* q = acc + (size_t)(c0 / 8) * pitch_o + (size_t)(o0 + jl + p.padf) * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) aq[ci][k] = *reinterpret_cast<const uint4*>(q + (size_t)k * pitch_o);
+          }
         }
-      };
-      if (do_acc) load_acc(0, 0);
-      mbar_wait(&acc2_full[buf], (j >> 1) & 1u);
-      mbar_wait(&a_full[sa], pa);                                 // (long complete: orders the slab reads after the TMA writes)
+      }
+      mbar_wait(&a_full[ra.i], ra.ph);                            // (long complete: orders the slab reads after the TMA writes)
+      mbar_wait(&acc2_full[r2.i], r2.ph);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(2 * K::ACC_COLS) + buf * (uint32_t)K::ACC_COLS;
+      const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + ((uint32_t)NB1 + r2.i) * (uint32_t)K::ACC_COLS;
+      uint32_t r[K::NCH][32];
 #pragma unroll
-      for (int ci = 0; ci < NCH; ++ci) {
-        const int ms = ci / CPS, cc = ci - ms * CPS, c0 = cc * 32;
+      for (int ci = 0; ci < K::NCH; ++ci) {
+        const int ms = ci / K::CPS, cc = ci - ms * K::CPS;
+        tmem_ld32_issue(tbase + (uint32_t)(ms * C + cc * 32), r[ci]);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&acc2_empty[r2.i]);                           // the accumulator is in registers
+        if (has_y16) bulk_wait_read<K::OUT_SLOTS - 1>();          // the bulk group that last used this staging set has read it
+      }
+      __syncwarp();
+      unsigned char* stage = my_stage + (size_t)oset * K::NCH * kPairBox;
+#pragma unroll
+      for (int ci = 0; ci < K::NCH; ++ci) {
+        const int ms = ci / K::CPS, cc = ci - ms * K::CPS, c0 = cc * 32;
         const int jl = ms * 128 + wj0 + lane;                     // in-tile output row of this lane
         const int row = o0 + jl;
         const bool row_ok = jl < K::OUT_ROWS && row < p.L;
-        const int srow = jl + K::P2 + K::P1;                      // the same time step inside the activation slab
-        const unsigned char* rp = slab + (size_t)srow * 128;
-        const uint32_t rx = (uint32_t)srow & 7u;
-        if (do_acc && ci + 1 < NCH) load_acc(ci + 1, (ci + 1) & 1);
-        uint32_t r[32];
-        tmem_ld32(tbase + (uint32_t)(ms * C + c0), r);
         float v[32];
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           const float4 bq = *reinterpret_cast<const float4*>(sbias2 + c0 + k4 * 4);
-          v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
-          v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
-          v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
-          v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
+          v[k4 * 4 + 0] = __uint_as_float(r[ci][k4 * 4 + 0]) + bq.x;
+          v[k4 * 4 + 1] = __uint_as_float(r[ci][k4 * 4 + 1]) + bq.y;
+          v[k4 * 4 + 2] = __uint_as_float(r[ci][k4 * 4 + 2]) + bq.z;
+          v[k4 * 4 + 3] = __uint_as_float(r[ci][k4 * 4 + 3]) + bq.w;
         }
+        {
+          const int srow = jl + K::P2 + K::P1;                    // this lane's time step inside the activation slab
+          const unsigned char* rp = slab + (size_t)srow * 128;
+          const uint32_t rx = (uint32_t)srow & 7u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          add_res8(v + k * 8, *reinterpret_cast<const uint4*>(rp + ((((uint32_t)(cc * 4 + k)) ^ rx) << 4)), neg_scale);
+          for (int k = 0; k < 4; ++k)
+            add_res8(v + k * 8, *reinterpret_cast<const uint4*>(rp + ((((uint32_t)(cc * 4 + k)) ^ rx) << 4)), neg_scale);
+        }
         if (has_acc) {
           if (do_acc && row_ok) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) add_res8(v + k * 8, aq[ci & 1][k], 1.f);
+            for (int k = 0; k < 4; ++k) add_res8(v + k * 8, aq[ci][k], 1.f);
           }
           if (inv_div != 1.f) {
 #pragma unroll
@@ -404,35 +464,39 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
           for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
         }
         if (has_y16) {
-          uint4 o[4];
+          // this lane's row of the [32 rows][32 channels] staging box of chunk ci (conflict-free under the swizzle)
+          unsigned char* box = stage + ci * kPairBox + sw_row;
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
-            o[k8].x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
-            o[k8].y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
-            o[k8].z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
-            o[k8].w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
+            uint4 o;
+            o.x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
+            o.y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
+            o.z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
+            o.w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
+            *reinterpret_cast<uint4*>(box + ((((uint32_t)k8) ^ sw_x) << 4)) = o;
           }
-          // stage the [32 rows][32 channels] box, then one lane stores it (rows >= L are clipped by the tensor map;
-          // the tile's last box holds only TAIL_ROWS valid rows and goes through the shorter tensor-map box)
-          unsigned char* box = my_stage + (ocnt & 1u) * kPairBox;
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(box + sw_row + ((((uint32_t)k) ^ sw_x) << 4)) = o[k];
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            const bool tail = ms == MSUB - 1 && qd == 3;
-            tma_store_3d(tail ? &tmYt : &tmY, box, c0, o0 + ms * 128 + wj0, (int)b);
-            bulk_commit();
-          }
-          ++ocnt;
         }
       }
-      tc_fence_before();
+      if (has_y16) {
+        // one lane stores the tile's boxes (rows >= L are clipped by the tensor map; the tile's last 32-row box holds only
+        // TAIL_ROWS valid rows and goes through the shorter tensor-map box)
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int ci = 0; ci < K::NCH; ++ci) {
+            const int ms = ci / K::CPS, cc = ci - ms * K::CPS;
+            const bool tail = ms == MSUB - 1 && qd == 3;
+            tma_store_3d(tail ? &tmYt : &tmY, stage + ci * kPairBox, cc * 32, o0 + ms * 128 + wj0, (int)b);
+          }
+          bulk_commit();
+        }
+        if (++oset == (uint32_t)K::OUT_SLOTS) oset = 0;
+      }
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&acc2_empty[buf]); mbar_arrive(&a_empty[sa]); }
-      if (++sa == kPairNA) { sa = 0; pa ^= 1; }
+      if (lane == 0) mbar_arrive(&a_empty[ra.i]);                 // the residual rows of this slab have been read
+      ring_next<2>(r2);
+      ring_next<NA>(ra);
     }
     if (lane == 0) bulk_wait_all();                 // staged stores complete before the CTA's smem goes away
   }
@@ -459,9 +523,9 @@ EncodeTiledFn pair_encode_tiled() {
   return fn;
 }
 
-template <int C, int NTAPS, int DIL, int MSUB>
+template <int C, int NTAPS, int DIL, int VAR>
 cudaError_t launch_pair_one(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st) {
-  using K = PairCfg<C, NTAPS, DIL, MSUB>;
+  using K = PairCfg<C, NTAPS, DIL, VAR>;
   EncodeTiledFn enc = pair_encode_tiled();
   if (!enc) return cudaErrorNotSupported;
   CUtensorMap tmA, tmW1, tmW2, tmY, tmYt;
@@ -501,7 +565,7 @@ cudaError_t launch_pair_one(const TcConvDesc& d1, const TcConvDesc& d2, int B, c
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rbpair_tc_kernel<C, NTAPS, DIL, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(rbpair_tc_kernel<C, NTAPS, DIL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)K::SMEM);
     if (e != cudaSuccess) return e;
     configured = true;
@@ -522,20 +586,31 @@ cudaError_t launch_pair_one(const TcConvDesc& d1, const TcConvDesc& d2, int B, c
   p.div = d2.div; p.out_slope = d2.out_slope; p.res_neg_scale = d2.res_neg_scale;
   const long long tiles = (long long)((L + K::OUT_ROWS - 1) / K::OUT_ROWS) * B;
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
-  cudaError_t le = launch_pdl(rbpair_tc_kernel<C, NTAPS, DIL, MSUB>, dim3(grid), dim3(kPairThreads), K::SMEM, st, p, tmA, tmW1,
+  cudaError_t le = launch_pdl(rbpair_tc_kernel<C, NTAPS, DIL, VAR>, dim3(grid), dim3(kPairThreads), K::SMEM, st, p, tmA, tmW1,
                               tmW2, tmY, tmYt);
   launch_counter().n++;
   return le != cudaSuccess ? le : cudaGetLastError();
 }
 
-template <int C, int NTAPS>
+// RVCB200_PAIR_CFG=1 selects the alternative pipeline shape of pair_sel() (A/B measurements, tools/bench_conv_tc.py --pair)
+int pair_variant() {
+  const char* e = getenv("RVCB200_PAIR_CFG");
+  return e ? atoi(e) : 0;
+}
+
+template <int C, int NTAPS, int VAR>
 cudaError_t launch_pair_d(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st) {
   switch (d1.dil) {
-    case 1: return launch_pair_one<C, NTAPS, 1, pair_msub(C, NTAPS, 1)>(d1, d2, B, st);
-    case 3: return launch_pair_one<C, NTAPS, 3, pair_msub(C, NTAPS, 3)>(d1, d2, B, st);
-    case 5: return launch_pair_one<C, NTAPS, 5, pair_msub(C, NTAPS, 5)>(d1, d2, B, st);
+    case 1: return launch_pair_one<C, NTAPS, 1, VAR>(d1, d2, B, st);
+    case 3: return launch_pair_one<C, NTAPS, 3, VAR>(d1, d2, B, st);
+    case 5: return launch_pair_one<C, NTAPS, 5, VAR>(d1, d2, B, st);
     default: return cudaErrorNotSupported;
   }
+}
+
+template <int C, int NTAPS>
+cudaError_t launch_pair_v(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st) {
+  return pair_variant() == 1 ? launch_pair_d<C, NTAPS, 1>(d1, d2, B, st) : launch_pair_d<C, NTAPS, 0>(d1, d2, B, st);
 }
 
 }  // namespace
@@ -558,8 +633,8 @@ bool rbpair_tc_supported(const TcConvDesc& d1, const TcConvDesc& d2) {
 
 cudaError_t launch_rbpair_tc(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st) {
   if (!rbpair_tc_supported(d1, d2) || B <= 0) return cudaErrorNotSupported;
-  if (d1.Cin == 32) return d1.ntaps == 3 ? launch_pair_d<32, 3>(d1, d2, B, st) : launch_pair_d<32, 7>(d1, d2, B, st);
-  return d1.ntaps == 3 ? launch_pair_d<64, 3>(d1, d2, B, st) : launch_pair_d<64, 7>(d1, d2, B, st);
+  if (d1.Cin == 32) return d1.ntaps == 3 ? launch_pair_v<32, 3>(d1, d2, B, st) : launch_pair_v<32, 7>(d1, d2, B, st);
+  return d1.ntaps == 3 ? launch_pair_v<64, 3>(d1, d2, B, st) : launch_pair_v<64, 7>(d1, d2, B, st);
 }
 
 }  // namespace rvc

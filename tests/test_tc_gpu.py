@@ -233,13 +233,15 @@ def _pair_descs(x16, h16, y16, xs, w1, w2, b1, b2, L, Cc, ntaps, dil, kind, bf16
     return d1, d2
 
 
+@pytest.mark.parametrize("variant", ["0", "1"], ids=["cfg0", "cfg1"])
 @pytest.mark.parametrize("kind", ["s", "a", "af"])
 @pytest.mark.parametrize("bf16", [False, True], ids=["fp16", "bf16"])
 @pytest.mark.parametrize("case", PAIR_CASES, ids=[c[0] for c in PAIR_CASES])
-def test_rbpair_tc(case, bf16, kind):
+def test_rbpair_tc(case, bf16, kind, variant, monkeypatch):
     """Fused ResBlock1 pair (rbpair_tc.cu) is bit-identical to the two rbconv_tc launches it replaces, and both match
     the fp64 restatement.  kind s: 16-bit stream out; a: planar fp16 branch sum (accumulate, /3); af: both."""
     name, B, L, Cc, ntaps, dil = case
+    monkeypatch.setenv("RVCB200_PAIR_CFG", variant)        # both pipeline shapes of rbpair_tc.cu (pair_sel)
     dev = torch.device("cuda", 0)
     lib = _lib.load()
     dt2 = torch.bfloat16 if bf16 else torch.float16
