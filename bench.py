@@ -57,9 +57,15 @@ def algorithmic_macs(cfg, T: int) -> dict:
             "enc_linear": enc_lin, "attention": attn}
 
 
+def pair_is_fused(C: int, k: int) -> bool:
+    """ResBlock1 pairs that run as ONE kernel with h in shared memory (csrc/rbpair_tc.cu: rbpair_tc_supported)."""
+    return os.environ.get("RVCB200_FUSE_PAIRS", "1") != "0" and C in (32, 64) and k in (3, 7)
+
+
 def resblock_bytes(cfg, T: int):
     """Algorithmic HBM bytes (read, write) of the decoder resblock convolutions of one item on the tensor path
-    (one fp16 stream copy, h as one 16-bit tensor, planar fp16 branch sum)."""
+    (one fp16 stream copy, h as one 16-bit tensor -- or not at all where the pair is fused --, planar fp16
+    branch sum)."""
     rd = wr = 0
     L, C = T, cfg.upsample_initial_channel
     nk = len(cfg.resblock_kernel_sizes)
@@ -69,7 +75,9 @@ def resblock_bytes(cfg, T: int):
         last_stage = i == len(cfg.upsample_rates) - 1
         for j, ds in enumerate(cfg.resblock_dilation_sizes):
             for d_i in range(len(ds)):
-                if cfg.resblock == "1":
+                if cfg.resblock == "1" and pair_is_fused(C, cfg.resblock_kernel_sizes[j]):
+                    rd += 2 * E                                   # fused pair: stream in (h and the residual stay on the SM)
+                elif cfg.resblock == "1":
                     rd += 2 * E; wr += 2 * E                      # conv1: stream in, h out
                     rd += 4 * E                                   # conv2: h + residual from the stream
                 else:
@@ -333,11 +341,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": T * cfg.upp * 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "decoder resblock convolutions (rbconv_tc_kernel on tcgen05; conv_f32_kernel in fp32 mode)",
+        "roofline": {"bound": "tensor", "kernel": "decoder resblock convolutions (rbconv_tc_kernel + fused-pair rbpair_tc_kernel on tcgen05; conv_f32_kernel in fp32 mode)",
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                     "traffic": rb_traffic, "traffic_note": "dram__bytes_read+write per launch, average over the 72 launches of a step: "
-                     "algorithmic bytes x the read/write ratios ncu measured on 12 sampled launches (profiles/r1_ncu_rbconv_v10.md: "
-                     "reads 1.001 x algorithmic, writes 0.80 x -- the rest is still dirty in L2 at kernel end)",
+                     "traffic": rb_traffic, "traffic_note": "dram__bytes_read+write per launch, average over the class's launches of a step: "
+                     "algorithmic bytes x the read/write ratios ncu measured on sampled launches (profiles/r1_ncu_rbconv_v10.md, "
+                     "r1_ncu_rbpair_v2.md: reads 1.001 x algorithmic, writes 0.77-0.80 x -- the rest is still dirty in L2 at kernel end)",
                      "algorithmic_bytes_per_launch": rb_bytes, "achieved_hbm_gbs": rb_bytes / (conv_ms_per_launch * 1e-3) / 1e9,
                      "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": rb_bytes / (conv_ms_per_launch * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "peak_source": peaks["src"],

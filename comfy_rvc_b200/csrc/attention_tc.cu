@@ -27,7 +27,8 @@ namespace {
 constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 3, MAXREL = 21;
 constexpr int kThreadsAtt = 192;
 // TMEM columns
-constexpr uint32_t TM_S = 0, TM_O = 64, TM_R = 160, TM_COLS = 256;
+// two S buffers: Q K^T of key tile t+1 is issued while the softmax warps still work on tile t
+constexpr uint32_t TM_S = 0, TM_O = 64, TM_R = 160, TM_S2 = 192, TM_COLS = 256;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
@@ -158,8 +159,8 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   uint64_t* v_full = &sm.bars[7];        // [NSTG]
   uint64_t* v_empty = &sm.bars[10];      // [NSTG]
   uint64_t* r_full = &sm.bars[13];
-  uint64_t* s_full = &sm.bars[14];
-  uint64_t* s_empty = &sm.bars[15];      // 4 softmax warps
+  uint64_t* s_full = &sm.bars[20];       // [2]
+  uint64_t* s_empty = &sm.bars[22];      // [2], 4 softmax warps each
   uint64_t* p_full = &sm.bars[16];       // 4 softmax warps
   uint64_t* p_empty = &sm.bars[17];
   uint64_t* pb_full = &sm.bars[18];      // 4 softmax warps
@@ -168,7 +169,8 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   if (threadIdx.x == 0) {
     bar_init(q_full, 1);
     for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); bar_init(&v_full[i], 1); bar_init(&v_empty[i], 1); }
-    bar_init(r_full, 1); bar_init(s_full, 1); bar_init(s_empty, 4); bar_init(p_full, 4); bar_init(p_empty, 1);
+    bar_init(r_full, 1); bar_init(p_full, 4); bar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) { bar_init(&s_full[i], 1); bar_init(&s_empty[i], 4); }
     bar_init(pb_full, 4); bar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -227,47 +229,50 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
     }
     __syncwarp();
     int ks_ = 0, vs_ = 0;
-    uint32_t kp = 0, vp = 0, sp = 1, pp = 0;
+    uint32_t kp = 0, vp = 0, pp = 0;
     uint32_t o_acc = 0;
-    int it = 0;
-    for (int pass = 0; pass < 2; ++pass)
-      for (int t = 0; t < ntiles; ++t, ++it) {
-        bar_wait(&k_full[ks_], kp);
-        bar_wait(s_empty, sp);            // softmax has read the previous S tile out of TMEM
-        sp ^= 1;
+    const int total = 2 * ntiles;                       // pass 0 (row max) then pass 1 (probabilities, P V)
+    auto issue_qk = [&](int it) {                       // S[it & 1] = Q K^T of key tile it % ntiles
+      const int buf = it & 1;
+      bar_wait(&k_full[ks_], kp);
+      bar_wait(&s_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);   // softmax has read this buffer's previous tile out of TMEM
+      fence_after();
+      if (elect1()) {
+        uint32_t acc = 0;
+        for (int ks = 0; ks < 6; ++ks) {
+          const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
+          const uint32_t b_lo = desc_lo(s_u32(sm.k[ks_][ks >> 2])) + 2u * (ks & 3);
+          mma_f16(tmem + (buf ? TM_S2 : TM_S), a_lo, b_lo, kDescHi, id_s, acc);
+          acc = 1;
+        }
+        commit(&s_full[buf]);
+        commit(&k_empty[ks_]);
+      }
+      __syncwarp();
+      if (++ks_ == NSTG) { ks_ = 0; kp ^= 1; }
+    };
+    issue_qk(0);
+    for (int it = 0; it < total; ++it) {
+      if (it + 1 < total) issue_qk(it + 1);             // one tile ahead of the softmax warps
+      if (it >= ntiles) {
+        bar_wait(p_full, pp);             // probabilities of this tile are in smem
+        pp ^= 1;
+        bar_wait(&v_full[vs_], vp);
         fence_after();
         if (elect1()) {
-          uint32_t acc = 0;
-          for (int ks = 0; ks < 6; ++ks) {
-            const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
-            const uint32_t b_lo = desc_lo(s_u32(sm.k[ks_][ks >> 2])) + 2u * (ks & 3);
-            mma_f16(tmem + TM_S, a_lo, b_lo, kDescHi, id_s, acc);
-            acc = 1;
+          const uint32_t p_lo = desc_lo(s_u32(sm.p)), v_lo = desc_lo(s_u32(sm.v[vs_]));
+          for (int ks = 0; ks < BKV / 16; ++ks) {
+            mma_f16(tmem + TM_O, p_lo + 2u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
+            o_acc = 1;
           }
-          commit(s_full);
-          commit(&k_empty[ks_]);
+          commit(p_empty);
+          commit(&v_empty[vs_]);
         }
         __syncwarp();
-        if (++ks_ == NSTG) { ks_ = 0; kp ^= 1; }
-        if (pass == 1) {
-          bar_wait(p_full, pp);           // probabilities of this tile are in smem
-          pp ^= 1;
-          bar_wait(&v_full[vs_], vp);
-          fence_after();
-          if (elect1()) {
-            const uint32_t p_lo = desc_lo(s_u32(sm.p)), v_lo = desc_lo(s_u32(sm.v[vs_]));
-            for (int ks = 0; ks < BKV / 16; ++ks) {
-              mma_f16(tmem + TM_O, p_lo + 2u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
-              o_acc = 1;
-            }
-            commit(p_empty);
-            commit(&v_empty[vs_]);
-          }
-          __syncwarp();
-          o_acc = 1;
-          if (++vs_ == NSTG) { vs_ = 0; vp ^= 1; }
-        }
+        o_acc = 1;
+        if (++vs_ == NSTG) { vs_ = 0; vp ^= 1; }
       }
+    }
     // O += Pband Ev  (K = 32: two MMAs)
     bar_wait(pb_full, 0);
     fence_after();
@@ -293,21 +298,21 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
       for (int r = 0; r < 24; ++r) sm.rtab[row * 24 + r] = rv[r];
     }
     float mx = -INFINITY, lsum = 0.f;
-    uint32_t sfp = 0, pep = 1;
-    const bool band_any_lo = true;
-    (void)band_any_lo;
+    uint32_t pep = 1;
+    int it = 0;
     for (int pass = 0; pass < 2; ++pass)
-      for (int t = 0; t < ntiles; ++t) {
+      for (int t = 0; t < ntiles; ++t, ++it) {
         const int j0 = t * BKV;
-        bar_wait(s_full, sfp);
-        sfp ^= 1;
+        const int buf = it & 1;
+        bar_wait(&s_full[buf], ((uint32_t)it >> 1) & 1u);
         fence_after();
         float s[BKV];
-        tmem_ld32(tmem + lane_base + TM_S, s);
-        tmem_ld32(tmem + lane_base + TM_S + 32, s + 32);
+        const uint32_t ts = tmem + lane_base + (buf ? TM_S2 : TM_S);
+        tmem_ld32(ts, s);
+        tmem_ld32(ts + 32, s + 32);
         fence_before();
         __syncwarp();
-        if (lane == 0) bar_arrive(s_empty);             // S is in registers: the next Q K^T may overwrite TMEM
+        if (lane == 0) bar_arrive(&s_empty[buf]);       // S is in registers: a later Q K^T may overwrite this buffer
         const bool band = j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window;
         if (band) {
 #pragma unroll

@@ -392,10 +392,10 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
             uint4 o[4];
 #pragma unroll
             for (int k8 = 0; k8 < 4; ++k8) {
-              o[k8].x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
-              o[k8].y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
-              o[k8].z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
-              o[k8].w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
+              o[k8].x = pack2(obf, lrelu_max(v[k8 * 8 + 0], slope), lrelu_max(v[k8 * 8 + 1], slope));
+              o[k8].y = pack2(obf, lrelu_max(v[k8 * 8 + 2], slope), lrelu_max(v[k8 * 8 + 3], slope));
+              o[k8].z = pack2(obf, lrelu_max(v[k8 * 8 + 4], slope), lrelu_max(v[k8 * 8 + 5], slope));
+              o[k8].w = pack2(obf, lrelu_max(v[k8 * 8 + 6], slope), lrelu_max(v[k8 * 8 + 7], slope));
             }
             if (K::EPI_TMA) {
               // stage the [32 rows][32 channels] box, then one lane stores it (rows >= L are clipped by the tensor map)
@@ -537,6 +537,8 @@ bool rbconv_tc_supported(const TcConvDesc& d) {
   if (d.g_off[0] != -((d.ntaps - 1) / 2) * d.dil) return false;
   if ((d.accum && !d.y32) || !d.x16 || !d.w16 || !d.bias || d.a_fp16) return false;
   if (d.res32 || (d.y32 && !d.acc_f16)) return false;      // fp32 planar residual / output: generic kernel only
+  // the epilogue computes lrelu as max(v, v * slope) and the residual expansion as min(r, r * scale)
+  if (!(d.out_slope > 0.f && d.out_slope <= 1.f) || !(d.res_neg_scale == 0.f || d.res_neg_scale >= 1.f)) return false;
   return true;
 }
 

@@ -34,19 +34,22 @@ namespace {
 
 using namespace tc;
 
-constexpr int kPairThreads = 64 + 32 * 8;   // TMA producer warp, MMA warp, 4 h-epilogue warps, 4 output-epilogue warps
+// threads: TMA producer warp, MMA warp, 4 h-epilogue warps, E2G x 4 output-epilogue warps
+constexpr int pair_threads(int e2g) { return 64 + 32 * (4 + 4 * e2g); }
 constexpr int kPairBox = 2048;              // one output staging box: 32 rows x 32 channels x 16 bit, SWIZZLE_64B
 constexpr int kPairSmemMax = 227 * 1024;
 
 // Pipeline shape of one instantiation: rows per tile, h tiles, conv1 look-ahead, output staging slots per warp.
-struct PairSel { int msub, nh, la, out_slots; };
+struct PairSel { int msub, nh, la, out_slots, e2g; };
 constexpr PairSel pair_sel(int C, int NTAPS, int variant) {
   if (C == 64) {
-    if (NTAPS == 3) return variant == 0 ? PairSel{1, 2, 2, 2} : PairSel{1, 3, 2, 2};
-    return PairSel{1, 1, 1, 1};                                              // k = 7: 112 KB of weights
+    if (NTAPS == 3) return variant == 0 ? PairSel{1, 2, 2, 1, 2} : PairSel{1, 3, 2, 1, 2};
+    // k = 7: 112 KB of weights, bound by MMA issue (profiles/r1_pair_shapes_v4_*.jsonl): one output-epilogue group, the
+    // shared memory of the second group's staging goes to a fourth slab instead
+    return variant == 0 ? PairSel{1, 1, 1, 1, 1} : PairSel{1, 1, 1, 1, 2};
   }
-  if (NTAPS == 3) return variant == 0 ? PairSel{2, 1, 1, 2} : PairSel{2, 2, 1, 1};
-  return variant == 0 ? PairSel{1, 2, 2, 2} : PairSel{1, 3, 2, 2};
+  if (NTAPS == 3) return variant == 0 ? PairSel{2, 1, 1, 1, 2} : PairSel{1, 2, 2, 1, 2};
+  return variant == 0 ? PairSel{1, 2, 2, 1, 2} : PairSel{1, 2, 2, 2, 1};
 }
 
 struct PairPlan {
@@ -64,7 +67,7 @@ constexpr PairPlan pair_plan(int C, int NTAPS, int DIL, PairSel s) {
   q.h_rows = (q.tile_m + NTAPS - 1 + 7) & ~7;
   q.h_bytes = q.h_rows * 128;
   q.w_bytes = C * 128;
-  q.epi_bytes = 4 * s.out_slots * s.msub * (C / 32) * kPairBox;      // [4 warps][sets][boxes of a tile][2 KB]
+  q.epi_bytes = 4 * s.e2g * s.out_slots * s.msub * (C / 32) * kPairBox;      // [warps][sets][boxes of a tile][2 KB]
   q.nb1 = s.la + 1;
   q.fixed = 1024 + s.nh * q.h_bytes + 2 * NTAPS * q.w_bytes + q.epi_bytes + 2 * C * 4 + 8 * (2 * 6 + 1 + 2 * q.nb1 + 4 + 2 * s.nh) + 64;
   q.na = (kPairSmemMax - q.fixed) / q.a_bytes;
@@ -96,6 +99,8 @@ struct PairCfg {
   static constexpr int NB1 = P.nb1;                        // conv1 accumulator buffers
   static constexpr int NA = P.na;                          // slab ring
   static constexpr int OUT_SLOTS = S.out_slots;
+  static constexpr int E2G = S.e2g;                        // output-epilogue groups (alternate tiles)
+  static constexpr int THREADS = pair_threads(S.e2g);
   static constexpr int KS = C / 16;                        // K=16 MMA steps (C <= 64: one 128-byte swizzled row)
   static constexpr int OUT_ROWS = P.out_rows;
   static constexpr int P2 = (NTAPS - 1) / 2;               // "same" padding of conv2 (dilation 1)
@@ -116,7 +121,7 @@ struct PairCfg {
   static constexpr int GCH = NCH >= 2 ? 2 : 1;             // chunks whose TMEM loads are issued together
   static_assert(C == 32 || C == 64, "C");
   static_assert(ACC_USED <= 512, "TMEM columns");
-  static_assert(NA >= LA + 2, "slab ring too small for the conv1 look-ahead");
+  static_assert(NA >= LA + 2 && NA >= 2, "slab ring too small for the conv1 look-ahead");
   static_assert(SMEM <= (size_t)kPairSmemMax, "shared memory");
   static_assert(RB <= 256 && A_BYTES % 1024 == 0 && H_BYTES % 1024 == 0 && W_BYTES % 1024 == 0, "box");
   static_assert(NTAPS - 1 < 32 && NCH % GCH == 0 && NCH <= 2, "tail box / chunk groups / epilogue registers");
@@ -145,7 +150,7 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int C, int NTAPS, int DIL, int VAR>
-__global__ void __launch_bounds__(kPairThreads, 1)
+__global__ void __launch_bounds__(pair_threads(pair_sel(C, NTAPS, VAR).e2g), 1)
 rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
                  const __grid_constant__ CUtensorMap tmYt) {
@@ -159,7 +164,7 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
   unsigned char* sH = sA + (size_t)NA * K::A_BYTES;               // [NH][H_ROWS][128 B] swizzled (written by epilogue 1)
   unsigned char* sW1 = sH + (size_t)NH * K::H_BYTES;              // [NTAPS][C][128 B] swizzled
   unsigned char* sW2 = sW1 + (size_t)NTAPS * K::W_BYTES;
-  unsigned char* sE = sW2 + (size_t)NTAPS * K::W_BYTES;           // [4 warps][OUT_SLOTS sets][NCH output boxes][2 KB]
+  unsigned char* sE = sW2 + (size_t)NTAPS * K::W_BYTES;           // [4 E2G warps][OUT_SLOTS sets][NCH output boxes][2 KB]
   float* sbias1 = reinterpret_cast<float*>(sE + K::EPI_BYTES);
   float* sbias2 = sbias1 + C;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sbias2 + C);
@@ -197,9 +202,9 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
                  "r"((uint32_t)K::TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < C; i += kPairThreads) { sbias1[i] = p.bias1[i]; sbias2[i] = p.bias2[i]; }
+  for (int i = threadIdx.x; i < C; i += K::THREADS) { sbias1[i] = p.bias1[i]; sbias2[i] = p.bias2[i]; }
   // rows [TILE_M, H_ROWS) of an h tile are only ever read for output rows that are discarded; keep them finite
-  for (int i = threadIdx.x; i < (int)((size_t)NH * K::H_BYTES / 16); i += kPairThreads)
+  for (int i = threadIdx.x; i < (int)((size_t)NH * K::H_BYTES / 16); i += K::THREADS)
     reinterpret_cast<uint4*>(sH)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
@@ -344,8 +349,8 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
             v[4] = __uint_as_float(r[u][k * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[u][k * 8 + 5]) + b1.y;
             v[6] = __uint_as_float(r[u][k * 8 + 6]) + b1.z; v[7] = __uint_as_float(r[u][k * 8 + 7]) + b1.w;
             uint4 o;
-            o.x = pack2(hbf, lrelu(v[0], hs), lrelu(v[1], hs)); o.y = pack2(hbf, lrelu(v[2], hs), lrelu(v[3], hs));
-            o.z = pack2(hbf, lrelu(v[4], hs), lrelu(v[5], hs)); o.w = pack2(hbf, lrelu(v[6], hs), lrelu(v[7], hs));
+            o.x = pack2(hbf, lrelu_max(v[0], hs), lrelu_max(v[1], hs)); o.y = pack2(hbf, lrelu_max(v[2], hs), lrelu_max(v[3], hs));
+            o.z = pack2(hbf, lrelu_max(v[4], hs), lrelu_max(v[5], hs)); o.w = pack2(hbf, lrelu_max(v[6], hs), lrelu_max(v[7], hs));
             if (!ok) o = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(hp + ((((uint32_t)(cc * 4 + k)) ^ sx) << 4)) = o;
           }
@@ -363,8 +368,10 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
     // barrier waits), so the branch-sum words (global loads) are in registers BEFORE the accumulator barrier is waited
     // for, the accumulator is handed back as soon as it is in registers, and the tile's output boxes share one proxy
     // fence and one bulk group.
+    // E2G groups of 4 warps take alternate tiles (group g: my tiles g, g + E2G, ...).
     pdl_wait();
     const int ew = warp - 6;
+    const uint32_t eg = (uint32_t)(warp - 6) >> 2;
     const int qd = warp & 3;
     const size_t pitch_o = (size_t)p.Lp_out * 16;   // bytes per planar-vector plane
     const bool obf = p.out_bf16 != 0;
@@ -377,9 +384,10 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
     unsigned char* my_stage = sE + (size_t)ew * K::OUT_SLOTS * K::NCH * kPairBox;   // [OUT_SLOTS sets][NCH boxes]
     const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = ((uint32_t)lane >> 1) & 3u;   // SWIZZLE_64B staging box
     uint32_t oset = 0;
-    Ring r2{0u, 0u}, ra{0u, 0u};
+    Ring r2{eg & 1u, 0u};                                         // accumulator buffer of my tile: (g + E2G n) mod 2
+    Ring ra{eg % (uint32_t)NA, 0u};                               // slab slot of my tile: (g + E2G n) mod NA
 #pragma unroll 1
-    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (unsigned tile = blockIdx.x + eg * gridDim.x; tile < total_tiles; tile += K::E2G * gridDim.x) {
       const unsigned b = tile / n_mt, mt = tile - b * n_mt;
       const int o0 = (int)mt * K::OUT_ROWS;
       const int wj0 = qd * 32;                                    // first in-tile row of this warp's group (sub-tile 0)
@@ -402,20 +410,10 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
       mbar_wait(&acc2_full[r2.i], r2.ph);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + ((uint32_t)NB1 + r2.i) * (uint32_t)K::ACC_COLS;
-      uint32_t r[K::NCH][32];
-#pragma unroll
-      for (int ci = 0; ci < K::NCH; ++ci) {
-        const int ms = ci / K::CPS, cc = ci - ms * K::CPS;
-        tmem_ld32_issue(tbase + (uint32_t)(ms * C + cc * 32), r[ci]);
+      if (has_y16) {
+        if (lane == 0) bulk_wait_read<K::OUT_SLOTS - 1>();        // the bulk group that last used this staging set has read it
+        __syncwarp();
       }
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&acc2_empty[r2.i]);                           // the accumulator is in registers
-        if (has_y16) bulk_wait_read<K::OUT_SLOTS - 1>();          // the bulk group that last used this staging set has read it
-      }
-      __syncwarp();
       unsigned char* stage = my_stage + (size_t)oset * K::NCH * kPairBox;
 #pragma unroll
       for (int ci = 0; ci < K::NCH; ++ci) {
@@ -423,14 +421,22 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
         const int jl = ms * 128 + wj0 + lane;                     // in-tile output row of this lane
         const int row = o0 + jl;
         const bool row_ok = jl < K::OUT_ROWS && row < p.L;
+        uint32_t r[32];                                           // one chunk at a time: 128 registers per thread at 448 threads
+        tmem_ld32_issue(tbase + (uint32_t)(ms * C + c0), r);
+        tmem_ld_wait();
+        if (ci == K::NCH - 1) {                                   // the accumulator is in registers: hand it back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc2_empty[r2.i]);
+        }
         float v[32];
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           const float4 bq = *reinterpret_cast<const float4*>(sbias2 + c0 + k4 * 4);
-          v[k4 * 4 + 0] = __uint_as_float(r[ci][k4 * 4 + 0]) + bq.x;
-          v[k4 * 4 + 1] = __uint_as_float(r[ci][k4 * 4 + 1]) + bq.y;
-          v[k4 * 4 + 2] = __uint_as_float(r[ci][k4 * 4 + 2]) + bq.z;
-          v[k4 * 4 + 3] = __uint_as_float(r[ci][k4 * 4 + 3]) + bq.w;
+          v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
+          v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
+          v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
+          v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
         }
         {
           const int srow = jl + K::P2 + K::P1;                    // this lane's time step inside the activation slab
@@ -469,10 +475,10 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
 #pragma unroll
           for (int k8 = 0; k8 < 4; ++k8) {
             uint4 o;
-            o.x = pack2(obf, lrelu(v[k8 * 8 + 0], slope), lrelu(v[k8 * 8 + 1], slope));
-            o.y = pack2(obf, lrelu(v[k8 * 8 + 2], slope), lrelu(v[k8 * 8 + 3], slope));
-            o.z = pack2(obf, lrelu(v[k8 * 8 + 4], slope), lrelu(v[k8 * 8 + 5], slope));
-            o.w = pack2(obf, lrelu(v[k8 * 8 + 6], slope), lrelu(v[k8 * 8 + 7], slope));
+            o.x = pack2(obf, lrelu_max(v[k8 * 8 + 0], slope), lrelu_max(v[k8 * 8 + 1], slope));
+            o.y = pack2(obf, lrelu_max(v[k8 * 8 + 2], slope), lrelu_max(v[k8 * 8 + 3], slope));
+            o.z = pack2(obf, lrelu_max(v[k8 * 8 + 4], slope), lrelu_max(v[k8 * 8 + 5], slope));
+            o.w = pack2(obf, lrelu_max(v[k8 * 8 + 6], slope), lrelu_max(v[k8 * 8 + 7], slope));
             *reinterpret_cast<uint4*>(box + ((((uint32_t)k8) ^ sw_x) << 4)) = o;
           }
         }
@@ -495,8 +501,8 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_empty[ra.i]);                 // the residual rows of this slab have been read
-      ring_next<2>(r2);
-      ring_next<NA>(ra);
+#pragma unroll
+      for (int e = 0; e < K::E2G; ++e) { ring_next<2>(r2); ring_next<NA>(ra); }
     }
     if (lane == 0) bulk_wait_all();                 // staged stores complete before the CTA's smem goes away
   }
@@ -586,7 +592,7 @@ cudaError_t launch_pair_one(const TcConvDesc& d1, const TcConvDesc& d2, int B, c
   p.div = d2.div; p.out_slope = d2.out_slope; p.res_neg_scale = d2.res_neg_scale;
   const long long tiles = (long long)((L + K::OUT_ROWS - 1) / K::OUT_ROWS) * B;
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
-  cudaError_t le = launch_pdl(rbpair_tc_kernel<C, NTAPS, DIL, VAR>, dim3(grid), dim3(kPairThreads), K::SMEM, st, p, tmA, tmW1,
+  cudaError_t le = launch_pdl(rbpair_tc_kernel<C, NTAPS, DIL, VAR>, dim3(grid), dim3(K::THREADS), K::SMEM, st, p, tmA, tmW1,
                               tmW2, tmY, tmYt);
   launch_counter().n++;
   return le != cudaSuccess ? le : cudaGetLastError();

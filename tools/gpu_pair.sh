@@ -5,7 +5,7 @@
 set -x
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests/test_tc_gpu.py -x -q --timeout 90 --timeout-method=thread -k "rbpair or rbconv or conv_tc" > gpurun_out/test_pair.log 2>&1
+timeout 900 python -m pytest tests/test_tc_gpu.py -x -q --timeout 90 --timeout-method=thread -k "rbpair or rbconv or conv_tc or attention" > gpurun_out/test_pair.log 2>&1
 rc=$?; echo "pair op tests rc=$rc" | tee gpurun_out/status.txt; tail -15 gpurun_out/test_pair.log
 if [ $rc -ne 0 ]; then
   timeout 300 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_tc_gpu.py -x -q --timeout 250 --timeout-method=thread -k "rbpair_tc and pair_c32_k3_d1 and fp16-s" > gpurun_out/sanitizer_pair.log 2>&1
