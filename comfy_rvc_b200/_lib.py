@@ -69,6 +69,7 @@ class TcConvDesc(C.Structure):
         ("out_len", C.c_void_p), ("dbg_alt", C.c_int32),
         ("res16", C.c_void_p), ("res_neg_scale", C.c_float), ("a_fp16", C.c_int32), ("acc_f16", C.c_int32),
         ("tma_out", C.c_int32),
+        ("tanh_out", C.c_void_p), ("acc_nostore", C.c_int32),
     ]
 
 

@@ -14,7 +14,9 @@
 //
 // Operands (all K-major, TMA + SWIZZLE_128B): qk16 [B][T][512] = q(h0|h1) k(h0|h1), 128 channels per head
 // (96 + zero pad); vt16 [B*heads][128][Tp] = V transposed (keys contiguous); ek16 [32][128]; evt16 [128][64].
-// Warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax (thread = query row = TMEM lane).
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax: thread = query row = TMEM lane, two warps per lane quadrant,
+// each owning 32 of a key tile's 64 columns (the per-tile softmax chain is what bounds the kernel; row max and row sum
+// are exchanged through shared memory once per pass).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -25,7 +27,8 @@ namespace rvc {
 namespace {
 
 constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 3, MAXREL = 21;
-constexpr int kThreadsAtt = 192;
+constexpr int kThreadsAtt = 64 + 256;
+constexpr int HC = BKV / 2;           // key columns of a tile per softmax warp
 // TMEM columns
 // two S buffers: Q K^T of key tile t+1 is issued while the softmax warps still work on tile t
 constexpr uint32_t TM_S = 0, TM_O = 64, TM_R = 160, TM_S2 = 192, TM_COLS = 256;
@@ -118,6 +121,7 @@ struct AttSmem {                        // 1024-byte aligned tiles, all [rows][1
   unsigned char ek[2][32 * 128];
   unsigned char evt[DKP * 128];
   float rtab[BQ * 24];                  // relative-key logits per query row (dynamic indexing)
+  float xch[2][2][BQ];                  // [max | sum][column half][row]: exchanged between the two warps of a row
   uint64_t bars[32];
   uint32_t tmem_slot;
 };
@@ -160,18 +164,18 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   uint64_t* v_empty = &sm.bars[10];      // [NSTG]
   uint64_t* r_full = &sm.bars[13];
   uint64_t* s_full = &sm.bars[20];       // [2]
-  uint64_t* s_empty = &sm.bars[22];      // [2], 4 softmax warps each
-  uint64_t* p_full = &sm.bars[16];       // 4 softmax warps
+  uint64_t* s_empty = &sm.bars[22];      // [2], 8 softmax warps each
+  uint64_t* p_full = &sm.bars[16];       // 8 softmax warps
   uint64_t* p_empty = &sm.bars[17];
-  uint64_t* pb_full = &sm.bars[18];      // 4 softmax warps
+  uint64_t* pb_full = &sm.bars[18];      // 8 softmax warps
   uint64_t* o_full = &sm.bars[19];
 
   if (threadIdx.x == 0) {
     bar_init(q_full, 1);
     for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); bar_init(&v_full[i], 1); bar_init(&v_empty[i], 1); }
-    bar_init(r_full, 1); bar_init(p_full, 4); bar_init(p_empty, 1);
-    for (int i = 0; i < 2; ++i) { bar_init(&s_full[i], 1); bar_init(&s_empty[i], 4); }
-    bar_init(pb_full, 4); bar_init(o_full, 1);
+    bar_init(r_full, 1); bar_init(p_full, 8); bar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) { bar_init(&s_full[i], 1); bar_init(&s_empty[i], 8); }
+    bar_init(pb_full, 8); bar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -285,55 +289,60 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   } else {
     // ======================================= softmax warps ======================================
     const int qd = warp & 3;
+    const int half = (warp - 2) >> 2;                   // which 32 of a key tile's 64 columns this warp owns
     const int row = qd * 32 + lane;                     // TMEM lane = query row in the tile
     const int qi = q0 + row;
     const uint32_t lane_base = ((uint32_t)(qd * 32) << 16);
-    // relative-key logits of this row -> smem (dynamic indexing by key offset)
+    // relative-key logits of this row -> smem (dynamic indexing by key offset); written by the row's first warp
     bar_wait(r_full, 0);
     fence_after();
-    {
+    if (half == 0) {
       float rv[32];
       tmem_ld32(tmem + lane_base + TM_R, rv);
 #pragma unroll
       for (int r = 0; r < 24; ++r) sm.rtab[row * 24 + r] = rv[r];
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 softmax warps
     float mx = -INFINITY, lsum = 0.f;
     uint32_t pep = 1;
     int it = 0;
-    for (int pass = 0; pass < 2; ++pass)
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) {                                  // row max over both column halves
+        sm.xch[0][half][row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(mx, sm.xch[0][half ^ 1][row]);
+      }
       for (int t = 0; t < ntiles; ++t, ++it) {
-        const int j0 = t * BKV;
+        const int j0 = t * BKV + half * HC;             // first key of this warp's columns
         const int buf = it & 1;
         bar_wait(&s_full[buf], ((uint32_t)it >> 1) & 1u);
         fence_after();
-        float s[BKV];
-        const uint32_t ts = tmem + lane_base + (buf ? TM_S2 : TM_S);
-        tmem_ld32(ts, s);
-        tmem_ld32(ts + 32, s + 32);
+        float s[HC];
+        tmem_ld32(tmem + lane_base + (buf ? TM_S2 : TM_S) + half * HC, s);
         fence_before();
         __syncwarp();
         if (lane == 0) bar_arrive(&s_empty[buf]);       // S is in registers: a later Q K^T may overwrite this buffer
-        const bool band = j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window;
+        const bool band = j0 <= q0 + BQ - 1 + a.window && j0 + HC - 1 >= q0 - a.window;
         if (band) {
 #pragma unroll
-          for (int c = 0; c < BKV; ++c) {
+          for (int c = 0; c < HC; ++c) {
             const int r = j0 + c - qi + a.window;
             if ((unsigned)r < (unsigned)nrel) s[c] += sm.rtab[row * 24 + r];
           }
         }
-        if (j0 + BKV > L) {
+        if (j0 + HC > L) {
 #pragma unroll
-          for (int c = 0; c < BKV; ++c)
+          for (int c = 0; c < HC; ++c)
             if (j0 + c >= L) s[c] = -INFINITY;
         }
         if (pass == 0) {
 #pragma unroll
-          for (int c = 0; c < BKV; ++c) mx = fmaxf(mx, s[c]);
+          for (int c = 0; c < HC; ++c) mx = fmaxf(mx, s[c]);
         } else {
           // probabilities (fp16) -> swizzled K-major smem tile; also harvest the band for the Ev term
-          uint32_t pk[BKV / 2];
+          uint32_t pk[HC / 2];
 #pragma unroll
-          for (int c = 0; c < BKV; c += 2) {
+          for (int c = 0; c < HC; c += 2) {
             const float p0 = __expf(s[c] - mx), p1 = __expf(s[c + 1] - mx);
             lsum += p0 + p1;
             __half2 hp = __floats2half2_rn(p0, p1);
@@ -341,7 +350,7 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
           }
           if (band) {
 #pragma unroll
-            for (int c = 0; c < BKV; ++c) {
+            for (int c = 0; c < HC; ++c) {
               const int r = j0 + c - qi + a.window;
               if ((unsigned)r < (unsigned)nrel) {
                 const uint32_t w = pk[c / 2];
@@ -353,25 +362,31 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
           bar_wait(p_empty, pep);                       // the previous P V MMA has finished reading sm.p
           pep ^= 1;
 #pragma unroll
-          for (int cc = 0; cc < BKV / 8; ++cc)
-            *reinterpret_cast<uint4*>(sm.p + row * 128 + ((cc ^ (row & 7)) << 4)) =
+          for (int cc = 0; cc < HC / 8; ++cc)
+            *reinterpret_cast<uint4*>(sm.p + row * 128 + (((half * (HC / 8) + cc) ^ (row & 7)) << 4)) =
                 make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) bar_arrive(p_full);
         }
       }
+    }
     // band tile complete -> final MMA, then normalise and store
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) bar_arrive(pb_full);
+    sm.xch[1][half][row] = lsum;                        // row sum over both column halves
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    lsum += sm.xch[1][half ^ 1][row];
     bar_wait(o_full, 0);
     fence_after();
     const bool valid = qi < L;
     const float inv = valid ? 1.f / lsum : 0.f;
     __half* orow = a.out + ((size_t)b * a.T + qi) * a.H + h * DKV;
+    // output columns: the row's first warp stores [0, 64), the second [64, 96)
 #pragma unroll
     for (int c0 = 0; c0 < DKV; c0 += 32) {
+      if ((c0 < 64) != (half == 0)) continue;
       float o[32];
       tmem_ld32(tmem + lane_base + TM_O + c0, o);
       if (qi < a.T) {

@@ -805,7 +805,12 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
     // lean epilogue with a 16-bit output in whole 32-column chunks: staged + TMA-stored (see the kernel)
     d.tma_out = (!d.generic && d.y16 && d.N % 32 == 0) ? 1 : 0;
-    const size_t budget = 208 * 1024 - (d.tma_out ? kStageBytes : 0);
+    size_t budget = 208 * 1024 - (d.tma_out ? kStageBytes : 0);
+    // Launches of at most two waves (the text encoder / flow contractions, M = T rows) can be given a small ring so that
+    // the CTAs of the NEXT launch fit on the SM beside them and run their prologue under this launch's tail
+    // (programmatic dependent launch, RVCB200_PDL=1): RVCB200_SMALL_SMEM_KB=<KB> (0 = off)
+    static const int small_kb = [] { const char* e = getenv("RVCB200_SMALL_SMEM_KB"); return e ? atoi(e) : 0; }();
+    if (small_kb > 0 && tiles <= 2 * 148 && budget > (size_t)small_kb * 1024) budget = (size_t)small_kb * 1024;
     const int nw = nkb * d.ntaps;
     const int na_max = d.a_mode != 1 ? 6 : 10;
     d.b_stationary = 0;

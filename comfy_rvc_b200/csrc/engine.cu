@@ -847,6 +847,11 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       return launch_conv_tc(d, B, st);
     };
     auto tmem_cols_for = [](int N) { int c = 32; while (c < N) c <<= 1; return c; };
+    // conv_post on the specialised tcgen05 kernel (same rule as weights.post_is_tc); RVCB200_POST_TC=0: CUDA-core kernel
+    const int c_last = f.up_init_channels >> f.n_ups;
+    const bool post_tc = [] { const char* e = getenv("RVCB200_POST_TC"); return e ? atoi(e) != 0 : true; }() &&
+                         f.resblock_kind == 1 && (c_last == 32 || c_last == 64 || c_last == 128) &&
+                         ctx->tensors.count("dec.post.wt.tc") != 0 && ctx->tensors.count("dec.post.bt") != 0;
     auto tc_base = [&]() {
       TcConvDesc d;
       memset(&d, 0, sizeof(d));
@@ -978,6 +983,12 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
             const bool final_branch = j == f.n_res_kernels - 1;
             o.y32 = ACC32; o.acc_f16 = 1; o.accum = j > 0; o.div = final_branch ? (float)f.n_res_kernels : 1.f;
             if (final_branch && !last_stage) { o.y16 = N16; o.out_slope = 0.1f; }
+            if (final_branch && last_stage && post_tc) {
+              // the decoder's last tensor is consumed once, by conv_post, as lrelu_{0.01}(x) (models.py:561): it leaves as
+              // that 16-bit channels-last operand; the planar branch sum is not written back unless a test taps it
+              o.y16 = N16; o.out_slope = 0.01f;
+              o.acc_nostore = (o.accum && tp.find(S("dec.stage.%d", i).c_str()) == nullptr) ? 1 : 0;
+            }
           } else {
             o.y16 = ynew; o.out_slope = 0.1f;
           }
@@ -1000,7 +1011,18 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       void* tmp = IN16; IN16 = N16; N16 = tmp;
       Lc = Ln; Cc = Cn; LpC = LpN; (void)LpC;
     }
-    CKC(3, launch_conv_post_pv16(ACC32, W("dec.post.w"), out, B, Lc, Cc, 7, LpC, kPadF, 0.01f, st), "dec.conv_post(pv16)");
+    if (post_tc) {
+      // conv_post + tanh (models.py:562-563) on the tensor core: IN16 (after the swap) holds lrelu_{0.01}(x) in fp16
+      TcConvDesc d = tc_base();
+      d.x16 = IN16; d.L_in = (int)Lc; d.w16 = W16h("dec.post.wt"); d.bias = W("dec.post.bt");
+      d.Cin = Cc; d.ntaps = 7; d.dil = 1; d.g_off[0] = -3;
+      d.N = Cc; d.Cout_total = Cc; d.tmem_cols = tmem_cols_for(d.N);
+      d.Lj = (int)Lc; d.Lp_out = LpC; d.tanh_out = out;
+      if (!ok) return RVCB200_ERR_MISSING;
+      CKC(3, launch_rbconv_tc(d, B, st), "dec.conv_post(tc)");
+    } else {
+      CKC(3, launch_conv_post_pv16(ACC32, W("dec.post.w"), out, B, Lc, Cc, 7, LpC, kPadF, 0.01f, st), "dec.conv_post(pv16)");
+    }
   }
   if (!ok) return RVCB200_ERR_MISSING;
   ctx->last_launches = launch_counter().n - launches0;

@@ -266,6 +266,8 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
     const bool has_y16 = p.y16 != nullptr;
     const bool has_acc = p.y32 != nullptr;          // planar-vector fp16 branch sum [C/8][Lp][8]
     const bool do_acc = has_acc && p.accum != 0;
+    const bool st_acc = has_acc && p.acc_nostore == 0;
+    float* const tanh_out = p.tanh_out;             // conv_post mode: column 0 -> tanh -> fp32 [B][Lj], nothing else
     unsigned char* my_stage = sE + (size_t)ew * K::EPI_WARP_BYTES;      // [2 residual][OUT_SLOTS output] boxes
     uint64_t* my_res_full = res_full + ew * 2;
     // byte offset of this lane's 16-byte piece j inside a SWIZZLE_64B box: row = lane (64 B), piece ^= (row >> 1) & 3
@@ -341,6 +343,10 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
               : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (tanh_out) {                             // (warp-uniform) the 128 B a warp stores are contiguous
+            if (c0 == 0 && row_ok) tanh_out[(size_t)b * (size_t)p.Lj + row] = tanhf(__uint_as_float(r[0]) + sbias[0]);
+            continue;
+          }
           float v[32];
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
@@ -374,7 +380,7 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
             }
-            if (row_ok) {
+            if (row_ok && st_acc) {
               unsigned char* q = acc + (size_t)(c0 / 8) * pitch_o + (size_t)(row + p.padf) * 16;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -537,6 +543,8 @@ bool rbconv_tc_supported(const TcConvDesc& d) {
   if (d.g_off[0] != -((d.ntaps - 1) / 2) * d.dil) return false;
   if ((d.accum && !d.y32) || !d.x16 || !d.w16 || !d.bias || d.a_fp16) return false;
   if (d.res32 || (d.y32 && !d.acc_f16)) return false;      // fp32 planar residual / output: generic kernel only
+  if (d.tanh_out && (d.y16 || d.y32 || d.res16 || d.Cin > 128)) return false;       // conv_post mode: the only output
+  if (d.acc_nostore && !(d.y32 && d.accum && d.y16)) return false;
   // the epilogue computes lrelu as max(v, v * slope) and the residual expansion as min(r, r * scale)
   if (!(d.out_slope > 0.f && d.out_slope <= 1.f) || !(d.res_neg_scale == 0.f || d.res_neg_scale >= 1.f)) return false;
   return true;

@@ -85,6 +85,13 @@ def ups_is_dense(cfg: SynthConfig, i: int) -> bool:
     return u == 2 and k == 2 * u and cin in (32, 64, 128, 256)
 
 
+def post_is_tc(cfg: SynthConfig) -> bool:
+    """conv_post (k = 7, C_last -> 1) runs on the specialised tcgen05 resblock kernel when C_last is one of its channel
+    counts.  Same rule as `post_tc` in csrc/engine.cu."""
+    c_last = cfg.upsample_initial_channel >> cfg.num_upsamples
+    return c_last in (32, 64, 128) and cfg.resblock == "1"
+
+
 def pack_conv_transpose_dense(w: torch.Tensor, u: int) -> torch.Tensor:
     """ConvTranspose1d weight [C_in, C_out, k = 2u] -> ordinary conv weight [3 taps][C_in][u*C_out]: output row j of
     the dense conv holds the u phases j*u .. j*u+u-1 side by side (= the channels-last tensor [L*u][C_out] itself);
@@ -225,6 +232,13 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
                     P[f"dec.rb.{n}.c.{d}.w"] = conv_w(w[f"dec.resblocks.{n}.convs.{d}.weight"])
                     P[f"dec.rb.{n}.c.{d}.b"] = w[f"dec.resblocks.{n}.convs.{d}.bias"].contiguous()
     P["dec.post.w"] = w["dec.conv_post.weight"][0].t().contiguous()           # [k][C]
+    if post_is_tc(cfg):
+        # conv_post on the tensor core: a C -> C convolution whose output channel 0 is conv_post (no bias) and whose other
+        # output channels are zero, so it runs on the specialised resblock kernel with a tanh-of-column-0 epilogue
+        wt = P["dec.post.w"].new_zeros(P["dec.post.w"].shape[0], P["dec.post.w"].shape[1], P["dec.post.w"].shape[1])
+        wt[:, :, 0] = P["dec.post.w"]
+        P["dec.post.wt"] = wt                                                 # [k][C_in][C_out]
+        P["dec.post.bt"] = P["dec.post.w"].new_zeros(P["dec.post.w"].shape[1])
     return P, S
 
 
@@ -292,4 +306,6 @@ def tc_weight_names(cfg: SynthConfig):
                     names += [f"dec.rb.{n}.c1.{d}.w", f"dec.rb.{n}.c2.{d}.w"]
                 else:
                     names.append(f"dec.rb.{n}.c.{d}.w")
+    if post_is_tc(cfg):
+        names.append("dec.post.wt")
     return names

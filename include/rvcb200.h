@@ -199,6 +199,12 @@ typedef struct rvcb200_tc_conv_desc {
                                 * instruction on sm_100a) */
   int32_t acc_f16;             /* 1: y32 (output and `accum` input) is planar-vector fp16 [B][Cout/8][Lp_out][8] */
   int32_t tma_out;             /* filled in by the launcher: y16 leaves through swizzled staging boxes + TMA stores */
+  /* ---- decoder tail on the specialised kernel (rvcb200_op_rbconv_tc only) ---- */
+  float* tanh_out;             /* non-null: the ONLY output is tanh_out[b][row] = tanh(v[0]), fp32 [B][Lj] -- conv_post
+                                * (/root/reference/lib/infer_pack/models.py:562-563) run as a C -> C convolution whose output
+                                * channels 1.. are zero; y16 / y32 / res16 must be null */
+  int32_t acc_nostore;         /* 1: y32 is read (accum) but not written back; only y16 leaves (the last pair of the last
+                                * stage, whose branch sum is consumed once, by conv_post, as y16 = lrelu_{0.01}(.)) */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 
