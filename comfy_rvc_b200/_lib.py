@@ -70,6 +70,8 @@ class TcConvDesc(C.Structure):
         ("res16", C.c_void_p), ("res_neg_scale", C.c_float), ("a_fp16", C.c_int32), ("acc_f16", C.c_int32),
         ("tma_out", C.c_int32),
         ("tanh_out", C.c_void_p), ("acc_nostore", C.c_int32),
+        ("inj_har", C.c_void_p), ("inj_w", C.c_void_p), ("inj_b", C.c_void_p),
+        ("inj_k", C.c_int32), ("inj_s", C.c_int32), ("inj_pad", C.c_int32), ("inj_cn", C.c_int32), ("inj_Lhar", C.c_int64),
     ]
 
 

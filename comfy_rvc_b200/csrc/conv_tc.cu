@@ -237,7 +237,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           for (int tap = 0; tap < p.ntaps; ++tap) {
             const int sb = kb * p.ntaps + tap;
             mbar_expect_tx(&b_full[sb], b_bytes);
-            tma_load_2d(slabB + (size_t)sb * b_stride, &tmW, 0, w_row(0, 0, tap, kb), &b_full[sb]);
+            tma_load_2d(slabB + (size_t)sb * b_stride, &tmW, 0, w_row((int)(blockIdx.x % (unsigned)p.G), 0, tap, kb), &b_full[sb]);
           }
       }
       pdl_wait();                         // activations come from the previous kernel (the weights above do not)
@@ -814,10 +814,16 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     const int nw = nkb * d.ntaps;
     const int na_max = d.a_mode != 1 ? 6 : 10;
     d.b_stationary = 0;
-    if (d.G == 1 && n_nt == 1 && nw <= 48 && (size_t)nw * bb + 3 * a <= budget && tiles > 2 * 148) {
+    // Phase groups (transposed conv, G > 1): with the phase fastest in the tile order and a grid that is a multiple of G,
+    // every tile of a CTA has the same phase blockIdx.x % G, so that phase's weights can stay resident as well.  Without
+    // it the 128 KB of weights of a 256 -> 128 stride-10 stage are re-streamed from L2 for every 128-row tile (ncu:
+    // 196 us, tensor pipe 24 % busy, epilogue warps waiting for the accumulator 31 % of their samples).
+    // (the 256 -> 128 stage needs 128 KB of weights + 3 slabs + 32 KB of output staging: it gets the last 10 KB of the SM)
+    const size_t budget_s = d.G > 1 ? budget + 10 * 1024 : budget;
+    if (n_nt == 1 && nw <= 48 && (size_t)nw * bb + 3 * a <= budget_s && tiles > 2 * 148 && d.G <= 148) {
       d.b_stationary = 1;
       d.nb_stages = nw;
-      long long na = (long long)(budget - (size_t)nw * bb) / (long long)a;
+      long long na = (long long)(budget_s - (size_t)nw * bb) / (long long)a;
       d.na_stages = (int)(na > na_max ? na_max : na);
     } else {
       d.na_stages = d.a_mode != 1 ? (nkb >= 2 ? 3 : 2) : 4;
@@ -874,7 +880,8 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     cfgd = smem;
   }
-  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
+  unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);            // persistent: one CTA per SM
+  if (d.b_stationary && d.G > 1) grid = (unsigned)((num_sms / d.G) * d.G);  // every tile of a CTA has phase blockIdx.x % G
   cudaError_t le = d.generic ? launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW, tmY)
                              : launch_pdl(conv_tc_kernel<false>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW, tmY);
   launch_counter().n++;

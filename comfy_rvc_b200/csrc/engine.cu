@@ -909,12 +909,23 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
       // When a test taps x, the fp32 planar path of the first version is used.
       static const int dense_ok = [] { const char* e = getenv("RVCB200_UPS_DENSE"); return e ? atoi(e) : 1; }();
       const float first_slope = f0 ? 1.f : 0.1f;      // with f0 the lrelu is applied by the injection kernel
+      bool injected = false;
       if (!want_tap && dense_ok && ups_dense(f, i)) {
         TcConvDesc d = tc_base();
         d.x16 = IN16; d.L_in = (int)Lc; d.w16 = W16h(S("dec.ups.%d.w3", i)); d.bias = W(S("dec.ups.%d.b3", i));
         d.Cin = Cc; d.ntaps = 3; d.dil = 1; d.g_off[0] = -1;
         d.N = Cc; d.Cout_total = Cc; d.tmem_cols = tmem_cols_for(d.N);
         d.Lj = (int)Lc; d.Lp_out = pv_pitch_rows(Lc); d.y16 = X16; d.out_slope = first_slope;   // [Lc][u*Cn] == [Ln][Cn]
+        // late stages: the noise conv has <= 4 taps, cheap enough for the epilogue of this (HBM-bound) launch -- the
+        // stream is then written once instead of written, re-read and re-written (RVCB200_INJECT_FUSED=0: separate)
+        static const int inj_ok = [] { const char* e = getenv("RVCB200_INJECT_FUSED"); return e ? atoi(e) : 1; }();
+        if (f0 && inj_ok && use_rb && nk <= 4 && (Cn == 32 || Cn == 64)) {
+          d.inj_har = pl.har; d.inj_w = W(S("dec.noise.%d.w", i)); d.inj_b = W(S("dec.noise.%d.b", i));
+          d.inj_k = nk; d.inj_s = ns; d.inj_pad = np; d.inj_cn = Cn; d.inj_Lhar = Lout;
+          d.out_slope = 0.1f;
+          injected = rbconv_tc_supported(d);
+          if (!injected) { d.inj_har = nullptr; d.out_slope = first_slope; }
+        }
         if (!ok) return RVCB200_ERR_MISSING;
         CKC(4, launch_rb(d), "dec.ups(dense)");
       } else {
@@ -939,7 +950,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
           CKC(3, launch_noise_add_pv(nullptr, nullptr, nullptr, X32, X16, true, B, Lout, Ln, Cn, 0, 1, 0, LpN, kPadF, 0.1f,
                                      false, st),
               "dec.to_stream(pv)");
-      } else if (f0) {
+      } else if (f0 && !injected) {
         CKC(3, launch_noise_add16(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X16, B, Lout, Ln, Cn, nk, ns,
                                   np, 0.1f, st),
             "dec.noise_add16");

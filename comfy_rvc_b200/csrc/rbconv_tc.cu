@@ -21,6 +21,7 @@ using namespace tc;
 
 constexpr int kRbThreads = 64 + 32 * 8;   // TMA producer warp, MMA warp, 8 epilogue warps (2 groups of 4)
 constexpr int kEpiBox = 2048;             // one epilogue staging box: 32 rows x 32 channels x 16 bit, SWIZZLE_64B
+constexpr int kInjFloats = 5 * 64;        // source-injection taps [<= 4][<= 64] + bias [<= 64]
 
 // Shared-memory plan of one instantiation (plain constexpr functions so that MSUB can be chosen by "does it fit").
 struct RbPlan {
@@ -80,7 +81,7 @@ struct RbCfg {
   static constexpr int TMEM_COLS = 2 * MSUB * C;           // two accumulator buffers of MSUB sub-tiles
   static constexpr int NCH = MSUB * (C / 32);              // 32-column epilogue chunks per tile and warp
   static constexpr int NBAR = 2 * NA + 2 * NB + 4 + 16;    // + 8 warps x 2 residual-box barriers
-  static constexpr size_t SMEM = 1024 + (size_t)NA * A_BYTES + (size_t)NB * W_BYTES + EPI_BYTES + C * sizeof(float) +
+  static constexpr size_t SMEM = 1024 + (size_t)NA * A_BYTES + (size_t)NB * W_BYTES + EPI_BYTES + (C + kInjFloats) * sizeof(float) +
                                  8 * NBAR + 64;
   static_assert(C % 32 == 0 && C <= 256, "C");
   static_assert(NA >= 2, "activation ring too small");
@@ -102,7 +103,8 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
   unsigned char* sW = sA + (size_t)K::NA * K::A_BYTES;            // [NB][C][128 B] swizzled
   unsigned char* sE = sW + (size_t)K::NB * K::W_BYTES;            // [8 warps][2 residual + OUT_SLOTS output boxes][2 KB]
   float* sbias = reinterpret_cast<float*>(sE + K::EPI_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sbias + C);
+  float* sinj = sbias + C;                                        // [inj_k][inj_cn] taps, then [inj_cn] bias
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sinj + kInjFloats);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + K::NA;
   uint64_t* b_full = a_empty + K::NA;
@@ -134,6 +136,10 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = threadIdx.x; i < C; i += kRbThreads) sbias[i] = p.bias[i];
+  if (p.inj_har) {
+    const int nw = p.inj_k * p.inj_cn;
+    for (int i = threadIdx.x; i < nw + p.inj_cn; i += kRbThreads) sinj[i] = i < nw ? p.inj_w[i] : p.inj_b[i - nw];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -356,6 +362,33 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
             v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
             v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
           }
+          if (p.inj_har) {
+            // source injection of a dense stride-u transposed conv: columns [c0, c0 + 32) are channels cb.. of phase ph,
+            // i.e. of output time row * u + ph
+            const int cn = p.inj_cn, ph = c0 / cn, cb = c0 - ph * cn;
+            const long long h0 = ((long long)row * (C / cn) + ph) * p.inj_s - p.inj_pad;
+            const float* hb = p.inj_har + (size_t)b * (size_t)p.inj_Lhar;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kk < p.inj_k) {
+                const long long h = h0 + kk;
+                const float hv = (row_ok && h >= 0 && h < p.inj_Lhar) ? __ldg(hb + h) : 0.f;
+                const float* wk = sinj + kk * cn + cb;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                  const float4 wq = *reinterpret_cast<const float4*>(wk + k4 * 4);
+                  v[k4 * 4 + 0] = fmaf(hv, wq.x, v[k4 * 4 + 0]); v[k4 * 4 + 1] = fmaf(hv, wq.y, v[k4 * 4 + 1]);
+                  v[k4 * 4 + 2] = fmaf(hv, wq.z, v[k4 * 4 + 2]); v[k4 * 4 + 3] = fmaf(hv, wq.w, v[k4 * 4 + 3]);
+                }
+              }
+            }
+            const float* bk = sinj + p.inj_k * cn + cb;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 bq = *reinterpret_cast<const float4*>(bk + k4 * 4);
+              v[k4 * 4 + 0] += bq.x; v[k4 * 4 + 1] += bq.y; v[k4 * 4 + 2] += bq.z; v[k4 * 4 + 3] += bq.w;
+            }
+          }
           if (has_r16) {
             if (K::EPI_TMA) {
               // residual box of this chunk: wait, read this lane's row, hand the slot back, refill it two chunks ahead
@@ -545,6 +578,9 @@ bool rbconv_tc_supported(const TcConvDesc& d) {
   if (d.res32 || (d.y32 && !d.acc_f16)) return false;      // fp32 planar residual / output: generic kernel only
   if (d.tanh_out && (d.y16 || d.y32 || d.res16 || d.Cin > 128)) return false;       // conv_post mode: the only output
   if (d.acc_nostore && !(d.y32 && d.accum && d.y16)) return false;
+  if (d.inj_har && (!d.inj_w || !d.inj_b || d.inj_k < 1 || d.inj_k > 4 || !(d.inj_cn == 32 || d.inj_cn == 64) ||
+                    d.Cin % d.inj_cn != 0 || !d.y16 || d.y32 || d.res16 || d.tanh_out || d.inj_s < 1))
+    return false;
   // the epilogue computes lrelu as max(v, v * slope) and the residual expansion as min(r, r * scale)
   if (!(d.out_slope > 0.f && d.out_slope <= 1.f) || !(d.res_neg_scale == 0.f || d.res_neg_scale >= 1.f)) return false;
   return true;

@@ -626,7 +626,7 @@ cudaError_t launch_pair_v(const TcConvDesc& d1, const TcConvDesc& d2, int B, cud
 // the residual is the pair's own input stream, and the output does not alias it (tiles read a halo of the input).
 bool rbpair_tc_supported(const TcConvDesc& d1, const TcConvDesc& d2) {
   if (!rbconv_tc_supported(d1) || !rbconv_tc_supported(d2)) return false;
-  if (d1.tanh_out || d2.tanh_out || d1.acc_nostore || d2.acc_nostore) return false;
+  if (d1.tanh_out || d2.tanh_out || d1.acc_nostore || d2.acc_nostore || d1.inj_har || d2.inj_har) return false;
   if (!(d1.Cin == 32 || d1.Cin == 64) || d2.Cin != d1.Cin) return false;
   if (!(d1.ntaps == 3 || d1.ntaps == 7) || d2.ntaps != d1.ntaps || d2.dil != 1) return false;
   if (d1.Lj != d2.Lj || d1.L_in != d2.L_in) return false;

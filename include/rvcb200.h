@@ -205,6 +205,11 @@ typedef struct rvcb200_tc_conv_desc {
                                 * channels 1.. are zero; y16 / y32 / res16 must be null */
   int32_t acc_nostore;         /* 1: y32 is read (accum) but not written back; only y16 leaves (the last pair of the last
                                 * stage, whose branch sum is consumed once, by conv_post, as y16 = lrelu_{0.01}(.)) */
+  /* Source injection x + noise_convs[i](har) (models.py:552-553) inside the epilogue of a stride-u transposed conv run
+   * as a dense convolution (output columns = u phases x inj_cn channels, output row j = time rows j*u .. j*u+u-1):
+   * v[ph*inj_cn + c] += inj_b[c] + sum_k har[b][(j*u + ph) * inj_s - inj_pad + k] * inj_w[k][c].  inj_k <= 4. */
+  const float* inj_har; const float* inj_w; const float* inj_b;
+  int32_t inj_k, inj_s, inj_pad, inj_cn; int64_t inj_Lhar;
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 

@@ -50,6 +50,9 @@ TC_CASES = [
     ("k11_d5_c32_long", 2, 40000, 32, 32, 11, 5, 1),
     ("k3_c128_long", 1, 45000, 128, 128, 3, 1, 1),
     ("k7_c128_ring_long", 1, 45000, 128, 128, 7, 1, 1),
+    # phase groups with > 296 tiles: one phase per CTA (grid a multiple of G), that phase's weights resident
+    ("ups10_256_128_long", 1, 6000, 256, 128, 2, 1, 10),
+    ("ups8_256_128_long_batch", 2, 2600, 256, 128, 2, 1, 8),
 ]
 
 
@@ -314,6 +317,53 @@ def test_infer_fused_pairs_equals_two_launch_form(name, precision, monkeypatch):
     assert torch.equal(outs[0][0], outs[1][0])
 
 
+@pytest.mark.parametrize("case", [("inj_c64_cn32_k1", 2, 3001, 64, 32, 1, 1, 0), ("inj_c128_cn64_k4", 1, 2500, 128, 64, 4, 2, 1),
+                                  ("inj_c64_cn32_k4", 1, 700, 64, 32, 4, 2, 1), ("inj_c128_cn64_k2", 2, 1300, 128, 64, 2, 1, 0)],
+                         ids=lambda c: c[0])
+def test_rbconv_source_injection(case):
+    """Dense stride-2 transposed conv (3-tap conv, output columns = 2 phases x cn channels) with the source injection
+    x + noise_convs[i](har) (models.py:552-553) and the lrelu fused into its epilogue, against an fp64 restatement."""
+    name, B, L, Cc, cn, k, s, pad = case
+    u = Cc // cn
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(len(name) * 13 + Cc + k)
+    x = torch.randn(B, L, Cc, generator=g).half().float()
+    w = (torch.randn(1, 3, Cc, Cc, generator=g) / math.sqrt(Cc * 3)).half().float()
+    bias = torch.randn(Cc, generator=g)
+    Lo = L * u
+    Lh = Lo * s
+    har = torch.randn(B, Lh, generator=g) * 0.5
+    wn = torch.randn(k, cn, generator=g)
+    nb = torch.randn(cn, generator=g)
+    raw = conv_cl(x.double(), w.double(), bias.double(), g_off=[-1], dil=1, out_stride=1).reshape(B, Lo, cn)
+    hp = torch.nn.functional.pad(har.double(), (pad, k))                       # har[t*s - pad + kk]
+    idx = (torch.arange(Lo) * s)[:, None] + torch.arange(k)[None, :]           # [Lo][k] into the padded signal
+    noise = torch.einsum("btk,kc->btc", hp[:, idx], wn.double()) + nb.double()
+    ref = raw + noise
+    want16 = torch.where(ref > 0, ref, ref * 0.1)
+    x16 = x.half().to(dev).contiguous()
+    y16 = torch.zeros(B, L, Cc, dtype=torch.float16, device=dev)
+    w16 = weights.pack_tc(w, torch.float16).to(dev)
+    bd, hd, wd, nd = bias.to(dev), har.to(dev).contiguous(), wn.to(dev).contiguous(), nb.to(dev)
+    d = _lib.TcConvDesc()
+    d.x16, d.L_in, d.padf = x16.data_ptr(), L, PADF
+    d.w16, d.bias = w16.data_ptr(), bd.data_ptr()
+    d.Cin, d.ntaps, d.dil, d.G = Cc, 3, 1, 1
+    d.g_off[0] = -1
+    d.N, d.Cout_total = Cc, Cc
+    d.Lj, d.out_stride, d.Lp_out = L, 1, pitch(L)
+    d.y16, d.out_slope, d.div = y16.data_ptr(), 0.1, 1.0
+    d.inj_har, d.inj_w, d.inj_b = hd.data_ptr(), wd.data_ptr(), nd.data_ptr()
+    d.inj_k, d.inj_s, d.inj_pad, d.inj_cn, d.inj_Lhar = k, s, pad, cn, Lh
+    assert lib.rvcb200_op_rbconv_tc(C.byref(d), B, C.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0
+    torch.cuda.synchronize()
+    got = y16.cpu().float().double().reshape(B, Lo, cn)
+    err = (got - want16).abs().max().item()
+    print(f"rbconv injection {name}: max abs err {err:.3e} (|ref|max {want16.abs().max().item():.2f})")
+    assert err < 0.02
+
+
 def test_rbconv_rejects_other_shapes():
     d = _lib.TcConvDesc()
     d.Cin = d.Cout_total = d.N = 16
@@ -385,9 +435,11 @@ def test_infer_tensor_core_path_snr(name, precision, min_snr):
 
 
 @pytest.mark.parametrize("name", ["c2_48k_v2", "c5_48k_v1_5stage", "c8_48k_v2_nono_ragged"])
-def test_fused_source_injection_equals_separate_kernel(name):
-    """Stages whose noise_conv kernel is short get it fused into the transposed conv's epilogue (engine.cu); tapping
-    `dec.ups.i` forces the separate fp32-planar + noise_add path.  Same arithmetic up to fp32 summation order."""
+def test_source_injection_paths_agree(name):
+    """Default decode (raw fp16 transposed-conv output + in-place injection on stages 1-2, injection fused into the dense
+    stride-2 conv's epilogue on the late stages) against the fp32-planar intermediate that tapping `dec.ups.i` forces
+    (engine.cu).  Same arithmetic up to where the fp16 roundings sit: the two waveforms agree to well below the gate of
+    either against the reference (measured 57-60 dB; bit-identical without f0, where there is nothing to inject)."""
     from tests.test_parity_gpu import build_net
     from tests._util import net_infer
     cfg, sd, inputs, noise, gold = load_golden(name)
@@ -397,5 +449,5 @@ def test_fused_source_injection_equals_separate_kernel(name):
     separate = net_infer(net, cfg, inputs, noise, taps)[0]
     torch.cuda.synchronize()
     snr = synthetic.snr_db(separate.cpu().numpy(), fused.cpu().numpy())
-    print(f"{name}: fused vs separate source injection: {snr:.1f} dB")
-    assert snr >= 65.0
+    print(f"{name}: default vs fp32-planar source injection: {snr:.1f} dB")
+    assert snr >= 52.0
