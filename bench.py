@@ -158,7 +158,27 @@ def cpu_oracle_rate(cfg, T: int, reps: int, warmup: int, threads: int):
     return audio_s / float(np.median(times)), audio_s, times
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner under
+    NCCL_DEBUG=VERSION, warnings of child tools) is sent to stderr for the lifetime of the process."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -200,7 +220,7 @@ def main():
                                        f"{args.cpu_frames} frames = {sample_s:.1f} s audio per step"},
             "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ product arm (CUDA) --------
@@ -309,6 +329,7 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     if dist is not None:
+        print(f"rank {rank}: {ms / args.steps:.3f} ms/step resident, {ms_e2e / args.steps:.3f} ms/step end to end", file=sys.stderr)
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
@@ -364,7 +385,7 @@ def main():
         rate, sample_s, _ = cpu_oracle_rate(cfg, args.cpu_frames, 3, 1, threads)
         line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",
                                 "sample": f"oracle/rvc_oracle.py fp32 PyTorch CPU, {args.cpu_frames} frames = {sample_s:.1f} s audio, median of 3"}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
