@@ -293,32 +293,41 @@ def main():
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     cur = torch.cuda.current_stream(dev)
 
-    def fetch():
+    # two preallocated sets of device input buffers (no allocator traffic in the loop): set k is refilled on the copy
+    # stream as soon as the step that last read it has finished
+    dev_in = [[torch.empty(t.shape, dtype=t.dtype, device=dev) for t in host] for _ in range(2)]
+    read_done = [None, None]
+
+    def fetch(i):
+        k = i % 2
         with torch.cuda.stream(s_in):
-            ins = [t.to(dev, non_blocking=True) for t in host]
+            if read_done[k] is not None:
+                s_in.wait_event(read_done[k])
+            for d, h in zip(dev_in[k], host):
+                d.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(s_in)
-        return ins, ev
+        return dev_in[k], ev
 
     def run_e2e(n):
-        nxt = fetch()
-        for _ in range(n):
+        nxt = fetch(0)
+        for i in range(n):
             ins, ev = nxt
             cur.wait_event(ev)
-            nxt = fetch()                              # H2D of the next step's inputs overlaps this step's kernels
+            nxt = fetch(i + 1)                         # H2D of the next step's inputs overlaps this step's kernels
             o = net.infer(*ins)[0]
-            for t in ins:
-                t.record_stream(cur)
             done = torch.cuda.Event()
             done.record(cur)
+            read_done[i % 2] = done
             s_out.wait_event(done)
             with torch.cuda.stream(s_out):
                 out_host.copy_(o, non_blocking=True)   # D2H of this step's PCM overlaps the next step's kernels
             o.record_stream(s_out)
         cur.wait_stream(s_out)
         cur.wait_stream(s_in)
+        read_done[0] = read_done[1] = None
 
-    run_e2e(2)
+    run_e2e(max(3, args.warmup) + 3)         # warm-up: lets the caching allocator reach its steady set of blocks
     barrier()
     f0_, f1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0_.record()

@@ -34,22 +34,23 @@ namespace {
 
 using namespace tc;
 
-// threads: TMA producer warp, MMA warp, 4 h-epilogue warps, E2G x 4 output-epilogue warps
-constexpr int pair_threads(int e2g) { return 64 + 32 * (4 + 4 * e2g); }
+// threads: TMA producer warp, MMA warp, E1G x 4 h-epilogue warps, E2G x 4 output-epilogue warps
+constexpr int pair_threads(int e1g, int e2g) { return 64 + 32 * (4 * e1g + 4 * e2g); }
 constexpr int kPairBox = 2048;              // one output staging box: 32 rows x 32 channels x 16 bit, SWIZZLE_64B
 constexpr int kPairSmemMax = 227 * 1024;
 
 // Pipeline shape of one instantiation: rows per tile, h tiles, conv1 look-ahead, output staging slots per warp.
-struct PairSel { int msub, nh, la, out_slots, e2g; };
+struct PairSel { int msub, nh, la, out_slots, e2g, e1g; };
 constexpr PairSel pair_sel(int C, int NTAPS, int variant) {
   if (C == 64) {
-    if (NTAPS == 3) return variant == 0 ? PairSel{1, 2, 2, 1, 2} : PairSel{1, 3, 2, 1, 2};
+    // k = 3: bound by the h-epilogue (profiles/r1_ncu_v16_final.md) -> variant 1 tries a second h-epilogue group
+    if (NTAPS == 3) return variant == 0 ? PairSel{1, 2, 2, 1, 2, 1} : PairSel{1, 2, 2, 1, 2, 2};
     // k = 7: 112 KB of weights, bound by MMA issue (profiles/r1_pair_shapes_v4_*.jsonl): one output-epilogue group, the
     // shared memory of the second group's staging goes to a fourth slab instead
-    return variant == 0 ? PairSel{1, 1, 1, 1, 1} : PairSel{1, 1, 1, 1, 2};
+    return variant == 0 ? PairSel{1, 1, 1, 1, 1, 1} : PairSel{1, 1, 1, 1, 2, 1};
   }
-  if (NTAPS == 3) return variant == 0 ? PairSel{2, 1, 1, 1, 2} : PairSel{1, 2, 2, 1, 2};
-  return variant == 0 ? PairSel{1, 2, 2, 1, 2} : PairSel{1, 2, 2, 2, 1};
+  if (NTAPS == 3) return variant == 0 ? PairSel{2, 1, 1, 1, 2, 1} : PairSel{1, 2, 2, 1, 2, 2};
+  return variant == 0 ? PairSel{1, 2, 2, 1, 2, 1} : PairSel{1, 2, 2, 1, 2, 2};
 }
 
 struct PairPlan {
@@ -100,7 +101,9 @@ struct PairCfg {
   static constexpr int NA = P.na;                          // slab ring
   static constexpr int OUT_SLOTS = S.out_slots;
   static constexpr int E2G = S.e2g;                        // output-epilogue groups (alternate tiles)
-  static constexpr int THREADS = pair_threads(S.e2g);
+  static constexpr int E1G = S.e1g;                        // h-epilogue groups (alternate tiles)
+  static constexpr int THREADS = pair_threads(S.e1g, S.e2g);
+  static_assert(S.e1g == 1 || (S.nh >= 2 && S.la + 1 >= 2), "two h-epilogue groups need two h tiles and two conv1 accumulators");
   static constexpr int KS = C / 16;                        // K=16 MMA steps (C <= 64: one 128-byte swizzled row)
   static constexpr int OUT_ROWS = P.out_rows;
   static constexpr int P2 = (NTAPS - 1) / 2;               // "same" padding of conv2 (dilation 1)
@@ -150,7 +153,7 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int C, int NTAPS, int DIL, int VAR>
-__global__ void __launch_bounds__(pair_threads(pair_sel(C, NTAPS, VAR).e2g), 1)
+__global__ void __launch_bounds__(pair_threads(pair_sel(C, NTAPS, VAR).e1g, pair_sel(C, NTAPS, VAR).e2g), 1)
 rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmY,
                  const __grid_constant__ CUtensorMap tmYt) {
@@ -302,14 +305,16 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
       }
       __syncwarp();
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + 4 * K::E1G) {
     // ============ epilogue 1: conv1 accumulator -> h = lrelu(. + b1) in the operand format of conv2 -> sH ============
+    // E1G groups of 4 warps take alternate tiles (group g: my tiles g, g + E1G, ...).
     const int qd = warp & 3;                        // TMEM lane quadrant this warp may access
+    const uint32_t hg = (uint32_t)(warp - 2) >> 2;
     const bool hbf = p.fmt2 != 0;
     const float hs = p.h_slope;
-    Ring r1{0u, 0u}, rh{0u, 0u};
+    Ring r1{hg % (uint32_t)NB1, 0u}, rh{hg % (uint32_t)NH, 0u};   // accumulator / h tile of my tile: (g + E1G n) mod ring
 #pragma unroll 1
-    for (unsigned tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (unsigned tile = blockIdx.x + hg * gridDim.x; tile < total_tiles; tile += K::E1G * gridDim.x) {
       const unsigned mt = tile % n_mt;
       const int th0 = (int)mt * K::OUT_ROWS - K::P2 + qd * 32 + lane;     // time index of this lane's h row (sub-tile 0)
       mbar_wait(&acc1_full[r1.i], r1.ph);
@@ -359,8 +364,8 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
       fence_proxy_async();                           // generic-proxy writes of sH -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&h_full[rh.i]);
-      ring_next<NB1>(r1);
-      ring_next<NH>(rh);
+#pragma unroll
+      for (int e = 0; e < K::E1G; ++e) { ring_next<NB1>(r1); ring_next<NH>(rh); }
     }
   } else {
     // ===== epilogue 2: conv2 accumulator + b2 + residual (from the slab) -> branch sum / 16-bit stream (TMA boxes) =====
@@ -370,8 +375,8 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
     // fence and one bulk group.
     // E2G groups of 4 warps take alternate tiles (group g: my tiles g, g + E2G, ...).
     pdl_wait();
-    const int ew = warp - 6;
-    const uint32_t eg = (uint32_t)(warp - 6) >> 2;
+    const int ew = warp - (2 + 4 * K::E1G);
+    const uint32_t eg = (uint32_t)ew >> 2;
     const int qd = warp & 3;
     const size_t pitch_o = (size_t)p.Lp_out * 16;   // bytes per planar-vector plane
     const bool obf = p.out_bf16 != 0;
