@@ -348,19 +348,21 @@ rbconv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, co
                 "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
               : "r"(taddr));
+          float4 bq[8];                               // bias: its smem latency hides under the TMEM load
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) bq[k4] = lds_f4(sbias + c0 + k4 * 4);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (tanh_out) {                             // (warp-uniform) the 128 B a warp stores are contiguous
-            if (c0 == 0 && row_ok) tanh_out[(size_t)b * (size_t)p.Lj + row] = tanhf(__uint_as_float(r[0]) + sbias[0]);
+            if (c0 == 0 && row_ok) tanh_out[(size_t)b * (size_t)p.Lj + row] = tanhf(__uint_as_float(r[0]) + bq[0].x);
             continue;
           }
           float v[32];
 #pragma unroll
           for (int k4 = 0; k4 < 8; ++k4) {
-            const float4 bq = *reinterpret_cast<const float4*>(sbias + c0 + k4 * 4);
-            v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
-            v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
-            v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
-            v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
+            v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq[k4].x;
+            v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq[k4].y;
+            v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq[k4].z;
+            v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq[k4].w;
           }
           if (p.inj_har) {
             // source injection of a dense stride-u transposed conv: columns [c0, c0 + 32) are channels cb.. of phase ph,

@@ -330,6 +330,12 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
           const int ci = g0 + u, ms = ci / K::CPS, cc = ci - ms * K::CPS;
           tmem_ld32_issue(tbase + (uint32_t)(ms * C + cc * 32), r[u]);
         }
+        float4 bq[8];                                 // bias of the first chunk: its smem latency hides under the TMEM load
+        {
+          const int cc0 = g0 % K::CPS;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) bq[k] = lds_f4(sbias1 + cc0 * 32 + k * 4);
+        }
         tmem_ld_wait();
         if (g0 + K::GCH >= K::NCH) {                  // the accumulator is in registers: hand it back to the MMA warp
           tc_fence_before();
@@ -339,6 +345,10 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
 #pragma unroll
         for (int u = 0; u < K::GCH; ++u) {
           const int ci = g0 + u, ms = ci / K::CPS, cc = ci - ms * K::CPS;
+          if (u > 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bq[k] = lds_f4(sbias1 + cc * 32 + k * 4);
+          }
           const int hrow = ms * 128 + qd * 32 + lane;
           const int th = th0 + ms * 128;
           const bool ok = th >= 0 && th < p.L;       // conv2 pads h with zeros outside [0, L)
@@ -347,8 +357,7 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             float v[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(sbias1 + cc * 32 + k * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(sbias1 + cc * 32 + k * 8 + 4);
+            const float4 b0 = bq[2 * k], b1 = bq[2 * k + 1];
             v[0] = __uint_as_float(r[u][k * 8 + 0]) + b0.x; v[1] = __uint_as_float(r[u][k * 8 + 1]) + b0.y;
             v[2] = __uint_as_float(r[u][k * 8 + 2]) + b0.z; v[3] = __uint_as_float(r[u][k * 8 + 3]) + b0.w;
             v[4] = __uint_as_float(r[u][k * 8 + 4]) + b1.x; v[5] = __uint_as_float(r[u][k * 8 + 5]) + b1.y;
@@ -428,6 +437,17 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
         const bool row_ok = jl < K::OUT_ROWS && row < p.L;
         uint32_t r[32];                                           // one chunk at a time: 128 registers per thread at 448 threads
         tmem_ld32_issue(tbase + (uint32_t)(ms * C + c0), r);
+        float4 bq[8];                                             // bias and residual row: smem latency under the TMEM load
+        uint4 rq[4];
+        {
+          const int srow = jl + K::P2 + K::P1;                    // this lane's time step inside the activation slab
+          const unsigned char* rp = slab + (size_t)srow * 128;
+          const uint32_t rx = (uint32_t)srow & 7u;
+#pragma unroll
+          for (int k4 = 0; k4 < 8; ++k4) bq[k4] = lds_f4(sbias2 + c0 + k4 * 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rq[k] = lds_u4(rp + ((((uint32_t)(cc * 4 + k)) ^ rx) << 4));
+        }
         tmem_ld_wait();
         if (ci == K::NCH - 1) {                                   // the accumulator is in registers: hand it back
           tc_fence_before();
@@ -437,20 +457,13 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
         float v[32];
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
-          const float4 bq = *reinterpret_cast<const float4*>(sbias2 + c0 + k4 * 4);
-          v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq.x;
-          v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq.y;
-          v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq.z;
-          v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq.w;
+          v[k4 * 4 + 0] = __uint_as_float(r[k4 * 4 + 0]) + bq[k4].x;
+          v[k4 * 4 + 1] = __uint_as_float(r[k4 * 4 + 1]) + bq[k4].y;
+          v[k4 * 4 + 2] = __uint_as_float(r[k4 * 4 + 2]) + bq[k4].z;
+          v[k4 * 4 + 3] = __uint_as_float(r[k4 * 4 + 3]) + bq[k4].w;
         }
-        {
-          const int srow = jl + K::P2 + K::P1;                    // this lane's time step inside the activation slab
-          const unsigned char* rp = slab + (size_t)srow * 128;
-          const uint32_t rx = (uint32_t)srow & 7u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            add_res8(v + k * 8, *reinterpret_cast<const uint4*>(rp + ((((uint32_t)(cc * 4 + k)) ^ rx) << 4)), neg_scale);
-        }
+        for (int k = 0; k < 4; ++k) add_res8(v + k * 8, rq[k], neg_scale);
         if (has_acc) {
           if (do_acc && row_ok) {
 #pragma unroll

@@ -102,6 +102,19 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t bas
          ((uint64_t)(base_offset & 7u) << 49) | (2ull << 61);
 }
 
+// Shared-memory loads the compiler may not move: issued between a tcgen05.ld and its wait so that the smem latency (bias,
+// residual rows) hides under the TMEM latency instead of stalling the first use after the wait
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
 // 16-byte read-only global load that does not allocate in L1 (streamed residuals)
 __device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) {
   uint4 v;
