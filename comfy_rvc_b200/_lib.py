@@ -78,6 +78,7 @@ class TcConvDesc(C.Structure):
 # every symbol include/rvcb200.h declares: (restype, argtypes)
 SYMBOLS = {
     "rvcb200_abi_version": (C.c_int32, []),
+    "rvcb200_sizeof": (C.c_int64, [C.c_int32]),
     "rvcb200_create": (C.c_int, [C.POINTER(RvcConfig), C.POINTER(C.c_void_p)]),
     "rvcb200_destroy": (None, [C.c_void_p]),
     "rvcb200_set_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]),
@@ -129,6 +130,10 @@ def load() -> C.CDLL:
         fn.argtypes = args
     if lib.rvcb200_abi_version() != 1:
         raise RuntimeError("librvcb200.so ABI version mismatch; rebuild")
+    for which, mirror in enumerate((RvcConfig, RvcTap, ConvDesc, TcConvDesc)):
+        if lib.rvcb200_sizeof(which) != C.sizeof(mirror):
+            raise RuntimeError(f"librvcb200.so is stale: sizeof({mirror.__name__}) is {lib.rvcb200_sizeof(which)} in the library, "
+                               f"{C.sizeof(mirror)} in _lib.py; rebuild with `python -m comfy_rvc_b200.build --force`")
     _lib = lib
     return lib
 

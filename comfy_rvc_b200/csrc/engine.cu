@@ -273,6 +273,16 @@ extern "C" {
 
 int32_t rvcb200_abi_version(void) { return RVCB200_ABI_VERSION; }
 
+int64_t rvcb200_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(rvcb200_config);
+    case 1: return (int64_t)sizeof(rvcb200_tap);
+    case 2: return (int64_t)sizeof(rvcb200_conv_desc);
+    case 3: return (int64_t)sizeof(rvcb200_tc_conv_desc);
+    default: return -1;
+  }
+}
+
 int rvcb200_create(const rvcb200_config* cfg, rvcb200_ctx** out) {
   if (!cfg || !out) return RVCB200_ERR_ARG;
   *out = nullptr;

@@ -139,6 +139,9 @@ int rvcb200_profile_collect(rvcb200_ctx* ctx, double* ms, int64_t* count);
 int64_t rvcb200_last_launch_count(const rvcb200_ctx* ctx);
 const char* rvcb200_last_error(const rvcb200_ctx* ctx);
 int32_t rvcb200_abi_version(void);
+/* sizeof() of the structs that cross this boundary, as the library was compiled (0: rvcb200_config, 1: rvcb200_tap,
+ * 2: rvcb200_conv_desc, 3: rvcb200_tc_conv_desc; -1 otherwise): a binding checks its own mirror against it. */
+int64_t rvcb200_sizeof(int32_t which);
 
 /* ---- op-level entry points (unit tests and micro-benchmarks; same kernels as infer) ---- */
 

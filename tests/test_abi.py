@@ -29,6 +29,11 @@ def test_struct_sizes_match_header_layout():
     import ctypes as C
     assert C.sizeof(_lib.RvcConfig) == 4 * (12 + 1 + 4 + 4 + 16 + 1 + 8 + 8 + 4 + 1)
     assert C.sizeof(_lib.RvcTap) == 24
+    # the library reports sizeof() of every struct that crosses the boundary: the ctypes mirrors must agree
+    lib = _lib.load()
+    for which, mirror in enumerate((_lib.RvcConfig, _lib.RvcTap, _lib.ConvDesc, _lib.TcConvDesc)):
+        assert lib.rvcb200_sizeof(which) == C.sizeof(mirror), mirror.__name__
+    assert lib.rvcb200_sizeof(99) == -1
 
 
 def test_reference_constructor_and_state_dict_contract():

@@ -112,3 +112,20 @@ def test_dense_transposed_conv_packing_matches_torch():
     from comfy_rvc_b200.config import NAMED_CONFIGS
     assert [weights.ups_is_dense(NAMED_CONFIGS["48k_v2"], i) for i in range(4)] == [False, False, True, True]
     assert [weights.ups_is_dense(NAMED_CONFIGS["48k"], i) for i in range(5)] == [False, False, True, True, True]
+
+
+def test_conv_post_tensor_core_image():
+    """conv_post as a C -> C convolution for the tcgen05 resblock kernel: output channel 0 carries the k x C taps, every
+    other output channel and the bias are zero; only where C_last is one of the kernel's channel counts."""
+    for name, cfg in NAMED_CONFIGS.items():
+        c_last = cfg.upsample_initial_channel >> cfg.num_upsamples
+        assert weights.post_is_tc(cfg) == (c_last in (32, 64, 128) and cfg.resblock == "1")
+        P, _ = weights.pack(cfg, synthetic.make_state_dict(cfg))
+        if weights.post_is_tc(cfg):
+            wt = P["dec.post.wt"]
+            assert tuple(wt.shape) == (7, c_last, c_last)
+            assert torch.equal(wt[:, :, 0], P["dec.post.w"]) and float(wt[:, :, 1:].abs().max()) == 0.0
+            assert float(P["dec.post.bt"].abs().max()) == 0.0 and P["dec.post.bt"].numel() == c_last
+            assert "dec.post.wt" in weights.tc_weight_names(cfg)
+        else:
+            assert "dec.post.wt" not in P and "dec.post.wt" not in weights.tc_weight_names(cfg)
