@@ -4,7 +4,7 @@
 //
 // Operands are staged by TMA (cp.async.bulk.tensor) into the canonical K-major SWIZZLE_128B layout
 // (8 rows x 128 B atoms, SBO = 1024 B) that tcgen05.mma reads at full rate.  A first version of this
-// kernel (conv_tc_noswizzle.cu.txt) used the no-swizzle "interleave" layout and measured ~256
+// kernel (git history: commit 421ed09) used the no-swizzle "interleave" layout and measured ~256
 // tensor-pipe cycles per 128xNx16 MMA independent of N (profiles/r1_conv_tc_shapes_v2.jsonl) -- 4x off
 // the N=128 floor.
 //
