@@ -116,7 +116,7 @@ struct AttSmem {                        // 1024-byte aligned tiles, all [rows][1
   unsigned char q[2][BQ * 128];         // 2 k-blocks of 64 channels
   unsigned char k[NSTG][2][BKV * 128];
   unsigned char v[NSTG][DKP * 128];     // V^T tile: 128 d-rows x 64 keys
-  unsigned char p[BQ * 128];            // probabilities, 64 keys per row
+  unsigned char p[2][BQ * 128];         // probabilities, 64 keys per row; two tiles: P(t+1) is written while P V(t) runs
   unsigned char pband[BQ * 128];        // P[i][i+r-w], r < 21 (columns >= 21 stay zero)
   unsigned char ek[2][32 * 128];
   unsigned char evt[DKP * 128];
@@ -165,16 +165,16 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   uint64_t* r_full = &sm.bars[13];
   uint64_t* s_full = &sm.bars[20];       // [2]
   uint64_t* s_empty = &sm.bars[22];      // [2], 8 softmax warps each
-  uint64_t* p_full = &sm.bars[16];       // 8 softmax warps
-  uint64_t* p_empty = &sm.bars[17];
+  uint64_t* p_full = &sm.bars[24];       // [2], 8 softmax warps each
+  uint64_t* p_empty = &sm.bars[26];      // [2]
   uint64_t* pb_full = &sm.bars[18];      // 8 softmax warps
   uint64_t* o_full = &sm.bars[19];
 
   if (threadIdx.x == 0) {
     bar_init(q_full, 1);
     for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); bar_init(&v_full[i], 1); bar_init(&v_empty[i], 1); }
-    bar_init(r_full, 1); bar_init(p_full, 8); bar_init(p_empty, 1);
-    for (int i = 0; i < 2; ++i) { bar_init(&s_full[i], 1); bar_init(&s_empty[i], 8); }
+    bar_init(r_full, 1);
+    for (int i = 0; i < 2; ++i) { bar_init(&s_full[i], 1); bar_init(&s_empty[i], 8); bar_init(&p_full[i], 8); bar_init(&p_empty[i], 1); }
     bar_init(pb_full, 8); bar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -233,7 +233,7 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
     }
     __syncwarp();
     int ks_ = 0, vs_ = 0;
-    uint32_t kp = 0, vp = 0, pp = 0;
+    uint32_t kp = 0, vp = 0;
     uint32_t o_acc = 0;
     const int total = 2 * ntiles;                       // pass 0 (row max) then pass 1 (probabilities, P V)
     auto issue_qk = [&](int it) {                       // S[it & 1] = Q K^T of key tile it % ntiles
@@ -259,17 +259,17 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
     for (int it = 0; it < total; ++it) {
       if (it + 1 < total) issue_qk(it + 1);             // one tile ahead of the softmax warps
       if (it >= ntiles) {
-        bar_wait(p_full, pp);             // probabilities of this tile are in smem
-        pp ^= 1;
+        const int j = it - ntiles, pb = j & 1;          // P buffer of this key tile
+        bar_wait(&p_full[pb], ((uint32_t)j >> 1) & 1u); // probabilities of this tile are in smem
         bar_wait(&v_full[vs_], vp);
         fence_after();
         if (elect1()) {
-          const uint32_t p_lo = desc_lo(s_u32(sm.p)), v_lo = desc_lo(s_u32(sm.v[vs_]));
+          const uint32_t p_lo = desc_lo(s_u32(sm.p[pb])), v_lo = desc_lo(s_u32(sm.v[vs_]));
           for (int ks = 0; ks < BKV / 16; ++ks) {
             mma_f16(tmem + TM_O, p_lo + 2u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
             o_acc = 1;
           }
-          commit(p_empty);
+          commit(&p_empty[pb]);
           commit(&v_empty[vs_]);
         }
         __syncwarp();
@@ -304,7 +304,6 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 softmax warps
     float mx = -INFINITY, lsum = 0.f;
-    uint32_t pep = 1;
     int it = 0;
     for (int pass = 0; pass < 2; ++pass) {
       if (pass == 1) {                                  // row max over both column halves
@@ -359,15 +358,15 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
               }
             }
           }
-          bar_wait(p_empty, pep);                       // the previous P V MMA has finished reading sm.p
-          pep ^= 1;
+          const int pb = t & 1;                         // P buffer of this key tile
+          bar_wait(&p_empty[pb], (((uint32_t)t >> 1) & 1u) ^ 1u);   // the P V MMA that last read this buffer has finished
 #pragma unroll
           for (int cc = 0; cc < HC / 8; ++cc)
-            *reinterpret_cast<uint4*>(sm.p + row * 128 + (((half * (HC / 8) + cc) ^ (row & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(sm.p[pb] + row * 128 + (((half * (HC / 8) + cc) ^ (row & 7)) << 4)) =
                 make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0) bar_arrive(p_full);
+          if (lane == 0) bar_arrive(&p_full[pb]);
         }
       }
     }
