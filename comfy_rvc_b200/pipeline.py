@@ -83,8 +83,16 @@ def split_points(audio: np.ndarray, window: int, t_query: int, t_center: int, t_
         # 2*t_query samples around each centre that are ever looked at (each element's sum is independent of the others,
         # so this is bit-identical to summing the whole song: 3x less host work for a 10 min song)
         n = audio.shape[0]
+        # float64 (what filtfilt returns): the same sums in the same order, in C over all host threads (csrc/host_plan.cu;
+        # _lib.load() raises if the library is not built).  Other dtypes keep the reference's numpy loop.
+        native = _lib.load().rvcb200_host_quiet_point if audio_pad.dtype == np.float64 and audio_pad.flags.c_contiguous else None
         for t in range(t_center, n, t_center):
             lo, hi = t - t_query, min(t + t_query, n)
+            if native is not None:
+                j = int(native(audio_pad.ctypes.data, lo, hi, window, 0))
+                if j >= 0:
+                    opt_ts.append(lo + j)
+                    continue
             seg = np.zeros(hi - lo, dtype=audio.dtype)
             for i in range(window):
                 seg += audio_pad[lo + i: hi + i]

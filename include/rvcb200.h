@@ -266,6 +266,14 @@ int rvcb200_op_absmax(const float* x, int64_t n, float* out, int32_t reset, void
  * NumPy >= 2 promotion). */
 int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t* out, void* stream);
 
+/* ---- host (CPU) side of the song-level driver (csrc/host_plan.cu) ---- */
+
+/* Quiet-point search of /root/reference/vc_infer_pipeline.py:127-135: the first j in [lo, hi) (returned relative to lo)
+ * that minimises |audio_pad[j] + audio_pad[j+1] + ... + audio_pad[j+window-1]|, each sum accumulated left to right in
+ * double from +0.0 like the reference's `audio_sum += audio_pad[i : i - window]` loop (bit-identical sums).  audio_pad must
+ * hold hi + window - 1 samples.  n_threads <= 0: all hardware threads.  -1 on bad arguments or if every sum is NaN. */
+int64_t rvcb200_host_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int32_t window, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,6 +33,29 @@ def test_plan_matches_oracle(secs, tiers, seed):
     assert [s.index for s in segs] == list(range(len(segs)))
 
 
+@pytest.mark.parametrize("n_threads", [0, 1, 3, 16])
+def test_native_quiet_point_is_the_reference_sum(n_threads):
+    """csrc/host_plan.cu: per-element sequential float64 window sums, first minimum of |sum| -- bit for bit the
+    reference's `audio_sum += audio_pad[i : i - window]` loop (vc_infer_pipeline.py:127-135), for any thread count,
+    with plateaus of equal minima (exact zeros), ragged ranges and ranges shorter than a thread's share."""
+    from comfy_rvc_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    window = 160
+    a = np.round(rng.standard_normal(400000) * 8) / 8.0                      # coarse values: many exactly equal sums
+    a[150000:170000] = 0.0                                                   # a plateau of exact zeros
+    pad = np.pad(a, (window // 2, window // 2), mode="reflect")
+    full = np.zeros_like(a)
+    for i in range(window):
+        full += pad[i: i - window]
+    for lo, hi in ((0, 400000), (100000, 260001), (399000, 400000), (5, 6), (123, 4500)):
+        seg = np.abs(full[lo:hi])
+        want = int(np.where(seg == seg.min())[0][0])
+        assert lib.rvcb200_host_quiet_point(pad.ctypes.data, lo, hi, window, n_threads) == want, (lo, hi)
+    assert lib.rvcb200_host_quiet_point(pad.ctypes.data, 10, 10, window, n_threads) == -1
+    assert lib.rvcb200_host_quiet_point(None, 0, 10, window, n_threads) == -1
+
+
 def test_constants_and_tiers():
     vc = pl.VC(48000, pl.PipelineConfig.for_device(is_half=True))
     assert (vc.x_pad, vc.x_query, vc.x_center, vc.x_max) == (3, 10, 60, 64)               # config.py:124-129
