@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|fp16|bf16]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference        # the reference algorithm's CPU path (oracle port), rank 0 only
+    python bench.py --impl reference        # the reference algorithm's CPU path (oracle port) on the SAME step, rank 0 only
 
 A "step" is one `net_g.infer()` of the BASELINE.json workload `configs[1]`: 48k_v2
 (SynthesizerTrnMs768NSFsid), one 60 s segment of synthetic 768-d features + f0 (T = 6000 frames,
@@ -96,8 +96,9 @@ def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json, sustained)"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "burst": d["bf16_tflops"],
+                "src": "measured (MEASURED_PEAKS.json, sustained: the class is timed inside a long step)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "burst": 1590.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -139,23 +140,118 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(cfg, T: int, reps: int, warmup: int, threads: int):
-    """RTF^-1 of the reference algorithm on the host cores (oracle port, fp32 PyTorch CPU)."""
+def cpu_oracle_rate(cfg, T: int, reps: int, warmup: int, threads: int, warmup_T: int = 0, check=None):
+    """RTF^-1 of the reference algorithm on the host cores (oracle port, fp32 PyTorch CPU).  `warmup` untimed steps at
+    `warmup_T` frames (default: the timed size), then `reps` timed steps at T frames."""
     from oracle import rvc_oracle
+    prev = torch.get_num_threads()
     torch.set_num_threads(threads)
-    sd = synthetic.make_state_dict(cfg)
-    w = rvc_oracle.fold_weight_norm(sd)
-    phone, lens, pitch, pitchf, sid = synthetic.make_inputs(cfg, 1, T)
-    times = []
-    for i in range(warmup + reps):
-        noise = synthetic.draw_noise(cfg, 1, T, seed=7 + i)
-        t0 = time.perf_counter()
-        rvc_oracle.infer(w, cfg, phone, lens, pitch, pitchf, sid, *noise)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
+    try:
+        sd = synthetic.make_state_dict(cfg)
+        w = rvc_oracle.fold_weight_norm(sd)
+        times = []
+        for i in range(warmup + reps):
+            Ti = T if i >= warmup or not warmup_T else warmup_T
+            phone, lens, pitch, pitchf, sid = synthetic.make_inputs(cfg, 1, Ti)
+            noise = synthetic.draw_noise(cfg, 1, Ti, seed=7 + max(i - warmup, 0))     # first timed step = the g2 fixture's draw
+            t0 = time.perf_counter()
+            o = rvc_oracle.infer(w, cfg, phone, lens, pitch, pitchf, sid, *noise)[0]
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            if i == warmup and check is not None:
+                check["first_timed_output"] = o[0, 0].numpy()
+    finally:
+        torch.set_num_threads(prev)
     audio_s = T * cfg.upp / cfg.sr
     return audio_s / float(np.median(times)), audio_s, times
+
+
+def oracle_vs_fixture(o, config_name: str, T: int):
+    """The CPU leg's first timed step is the g2 fixture's step: how far the oracle port is from the waveform the unmodified
+    reference produced (the oracle's pin at BASELINE size, re-checked on the machine that runs the bench)."""
+    path = os.path.join(ROOT, "tests", "golden", "g2_48k_v2_T6000.npz")
+    if o is None or config_name != "48k_v2" or T != 6000 or not os.path.exists(path):
+        return None
+    gold = np.load(path, allow_pickle=True)
+    d = np.abs(synthetic.to_int16(o).astype(np.int32) - gold["o_i16"][0].astype(np.int32))
+    return {"int16_max_lsb_diff": int(d.max()), "int16_frac_differing": float((d > 0).mean()),
+            "against": "tests/golden/g2_48k_v2_T6000.npz (unmodified reference, 1 CPU thread)"}
+
+
+def gpu_incumbent_rate(cfg, T: int, dev, half: bool, reps: int = 3):
+    """The eager-PyTorch incumbent on the same GPU: the oracle port -- pure torch.nn.functional, the
+    reference's own op sequence -- on CUDA tensors, cuDNN / cuBLAS kernels, fp16 as the reference ships it on CUDA
+    (`is_half`, /root/reference/vc_infer_pipeline.py:223-226) or fp32 with TF32 off.  Same step as the product arm
+    (noise drawn on the device inside the step).  The port's attention is the banded form, i.e. it does LESS work than
+    the reference's zero-padded relative-position matmuls: the incumbent figure errs on the fast side."""
+    from oracle import rvc_oracle
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        dt = torch.float16 if half else torch.float32
+        sd = synthetic.make_state_dict(cfg)
+        w = {k: v.to(dev, dtype=dt) for k, v in rvc_oracle.fold_weight_norm(sd).items()}
+        phone, lens, pitch, pitchf, sid = [t.to(dev) for t in synthetic.make_inputs(cfg, 1, T)]
+        L = T * cfg.upp
+
+        def step():
+            nz = torch.randn(1, cfg.inter_channels, T, device=dev, dtype=dt)
+            ri = torch.rand(1, 1, device=dev)
+            ns = torch.randn(1, L, 1, device=dev)
+            return rvc_oracle.infer(w, cfg, phone.to(dt), lens, pitch, pitchf, sid, nz, ri, ns)[0]
+
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            o = step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        del w, o
+        torch.cuda.empty_cache()
+        return T * cfg.upp / cfg.sr / (ms / 1e3), ms
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+
+
+def parity_block(net, cfg, T: int, precision: str, config_name: str):
+    """One more step of the timed workload with the fixture's seeded noise injected (the timed steps draw theirs on the
+    device like the reference, so their waveforms are not comparable sample by sample), checked OUTSIDE the timed region
+    against the waveform the unmodified reference produced for this step in the build container
+    (tests/golden/g2_48k_v2_T6000.npz, minted by tests/golden/make_golden_big.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "g2_48k_v2_T6000.npz")
+    if config_name != "48k_v2" or T != 6000 or not os.path.exists(path):
+        return {"checked": False, "why": "the reference-minted fixture covers the default workload only (48k_v2, T=6000)"}
+    gold = np.load(path, allow_pickle=True)
+    inputs = synthetic.make_inputs(cfg, 1, T, seed=int(gold["meta"][6]))
+    noise = synthetic.draw_noise(cfg, 1, T, seed=int(gold["meta"][7]))
+    dev = net._device
+    o = net.infer(*[t.to(dev) for t in inputs], noise=noise)[0][0, 0].cpu().numpy()
+    i16 = gold["o_i16"][0].astype(np.float64)
+    ref = (i16 + 0.5 * np.sign(i16)) * float(gold["audio_max"][0]) / 32768.0       # mid-point of the truncation step
+    d = np.abs(synthetic.to_int16(o).astype(np.int32) - gold["o_i16"][0].astype(np.int32))
+    gate = "int16 within +-1 LSB" if precision == "fp32" else "SNR >= 45 dB"
+    snr = synthetic.snr_db(ref, o)
+    ok = bool(d.max() <= 1) if precision == "fp32" else bool(snr >= 45.0)
+    return {"checked": True, "against": "tests/golden/g2_48k_v2_T6000.npz (unmodified reference, fp32 CPU, same weights / inputs / noise)",
+            "snr_db": snr, "int16_max_lsb_diff": int(d.max()), "int16_frac_differing": float((d > 0).mean()),
+            "gate": gate, "pass": ok, "samples": int(o.shape[0])}
+
+
+def measured_traffic(precision: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel class from the committed ncu capture of this
+    build (profiles/r2_dram_traffic.json, written by tools/ncu_traffic.py from `ncu --metrics dram__bytes_*` over one
+    step of this command); None if no capture exists for the precision."""
+    p = os.path.join(ROOT, "profiles", "r2_dram_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(precision)
+    return d
 
 
 _REAL_STDOUT = None
@@ -189,8 +285,13 @@ def main():
                          "dtype, same speed, ~61 dB) or fp32 (CUDA-core path, +-1 LSB gate)")
     ap.add_argument("--config", default="48k_v2")
     ap.add_argument("--seconds", type=float, default=60.0)
-    ap.add_argument("--cpu-frames", type=int, default=300, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=0,
+                    help="frames per step of the CPU arms (default 0 = the full step, same T as the product arm)")
+    ap.add_argument("--cpu-1thread-frames", type=int, default=500, help="frames of the bounded 1-thread CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-incumbent", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-extra-precision", action="store_true", help="skip the fp16 leg beside the bf16 headline")
     args = ap.parse_args()
 
     cfg = NAMED_CONFIGS[args.config]
@@ -201,6 +302,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     workload = f"{args.config} SynthesizerTrnMs{cfg.feat_dim}NSFsid.infer, B=1, T={T} frames ({audio_s:.0f} s segment) per GPU"
     metric = "seconds of output audio synthesised per second (RTF^-1)"
+    # the SAME dict in both arms (the driver compares them): it names the workload only
+    config = {"workload": workload, "parallelism": f"segments x{world}, no collective",
+              "l2": "no flush needed: each step streams >1 GB of stage activations (>> 126 MB L2)"}
+    cpu_T = args.cpu_frames if args.cpu_frames > 0 else T
 
     # ------------------------------------------------------------------ reference arm (CPU) -------
     if args.impl == "reference":
@@ -208,20 +313,24 @@ def main():
             return
         threads = os.cpu_count() or 1
         steps, warm = max(1, args.steps), max(0, args.warmup)
-        # bounded sample: cpu_frames (default 300 = 3 s of audio, ~0.3 s of CPU work on a 16-core host) of the same workload
-        # per step, EXACTLY `steps` timed steps after `warm` untimed ones; value = audio produced / total time of the K steps
-        _, sample_s, times = cpu_oracle_rate(cfg, args.cpu_frames, steps, warm, threads)
+        # every step is the product arm's step: one full infer() of T frames on all host cores (oracle port, fp32).
+        # EXACTLY `steps` timed steps after `warm` untimed ones; value = audio produced / total time of the K steps
+        chk = {}
+        _, sample_s, times = cpu_oracle_rate(cfg, cpu_T, steps, warm, threads, check=chk)
         rate = steps * sample_s / float(np.sum(times))
+        sample = (f"oracle/rvc_oracle.py (fp32 PyTorch CPU restatement of the reference infer), {cpu_T} frames = {sample_s:.1f} s "
+                  f"audio per step" + (" = the full step" if cpu_T == T else " (bounded sample of the step)"))
         line = {
             "impl": "reference", "metric": metric, "value": rate, "unit": "audio-s/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": float(np.mean(times)) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "timed_sample": f"{args.cpu_frames} frames ({sample_s:.1f} s of audio) per step"},
-            "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                             "sample": f"oracle/rvc_oracle.py (fp32 PyTorch CPU restatement of the reference infer), "
-                                       f"{args.cpu_frames} frames = {sample_s:.1f} s audio per step"},
+            "config": config, "timed_sample": sample,
+            "cpu_baseline": {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
+        pin = oracle_vs_fixture(chk.get("first_timed_output"), args.config, cpu_T)
+        if pin:
+            line["oracle_vs_reference_fixture"] = pin
         emit(line)
         return
 
@@ -359,25 +468,23 @@ def main():
     achieved = conv_flops / conv_launches_per_step / (conv_ms_per_launch * 1e-3) / 1e12
     rb_rd, rb_wr = resblock_bytes(cfg, T)
     rb_bytes = (rb_rd + rb_wr) / max(conv_launches_per_step, 1)
-    rb_traffic = (1.001 * rb_rd + 0.80 * rb_wr) / max(conv_launches_per_step, 1) if args.precision != "fp32" else None
+    tr = measured_traffic(args.precision)
     h2d = sum(t.numel() * t.element_size() for t in host)
     line = {
         "metric": metric, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "fp16": "f16 operands, f32 accumulate", "bf16": "bf16 operands (resblocks) / f16 operands (ladder, encoder, flow), f32 accumulate"}[args.precision],
         "data": "synthetic (seeded random-init weights stored as fp16, N(0,1) features, contour f0)",
-        "config": {"workload": workload, "precision": args.precision, "parallelism": f"segments x{world}, no collective",
-                   "l2": "no flush needed: each step streams >1 GB of stage activations (>> 126 MB L2)",
-                   "roofline_pass": "per-launch CUDA events in a second pass of the same K steps (event records between kernels "
-                                    "would serialise the programmatic dependent launches of the timed pass)"},
+        "config": config, "precision": args.precision,
+        "roofline_pass": "per-launch CUDA events in a second pass of the same K steps (kept out of `value`)",
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": T * cfg.upp * 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "decoder resblock convolutions (rbconv_tc_kernel + fused-pair rbpair_tc_kernel on tcgen05; conv_f32_kernel in fp32 mode)",
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                     "traffic": rb_traffic, "traffic_note": "dram__bytes_read+write per launch, average over the class's launches of a step: "
-                     "algorithmic bytes x the read/write ratios ncu measured on sampled launches (profiles/r1_ncu_rbconv_v10.md, "
-                     "r1_ncu_rbpair_v2.md: reads 1.001 x algorithmic, writes 0.77-0.80 x -- the rest is still dirty in L2 at kernel end)",
+                     "traffic": (tr["bytes_per_step"] / tr["launches_per_step"]) if tr else None,
+                     "traffic_source": (tr["source"] if tr else "no ncu capture committed for this precision"),
+                     "peak_burst": peaks["burst"], "frac_of_burst": achieved / peaks["burst"],
                      "algorithmic_bytes_per_launch": rb_bytes, "achieved_hbm_gbs": rb_bytes / (conv_ms_per_launch * 1e-3) / 1e9,
                      "hbm_peak_gbs": peaks["hbm_gbs"], "hbm_frac": rb_bytes / (conv_ms_per_launch * 1e-3) / 1e9 / peaks["hbm_gbs"],
                      "peak_source": peaks["src"],
@@ -391,11 +498,52 @@ def main():
         "algorithmic_gflop_per_step": {k: 2.0 * v / 1e9 for k, v in macs.items()},
         "clocks": clocks,
     }
+    if not args.no_parity:
+        line["parity"] = parity_block(net, cfg, T, args.precision, args.config)
+    if world == 1 and args.precision == "bf16" and not args.no_extra_precision:
+        # the drop-in's own default for `is_half` checkpoints is fp16 operands (the reference's GPU dtype): same K steps
+        net.set_precision("fp16")
+        for _ in range(max(3, args.warmup)):
+            step_resident()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            step_resident()
+        g1.record()
+        torch.cuda.synchronize()
+        ms16 = g0.elapsed_time(g1)
+        line["fp16"] = {"value": args.steps * audio_s / (ms16 / 1e3), "unit": "audio-s/s", "ms_per_step": ms16 / args.steps,
+                        "note": "set_precision('fp16'): what get_vc(is_half=True) selects; device-resident inputs like `value`"}
+        if not args.no_parity:
+            line["fp16"]["parity"] = parity_block(net, cfg, T, "fp16", args.config)
+        net.set_precision(args.precision)
+    if world == 1 and not args.no_gpu_incumbent:
+        inc = {}
+        for name, half in (("fp16", True), ("fp32_tf32_off", False)):
+            try:
+                v, ms_i = gpu_incumbent_rate(cfg, T, dev, half)
+                inc[name] = {"value": v, "unit": "audio-s/s", "ms_per_step": ms_i}
+            except Exception as e:                      # e.g. out of memory on a smaller part: report, do not fail the line
+                inc[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        inc["what"] = ("eager PyTorch (cuDNN/cuBLAS) on this GPU: oracle/rvc_oracle.py, the reference's op sequence, on CUDA "
+                       "tensors, same step, 3 timed reps after 2 warm-ups; measurement context only, never on the product path")
+        line["gpu_incumbent"] = inc
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, sample_s, _ = cpu_oracle_rate(cfg, args.cpu_frames, 3, 1, threads)
+        # all host cores on the FULL step (one timed step after a short warm-up step), and one thread on a bounded sample
+        chk = {}
+        rate, sample_s, _ = cpu_oracle_rate(cfg, cpu_T, 1, 1, threads, warmup_T=min(200, cpu_T), check=chk)
+        n1 = min(args.cpu_1thread_frames, cpu_T)
+        rate1, sample1_s, _ = cpu_oracle_rate(cfg, n1, 1, 1, 1, warmup_T=min(100, n1))
         line["cpu_baseline"] = {"value": rate, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                                "sample": f"oracle/rvc_oracle.py fp32 PyTorch CPU, {args.cpu_frames} frames = {sample_s:.1f} s audio, median of 3"}
+                                "sample": f"oracle/rvc_oracle.py fp32 PyTorch CPU, {cpu_T} frames = {sample_s:.1f} s audio"
+                                          + (" (the full step)" if cpu_T == T else "") + ", one timed step",
+                                "one_thread": {"value": rate1, "unit": "audio-s/s", "cores": 1,
+                                               "sample": f"{n1} frames = {sample1_s:.1f} s audio, one timed step"}}
+        pin = oracle_vs_fixture(chk.get("first_timed_output"), args.config, cpu_T)
+        if pin:
+            line["cpu_baseline"]["oracle_vs_reference_fixture"] = pin
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

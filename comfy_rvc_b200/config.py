@@ -49,12 +49,19 @@ class SynthConfig:
         sr = a[17]
         if isinstance(sr, str):
             sr = SR2SR[sr]
+        dils = tuple(tuple(int(d) for d in ds) for ds in a[11])
+        if str(a[9]) != "1":
+            # ResBlock2 builds exactly two convs, from dilation[0] and dilation[1] (modules.py:319-339); further entries
+            # of the config list are ignored by the reference, fewer than two raise there as well
+            if any(len(ds) < 2 for ds in dils):
+                raise IndexError("ResBlock2 needs two dilations per kernel (modules.py:327,337)")
+            dils = tuple(ds[:2] for ds in dils)
         return SynthConfig(
             spec_channels=int(a[0]), segment_size=int(a[1]), inter_channels=int(a[2]),
             hidden_channels=int(a[3]), filter_channels=int(a[4]), n_heads=int(a[5]),
             n_layers=int(a[6]), kernel_size=int(a[7]), p_dropout=float(a[8]), resblock=str(a[9]),
             resblock_kernel_sizes=tuple(int(k) for k in a[10]),
-            resblock_dilation_sizes=tuple(tuple(int(d) for d in ds) for ds in a[11]),
+            resblock_dilation_sizes=dils,
             upsample_rates=tuple(int(u) for u in a[12]), upsample_initial_channel=int(a[13]),
             upsample_kernel_sizes=tuple(int(k) for k in a[14]), spk_embed_dim=int(a[15]),
             gin_channels=int(a[16]), sr=int(sr), feat_dim=int(feat_dim), f0=bool(f0),
@@ -128,6 +135,31 @@ def nono(cfg: SynthConfig) -> SynthConfig:
     """The no-f0 variant of a configuration (`SynthesizerTrnMs{256,768}NSFsid_nono`)."""
     from dataclasses import replace
     return replace(cfg, f0=False)
+
+
+def resblock2(cfg: SynthConfig, kernels=(3, 7, 11), dilations=((1, 3), (1, 3), (1, 3))) -> SynthConfig:
+    """A configuration with `resblock="2"` (modules.ResBlock2, modules.py:311-355: one conv per dilation, no pair;
+    selected at models.py:496).  No shipped config uses it; the defaults are ResBlock2's own `dilation=(1, 3)`."""
+    from dataclasses import replace
+    return replace(cfg, resblock="2", resblock_kernel_sizes=tuple(kernels),
+                   resblock_dilation_sizes=tuple(tuple(d)[:2] for d in dilations))
+
+
+VARIANTS = {
+    "nono": nono,
+    "rb2": resblock2,
+    # HiFi-GAN V3-like kernel/dilation table (values outside the shipped one: exercises the generic conv kernels)
+    "rb2x": lambda cfg: resblock2(cfg, (3, 5, 7), ((1, 2), (2, 6), (3, 8))),
+}
+
+
+def resolve(name: str) -> SynthConfig:
+    """`"48k_v2"`, `"40k:nono"`, `"40k:rb2"` ... -> SynthConfig (fixture metadata stores these names)."""
+    base, *mods = name.split(":")
+    cfg = NAMED_CONFIGS[base]
+    for m in mods:
+        cfg = VARIANTS[m](cfg)
+    return cfg
 
 
 def state_dict_shapes(cfg: SynthConfig) -> Dict[str, Tuple[int, ...]]:

@@ -239,13 +239,8 @@ __global__ void __launch_bounds__(NTHR) attention_f32_kernel(const float* __rest
 cudaError_t launch_attention_f32(const float* qkv, const float* rel_k, const float* rel_v, const int* len, float* out,
                                  int B, int T, int n_heads, int dk, int window, cudaStream_t st) {
   if (dk != DK || 2 * window + 1 > MAXR || B <= 0 || T <= 0) return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(AttnSmem));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(attention_f32_kernel, sizeof(AttnSmem), opt)) return e;
   dim3 grid((T + BQ - 1) / BQ, n_heads, B);
   attention_f32_kernel<<<grid, NTHR, sizeof(AttnSmem), st>>>(qkv, rel_k, rel_v, len, out, T, n_heads, window);
   launch_counter().n++;

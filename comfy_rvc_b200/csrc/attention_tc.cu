@@ -485,12 +485,8 @@ cudaError_t launch_attention_tc(const void* qkv16, void* vt, const void* ek16, c
     if (!make_map(&tmEv, evt16, 2, evd, evs, boxev)) return cudaErrorInvalidValue;
   }
   const size_t smem = sizeof(AttSmem) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(attention_tc_kernel, smem, opt)) return e;
   AttArgs a;
   a.len = len; a.out = reinterpret_cast<__half*>(out); a.T = T; a.n_heads = n_heads; a.window = window; a.H = n_heads * DKV;
   dim3 grid((T + BQ - 1) / BQ, n_heads, B);

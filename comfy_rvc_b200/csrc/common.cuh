@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/rvcb200.h"
 
 namespace rvc {
@@ -43,6 +45,30 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
+
+// ---- per-device launch state ---------------------------------------------------------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel and the SM count is a property of
+// the current device, so both are cached per device ordinal (a process may run `SynthesizerB200.to("cuda:1")` after
+// cuda:0).  Atomics only: a redundant cudaFuncSetAttribute from a racing thread is harmless.
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+  std::atomic<size_t> bytes[kMaxDevices];
+  SmemOptIn() { for (auto& b : bytes) b.store(0); }
+};
+template <typename Kern>
+inline cudaError_t opt_in_smem(Kern kern, size_t smem, SmemOptIn& cache) {
+  if (smem <= 48 * 1024) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const bool cached = dev >= 0 && dev < kMaxDevices;
+  if (cached && cache.bytes[dev].load(std::memory_order_acquire) >= smem) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (cached) cache.bytes[dev].store(smem, std::memory_order_release);
+  return cudaSuccess;
+}
+int current_num_sms();   // SM count of the current device (small_kernels.cu)
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }

@@ -240,12 +240,8 @@ cudaError_t launch_t(const ConvDesc& d, int B, cudaStream_t st) {
   const int halo = (d.ntaps - 1) * d.dil;
   const int lda = lda_for(TL::BM + halo);
   const size_t smem = sizeof(float) * (2 * BK * lda + 2 * (size_t)d.ntaps * BK * BN);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_f32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(conv_f32_kernel<BN>, smem, opt)) return e;
   dim3 grid((d.Lj + TL::BM - 1) / TL::BM, d.Cout / BN, B * d.G);
   conv_f32_kernel<BN><<<grid, kThreads, smem, st>>>(d);
   launch_counter().n++;

@@ -867,19 +867,10 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return cudaErrorInvalidValue;
   }
-  static size_t cfgd = 0;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
-  if (smem > cfgd) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cfgd = smem;
-  }
+  static SmemOptIn opt_s, opt_g;
+  const int num_sms = current_num_sms();
+  if (cudaError_t e = opt_in_smem(conv_tc_kernel<false>, smem, opt_s)) return e;
+  if (cudaError_t e = opt_in_smem(conv_tc_kernel<true>, smem, opt_g)) return e;
   unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);            // persistent: one CTA per SM
   if (d.b_stationary && d.G > 1) grid = (unsigned)((num_sms / d.G) * d.G);  // every tile of a CTA has phase blockIdx.x % G
   cudaError_t le = d.generic ? launch_pdl(conv_tc_kernel<true>, dim3(grid), dim3(kThreadsTC), smem, st, d, tmA, tmW, tmY)
@@ -916,12 +907,8 @@ cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* 
   };
   while (TR > 8 && smem_for(TR) > 100 * 1024) TR >>= 1;
   const size_t smem = smem_for(TR);
-  static size_t cfgd = 48 * 1024;
-  if (smem > cfgd) {
-    cudaError_t e = cudaFuncSetAttribute(noise_add_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cfgd = smem;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(noise_add_tile_kernel, smem, opt)) return e;
   const long long n_tiles = (L + TR - 1) / TR;
   const long long per = smem > 56 * 1024 ? 2 : 4;                  // resident blocks per SM
   dim3 grid((unsigned)(n_tiles < 148 * per ? n_tiles : 148 * per), B);
@@ -941,12 +928,8 @@ cudaError_t launch_noise_add16(const float* har, const float* wn, const float* n
   auto smem_for = [&](int tr) { return sizeof(float) * ((size_t)k * C + C + (size_t)(tr + (k + s - 1) / s) * (s + 1)); };
   while (TR > 8 && smem_for(TR) > 100 * 1024) TR >>= 1;
   const size_t smem = smem_for(TR);
-  static size_t cfgd = 48 * 1024;
-  if (smem > cfgd) {
-    cudaError_t e = cudaFuncSetAttribute(noise_add16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cfgd = smem;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(noise_add16_kernel, smem, opt)) return e;
   const long long n_tiles = (L + TR - 1) / TR;
   const long long per = smem > 56 * 1024 ? 2 : (smem > 24 * 1024 ? 4 : 8);
   dim3 grid((unsigned)(n_tiles < 148 * per ? n_tiles : 148 * per), B);

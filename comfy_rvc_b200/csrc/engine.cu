@@ -306,6 +306,8 @@ int rvcb200_create(const rvcb200_config* cfg, rvcb200_ctx** out) {
   }
   for (int j = 0; ok && j < f.n_res_kernels; ++j) {
     if (f.res_kernels[j] % 2 != 1 || f.n_res_dils[j] < 1 || f.n_res_dils[j] > RVCB200_MAX_DIL) ok = false;
+    // ResBlock2 has exactly two convs (modules.py:319-339); the fp32 decoder's XB/XT hand-over below relies on it
+    if (f.resblock_kind == 2 && f.n_res_dils[j] != 2) ok = false;
     for (int d = 0; ok && d < f.n_res_dils[j]; ++d)
       if ((f.res_kernels[j] - 1) * f.res_dils[j][d] > 50) ok = false;
   }
@@ -345,6 +347,19 @@ int rvcb200_profile_collect(rvcb200_ctx* ctx, double* ms, int64_t* count) {
   ctx->ev_used = 0;
   for (int i = 0; i < RVCB200_PROF_CLASSES; ++i) { ms[i] = ctx->cls_ms[i]; count[i] = ctx->cls_n[i]; }
   return RVCB200_OK;
+}
+
+int64_t rvcb200_profile_launches(rvcb200_ctx* ctx, int32_t* cls, float* ms, int64_t cap) {
+  if (!ctx || !cls || cap < 0) return -1;
+  const int64_t n = (int64_t)(ctx->ev_used / 2);
+  for (int64_t i = 0; i < n && i < cap; ++i) {
+    cls[i] = ctx->ev_cls[i];
+    if (ms) {
+      if (cudaEventSynchronize(ctx->ev[2 * i + 1]) != cudaSuccess) return -1;
+      if (cudaEventElapsedTime(&ms[i], ctx->ev[2 * i], ctx->ev[2 * i + 1]) != cudaSuccess) return -1;
+    }
+  }
+  return n;
 }
 
 int rvcb200_set_tensor(rvcb200_ctx* ctx, const char* name, const void* dev_ptr, int64_t numel, int32_t dtype) {

@@ -530,19 +530,9 @@ cudaError_t launch_one(const TcConvDesc& d, int B, cudaStream_t st) {
         return cudaErrorInvalidValue;
     }
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rbconv_tc_kernel<C, NTAPS, DIL, MSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)K::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(rbconv_tc_kernel<C, NTAPS, DIL, MSUB>, K::SMEM, opt)) return e;
+  const int num_sms = current_num_sms();
   TcConvDesc p = d;
   p.batch = B;
   const long long tiles = (long long)((d.Lj + K::TILE_M - 1) / K::TILE_M) * B;

@@ -587,19 +587,9 @@ cudaError_t launch_pair_one(const TcConvDesc& d1, const TcConvDesc& d2, int B, c
         return cudaErrorInvalidValue;
     }
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(rbpair_tc_kernel<C, NTAPS, DIL, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)K::SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(rbpair_tc_kernel<C, NTAPS, DIL, VAR>, K::SMEM, opt)) return e;
+  const int num_sms = current_num_sms();
   PairParams p{};
   p.bias1 = d1.bias; p.bias2 = d2.bias;
   p.L = L; p.batch = B;

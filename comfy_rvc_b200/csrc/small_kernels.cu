@@ -12,6 +12,18 @@ LaunchCounter& launch_counter() {
   return c;
 }
 
+int current_num_sms() {
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const bool cached = dev >= 0 && dev < kMaxDevices;
+  int n = cached ? cache[dev].load(std::memory_order_acquire) : 0;
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  if (cached) cache[dev].store(n, std::memory_order_release);
+  return n;
+}
+
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("RVCB200_PDL"); return e ? atoi(e) != 0 : false; }();
   return on;
@@ -233,12 +245,8 @@ cudaError_t launch_noise_conv_add(const float* har, const float* wn, const float
                                   long long L_out, int C, int k, int s, int pad, cudaStream_t st) {
   if (C % 4 != 0) return cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * ((size_t)k * C + C);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(noise_conv_add_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(noise_conv_add_kernel<4>, smem, opt)) return e;
   const long long total = L_out * (C / 4);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -252,12 +260,8 @@ cudaError_t launch_conv_post_tanh(const float* x, const float* w, float* out, in
                                   float slope, cudaStream_t st) {
   const int TB = 256;
   const size_t smem = sizeof(float) * ((size_t)(TB + k - 1) * (C + 1) + (size_t)k * C);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_post_tanh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
+  static SmemOptIn opt;
+  if (cudaError_t e = opt_in_smem(conv_post_tanh_kernel, smem, opt)) return e;
   dim3 grid((unsigned)((L + TB - 1) / TB), B);
   conv_post_tanh_kernel<<<grid, TB, smem, st>>>(x, w, out, L, C, k, slope);
   launch_counter().n++;

@@ -134,6 +134,11 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T,
 #define RVCB200_PROF_CLASSES 8
 int rvcb200_profile_enable(rvcb200_ctx* ctx, int32_t on);
 int rvcb200_profile_collect(rvcb200_ctx* ctx, double* ms, int64_t* count);
+/* Class (0..RVCB200_PROF_CLASSES-1) and CUDA-event time of every launch recorded since `enable`, in launch order: lets a
+ * profiler's per-launch list (ncu) be joined with the classes above.  Call BEFORE `collect` (which resets the
+ * record); synchronises on the events.  Returns the number of launches recorded (may exceed `cap`; at most `cap`
+ * entries are written), < 0 on error.  `ms` may be NULL. */
+int64_t rvcb200_profile_launches(rvcb200_ctx* ctx, int32_t* cls, float* ms, int64_t cap);
 
 /* Number of kernel launches the last `rvcb200_infer` enqueued (bench.py's gpu_launches). */
 int64_t rvcb200_last_launch_count(const rvcb200_ctx* ctx);

@@ -69,7 +69,7 @@ def _attention(w, pfx, x, attn_mask, n_heads, window):
     rel_k = w[pfx + ".emb_rel_k"]                              # [1, 2w+1, dk] (heads_share)
     rel_v = w[pfx + ".emb_rel_v"]
     rel_logits = torch.matmul(qs, rel_k.unsqueeze(0).transpose(-2, -1))   # [B,h,T,2w+1]
-    idx = torch.arange(T)
+    idx = torch.arange(T, device=x.device)
     for r in range(2 * window + 1):
         off = r - window                                        # key j = i + off
         i0, i1 = max(0, -off), min(T, T - off)
@@ -80,7 +80,7 @@ def _attention(w, pfx, x, attn_mask, n_heads, window):
     scores = scores.masked_fill(attn_mask == 0, -1e4)          # :245-246
     p = F.softmax(scores, dim=-1)
     out = torch.matmul(p, v)
-    band = torch.zeros(B, n_heads, T, 2 * window + 1, dtype=p.dtype)
+    band = torch.zeros(B, n_heads, T, 2 * window + 1, dtype=p.dtype, device=p.device)
     for r in range(2 * window + 1):
         off = r - window
         i0, i1 = max(0, -off), min(T, T - off)
@@ -111,7 +111,7 @@ def text_encoder(w, cfg, phone, pitch, lengths):
     x = F.leaky_relu(x, 0.1)
     x = x.transpose(1, -1)
     T = x.shape[2]
-    x_mask = (torch.arange(T).unsqueeze(0) < lengths.unsqueeze(1)).unsqueeze(1).to(x.dtype)  # commons.py:232-236
+    x_mask = (torch.arange(T, device=x.device).unsqueeze(0) < lengths.unsqueeze(1)).unsqueeze(1).to(x.dtype)  # commons.py:232-236
     attn_mask = x_mask.unsqueeze(2) * x_mask.unsqueeze(-1)
     x = x * x_mask
     x = x * x_mask
@@ -186,6 +186,7 @@ def sine_source(w, cfg, f0, rand_ini, noise_sine):
     noise_amp = uv * 0.003 + (1 - uv) * 0.1 / 3                       # :408
     noise = noise_amp * noise_sine.float()                            # :409
     sine = sine * uv + noise                                          # :410
+    sine = sine.to(w["dec.m_source.l_linear.weight"].dtype)           # :464-465 (`.half()` when is_half; no-op in fp32)
     merged = torch.tanh(F.linear(sine, w["dec.m_source.l_linear.weight"], w["dec.m_source.l_linear.bias"]))  # :466
     return merged.transpose(1, 2)                                     # [B,1,L]
 
@@ -249,7 +250,7 @@ def infer(sd_folded, cfg, phone, phone_lengths, pitch, nsff0, sid, noise_zp, ran
     """
     w = sd_folded
     g = F.embedding(sid, w["emb_g.weight"]).unsqueeze(-1)            # [B,256,1]
-    m_p, logs_p, x_mask = text_encoder(w, cfg, phone.float(), pitch, phone_lengths)
+    m_p, logs_p, x_mask = text_encoder(w, cfg, phone.to(w["emb_g.weight"].dtype), pitch, phone_lengths)
     z_p = (m_p + torch.exp(logs_p) * noise_zp * 0.66666) * x_mask
     if rate:
         head = int(z_p.shape[2] * rate)
@@ -271,7 +272,7 @@ def infer_nono(sd_folded, cfg, phone, phone_lengths, sid, noise_zp, rate=None, t
     text encoder (`enc_p(phone, None, lengths)`, models.py:50-53), plain `Generator` decoder, one RNG draw."""
     w = sd_folded
     g = F.embedding(sid, w["emb_g.weight"]).unsqueeze(-1)
-    m_p, logs_p, x_mask = text_encoder(w, cfg, phone.float(), None, phone_lengths)
+    m_p, logs_p, x_mask = text_encoder(w, cfg, phone.to(w["emb_g.weight"].dtype), None, phone_lengths)
     z_p = (m_p + torch.exp(logs_p) * noise_zp * 0.66666) * x_mask
     if rate:
         head = int(z_p.shape[2] * rate)

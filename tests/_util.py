@@ -8,20 +8,18 @@ import numpy as np
 import torch
 
 from comfy_rvc_b200 import synthetic
-from comfy_rvc_b200.config import NAMED_CONFIGS, nono
+from comfy_rvc_b200.config import NAMED_CONFIGS, resolve
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["c1_40k_v1", "c2_48k_v2", "c3_32k_v2_ragged", "c4_48k_v2_unvoiced", "c5_48k_v1_5stage", "c6_40k_v1_tiny",
-                "c7_40k_v1_nono", "c8_48k_v2_nono_ragged"]
+                "c7_40k_v1_nono", "c8_48k_v2_nono_ragged", "c9_40k_v1_resblock2", "c10_48k_v2_resblock2x"]
 
 
 def load_golden(name):
     """Returns (cfg, state_dict, inputs, noise, golden arrays) for one fixture minted by make_golden.py."""
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=True)
     cfg_name, B, T, lengths, f0v, wseed, iseed, nseed, _torch_ver = [str(x) for x in z["meta"]]
-    cfg = NAMED_CONFIGS[cfg_name.split(":")[0]]
-    if cfg_name.endswith(":nono"):                 # the no-f0 classes (models.py:812-1021)
-        cfg = nono(cfg)
+    cfg = resolve(cfg_name)                        # ":nono" = the no-f0 classes (models.py:812-1021), ":rb2" = ResBlock2
     B, T = int(B), int(T)
     lengths = ast.literal_eval(lengths)
     sd = synthetic.make_state_dict(cfg, seed=int(wseed))

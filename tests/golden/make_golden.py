@@ -26,7 +26,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from comfy_rvc_b200.config import NAMED_CONFIGS, nono, state_dict_shapes  # noqa: E402
+from comfy_rvc_b200.config import resolve, state_dict_shapes  # noqa: E402
 from comfy_rvc_b200 import synthetic  # noqa: E402
 
 CASES = [
@@ -40,6 +40,10 @@ CASES = [
     # no-f0 synthesizers (SynthesizerTrnMs{256,768}NSFsid_nono, models.py:812-1021): config name suffixed ":nono"
     ("c7_40k_v1_nono", "40k:nono", 1, 110, None, "contour",  0, 6, 12),
     ("c8_48k_v2_nono_ragged", "48k_v2:nono", 2, 80, [80, 57], "contour", 0, 7, 13),
+    # ResBlock2 decoders (modules.py:311-355, selected at models.py:496 when resblock != "1"); ":rb2x" has kernel/dilation
+    # values outside the shipped table
+    ("c9_40k_v1_resblock2", "40k:rb2", 1, 100, None, "contour", 0, 8, 14),
+    ("c10_48k_v2_resblock2x", "48k_v2:rb2x", 2, 72, [72, 50], "contour", 0, 9, 15),
 ]
 
 
@@ -74,10 +78,11 @@ def sha(a: np.ndarray) -> str:
 def main():
     torch.set_num_threads(1)        # pin: 1 vs 8 threads already moves 1 LSB
     ref_models = import_reference()
+    only = set(sys.argv[1:])
     for name, cfg_name, B, T, lengths, f0v, wseed, iseed, nseed in CASES:
-        cfg = NAMED_CONFIGS[cfg_name.split(":")[0]]
-        if cfg_name.endswith(":nono"):
-            cfg = nono(cfg)
+        if only and name not in only:
+            continue
+        cfg = resolve(cfg_name)
         sd = synthetic.make_state_dict(cfg, seed=wseed)
         net = build_reference_model(ref_models, cfg, sd)
         phone, lens, pitch, pitchf, sid = synthetic.make_inputs(cfg, B, T, seed=iseed, lengths=lengths, f0_variant=f0v)

@@ -117,3 +117,19 @@ def test_no_fallback_without_weights():
     net = rvc.SynthesizerTrnMs256NSFsid(*cfg.to_positional(), is_half=False)
     with pytest.raises(RuntimeError):
         net.infer(*[t.cuda() for t in synthetic.make_inputs(cfg, 1, 8)])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two CUDA devices in one process")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_same_process_two_devices(precision):
+    """The per-kernel shared-memory opt-in and the SM count are per-device state (csrc/common.cuh opt_in_smem):
+    a process that synthesises on cuda:0 and then on cuda:1 must get the same waveform on both."""
+    cfg, sd, inputs, noise, gold = load_golden("c2_48k_v2")
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        net = build_net(cfg, sd, precision).to(dev).set_precision(precision)
+        o = net_infer(net, cfg, inputs, noise, device=dev)[0]
+        torch.cuda.synchronize(dev)
+        outs.append(o.cpu())
+    assert torch.equal(outs[0], outs[1])
+    assert int16_lsb_diff(gold["o_f32"][0], outs[1][0, 0].numpy()) <= (1 if precision == "fp32" else 400)
