@@ -59,7 +59,7 @@ def algorithmic_macs(cfg, T: int) -> dict:
 
 def pair_is_fused(C: int, k: int) -> bool:
     """ResBlock1 pairs that run as ONE kernel with h in shared memory (csrc/rbpair_tc.cu: rbpair_tc_supported)."""
-    return os.environ.get("RVCB200_FUSE_PAIRS", "1") != "0" and C in (32, 64) and k in (3, 7)
+    return os.environ.get("RVCB200_FUSE_PAIRS", "1") != "0" and C in (32, 64) and (k in (3, 7) or (k == 11 and C == 32))
 
 
 def resblock_bytes(cfg, T: int):

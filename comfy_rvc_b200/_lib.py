@@ -90,7 +90,8 @@ SYMBOLS = {
                                 C.c_void_p, C.c_int64, C.c_int32, C.POINTER(RvcTap), C.c_int32, C.c_void_p]),
     "rvcb200_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "rvcb200_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
-    "rvcb200_profile_launches": (C.c_int64, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.c_int64]),
+    "rvcb200_profile_launches": (C.c_int64, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                           C.c_int64]),
     "rvcb200_last_launch_count": (C.c_int64, [C.c_void_p]),
     "rvcb200_last_error": (C.c_char_p, [C.c_void_p]),
     "rvcb200_op_conv_f32": (C.c_int, [C.POINTER(ConvDesc), C.c_int32, C.c_void_p]),
@@ -111,6 +112,8 @@ SYMBOLS = {
     "rvcb200_op_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "rvcb200_op_to_int16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rvcb200_host_quiet_point": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
+    "rvcb200_host_filtfilt_pad": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
+                                            C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

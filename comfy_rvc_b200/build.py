@@ -12,7 +12,9 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librvcb200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--fmad=true", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "--fmad=true", "-cudart", "static",
+              # host code: no FMA contraction (csrc/host_plan.cu restates scipy's lfilter bit for bit)
+              "-Xcompiler", "-ffp-contract=off"]
 
 
 def sources():

@@ -35,6 +35,7 @@ struct rvcb200_ctx {
   bool prof = false;
   std::vector<cudaEvent_t> ev;   // pairs (start, stop)
   std::vector<int> ev_cls;
+  std::vector<int> ev_nk;        // kernels launched inside the scope (a launcher may enqueue several)
   size_t ev_used = 0;
   double cls_ms[RVCB200_PROF_CLASSES] = {0};
   long long cls_n[RVCB200_PROF_CLASSES] = {0};
@@ -243,6 +244,7 @@ struct ProfScope {  // records an event pair around one launch when profiling is
   rvcb200_ctx* c;
   cudaStream_t st;
   bool on;
+  long long n0 = 0;
   ProfScope(rvcb200_ctx* c_, int cls, cudaStream_t st_) : c(c_), st(st_), on(c_->prof) {
     if (!on) return;
     if (c->ev_used + 2 > c->ev.size()) {
@@ -251,12 +253,15 @@ struct ProfScope {  // records an event pair around one launch when profiling is
       c->ev.push_back(a); c->ev.push_back(b);
     }
     c->ev_cls.resize(c->ev.size() / 2);
+    c->ev_nk.resize(c->ev.size() / 2);
     c->ev_cls[c->ev_used / 2] = cls;
+    n0 = launch_counter().n;
     cudaEventRecord(c->ev[c->ev_used], st);
   }
   ~ProfScope() {
     if (!on) return;
     cudaEventRecord(c->ev[c->ev_used + 1], st);
+    c->ev_nk[c->ev_used / 2] = (int)(launch_counter().n - n0);
     c->ev_used += 2;
   }
 };
@@ -349,11 +354,12 @@ int rvcb200_profile_collect(rvcb200_ctx* ctx, double* ms, int64_t* count) {
   return RVCB200_OK;
 }
 
-int64_t rvcb200_profile_launches(rvcb200_ctx* ctx, int32_t* cls, float* ms, int64_t cap) {
+int64_t rvcb200_profile_launches(rvcb200_ctx* ctx, int32_t* cls, int32_t* nkern, float* ms, int64_t cap) {
   if (!ctx || !cls || cap < 0) return -1;
   const int64_t n = (int64_t)(ctx->ev_used / 2);
   for (int64_t i = 0; i < n && i < cap; ++i) {
     cls[i] = ctx->ev_cls[i];
+    if (nkern) nkern[i] = ctx->ev_nk[i];
     if (ms) {
       if (cudaEventSynchronize(ctx->ev[2 * i + 1]) != cudaSuccess) return -1;
       if (cudaEventElapsedTime(&ms[i], ctx->ev[2 * i], ctx->ev[2 * i + 1]) != cudaSuccess) return -1;

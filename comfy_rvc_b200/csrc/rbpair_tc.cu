@@ -50,6 +50,8 @@ constexpr PairSel pair_sel(int C, int NTAPS, int variant) {
     return variant == 0 ? PairSel{1, 1, 1, 1, 1, 1} : PairSel{1, 1, 1, 1, 2, 1};
   }
   if (NTAPS == 3) return variant == 0 ? PairSel{2, 1, 1, 1, 2, 1} : PairSel{1, 2, 2, 1, 2, 2};
+  // C = 32, k = 11: 88 KB of weights; two h tiles and a conv1 look-ahead of one tile leave three slab slots at dilation 5
+  if (NTAPS == 11) return variant == 0 ? PairSel{1, 2, 1, 1, 2, 1} : PairSel{1, 1, 1, 1, 2, 1};
   return variant == 0 ? PairSel{1, 2, 2, 1, 2, 1} : PairSel{1, 2, 2, 1, 2, 2};
 }
 
@@ -630,13 +632,14 @@ cudaError_t launch_pair_v(const TcConvDesc& d1, const TcConvDesc& d2, int B, cud
 }  // namespace
 
 // The fused kernel covers a (conv1, conv2) pair when both are resblock shapes of rbconv_tc.cu with C in {32, 64},
-// k in {3, 7} (both weight sets resident in shared memory), conv2 has dilation 1 and consumes conv1's 16-bit output,
+// k in {3, 7} -- and k = 11 at C = 32 -- (both weight sets resident in shared memory: C = 64, k = 11 would need 176 KB),
+// conv2 has dilation 1 and consumes conv1's 16-bit output,
 // the residual is the pair's own input stream, and the output does not alias it (tiles read a halo of the input).
 bool rbpair_tc_supported(const TcConvDesc& d1, const TcConvDesc& d2) {
   if (!rbconv_tc_supported(d1) || !rbconv_tc_supported(d2)) return false;
   if (d1.tanh_out || d2.tanh_out || d1.acc_nostore || d2.acc_nostore || d1.inj_har || d2.inj_har) return false;
   if (!(d1.Cin == 32 || d1.Cin == 64) || d2.Cin != d1.Cin) return false;
-  if (!(d1.ntaps == 3 || d1.ntaps == 7) || d2.ntaps != d1.ntaps || d2.dil != 1) return false;
+  if (!(d1.ntaps == 3 || d1.ntaps == 7 || (d1.ntaps == 11 && d1.Cin == 32)) || d2.ntaps != d1.ntaps || d2.dil != 1) return false;
   if (d1.Lj != d2.Lj || d1.L_in != d2.L_in) return false;
   if (!d1.y16 || d1.y32 || d1.res16 || d1.accum || d1.div != 1.f) return false;      // conv1: 16-bit store of lrelu(.) only
   if (d2.x16 != d1.y16 || d1.out_bf16 != d2.in_bf16) return false;                   // conv2 consumes h
@@ -648,6 +651,7 @@ bool rbpair_tc_supported(const TcConvDesc& d1, const TcConvDesc& d2) {
 
 cudaError_t launch_rbpair_tc(const TcConvDesc& d1, const TcConvDesc& d2, int B, cudaStream_t st) {
   if (!rbpair_tc_supported(d1, d2) || B <= 0) return cudaErrorNotSupported;
+  if (d1.Cin == 32 && d1.ntaps == 11) return launch_pair_v<32, 11>(d1, d2, B, st);
   if (d1.Cin == 32) return d1.ntaps == 3 ? launch_pair_v<32, 3>(d1, d2, B, st) : launch_pair_v<32, 7>(d1, d2, B, st);
   return d1.ntaps == 3 ? launch_pair_v<64, 3>(d1, d2, B, st) : launch_pair_v<64, 7>(d1, d2, B, st);
 }

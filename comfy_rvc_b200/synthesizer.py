@@ -17,6 +17,8 @@ device `infer` raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -58,6 +60,14 @@ class SynthesizerB200(nn.Module):
         self._ws: Optional[torch.Tensor] = None
         self._tc_done = set()
         self.last_launches = 0
+        # CUDA graphs: an infer() of at most `graph_max_frames` frames (B*T) is launch-bound (one C call enqueues ~170
+        # kernels, ~13 us of host work each), so its launch sequence is captured once per (B, T, precision) into a CUDA
+        # graph over static buffers and replayed (0 disables; RVCB200_GRAPH_FRAMES overrides the default)
+        self.graph_max_frames = int(os.environ.get("RVCB200_GRAPH_FRAMES", "2500"))
+        self.graph_cache_size = 16
+        self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
+        self._graph_ws: Optional[torch.Tensor] = None
+        self.last_graph_replay = False
 
     # ---- nn.Module protocol the reference callers use ------------------------------------------
     def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
@@ -104,13 +114,20 @@ class SynthesizerB200(nn.Module):
     def set_precision(self, precision: str):
         if precision not in _lib.PREC:
             raise ValueError(precision)
+        if precision != self.precision:
+            self._drop_graphs()                  # the captured launches point at the previous precision's weight images
         self.precision = precision
         if self._ctx is not None:
             self._ensure_tc()
         return self
 
     # ---- engine management ----------------------------------------------------------------------
+    def _drop_graphs(self):
+        self._graphs.clear()
+        self._graph_ws = None
+
     def _release(self):
+        self._drop_graphs()
         if self._ctx is not None:
             _lib.load().rvcb200_destroy(self._ctx)
         self._ctx, self._packed, self._ws = None, None, None
@@ -258,17 +275,10 @@ class SynthesizerB200(nn.Module):
                 else:
                     nz, _ri, ns = noise
                 ns = ns.to(dev, dtype=torch.float32).reshape(B, L).contiguous()
-                pitch_p, f0_p, ns_p = pitch_d.data_ptr(), f0_d.data_ptr(), ns.data_ptr()
             else:                                    # one RNG draw only (models.py:908)
                 nz = noise[0] if noise is not None else torch.randn(B, cfg.inter_channels, T, device=dev)
-                pitch_p = f0_p = ns_p = None
             nz = nz.to(dev, dtype=torch.float32).contiguous()
             prec = _lib.PREC[self.precision]
-            ws = self._workspace(B, T, prec)
-            o = torch.empty(B, 1, L, device=dev, dtype=torch.float32)
-            stats = torch.empty(B, T, 2 * cfg.inter_channels, device=dev, dtype=torch.float32)
-            z_p = torch.empty(B, T, cfg.inter_channels, device=dev, dtype=torch.float32)
-            z = torch.empty(B, T, cfg.inter_channels, device=dev, dtype=torch.float32)
             tap_arr, n_taps, tap_keep = None, 0, {}
             if taps is not None:
                 shapes = self._tap_shapes(B, T)
@@ -281,15 +291,15 @@ class SynthesizerB200(nn.Module):
                     tap_arr[i].dst = t.data_ptr()
                     tap_arr[i].bytes = t.numel() * 4
                 n_taps = len(names)
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            st = lib.rvcb200_infer(
-                self._ctx, B, T, C.c_void_p(phone_d.data_ptr()), C.c_void_p(len_d.data_ptr()),
-                C.c_void_p(pitch_p), C.c_void_p(f0_p), C.c_void_p(sid_d.data_ptr()),
-                C.c_void_p(nz.data_ptr()), C.c_void_p(ns_p), C.c_void_p(o.data_ptr()),
-                C.c_void_p(stats.data_ptr()), C.c_void_p(z_p.data_ptr()), C.c_void_p(z.data_ptr()),
-                C.c_void_p(ws.data_ptr()), ws.numel(), prec, tap_arr, n_taps, C.c_void_p(stream))
-            _lib.check(st, self._ctx, "infer")
-            self.last_launches = int(lib.rvcb200_last_launch_count(self._ctx))
+            ins = {"phone": phone_d, "len": len_d, "sid": sid_d, "nz": nz}
+            if self.f0:
+                ins.update(pitch=pitch_d, f0=f0_d, ns=ns)
+            self.last_graph_replay = False
+            if taps is None and 0 < B * T <= self.graph_max_frames:
+                o, stats, z_p, z = self._infer_graphed(B, T, prec, ins)
+            else:
+                o, stats, z_p, z = self._outputs(B, T, dev)
+                self._enqueue(B, T, prec, ins, (o, stats, z_p, z), self._workspace(B, T, prec), tap_arr, n_taps)
             if taps is not None:
                 taps.update(tap_keep)
             x_mask = (torch.arange(T, device=dev).unsqueeze(0) < len_d.unsqueeze(1)).unsqueeze(1).to(torch.float32)
@@ -297,6 +307,64 @@ class SynthesizerB200(nn.Module):
             m_p = stats[:, :, :Ci].transpose(1, 2)
             logs_p = stats[:, :, Ci:].transpose(1, 2)
             return o, x_mask, (z.transpose(1, 2), z_p.transpose(1, 2), m_p, logs_p)
+
+    def _outputs(self, B, T, dev):
+        cfg = self.cfg
+        return (torch.empty(B, 1, T * cfg.upp, device=dev, dtype=torch.float32),
+                torch.empty(B, T, 2 * cfg.inter_channels, device=dev, dtype=torch.float32),
+                torch.empty(B, T, cfg.inter_channels, device=dev, dtype=torch.float32),
+                torch.empty(B, T, cfg.inter_channels, device=dev, dtype=torch.float32))
+
+    def _enqueue(self, B, T, prec, ins, outs, ws, tap_arr=None, n_taps=0):
+        """One `rvcb200_infer` call: enqueues every kernel of the step on the current stream of the device."""
+        lib = _lib.load()
+        o, stats, z_p, z = outs
+        ptr = lambda name: C.c_void_p(ins[name].data_ptr()) if name in ins else C.c_void_p(None)
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        st = lib.rvcb200_infer(
+            self._ctx, B, T, ptr("phone"), ptr("len"), ptr("pitch"), ptr("f0"), ptr("sid"), ptr("nz"), ptr("ns"),
+            C.c_void_p(o.data_ptr()), C.c_void_p(stats.data_ptr()), C.c_void_p(z_p.data_ptr()), C.c_void_p(z.data_ptr()),
+            C.c_void_p(ws.data_ptr()), ws.numel(), prec, tap_arr, n_taps, C.c_void_p(stream))
+        _lib.check(st, self._ctx, "infer")
+        self.last_launches = int(lib.rvcb200_last_launch_count(self._ctx))
+
+    def _infer_graphed(self, B, T, prec, ins):
+        """Launch-bound sizes: the step's launch sequence is captured once per (B, T, precision) over static input /
+        output / workspace buffers and replayed.  The first call of a key runs eagerly on the static buffers (it is also
+        the warm-up that a capture needs: per-device kernel attributes are set outside the capture) and then captures;
+        later calls copy their inputs in, replay, and return fresh copies of the outputs (the caller owns what infer()
+        returns, like the reference)."""
+        dev = self._device
+        key = (B, T, prec)
+        need = int(_lib.load().rvcb200_workspace_bytes(self._ctx, B, T, prec))
+        if need <= 0:
+            raise RuntimeError("rvcb200_workspace_bytes failed")
+        if self._graph_ws is None or self._graph_ws.numel() < need:
+            self._graphs.clear()                          # captured launches point into the old workspace
+            self._graph_ws = None
+            self._graph_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        e = self._graphs.get(key)
+        if e is None:
+            while len(self._graphs) >= self.graph_cache_size:
+                self._graphs.popitem(last=False)
+            e = {"ins": {k: torch.empty_like(v) for k, v in ins.items()}, "outs": self._outputs(B, T, dev), "graph": None}
+            self._graphs[key] = e
+        else:
+            self._graphs.move_to_end(key)
+        for k, v in ins.items():
+            e["ins"][k].copy_(v)
+        if e["graph"] is None:
+            self._enqueue(B, T, prec, e["ins"], e["outs"], self._graph_ws)       # eager: result of this call + warm-up
+            launches = self.last_launches
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._enqueue(B, T, prec, e["ins"], e["outs"], self._graph_ws)
+            e["graph"], e["launches"] = g, launches
+        else:
+            e["graph"].replay()
+            self.last_launches = e["launches"]
+            self.last_graph_replay = True
+        return tuple(t.clone() for t in e["outs"])
 
     def _tap_shapes(self, B, T):
         cfg = self.cfg

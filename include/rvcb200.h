@@ -134,11 +134,12 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T,
 #define RVCB200_PROF_CLASSES 8
 int rvcb200_profile_enable(rvcb200_ctx* ctx, int32_t on);
 int rvcb200_profile_collect(rvcb200_ctx* ctx, double* ms, int64_t* count);
-/* Class (0..RVCB200_PROF_CLASSES-1) and CUDA-event time of every launch recorded since `enable`, in launch order: lets a
- * profiler's per-launch list (ncu) be joined with the classes above.  Call BEFORE `collect` (which resets the
- * record); synchronises on the events.  Returns the number of launches recorded (may exceed `cap`; at most `cap`
- * entries are written), < 0 on error.  `ms` may be NULL. */
-int64_t rvcb200_profile_launches(rvcb200_ctx* ctx, int32_t* cls, float* ms, int64_t cap);
+/* Class (0..RVCB200_PROF_CLASSES-1), number of kernels and CUDA-event time of every timed scope recorded since `enable`, in
+ * launch order (a scope is one launcher call; a few launchers enqueue several kernels): lets a profiler's per-launch
+ * list (ncu) be joined with the classes above.  Call BEFORE `collect` (which resets the record); synchronises on the
+ * events.  Returns the number of scopes recorded (may exceed `cap`; at most `cap` entries are written), < 0 on error.
+ * `nkern` and `ms` may be NULL. */
+int64_t rvcb200_profile_launches(rvcb200_ctx* ctx, int32_t* cls, int32_t* nkern, float* ms, int64_t cap);
 
 /* Number of kernel launches the last `rvcb200_infer` enqueued (bench.py's gpu_launches). */
 int64_t rvcb200_last_launch_count(const rvcb200_ctx* ctx);
@@ -278,6 +279,14 @@ int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t*
  * double from +0.0 like the reference's `audio_sum += audio_pad[i : i - window]` loop (bit-identical sums).  audio_pad must
  * hold hi + window - 1 samples.  n_threads <= 0: all hardware threads.  -1 on bad arguments or if every sum is NaN. */
 int64_t rvcb200_host_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int32_t window, int32_t n_threads);
+
+/* Host (CPU) restatement of `audio = signal.filtfilt(bh, ah, audio)` (/root/reference/vc_infer_pipeline.py:122, scipy
+ * defaults: odd padding of 3 * (order + 1) samples, transposed direct form II in double) followed by the reflect padding of
+ * :141, bit-identical to scipy / numpy (sequential: see csrc/host_plan.cu for why it cannot be chunked).  b, a: order + 1
+ * coefficients; zi: scipy.signal.lfilter_zi(b, a) (order values, contiguous); out: n + 2 * pad doubles (may be pinned
+ * memory); scratch: n + 6 * (order + 1) doubles.  Returns 0, or 1 on a bad argument. */
+int rvcb200_host_filtfilt_pad(const double* x, int64_t n, const double* b, const double* a, const double* zi, int32_t order,
+                              int64_t pad, double* out, double* scratch);
 
 #ifdef __cplusplus
 }

@@ -174,12 +174,15 @@ def test_layernorm():
     assert (y.cpu().double() - ref).abs().max().item() < 1e-5
 
 
-def _attention_ref(qkv, rel_k, rel_v, lens, n_heads, window):
-    """fp64 banded attention on [B][T][3H] -> [B][T][H]; rows >= len are zero."""
+def _attention_ref(qkv, rel_k, rel_v, lens, n_heads, window, device=None):
+    """fp64 banded attention on [B][T][3H] -> [B][T][H]; rows >= len are zero.  `device`: where the
+    plain-torch fp64 arithmetic runs (the result comes back on the CPU)."""
+    if device is not None:
+        return _attention_ref(qkv.to(device), rel_k.to(device), rel_v.to(device), lens, n_heads, window).cpu()
     B, T, H3 = qkv.shape
     H = H3 // 3
     dk = H // n_heads
-    out = torch.zeros(B, T, H, dtype=torch.float64)
+    out = torch.zeros(B, T, H, dtype=torch.float64, device=qkv.device)
     for b in range(B):
         L = int(lens[b])
         for h in range(n_heads):
@@ -188,7 +191,7 @@ def _attention_ref(qkv, rel_k, rel_v, lens, n_heads, window):
             v = qkv[b, :L, 2 * H + h * dk:2 * H + (h + 1) * dk].double()
             s = q @ k.t()
             rl = q @ rel_k.double().t()                        # [L][2w+1]
-            i = torch.arange(L)
+            i = torch.arange(L, device=qkv.device)
             for r in range(2 * window + 1):
                 j = i + r - window
                 ok = (j >= 0) & (j < L)

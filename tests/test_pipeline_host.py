@@ -161,3 +161,36 @@ def test_sharded_pipeline_world2_gloo_matches_single_process_and_reference(name)
     a = res[0][1]
     assert sorted(i for r in a for i in r) == list(range(len(plan1["segments"]))) and all(len(r) > 0 for r in a)
     assert np.array_equal(res[0][0], single)
+
+
+@pytest.mark.parametrize("secs,seed,t_pad", [(41.7, 3, 48000), (7.0, 4, 16000), (2.5, 5, 48000), (0.001, 6, 16000)])
+def test_filtfilt_pad_is_bit_identical_to_scipy(secs, seed, t_pad):
+    """csrc/host_plan.cu restates scipy's filtfilt (odd padding, transposed direct form II, zi scaling) + np.pad reflect:
+    bit for bit the same doubles as `np.pad(signal.filtfilt(bh, ah, audio), (t_pad, t_pad), mode="reflect")`
+    (vc_infer_pipeline.py:122, :141); clips too short for the C path fall back to scipy / numpy."""
+    from scipy import signal
+    if secs < 0.01:
+        audio = np.random.default_rng(seed).standard_normal(19) * 0.1          # n = padlen + 1: scipy's shortest input
+        t_pad = 10
+    else:
+        audio = synthetic.make_song(secs, seed=seed)
+    want = np.pad(signal.filtfilt(pl._BH, pl._AH, audio), (t_pad, t_pad), mode="reflect")
+    got = pl.filtfilt_pad(audio, t_pad)
+    assert got.dtype == np.float64 and got.shape == want.shape
+    assert np.array_equal(got, want)
+    buf = np.full(want.shape[0] + 7, np.nan)
+    assert np.array_equal(pl.filtfilt_pad(audio, t_pad, out=buf), want) and np.isnan(buf[want.shape[0]:]).all()
+
+
+def test_plan_matches_reference_order_of_operations():
+    """VC.plan (C filtfilt + fused padding + quiet points on a view of the padded buffer) against the reference's own
+    sequence of scipy / numpy calls (vc_infer_pipeline.py:122-141)."""
+    from scipy import signal
+    vc = pl.VC(40000, pl.PipelineConfig(1, 6, 38, 41, is_half=False, device="cuda:0"))
+    audio = synthetic.make_song(150.0, seed=9)
+    a, ap, opt_ts, segs = vc.plan(audio)
+    a_ref = signal.filtfilt(pl._BH, pl._AH, audio)
+    assert np.array_equal(a, a_ref)
+    assert np.array_equal(ap, np.pad(a_ref, (vc.t_pad, vc.t_pad), mode="reflect"))
+    assert opt_ts == pl.split_points(a_ref, vc.window, vc.t_query, vc.t_center, vc.t_max) and len(opt_ts) >= 2
+    assert [(s.start, s.end) for s in segs] == [(s.start, s.end) for s in pl.plan_segments(ap.shape[0], opt_ts, vc.window, vc.t_pad2)]

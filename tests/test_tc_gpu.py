@@ -214,6 +214,9 @@ PAIR_CASES = [
     ("pair_c64_k7_d1", 3, 254, 64, 7, 1),
     ("pair_c64_k7_d5_long", 1, 60000, 64, 7, 5),
     ("pair_c64_k3_d5_tiny", 1, 5, 64, 3, 5),
+    ("pair_c32_k11_d1", 2, 777, 32, 11, 1),
+    ("pair_c32_k11_d3", 1, 118, 32, 11, 3),
+    ("pair_c32_k11_d5_long", 1, 80011, 32, 11, 5),
 ]
 
 
@@ -372,7 +375,8 @@ def test_rbconv_rejects_other_shapes():
     assert _lib.load().rvcb200_op_rbconv_tc(C.byref(d), 1, None) == 1
 
 
-@pytest.mark.parametrize("T,lens", [(7, [7]), (64, [64, 33]), (300, [300, 211]), (1000, [1000]), (2500, [2500, 1999])])
+@pytest.mark.parametrize("T,lens", [(7, [7]), (64, [64, 33]), (300, [300, 211]), (1000, [1000]), (2500, [2500, 1999]),
+                                    (6000, [6000]), (8600, [8600, 8123])])       # the bench's T and the pipeline's longest segment
 def test_attention_tc(T, lens):
     """tcgen05 attention vs the fp64 banded restatement on fp16-rounded operands."""
     from tests.test_ops_gpu import _attention_ref
@@ -383,7 +387,8 @@ def test_attention_tc(T, lens):
     qkv = (torch.randn(B, T, 3 * nh * dk, generator=g)).half().float()        # q|k|v, head-major, unpadded
     rel_k = (torch.randn(21, dk, generator=g) * 0.1).half().float()
     rel_v = (torch.randn(21, dk, generator=g) * 0.1).half().float()
-    ref = _attention_ref(qkv, rel_k, rel_v, lens, nh, 10)                      # divides q by sqrt(dk) itself
+    # divides q by sqrt(dk) itself; the long cases run the fp64 restatement on the GPU (plain torch, checker only)
+    ref = _attention_ref(qkv, rel_k, rel_v, lens, nh, 10, device=dev if T > 3000 else None)
     # padded fp16 operand: [q h0|q h1|k h0|k h1|v h0|v h1] x 128, q pre-scaled
     qp = torch.zeros(B, T, 3 * nh * 128)
     for pi in range(3):
@@ -407,7 +412,7 @@ def test_attention_tc(T, lens):
 
 @pytest.mark.parametrize("precision,min_snr", [("fp16", 45.0), ("bf16", 45.0)])
 @pytest.mark.parametrize("name", ["c2_48k_v2", "c1_40k_v1", "c3_32k_v2_ragged", "c5_48k_v1_5stage", "c7_40k_v1_nono",
-                                  "c8_48k_v2_nono_ragged"])
+                                  "c8_48k_v2_nono_ragged", "c9_40k_v1_resblock2", "c10_48k_v2_resblock2x"])
 def test_infer_tensor_core_path_snr(name, precision, min_snr):
     from tests.test_parity_gpu import build_net
     from tests._util import net_infer

@@ -40,8 +40,8 @@ def bench_pairs(args, lib):
         xs = torch.zeros(1, Cc // 8, Lp, 8, dtype=torch.float16, device=dev)
         bias = torch.randn(Cc, device=dev)
         keep = {int(v) for v in args.ks.split(",")} if args.ks else None
-        for k, dil in ((3, 1), (3, 5), (7, 1), (7, 5)):
-            if keep is not None and k not in keep:
+        for k, dil in ((3, 1), (3, 5), (7, 1), (7, 5), (11, 1), (11, 5)):
+            if (keep is not None and k not in keep) or (k == 11 and Cc != 32):     # C = 64, k = 11 is not a fused shape
                 continue
             w = weights.pack_tc(torch.randn(1, k, Cc, Cc) / (Cc * k) ** 0.5, torch.float16).to(dev)
             for kind in ("s", "a"):

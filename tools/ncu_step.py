@@ -50,12 +50,13 @@ def main():
     net.infer(*ins, noise=noise)
     torch.cuda.synchronize()
     cap = 4096
-    cl, ms = (C.c_int32 * cap)(), (C.c_float * cap)()
-    n = int(lib.rvcb200_profile_launches(net._ctx, cl, ms, cap))
+    cl, nk, ms = (C.c_int32 * cap)(), (C.c_int32 * cap)(), (C.c_float * cap)()
+    n = int(lib.rvcb200_profile_launches(net._ctx, cl, nk, ms, cap))
     lib.rvcb200_profile_enable(net._ctx, 0)
     os.makedirs(args.out, exist_ok=True)
     json.dump({"precision": args.precision, "config": args.config, "T": T, "B": args.batch, "launches": n,
-               "cls": [int(cl[i]) for i in range(n)], "event_ms": [float(ms[i]) for i in range(n)]},
+               "cls": [int(cl[i]) for i in range(n)], "kernels": [int(nk[i]) for i in range(n)],
+               "event_ms": [float(ms[i]) for i in range(n)]},
               open(os.path.join(args.out, f"step_classes_{args.precision}.json"), "w"))
     torch.cuda.cudart().cudaProfilerStart()
     net.infer(*ins, noise=noise)

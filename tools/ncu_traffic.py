@@ -23,7 +23,8 @@ def main():
     rows = list(csv.DictReader(lines))
     per = collections.OrderedDict()            # launch id -> {metric: value}
     for r in rows:
-        d = per.setdefault(r["ID"], {"name": re.sub(r"\(.*", "", r["Kernel Name"]).split("::")[-1], "grid": r["Grid Size"]})
+        full = re.sub(r"\(.*", "", r["Kernel Name"])
+        d = per.setdefault(r["ID"], {"name": full.split("::")[-1] if full.startswith(("rvc::", "void rvc::")) else "at::" + full.split("::")[-1], "grid": r["Grid Size"]})
         v = float(r["Metric Value"].replace(",", ""))
         unit = r["Metric Unit"]
         if r["Metric Name"].startswith("dram__bytes"):
@@ -31,11 +32,16 @@ def main():
         if r["Metric Name"] == "gpu__time_duration.sum":
             v *= {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1, "us": 1, "msecond": 1e3, "ms": 1e3}.get(unit, 1e-3)   # -> us
         d[r["Metric Name"]] = v
-    launches = list(per.values())
-    assert len(launches) == meta["launches"], (len(launches), meta["launches"])
+    launches = [l for l in per.values() if not l["name"].startswith("at::")]   # this repo's kernels only
+    kernels = meta.get("kernels") or [1] * meta["launches"]
+    assert len(launches) == sum(kernels), (len(launches), sum(kernels))
+    cls_of, ev_of = [], []
+    for c, k, ev in zip(meta["cls"], kernels, meta["event_ms"]):      # a scope of k kernels: its event time is split evenly
+        cls_of += [c] * k
+        ev_of += [ev / max(k, 1)] * k
     by_cls = collections.OrderedDict()
     by_kernel = collections.OrderedDict()
-    for l, c, ev in zip(launches, meta["cls"], meta["event_ms"]):
+    for l, c, ev in zip(launches, cls_of, ev_of):
         a = by_cls.setdefault(CLASS_NAMES[c], {"launches": 0, "read": 0.0, "write": 0.0, "ncu_us": 0.0, "event_us": 0.0})
         k = by_kernel.setdefault((CLASS_NAMES[c], l["name"], l["grid"]), {"launches": 0, "read": 0.0, "write": 0.0, "ncu_us": 0.0, "event_us": 0.0})
         for t in (a, k):
