@@ -111,6 +111,7 @@ SYMBOLS = {
                                            C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "rvcb200_op_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "rvcb200_op_to_int16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rvcb200_op_quiet_point": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "rvcb200_host_quiet_point": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "rvcb200_host_filtfilt_pad": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                             C.c_void_p, C.c_void_p]),

@@ -122,5 +122,7 @@ cudaError_t launch_prepare_feats(const void* f, const void* f0, int dtype, const
                                  float protect, int use_protect, cudaStream_t st);
 cudaError_t launch_absmax(const float* x, long long n, float* out, int reset, cudaStream_t st);
 cudaError_t launch_to_int16(const float* x, long long n, const float* absmax, short* out, cudaStream_t st);
+cudaError_t launch_quiet_point(const double* audio_pad, long long lo, long long hi, int window, double* best_v, long long* best_j,
+                               int n_blocks, cudaStream_t st);
 
 }  // namespace rvc

@@ -1142,4 +1142,11 @@ int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t*
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 
+int rvcb200_op_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int32_t window, double* best_v, int64_t* best_j,
+                           int32_t n_blocks, void* stream) {
+  cudaError_t e = launch_quiet_point(audio_pad, lo, hi, window, best_v, reinterpret_cast<long long*>(best_j), n_blocks,
+                                     reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
 }  // extern "C"

@@ -84,6 +84,41 @@ __global__ void to_int16_kernel(const float* __restrict__ x, long long n, const 
     out[i] = cvt_i16(x[i], audio_max);
 }
 
+// Quiet-point search of VC.pipeline (vc_infer_pipeline.py:127-135) for ONE centre: candidates j in [lo, hi), value
+// |audio_pad[j] + ... + audio_pad[j + window - 1]| with the sum accumulated left to right in double from +0.0 -- the
+// reference's `audio_sum += audio_pad[i : i - window]` order per element, so the sums are bit-identical to numpy's.
+// Block b scans its contiguous share of the range and writes its first minimum; the (few) block results are reduced by
+// the caller in ascending block order with a strict '<' (first minimum overall, like np.where(seg == seg.min())[0][0]).
+__global__ void quiet_point_kernel(const double* __restrict__ a, long long lo, long long hi, int window, double* __restrict__ best_v,
+                                   long long* __restrict__ best_j) {
+  const long long per = (hi - lo + gridDim.x - 1) / gridDim.x;
+  const long long j0 = lo + (long long)blockIdx.x * per;
+  const long long j1 = j0 + per < hi ? j0 + per : hi;
+  double bv = INFINITY;
+  long long bj = -1;
+  for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
+    double acc = 0.0;
+    for (int i = 0; i < window; ++i) acc = __dadd_rn(acc, a[j + i]);
+    const double v = fabs(acc);
+    if (v < bv) { bv = v; bj = j; }
+  }
+  __shared__ double sv[256];
+  __shared__ long long sj[256];
+  sv[threadIdx.x] = bv; sj[threadIdx.x] = bj;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const double v2 = sv[threadIdx.x + o];
+      const long long j2 = sj[threadIdx.x + o];
+      const double v1 = sv[threadIdx.x];
+      const long long jj = sj[threadIdx.x];
+      if (j2 >= 0 && (jj < 0 || v2 < v1 || (v2 == v1 && j2 < jj))) { sv[threadIdx.x] = v2; sj[threadIdx.x] = j2; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { best_v[blockIdx.x] = sv[0]; best_j[blockIdx.x] = sj[0]; }
+}
+
 inline unsigned stream_grid(long long work, int threads) {
   long long blocks = (work + threads - 1) / threads;
   const long long cap = 148 * 8;
@@ -114,6 +149,14 @@ cudaError_t launch_absmax(const float* x, long long n, float* out, int reset, cu
   }
   if (n == 0) return cudaSuccess;
   absmax_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, st>>>(x, n, reinterpret_cast<unsigned*>(out));
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_quiet_point(const double* audio_pad, long long lo, long long hi, int window, double* best_v, long long* best_j,
+                               int n_blocks, cudaStream_t st) {
+  if (!audio_pad || !best_v || !best_j || hi <= lo || window < 1 || n_blocks < 1 || n_blocks > 65535) return cudaErrorInvalidValue;
+  quiet_point_kernel<<<n_blocks, 256, 0, st>>>(audio_pad, lo, hi, window, best_v, best_j);
   launch_counter().n++;
   return cudaGetLastError();
 }

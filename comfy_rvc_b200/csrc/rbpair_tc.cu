@@ -50,8 +50,10 @@ constexpr PairSel pair_sel(int C, int NTAPS, int variant) {
     return variant == 0 ? PairSel{1, 1, 1, 1, 1, 1} : PairSel{1, 1, 1, 1, 2, 1};
   }
   if (NTAPS == 3) return variant == 0 ? PairSel{2, 1, 1, 1, 2, 1} : PairSel{1, 2, 2, 1, 2, 2};
-  // C = 32, k = 11: 88 KB of weights; two h tiles and a conv1 look-ahead of one tile leave three slab slots at dilation 5
-  if (NTAPS == 11) return variant == 0 ? PairSel{1, 2, 1, 1, 2, 1} : PairSel{1, 1, 1, 1, 2, 1};
+  // C = 32, k = 11: 88 KB of weights.  One h tile + four slab slots (measured 192-198 us per pair at L = 2.88 M against
+  // 205-231 us as two launches); two h tiles leave three slots at dilation 5 and lose there (241 us):
+  // profiles/r2_pair_k11_cfg{0,1}.jsonl.  The shape sits at the shared-memory operand bound of N = 32 MMAs (~0.66 PFLOP/s)
+  if (NTAPS == 11) return variant == 0 ? PairSel{1, 1, 1, 1, 2, 1} : PairSel{1, 2, 1, 1, 2, 1};
   return variant == 0 ? PairSel{1, 2, 2, 1, 2, 1} : PairSel{1, 2, 2, 1, 2, 2};
 }
 

@@ -417,7 +417,8 @@ class VC(FeatureExtractor):
         dist, rank, world = self._dist()
         t0 = time.time()
         index, big_npy = self.load_index(file_index)
-        audio, audio_pad, opt_ts, segs = self.plan(np.asarray(audio))
+        audio, audio_pad, opt_ts, segs, staged_audio = self._plan_song(np.asarray(audio))
+        t_plan = time.time()
         inp_f0 = None
         if f0_file is not None:                                                                # :144-149
             try:
@@ -440,9 +441,10 @@ class VC(FeatureExtractor):
         mine = assignment[rank]
         self.last_plan = {"opt_ts": list(opt_ts), "segments": segs, "assignment": assignment,
                           "makespan_bound": makespan_bound(lengths, world)}
-        staged = self._stage(audio_pad, pitch, pitchf, sid, net_g)                             # H2D once per song
+        staged = self._stage(audio_pad, pitch, pitchf, sid, net_g, staged_audio)               # H2D once per song
         t1 = time.time()
         times[1] += t1 - t0                                                                    # :164-165
+        ev0 = self._record_event(staged)
         parts = []
         for s in segs:
             T_formula = min(s.n_samples // self.window, 2 * hubert_frames(s.n_samples))
@@ -453,6 +455,14 @@ class VC(FeatureExtractor):
             if run:
                 parts.append((s.index, self._convert(staged, model, net_g, s, T_formula, index, big_npy, index_rate,
                                                      version, protect, noise)))
+        t_enq = time.time()
+        if world > 1 and self._device_collectives(dist, staged):
+            # NCCL group: the peak is one 4-byte all-reduce and the int16 pieces travel GPU to GPU (NVLink); rank 0 orders
+            # them on the device and does the song's single D2H -- no pickling, no host round trip per rank
+            out = self._finalize_gather_device(staged, parts, len(segs), assignment, dist, rank, world, all_ranks)
+            self._timing(staged, ev0, t0, t_plan, t1, t_enq)
+            times[2] += time.time() - t1
+            return out
 
         def exchange_peak(local_peak: float) -> float:                                         # the only reduction
             if world == 1:
@@ -462,6 +472,7 @@ class VC(FeatureExtractor):
             return max(peaks)
 
         mine_np = self._finalize(staged, parts, exchange_peak if world > 1 else None)          # :182-189
+        self._timing(staged, ev0, t0, t_plan, t1, t_enq)
         if world > 1:
             gathered = [None] * world
             hg = self._gloo_group(dist)
@@ -479,13 +490,71 @@ class VC(FeatureExtractor):
         times[2] += time.time() - t1
         return out
 
+    # ---- hooks with a host default (the CPU test double overrides the device ones below) ------------------------
+    def _plan_song(self, audio: np.ndarray):
+        """Planning for `pipeline`: like `plan`, but with a CUDA device the quiet-point search runs there on the staged
+        float64 song (same sums in the same order, `rvcb200_op_quiet_point`), so the song crosses PCIe once, as float64,
+        straight from the pinned buffer the filter wrote.  Returns (..., staged float64 device tensor or None)."""
+        dev = torch.device(self.device)
+        n, h = audio.shape[0], self.window // 2
+        if (dev.type != "cuda" or not torch.cuda.is_available() or type(self)._stage is not VC._stage
+                or not (audio.ndim == 1 and n > max(self.t_pad, 18) and self.t_pad >= h)):
+            return (*self.plan(audio), None)
+        dev = self._torch_device()
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            audio_pad = filtfilt_pad(audio, self.t_pad, out=self._staging(n + 2 * self.t_pad))  # :122 + :141
+            audio_d = torch.from_numpy(audio_pad).to(dev, non_blocking=True)
+            opt_ts: List[int] = []
+            if n + 2 * h > self.t_max:                                                         # :127
+                centres = list(range(self.t_center, n, self.t_center))
+                nb = 64
+                bv = torch.empty(len(centres), nb, dtype=torch.float64, device=dev)
+                bj = torch.empty(len(centres), nb, dtype=torch.int64, device=dev)
+                stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                base = audio_d.data_ptr() + (self.t_pad - h) * 8                               # audio reflect-padded by window // 2
+                for k, t in enumerate(centres):
+                    lo, hi = t - self.t_query, min(t + self.t_query, n)
+                    _lib.check(lib.rvcb200_op_quiet_point(C.c_void_p(base), lo, hi, self.window, C.c_void_p(bv[k].data_ptr()),
+                                                          C.c_void_p(bj[k].data_ptr()), nb, stream), None, "quiet_point")
+                bv_h, bj_h = bv.cpu().numpy(), bj.cpu().numpy()                                # one small D2H (sync)
+                for k in range(len(centres)):
+                    best_v, best_j = np.inf, -1
+                    for b in range(nb):                                                        # ascending ranges: first minimum
+                        if bj_h[k, b] >= 0 and bv_h[k, b] < best_v:
+                            best_v, best_j = bv_h[k, b], int(bj_h[k, b])
+                    if best_j < 0:                                                             # every sum NaN: numpy's argmin rule
+                        best_j = centres[k] - self.t_query
+                    opt_ts.append(best_j)
+        segs = plan_segments(audio_pad.shape[0], opt_ts, self.window, self.t_pad2)
+        return audio_pad[self.t_pad: self.t_pad + n], audio_pad, opt_ts, segs, audio_d
+
     # ---- device side of the song-level driver (everything below touches the GPU) -----------------------------
-    def _stage(self, audio_pad, pitch, pitchf, sid, net_g) -> dict:
+    def _record_event(self, staged):
+        if staged["dev"].type != "cuda":
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(staged["dev"]))
+        return ev
+
+    def _timing(self, staged, ev0, t0, t_plan, t_stage, t_enq):
+        """Where the call's time went: host phases by wall clock, the enqueued device work by CUDA events."""
+        ev1 = self._record_event(staged)
+        if ev1 is not None:
+            ev1.synchronize()
+        self.last_plan["host_s"] = {"plan": t_plan - t0, "f0_and_stage": t_stage - t_plan, "enqueue": t_enq - t_stage,
+                                    "total": time.time() - t0}
+        self.last_plan["device_ms"] = ev0.elapsed_time(ev1) if ev0 is not None else None
+
+    def _device_collectives(self, dist, staged) -> bool:
+        return staged["dev"].type == "cuda" and dist.get_backend(self.group) == "nccl"
+
+    def _stage(self, audio_pad, pitch, pitchf, sid, net_g, staged_audio=None) -> dict:
         dev = self._torch_device()
         with torch.cuda.device(dev):
             # the whole song, once: float64 from the (pinned) staging buffer, rounded to the model dtype on the device --
             # the same single rounding as the reference's `torch.from_numpy(audio0).half() / .float()` (:40-44)
-            audio_d = torch.from_numpy(audio_pad).to(dev, non_blocking=True)
+            audio_d = staged_audio if staged_audio is not None else torch.from_numpy(audio_pad).to(dev, non_blocking=True)
             return {
                 "dev": dev,
                 "audio": audio_d.half() if self.is_half else audio_d.float(),
@@ -506,6 +575,65 @@ class VC(FeatureExtractor):
                 raise RuntimeError("HuBERT front end does not follow the 400/320 frame formula; reference-order noise "
                                    "cannot be pre-drawn")
             return o[self.t_pad_tgt: o.shape[0] - self.t_pad_tgt]                              # :174/:180 trim, on device
+
+    def _finalize_gather_device(self, staged, parts, n_segs, assignment, dist, rank, world, all_ranks):
+        """`_finalize` + the gather for an NCCL group, all on the device: peak = all-reduce(max) of one float; every rank
+        converts its segments to int16 against the song-wide peak; the pieces go to rank 0 (to every rank with
+        `all_ranks`) as bytes over NVLink; the destination orders them by segment index and copies the song to the host
+        once.  No collective touches the synthesis itself."""
+        dev = staged["dev"]
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            local = torch.cat([p for _, p in parts]) if parts else torch.empty(0, device=dev)
+            peak = torch.zeros(1, device=dev, dtype=torch.float32)
+            _lib.check(lib.rvcb200_op_absmax(C.c_void_p(local.data_ptr()), local.numel(), C.c_void_p(peak.data_ptr()), 1,
+                                             stream), None, "absmax")
+            dist.all_reduce(peak, op=dist.ReduceOp.MAX, group=self.group)                      # :188, the only reduction
+            sizes = torch.zeros(n_segs, device=dev, dtype=torch.int64)                         # samples per segment, from its owner
+            for i, p in parts:
+                sizes[i] = p.numel()
+            dist.all_reduce(sizes, op=dist.ReduceOp.SUM, group=self.group)
+            pcm = torch.empty(local.numel(), device=dev, dtype=torch.int16)
+            _lib.check(lib.rvcb200_op_to_int16(C.c_void_p(local.data_ptr()), local.numel(), C.c_void_p(peak.data_ptr()),
+                                               C.c_void_p(pcm.data_ptr()), stream), None, "to_int16")
+            sizes_h = sizes.cpu().tolist()
+            per_rank = [sum(sizes_h[i] for i in assignment[r]) for r in range(world)]
+            dst_ranks = list(range(world)) if all_ranks else [0]
+            bufs = {}
+            ops = []
+            grp = self.group
+            g = (lambda r: dist.get_global_rank(grp, r)) if grp is not None else (lambda r: r)
+            mine = pcm.view(torch.uint8)
+            if rank in dst_ranks:
+                for r in range(world):
+                    if r == rank:
+                        bufs[r] = mine
+                    elif per_rank[r]:
+                        bufs[r] = torch.empty(2 * per_rank[r], device=dev, dtype=torch.uint8)
+                        ops.append(dist.P2POp(dist.irecv, bufs[r], g(r), group=grp))
+            if mine.numel():
+                for d in dst_ranks:
+                    if d != rank:
+                        ops.append(dist.P2POp(dist.isend, mine, g(d), group=grp))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            if rank not in dst_ranks:
+                torch.cuda.current_stream(dev).synchronize()
+                return None
+            offs = np.concatenate([[0], np.cumsum(sizes_h)]).astype(np.int64)
+            song = torch.empty(int(offs[-1]), device=dev, dtype=torch.int16)
+            for r in range(world):
+                o = 0
+                for i in assignment[r]:
+                    n = sizes_h[i]
+                    song[offs[i]: offs[i] + n] = bufs[r].view(torch.int16)[o: o + n]
+                    o += n
+            out_h = torch.empty(song.numel(), dtype=torch.int16).pin_memory()
+            out_h.copy_(song, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        return out_h.numpy()
 
     def _finalize(self, staged, parts, exchange_peak) -> dict:
         """Concatenate this rank's trimmed segments, peak-normalise against the song-wide max and convert to int16 on the

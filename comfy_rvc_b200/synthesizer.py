@@ -339,26 +339,27 @@ class SynthesizerB200(nn.Module):
         need = int(_lib.load().rvcb200_workspace_bytes(self._ctx, B, T, prec))
         if need <= 0:
             raise RuntimeError("rvcb200_workspace_bytes failed")
-        if self._graph_ws is None or self._graph_ws.numel() < need:
-            self._graphs.clear()                          # captured launches point into the old workspace
-            self._graph_ws = None
-            self._graph_ws = torch.empty(need, dtype=torch.uint8, device=dev)
         e = self._graphs.get(key)
         if e is None:
             while len(self._graphs) >= self.graph_cache_size:
                 self._graphs.popitem(last=False)
-            e = {"ins": {k: torch.empty_like(v) for k, v in ins.items()}, "outs": self._outputs(B, T, dev), "graph": None}
+            # graphs replay on one stream, so they share a workspace; when a new key needs a bigger one, a new buffer is
+            # allocated for it and later keys -- graphs captured earlier keep (and keep alive) the buffer they point into
+            if self._graph_ws is None or self._graph_ws.numel() < need:
+                self._graph_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            e = {"ins": {k: torch.empty_like(v) for k, v in ins.items()}, "outs": self._outputs(B, T, dev), "graph": None,
+                 "ws": self._graph_ws}
             self._graphs[key] = e
         else:
             self._graphs.move_to_end(key)
         for k, v in ins.items():
             e["ins"][k].copy_(v)
         if e["graph"] is None:
-            self._enqueue(B, T, prec, e["ins"], e["outs"], self._graph_ws)       # eager: result of this call + warm-up
+            self._enqueue(B, T, prec, e["ins"], e["outs"], e["ws"])             # eager: result of this call + warm-up
             launches = self.last_launches
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._enqueue(B, T, prec, e["ins"], e["outs"], self._graph_ws)
+                self._enqueue(B, T, prec, e["ins"], e["outs"], e["ws"])
             e["graph"], e["launches"] = g, launches
         else:
             e["graph"].replay()

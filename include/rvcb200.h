@@ -272,6 +272,12 @@ int rvcb200_op_absmax(const float* x, int64_t n, float* out, int32_t reset, void
  * NumPy >= 2 promotion). */
 int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t* out, void* stream);
 
+/* Device form of the quiet-point search below (same sums, same order, one thread per candidate): block k of `n_blocks`
+ * writes the first minimum of its contiguous share of [lo, hi) to best_v[k] / best_j[k] (absolute index, -1 if the share
+ * is empty); the caller takes the first minimum over blocks in ascending order.  audio_pad: device float64. */
+int rvcb200_op_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int32_t window, double* best_v, int64_t* best_j,
+                           int32_t n_blocks, void* stream);
+
 /* ---- host (CPU) side of the song-level driver (csrc/host_plan.cu) ---- */
 
 /* Quiet-point search of /root/reference/vc_infer_pipeline.py:127-135: the first j in [lo, hi) (returned relative to lo)

@@ -19,7 +19,7 @@ class OracleNet:
 
 
 class HostVC(VC):
-    def _stage(self, audio_pad, pitch, pitchf, sid, net_g):
+    def _stage(self, audio_pad, pitch, pitchf, sid, net_g, staged_audio=None):
         return {"dev": torch.device("cpu"), "audio": audio_pad, "sid": torch.tensor(sid).reshape(1).long(),
                 "pitch": torch.from_numpy(pitch).unsqueeze(0), "pitchf": torch.from_numpy(pitchf).unsqueeze(0)}
 

@@ -178,3 +178,19 @@ def test_absmax_and_int16_bit_exact(n):
     assert lib.rvcb200_op_absmax(C.c_void_p(small.data_ptr()), 8, C.c_void_p(peak.data_ptr()), 0, st) == 0
     torch.cuda.synchronize()
     assert peak.item() == float(want_peak)
+
+
+@pytest.mark.parametrize("secs,tier,seed", [(200.0, (1, 6, 38, 41), 4), (95.0, (1, 5, 30, 32), 5), (20.0, (3, 10, 60, 64), 6)])
+def test_device_planning_equals_host_planning(secs, tier, seed):
+    """`VC.pipeline` plans on the device (quiet-point kernel over the staged float64 song); `VC.plan` is the host form
+    (C, csrc/host_plan.cu).  Same sums in the same order: identical split points, and the staged song is the filtered,
+    reflect-padded float64 audio bit for bit."""
+    vc = pl.VC(48000, pl.PipelineConfig(*tier, is_half=False, device="cuda:0"))
+    audio = synthetic.make_song(secs, seed=seed)
+    a, ap, opt, segs = vc.plan(audio)
+    ap = ap.copy()                                                  # `plan` and `_plan_song` share the staging buffer
+    a2, ap2, opt2, segs2, staged = vc._plan_song(audio)
+    assert staged is not None and opt2 == opt and (len(opt) > 0) == (secs > tier[3])
+    assert np.array_equal(ap2, ap) and np.array_equal(staged.cpu().numpy(), ap)
+    assert [(s.start, s.end) for s in segs2] == [(s.start, s.end) for s in segs]
+    assert vc.last_plan is None

@@ -57,6 +57,9 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--song-seconds", type=float, default=600.0)
+    ap.add_argument("--tiers", default="", help="song: comma list of x_center values to keep (60,38,30); default all")
+    ap.add_argument("--check", action="store_true", help="song under torchrun: also run unsharded and compare bit for bit")
+    ap.add_argument("--max-frames", type=int, default=0, help="sweep: only points with batch * frames <= this (0 = all)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -77,57 +80,99 @@ def main():
         torch.cuda.empty_cache()
 
     if "song" in what:
+        # configs[3]: one 10 min song through VC.pipeline, the reference's own segments sharded over the ranks.  The three
+        # x_pad/x_query/x_center/x_max tiers are all reference behaviour (config.py:124-141); they change the segment count.
         cfg = NAMED_CONFIGS["48k_v2"]
         net = build(cfg, args.precision, dev)
         audio = synthetic.make_song(args.song_seconds, seed=0)
-        vc = pl.VC(cfg.sr, pl.PipelineConfig(3, 10, 60, 64, is_half=False, device=str(dev)), noise="device")   # the half-mode tier
-        vc.f0_method_dict["synthetic"] = synthetic.pipeline_f0
         hubert = synthetic.FakeHubert(cfg.feat_dim)
-        walls = []
-        for it in range(1 + args.reps):
+        solo = [dist.new_group([r]) for r in range(world)] if world > 1 else None       # 1-rank groups: the unsharded run
+        for tier in [t for t in ((3, 10, 60, 64), (1, 6, 38, 41), (1, 5, 30, 32)) if not args.tiers or str(t[2]) in args.tiers.split(",")]:
+            def make_vc(group=None):
+                v = pl.VC(cfg.sr, pl.PipelineConfig(*tier, is_half=False, device=str(dev)), noise="device", group=group)
+                v.f0_method_dict["synthetic"] = synthetic.pipeline_f0
+                return v
+
+            def run(v):
+                return v.pipeline(hubert, net, 0, audio.copy(), [0, 0, 0], 0, "synthetic", "median", "", 0.0, 1, 3, cfg.sr, 0, 1.0,
+                                  "v2", 0.5, 160, False, False, None, 50, 1100)
+            vc = make_vc()
+            walls, dev_ms, host = [], [], []
+            for it in range(1 + args.reps):
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                out = run(vc)
+                torch.cuda.synchronize(dev)
+                if world > 1:
+                    dist.barrier()
+                if it:
+                    walls.append(time.perf_counter() - t0)
+                    dev_ms.append(vc.last_plan["device_ms"])
+                    host.append(vc.last_plan["host_s"])
+            same = None
+            if world > 1 and args.check:
+                ref = run(make_vc(solo[rank]))                                           # every rank: the whole song on its own GPU
+                same = bool(np.array_equal(ref, out)) if rank == 0 else None
+            dm = torch.tensor([float(np.median(dev_ms))], device=dev)
             if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            out = vc.pipeline(hubert, net, 0, audio.copy(), [0, 0, 0], 0, "synthetic", "median", "", 0.0, 1, 3, cfg.sr, 0, 1.0,
-                              "v2", 0.5, 160, False, False, None, 50, 1100)
-            torch.cuda.synchronize(dev)
-            if world > 1:
-                dist.barrier()
-            if it:
-                walls.append(time.perf_counter() - t0)
-        if rank == 0:
-            plan = vc.last_plan
-            secs = out.shape[0] / cfg.sr
-            w = float(np.median(walls))
-            print(json.dumps({"config": f"48k_v2 VC.pipeline, {args.song_seconds:.0f} s song, tier (3,10,60,64)", "n_gpus": world,
-                              "precision": args.precision, "segments": len(plan["segments"]),
-                              "segment_seconds": [round(s.n_samples / 16000, 1) for s in plan["segments"]],
-                              "makespan_bound": plan["makespan_bound"], "wall_s": round(w, 4),
-                              "audio_s_per_s": round(secs / w, 1),
-                              "note": "wall clock of the whole call: host planning + filtfilt + f0 post-processing, H2D, all "
-                                      "segments, device-side finalise, D2H, gather"}), flush=True)
+                dist.all_reduce(dm, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                plan = vc.last_plan
+                secs = out.shape[0] / cfg.sr
+                w = float(np.median(walls))
+                h = {k: round(float(np.median([x[k] for x in host])), 4) for k in host[0]}
+                print(json.dumps({"config": f"48k_v2 VC.pipeline, {args.song_seconds:.0f} s song", "tier": list(tier), "n_gpus": world,
+                                  "precision": args.precision, "segments": len(plan["segments"]),
+                                  "segment_seconds": [round(s.n_samples / 16000, 1) for s in plan["segments"]],
+                                  "assignment": plan["assignment"], "makespan_bound": round(plan["makespan_bound"], 3),
+                                  "wall_s": round(w, 4), "audio_s_per_s": round(secs / w, 1),
+                                  "device_ms_max_over_ranks": round(float(dm), 2),
+                                  "device_audio_s_per_s": round(secs / (float(dm) / 1e3), 1), "host_s_rank0": h,
+                                  "sharded_equals_unsharded": same,
+                                  "note": "wall = whole call on rank 0 (C filtfilt, H2D, device quiet-point search, segments, device "
+                                          "gather, D2H); device_ms = CUDA events from the first segment to the end of the gather"}),
+                      flush=True)
         del net
         torch.cuda.empty_cache()
 
-    if "sweep" in what and rank == 0:
+    if "sweep" in what:
+        # configs[4]: every rank runs the same (length, batch) point on its own GPU (weak scaling, no collective on the data
+        # path); the time of a point is the max over ranks and the rate the aggregate of all ranks
         for cname in ("40k", "48k_v2"):
             cfg = NAMED_CONFIGS[cname]
             net = build(cfg, args.precision, dev)
+            ref32 = build(cfg, "fp32", dev) if args.check else None
             for secs in (1, 2, 5, 10, 20, 30):
-                for B in (1, 4, 16, 64):
+                for B in (1, 4, 16, 64, 256):
                     T = secs * 100
-                    if B * T > 64 * 3000:          # keep the workspace under ~60 GB
+                    if B * T > 256 * 1000 or (args.max_frames and B * T > args.max_frames):   # workspace under ~80 GB
                         continue
                     try:
                         ms, rate = time_infer(net, cfg, B, T, args.reps, dev)
+                        snr = None
+                        if ref32 is not None:            # item 0 of the batch against the +-1 LSB fp32 path, same inputs and noise
+                            ins = [t.to(dev) for t in synthetic.make_inputs(cfg, B, T, seed=3)]
+                            noise = net.draw_noise(B, T)
+                            o = net.infer(*ins, noise=noise)[0][0, 0]
+                            r = ref32.infer(*[t[:1] for t in ins], noise=tuple(t[:1] for t in noise))[0][0, 0]
+                            snr = synthetic.snr_db(r.cpu().numpy(), o.cpu().numpy())
                     except RuntimeError as e:     # out of memory on this box: report and go on
-                        print(json.dumps({"config": cname, "seconds": secs, "batch": B, "error": str(e)[:80]}), flush=True)
+                        if rank == 0:
+                            print(json.dumps({"config": cname, "seconds": secs, "batch": B, "error": str(e)[:80]}), flush=True)
                         torch.cuda.empty_cache()
-                        continue
-                    print(json.dumps({"config": cname, "precision": args.precision, "seconds": secs, "batch": B,
-                                      "ms": round(ms, 3), "audio_s_per_s": round(rate, 1)}), flush=True)
-            del net
+                        ms = float("nan")
+                    t = torch.tensor([ms], device=dev)
+                    if world > 1:
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    if rank == 0 and ms == ms:
+                        ms_all = float(t)
+                        print(json.dumps({"config": cname, "precision": args.precision, "seconds": secs, "batch": B, "n_gpus": world,
+                                          "ms": round(ms_all, 3), "audio_s_per_s": round(world * B * T * cfg.upp / cfg.sr / (ms_all / 1e3), 1),
+                                          "graph_replay": bool(net.last_graph_replay),
+                                          "snr_db_item0_vs_fp32_path": None if snr is None else round(snr, 1)}), flush=True)
+            del net, ref32
             torch.cuda.empty_cache()
     if world > 1:
         dist.destroy_process_group()
