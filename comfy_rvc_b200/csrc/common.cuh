@@ -28,12 +28,14 @@ inline int cuda_ok(cudaError_t e, const char* what, char* errbuf, size_t errlen)
 // CTAs retire and run their prologue (barrier init, TMEM allocation, tensor-map fetch, constant weights -> smem) under
 // this grid's tail; before touching anything a predecessor wrote -- or writing anything a predecessor may still read --
 // every thread that accesses global memory executes pdl_wait(), which returns once all prerequisite grids have
-// completed and their memory is visible.  Measured on B200 (60 s segment, 181 launches): 12.20 ms with, 12.13 ms without --
-// the step is the sum of its kernel times, there is no launch gap to hide -- so it is OFF by default (RVCB200_PDL=1 turns
-// it on; without the launch attribute both instructions are no-ops).
+// completed and their memory is visible.  Measured on B200: 60 s segment (181 launches) 12.20 ms with, 12.13 ms without --
+// the step is the sum of its kernel times, there is no launch gap to hide; 1 s segment 1.89 ms with, 2.05 ms without.  So the
+// engine turns it on for launch-bound sizes only (RVCB200_PDL=0/1 forces it; without the launch attribute both
+// instructions are no-ops).
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
+void pdl_set_auto(bool on);      // per-call default when RVCB200_PDL is not set (engine.cu: launch-bound sizes)
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -500,6 +500,10 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     return fail(ctx, RVCB200_ERR_WORKSPACE, "workspace too small%s: need %lld bytes", "", (long long)(pl.bytes + 256));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   TapSet tp{taps, n_taps, st};
+  struct PdlScope {            // programmatic dependent launch for launch-bound sizes (common.cuh), this call only
+    explicit PdlScope(bool on) { pdl_set_auto(on); }
+    ~PdlScope() { pdl_set_auto(false); }
+  } pdl_scope((long long)B * T <= 2500 && n_taps == 0 && !ctx->prof);
   const long long launches0 = launch_counter().n;
   bool ok = true;
   auto W = [&](const std::string& n) { return T32(ctx, n, 0, &ok); };

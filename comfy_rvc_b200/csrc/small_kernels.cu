@@ -24,9 +24,16 @@ int current_num_sms() {
   return n;
 }
 
+// RVCB200_PDL=0/1 forces programmatic dependent launch off/on; unset, the engine turns it on per infer() call for
+// launch-bound sizes (pdl_set_auto): measured 5-8 % on 1-10 s segments (the step is ~165 kernels of 6-30 us, so the
+// prologue of kernel n+1 under the tail of kernel n is visible), nothing on a 60 s segment.
+namespace {
+thread_local bool g_pdl_auto = false;
+}
+void pdl_set_auto(bool on) { g_pdl_auto = on; }
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("RVCB200_PDL"); return e ? atoi(e) != 0 : false; }();
-  return on;
+  static const int env = [] { const char* e = getenv("RVCB200_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+  return env >= 0 ? env != 0 : g_pdl_auto;
 }
 
 namespace {

@@ -67,6 +67,7 @@ class SynthesizerB200(nn.Module):
         self.graph_cache_size = 16
         self._graphs: "OrderedDict[tuple, dict]" = OrderedDict()
         self._graph_ws: Optional[torch.Tensor] = None
+        self._capture_stream = None
         self.last_graph_replay = False
 
     # ---- nn.Module protocol the reference callers use ------------------------------------------
@@ -358,7 +359,9 @@ class SynthesizerB200(nn.Module):
             self._enqueue(B, T, prec, e["ins"], e["outs"], e["ws"])             # eager: result of this call + warm-up
             launches = self.last_launches
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            if self._capture_stream is None or self._capture_stream.device != dev:
+                self._capture_stream = torch.cuda.Stream(device=dev)     # torch's default capture stream is per process, not per device
+            with torch.cuda.graph(g, stream=self._capture_stream, capture_error_mode="thread_local"):
                 self._enqueue(B, T, prec, e["ins"], e["outs"], e["ws"])
             e["graph"], e["launches"] = g, launches
         else:

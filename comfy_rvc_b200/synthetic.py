@@ -197,12 +197,17 @@ class FakeHubert:
     (/root/reference/lib/infer_pack/loaders.py:43-61): 20 ms hop, receptive field 400 samples, so
     `source[1, n]` → `[1, (n - 400)//320 + 1, C_f]`; values are N(0,1) seeded by n."""
 
-    def __init__(self, feat_dim: int, seed: int = 100):
-        self.feat_dim, self.seed = feat_dim, seed
+    def __init__(self, feat_dim: int, seed: int = 100, device_rng: bool = False):
+        # device_rng: draw the features on `source`'s device (throughput measurements: a real front end produces its
+        # features there; the CPU generator is what the reference-minted pipeline fixtures were made with)
+        self.feat_dim, self.seed, self.device_rng = feat_dim, seed, device_rng
 
     def extract_features(self, version=None, source=None, padding_mask=None, output_layer=None, **_):
         n = int(source.shape[-1])
         frames = (n - 400) // 320 + 1
+        if self.device_rng and source.device.type == "cuda":
+            g = torch.Generator(device=source.device).manual_seed(self.seed + n)
+            return torch.randn(1, frames, self.feat_dim, generator=g, device=source.device, dtype=torch.float32).to(source.dtype)
         g = torch.Generator().manual_seed(self.seed + n)
         feats = torch.randn(1, frames, self.feat_dim, generator=g, dtype=torch.float32)
         return feats.to(device=source.device, dtype=source.dtype)
@@ -222,3 +227,88 @@ class FakeIndex:
         d = (a * a).sum(1, keepdims=True) - 2.0 * a @ b.T + (b * b).sum(1)[None, :]
         ix = np.argsort(d, axis=1, kind="stable")[:, :k]
         return np.take_along_axis(d, ix, axis=1).astype(np.float32), ix.astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------
+# HuBERT / ContentVec front end: seeded weights in the HuggingFace `HubertModel` key layout the
+# reference loads (/root/reference/lib/infer_pack/loaders.py:21-32, + `final_proj`), base architecture.
+# ---------------------------------------------------------------------------------------------
+HUBERT_BASE = dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                   conv_dim=(512,) * 7, conv_stride=(5, 2, 2, 2, 2, 2, 2), conv_kernel=(10, 3, 3, 3, 3, 2, 2), conv_bias=False,
+                   feat_extract_norm="group", feat_extract_activation="gelu", hidden_act="gelu", num_conv_pos_embeddings=128,
+                   num_conv_pos_embedding_groups=16, do_stable_layer_norm=False, layer_norm_eps=1e-5,
+                   classifier_proj_size=256, feat_proj_layer_norm=True)
+
+
+def hubert_state_dict_shapes(h: dict = HUBERT_BASE) -> Dict[str, Tuple[int, ...]]:
+    H, I = h["hidden_size"], h["intermediate_size"]
+    s: Dict[str, Tuple[int, ...]] = {"masked_spec_embed": (H,)}
+    cin = 1
+    for i, (c, k) in enumerate(zip(h["conv_dim"], h["conv_kernel"])):
+        s[f"feature_extractor.conv_layers.{i}.conv.weight"] = (c, cin, k)
+        cin = c
+    s["feature_extractor.conv_layers.0.layer_norm.weight"] = (h["conv_dim"][0],)
+    s["feature_extractor.conv_layers.0.layer_norm.bias"] = (h["conv_dim"][0],)
+    s["feature_projection.layer_norm.weight"] = (cin,)
+    s["feature_projection.layer_norm.bias"] = (cin,)
+    s["feature_projection.projection.weight"] = (H, cin)
+    s["feature_projection.projection.bias"] = (H,)
+    kp, g = h["num_conv_pos_embeddings"], h["num_conv_pos_embedding_groups"]
+    s["encoder.pos_conv_embed.conv.bias"] = (H,)
+    s["encoder.pos_conv_embed.conv.parametrizations.weight.original0"] = (1, 1, kp)
+    s["encoder.pos_conv_embed.conv.parametrizations.weight.original1"] = (H, H // g, kp)
+    s["encoder.layer_norm.weight"] = (H,)
+    s["encoder.layer_norm.bias"] = (H,)
+    for l in range(h["num_hidden_layers"]):
+        p = f"encoder.layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            s[p + f"attention.{n}.weight"] = (H, H)
+            s[p + f"attention.{n}.bias"] = (H,)
+        for n in ("layer_norm", "final_layer_norm"):
+            s[p + n + ".weight"] = (H,)
+            s[p + n + ".bias"] = (H,)
+        s[p + "feed_forward.intermediate_dense.weight"] = (I, H)
+        s[p + "feed_forward.intermediate_dense.bias"] = (I,)
+        s[p + "feed_forward.output_dense.weight"] = (H, I)
+        s[p + "feed_forward.output_dense.bias"] = (H,)
+    s["final_proj.weight"] = (h["classifier_proj_size"], H)
+    s["final_proj.bias"] = (h["classifier_proj_size"],)
+    return s
+
+
+def make_hubert_state_dict(seed: int = 0, h: dict = HUBERT_BASE, fp16_roundtrip: bool = True) -> Dict[str, torch.Tensor]:
+    """Seeded, well-conditioned weights (fan-in scaled; LayerNorm / GroupNorm gains near 1) stored through fp16 like the
+    shipped `content-vec-best.safetensors`."""
+    sd: Dict[str, torch.Tensor] = {}
+    for key, shape in sorted(hubert_state_dict_shapes(h).items()):
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFF)
+        r = torch.randn(shape, generator=g, dtype=torch.float32)
+        if key.endswith("layer_norm.weight") or key.endswith("original0"):
+            t = 1.0 + 0.1 * r
+        elif key.endswith(".bias"):
+            t = 0.05 * r
+        elif key == "masked_spec_embed":
+            t = r
+        elif key.endswith("original1"):
+            t = r * (1.0 / math.sqrt(shape[1] * shape[2]))
+        elif "feature_extractor" in key:
+            t = r * (1.6 / math.sqrt(_fan_in(shape)))          # GELU roughly halves the variance
+        else:
+            t = r * (1.0 / math.sqrt(_fan_in(shape)))
+        sd[key] = t
+    if fp16_roundtrip:
+        sd = {k: v.half().float() for k, v in sd.items()}
+    return sd
+
+
+def make_speech(seconds: float, seed: int = 0, sr: int = 16000) -> torch.Tensor:
+    """Synthetic 16 kHz 'speech' [1, n] for the front end: harmonic tone with vibrato + noise bursts, peak ~0.5."""
+    n = int(round(seconds * sr))
+    t = torch.arange(n, dtype=torch.float64) / sr
+    g = torch.Generator().manual_seed(seed + 77)
+    f0 = 140.0 + 40.0 * torch.sin(2 * math.pi * 0.7 * t + seed)
+    ph = 2 * math.pi * torch.cumsum(f0, 0) / sr
+    x = sum(torch.sin(k * ph) / k for k in range(1, 6)) * 0.2
+    env = 0.55 + 0.45 * torch.sin(2 * math.pi * 1.3 * t)
+    x = x * env + 0.05 * torch.randn(n, generator=g, dtype=torch.float64) * (torch.sin(2 * math.pi * 0.4 * t) > 0.3)
+    return x.float()[None, :]

@@ -66,3 +66,19 @@ def test_graph_draws_fresh_noise_and_survives_precision_switch():
     torch.manual_seed(3)
     assert torch.equal(net.infer(*ins)[0], a) and net.last_graph_replay is False
     assert c.shape == a.shape
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_programmatic_dependent_launch_is_bit_identical(precision):
+    """Launch-bound sizes run with programmatic dependent launch (engine.cu PdlScope: kernel n+1's prologue under kernel
+    n's tail; every kernel waits on `griddepcontrol.wait` before it touches a predecessor's data).  A call that taps an
+    intermediate runs without it (and without graph replay): same waveform bit for bit."""
+    cfg = NAMED_CONFIGS["48k_v2"]
+    sd = synthetic.make_state_dict(cfg)
+    net = build_net(cfg, sd, precision)
+    for T in (40, 150):
+        inputs = [t.cuda() for t in synthetic.make_inputs(cfg, 2, T, seed=T, lengths=[T, T - 7])]
+        noise = synthetic.draw_noise(cfg, 2, T, seed=T + 1)
+        plain = net.infer(*inputs, noise=noise, taps={"x_enc": None})[0]
+        for _ in range(3):                                        # eager + capture, then replays
+            assert torch.equal(net.infer(*inputs, noise=noise)[0], plain)

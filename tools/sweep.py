@@ -85,7 +85,7 @@ def main():
         cfg = NAMED_CONFIGS["48k_v2"]
         net = build(cfg, args.precision, dev)
         audio = synthetic.make_song(args.song_seconds, seed=0)
-        hubert = synthetic.FakeHubert(cfg.feat_dim)
+        hubert = synthetic.FakeHubert(cfg.feat_dim, device_rng=True)
         solo = [dist.new_group([r]) for r in range(world)] if world > 1 else None       # 1-rank groups: the unsharded run
         for tier in [t for t in ((3, 10, 60, 64), (1, 6, 38, 41), (1, 5, 30, 32)) if not args.tiers or str(t[2]) in args.tiers.split(",")]:
             def make_vc(group=None):
