@@ -72,6 +72,7 @@ class TcConvDesc(C.Structure):
         ("tanh_out", C.c_void_p), ("acc_nostore", C.c_int32),
         ("inj_har", C.c_void_p), ("inj_w", C.c_void_p), ("inj_b", C.c_void_p),
         ("inj_k", C.c_int32), ("inj_s", C.c_int32), ("inj_pad", C.c_int32), ("inj_cn", C.c_int32), ("inj_Lhar", C.c_int64),
+        ("gelu", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -111,6 +112,10 @@ SYMBOLS = {
                                            C.c_int32, C.c_float, C.c_int32, C.c_void_p]),
     "rvcb200_op_absmax": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
     "rvcb200_op_to_int16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rvcb200_op_hubert_conv0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                          C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int64, C.c_void_p]),
+    "rvcb200_op_layernorm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                         C.c_float, C.c_void_p]),
     "rvcb200_op_quiet_point": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "rvcb200_host_quiet_point": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "rvcb200_host_filtfilt_pad": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,

@@ -127,4 +127,8 @@ cudaError_t launch_to_int16(const float* x, long long n, const float* absmax, sh
 cudaError_t launch_quiet_point(const double* audio_pad, long long lo, long long hi, int window, double* best_v, long long* best_j,
                                int n_blocks, cudaStream_t st);
 
+// ---- HuBERT / ContentVec front end, first layer (hubert_kernels.cu) ----
+cudaError_t launch_hubert_conv0(const float* x, const float* w, const float* gn_w, const float* gn_b, double* stats, void* y16,
+                                int B, long long n, int C, int K, int S, float eps, long long y_bstride, cudaStream_t st);
+
 }  // namespace rvc

@@ -84,6 +84,10 @@ __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.pre_slope);
   }
+  if (p.gelu) {   // exact GELU (torch.nn.functional.gelu default): 0.5 x (1 + erf(x / sqrt(2)))
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+  }
   if (p.mask_pre && !valid) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -784,7 +788,7 @@ inline unsigned grid_for(long long total, int threads) {
 cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   TcConvDesc d = d_in;
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.Cin % 8 != 0 || d.Cout_total % d.N != 0 || d.G < 1 || d.G > 16 ||
-      d.Lj <= 0 || d.L_in <= 0 || (d.ntaps - 1) * d.dil > 120 || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
+      d.Lj <= 0 || d.L_in <= 0 || (d.ntaps - 1) * d.dil > 127 || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
       d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)))
     return cudaErrorInvalidValue;
   EncodeTiledFn enc = encode_tiled();

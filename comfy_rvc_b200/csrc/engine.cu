@@ -1146,6 +1146,19 @@ int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t*
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 
+int rvcb200_op_hubert_conv0(const float* x, const float* w, const float* gn_w, const float* gn_b, double* stats, void* y16,
+                            int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, float eps, int64_t y_bstride, void* stream) {
+  cudaError_t e = launch_hubert_conv0(x, w, gn_w, gn_b, stats, y16, B, n, C, K, S, eps, y_bstride,
+                                      reinterpret_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
+int rvcb200_op_layernorm16(const float* x, const float* gamma, const float* beta, float* y, void* y16, int64_t rows, int32_t C,
+                           float eps, void* stream) {
+  cudaError_t e = launch_layernorm(x, gamma, beta, y, rows, C, eps, reinterpret_cast<cudaStream_t>(stream), y16);
+  return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
+}
+
 int rvcb200_op_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int32_t window, double* best_v, int64_t* best_j,
                            int32_t n_blocks, void* stream) {
   cudaError_t e = launch_quiet_point(audio_pad, lo, hi, window, best_v, reinterpret_cast<long long*>(best_j), n_blocks,

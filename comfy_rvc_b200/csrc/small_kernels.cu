@@ -39,6 +39,7 @@ bool pdl_enabled() {
 namespace {
 
 // ---- LayerNorm over contiguous channels: one warp per row (modules.py:25-28) ---------------
+template <int NV>   // NV = ceil(C / 32) values per lane: 8 (C <= 256, the synthesizer) or 32 (C <= 1024, the HuBERT front end)
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* __restrict__ y, long long rows, int C,
                                  float eps, __half* __restrict__ y16, const int* __restrict__ len, int T) {
@@ -48,7 +49,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
   pdl_wait();
   if (row >= rows) return;
   const float* xr = x + row * C;
-  float v[8];  // C <= 256
+  float v[NV];
   float s = 0.f;
   int n = 0;
   for (int c = lane; c < C; c += 32) { v[n] = xr[c]; s += v[n]; ++n; }
@@ -218,10 +219,15 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, int lds, float* 
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, long long rows, int C,
                              float eps, cudaStream_t st, void* y16, const int* len, int T) {
-  if (C > 256 || rows <= 0) return cudaErrorInvalidValue;
+  if (C > 1024 || rows <= 0) return cudaErrorInvalidValue;
   const int wpb = 8;
-  launch_pdl(layernorm_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, st, x, gamma, beta, y, rows, C, eps,
-                                                                            reinterpret_cast<__half*>(y16), len, T > 0 ? T : 1);
+  const dim3 grid((unsigned)((rows + wpb - 1) / wpb)), block(wpb * 32);
+  if (C <= 256)
+    launch_pdl(layernorm_kernel<8>, grid, block, 0, st, x, gamma, beta, y, rows, C, eps, reinterpret_cast<__half*>(y16), len,
+               T > 0 ? T : 1);
+  else
+    launch_pdl(layernorm_kernel<32>, grid, block, 0, st, x, gamma, beta, y, rows, C, eps, reinterpret_cast<__half*>(y16), len,
+               T > 0 ? T : 1);
   launch_counter().n++;
   return cudaGetLastError();
 }

@@ -219,6 +219,9 @@ typedef struct rvcb200_tc_conv_desc {
    * v[ph*inj_cn + c] += inj_b[c] + sum_k har[b][(j*u + ph) * inj_s - inj_pad + k] * inj_w[k][c].  inj_k <= 4. */
   const float* inj_har; const float* inj_w; const float* inj_b;
   int32_t inj_k, inj_s, inj_pad, inj_cn; int64_t inj_Lhar;
+  int32_t gelu;                /* generic epilogue: exact (erf) GELU right after bias / cond / gather / alpha, before the
+                                * residual (the HuBERT front end: conv stack, positional conv, feed-forward) */
+  int32_t reserved0;
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 
@@ -271,6 +274,22 @@ int rvcb200_op_absmax(const float* x, int64_t n, float* out, int32_t reset, void
 /* out[i] = (int16) trunc(x[i] * 32768 / (*absmax / 0.99)) in float32 arithmetic (vc_infer_pipeline.py:188-189,
  * NumPy >= 2 promotion). */
 int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t* out, void* stream);
+
+/* ---- HuBERT / ContentVec front end (host orchestration in comfy_rvc_b200/hubert.py) ----
+ * Replaces transformers.HubertModel as reached from /root/reference/lib/infer_pack/loaders.py:52-61.  Every contraction
+ * of the model runs through rvcb200_op_conv_tc (generic epilogue, `gelu`) and rvcb200_op_attention_tc; these two entries
+ * are what is left: */
+
+/* First feature-encoder layer: y16[b][t][c] = GELU(GroupNorm_c(sum_k w[c][k] x[b][t*S + k])) as fp16 channels-last,
+ * t < L0 = (n - K) / S + 1; per-channel statistics over time, biased variance, affine gn_w / gn_b.  stats: scratch of
+ * B * 2 * C doubles; y_bstride: elements between batch items of y16.  K <= 16. */
+int rvcb200_op_hubert_conv0(const float* x, const float* w, const float* gn_w, const float* gn_b, double* stats, void* y16,
+                            int32_t B, int64_t n, int32_t C, int32_t K, int32_t S, float eps, int64_t y_bstride, void* stream);
+
+/* LayerNorm over the last (contiguous) axis, C <= 1024: y (fp32) and, if y16 != NULL, an fp16 copy (the MMA operand of
+ * the next contraction). */
+int rvcb200_op_layernorm16(const float* x, const float* gamma, const float* beta, float* y, void* y16, int64_t rows, int32_t C,
+                           float eps, void* stream);
 
 /* Device form of the quiet-point search below (same sums, same order, one thread per candidate): block k of `n_blocks`
  * writes the first minimum of its contiguous share of [lo, hi) to best_v[k] / best_j[k] (absolute index, -1 if the share
