@@ -45,8 +45,12 @@ using namespace tc;
 
 // Generic epilogue (text encoder / flow): channels-last or PV fp32 I/O, embedding gather, scale, gate,
 // masks, residual modes.  One pass over 16 accumulator columns of this thread's row.
+// `sb`: bias (+ speaker conditioning) of these 16 columns, staged in shared memory before the accumulator was waited for;
+// `pre`: the residual (or the running sum of `accum`) of this row's output columns, loaded before that wait as well (null:
+// loaded here).  Both used to be global loads issued after the accumulator arrived, one L2 round trip after the other per
+// 16-column pass -- ~10 of the 15 us of a one-tile launch (profiles/r2_short_step_T100.md).
 __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t taddr, bool row_ok, bool valid, int b,
-                                                   long long orow, int co) {
+                                                   long long orow, int co, const float* sb, const float4* pre) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -58,12 +62,7 @@ __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t
   const long long Lout = (long long)p.Lj * p.out_stride;
   float v[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __ldg(p.bias + co + i);
-  if (p.cond) {
-    const float* cond = p.cond + (size_t)b * p.cond_bstride;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += __ldg(cond + co + i);
-  }
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sb[i];
   if (p.gather) {
     const long long gi = p.gidx[(long long)b * p.gidx_bstride + orow];
     const float* gr = p.gather + gi * p.Cout_total + co;
@@ -106,7 +105,7 @@ __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4)
       if (k4 * 4 < nout) {
-        const float4 q = *reinterpret_cast<const float4*>(rp + k4 * cstep);
+        const float4 q = pre ? pre[k4] : *reinterpret_cast<const float4*>(rp + k4 * cstep);
         if (p.res_mode == 2) {
           v[k4 * 4 + 0] = q.x - v[k4 * 4 + 0]; v[k4 * 4 + 1] = q.y - v[k4 * 4 + 1];
           v[k4 * 4 + 2] = q.z - v[k4 * 4 + 2]; v[k4 * 4 + 3] = q.w - v[k4 * 4 + 3];
@@ -124,7 +123,7 @@ __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4)
       if (k4 * 4 < nout) {
-        const float4 q = *reinterpret_cast<const float4*>(yp + k4 * cstep);
+        const float4 q = (pre && !p.res32) ? pre[k4] : *reinterpret_cast<const float4*>(yp + k4 * cstep);
         v[k4 * 4 + 0] += q.x; v[k4 * 4 + 1] += q.y; v[k4 * 4 + 2] += q.z; v[k4 * 4 + 3] += q.w;
       }
   }
@@ -391,12 +390,42 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       const int row = mt * BM + qd * 32 + lane;
       const bool row_ok = row < p.Lj;
       const long long orow = (long long)row * p.out_stride + g;
+      float4 pre[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool have_pre = false;
+      bool valid = true;
+      float* sb = nullptr;
+      if (GENERIC) {
+        // everything the epilogue needs from global memory is fetched BEFORE the accumulator is waited for, i.e. under
+        // the tile's TMA loads and MMAs: bias + conditioning -> shared memory (one copy per epilogue group), this row's
+        // residual / running sum -> registers, the row's mask bit
+        sb = reinterpret_cast<float*>(sE) + eg * 256;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");        // the group's previous tile no longer reads sb
+        const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
+        for (int i = qd * 32 + lane; i < p.N; i += 128) sb[i] = __ldg(p.bias + nt * p.N + i) + (cond ? __ldg(cond + nt * p.N + i) : 0.f);
+        valid = p.out_len ? (orow < p.out_len[b]) : true;
+        have_pre = p.f32_cl && !p.gate && p.N <= 64 && ((p.res32 != nullptr) != (p.accum != 0)) && row_ok;
+        if (have_pre) {
+          const float* src = p.res32 ? p.res32 + ((size_t)b * Lout + orow) * p.ldr32 : p.y32 + ((size_t)b * Lout + orow) * p.ldy32;
+          src += nt * p.N;
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k * 4 < p.N) pre[k] = *reinterpret_cast<const float4*>(src + k * 4);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + eg) : "memory");        // sb is complete
+      }
       mbar_wait(&acc_full[eg], (t >> 1) & 1);
       tc_fence_after();
       if (GENERIC) {
-        const bool valid = p.out_len ? (orow < p.out_len[b]) : true;
-        for (int c0 = 0; c0 < p.N; c0 += 16)
-          epilogue_generic16(p, tbase + (uint32_t)c0, row_ok, valid, b, orow, nt * p.N + c0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          float4 pq[4];                                  // this pass's 16 prefetched words (static indices: registers)
+          const int ci = c0 >> 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pq[k] = ci == 0 ? pre[k] : ci == 1 ? pre[4 + k] : ci == 2 ? pre[8 + k] : pre[12 + k];
+          epilogue_generic16(p, tbase + (uint32_t)c0, row_ok, valid, b, orow, nt * p.N + c0, sb + c0, have_pre ? pq : nullptr);
+        }
       } else {
         const size_t orow16 = (size_t)(orow + p.padf) * 16;
         unsigned char* y32 = p.y32 ? reinterpret_cast<unsigned char*>(p.y32) + (size_t)b * (p.Cout_total / (p.acc_f16 ? 8 : 4)) * pitch_o
@@ -451,6 +480,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
 }
 
 constexpr size_t kStageBytes = 8 * 2 * 2048 + 1024;   // tma_out staging (+ alignment slack)
+constexpr size_t kGenericBiasBytes = 2 * 256 * 4 + 1024;   // generic epilogue: staged bias + conditioning per epilogue group
 
 size_t tc_smem_bytes(const TcConvDesc& d) {
   const int halo = (d.ntaps - 1) * d.dil;
@@ -458,7 +488,7 @@ size_t tc_smem_bytes(const TcConvDesc& d) {
   const size_t a = (((size_t)R * 128) + 1023) & ~(size_t)1023;
   const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
   return 1024 + d.na_stages * a + d.nb_stages * bb + 8 * (2 * d.na_stages + 2 * d.nb_stages + 4) + 16 + 128 +
-         (d.tma_out ? kStageBytes : 0);
+         (d.tma_out ? kStageBytes : 0) + (d.generic ? kGenericBiasBytes : 0);
 }
 
 // ---- driver entry point for tensor-map encoding (no link-time dependency on libcuda) --------------
@@ -809,7 +839,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
     // lean epilogue with a 16-bit output in whole 32-column chunks: staged + TMA-stored (see the kernel)
     d.tma_out = (!d.generic && d.y16 && d.N % 32 == 0) ? 1 : 0;
-    size_t budget = 208 * 1024 - (d.tma_out ? kStageBytes : 0);
+    size_t budget = 208 * 1024 - (d.tma_out ? kStageBytes : 0) - (d.generic ? kGenericBiasBytes : 0);
     // Launches of at most two waves (the text encoder / flow contractions, M = T rows) can be given a small ring so that
     // the CTAs of the NEXT launch fit on the SM beside them and run their prologue under this launch's tail
     // (programmatic dependent launch, RVCB200_PDL=1): RVCB200_SMALL_SMEM_KB=<KB> (0 = off)
