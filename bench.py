@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-incumbent", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-front-end", action="store_true")
     ap.add_argument("--no-extra-precision", action="store_true", help="skip the fp16 leg beside the bf16 headline")
     args = ap.parse_args()
 
@@ -518,6 +519,31 @@ def main():
         if not args.no_parity:
             line["fp16"]["parity"] = parity_block(net, cfg, T, "fp16", args.config)
         net.set_precision(args.precision)
+    if world == 1 and not args.no_front_end:
+        # the step in front of the synthesizer in the real node: HuBERT / ContentVec features of the
+        # same 60 s of 16 kHz audio on the same kernels (comfy_rvc_b200.HubertB200), device-resident input; context for how
+        # a whole VC.vc segment divides between front end and synthesis -- not part of `value`
+        try:
+            from comfy_rvc_b200.hubert import HubertB200
+            hub = HubertB200(synthetic.HUBERT_BASE, synthetic.make_hubert_state_dict(0), dev)
+            src = synthetic.make_speech(audio_s, seed=1).to(dev)
+            for _ in range(3):
+                hub.extract_features(version="v2", source=src)
+            torch.cuda.synchronize()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(args.steps):
+                hub.extract_features(version="v2", source=src)
+            h1.record()
+            torch.cuda.synchronize()
+            hms = h0.elapsed_time(h1) / args.steps
+            line["front_end"] = {"what": "HubertB200.extract_features(v2) on the segment's 16 kHz audio", "ms_per_segment": hms,
+                                 "audio_s_per_s": audio_s / (hms / 1e3), "launches": hub.last_launches,
+                                 "segment_ms_front_end_plus_synthesis": hms + ms / args.steps}
+            del hub, src
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            line["front_end"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     if world == 1 and not args.no_gpu_incumbent:
         inc = {}
         for name, half in (("fp16", True), ("fp32_tf32_off", False)):

@@ -860,9 +860,17 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
       long long na = (long long)(budget_s - (size_t)nw * bb) / (long long)a;
       d.na_stages = (int)(na > na_max ? na_max : na);
     } else {
-      d.na_stages = d.a_mode != 1 ? (nkb >= 2 ? 3 : 2) : 4;
+      // ring depths: a one-tile-per-CTA contraction (text encoder, flow, HuBERT) is bound by how many bytes each CTA keeps
+      // in flight against the ~1.5-2 us L2 / HBM latency, so generic launches take deeper rings than the streaming convs
+      // (RVCB200_GEN_NA / RVCB200_GEN_NB override for A/B runs)
+      static const int gen_na = [] { const char* e = getenv("RVCB200_GEN_NA"); return e ? atoi(e) : 5; }();
+      static const int gen_nb = [] { const char* e = getenv("RVCB200_GEN_NB"); return e ? atoi(e) : 16; }();
+      const int na_pref = d.generic ? (nkb < gen_na ? (nkb < 2 ? 2 : nkb) : gen_na) : (nkb >= 2 ? 3 : 2);
+      d.na_stages = d.a_mode != 1 ? na_pref : 4;
+      while (d.na_stages > 2 && (size_t)d.na_stages * a + 4 * bb > budget) --d.na_stages;
+      const long long nb_cap = d.generic ? gen_nb : 10;
       long long nb = (long long)(budget - (size_t)d.na_stages * a) / (long long)bb;
-      d.nb_stages = (int)(nb > 10 ? 10 : (nb < 2 ? 2 : nb));
+      d.nb_stages = (int)(nb > nb_cap ? nb_cap : (nb < 2 ? 2 : nb));
     }
   }
   const size_t smem = tc_smem_bytes(d);

@@ -115,6 +115,11 @@ class HubertB200:
         W: Dict[str, torch.Tensor] = {}
         f32 = lambda t: t.to(dev, torch.float32).contiguous()
         img = lambda w, n: pack_tc(w, torch.float16, n).to(dev)          # [taps][C_in][C_out] -> tcgen05 weight image
+        self._src: Dict[str, torch.Tensor] = {}                          # fp32 sources of the re-tileable projections
+
+        def proj(name, w):                                               # image for the default N = 64; others on demand
+            self._src[name] = w.contiguous()
+            return img(w, 64)
         C0 = self.conv_dim[0]
         W["conv0.w"] = f32(sd["feature_extractor.conv_layers.0.conv.weight"][:, 0, :])               # [C][K]
         W["conv0.gn_w"] = f32(sd["feature_extractor.conv_layers.0.layer_norm.weight"])
@@ -129,7 +134,7 @@ class HubertB200:
                 taps[1, :C0] = w[:, :, 2].t()                                                         # row 2t+2
             W[f"conv{i}.w"] = img(taps, 256)
         W["fp.ln_w"], W["fp.ln_b"] = f32(sd["feature_projection.layer_norm.weight"]), f32(sd["feature_projection.layer_norm.bias"])
-        W["fp.w"] = img(sd["feature_projection.projection.weight"].t()[None], 64)
+        W["fp.w"] = proj("fp.w", sd["feature_projection.projection.weight"].t()[None])
         W["fp.b"] = f32(sd["feature_projection.projection.bias"])
         p = "encoder.pos_conv_embed.conv."
         if p + "parametrizations.weight.original0" in sd:
@@ -155,16 +160,16 @@ class HubertB200:
                     c0 = (pi * nh + h) * HEAD_PAD
                     wq[:, c0:c0 + dk] = wn[:, h * dk:(h + 1) * dk] * sc
                     bq[c0:c0 + dk] = bn[h * dk:(h + 1) * dk] * sc
-            W[f"l{l}.qkv.w"], W[f"l{l}.qkv.b"] = img(wq[None], 64), f32(bq)
+            W[f"l{l}.qkv.w"], W[f"l{l}.qkv.b"] = proj(f"l{l}.qkv.w", wq[None]), f32(bq)
             wo = torch.zeros(nh * HEAD_OUT, H)
             wt = sd[q + "attention.out_proj.weight"].t()                                               # [in][out]
             for h in range(nh):
                 wo[h * HEAD_OUT:h * HEAD_OUT + dk] = wt[h * dk:(h + 1) * dk]
-            W[f"l{l}.o.w"], W[f"l{l}.o.b"] = img(wo[None], 64), f32(sd[q + "attention.out_proj.bias"])
+            W[f"l{l}.o.w"], W[f"l{l}.o.b"] = proj(f"l{l}.o.w", wo[None]), f32(sd[q + "attention.out_proj.bias"])
             W[f"l{l}.ln1_w"], W[f"l{l}.ln1_b"] = f32(sd[q + "layer_norm.weight"]), f32(sd[q + "layer_norm.bias"])
-            W[f"l{l}.ff1.w"] = img(sd[q + "feed_forward.intermediate_dense.weight"].t()[None], 64)
+            W[f"l{l}.ff1.w"] = proj(f"l{l}.ff1.w", sd[q + "feed_forward.intermediate_dense.weight"].t()[None])
             W[f"l{l}.ff1.b"] = f32(sd[q + "feed_forward.intermediate_dense.bias"])
-            W[f"l{l}.ff2.w"] = img(sd[q + "feed_forward.output_dense.weight"].t()[None], 64)
+            W[f"l{l}.ff2.w"] = proj(f"l{l}.ff2.w", sd[q + "feed_forward.output_dense.weight"].t()[None])
             W[f"l{l}.ff2.b"] = f32(sd[q + "feed_forward.output_dense.bias"])
             W[f"l{l}.ln2_w"], W[f"l{l}.ln2_b"] = f32(sd[q + "final_layer_norm.weight"]), f32(sd[q + "final_layer_norm.bias"])
         W["final.w"] = img(sd["final_proj.weight"].t()[None], 64)
@@ -196,6 +201,23 @@ class HubertB200:
         if st != 0:
             raise RuntimeError(f"rvcb200_op_conv_tc failed with status {st} (Cin={Cin}, Cout={Cout}, taps={ntaps}, rows={Lj})")
         self.last_launches += 1
+
+    def _tiled(self, name, rows, Cout):
+        """(weight image, N tile) for a projection of `rows` x `Cout` outputs: the widest N in {256, 128, 64} that still
+        yields a full wave of 128-row tiles (>= 132 CTAs) -- a wide tile re-reads the activation rows from L2 fewer times
+        (N = 64: every 128 x K block is fetched C_out / 64 times); short inputs keep N = 64 to occupy more SMs."""
+        mt = (rows + 127) // 128
+        n = 64
+        for cand in (256, 128):
+            if Cout % cand == 0 and mt * (Cout // cand) >= 132:
+                n = cand
+                break
+        if n == 64:
+            return self._w[name], 64
+        key = f"{name}@{n}"
+        if key not in self._w:
+            self._w[key] = pack_tc(self._src[name], torch.float16, n).to(self.device)
+        return self._w[key], n
 
     def _ln(self, x32, gw, gb, y32, y16, rows, Cn):
         st = _lib.load().rvcb200_op_layernorm16(C.c_void_p(x32.data_ptr()), C.c_void_p(gw.data_ptr()), C.c_void_p(gb.data_ptr()),
@@ -266,7 +288,8 @@ class HubertB200:
             self._ln(feat32, W["fp.ln_w"], W["fp.ln_b"], ln32, ln16, T, C0)
             h32 = torch.empty(T, H, dtype=torch.float32, device=dev)
             h16 = torch.empty(T, H, dtype=torch.float16, device=dev)
-            self._gemm(ln16.data_ptr(), T, C0, W["fp.w"], W["fp.b"], H, T, y32=h32.data_ptr(), ldy32=H, y16=h16.data_ptr(), ldy16=H)
+            w16, nt_ = self._tiled("fp.w", T, H)
+            self._gemm(ln16.data_ptr(), T, C0, w16, W["fp.b"], H, T, n_tile=nt_, y32=h32.data_ptr(), ldy32=H, y16=h16.data_ptr(), ldy16=H)
             # positional convolution: h + GELU(conv_k128_groups16(h) + b), one launch per group
             t32 = torch.empty(T, H, dtype=torch.float32, device=dev)
             cg = H // self.gpos
@@ -283,7 +306,8 @@ class HubertB200:
             att16 = torch.empty(T, nh * HEAD_OUT, dtype=torch.float16, device=dev)
             ff16 = torch.empty(T, self.inter, dtype=torch.float16, device=dev)
             for l in range(n_layers):
-                self._gemm(h16.data_ptr(), T, H, W[f"l{l}.qkv.w"], W[f"l{l}.qkv.b"], 3 * nh * HEAD_PAD, T, y16=qkv16.data_ptr(),
+                w16, nt_ = self._tiled(f"l{l}.qkv.w", T, 3 * nh * HEAD_PAD)
+                self._gemm(h16.data_ptr(), T, H, w16, W[f"l{l}.qkv.b"], 3 * nh * HEAD_PAD, T, n_tile=nt_, y16=qkv16.data_ptr(),
                            ldy16=3 * nh * HEAD_PAD)
                 st = lib.rvcb200_op_attention_tc(C.c_void_p(qkv16.data_ptr()), C.c_void_p(vt16.data_ptr()),
                                                  C.c_void_p(W["ek0"].data_ptr()), C.c_void_p(W["evt0"].data_ptr()), None,
@@ -291,12 +315,15 @@ class HubertB200:
                 if st != 0:
                     raise RuntimeError(f"rvcb200_op_attention_tc failed with status {st}")
                 self.last_launches += 2
-                self._gemm(att16.data_ptr(), T, nh * HEAD_OUT, W[f"l{l}.o.w"], W[f"l{l}.o.b"], H, T, y32=t32.data_ptr(), ldy32=H,
+                w16, nt_ = self._tiled(f"l{l}.o.w", T, H)
+                self._gemm(att16.data_ptr(), T, nh * HEAD_OUT, w16, W[f"l{l}.o.b"], H, T, n_tile=nt_, y32=t32.data_ptr(), ldy32=H,
                            res32=h32.data_ptr(), ldr32=H)
                 self._ln(t32, W[f"l{l}.ln1_w"], W[f"l{l}.ln1_b"], h32, h16, T, H)
-                self._gemm(h16.data_ptr(), T, H, W[f"l{l}.ff1.w"], W[f"l{l}.ff1.b"], self.inter, T, gelu=True, y16=ff16.data_ptr(),
+                w16, nt_ = self._tiled(f"l{l}.ff1.w", T, self.inter)
+                self._gemm(h16.data_ptr(), T, H, w16, W[f"l{l}.ff1.b"], self.inter, T, n_tile=nt_, gelu=True, y16=ff16.data_ptr(),
                            ldy16=self.inter)
-                self._gemm(ff16.data_ptr(), T, self.inter, W[f"l{l}.ff2.w"], W[f"l{l}.ff2.b"], H, T, y32=t32.data_ptr(), ldy32=H,
+                w16, nt_ = self._tiled(f"l{l}.ff2.w", T, H)
+                self._gemm(ff16.data_ptr(), T, self.inter, w16, W[f"l{l}.ff2.b"], H, T, n_tile=nt_, y32=t32.data_ptr(), ldy32=H,
                            res32=h32.data_ptr(), ldr32=H)
                 self._ln(t32, W[f"l{l}.ln2_w"], W[f"l{l}.ln2_b"], h32, h16, T, H)
             if version == "v1":

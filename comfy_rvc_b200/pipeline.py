@@ -272,6 +272,7 @@ class VC(FeatureExtractor):
         self.noise_mode, self.seed, self.group = noise, int(seed), group
         self._host_group = None
         self._stage_buf: Optional[torch.Tensor] = None
+        self._out_buf: Optional[torch.Tensor] = None
         self.last_plan: Optional[dict] = None
 
     # ---- one segment ------------------------------------------------------------------------------------
@@ -395,6 +396,12 @@ class VC(FeatureExtractor):
         segs = plan_segments(audio_pad.shape[0], opt_ts, self.window, self.t_pad2)
         return audio, audio_pad, opt_ts, segs
 
+    def _pinned_out(self, n: int) -> torch.Tensor:
+        """Reusable pinned int16 buffer for the song's single D2H copy (cudaHostAlloc of ~60 MB costs ~10 ms per call)."""
+        if self._out_buf is None or self._out_buf.numel() < n:
+            self._out_buf = torch.empty(max(n, 1), dtype=torch.int16).pin_memory()
+        return self._out_buf[:n]
+
     def _staging(self, n: int) -> np.ndarray:
         """Reusable float64 host buffer the filtered, padded song is written into: pinned when a CUDA device is present
         (it is the source of the song's one H2D copy), plain memory otherwise (host-only planning)."""
@@ -459,7 +466,8 @@ class VC(FeatureExtractor):
         if world > 1 and self._device_collectives(dist, staged):
             # NCCL group: the peak is one 4-byte all-reduce and the int16 pieces travel GPU to GPU (NVLink); rank 0 orders
             # them on the device and does the song's single D2H -- no pickling, no host round trip per rank
-            out = self._finalize_gather_device(staged, parts, len(segs), assignment, dist, rank, world, all_ranks)
+            sizes = [min(s.n_samples // self.window, 2 * hubert_frames(s.n_samples)) * net_g.cfg.upp - 2 * self.t_pad_tgt for s in segs]
+            out = self._finalize_gather_device(staged, parts, sizes, assignment, dist, rank, world, all_ranks)
             self._timing(staged, ev0, t0, t_plan, t1, t_enq)
             times[2] += time.time() - t1
             return out
@@ -576,7 +584,7 @@ class VC(FeatureExtractor):
                                    "cannot be pre-drawn")
             return o[self.t_pad_tgt: o.shape[0] - self.t_pad_tgt]                              # :174/:180 trim, on device
 
-    def _finalize_gather_device(self, staged, parts, n_segs, assignment, dist, rank, world, all_ranks):
+    def _finalize_gather_device(self, staged, parts, sizes_h, assignment, dist, rank, world, all_ranks):
         """`_finalize` + the gather for an NCCL group, all on the device: peak = all-reduce(max) of one float; every rank
         converts its segments to int16 against the song-wide peak; the pieces go to rank 0 (to every rank with
         `all_ranks`) as bytes over NVLink; the destination orders them by segment index and copies the song to the host
@@ -590,14 +598,13 @@ class VC(FeatureExtractor):
             _lib.check(lib.rvcb200_op_absmax(C.c_void_p(local.data_ptr()), local.numel(), C.c_void_p(peak.data_ptr()), 1,
                                              stream), None, "absmax")
             dist.all_reduce(peak, op=dist.ReduceOp.MAX, group=self.group)                      # :188, the only reduction
-            sizes = torch.zeros(n_segs, device=dev, dtype=torch.int64)                         # samples per segment, from its owner
-            for i, p in parts:
-                sizes[i] = p.numel()
-            dist.all_reduce(sizes, op=dist.ReduceOp.SUM, group=self.group)
+            for i, p in parts:           # every rank derives all piece sizes from the plan (400 / 320 frame formula of the front end)
+                if int(p.numel()) != sizes_h[i]:
+                    raise RuntimeError("HuBERT front end does not follow the 400/320 frame formula; segment sizes cannot be "
+                                       "derived from the plan for the device-side gather")
             pcm = torch.empty(local.numel(), device=dev, dtype=torch.int16)
             _lib.check(lib.rvcb200_op_to_int16(C.c_void_p(local.data_ptr()), local.numel(), C.c_void_p(peak.data_ptr()),
                                                C.c_void_p(pcm.data_ptr()), stream), None, "to_int16")
-            sizes_h = sizes.cpu().tolist()
             per_rank = [sum(sizes_h[i] for i in assignment[r]) for r in range(world)]
             dst_ranks = list(range(world)) if all_ranks else [0]
             bufs = {}
@@ -630,10 +637,10 @@ class VC(FeatureExtractor):
                     n = sizes_h[i]
                     song[offs[i]: offs[i] + n] = bufs[r].view(torch.int16)[o: o + n]
                     o += n
-            out_h = torch.empty(song.numel(), dtype=torch.int16).pin_memory()
+            out_h = self._pinned_out(song.numel())
             out_h.copy_(song, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-        return out_h.numpy()
+        return out_h.numpy().copy()              # the caller owns the result; the pinned buffer is reused by the next song
 
     def _finalize(self, staged, parts, exchange_peak) -> dict:
         """Concatenate this rank's trimmed segments, peak-normalise against the song-wide max and convert to int16 on the
@@ -651,7 +658,7 @@ class VC(FeatureExtractor):
             pcm = torch.empty(local.numel(), device=dev, dtype=torch.int16)
             _lib.check(lib.rvcb200_op_to_int16(C.c_void_p(local.data_ptr()), local.numel(), C.c_void_p(peak.data_ptr()),
                                                C.c_void_p(pcm.data_ptr()), stream), None, "to_int16")
-            out_h = torch.empty(pcm.numel(), dtype=torch.int16).pin_memory()
+            out_h = self._pinned_out(pcm.numel())
             out_h.copy_(pcm, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
         out = out_h.numpy()
