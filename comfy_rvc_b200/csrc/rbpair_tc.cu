@@ -91,6 +91,7 @@ struct PairParams {
   void* y32;                   // planar-vector fp16 branch sum [B][C/8][Lp_out][8] (or null)
   void* y16;                   // 16-bit channels-last output lrelu_{out_slope}(x') (or null)
   int Lp_out, padf, accum, out_bf16;
+  int acc_nostore;             // 1: the branch sum is read (accum) but not written back (the decoder's last tensor leaves as y16 only)
   float div, out_slope, res_neg_scale;
 };
 
@@ -399,6 +400,7 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
     const bool has_y16 = p.y16 != nullptr;
     const bool has_acc = p.y32 != nullptr;
     const bool do_acc = has_acc && p.accum != 0;
+    const bool st_acc = p.acc_nostore == 0;
     unsigned char* my_stage = sE + (size_t)ew * K::OUT_SLOTS * K::NCH * kPairBox;   // [OUT_SLOTS sets][NCH boxes]
     const uint32_t sw_row = (uint32_t)lane * 64u, sw_x = ((uint32_t)lane >> 1) & 3u;   // SWIZZLE_64B staging box
     uint32_t oset = 0;
@@ -477,7 +479,7 @@ rbpair_tc_kernel(const PairParams p, const __grid_constant__ CUtensorMap tmA, co
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = v[i] / inv_div;
           }
-          if (row_ok) {
+          if (row_ok && st_acc) {
             unsigned char* q = acc + (size_t)(c0 / 8) * pitch_o + (size_t)(row + p.padf) * 16;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -601,6 +603,7 @@ cudaError_t launch_pair_one(const TcConvDesc& d1, const TcConvDesc& d2, int B, c
   p.h_slope = d1.out_slope;
   p.y32 = d2.y32; p.y16 = d2.y16;
   p.Lp_out = d2.Lp_out; p.padf = d2.padf; p.accum = d2.accum; p.out_bf16 = d2.out_bf16;
+  p.acc_nostore = d2.acc_nostore;
   p.div = d2.div; p.out_slope = d2.out_slope; p.res_neg_scale = d2.res_neg_scale;
   const long long tiles = (long long)((L + K::OUT_ROWS - 1) / K::OUT_ROWS) * B;
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);      // persistent: one CTA per SM
@@ -639,7 +642,7 @@ cudaError_t launch_pair_v(const TcConvDesc& d1, const TcConvDesc& d2, int B, cud
 // the residual is the pair's own input stream, and the output does not alias it (tiles read a halo of the input).
 bool rbpair_tc_supported(const TcConvDesc& d1, const TcConvDesc& d2) {
   if (!rbconv_tc_supported(d1) || !rbconv_tc_supported(d2)) return false;
-  if (d1.tanh_out || d2.tanh_out || d1.acc_nostore || d2.acc_nostore || d1.inj_har || d2.inj_har) return false;
+  if (d1.tanh_out || d2.tanh_out || d1.acc_nostore || d1.inj_har || d2.inj_har) return false;
   if (!(d1.Cin == 32 || d1.Cin == 64) || d2.Cin != d1.Cin) return false;
   if (!(d1.ntaps == 3 || d1.ntaps == 7 || (d1.ntaps == 11 && d1.Cin == 32)) || d2.ntaps != d1.ntaps || d2.dil != 1) return false;
   if (d1.Lj != d2.Lj || d1.L_in != d2.L_in) return false;
