@@ -793,30 +793,6 @@ __global__ void pv16_to_cl_kernel(const unsigned char* __restrict__ x16, float* 
   }
 }
 
-__global__ void har_im2col16_kernel(const float* __restrict__ har, unsigned char* __restrict__ col, long long L_har, long long L, int k,
-                                    int s, int pad, int Kp) {
-  if (threadIdx.x == 0) pdl_trigger();
-  pdl_wait();
-  const int b = blockIdx.y;
-  const float* hb = har + (long long)b * L_har;
-  const int pieces = Kp / 8;
-  const long long total = L * pieces;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long t = idx / pieces;
-    const int j0 = (int)(idx - t * pieces) * 8;
-    const long long h0 = t * s - pad + j0;
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const long long h = h0 + j;
-      f[j] = (j0 + j < k && h >= 0 && h < L_har) ? __ldg(hb + h) : 0.f;
-    }
-    uint4 o;
-    o.x = pack2(false, f[0], f[1]); o.y = pack2(false, f[2], f[3]); o.z = pack2(false, f[4], f[5]); o.w = pack2(false, f[6], f[7]);
-    *reinterpret_cast<uint4*>(col + (((long long)b * L + t) * Kp + j0) * 2) = o;
-  }
-}
-
 __global__ void pv32_to_cl_kernel(const unsigned char* __restrict__ x32, float* __restrict__ y, long long L, int C, int Lp, int padf) {
   // debug/tap helper: PV32 -> channels-last [B][L][C]
   const int b = blockIdx.y;
@@ -884,17 +860,11 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
       long long na = (long long)(budget_s - (size_t)nw * bb) / (long long)a;
       d.na_stages = (int)(na > na_max ? na_max : na);
     } else {
-      // ring depths: a one-tile-per-CTA contraction (text encoder, flow, HuBERT) is bound by how many bytes each CTA keeps
-      // in flight against the ~1.5-2 us L2 / HBM latency, so generic launches take deeper rings than the streaming convs
-      // (RVCB200_GEN_NA / RVCB200_GEN_NB override for A/B runs)
-      static const int gen_na = [] { const char* e = getenv("RVCB200_GEN_NA"); return e ? atoi(e) : 5; }();
-      static const int gen_nb = [] { const char* e = getenv("RVCB200_GEN_NB"); return e ? atoi(e) : 16; }();
-      const int na_pref = d.generic ? (nkb < gen_na ? (nkb < 2 ? 2 : nkb) : gen_na) : (nkb >= 2 ? 3 : 2);
-      d.na_stages = d.a_mode != 1 ? na_pref : 4;
-      while (d.na_stages > 2 && (size_t)d.na_stages * a + 4 * bb > budget) --d.na_stages;
-      const long long nb_cap = d.generic ? gen_nb : 10;
+      // (ring depths: 5 slabs / 16 weight tiles instead of 3 / 10 changed nothing for the one-tile-per-CTA contractions,
+      //  profiles/r2_ab_rings_injgemm.md)
+      d.na_stages = d.a_mode != 1 ? (nkb >= 2 ? 3 : 2) : 4;
       long long nb = (long long)(budget - (size_t)d.na_stages * a) / (long long)bb;
-      d.nb_stages = (int)(nb > nb_cap ? nb_cap : (nb < 2 ? 2 : nb));
+      d.nb_stages = (int)(nb > 10 ? 10 : (nb < 2 ? 2 : nb));
     }
   }
   const size_t smem = tc_smem_bytes(d);
@@ -1001,18 +971,6 @@ cudaError_t launch_noise_add16(const float* har, const float* wn, const float* n
   dim3 grid((unsigned)(n_tiles < 148 * per ? n_tiles : 148 * per), B);
   cudaError_t le = launch_pdl(noise_add16_kernel, grid, dim3(256), smem, st, har, wn, nb, reinterpret_cast<unsigned char*>(x16), L_har,
                               L, C, k, s, pad, slope, TR);
-  launch_counter().n++;
-  return le != cudaSuccess ? le : cudaGetLastError();
-}
-
-// Harmonic source -> the A operand of the injection GEMM: col[b][t][j] = har[b][t*s - pad + j] (0 outside the signal and for
-// j >= k), fp16, Kp columns per row.  11.5 MB per 60 s segment and stage.
-cudaError_t launch_har_im2col16(const float* har, void* col16, int B, long long L_har, long long L, int k, int s, int pad, int Kp,
-                                cudaStream_t st) {
-  if (!har || !col16 || B <= 0 || L <= 0 || k < 1 || Kp < k || Kp % 8 != 0 || s < 1) return cudaErrorInvalidValue;
-  dim3 grid(grid_for(L * (Kp / 8), 256), B);
-  cudaError_t le = launch_pdl(har_im2col16_kernel, grid, dim3(256), 0, st, har, reinterpret_cast<unsigned char*>(col16), L_har, L, k, s,
-                              pad, Kp);
   launch_counter().n++;
   return le != cudaSuccess ? le : cudaGetLastError();
 }

@@ -28,9 +28,6 @@ cudaError_t launch_noise_add_pv(const float* har, const float* wn, const float* 
 // in place on the 16-bit stream: x16 <- lrelu(x16 + noise_conv(har)), x16 holding the transposed conv's raw fp16 output
 cudaError_t launch_noise_add16(const float* har, const float* wn, const float* nb, void* x16, int B, long long L_har,
                                long long L, int C, int k, int s, int pad, float slope, cudaStream_t st);
-// harmonic source -> fp16 im2col rows [B][L][Kp] of the injection GEMM (col[t][j] = har[t*s - pad + j])
-cudaError_t launch_har_im2col16(const float* har, void* col16, int B, long long L_har, long long L, int k, int s, int pad, int Kp,
-                                cudaStream_t st);
 cudaError_t launch_conv_post_pv(const void* x32, const float* w, float* out, int B, long long L, int C, int k, int Lp,
                                 int padf, float slope, cudaStream_t st);
 // same, x planar-vector fp16 [B][C/8][Lp][8] (k = 7)

@@ -986,31 +986,12 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
                                      false, st),
               "dec.to_stream(pv)");
       } else if (f0 && !injected) {
-        // x <- lrelu(x + noise_convs[i](har)) in place on the raw fp16 stream.  Early stages (8 / 80 taps at 48k_v2): the
-        // noise conv is a GEMM [L x k] x [k x C] -- 1.5 GFMA of CUDA-core work at stage 1 (161 us for a tensor that moves in
-        // 15) -- so the harmonic source is laid out once as fp16 im2col rows and the product runs on the tensor core with the
-        // stream as the epilogue's 16-bit residual (RVCB200_INJECT_GEMM=0: the CUDA-core kernel).  IN16 is free here: the
-        // transposed conv has consumed it and the stage's last pair writes the OTHER buffer.
-        static const int inj_gemm = [] { const char* e = getenv("RVCB200_INJECT_GEMM"); return e ? atoi(e) : 1; }();
-        const int Kp = (nk + 7) & ~7;
-        const bool gemm_ok = inj_gemm && nk >= 8 && Cn % 32 == 0 && Cn <= 256 && ctx->tensors.count(S("dec.noise.%d.wg.tc", i)) != 0 &&
-                             (size_t)Kp * (size_t)Ln <= (size_t)Cc * (size_t)pv_pitch_rows(Lc);
-        if (gemm_ok) {
-          CKC(3, launch_har_im2col16(pl.har, IN16, B, Lout, Ln, nk, ns, np, Kp, st), "dec.noise.im2col");
-          TcConvDesc d = tc_base();
-          d.x16 = IN16; d.L_in = (int)Ln; d.w16 = T16(ctx, S("dec.noise.%d.wg.tc", i), 0, 1, &ok); d.bias = W(S("dec.noise.%d.b", i));
-          d.Cin = Kp; d.ntaps = 1; d.g_off[0] = 0;
-          d.N = Cn; d.Cout_total = Cn; d.tmem_cols = tmem_cols_for(d.N);
-          d.Lj = (int)Ln; d.Lp_out = LpN;
-          d.res16 = X16; d.res_neg_scale = 0.f;                  // plain residual: the stream still holds the raw conv output
-          d.y16 = X16; d.out_slope = 0.1f;
-          if (!ok) return RVCB200_ERR_MISSING;
-          CKC(3, launch_conv_tc(d, B, st), "dec.noise.gemm");
-        } else {
-          CKC(3, launch_noise_add16(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X16, B, Lout, Ln, Cn, nk, ns,
-                                    np, 0.1f, st),
-              "dec.noise_add16");
-        }
+        // (tried in round 2: the early stages' noise conv as an im2col GEMM on the tensor core with the stream as 16-bit
+        //  residual -- 0.61 ms of glue instead of 0.53: the extra pass over the im2col rows and the generic kernel's
+        //  thread-per-row residual reads cost more than the CUDA-core FMAs they replace)
+        CKC(3, launch_noise_add16(pl.har, W(S("dec.noise.%d.w", i)), W(S("dec.noise.%d.b", i)), X16, B, Lout, Ln, Cn, nk, ns,
+                                  np, 0.1f, st),
+            "dec.noise_add16");
       }
       if (const rvcb200_tap* t = tp.find(S("dec.ups.%d", i).c_str()))
         CK(launch_pv32_to_cl(X32, reinterpret_cast<float*>(t->dst), B, Ln, Cn, LpN, kPadF, st), "tap");

@@ -85,15 +85,6 @@ def ups_is_dense(cfg: SynthConfig, i: int) -> bool:
     return u == 2 and k == 2 * u and cin in (32, 64, 128, 256)
 
 
-def noise_is_gemm(cfg: SynthConfig, i: int) -> bool:
-    """Stage i's source injection `x + noise_convs[i](har)` (models.py:552-553) runs as [L x k] x [k x C] on the tensor core:
-    the stages whose noise conv has >= 8 taps (the late, <= 4-tap ones sit in the dense ladder's epilogue) and 32 | C <= 256
-    (same rule as csrc/engine.cu)."""
-    k, _, _ = cfg.noise_conv_geometry(i)
-    c = cfg.stage_channels(i)
-    return cfg.f0 and k >= 8 and c % 32 == 0 and c <= 256
-
-
 def post_is_tc(cfg: SynthConfig) -> bool:
     """conv_post (k = 7, C_last -> 1) runs on the specialised tcgen05 resblock kernel when C_last is one of its channel
     counts.  Same rule as `post_tc` in csrc/engine.cu."""
@@ -230,10 +221,6 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
         if cfg.f0:
             P[f"dec.noise.{i}.w"] = w[f"dec.noise_convs.{i}.weight"][:, 0, :].t().contiguous()   # [k][C]
             P[f"dec.noise.{i}.b"] = w[f"dec.noise_convs.{i}.bias"].contiguous()
-            if noise_is_gemm(cfg, i):       # early stages: the injection runs as an im2col GEMM on the tensor core (engine.cu)
-                wk = P[f"dec.noise.{i}.w"]                                                        # [k][C]
-                kp = (wk.shape[0] + 7) // 8 * 8
-                P[f"dec.noise.{i}.wg"] = torch.cat([wk, wk.new_zeros(kp - wk.shape[0], wk.shape[1])], 0)[None].contiguous()
         for j in range(nk):
             n = i * nk + j
             for d in range(len(cfg.resblock_dilation_sizes[j])):
@@ -312,8 +299,6 @@ def tc_weight_names(cfg: SynthConfig):
         names.append(f"dec.ups.{i}.w")
         if ups_is_dense(cfg, i):
             names.append(f"dec.ups.{i}.w3")
-        if noise_is_gemm(cfg, i):
-            names.append(f"dec.noise.{i}.wg")
         for j in range(nk):
             n = i * nk + j
             for d in range(len(cfg.resblock_dilation_sizes[j])):

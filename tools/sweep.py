@@ -57,6 +57,9 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--song-seconds", type=float, default=600.0)
+    ap.add_argument("--front-end", default="fake", choices=["fake", "b200"],
+                    help="song: `fake` = seeded random features drawn on the device (isolates the synthesis path), `b200` = the "
+                         "HuBERT / ContentVec front end on the same kernels (comfy_rvc_b200.HubertB200, seeded weights)")
     ap.add_argument("--tiers", default="", help="song: comma list of x_center values to keep (60,38,30); default all")
     ap.add_argument("--check", action="store_true", help="song under torchrun: also run unsharded and compare bit for bit")
     ap.add_argument("--max-frames", type=int, default=0, help="sweep: only points with batch * frames <= this (0 = all)")
@@ -85,7 +88,11 @@ def main():
         cfg = NAMED_CONFIGS["48k_v2"]
         net = build(cfg, args.precision, dev)
         audio = synthetic.make_song(args.song_seconds, seed=0)
-        hubert = synthetic.FakeHubert(cfg.feat_dim, device_rng=True)
+        if args.front_end == "b200":
+            from comfy_rvc_b200.hubert import HubertB200
+            hubert = HubertB200(synthetic.HUBERT_BASE, synthetic.make_hubert_state_dict(0), dev)
+        else:
+            hubert = synthetic.FakeHubert(cfg.feat_dim, device_rng=True)
         solo = [dist.new_group([r]) for r in range(world)] if world > 1 else None       # 1-rank groups: the unsharded run
         for tier in [t for t in ((3, 10, 60, 64), (1, 6, 38, 41), (1, 5, 30, 32)) if not args.tiers or str(t[2]) in args.tiers.split(",")]:
             def make_vc(group=None):
@@ -123,7 +130,8 @@ def main():
                 secs = out.shape[0] / cfg.sr
                 w = float(np.median(walls))
                 h = {k: round(float(np.median([x[k] for x in host])), 4) for k in host[0]}
-                print(json.dumps({"config": f"48k_v2 VC.pipeline, {args.song_seconds:.0f} s song", "tier": list(tier), "n_gpus": world,
+                print(json.dumps({"config": f"48k_v2 VC.pipeline, {args.song_seconds:.0f} s song", "front_end": args.front_end,
+                                  "tier": list(tier), "n_gpus": world,
                                   "precision": args.precision, "segments": len(plan["segments"]),
                                   "segment_seconds": [round(s.n_samples / 16000, 1) for s in plan["segments"]],
                                   "assignment": plan["assignment"], "makespan_bound": round(plan["makespan_bound"], 3),
