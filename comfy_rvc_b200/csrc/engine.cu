@@ -477,15 +477,20 @@ int64_t rvcb200_workspace_bytes(const rvcb200_ctx* ctx, int32_t B, int32_t T, in
 int64_t rvcb200_last_launch_count(const rvcb200_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
 const char* rvcb200_last_error(const rvcb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 
-int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, const int64_t* phone_lengths,
-                  const int64_t* pitch, const float* nsff0, const int64_t* sid, const float* noise_zp,
-                  const float* noise_sine, float* out, float* stats_out, float* zp_out, float* z_out, void* workspace,
-                  int64_t workspace_bytes, int32_t precision, const rvcb200_tap* taps, int32_t n_taps, void* stream) {
+}  // extern "C"
+
+// `zp_in` != NULL: start from a given (masked) prior sample z_p [B][T][inter] instead of running the text encoder -- the
+// second half of `infer(..., rate=r)` (models.py:802-806: flow and decoder on the last int(T * r) frames).
+static int infer_impl(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, const int64_t* phone_lengths,
+                      const int64_t* pitch, const float* nsff0, const int64_t* sid, const float* noise_zp,
+                      const float* noise_sine, const float* zp_in, float* out, float* stats_out, float* zp_out, float* z_out,
+                      void* workspace, int64_t workspace_bytes, int32_t precision, const rvcb200_tap* taps, int32_t n_taps,
+                      void* stream) {
   if (!ctx) return RVCB200_ERR_ARG;
   if (!ctx->finalized) return fail(ctx, RVCB200_ERR_MISSING, "rvcb200_finalize() has not succeeded%s", "");
   const bool f0 = ctx->cfg.no_f0 == 0;
-  if (B <= 0 || T <= 0 || !phone || !phone_lengths || !sid || !noise_zp || !out || !workspace ||
-      (f0 && (!pitch || !nsff0 || !noise_sine)))
+  if (B <= 0 || T <= 0 || !phone_lengths || !sid || !out || !workspace || (f0 && (!nsff0 || !noise_sine)) ||
+      (!zp_in && (!phone || !noise_zp || (f0 && !pitch))))
     return fail(ctx, RVCB200_ERR_ARG, "null or empty argument%s", "");
   if (precision != RVCB200_PREC_FP32 && precision != RVCB200_PREC_FP16 && precision != RVCB200_PREC_BF16)
     return fail(ctx, RVCB200_ERR_ARG, "unknown precision %s%lld", "", precision);
@@ -520,6 +525,9 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
      "cond_gemv");
 
   if (!tc) {
+  if (zp_in) {
+    CK(cudaMemcpyAsync(zp, zp_in, sizeof(float) * BT * C, cudaMemcpyDeviceToDevice, st), "z_p in");
+  } else {
   // ---------------- TextEncoder (models.py:43-58 / 90-105) -----------------------------------
   {
     ConvDesc d = base_desc();
@@ -583,6 +591,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
   CK(tp.emit("stats", stats, sizeof(float) * BT * 2 * C), "tap");
   CKC(3, launch_zp_sample(stats, noise_zp, pl.len32, zp, B, T, C, st), "zp_sample");
   CK(tp.emit("z_p", zp, sizeof(float) * BT * C), "tap");
+  }
 
   // ---------------- reverse flow (models.py:185-192; modules.py:436-455) ----------------------
   if (z != zp) CK(cudaMemcpyAsync(z, zp, sizeof(float) * BT * C, cudaMemcpyDeviceToDevice, st), "z copy");
@@ -662,6 +671,11 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     if (!ok) return RVCB200_ERR_MISSING;          \
     CKC(cls, launch_conv_tc(d, B, st), what);     \
   } while (0)
+    if (zp_in) {
+      CK(cudaMemcpyAsync(zp, zp_in, sizeof(float) * BT * C, cudaMemcpyDeviceToDevice, st), "z_p in");
+      if (z != zp) CK(cudaMemcpyAsync(z, zp_in, sizeof(float) * BT * C, cudaMemcpyDeviceToDevice, st), "z in");
+      CKC(3, launch_cl32_to_cl16(zp_in, pl.z16, (long long)BT * C, 1.f, false, st), "z_p->fp16");
+    } else {
     CKC(3, launch_cl32_to_cl16(phone, pl.phone16, (long long)BT * f.feat_dim, 1.f, false, st), "phone->fp16");
     {  // x = lrelu((emb_phone(phone) + emb_pitch[pitch]) * sqrt(H)) * mask   models.py:92-100
       TcConvDesc d = gen(pl.phone16, f.feat_dim, "enc.emb.w", "enc.emb.b", H);
@@ -726,6 +740,7 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
     CK(tp.emit("stats", stats, sizeof(float) * BT * 2 * C), "tap");
     CKC(3, launch_zp_sample(stats, noise_zp, pl.len32, zp, B, T, C, st, z != zp ? z : nullptr, pl.z16), "zp_sample");
     CK(tp.emit("z_p", zp, sizeof(float) * BT * C), "tap");
+    }
     {
       bool flipped = false;
       const unsigned short* z16 = reinterpret_cast<const unsigned short*>(pl.z16);
@@ -1076,6 +1091,24 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, co
   if (!ok) return RVCB200_ERR_MISSING;
   ctx->last_launches = launch_counter().n - launches0;
   return RVCB200_OK;
+}
+
+extern "C" {
+
+int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone, const int64_t* phone_lengths,
+                  const int64_t* pitch, const float* nsff0, const int64_t* sid, const float* noise_zp,
+                  const float* noise_sine, float* out, float* stats_out, float* zp_out, float* z_out, void* workspace,
+                  int64_t workspace_bytes, int32_t precision, const rvcb200_tap* taps, int32_t n_taps, void* stream) {
+  return infer_impl(ctx, B, T, phone, phone_lengths, pitch, nsff0, sid, noise_zp, noise_sine, nullptr, out, stats_out, zp_out,
+                    z_out, workspace, workspace_bytes, precision, taps, n_taps, stream);
+}
+
+int rvcb200_infer_tail(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* z_p, const int64_t* lengths, const float* nsff0,
+                       const int64_t* sid, const float* noise_sine, float* out, float* z_out, void* workspace,
+                       int64_t workspace_bytes, int32_t precision, void* stream) {
+  if (!z_p) return RVCB200_ERR_ARG;
+  return infer_impl(ctx, B, T, nullptr, lengths, nullptr, nsff0, sid, nullptr, noise_sine, z_p, out, nullptr, nullptr, z_out,
+                    workspace, workspace_bytes, precision, nullptr, 0, stream);
 }
 
 // ---------------------------------- op-level entry points --------------------------------------

@@ -251,7 +251,7 @@ class SynthesizerB200(nn.Module):
             raise TypeError(f"infer() takes {'(phone, phone_lengths, pitch, nsff0, sid)' if self.f0 else '(phone, phone_lengths, sid)'}")
         pitch, nsff0, sid = rest if self.f0 else (None, None, rest[0])
         if rate:
-            raise NotImplementedError("rate= (tail re-synthesis) is never used by vc_infer_pipeline; not built")
+            return self._infer_rate(phone, phone_lengths, pitch, nsff0, sid, float(rate), noise)
         self._materialize()
         lib = _lib.load()
         dev = self._device
@@ -308,6 +308,59 @@ class SynthesizerB200(nn.Module):
             m_p = stats[:, :, :Ci].transpose(1, 2)
             logs_p = stats[:, :, Ci:].transpose(1, 2)
             return o, x_mask, (z.transpose(1, 2), z_p.transpose(1, 2), m_p, logs_p)
+
+    def _infer_rate(self, phone, phone_lengths, pitch, nsff0, sid, rate, noise):
+        """`infer(..., rate=r)` (models.py:802-806 / :908-912): the text encoder and the prior sample see the whole input,
+        the flow and the decoder only the last `head = int(T * r)` frames.  Not on the pipeline's path (nothing in the
+        reference passes `rate`), so it is built from two engine calls: a full `infer` for m_p / logs_p / z_p, then
+        `rvcb200_infer_tail` on the tail of z_p.  RNG order as in the reference: prior noise for T frames first, then the
+        source's draws for the tail."""
+        dev, cfg = self._device, self.cfg
+        B, T, _ = phone.shape
+        head = int(T * rate)
+        if head <= 0:
+            head = T                         # `z_p[:, :, -0:]` is the whole tensor
+        head = min(head, T)
+        Lh = head * cfg.upp
+        with torch.cuda.device(dev):
+            if noise is None:
+                nz = torch.randn(B, cfg.inter_channels, T, device=dev)
+                ns_tail = None
+                if self.f0:
+                    torch.rand(B, 1, device=dev)                                             # models.py:378 (zeroed, but drawn)
+                    ns_tail = torch.randn(B, Lh, 1, device=dev)
+            else:
+                nz = noise[0]
+                ns_tail = None
+                if self.f0:
+                    ns = noise[2].reshape(B, -1)
+                    ns_tail = ns if ns.shape[1] == Lh else ns[:, -Lh:]
+            full_noise = (nz, None, torch.zeros(B, T * cfg.upp, device=dev)) if self.f0 else (nz,)
+            keep = self.graph_max_frames
+            self.graph_max_frames = 0
+            try:
+                if self.f0:
+                    _, x_mask, (_, z_p, m_p, logs_p) = self.infer(phone, phone_lengths, pitch, nsff0, sid, noise=full_noise)
+                else:
+                    _, x_mask, (_, z_p, m_p, logs_p) = self.infer(phone, phone_lengths, sid, noise=full_noise)
+            finally:
+                self.graph_max_frames = keep
+            lib = _lib.load()
+            zp_tail = z_p[:, :, T - head:].transpose(1, 2).contiguous()                      # channels-last [B][head][C]
+            len_tail = (phone_lengths.to(dev, torch.int64).reshape(-1) - (T - head)).clamp(0, head).contiguous()
+            sid_d = sid.to(dev, torch.int64).reshape(-1).contiguous()
+            f0_tail = nsff0.to(dev, torch.float32)[:, T - head:].contiguous() if self.f0 else None
+            ns_d = ns_tail.to(dev, torch.float32).reshape(B, Lh).contiguous() if self.f0 else None
+            prec = _lib.PREC[self.precision]
+            ws = self._workspace(B, head, prec)
+            o = torch.empty(B, 1, Lh, device=dev, dtype=torch.float32)
+            z = torch.empty(B, head, cfg.inter_channels, device=dev, dtype=torch.float32)
+            p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+            st = lib.rvcb200_infer_tail(self._ctx, B, head, p(zp_tail), p(len_tail), p(f0_tail), p(sid_d), p(ns_d), p(o), p(z),
+                                        p(ws), ws.numel(), prec, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(st, self._ctx, "infer_tail")
+            self.last_launches += int(lib.rvcb200_last_launch_count(self._ctx))
+            return o, x_mask[:, :, T - head:], (z.transpose(1, 2), z_p[:, :, T - head:], m_p, logs_p)
 
     def _outputs(self, B, T, dev):
         cfg = self.cfg

@@ -125,6 +125,13 @@ int rvcb200_infer(rvcb200_ctx* ctx, int32_t B, int32_t T,
                   void* workspace, int64_t workspace_bytes, int32_t precision,
                   const rvcb200_tap* taps, int32_t n_taps, void* stream);
 
+/* Second half of `net_g.infer(..., rate=r)` (models.py:802-806): reverse flow + source + decoder starting from a given masked
+ * prior sample `z_p` [B][T][inter] (channels-last, the last int(T_full * r) frames of what rvcb200_infer returned), with
+ * `lengths` / `nsff0` / `noise_sine` already cut to that tail.  Outputs `out` [B][T*upp], optional `z` [B][T][inter]. */
+int rvcb200_infer_tail(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* z_p, const int64_t* lengths, const float* nsff0,
+                       const int64_t* sid, const float* noise_sine, float* out, float* z, void* workspace,
+                       int64_t workspace_bytes, int32_t precision, void* stream);
+
 /* Per-class device timing of the launches inside rvcb200_infer (CUDA events on the caller's stream,
  * accumulated until the next enable): class 0 = decoder resblock convolutions, 1 = attention,
  * 2 = NSF sine source, 3 = bandwidth-bound glue (LayerNorm, prior sample, source injection, conv_post,

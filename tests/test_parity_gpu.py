@@ -133,3 +133,34 @@ def test_same_process_two_devices(precision):
         outs.append(o.cpu())
     assert torch.equal(outs[0], outs[1])
     assert int16_lsb_diff(gold["o_f32"][0], outs[1][0, 0].numpy()) <= (1 if precision == "fp32" else 400)
+
+
+@pytest.mark.parametrize("name,rate", [("c2_48k_v2", 0.4), ("c3_32k_v2_ragged", 0.75), ("c7_40k_v1_nono", 0.5), ("c1_40k_v1", 0.001)])
+def test_infer_rate_matches_oracle(name, rate):
+    """`infer(..., rate=r)` (models.py:802-806): encoder and prior over the whole input, flow + decoder over the last
+    int(T * r) frames; r so small that head = 0 means the whole tensor (`z_p[:, :, -0:]`)."""
+    cfg, sd, (phone, lens, pitch, pitchf, sid), noise, gold = load_golden(name)
+    net = build_net(cfg, sd)
+    w = rvc_oracle.fold_weight_norm(sd)
+    ins = [t.cuda() for t in (phone, lens, pitch, pitchf, sid)]
+    if cfg.f0:
+        ref = rvc_oracle.infer(w, cfg, phone, lens, pitch, pitchf, sid, *noise, rate=rate)
+        got = net.infer(*ins, rate=rate, noise=noise)
+    else:
+        ref = rvc_oracle.infer_nono(w, cfg, phone, lens, sid, noise[0], rate=rate)
+        got = net.infer(ins[0], ins[1], ins[4], rate=rate, noise=noise[:1])
+    torch.cuda.synchronize()
+    T = phone.shape[1]
+    head = int(T * rate) or T
+    assert got[0].shape == ref[0].shape == (phone.shape[0], 1, head * cfg.upp)
+    assert torch.equal(got[1].cpu(), ref[1]) and got[2][0].shape == ref[2][0].shape == got[2][1].shape
+    for g, r in zip(got[2], ref[2]):
+        np.testing.assert_allclose(g.cpu().numpy(), r.numpy(), rtol=0, atol=1e-4)
+    for b in range(phone.shape[0]):
+        n_valid = max(int(lens[b]) - (T - head), 0)
+        n = (n_valid - 12) * cfg.upp if n_valid < head else head * cfg.upp
+        if n > 0:
+            a, e = ref[0][b, 0, :n].numpy(), got[0][b, 0, :n].cpu().numpy()
+            peak = np.abs(ref[0][b, 0, : max(n_valid, 1) * cfg.upp].numpy()).max() / 0.99
+            d = np.abs((a * 32768 / peak).astype(np.int16).astype(np.int32) - (e * 32768 / peak).astype(np.int16).astype(np.int32)).max()
+            assert d <= 1, (b, int(d))
