@@ -555,7 +555,7 @@ def main():
         inc["what"] = ("eager PyTorch (cuDNN/cuBLAS) on this GPU: oracle/rvc_oracle.py, the reference's op sequence, on CUDA "
                        "tensors, same step, 3 timed reps after 2 warm-ups; measurement context only, never on the product path")
         line["gpu_incumbent"] = inc
-    if not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline:        # the CPU leg is timed at N = 1 only (rank 0's host cores)
         threads = os.cpu_count() or 1
         # all host cores on the FULL step (one timed step after a short warm-up step), and one thread on a bounded sample
         chk = {}

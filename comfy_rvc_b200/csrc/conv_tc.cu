@@ -231,12 +231,8 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   };
   // weight row coordinate of tile (g, nt), tap, k-block in the [..][N][64] table
   auto w_row = [&](int g, int nt, int tap, int kb) { return (((g * n_nt + nt) * p.ntaps + tap) * nkb + kb) * p.N; };
-  // Generic (one tile per CTA) launches: every CTA of an N tile walks the same weight tiles, and the ~47 M-tile CTAs of a
-  // launch start together, so they all ask L2 for the same 8 KB at the same moment.  The K loop of M tile mt therefore
-  // starts at k-block mt % nkb (a rotation that depends on the row tile only: a batch item computes the same sums in the
-  // same order whatever else is in the batch).  RVCB200_KROT=0 restores the common order.
-  const bool krot = GENERIC && p.dbg_alt == 0 && !stat;
-  auto kb_rot = [&](int mt) { return krot ? mt % nkb : 0; };
+  // (tried in round 2: starting the K loop of M tile mt at k-block mt % nkb so that the ~47 CTAs of a launch do not ask L2 for
+  //  the same weight tile at the same moment -- no change in the flow / encoder classes, profiles/r2_ab_rings_injgemm.md)
 
   if (warp == 0) {
     // =========================== producer: TMA global -> swizzled smem ============================
@@ -257,9 +253,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         decode((long long)blockIdx.x + (long long)t * gridDim.x, mt, nt, g, b);
         const int row0 = mt * BM + p.g_off[g];
         int wrow = w_row(g, nt, 0, 0);
-        const int rot = kb_rot(mt);
-        for (int kbi = 0; kbi < nkb; ++kbi) {
-          const int kb = kbi + rot < nkb ? kbi + rot : kbi + rot - nkb;
+        for (int kb = 0; kb < nkb; ++kb) {
           if (slab) {
             mbar_wait(&a_empty[sa], pa);
             mbar_expect_tx(&a_full[sa], a_bytes);
@@ -305,11 +299,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
       uint32_t accum = 0;
-      int mt_m, nt_m, g_m, b_m;
-      decode((long long)blockIdx.x + (long long)t * gridDim.x, mt_m, nt_m, g_m, b_m);
-      const int rot = kb_rot(mt_m);
-      for (int kbi = 0; kbi < nkb; ++kbi) {
-        const int kb = kbi + rot < nkb ? kbi + rot : kbi + rot - nkb;
+      for (int kb = 0; kb < nkb; ++kb) {
         const int kleft = p.Cin - kb * KBLK;
         const int ksteps = kleft >= KBLK ? KBLK / 16 : (kleft + 15) / 16;     // skip the zero-padded K of narrow stages
         if (slab) {
@@ -835,8 +825,6 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     return cudaErrorInvalidValue;
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return cudaErrorNotSupported;
-  static const int krot_on = [] { const char* e = getenv("RVCB200_KROT"); return e ? atoi(e) : 1; }();
-  if (!krot_on) d.dbg_alt = 1;                 // A/B switch of the rotated K loop of generic launches (see the kernel)
   d.batch = B;
   int cols = 32;
   while (cols < 2 * d.N) cols <<= 1;          // two accumulator buffers
