@@ -36,6 +36,18 @@
 namespace rvc {
 namespace {
 
+// Phase timestamps of one launch (tools/trace_generic.py): when a trace buffer is set, a few threads of every CTA record
+// globaltimer at fixed points -- 16 slots per CTA.  Null (the default): one predictable branch per point.
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_mark(int slot) {
+  unsigned long long* t = g_trace;
+  if (t) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+    t[(size_t)blockIdx.x * 16 + slot] = now;
+  }
+}
+
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsTC = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
 constexpr int BM = 128;
@@ -165,6 +177,7 @@ __global__ void __launch_bounds__(kThreadsTC, 1)
 conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmY) {
   extern __shared__ unsigned char smem_raw[];
+  if (threadIdx.x == 0) trace_mark(0);                                     // CTA started
   // aligned with pointer arithmetic on the __shared__ array (not through an integer cast): the compiler keeps the
   // shared address space and emits LDS/STS instead of generic LD/ST for every access derived from it
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -218,6 +231,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_mark(1);                                     // barriers initialised, TMEM allocated
 
   // Tile order: phase g fastest, then the N tile, then the M tile.  The G phases (and N tiles) of one M tile run on
   // neighbouring CTAs at the same time, so the activation slab is read from HBM once (L2 hits for the rest) and the
@@ -246,6 +260,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           }
       }
       pdl_wait();                         // activations come from the previous kernel (the weights above do not)
+      trace_mark(2);                      // producer may load activations
       int sa = 0, sb = 0;                 // ring slots; phase bits flip on wrap (no div/mod in the loop)
       uint32_t pa = 1, pb = 1;            // producer waits on "empty" with inverted parity
       for (int t = 0; t < my_tiles; ++t) {
@@ -305,6 +320,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         if (slab) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
+          if (t == 0 && kb == 0 && lane == 0) trace_mark(3);               // first activation slab has landed
         }
         if (slab && stat) {
           // fast path: nothing to wait for inside the k-block -> every tap is issued back to back.  The loop
@@ -366,6 +382,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         }
       }
       if (elect_one()) tc_commit(&acc_full[buf]);
+      if (t == 0 && lane == 0) trace_mark(4);                               // first tile: every MMA issued
       __syncwarp();
     }
   } else {
@@ -419,6 +436,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       }
       mbar_wait(&acc_full[eg], (t >> 1) & 1);
       tc_fence_after();
+      if (t == 0 && warp == 2 && lane == 0) trace_mark(5);                  // first tile: accumulator complete
       if (GENERIC) {
 #pragma unroll 1
         for (int c0 = 0; c0 < p.N; c0 += 16) {
@@ -474,6 +492,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
     if (p.tma_out && lane == 0) bulk_wait_all();    // staged stores complete before the CTA's smem goes away
   }
   // ------------------------------------ teardown -------------------------------------------------
+  if (warp == 2 && lane == 0) trace_mark(6);                                // first epilogue warp done
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -816,6 +835,11 @@ inline unsigned grid_for(long long total, int threads) {
 }
 
 }  // namespace
+
+cudaError_t conv_tc_set_trace(void* buf) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+  return cudaMemcpyToSymbol(g_trace, &p, sizeof(p));
+}
 
 cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   TcConvDesc d = d_in;

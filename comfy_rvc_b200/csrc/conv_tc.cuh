@@ -12,6 +12,8 @@ constexpr int kPadF = 32;                                   // zero rows in fron
 inline int pv_pitch_rows(long long L) { return (int)(((L + 127) / 128) * 128 + 128); }   // Lp
 
 cudaError_t launch_conv_tc(const TcConvDesc& d, int B, cudaStream_t st);
+// debug: device buffer of 16 x grid uint64 that receives phase timestamps of the following launches (nullptr: off)
+cudaError_t conv_tc_set_trace(void* buf);
 // Compile-time specialised resblock convolution (rbconv_tc.cu); cudaErrorNotSupported if the shape is not covered.
 bool rbconv_tc_supported(const TcConvDesc& d);
 cudaError_t launch_rbconv_tc(const TcConvDesc& d, int B, cudaStream_t st);

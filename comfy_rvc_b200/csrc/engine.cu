@@ -1124,6 +1124,10 @@ int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream) {
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 
+int rvcb200_debug_trace_conv_tc(void* buf) {
+  return conv_tc_set_trace(buf) == cudaSuccess ? RVCB200_OK : RVCB200_ERR_CUDA;
+}
+
 int rvcb200_op_rbconv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream) {
   if (!d) return RVCB200_ERR_ARG;
   cudaError_t e = launch_rbconv_tc(*d, B, reinterpret_cast<cudaStream_t>(stream));

@@ -282,6 +282,11 @@ int rvcb200_op_absmax(const float* x, int64_t n, float* out, int32_t reset, void
  * NumPy >= 2 promotion). */
 int rvcb200_op_to_int16(const float* x, int64_t n, const float* absmax, int16_t* out, void* stream);
 
+/* Measurement aid: while `buf` (device, 16 x grid uint64) is set, every CTA of rvcb200_op_conv_tc launches records globaltimer
+ * at 8 fixed points (start, prologue done, producer released, first slab landed, MMAs issued, accumulator complete,
+ * epilogue done, exit); NULL switches it off.  tools/trace_generic.py. */
+int rvcb200_debug_trace_conv_tc(void* buf);
+
 /* ---- HuBERT / ContentVec front end (host orchestration in comfy_rvc_b200/hubert.py) ----
  * Replaces transformers.HubertModel as reached from /root/reference/lib/infer_pack/loaders.py:52-61.  Every contraction
  * of the model runs through rvcb200_op_conv_tc (generic epilogue, `gelu`) and rvcb200_op_attention_tc; these two entries

@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Where does a one-tile-per-CTA contraction spend its ~20 us?  Launches text-encoder / flow shaped contractions through
+`rvcb200_op_conv_tc` with the kernel's phase recorder on (`rvcb200_debug_trace_conv_tc`) and prints, per shape, the median
+over CTAs of the time between the recorded points (globaltimer, ns) plus the launch's CUDA-event time.
+
+    python tools/trace_generic.py [--T 6000] [--reps 20]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from comfy_rvc_b200 import _lib, weights  # noqa: E402
+
+POINTS = ["start", "prologue", "producer_go", "slab0_landed", "mmas_issued", "acc_complete", "epilogue_done"]
+SHAPES = [  # name, Cin, ntaps, Cout, gate, relu, res
+    ("flow.in   K=5x192 N=384 gate", 192, 5, 384, 1, 0, 0),
+    ("flow.res  K=192   N=192 +res", 192, 1, 192, 0, 0, 1),
+    ("enc.qkv   K=192   N=768", 192, 1, 768, 0, 0, 0),
+    ("enc.ffn1  K=3x192 N=768 relu", 192, 3, 768, 0, 1, 0),
+    ("enc.ffn2  K=3x768 N=192 +res", 768, 3, 192, 0, 0, 1),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--T", type=int, default=6000)
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    lib = _lib.load()
+    T = args.T
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for name, Cin, ntaps, Cout, gate, relu, res in SHAPES:
+        x16 = torch.randn(1, T, Cin, device=dev).half()
+        w = torch.randn(ntaps, Cin, Cout) / (Cin * ntaps) ** 0.5
+        w16 = weights.pack_tc(w, torch.float16, 64).to(dev)
+        bias = torch.randn(Cout, device=dev)
+        cout_eff = Cout // 2 if gate else Cout
+        y32 = torch.zeros(1, T, cout_eff, device=dev)
+        y16 = torch.zeros(1, T, cout_eff, device=dev, dtype=torch.float16)
+        r32 = torch.randn(1, T, cout_eff, device=dev)
+        d = _lib.TcConvDesc()
+        d.x16, d.L_in, d.padf = x16.data_ptr(), T, 32
+        d.w16, d.bias = w16.data_ptr(), bias.data_ptr()
+        d.Cin, d.ntaps, d.dil, d.G = Cin, ntaps, 1, 1
+        d.g_off[0] = -((ntaps - 1) // 2)
+        d.N, d.Cout_total, d.Lj, d.out_stride, d.Lp_out = 64, Cout, T, 1, ((T + 127) // 128) * 128 + 128
+        d.div, d.out_slope, d.alpha, d.pre_slope = 1.0, 1.0, 1.0, 1.0
+        d.generic, d.f32_cl, d.gate, d.relu = 1, 1, gate, relu
+        d.y32, d.ldy32, d.y16 = y32.data_ptr(), cout_eff, y16.data_ptr()
+        if res:
+            d.res32, d.ldr32, d.res_mode = r32.data_ptr(), cout_eff, 1
+        n_cta = min(((T + 127) // 128) * (Cout // 64), 148)
+        trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+        for _ in range(3):
+            assert lib.rvcb200_op_conv_tc(C.byref(d), 1, st) == 0
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.reps):
+            lib.rvcb200_op_conv_tc(C.byref(d), 1, st)
+        e1.record()
+        torch.cuda.synchronize()
+        us_plain = e0.elapsed_time(e1) / args.reps * 1e3
+        assert lib.rvcb200_debug_trace_conv_tc(C.c_void_p(trace.data_ptr())) == 0
+        segs = []
+        for _ in range(args.reps):
+            trace.zero_()
+            torch.cuda.synchronize()
+            lib.rvcb200_op_conv_tc(C.byref(d), 1, st)
+            torch.cuda.synchronize()
+            t = trace.cpu().numpy().reshape(148, 16)[:n_cta].astype(np.float64)
+            t0 = t[:, 0].min()
+            segs.append(np.concatenate([[np.median(t[:, 0] - t0)], np.median(np.diff(t[:, :7], axis=1), axis=0),
+                                        [t[:, 6].max() - t0]]))
+        lib.rvcb200_debug_trace_conv_tc(None)
+        m = np.median(np.array(segs), axis=0) / 1e3
+        line = {"shape": name, "T": T, "ctas": n_cta, "event_us_back_to_back": round(us_plain, 2),
+                "cta_start_skew_us": round(m[0], 2)}
+        for i in range(6):
+            line[f"{POINTS[i]}->{POINTS[i + 1]}_us"] = round(m[1 + i], 2)
+        line["first_start->last_epilogue_done_us"] = round(m[7], 2)
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
