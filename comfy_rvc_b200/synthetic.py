@@ -312,3 +312,87 @@ def make_speech(seconds: float, seed: int = 0, sr: int = 16000) -> torch.Tensor:
     env = 0.55 + 0.45 * torch.sin(2 * math.pi * 1.3 * t)
     x = x * env + 0.05 * torch.randn(n, generator=g, dtype=torch.float64) * (torch.sin(2 * math.pi * 0.4 * t) > 0.3)
     return x.float()[None, :]
+
+
+# ---- RMVPE --------------------------------------------------------------------------------------------
+def rmvpe_state_dict_shapes(n_blocks: int = 4, en_de_layers: int = 5, inter_layers: int = 4, en_out: int = 16,
+                            n_mels: int = 128, hidden: int = 256, n_class: int = 360) -> Dict[str, Tuple[int, ...]]:
+    """Key -> shape of `E2E(4, 1, (2, 2))` (/root/reference/lib/rmvpe.py:431-472, built at :578), in module order."""
+    s: Dict[str, Tuple[int, ...]] = {}
+
+    def bn(p, c):
+        s[p + "weight"], s[p + "bias"], s[p + "running_mean"], s[p + "running_var"] = (c,), (c,), (c,), (c,)
+        s[p + "num_batches_tracked"] = ()
+
+    def block(p, cin, cout):                                  # ConvBlockRes, rmvpe.py:232-267
+        s[p + "conv.0.weight"] = (cout, cin, 3, 3)
+        bn(p + "conv.1.", cout)
+        s[p + "conv.3.weight"] = (cout, cout, 3, 3)
+        bn(p + "conv.4.", cout)
+        if cin != cout:
+            s[p + "shortcut.weight"], s[p + "shortcut.bias"] = (cout, cin, 1, 1), (cout,)
+
+    bn("unet.encoder.bn.", 1)
+    cin, cout = 1, en_out
+    for i in range(en_de_layers):
+        for j in range(n_blocks):
+            block(f"unet.encoder.layers.{i}.conv.{j}.", cin if j == 0 else cout, cout)
+        cin, cout = cout, cout * 2
+    for i in range(inter_layers):
+        for j in range(n_blocks):
+            block(f"unet.intermediate.layers.{i}.conv.{j}.", cin if (i == 0 and j == 0) else cout, cout)
+    cin = cout
+    for i in range(en_de_layers):
+        cout = cin // 2
+        p = f"unet.decoder.layers.{i}."
+        s[p + "conv1.0.weight"] = (cin, cout, 3, 3)           # ConvTranspose2d: [C_in][C_out][3][3]
+        bn(p + "conv1.1.", cout)
+        for j in range(n_blocks):
+            block(p + f"conv2.{j}.", cout * 2 if j == 0 else cout, cout)
+        cin = cout
+    s["cnn.weight"], s["cnn.bias"] = (3, en_out, 3, 3), (3,)
+    for sfx in ("", "_reverse"):
+        s["fc.0.gru.weight_ih_l0" + sfx] = (3 * hidden, 3 * n_mels)
+        s["fc.0.gru.weight_hh_l0" + sfx] = (3 * hidden, hidden)
+        s["fc.0.gru.bias_ih_l0" + sfx] = (3 * hidden,)
+        s["fc.0.gru.bias_hh_l0" + sfx] = (3 * hidden,)
+    s["fc.1.weight"], s["fc.1.bias"] = (n_class, 2 * hidden), (n_class,)
+    return s
+
+
+def make_rmvpe_state_dict(seed: int = 0, **arch) -> Dict[str, torch.Tensor]:
+    """Seeded RMVPE weights in the reference's state_dict layout (the real `rmvpe.pt` is 181 MB and not available offline).
+    He-scaled convolutions, non-trivial BatchNorm statistics, and small BatchNorm gains so that the 56 residual blocks keep the
+    activations O(1)-O(10); the final Linear is scaled up so the salience is not flat."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    rn = lambda *shape: torch.randn(*shape, generator=g)
+    ru = lambda *shape: torch.rand(*shape, generator=g)
+    sd: Dict[str, torch.Tensor] = {}
+    for k, shape in rmvpe_state_dict_shapes(**arch).items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.tensor(100, dtype=torch.long)
+        elif k.endswith("running_mean"):
+            sd[k] = 0.1 * rn(*shape)
+        elif k.endswith("running_var"):
+            sd[k] = 0.5 + ru(*shape)
+        elif k.rsplit(".", 1)[0].endswith(("conv.1", "conv.4", "conv1.1")) or k.startswith("unet.encoder.bn."):
+            first_bn = k.startswith("unet.encoder.bn.")
+            if k.endswith("weight"):
+                sd[k] = (0.25 + 0.3 * ru(*shape)) if not first_bn else torch.full(shape, 0.35)
+            else:
+                sd[k] = 0.1 * rn(*shape) if not first_bn else torch.full(shape, 1.2)
+        elif "gru" in k:
+            sd[k] = (ru(*shape) * 2 - 1) / 16.0
+        elif k == "fc.1.weight":
+            sd[k] = rn(*shape) * 0.15
+        elif k == "fc.1.bias":
+            sd[k] = -2.0 + 0.1 * rn(*shape)
+        elif k == "cnn.weight":
+            sd[k] = rn(*shape) * 0.25 * math.sqrt(2.0 / _fan_in(shape))
+        elif k.endswith("bias"):
+            sd[k] = 0.1 * rn(*shape)
+        elif k.endswith("conv1.0.weight"):                                 # transposed conv: fan-in = C_in * 9 / 4 on average
+            sd[k] = rn(*shape) * math.sqrt(2.0 / (shape[0] * 9 / 4))
+        else:
+            sd[k] = rn(*shape) * math.sqrt(2.0 / _fan_in(shape))
+    return sd
