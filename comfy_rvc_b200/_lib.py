@@ -72,7 +72,8 @@ class TcConvDesc(C.Structure):
         ("tanh_out", C.c_void_p), ("acc_nostore", C.c_int32),
         ("inj_har", C.c_void_p), ("inj_w", C.c_void_p), ("inj_b", C.c_void_p),
         ("inj_k", C.c_int32), ("inj_s", C.c_int32), ("inj_pad", C.c_int32), ("inj_cn", C.c_int32), ("inj_Lhar", C.c_int64),
-        ("gelu", C.c_int32), ("reserved0", C.c_int32),
+        ("gelu", C.c_int32), ("tap_w", C.c_int32), ("dil2", C.c_int32), ("pad_period", C.c_int32), ("pad_valid", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -100,6 +101,15 @@ SYMBOLS = {
     "rvcb200_op_conv_f32": (C.c_int, [C.POINTER(ConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_conv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_debug_trace_conv_tc": (C.c_int, [C.c_void_p]),
+    "rvcb200_op_rmvpe_logmel": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "rvcb200_op_rmvpe_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "rvcb200_op_rmvpe_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "rvcb200_op_rmvpe_gru_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "rvcb200_op_rmvpe_gru": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "rvcb200_op_rmvpe_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                          C.c_void_p]),
+    "rvcb200_op_rmvpe_mel_to_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p]),
     "rvcb200_op_rbconv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_rbpair_tc": (C.c_int, [C.POINTER(TcConvDesc), C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_sine_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),

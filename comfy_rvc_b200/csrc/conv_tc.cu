@@ -48,6 +48,13 @@ __device__ __forceinline__ void trace_mark(int slot) {
   }
 }
 
+// Row offset of tap `tap`: 1-D kernels step by `dil`; 2-D kernels (tap_w taps per kernel row, RMVPE's 3 x 3 / 2 x 2 convolutions
+// over an image stored as rows of W + 1 pixels) step by `dil` inside a kernel row and by `dil2` between kernel rows.
+__host__ __device__ __forceinline__ int tap_row_off(const TcConvDesc& p, int tap) {
+  return p.tap_w > 0 ? (tap / p.tap_w) * p.dil2 + (tap % p.tap_w) * p.dil : tap * p.dil;
+}
+__host__ __device__ __forceinline__ int tap_halo(const TcConvDesc& p) { return p.ntaps > 0 ? tap_row_off(p, p.ntaps - 1) : 0; }
+
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsTC = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
 constexpr int BM = 128;
@@ -183,7 +190,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const int halo = (p.ntaps - 1) * p.dil;
+  const int halo = tap_halo(p);
   const bool slab = p.a_mode != 1;                             // a_mode 0/2/3: one box per k-block (+ base_offset probes)
   const int R = slab ? ((BM + halo + 7) & ~7) : BM;            // rows per activation box
   const int nkb = (p.Cin + KBLK - 1) / KBLK;
@@ -279,7 +286,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
             if (!slab) {
               mbar_wait(&a_empty[sa], pa);
               mbar_expect_tx(&a_full[sa], a_bytes);
-              tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0 + tap * p.dil, b, &a_full[sa]);
+              tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0 + tap_row_off(p, tap), b, &a_full[sa]);
               if (++sa == NA) { sa = 0; pa ^= 1; }
             }
             if (!stat) {
@@ -330,12 +337,17 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
             uint32_t a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
             uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4);
             const uint32_t a_step = (uint32_t)(p.dil * 128) >> 4, b_step = b_stride >> 4;
+            // 2-D kernels: after tap_w taps the offset jumps to the next kernel row (no division in the loop)
+            const uint32_t a_wrap = p.tap_w > 0 ? (uint32_t)((p.dil2 - (p.tap_w - 1) * p.dil) * 128) >> 4 : a_step;
+            const int tw = p.tap_w > 0 ? p.tap_w : 0x7fffffff;
+            int tx = 0;
             for (int tap = 0; tap < p.ntaps; ++tap) {
               for (int ks = 0; ks < ksteps; ++ks) {
                 tc_mma_f16_pred(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum, leader);
                 accum = 1;
               }
-              a_lo += a_step; b_lo += b_step;
+              if (++tx == tw) { tx = 0; a_lo += a_wrap; } else { a_lo += a_step; }
+              b_lo += b_step;
             }
             tc_commit_pred(&a_empty[sa], leader);
           }
@@ -347,7 +359,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         for (int tap = 0; tap < p.ntaps; ++tap) {
           uint32_t a_lo;
           if (slab) {
-            a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride + (uint32_t)(tap * p.dil) * 128u) >> 4);
+            a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride + (uint32_t)tap_row_off(p, tap) * 128u) >> 4);
           } else {
             mbar_wait(&a_full[sa], pa);
             tc_fence_after();
@@ -424,6 +436,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         const float* cond = p.cond ? p.cond + (size_t)b * p.cond_bstride : nullptr;
         for (int i = qd * 32 + lane; i < p.N; i += 128) sb[i] = __ldg(p.bias + nt * p.N + i) + (cond ? __ldg(cond + nt * p.N + i) : 0.f);
         valid = p.out_len ? (orow < p.out_len[b]) : true;
+        if (p.pad_period > 0) valid = valid && (int)(orow % p.pad_period) < p.pad_valid;   // image pad pixels stay zero
         have_pre = p.f32_cl && !p.gate && p.N <= 64 && ((p.res32 != nullptr) != (p.accum != 0)) && row_ok;
         if (have_pre) {
           const float* src = p.res32 ? p.res32 + ((size_t)b * Lout + orow) * p.ldr32 : p.y32 + ((size_t)b * Lout + orow) * p.ldy32;
@@ -504,7 +517,7 @@ constexpr size_t kStageBytes = 8 * 2 * 2048 + 1024;   // tma_out staging (+ alig
 constexpr size_t kGenericBiasBytes = 2 * 256 * 4 + 1024;   // generic epilogue: staged bias + conditioning per epilogue group
 
 size_t tc_smem_bytes(const TcConvDesc& d) {
-  const int halo = (d.ntaps - 1) * d.dil;
+  const int halo = tap_halo(d);
   const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
   const size_t a = (((size_t)R * 128) + 1023) & ~(size_t)1023;
   const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
@@ -844,7 +857,8 @@ cudaError_t conv_tc_set_trace(void* buf) {
 cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   TcConvDesc d = d_in;
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.Cin % 8 != 0 || d.Cout_total % d.N != 0 || d.G < 1 || d.G > 16 ||
-      d.Lj <= 0 || d.L_in <= 0 || (d.ntaps - 1) * d.dil > 127 || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
+      d.Lj <= 0 || d.L_in <= 0 || (d.a_mode != 1 && tap_halo(d) > 127) || tap_halo(d) < 0 || d.tap_w < 0 ||
+      (d.tap_w > 0 && (d.ntaps % d.tap_w != 0 || d.dil2 < (d.tap_w - 1) * d.dil)) || d.pad_period < 0 || (d.pad_period > 0 && !d.generic) || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
       d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)))
     return cudaErrorInvalidValue;
   EncodeTiledFn enc = encode_tiled();
@@ -854,7 +868,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   while (cols < 2 * d.N) cols <<= 1;          // two accumulator buffers
   d.tmem_cols = cols;
   const int nkb = (d.Cin + KBLK - 1) / KBLK;
-  const int halo = (d.ntaps - 1) * d.dil;
+  const int halo = tap_halo(d);
   const int n_nt = d.Cout_total / d.N;
   const long long tiles = (long long)((d.Lj + BM - 1) / BM) * n_nt * d.G * B;
   {

@@ -1206,4 +1206,46 @@ int rvcb200_op_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int3
   return e == cudaSuccess ? RVCB200_OK : (e == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA);
 }
 
+#define RVC_RET(e) return (e) == cudaSuccess ? RVCB200_OK : ((e) == cudaErrorInvalidValue ? RVCB200_ERR_ARG : RVCB200_ERR_CUDA)
+
+int rvcb200_op_rmvpe_logmel(const float* audio, int64_t n, const float* window, const float* twiddle, const float* mel_basis,
+                            const int32_t* mel_range, float bn_scale, float bn_shift, float* mel_out, void* img16, int32_t n_frames,
+                            int32_t frames_out, void* stream) {
+  cudaError_t e = launch_rmvpe_logmel(audio, n, window, twiddle, mel_basis, mel_range, bn_scale, bn_shift, mel_out, img16, n_frames,
+                                      frames_out, reinterpret_cast<cudaStream_t>(stream));
+  RVC_RET(e);
+}
+
+int rvcb200_op_rmvpe_pool(const float* x32, int32_t ldx, void* y16, int32_t H2, int32_t W2, int32_t C, void* stream) {
+  cudaError_t e = launch_rmvpe_pool(x32, ldx, y16, H2, W2, C, reinterpret_cast<cudaStream_t>(stream));
+  RVC_RET(e);
+}
+
+int rvcb200_op_rmvpe_shuffle(const void* g16, void* out16, int32_t H, int32_t W, int32_t Co, int32_t ld, void* stream) {
+  cudaError_t e = launch_rmvpe_shuffle(g16, out16, H, W, Co, ld, reinterpret_cast<cudaStream_t>(stream));
+  RVC_RET(e);
+}
+
+int rvcb200_op_rmvpe_gru_pack(const float* y32, int32_t ldc, void* x16, int64_t T, int32_t W, void* stream) {
+  cudaError_t e = launch_rmvpe_gru_pack(y32, ldc, x16, T, W, reinterpret_cast<cudaStream_t>(stream));
+  RVC_RET(e);
+}
+
+int rvcb200_op_rmvpe_gru(const float* gi, const float* w_hh, const float* b_hh, void* out16, float* out32, int32_t T, void* stream) {
+  cudaError_t e = launch_rmvpe_gru(gi, w_hh, b_hh, out16, out32, T, reinterpret_cast<cudaStream_t>(stream));
+  RVC_RET(e);
+}
+
+int rvcb200_op_rmvpe_decode(const float* in, int32_t ld, int32_t from_hidden, float* hidden, double* f0, double* cents, int32_t T,
+                            float thred, void* stream) {
+  cudaError_t e = launch_rmvpe_decode(in, ld, from_hidden, hidden, f0, cents, T, thred, reinterpret_cast<cudaStream_t>(stream));
+  RVC_RET(e);
+}
+
+int rvcb200_op_rmvpe_mel_to_img(const float* mel, void* img16, int32_t n_frames, int32_t frames_out, float bn_scale, float bn_shift,
+                                void* stream) {
+  cudaError_t e = launch_rmvpe_mel_to_img(mel, img16, n_frames, frames_out, bn_scale, bn_shift, reinterpret_cast<cudaStream_t>(stream));
+  RVC_RET(e);
+}
+
 }  // extern "C"

@@ -56,6 +56,7 @@ class PipelineConfig:
     x_max: int = 64
     is_half: bool = True
     device: str = "cuda:0"
+    rmvpe_model_path: Optional[str] = None     # BASE_MODELS_DIR/rmvpe.pt in the reference (pitch_extraction.py:193)
 
     @classmethod
     def for_device(cls, is_half: bool = True, gpu_mem_gb: Optional[int] = None, device: str = "cuda:0") -> "PipelineConfig":
@@ -192,9 +193,28 @@ class FeatureExtractor:
         self.t_max = self.sr * self.x_max
         self.device = config.device
         self.onnx = onnx
-        # the reference registers pm/harvest/dio/rmvpe/crepe here; those estimators are upstream of this path —
-        # register any callable `fn(x=, f0_up_key=, f0_min=, f0_max=, ...) -> f0[frames]`
-        self.f0_method_dict = {}
+        # the reference registers pm/harvest/dio/rmvpe/crepe here (pitch_extraction.py:28-45).  RMVPE -- the nodes' default
+        # (custom_nodes/rvc_nodes.py:49) -- runs on the B200 kernels (comfy_rvc_b200/rmvpe.py); the CPU estimators (parselmouth,
+        # pyworld, torchcrepe) are upstream of this path: register any callable `fn(x=, f0_up_key=, f0_min=, f0_max=, ...) -> f0[frames]`
+        self.f0_method_dict = {"rmvpe": self.get_rmvpe, "rmvpe+": self.get_pitch_dependant_rmvpe}
+        self.rmvpe_model_path = getattr(config, "rmvpe_model_path", None)
+
+    def _rmvpe(self):
+        """pitch_extraction.py:192-193: built on first use and kept; attach a ready model as `self.model_rmvpe` to share it."""
+        if not hasattr(self, "model_rmvpe"):
+            if not self.rmvpe_model_path:
+                raise RuntimeError("f0_method 'rmvpe' needs `model_rmvpe` (a comfy_rvc_b200.RMVPE) or `config.rmvpe_model_path` (rmvpe.pt)")
+            from .rmvpe import RMVPE
+            self.model_rmvpe = RMVPE(self.rmvpe_model_path, is_half=self.is_half, device=self.device, onnx=self.onnx)
+        return self.model_rmvpe
+
+    def get_rmvpe(self, x, *args, **kwargs):
+        """pitch_extraction.py:191-195."""
+        return self._rmvpe().infer_from_audio(x, thred=0.03)
+
+    def get_pitch_dependant_rmvpe(self, x, f0_min=0, f0_max=40000, *args, **kwargs):
+        """pitch_extraction.py:197-201."""
+        return self._rmvpe().infer_from_audio_with_pitch(x, thred=0.03, f0_min=f0_min, f0_max=f0_max)
 
     def load_index(self, file_index):
         """pitch_extraction.py:49-73: a preloaded `(index, big_npy)` tuple, "" for none, or a faiss file path."""

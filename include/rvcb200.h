@@ -228,6 +228,11 @@ typedef struct rvcb200_tc_conv_desc {
   int32_t inj_k, inj_s, inj_pad, inj_cn; int64_t inj_Lhar;
   int32_t gelu;                /* generic epilogue: exact (erf) GELU right after bias / cond / gather / alpha, before the
                                 * residual (the HuBERT front end: conv stack, positional conv, feed-forward) */
+  /* 2-D kernels over an image stored row-major as lines of (W + 1) pixels, the last one a zero pad pixel (RMVPE's DeepUnet,
+   * /root/reference/lib/rmvpe.py:232-267): tap t reads row offset (t / tap_w) * dil2 + (t % tap_w) * dil (tap_w = 0: 1-D,
+   * t * dil).  Rows before 0 / past L_in are zero-filled by the tensor map, the pad pixel supplies the left / right border.
+   * pad_period > 0 (generic epilogue): with mask_post, output rows whose (row % pad_period) >= pad_valid are written as 0. */
+  int32_t tap_w, dil2, pad_period, pad_valid;
   int32_t reserved0;
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
@@ -308,6 +313,44 @@ int rvcb200_op_layernorm16(const float* x, const float* gamma, const float* beta
  * is empty); the caller takes the first minimum over blocks in ascending order.  audio_pad: device float64. */
 int rvcb200_op_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int32_t window, double* best_v, int64_t* best_j,
                            int32_t n_blocks, void* stream);
+
+/* ---- RMVPE f0 estimator (host orchestration in comfy_rvc_b200/rmvpe.py) ----
+ * Replaces the torch modules of /root/reference/lib/rmvpe.py as reached from pitch_extraction.py:191-201.  The DeepUnet's
+ * convolutions, the GRU input projection and the output Linear run through rvcb200_op_conv_tc (2-D taps); these entries are
+ * what is left.  Images are fp16 channels-last, stored as lines of W + 1 pixels whose last pixel is zero. */
+
+/* `MelSpectrogram.forward` (rmvpe.py:489-556; n_fft 1024, hop 160, 128 HTK mel filters 30-8000 Hz, log(clamp 1e-5)) of
+ * audio[n] (16 kHz, n > 512), n_frames = n / 160 + 1.  window[1024]: periodic Hann; twiddle[512][2]: (cos, -sin)(2 pi i / 1024);
+ * mel_basis[128][513]; mel_range[128][2]: first / one-past-last non-zero bin of each filter.  Outputs (either may be NULL):
+ * mel_out fp32 [128][n_frames]; img16 fp16 [frames_out][129][8], channel 0 = mel * bn_scale + bn_shift (`Encoder.bn`,
+ * rmvpe.py:299), frames n_frames.. = the reflect padding of `mel2hidden` (rmvpe.py:594-595); img16 must be zero-initialised. */
+int rvcb200_op_rmvpe_logmel(const float* audio, int64_t n, const float* window, const float* twiddle, const float* mel_basis,
+                            const int32_t* mel_range, float bn_scale, float bn_shift, float* mel_out, void* img16, int32_t n_frames,
+                            int32_t frames_out, void* stream);
+
+/* AvgPool2d((2, 2)) (rmvpe.py:318): x32 fp32 [2 H2][2 W2 + 1][ldx] -> y16 fp16 [H2][W2 + 1][C] (pad pixel zero). */
+int rvcb200_op_rmvpe_pool(const float* x32, int32_t ldx, void* y16, int32_t H2, int32_t W2, int32_t C, void* stream);
+
+/* Scatter behind ConvTranspose2d(3 x 3, stride 2, padding 1, output_padding 1) (rmvpe.py:355-366) computed as a 2 x 2-tap GEMM
+ * with (phase, channel) columns: g16 fp16 [H][W + 1][4][Co] -> out16 fp16 [2 H][2 W + 1][ld], channels [0, Co). */
+int rvcb200_op_rmvpe_shuffle(const void* g16, void* out16, int32_t H, int32_t W, int32_t Co, int32_t ld, void* stream);
+
+/* `x.transpose(1, 2).flatten(-2)` (rmvpe.py:468): y32 fp32 [T][W + 1][ldc] (channels 0..2) -> x16 fp16 [T][3 W], column c W + w. */
+int rvcb200_op_rmvpe_gru_pack(const float* y32, int32_t ldc, void* x16, int64_t T, int32_t W, void* stream);
+
+/* Recurrence of nn.GRU(384, 256, bidirectional=True) (rmvpe.py:217-229): gi fp32 [T][2][3][256] = W_ih x + b_ih (gates r|z|n),
+ * w_hh fp32 [2][768][256], b_hh fp32 [2][768] -> out16 fp16 [T][512] (forward | reverse), out32 the same in fp32 or NULL. */
+int rvcb200_op_rmvpe_gru(const float* gi, const float* w_hh, const float* b_hh, void* out16, float* out32, int32_t T, void* stream);
+
+/* Sigmoid (from_hidden = 0: `in` = logits [T][ld], `hidden` [T][360] receives the salience, may be NULL) and
+ * `to_local_average_cents` + `decode` (rmvpe.py:610-615, 658-684) in float64 -> f0 [T] (Hz, 0 = unvoiced) and / or
+ * cents [T] (the value `to_local_average_cents` returns); at least one of the two non-NULL. */
+int rvcb200_op_rmvpe_decode(const float* in, int32_t ld, int32_t from_hidden, float* hidden, double* f0, double* cents, int32_t T,
+                            float thred, void* stream);
+
+/* `mel2hidden` called with a caller-supplied log-mel: mel fp32 [128][n_frames] -> the img16 of rvcb200_op_rmvpe_logmel. */
+int rvcb200_op_rmvpe_mel_to_img(const float* mel, void* img16, int32_t n_frames, int32_t frames_out, float bn_scale, float bn_shift,
+                                void* stream);
 
 /* ---- host (CPU) side of the song-level driver (csrc/host_plan.cu) ---- */
 

@@ -94,10 +94,12 @@ def _conv_block_res(x, w, p):
 
 @torch.no_grad()
 def e2e_forward(sd: Dict[str, torch.Tensor], mel: torch.Tensor, n_blocks: int = 4, en_de_layers: int = 5, inter_layers: int = 4,
-                taps=None) -> torch.Tensor:
-    """rmvpe.py:465-472: mel [B, 128, T] (T a multiple of 32) -> salience [B, T, 360]."""
-    w = {k: v.float() for k, v in sd.items()}
-    x = mel.float().transpose(-1, -2).unsqueeze(1)                                   # [B, 1, T, 128]
+                taps=None, gru=None, dtype=torch.float32) -> torch.Tensor:
+    """rmvpe.py:465-472: mel [B, 128, T] (T a multiple of 32) -> salience [B, T, 360].
+    `gru` (optional): a callable replacing the explicit recurrence below, e.g. a `torch.nn.GRU` holding the same weights -- used by
+    tools/bench_rmvpe.py to time the library (cuDNN) path the reference takes on a GPU; `dtype` float16 = the reference's is_half."""
+    w = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    x = mel.to(dtype).transpose(-1, -2).unsqueeze(1)                                 # [B, 1, T, 128]
     x = _bn(x, w, "unet.encoder.bn.")                                                # :299
     skips = []
     for i in range(en_de_layers):                                                    # :300-303, :320-327
@@ -125,7 +127,7 @@ def e2e_forward(sd: Dict[str, torch.Tensor], mel: torch.Tensor, n_blocks: int = 
     x = x.transpose(1, 2).flatten(-2)                                                # [B, T, 3 * 128]
     if taps is not None:
         taps["gru_in"] = x
-    x = bigru(x, w, "fc.0.gru.")
+    x = gru(x) if gru is not None else bigru(x, w, "fc.0.gru.")
     if taps is not None:
         taps["gru_out"] = x
     return torch.sigmoid(F.linear(x, w["fc.1.weight"], w["fc.1.bias"]))              # :451-456 (Dropout is identity in eval)
@@ -141,8 +143,8 @@ def bigru(x: torch.Tensor, w: Dict[str, torch.Tensor], p: str) -> torch.Tensor:
         b_ih, b_hh = w[p + "bias_ih_l0" + sfx], w[p + "bias_hh_l0" + sfx]
         H = w_hh.shape[1]
         gi = F.linear(x, w_ih, b_ih)
-        h = torch.zeros(B, H)
-        out = torch.empty(B, T, H)
+        h = torch.zeros(B, H, dtype=x.dtype, device=x.device)
+        out = torch.empty(B, T, H, dtype=x.dtype, device=x.device)
         for t in order:
             gh = F.linear(h, w_hh, b_hh)
             r = torch.sigmoid(gi[:, t, :H] + gh[:, :H])
