@@ -9,7 +9,7 @@
 //   * AvgPool2d(2, 2) (rmvpe.py:318) fp32 image -> fp16 operand of the next level;
 //   * the pixel shuffle behind a transposed convolution run as a GEMM over (phase, channel) columns (rmvpe.py:355-366);
 //   * the bidirectional GRU recurrence (rmvpe.py:217-229): one 8-CTA cluster per direction, W_hh resident in registers,
-//     the hidden state exchanged through distributed shared memory, one cluster barrier per time step;
+//     the hidden state exchanged through distributed shared memory (st.async + mbarrier complete_tx);
 //   * sigmoid + `to_local_average_cents` + `decode` (rmvpe.py:610-615, 658-684) in float64 like the reference's numpy.
 #include <cuda_fp16.h>
 
@@ -155,19 +155,34 @@ __global__ void rmvpe_gru_pack_kernel(const float* __restrict__ y, int ldc, __ha
 // CTA `rank` owns hidden units [32 rank, 32 rank + 32): thread (unit, slice s of 8) keeps the 3 x 32 weights of its unit's rows
 // for columns {4 (8 i + s) .. + 3, i < 8} in registers.  Per step: 96 FMAs against the hidden state in shared memory, an 8-lane
 // butterfly, the gate arithmetic (every lane of the 8 redundantly), then lane s stores the unit's new value into CTA s's copy of
-// the state (st.shared::cluster) and one cluster barrier (release / acquire) publishes it; the state is double-buffered so one
-// barrier per step is enough.  Step time ~ barrier (~380 clk) + DSMEM store (~200 clk) + matvec: ~0.4 us, both directions
-// concurrently.
+// the state through distributed shared memory (see the exchange note below); both directions run concurrently.
 constexpr int kGruH = 256, kGruCl = 8, kGruUnits = kGruH / kGruCl;
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "GRU_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra GRU_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// sigmoid / tanh from the hardware exponential (ex2.approx, 2 ulp): ~1e-7 absolute on the gates
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
+// Exchange of the hidden state (second version; the first used one barrier.cluster per step and took 1.02 us per step,
+// profiles/r2_rmvpe_bench_v1.jsonl): every new value travels as ONE `st.async` to each CTA of the cluster that both writes the
+// float into that CTA's state buffer and counts 4 bytes on that CTA's mbarrier (complete_tx), so data and "it is there" are the
+// same message; a CTA waits on its own mbarrier for the 1024 bytes of a step.  The state is double-buffered and the data
+// dependency orders the reuse of a buffer: a CTA can only send step it + 1 values after it has received every step it value,
+// which every sender emitted after its own reads of the buffer those values now overwrite.
 __global__ void __cluster_dims__(kGruCl, 1, 1) __launch_bounds__(256, 1)
 rmvpe_gru_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, const float* __restrict__ b_hh,
                  __half* __restrict__ out16, float* __restrict__ out32, int T) {
   __shared__ __align__(16) float hbuf[2][kGruH];
+  __shared__ __align__(8) unsigned long long bars[2];
   const int dir = blockIdx.x / kGruCl;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -181,48 +196,75 @@ rmvpe_gru_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh, c
   const float bh_r = b_hh[dir * 3 * kGruH + u], bh_z = b_hh[dir * 3 * kGruH + kGruH + u], bh_n = b_hh[dir * 3 * kGruH + 2 * kGruH + u];
   hbuf[0][tid] = 0.f;
   hbuf[1][tid] = 0.f;
-  uint32_t remote;                                                    // hbuf of cluster CTA `s`
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_addr(&hbuf[0][0])), "r"((uint32_t)s));
+  const uint32_t bar0 = smem_addr(&bars[0]);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // buffer 1 receives the results of step 0, buffer 0 those of step 1
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8), "r"(kGruH * 4) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"(kGruH * 4) : "memory");
+  }
+  uint32_t remote_h, remote_bar;                                      // state buffer and barriers of cluster CTA `s`
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_h) : "r"(smem_addr(&hbuf[0][0])), "r"((uint32_t)s));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_bar) : "r"(bar0), "r"((uint32_t)s));
   __syncthreads();
-  cluster_sync_all();                                                 // every CTA of the cluster runs and has zeroed its state
+  cluster_sync_all();                                                 // every CTA runs, has zeroed its state and armed its barriers
   const float* gp = gi + dir * 3 * kGruH + u;
   const size_t ldg = 2 * 3 * kGruH;
-  int t = dir ? T - 1 : 0;
   const int dt = dir ? -1 : 1;
+  int t = dir ? T - 1 : 0;
+  // input gates of this step and the next one (two steps of load latency hidden)
   float gr = gp[(size_t)t * ldg], gz = gp[(size_t)t * ldg + kGruH], gn = gp[(size_t)t * ldg + 2 * kGruH];
+  float gr1 = 0.f, gz1 = 0.f, gn1 = 0.f;
+  if (T > 1) { const size_t o = (size_t)(t + dt) * ldg; gr1 = gp[o]; gz1 = gp[o + kGruH]; gn1 = gp[o + 2 * kGruH]; }
 #pragma unroll 1
   for (int it = 0; it < T; ++it) {
-    const float* hcur = hbuf[it & 1];
+    const int cur = it & 1;
+    if (it > 0) {
+      // step it - 1's 256 values have landed in hbuf[cur]: use number (it - 1) / 2 of bars[cur] -> parity ((it - 1) >> 1) & 1
+      mbar_wait_parity(bar0 + 8 * cur, (uint32_t)(((it - 1) >> 1) & 1));
+      if (tid == 0 && it + 2 < T)                                     // arm it for its next use (the results of step it + 1)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * cur), "r"(kGruH * 4) : "memory");
+    }
+    const float* hcur = hbuf[cur];
     const float4* hc = reinterpret_cast<const float4*>(hcur);
-    float ar = 0.f, az = 0.f, an = 0.f;
+    float ar = 0.f, az = 0.f, an = 0.f, br = 0.f, bz = 0.f, bn = 0.f;  // two chains per gate
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 h4 = hc[8 * i + s];
+    for (int i = 0; i < 8; i += 2) {
+      const float4 h4 = hc[8 * i + s], k4 = hc[8 * (i + 1) + s];
       ar = fmaf(w[0][i].x, h4.x, ar); ar = fmaf(w[0][i].y, h4.y, ar); ar = fmaf(w[0][i].z, h4.z, ar); ar = fmaf(w[0][i].w, h4.w, ar);
       az = fmaf(w[1][i].x, h4.x, az); az = fmaf(w[1][i].y, h4.y, az); az = fmaf(w[1][i].z, h4.z, az); az = fmaf(w[1][i].w, h4.w, az);
       an = fmaf(w[2][i].x, h4.x, an); an = fmaf(w[2][i].y, h4.y, an); an = fmaf(w[2][i].z, h4.z, an); an = fmaf(w[2][i].w, h4.w, an);
+      br = fmaf(w[0][i + 1].x, k4.x, br); br = fmaf(w[0][i + 1].y, k4.y, br); br = fmaf(w[0][i + 1].z, k4.z, br); br = fmaf(w[0][i + 1].w, k4.w, br);
+      bz = fmaf(w[1][i + 1].x, k4.x, bz); bz = fmaf(w[1][i + 1].y, k4.y, bz); bz = fmaf(w[1][i + 1].z, k4.z, bz); bz = fmaf(w[1][i + 1].w, k4.w, bz);
+      bn = fmaf(w[2][i + 1].x, k4.x, bn); bn = fmaf(w[2][i + 1].y, k4.y, bn); bn = fmaf(w[2][i + 1].z, k4.z, bn); bn = fmaf(w[2][i + 1].w, k4.w, bn);
     }
+    ar += br; az += bz; an += bn;
+    const float hp = hcur[u];
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
       ar += __shfl_xor_sync(0xffffffffu, ar, o);
       az += __shfl_xor_sync(0xffffffffu, az, o);
       an += __shfl_xor_sync(0xffffffffu, an, o);
     }
-    const float hp = hcur[u];
-    const float r = 1.f / (1.f + expf(-(gr + (ar + bh_r))));
-    const float z = 1.f / (1.f + expf(-(gz + (az + bh_z))));
-    const float nn = tanhf(gn + r * (an + bh_n));
+    const float r = fast_sigmoid(gr + (ar + bh_r));
+    const float z = fast_sigmoid(gz + (az + bh_z));
+    const float nn = fast_tanh(gn + r * (an + bh_n));
     const float hn = (hp - nn) * z + nn;                              // ATen's gru cell: (h - n) * z + n
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + (uint32_t)((((it + 1) & 1) * kGruH + u) * 4)), "f"(hn) : "memory");
+    if (it + 1 < T) {                                                 // nobody reads the last step's state: no traffic after exit
+      const uint32_t dst = remote_h + (uint32_t)(((cur ^ 1) * kGruH + u) * 4);
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst), "r"(__float_as_uint(hn)),
+                   "r"(remote_bar + 8 * (cur ^ 1))
+                   : "memory");
+    }
     if (s == 0) {
       out16[(size_t)t * (2 * kGruH) + dir * kGruH + u] = __float2half_rn(hn);
       if (out32) out32[(size_t)t * (2 * kGruH) + dir * kGruH + u] = hn;
     }
     t += dt;
-    if (it + 1 < T) {                                                 // next step's input gates: in flight across the barrier
-      gr = gp[(size_t)t * ldg]; gz = gp[(size_t)t * ldg + kGruH]; gn = gp[(size_t)t * ldg + 2 * kGruH];
-    }
-    cluster_sync_all();
+    gr = gr1; gz = gz1; gn = gn1;
+    if (it + 2 < T) { const size_t o = (size_t)(t + dt) * ldg; gr1 = gp[o]; gz1 = gp[o + kGruH]; gn1 = gp[o + 2 * kGruH]; }
   }
 }
 
@@ -254,21 +296,24 @@ rmvpe_decode_kernel(const float* __restrict__ in, int ld, int from_hidden, float
   }
   __syncwarp();
   if (lane == 0) {
-    // rmvpe.py:658-684: 9 bins around the arg-max of the zero-padded salience, products and sums in float64; numpy sums 9
+    // rmvpe.py:658-684: 9 bins around the arg-max of the zero-padded salience.  The products (float32 salience x float64 cents)
+    // and their sum are float64, the weight sum is a FLOAT32 sum of the float32 salience (np.sum keeps the dtype); numpy sums 9
     // contiguous values as ((a0+a1)+(a2+a3))+((a4+a5)+(a6+a7)) + a8
-    double p[9], q[9];
+    double p[9];
+    float q[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const int c = bi - 4 + k;
       const bool in_range = c >= 0 && c < kClasses;
-      const double sv = in_range ? (double)sal[warp][c] : 0.0;
+      const float sv = in_range ? sal[warp][c] : 0.f;
       const double cents = in_range ? 20.0 * (double)c + 1997.3794084376191 : 0.0;
-      p[k] = sv * cents;
+      p[k] = (double)sv * cents;
       q[k] = sv;
     }
     const double ps = (((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]))) + p[8];
-    const double ws = (((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]))) + q[8];
-    double cents_pred = ps / ws;
+    const float ws = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3])),
+                                         __fadd_rn(__fadd_rn(q[4], q[5]), __fadd_rn(q[6], q[7]))), q[8]);
+    double cents_pred = ps / (double)ws;
     if (best <= thred) cents_pred = 0.0;
     if (cents_out) cents_out[t] = cents_pred;
     double f = 10.0 * exp2(cents_pred / 1200.0);                      // rmvpe.py:612

@@ -25,21 +25,36 @@ SHAPES = [  # name, Cin, ntaps, Cout, gate, relu, res
     ("enc.ffn1  K=3x192 N=768 relu", 192, 3, 768, 0, 1, 0),
     ("enc.ffn2  K=3x768 N=192 +res", 768, 3, 192, 0, 0, 1),
 ]
+# RMVPE DeepUnet shapes (--rmvpe): name, image lines per 100 frames, W, Cin, Cout, N tile (rows = lines * (W + 1); 3 x 3 taps)
+RMVPE_SHAPES = [
+    ("unet L5 512->512 3x3 W=4", 100 / 32, 4, 512, 512, 64),
+    ("unet L4 256->256 3x3 W=8", 100 / 16, 8, 256, 256, 64),
+    ("unet L3 128->128 3x3 W=16", 100 / 8, 16, 128, 128, 64),
+    ("unet L2 64->64 3x3 W=32", 100 / 4, 32, 64, 64, 64),
+]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--T", type=int, default=6000)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--rmvpe", action="store_true", help="the DeepUnet's 3 x 3 image convolutions instead (T = frames)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib = _lib.load()
     T = args.T
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for name, Cin, ntaps, Cout, gate, relu, res in SHAPES:
+    shapes = SHAPES
+    if args.rmvpe:
+        shapes = [(name, Cin, 9, Cout, 0, 0, 1, W, int(round(T / 100 * lines)) * (W + 1), nt)
+                  for name, lines, W, Cin, Cout, nt in RMVPE_SHAPES]
+    frames = T
+    for shape in shapes:
+        name, Cin, ntaps, Cout, gate, relu, res = shape[:7]
+        Wimg, T, ntile = (shape[7], shape[8], shape[9]) if args.rmvpe else (0, frames, 64)
         x16 = torch.randn(1, T, Cin, device=dev).half()
         w = torch.randn(ntaps, Cin, Cout) / (Cin * ntaps) ** 0.5
-        w16 = weights.pack_tc(w, torch.float16, 64).to(dev)
+        w16 = weights.pack_tc(w, torch.float16, ntile).to(dev)
         bias = torch.randn(Cout, device=dev)
         cout_eff = Cout // 2 if gate else Cout
         y32 = torch.zeros(1, T, cout_eff, device=dev)
@@ -50,13 +65,16 @@ def main():
         d.w16, d.bias = w16.data_ptr(), bias.data_ptr()
         d.Cin, d.ntaps, d.dil, d.G = Cin, ntaps, 1, 1
         d.g_off[0] = -((ntaps - 1) // 2)
-        d.N, d.Cout_total, d.Lj, d.out_stride, d.Lp_out = 64, Cout, T, 1, ((T + 127) // 128) * 128 + 128
+        d.N, d.Cout_total, d.Lj, d.out_stride, d.Lp_out = ntile, Cout, T, 1, ((T + 127) // 128) * 128 + 128
+        if args.rmvpe:
+            d.tap_w, d.dil2, d.g_off[0] = 3, Wimg + 1, -(Wimg + 2)
+            d.pad_period, d.pad_valid, d.mask_post, d.pre_slope = Wimg + 1, Wimg, 1, 0.0
         d.div, d.out_slope, d.alpha, d.pre_slope = 1.0, 1.0, 1.0, 1.0
         d.generic, d.f32_cl, d.gate, d.relu = 1, 1, gate, relu
         d.y32, d.ldy32, d.y16 = y32.data_ptr(), cout_eff, y16.data_ptr()
         if res:
             d.res32, d.ldr32, d.res_mode = r32.data_ptr(), cout_eff, 1
-        n_cta = min(((T + 127) // 128) * (Cout // 64), 148)
+        n_cta = min(((T + 127) // 128) * (Cout // ntile), 148)
         trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
         for _ in range(3):
             assert lib.rvcb200_op_conv_tc(C.byref(d), 1, st) == 0
