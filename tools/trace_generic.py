@@ -39,6 +39,8 @@ def main():
     ap.add_argument("--T", type=int, default=6000)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--rmvpe", action="store_true", help="the DeepUnet's 3 x 3 image convolutions instead (T = frames)")
+    ap.add_argument("--micro", action="store_true", help="who limits the weight stream: 1 CTA alone, 8 CTAs on the same weights, "
+                    "8 CTAs on the same rows, 64 CTAs (K = 9 x 512, N tile 64)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     lib = _lib.load()
@@ -48,6 +50,12 @@ def main():
     if args.rmvpe:
         shapes = [(name, Cin, 9, Cout, 0, 0, 1, W, int(round(T / 100 * lines)) * (W + 1), nt)
                   for name, lines, W, Cin, Cout, nt in RMVPE_SHAPES]
+    if args.micro:      # name, Cin, taps, Cout, gate, relu, res, W, rows, N tile
+        args.rmvpe = True
+        shapes = [("1 CTA (1 m x 1 n)", 512, 9, 64, 0, 0, 1, 4, 125, 64), ("8 CTAs, same weights (8 m x 1 n)", 512, 9, 64, 0, 0, 1, 4, 1000, 64),
+                  ("8 CTAs, same rows (1 m x 8 n)", 512, 9, 512, 0, 0, 1, 4, 125, 64), ("64 CTAs (8 m x 8 n)", 512, 9, 512, 0, 0, 1, 4, 1000, 64),
+                  ("1 CTA, N tile 128", 512, 9, 128, 0, 0, 1, 4, 125, 128), ("1 CTA, N tile 256", 512, 9, 256, 0, 0, 1, 4, 125, 256),
+                  ("1 CTA, 1 tap x 4608 ch (no slab reuse)", 4608, 1, 64, 0, 0, 1, 4, 125, 64)]
     frames = T
     for shape in shapes:
         name, Cin, ntaps, Cout, gate, relu, res = shape[:7]
@@ -66,7 +74,7 @@ def main():
         d.Cin, d.ntaps, d.dil, d.G = Cin, ntaps, 1, 1
         d.g_off[0] = -((ntaps - 1) // 2)
         d.N, d.Cout_total, d.Lj, d.out_stride, d.Lp_out = ntile, Cout, T, 1, ((T + 127) // 128) * 128 + 128
-        if args.rmvpe:
+        if args.rmvpe and ntaps == 9:
             d.tap_w, d.dil2, d.g_off[0] = 3, Wimg + 1, -(Wimg + 2)
             d.pad_period, d.pad_valid, d.mask_post, d.pre_slope = Wimg + 1, Wimg, 1, 0.0
         d.div, d.out_slope, d.alpha, d.pre_slope = 1.0, 1.0, 1.0, 1.0
@@ -75,7 +83,7 @@ def main():
         if res:
             d.res32, d.ldr32, d.res_mode = r32.data_ptr(), cout_eff, 1
         n_cta = min(((T + 127) // 128) * (Cout // ntile), 148)
-        trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+        trace = torch.zeros(148 * 16 + 3 * 512, dtype=torch.int64, device=dev)
         for _ in range(3):
             assert lib.rvcb200_op_conv_tc(C.byref(d), 1, st) == 0
         torch.cuda.synchronize()
@@ -93,7 +101,9 @@ def main():
             torch.cuda.synchronize()
             lib.rvcb200_op_conv_tc(C.byref(d), 1, st)
             torch.cuda.synchronize()
-            t = trace.cpu().numpy().reshape(148, 16)[:n_cta].astype(np.float64)
+            full = trace.cpu().numpy()
+            steps = full[148 * 16:].reshape(3, 512).astype(np.float64)
+            t = full[:148 * 16].reshape(148, 16)[:n_cta].astype(np.float64)
             t0 = t[:, 0].min()
             segs.append(np.concatenate([[np.median(t[:, 0] - t0)], np.median(np.diff(t[:, :7], axis=1), axis=0),
                                         [t[:, 6].max() - t0]]))
@@ -104,6 +114,16 @@ def main():
         for i in range(6):
             line[f"{POINTS[i]}->{POINTS[i + 1]}_us"] = round(m[1 + i], 2)
         line["first_start->last_epilogue_done_us"] = round(m[7], 2)
+        nst = int((steps[0] > 0).sum())                                      # CTA 0, first tile, last repetition
+        if nst >= 12:
+            iss, rdy, mma = steps[0, :nst], steps[1, :nst], steps[2, :nst]
+            line["cta0_steps"] = nst
+            line["cta0_issue_interval_first10_us"] = round(float(np.diff(iss[:10]).mean()) / 1e3, 3)
+            line["cta0_issue_interval_steady_us"] = round(float(np.diff(iss[10:]).mean()) / 1e3, 3)
+            line["cta0_issue->full_first10_us"] = [round(float(v) / 1e3, 2) for v in (rdy - iss)[:10]]
+            line["cta0_issue->full_steady_us"] = round(float(np.median((rdy - iss)[10:])) / 1e3, 3)
+            line["cta0_full->mma_issued_us"] = round(float(np.median(mma - rdy)) / 1e3, 3)
+            line["cta0_mma_issued->slot_reissued_us"] = round(float(np.median(iss[10:] - mma[:nst - 10])) / 1e3, 3)
         print(json.dumps(line), flush=True)
 
 
