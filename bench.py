@@ -544,6 +544,28 @@ def main():
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001
             line["front_end"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        # ... and the other model in front of it: RMVPE f0 of the same audio (comfy_rvc_b200.RMVPE),
+        # host audio in, host f0 out like the reference's `infer_from_audio`
+        try:
+            from comfy_rvc_b200.rmvpe import RMVPE
+            rm = RMVPE(synthetic.make_rmvpe_state_dict(0), is_half=True, device=dev)
+            wav = synthetic.make_speech(audio_s, seed=1)[0].numpy()
+            for _ in range(3):
+                rm.infer_from_audio(wav)
+            torch.cuda.synchronize()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(args.steps):
+                rm.infer_from_audio(wav)
+            h1.record()
+            torch.cuda.synchronize()
+            rms = h0.elapsed_time(h1) / args.steps
+            line["f0_front_end"] = {"what": "RMVPE.infer_from_audio on the segment's 16 kHz audio (host in, host out)",
+                                    "ms_per_segment": rms, "audio_s_per_s": audio_s / (rms / 1e3), "launches": rm.last_launches}
+            del rm
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            line["f0_front_end"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     if world == 1 and not args.no_gpu_incumbent:
         inc = {}
         for name, half in (("fp16", True), ("fp32_tf32_off", False)):

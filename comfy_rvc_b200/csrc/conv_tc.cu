@@ -54,6 +54,11 @@ __host__ __device__ __forceinline__ int tap_row_off(const TcConvDesc& p, int tap
   return p.tap_w > 0 ? (tap / p.tap_w) * p.dil2 + (tap % p.tap_w) * p.dil : tap * p.dil;
 }
 __host__ __device__ __forceinline__ int tap_halo(const TcConvDesc& p) { return p.ntaps > 0 ? tap_row_off(p, p.ntaps - 1) : 0; }
+// a_mode 2 ("row slabs", 2-D kernels only): one activation box per (k-block, kernel ROW) at row offset kh * dil2, holding
+// 128 + (tap_w - 1) * dil rows; the tap_w taps of that kernel row are descriptor offsets into it.  A 3 x 3 convolution over a wide
+// image (W = 128: a_mode 0 would need a 128 + 2 W + 4 row box, a_mode 1 nine boxes and nine wait / commit round trips per tile --
+// 3.5 us per 128-row tile at C = 16, profiles/r2_rmvpe_launches_60s_v2.csv) takes three boxes and three waits per tile.
+__host__ __device__ __forceinline__ int slab_rows_halo(const TcConvDesc& p) { return p.a_mode == 2 ? (p.tap_w - 1) * p.dil : tap_halo(p); }
 
 constexpr int kEpiWarps = 8;
 constexpr int kThreadsTC = 64 + 32 * kEpiWarps;   // producer warp + MMA warp + epilogue warps
@@ -190,8 +195,10 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const int halo = tap_halo(p);
-  const bool slab = p.a_mode != 1;                             // a_mode 0/2/3: one box per k-block (+ base_offset probes)
+  const int halo = slab_rows_halo(p);
+  const bool slab = p.a_mode != 1;                             // a_mode 0: one box per k-block; 2: one per (k-block, kernel row)
+  const int KH = p.a_mode == 2 ? p.ntaps / p.tap_w : 1;        // activation boxes per k-block
+  const int TW = p.a_mode == 2 ? p.tap_w : p.ntaps;            // taps per activation box
   const int R = slab ? ((BM + halo + 7) & ~7) : BM;            // rows per activation box
   const int nkb = (p.Cin + KBLK - 1) / KBLK;
   const uint32_t a_bytes = (uint32_t)R * 128;
@@ -275,14 +282,15 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         decode((long long)blockIdx.x + (long long)t * gridDim.x, mt, nt, g, b);
         const int row0 = mt * BM + p.g_off[g];
         int wrow = w_row(g, nt, 0, 0);
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb)
+         for (int kh = 0; kh < KH; ++kh) {
           if (slab) {
             mbar_wait(&a_empty[sa], pa);
             mbar_expect_tx(&a_full[sa], a_bytes);
-            tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0, b, &a_full[sa]);
+            tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0 + kh * p.dil2, b, &a_full[sa]);
             if (++sa == NA) { sa = 0; pa ^= 1; }
           }
-          for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int tap = kh * TW; tap < kh * TW + TW; ++tap) {
             if (!slab) {
               mbar_wait(&a_empty[sa], pa);
               mbar_expect_tx(&a_full[sa], a_bytes);
@@ -321,9 +329,11 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
       uint32_t accum = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = 0; kb < nkb; ++kb)
+       for (int kh = 0; kh < KH; ++kh) {
         const int kleft = p.Cin - kb * KBLK;
         const int ksteps = kleft >= KBLK ? KBLK / 16 : (kleft + 15) / 16;     // skip the zero-padded K of narrow stages
+        const int tap0 = kh * TW;                                            // first tap served by this activation box
         if (slab) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
@@ -335,13 +345,13 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           {
             const uint32_t leader = elect_one() ? 1u : 0u;
             uint32_t a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
-            uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps) * b_stride) >> 4);
+            uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)(kb * p.ntaps + tap0) * b_stride) >> 4);
             const uint32_t a_step = (uint32_t)(p.dil * 128) >> 4, b_step = b_stride >> 4;
             // 2-D kernels: after tap_w taps the offset jumps to the next kernel row (no division in the loop)
-            const uint32_t a_wrap = p.tap_w > 0 ? (uint32_t)((p.dil2 - (p.tap_w - 1) * p.dil) * 128) >> 4 : a_step;
-            const int tw = p.tap_w > 0 ? p.tap_w : 0x7fffffff;
+            const uint32_t a_wrap = (p.tap_w > 0 && KH == 1) ? (uint32_t)((p.dil2 - (p.tap_w - 1) * p.dil) * 128) >> 4 : a_step;
+            const int tw = (p.tap_w > 0 && KH == 1) ? p.tap_w : 0x7fffffff;
             int tx = 0;
-            for (int tap = 0; tap < p.ntaps; ++tap) {
+            for (int tap = 0; tap < TW; ++tap) {
               for (int ks = 0; ks < ksteps; ++ks) {
                 tc_mma_f16_pred(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum, leader);
                 accum = 1;
@@ -356,10 +366,11 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           if (++sa == NA) { sa = 0; pa ^= 1; }
           continue;
         }
-        for (int tap = 0; tap < p.ntaps; ++tap) {
+        for (int tap = tap0; tap < tap0 + TW; ++tap) {
           uint32_t a_lo;
           if (slab) {
-            a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride + (uint32_t)tap_row_off(p, tap) * 128u) >> 4);
+            const int roff = KH > 1 ? (tap - tap0) * p.dil : tap_row_off(p, tap);
+            a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride + (uint32_t)roff * 128u) >> 4);
           } else {
             mbar_wait(&a_full[sa], pa);
             tc_fence_after();
@@ -517,7 +528,7 @@ constexpr size_t kStageBytes = 8 * 2 * 2048 + 1024;   // tma_out staging (+ alig
 constexpr size_t kGenericBiasBytes = 2 * 256 * 4 + 1024;   // generic epilogue: staged bias + conditioning per epilogue group
 
 size_t tc_smem_bytes(const TcConvDesc& d) {
-  const int halo = tap_halo(d);
+  const int halo = slab_rows_halo(d);
   const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
   const size_t a = (((size_t)R * 128) + 1023) & ~(size_t)1023;
   const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
@@ -857,7 +868,8 @@ cudaError_t conv_tc_set_trace(void* buf) {
 cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   TcConvDesc d = d_in;
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.Cin % 8 != 0 || d.Cout_total % d.N != 0 || d.G < 1 || d.G > 16 ||
-      d.Lj <= 0 || d.L_in <= 0 || (d.a_mode != 1 && tap_halo(d) > 127) || tap_halo(d) < 0 || d.tap_w < 0 ||
+      d.Lj <= 0 || d.L_in <= 0 || (d.a_mode != 1 && slab_rows_halo(d) > 127) || tap_halo(d) < 0 || d.tap_w < 0 ||
+      d.a_mode < 0 || d.a_mode > 2 || (d.a_mode == 2 && d.tap_w <= 0) ||
       (d.tap_w > 0 && (d.ntaps % d.tap_w != 0 || d.dil2 < (d.tap_w - 1) * d.dil)) || d.pad_period < 0 || (d.pad_period > 0 && !d.generic) || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
       d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)))
     return cudaErrorInvalidValue;
@@ -868,7 +880,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   while (cols < 2 * d.N) cols <<= 1;          // two accumulator buffers
   d.tmem_cols = cols;
   const int nkb = (d.Cin + KBLK - 1) / KBLK;
-  const int halo = tap_halo(d);
+  const int halo = slab_rows_halo(d);
   const int n_nt = d.Cout_total / d.N;
   const long long tiles = (long long)((d.Lj + BM - 1) / BM) * n_nt * d.G * B;
   {
@@ -902,7 +914,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     } else {
       // (ring depths: 5 slabs / 16 weight tiles instead of 3 / 10 changed nothing for the one-tile-per-CTA contractions,
       //  profiles/r2_ab_rings_injgemm.md)
-      d.na_stages = d.a_mode != 1 ? (nkb >= 2 ? 3 : 2) : 4;
+      d.na_stages = d.a_mode == 0 ? (nkb >= 2 ? 3 : 2) : 4;
       long long nb = (long long)(budget - (size_t)d.na_stages * a) / (long long)bb;
       d.nb_stages = (int)(nb > 10 ? 10 : (nb < 2 ? 2 : nb));
     }

@@ -241,7 +241,7 @@ class RMVPE:
         else:
             d.tap_w, d.dil2, d.g_off[0] = 0, 0, 0
         halo = (taps // d.tap_w - 1) * Wp + (d.tap_w - 1) if d.tap_w else 0
-        d.a_mode = 1 if halo > 127 else 0
+        d.a_mode = 2 if halo > 127 else 0          # wide images: one activation box per kernel row (conv_tc.cu, a_mode 2)
         d.N, d.Cout_total = n_tile, cout
         d.Lj, d.out_stride, d.Lp_out = rows, 1, ((rows + 127) // 128) * 128 + 128
         d.div, d.out_slope, d.alpha = 1.0, 1.0, 1.0

@@ -181,7 +181,8 @@ int rvcb200_op_conv_f32(const rvcb200_conv_desc* d, int32_t B, void* stream);
  * both staged by TMA into SWIZZLE_128B shared memory.  fp32 side (residual res32, output y32):
  * planar-vector [B][C/4][Lp_out][4] with `padf` rows in front; 16-bit output y16: channels-last
  * [B][Lj*out_stride][Cout_total] holding lrelu_{out_slope}(result).  a_mode 0 = one activation box per
- * k-block + per-tap descriptor offsets, 1 = one TMA box per (k-block, tap). */
+ * k-block + per-tap descriptor offsets, 1 = one TMA box per (k-block, tap), 2 (2-D kernels, tap_w > 0) = one box per
+ * (k-block, kernel row) whose tap_w taps are descriptor offsets. */
 typedef struct rvcb200_tc_conv_desc {
   const void* x16; int32_t L_in; int32_t padf;
   const void* w16; const float* bias;

@@ -158,11 +158,14 @@ def test_rmvpe_gru_matches_oracle(T):
     assert (o16.float().cpu() - want).abs().max().item() <= 1e-3
 
 
-@pytest.mark.parametrize("H,W,cin,cout,taps", [(8, 128, 16, 16, 9), (64, 128, 8, 16, 9), (32, 64, 32, 32, 9), (16, 16, 128, 128, 9),
-                                               (6, 4, 256, 512, 9), (12, 8, 512, 1024, 4), (64, 128, 32, 16, 1)])
-def test_rmvpe_image_convolution_matches_torch(H, W, cin, cout, taps):
-    """The generic tcgen05 kernel with 2-D taps (a_mode 1 for wide images, slab mode for narrow ones) against F.conv2d /
-    F.conv_transpose2d on the same fp16-rounded operands."""
+@pytest.mark.parametrize("H,W,cin,cout,taps,a_mode", [
+    (8, 128, 16, 16, 9, 2), (8, 128, 16, 16, 9, 1), (64, 128, 8, 16, 9, 2), (32, 64, 32, 32, 9, 2), (32, 64, 32, 32, 9, 1),
+    (700, 128, 16, 16, 9, 2),                                         # > 2 waves of tiles: resident weights + row slabs
+    (16, 16, 128, 128, 9, 0), (16, 16, 128, 128, 9, 2), (6, 4, 256, 512, 9, 0), (6, 4, 256, 512, 9, 2),
+    (12, 8, 512, 1024, 4, 0), (12, 8, 512, 1024, 4, 2), (64, 128, 32, 16, 1, 0)])
+def test_rmvpe_image_convolution_matches_torch(H, W, cin, cout, taps, a_mode):
+    """The generic tcgen05 kernel with 2-D taps -- one activation box per k-block (a_mode 0, narrow images), per tap (1) or per
+    kernel row (2, what the model uses for wide images) -- against F.conv2d / F.conv_transpose2d on the same fp16-rounded operands."""
     lib = _lib.load()
     g = torch.Generator().manual_seed(H * 1000 + W + cin)
     Wp, rows = W + 1, H * (W + 1)
@@ -206,7 +209,7 @@ def test_rmvpe_image_convolution_matches_torch(H, W, cin, cout, taps):
         d.tap_w, d.dil2, d.g_off[0] = 3, Wp, -(Wp + 1)
     elif taps == 4:
         d.tap_w, d.dil2 = 2, Wp
-    d.a_mode = 1 if (taps == 9 and 2 * Wp + 2 > 127) or (taps == 4 and Wp + 1 > 127) else 0
+    d.a_mode = a_mode
     d.N, d.Cout_total = n_tile, cout
     d.Lj, d.out_stride, d.Lp_out = rows, 1, ((rows + 127) // 128) * 128 + 128
     d.div, d.out_slope, d.alpha, d.pre_slope = 1.0, 1.0, 1.0, 0.0

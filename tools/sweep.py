@@ -60,6 +60,9 @@ def main():
     ap.add_argument("--front-end", default="fake", choices=["fake", "b200"],
                     help="song: `fake` = seeded random features drawn on the device (isolates the synthesis path), `b200` = the "
                          "HuBERT / ContentVec front end on the same kernels (comfy_rvc_b200.HubertB200, seeded weights)")
+    ap.add_argument("--f0", default="synthetic", choices=["synthetic", "rmvpe"],
+                    help="song: `synthetic` = a seeded contour (isolates the synthesis path), `rmvpe` = the RMVPE f0 estimator on the "
+                         "same kernels (comfy_rvc_b200.RMVPE, seeded weights), as the nodes' default f0_method does")
     ap.add_argument("--tiers", default="", help="song: comma list of x_center values to keep (60,38,30); default all")
     ap.add_argument("--check", action="store_true", help="song under torchrun: also run unsharded and compare bit for bit")
     ap.add_argument("--max-frames", type=int, default=0, help="sweep: only points with batch * frames <= this (0 = all)")
@@ -93,15 +96,21 @@ def main():
             hubert = HubertB200(synthetic.HUBERT_BASE, synthetic.make_hubert_state_dict(0), dev)
         else:
             hubert = synthetic.FakeHubert(cfg.feat_dim, device_rng=True)
+        rmvpe_model = None
+        if args.f0 == "rmvpe":
+            from comfy_rvc_b200.rmvpe import RMVPE
+            rmvpe_model = RMVPE(synthetic.make_rmvpe_state_dict(0), is_half=True, device=dev)
         solo = [dist.new_group([r]) for r in range(world)] if world > 1 else None       # 1-rank groups: the unsharded run
         for tier in [t for t in ((3, 10, 60, 64), (1, 6, 38, 41), (1, 5, 30, 32)) if not args.tiers or str(t[2]) in args.tiers.split(",")]:
             def make_vc(group=None):
                 v = pl.VC(cfg.sr, pl.PipelineConfig(*tier, is_half=False, device=str(dev)), noise="device", group=group)
                 v.f0_method_dict["synthetic"] = synthetic.pipeline_f0
+                if rmvpe_model is not None:
+                    v.model_rmvpe = rmvpe_model
                 return v
 
             def run(v):
-                return v.pipeline(hubert, net, 0, audio.copy(), [0, 0, 0], 0, "synthetic", "median", "", 0.0, 1, 3, cfg.sr, 0, 1.0,
+                return v.pipeline(hubert, net, 0, audio.copy(), [0, 0, 0], 0, args.f0, "median", "", 0.0, 1, 3, cfg.sr, 0, 1.0,
                                   "v2", 0.5, 160, False, False, None, 50, 1100)
             vc = make_vc()
             walls, dev_ms, host = [], [], []
@@ -130,7 +139,7 @@ def main():
                 secs = out.shape[0] / cfg.sr
                 w = float(np.median(walls))
                 h = {k: round(float(np.median([x[k] for x in host])), 4) for k in host[0]}
-                print(json.dumps({"config": f"48k_v2 VC.pipeline, {args.song_seconds:.0f} s song", "front_end": args.front_end,
+                print(json.dumps({"config": f"48k_v2 VC.pipeline, {args.song_seconds:.0f} s song", "front_end": args.front_end, "f0": args.f0,
                                   "tier": list(tier), "n_gpus": world,
                                   "precision": args.precision, "segments": len(plan["segments"]),
                                   "segment_seconds": [round(s.n_samples / 16000, 1) for s in plan["segments"]],
