@@ -18,7 +18,7 @@ def load_rmvpe_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     n, wseed, aseed = int(z["n_samples"]), int(z["weight_seed"]), int(z["audio_seed"])
     audio = synthetic.make_speech(n / 16000.0, seed=aseed)[0].numpy()
-    assert audio.shape[0] == n
+    assert audio.shape[0] == n                          # (fixtures of long inputs keep every `frame_step`-th frame of mel / hidden)
     return synthetic.make_rmvpe_state_dict(wseed), audio, z
 
 
