@@ -205,10 +205,16 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
   const uint32_t b_bytes = (uint32_t)p.N * 128;
   const int NA = p.na_stages, NB = p.nb_stages;
   const uint32_t a_stride = (a_bytes + 1023) & ~1023u, b_stride = (b_bytes + 1023) & ~1023u;
+  // Weight ring of the non-resident case: one ring stage = SG weight tiles (one wait / expect / commit per stage instead of
+  // per tile).  The two single-thread loops below are instruction-bound -- ~0.45 us per ring step whatever its bytes and
+  // whatever the contention (profiles/r2_trace_generic.md) -- so a stage carries SG consecutive k-blocks of a 1-tap contraction or
+  // SG consecutive taps of a k-block; the launcher picks SG (b_group).
+  const int SG = (p.b_stationary || p.a_mode == 1 || p.b_group < 1) ? 1 : p.b_group;
+  const uint32_t b_slot = (uint32_t)SG * b_stride;          // bytes per ring stage
 
   unsigned char* slabA = smem;                              // [NA][R][128 B] swizzled
-  unsigned char* slabB = smem + (size_t)NA * a_stride;      // [NB][N][128 B] swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slabB + (size_t)NB * b_stride);
+  unsigned char* slabB = smem + (size_t)NA * a_stride;      // [NB][SG][N][128 B] swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(slabB + (size_t)NB * b_slot);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NA;
   uint64_t* b_full = a_empty + NA;
@@ -282,6 +288,42 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         decode((long long)blockIdx.x + (long long)t * gridDim.x, mt, nt, g, b);
         const int row0 = mt * BM + p.g_off[g];
         int wrow = w_row(g, nt, 0, 0);
+        if (SG > 1) {                     // grouped ring stages (slab modes, weights not resident)
+          if (p.ntaps == 1) {             // a stage = SG consecutive k-blocks; their activation boxes first
+            for (int kbg = 0; kbg < nkb; kbg += SG) {
+              const int cnt = nkb - kbg < SG ? nkb - kbg : SG;
+              for (int kk = 0; kk < cnt; ++kk) {
+                mbar_wait(&a_empty[sa], pa);
+                mbar_expect_tx(&a_full[sa], a_bytes);
+                tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, (kbg + kk) * KBLK, row0, b, &a_full[sa]);
+                if (++sa == NA) { sa = 0; pa ^= 1; }
+              }
+              mbar_wait(&b_empty[sb], pb);
+              mbar_expect_tx(&b_full[sb], (uint32_t)cnt * b_bytes);
+              for (int kk = 0; kk < cnt; ++kk)
+                tma_load_2d(slabB + (size_t)sb * b_slot + (size_t)kk * b_stride, &tmW, 0, wrow + (kbg + kk) * p.N, &b_full[sb]);
+              if (++sb == NB) { sb = 0; pb ^= 1; }
+            }
+          } else {                        // a stage = SG consecutive taps of one (k-block, activation box)
+            for (int kb = 0; kb < nkb; ++kb)
+              for (int kh = 0; kh < KH; ++kh) {
+                mbar_wait(&a_empty[sa], pa);
+                mbar_expect_tx(&a_full[sa], a_bytes);
+                tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0 + kh * p.dil2, b, &a_full[sa]);
+                if (++sa == NA) { sa = 0; pa ^= 1; }
+                for (int tg = 0; tg < TW; tg += SG) {
+                  const int cnt = TW - tg < SG ? TW - tg : SG;
+                  mbar_wait(&b_empty[sb], pb);
+                  mbar_expect_tx(&b_full[sb], (uint32_t)cnt * b_bytes);
+                  for (int tl = 0; tl < cnt; ++tl)
+                    tma_load_2d(slabB + (size_t)sb * b_slot + (size_t)tl * b_stride, &tmW, 0,
+                                wrow + ((kh * TW + tg + tl) * nkb + kb) * p.N, &b_full[sb]);
+                  if (++sb == NB) { sb = 0; pb ^= 1; }
+                }
+              }
+          }
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb)
          for (int kh = 0; kh < KH; ++kh) {
           if (slab) {
@@ -329,6 +371,73 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.N);
       uint32_t accum = 0;
+      if (SG > 1) {
+        // grouped ring stages: one wait and one commit per stage; inside a stage the loop is warp-uniform with predicated MMAs
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t b_step = b_stride >> 4;
+        if (p.ntaps == 1) {
+          for (int kbg = 0; kbg < nkb; kbg += SG) {
+            const int cnt = nkb - kbg < SG ? nkb - kbg : SG;
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)sb * b_slot) >> 4);
+            for (int kk = 0; kk < cnt; ++kk) {
+              const int kleft = p.Cin - (kbg + kk) * KBLK;
+              const int ksteps = kleft >= KBLK ? KBLK / 16 : (kleft + 15) / 16;
+              mbar_wait(&a_full[sa], pa);
+              tc_fence_after();
+              if (t == 0 && kbg == 0 && kk == 0 && lane == 0) trace_mark(3);
+              const uint32_t a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
+              for (int ks = 0; ks < ksteps; ++ks) {
+                tc_mma_f16_pred(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum, leader);
+                accum = 1;
+              }
+              tc_commit_pred(&a_empty[sa], leader);
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+              b_lo += b_step;
+            }
+            tc_commit_pred(&b_empty[sb], leader);
+            if (++sb == NB) { sb = 0; pb ^= 1; }
+          }
+        } else {
+          const uint32_t a_step = (uint32_t)(p.dil * 128) >> 4;
+          const uint32_t a_wrap = (p.tap_w > 0 && KH == 1) ? (uint32_t)((p.dil2 - (p.tap_w - 1) * p.dil) * 128) >> 4 : a_step;
+          const int tw = (p.tap_w > 0 && KH == 1) ? p.tap_w : 0x7fffffff;
+          for (int kb = 0; kb < nkb; ++kb) {
+            const int kleft = p.Cin - kb * KBLK;
+            const int ksteps = kleft >= KBLK ? KBLK / 16 : (kleft + 15) / 16;
+            for (int kh = 0; kh < KH; ++kh) {
+              mbar_wait(&a_full[sa], pa);
+              tc_fence_after();
+              if (t == 0 && kb == 0 && kh == 0 && lane == 0) trace_mark(3);
+              uint32_t a_lo = d_lo0 + ((slabA_u + (uint32_t)sa * a_stride) >> 4);
+              int tx = 0;
+              for (int tg = 0; tg < TW; tg += SG) {
+                const int cnt = TW - tg < SG ? TW - tg : SG;
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                uint32_t b_lo = d_lo0 + ((slabB_u + (uint32_t)sb * b_slot) >> 4);
+                for (int tl = 0; tl < cnt; ++tl) {
+                  for (int ks = 0; ks < ksteps; ++ks) {
+                    tc_mma_f16_pred(d_tmem, a_lo + 2u * ks, d_hi0, b_lo + 2u * ks, d_hi0, idesc, accum, leader);
+                    accum = 1;
+                  }
+                  if (++tx == tw) { tx = 0; a_lo += a_wrap; } else { a_lo += a_step; }
+                  b_lo += b_step;
+                }
+                tc_commit_pred(&b_empty[sb], leader);
+                if (++sb == NB) { sb = 0; pb ^= 1; }
+              }
+              tc_commit_pred(&a_empty[sa], leader);
+              if (++sa == NA) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+        tc_commit_pred(&acc_full[buf], leader);
+        if (t == 0 && lane == 0) trace_mark(4);
+        __syncwarp();
+        continue;
+      }
       for (int kb = 0; kb < nkb; ++kb)
        for (int kh = 0; kh < KH; ++kh) {
         const int kleft = p.Cin - kb * KBLK;
@@ -532,7 +641,8 @@ size_t tc_smem_bytes(const TcConvDesc& d) {
   const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
   const size_t a = (((size_t)R * 128) + 1023) & ~(size_t)1023;
   const size_t bb = (((size_t)d.N * 128) + 1023) & ~(size_t)1023;
-  return 1024 + d.na_stages * a + d.nb_stages * bb + 8 * (2 * d.na_stages + 2 * d.nb_stages + 4) + 16 + 128 +
+  const size_t sg = (d.b_stationary || d.a_mode == 1 || d.b_group < 1) ? 1 : (size_t)d.b_group;
+  return 1024 + d.na_stages * a + d.nb_stages * sg * bb + 8 * (2 * d.na_stages + 2 * d.nb_stages + 4) + 16 + 128 +
          (d.tma_out ? kStageBytes : 0) + (d.generic ? kGenericBiasBytes : 0);
 }
 
@@ -915,7 +1025,26 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
       // (ring depths: 5 slabs / 16 weight tiles instead of 3 / 10 changed nothing for the one-tile-per-CTA contractions,
       //  profiles/r2_ab_rings_injgemm.md)
       d.na_stages = d.a_mode == 0 ? (nkb >= 2 ? 3 : 2) : 4;
-      long long nb = (long long)(budget - (size_t)d.na_stages * a) / (long long)bb;
+      // grouped ring stages (slab modes): SG weight tiles per stage, <= 48 KB, at least 3 stages beside the activation boxes.
+      // 1-tap contractions group k-blocks (and need SG + 1 activation boxes in flight), the others group the taps of one box.
+      static const int max_group = [] { const char* e = getenv("RVCB200_BGROUP"); return e ? atoi(e) : 8; }();
+      d.b_group = 1;
+      if (d.a_mode != 1 && max_group > 1) {
+        const int per_box = d.ntaps == 1 ? nkb : (d.a_mode == 2 ? d.tap_w : d.ntaps);     // tiles that can share a stage
+        int sg = per_box < max_group ? per_box : max_group;
+        while (sg > 1) {
+          if (d.ntaps != 1 && per_box % sg != 0 && per_box > sg) { --sg; continue; }       // even groups (9 taps -> 3, 5 -> 5)
+          const int na = d.ntaps == 1 ? sg + 2 : d.na_stages;
+          const size_t ring = budget > (size_t)na * a ? budget - (size_t)na * a : 0;
+          if ((size_t)sg * bb <= 48 * 1024 && ring / ((size_t)sg * bb) >= 3 && na <= 8) {
+            d.b_group = sg;
+            d.na_stages = na;
+            break;
+          }
+          --sg;
+        }
+      }
+      long long nb = (long long)(budget - (size_t)d.na_stages * a) / (long long)((size_t)d.b_group * bb);
       d.nb_stages = (int)(nb > 10 ? 10 : (nb < 2 ? 2 : nb));
     }
   }

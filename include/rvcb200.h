@@ -234,7 +234,7 @@ typedef struct rvcb200_tc_conv_desc {
    * t * dil).  Rows before 0 / past L_in are zero-filled by the tensor map, the pad pixel supplies the left / right border.
    * pad_period > 0 (generic epilogue): with mask_post, output rows whose (row % pad_period) >= pad_valid are written as 0. */
   int32_t tap_w, dil2, pad_period, pad_valid;
-  int32_t reserved0;
+  int32_t b_group;             /* filled in by the launcher: weight tiles per ring stage (non-resident weights) */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 

@@ -1,0 +1,25 @@
+#!/bin/bash
+# Round-2 visit 15 (1 GPU): grouped weight-ring stages in the generic kernel: whole GPU suite, then A/B (RVCB200_BGROUP=1 = old behaviour)
+set -x
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+timeout 1200 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_v15.log 2>&1
+echo "pytest rc=$?" | tee gpurun_out/status.txt; tail -6 gpurun_out/pytest_v15.log
+for g in 1 8; do
+  RVCB200_BGROUP=$g timeout 300 python tools/bench_rmvpe.py --seconds 5,60 --no-incumbent > gpurun_out/rmvpe_bench_bg$g.jsonl 2>> gpurun_out/rmvpe_bench.err; cat gpurun_out/rmvpe_bench_bg$g.jsonl
+  RVCB200_BGROUP=$g timeout 300 python tools/bench_hubert.py --seconds 5,60 > gpurun_out/hubert_bench_bg$g.jsonl 2>> gpurun_out/hubert_bench.err; cut -c1-200 gpurun_out/hubert_bench_bg$g.jsonl
+  RVCB200_BGROUP=$g timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-incumbent --no-front-end > gpurun_out/bench_bg$g.json 2> gpurun_out/bench_bg$g.err; echo "bench rc=$?"
+  python - <<P
+import json
+d = json.load(open("gpurun_out/bench_bg$g.json"))
+print("BGROUP=$g", round(d["ms_per_step"],3), d["clocks"]["sm_mhz"], {k: round(v,3) for k,v in d["time_by_class_ms_per_step"].items()}, d["parity"]["snr_db"])
+P
+done
+timeout 200 python tools/trace_generic.py --T 6000 > gpurun_out/trace_generic_T6000_v4_grouped.jsonl 2> gpurun_out/trace.err
+timeout 200 python tools/trace_generic.py --rmvpe --T 6000 > gpurun_out/trace_rmvpe_T6000_v3_grouped.jsonl 2>> gpurun_out/trace.err
+python - <<'P'
+import json
+for f in ("gpurun_out/trace_generic_T6000_v4_grouped.jsonl", "gpurun_out/trace_rmvpe_T6000_v3_grouped.jsonl"):
+    for l in open(f):
+        d = json.loads(l); print(d["shape"], d["event_us_back_to_back"], "mma", d["slab0_landed->mmas_issued_us"], "epi", d["acc_complete->epilogue_done_us"])
+P
