@@ -161,11 +161,13 @@ constexpr int kGruH = 256, kGruCl = 8, kGruUnits = kGruH / kGruCl;
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// (plain try_wait, as for TMA / multicast data: with `.acquire.cluster` every step paid a CCTL.IVALL -- an L1 invalidate, 11 % of
+//  the kernel's stall samples in profiles/r2_ncu_rmvpe.md; the mbarrier's complete_tx is what orders the st.async data)
 __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "GRU_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@!p bra GRU_WAIT_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 // sigmoid / tanh from the hardware exponential (ex2.approx, 2 ulp): ~1e-7 absolute on the gates
