@@ -219,6 +219,48 @@ def gpu_incumbent_rate(cfg, T: int, dev, half: bool, reps: int = 3):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
 
 
+def rmvpe_incumbent(wav, dev, half: bool, reps: int = 3):
+    """The eager-PyTorch incumbent of the f0 estimator on the same GPU: the oracle's functional form of lib/rmvpe.py (cuDNN
+    convolutions) with a `torch.nn.GRU` holding the same weights (cuDNN GRU, what the reference's `nn.GRU` runs), fp16 (`is_half`)
+    or fp32 with TF32 off.  Returns (ms per call, salience [frames, 360] fp32 on the host).  Measurement context only."""
+    from oracle import rmvpe_oracle as ro
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        dt = torch.float16 if half else torch.float32
+        sd = synthetic.make_rmvpe_state_dict(0)
+        gru = torch.nn.GRU(384, 256, num_layers=1, batch_first=True, bidirectional=True)
+        gru.load_state_dict({k[len("fc.0.gru."):]: v for k, v in sd.items() if k.startswith("fc.0.gru.")})
+        gru = gru.to(dev, dt).eval()
+        sd_dev = {k: v.to(dev) for k, v in sd.items()}
+        ro._BASIS_CACHE["basis"] = ro.stft_forward_basis().to(dev)
+        ro._BASIS_CACHE["mel"] = torch.from_numpy(ro.mel_filterbank()).float().to(dev)
+
+        def call():
+            with torch.no_grad():
+                mel = ro.log_mel(torch.from_numpy(wav).float().to(dev)[None])
+                n = mel.shape[-1]
+                mel = torch.nn.functional.pad(mel, (0, min(32 * ((n - 1) // 32 + 1) - n, n)), mode="reflect")
+                return ro.e2e_forward(sd_dev, mel.to(dt), gru=lambda x: gru(x)[0], dtype=dt)[0, :n].float().cpu().numpy()
+
+        for _ in range(2):
+            call()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            hid = call()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ro._BASIS_CACHE.clear()
+        del gru, sd_dev
+        torch.cuda.empty_cache()
+        return e0.elapsed_time(e1) / reps, hid
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
+
+
 def parity_block(net, cfg, T: int, precision: str, config_name: str):
     """One more step of the timed workload with the fixture's seeded noise injected (the timed steps draw theirs on the
     device like the reference, so their waveforms are not comparable sample by sample), checked OUTSIDE the timed region
@@ -562,6 +604,17 @@ def main():
             rms = h0.elapsed_time(h1) / args.steps
             line["f0_front_end"] = {"what": "RMVPE.infer_from_audio on the segment's 16 kHz audio (host in, host out)",
                                     "ms_per_segment": rms, "audio_s_per_s": audio_s / (rms / 1e3), "launches": rm.last_launches}
+            if not args.no_gpu_incumbent:
+                taps = {}
+                rm.infer_from_audio(wav, taps=taps)
+                ours = taps["hidden"].cpu().numpy().astype(np.float64)
+                lg = lambda q: np.log(np.clip(q, 1e-7, 1 - 1e-7)) - np.log1p(-np.clip(q, 1e-7, 1 - 1e-7))
+                ms32, ref = rmvpe_incumbent(wav, dev, False)
+                ms16, h16 = rmvpe_incumbent(wav, dev, True)
+                line["f0_front_end"]["gpu_incumbent"] = {
+                    "fp32_tf32_off_ms": ms32, "fp16_ms": ms16, "logit_snr_db_vs_incumbent_fp32": synthetic.snr_db(lg(ref), lg(ours)),
+                    "incumbent_fp16_logit_snr_db": synthetic.snr_db(lg(ref), lg(h16)),
+                    "what": "the same network in eager PyTorch on this GPU (oracle/rmvpe_oracle.py's functional form + torch.nn.GRU)"}
             del rm
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001

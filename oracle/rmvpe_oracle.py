@@ -14,7 +14,8 @@ scale, triangular filters built from `np.subtract.outer`, Slaney area normalisat
 
 Parity pin: `tests/golden/make_rmvpe_golden.py` runs the reference's own classes (lib/rmvpe.py imported read-only, `librosa`
 stubbed with the three helpers it imports) on seeded weights and audio in the build container; `tests/test_rmvpe_oracle.py`
-replays the fixtures against this file.  Only `tests/` and `tools/bench_rmvpe.py`'s incumbent leg may import this module.
+replays the fixtures against this file.  Only `tests/` and `bench.py`'s incumbent leg (`rmvpe_incumbent`: this functional form on CUDA
+tensors as the eager-PyTorch figure to compare with) may import this module.
 """
 from __future__ import annotations
 
@@ -97,7 +98,7 @@ def e2e_forward(sd: Dict[str, torch.Tensor], mel: torch.Tensor, n_blocks: int = 
                 taps=None, gru=None, dtype=torch.float32) -> torch.Tensor:
     """rmvpe.py:465-472: mel [B, 128, T] (T a multiple of 32) -> salience [B, T, 360].
     `gru` (optional): a callable replacing the explicit recurrence below, e.g. a `torch.nn.GRU` holding the same weights -- used by
-    tools/bench_rmvpe.py to time the library (cuDNN) path the reference takes on a GPU; `dtype` float16 = the reference's is_half."""
+    bench.py's `rmvpe_incumbent` to time the library (cuDNN) path the reference takes on a GPU; `dtype` float16 = the reference's is_half."""
     w = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     x = mel.to(dtype).transpose(-1, -2).unsqueeze(1)                                 # [B, 1, T, 128]
     x = _bn(x, w, "unet.encoder.bn.")                                                # :299

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """RMVPE f0 estimator: the B200 kernels (comfy_rvc_b200.RMVPE.infer_from_audio: host audio in, host f0 out) against the incumbent
-the reference runs on a GPU -- the same network in eager PyTorch (cuDNN convolutions, cuDNN GRU; the oracle's functional form with
-a `torch.nn.GRU` holding the same weights), fp32 (TF32 off) and fp16 (`is_half`) -- on one utterance of `--seconds` at 16 kHz.
+the reference runs on a GPU -- the same network in eager PyTorch (cuDNN convolutions, cuDNN GRU), fp32 (TF32 off) and fp16
+(`is_half`), through `bench.py`'s `rmvpe_incumbent` leg -- on one utterance of `--seconds` at 16 kHz.
 One JSON line per length: ms per call, audio seconds per second, launches, the GRU recurrence alone, parity against the incumbent's
 fp32 salience.
 
@@ -50,26 +50,10 @@ def main():
     ours = RMVPE(sd, is_half=True, device=dev)
     lib = _lib.load()
     inc = None
-    if not args.no_incumbent:
-        from oracle import rmvpe_oracle as ro                      # incumbent leg only (see the oracle's header)
-        gru = torch.nn.GRU(384, 256, num_layers=1, batch_first=True, bidirectional=True)
-        gru.load_state_dict({k[len("fc.0.gru."):]: v for k, v in sd.items() if k.startswith("fc.0.gru.")})
-        gru = gru.to(dev).eval()
-        sd_dev = {k: v.to(dev) for k, v in sd.items()}
-        ro._BASIS_CACHE["basis"] = ro.stft_forward_basis().to(dev)
-        ro._BASIS_CACHE["mel"] = torch.from_numpy(ro.mel_filterbank()).float().to(dev)
-
-        def incumbent(audio_np, dtype):
-            with torch.no_grad():
-                a = torch.from_numpy(audio_np).float().to(dev)[None]
-                mel = ro.log_mel(a)
-                n = mel.shape[-1]
-                pad = min(32 * ((n - 1) // 32 + 1) - n, n)
-                mel = torch.nn.functional.pad(mel, (0, pad), mode="reflect")
-                g = gru.half() if dtype == torch.float16 else gru.float()
-                hid = ro.e2e_forward(sd_dev, mel.to(dtype), gru=lambda x: g(x)[0], dtype=dtype)[:, :n]
-                return hid.squeeze(0).float().cpu().numpy()
-        inc = incumbent
+    if not args.no_incumbent:                                      # the incumbent leg lives in bench.py (oracle/ is test infrastructure)
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench as _bench
+        inc = lambda audio_np, dtype: _bench.rmvpe_incumbent(audio_np, dev, dtype == torch.float16, reps=1)[1]
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     for secs in [float(s) for s in args.seconds.split(",")]:
