@@ -102,14 +102,17 @@ SYMBOLS = {
     "rvcb200_op_conv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_debug_trace_conv_tc": (C.c_int, [C.c_void_p]),
     "rvcb200_op_rmvpe_logmel": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
-                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
-    "rvcb200_op_rmvpe_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
-    "rvcb200_op_rmvpe_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
-    "rvcb200_op_rmvpe_gru_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "rvcb200_op_rmvpe_pool": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_void_p]),
+    "rvcb200_op_rmvpe_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_void_p]),
+    "rvcb200_op_rmvpe_gru_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "rvcb200_op_rmvpe_gru": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "rvcb200_op_rmvpe_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
                                           C.c_void_p]),
-    "rvcb200_op_rmvpe_mel_to_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p]),
+    "rvcb200_op_rmvpe_mel_to_img": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                              C.c_void_p]),
     "rvcb200_op_rbconv_tc": (C.c_int, [C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_rbpair_tc": (C.c_int, [C.POINTER(TcConvDesc), C.POINTER(TcConvDesc), C.c_int32, C.c_void_p]),
     "rvcb200_op_sine_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),

@@ -135,14 +135,15 @@ cudaError_t launch_hubert_conv0(const float* x, const float* w, const float* gn_
 // ---- RMVPE f0 estimator: the non-contraction steps (rmvpe_kernels.cu) ----
 cudaError_t launch_rmvpe_logmel(const float* audio, long long n, const float* window, const void* twiddle, const float* mel_basis,
                                 const void* mel_range, float bn_scale, float bn_shift, float* mel_out, void* img, int n_frames,
-                                int frames_out, cudaStream_t st);
-cudaError_t launch_rmvpe_pool(const float* x, int ldx, void* y16, int H2, int W2, int C, cudaStream_t st);
-cudaError_t launch_rmvpe_shuffle(const void* g16, void* out16, int H, int W, int Co, int ld, cudaStream_t st);
-cudaError_t launch_rmvpe_gru_pack(const float* y, int ldc, void* x16, long long T, int W, cudaStream_t st);
+                                int frames_out, int img_pitch, int img_c, cudaStream_t st);
+cudaError_t launch_rmvpe_pool(const float* x, int ldx, void* y16, int H2, int W2, int C, int p_in, int p_out, cudaStream_t st);
+cudaError_t launch_rmvpe_shuffle(const void* g16, void* out16, int H, int W, int Co, int ld, int p_in, int fp_out, int pack,
+                                 cudaStream_t st);
+cudaError_t launch_rmvpe_gru_pack(const float* y, int ldc, void* x16, long long T, int W, int pitch, cudaStream_t st);
 cudaError_t launch_rmvpe_gru(const float* gi, const float* w_hh, const float* b_hh, void* out16, float* out32, int T, cudaStream_t st);
 cudaError_t launch_rmvpe_decode(const float* in, int ld, int from_hidden, float* hidden, double* f0, double* cents, int T,
                                 float thred, cudaStream_t st);
 cudaError_t launch_rmvpe_mel_to_img(const float* mel, void* img, int n_frames, int frames_out, float bn_scale, float bn_shift,
-                                    cudaStream_t st);
+                                    int img_pitch, int img_c, cudaStream_t st);
 
 }  // namespace rvc

@@ -1210,24 +1210,26 @@ int rvcb200_op_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int3
 
 int rvcb200_op_rmvpe_logmel(const float* audio, int64_t n, const float* window, const float* twiddle, const float* mel_basis,
                             const int32_t* mel_range, float bn_scale, float bn_shift, float* mel_out, void* img16, int32_t n_frames,
-                            int32_t frames_out, void* stream) {
+                            int32_t frames_out, int32_t img_pitch, int32_t img_c, void* stream) {
   cudaError_t e = launch_rmvpe_logmel(audio, n, window, twiddle, mel_basis, mel_range, bn_scale, bn_shift, mel_out, img16, n_frames,
-                                      frames_out, reinterpret_cast<cudaStream_t>(stream));
+                                      frames_out, img_pitch, img_c, reinterpret_cast<cudaStream_t>(stream));
   RVC_RET(e);
 }
 
-int rvcb200_op_rmvpe_pool(const float* x32, int32_t ldx, void* y16, int32_t H2, int32_t W2, int32_t C, void* stream) {
-  cudaError_t e = launch_rmvpe_pool(x32, ldx, y16, H2, W2, C, reinterpret_cast<cudaStream_t>(stream));
+int rvcb200_op_rmvpe_pool(const float* x32, int32_t ldx, void* y16, int32_t H2, int32_t W2, int32_t C, int32_t p_in, int32_t p_out,
+                          void* stream) {
+  cudaError_t e = launch_rmvpe_pool(x32, ldx, y16, H2, W2, C, p_in, p_out, reinterpret_cast<cudaStream_t>(stream));
   RVC_RET(e);
 }
 
-int rvcb200_op_rmvpe_shuffle(const void* g16, void* out16, int32_t H, int32_t W, int32_t Co, int32_t ld, void* stream) {
-  cudaError_t e = launch_rmvpe_shuffle(g16, out16, H, W, Co, ld, reinterpret_cast<cudaStream_t>(stream));
+int rvcb200_op_rmvpe_shuffle(const void* g16, void* out16, int32_t H, int32_t W, int32_t Co, int32_t ld, int32_t p_in, int32_t fp_out,
+                             int32_t pack, void* stream) {
+  cudaError_t e = launch_rmvpe_shuffle(g16, out16, H, W, Co, ld, p_in, fp_out, pack, reinterpret_cast<cudaStream_t>(stream));
   RVC_RET(e);
 }
 
-int rvcb200_op_rmvpe_gru_pack(const float* y32, int32_t ldc, void* x16, int64_t T, int32_t W, void* stream) {
-  cudaError_t e = launch_rmvpe_gru_pack(y32, ldc, x16, T, W, reinterpret_cast<cudaStream_t>(stream));
+int rvcb200_op_rmvpe_gru_pack(const float* y32, int32_t ldc, void* x16, int64_t T, int32_t W, int32_t pitch, void* stream) {
+  cudaError_t e = launch_rmvpe_gru_pack(y32, ldc, x16, T, W, pitch, reinterpret_cast<cudaStream_t>(stream));
   RVC_RET(e);
 }
 
@@ -1243,8 +1245,9 @@ int rvcb200_op_rmvpe_decode(const float* in, int32_t ld, int32_t from_hidden, fl
 }
 
 int rvcb200_op_rmvpe_mel_to_img(const float* mel, void* img16, int32_t n_frames, int32_t frames_out, float bn_scale, float bn_shift,
-                                void* stream) {
-  cudaError_t e = launch_rmvpe_mel_to_img(mel, img16, n_frames, frames_out, bn_scale, bn_shift, reinterpret_cast<cudaStream_t>(stream));
+                                int32_t img_pitch, int32_t img_c, void* stream) {
+  cudaError_t e = launch_rmvpe_mel_to_img(mel, img16, n_frames, frames_out, bn_scale, bn_shift, img_pitch, img_c,
+                                          reinterpret_cast<cudaStream_t>(stream));
   RVC_RET(e);
 }
 

@@ -18,7 +18,7 @@
 namespace rvc {
 namespace {
 
-constexpr int kNfft = 1024, kHop = 160, kMels = 128, kBins = 513, kImgC = 8;
+constexpr int kNfft = 1024, kHop = 160, kMels = 128, kBins = 513;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -26,7 +26,7 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 __global__ void __launch_bounds__(256)
 rmvpe_logmel_kernel(const float* __restrict__ audio, long long n, const float* __restrict__ window, const float2* __restrict__ twiddle,
                     const float* __restrict__ mel_basis, const int2* __restrict__ mel_range, float bn_scale, float bn_shift,
-                    float* __restrict__ mel_out, __half* __restrict__ img, int n_frames) {
+                    float* __restrict__ mel_out, __half* __restrict__ img, int n_frames, int img_pitch, int img_c) {
   __shared__ float re[kNfft], im[kNfft];
   __shared__ float2 tw[kNfft / 2];
   __shared__ float mag[kBins + 3];
@@ -68,22 +68,21 @@ rmvpe_logmel_kernel(const float* __restrict__ audio, long long n, const float* _
     if (mel_out && j < n_frames) mel_out[(size_t)tid * n_frames + j] = lm;
     if (img) {
       const __half h = __float2half_rn(fmaf(lm, bn_scale, bn_shift));                           // Encoder.bn, rmvpe.py:299
-      uint4 o = make_uint4((uint32_t)__half_as_ushort(h), 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(img + ((size_t)j * (kMels + 1) + tid) * kImgC) = o;
+      img[((size_t)j * img_pitch + tid) * img_c] = h;                                          // channel 0; the rest stays zero
     }
   }
 }
 
 // `mel2hidden` called with a caller-supplied log-mel (rmvpe.py:591-608): mel fp32 [128][n_frames] -> the same image as above
 __global__ void rmvpe_mel_to_img_kernel(const float* __restrict__ mel, __half* __restrict__ img, int n_frames, int frames_out,
-                                        float bn_scale, float bn_shift) {
+                                        float bn_scale, float bn_shift, int img_pitch, int img_c) {
   const long long total = (long long)frames_out * kMels;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(idx % kMels);
     const int j = (int)(idx / kMels);
     const int src = j < n_frames ? j : 2 * n_frames - 2 - j;
     const __half h = __float2half_rn(fmaf(mel[(size_t)m * n_frames + src], bn_scale, bn_shift));
-    *reinterpret_cast<uint4*>(img + ((size_t)j * (kMels + 1) + m) * kImgC) = make_uint4((uint32_t)__half_as_ushort(h), 0u, 0u, 0u);
+    img[((size_t)j * img_pitch + m) * img_c] = h;
   }
 }
 
@@ -93,19 +92,21 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// x fp32 [2 H2][2 W2 + 1][C] (ldx floats per pixel) -> y fp16 [H2][W2 + 1][C]; the pad pixel of y is written as zero
-__global__ void rmvpe_pool_kernel(const float* __restrict__ x, int ldx, __half* __restrict__ y, int H2, int W2, int C) {
+// x fp32 [2 H2][p_in pixels][C] (ldx floats per pixel) -> y fp16 [H2][p_out pixels][C]; pixels [W2, p_out) of a line of y (its
+// zero padding) are written as zero
+__global__ void rmvpe_pool_kernel(const float* __restrict__ x, int ldx, __half* __restrict__ y, int H2, int W2, int C, int p_in,
+                                  int p_out) {
   const int c8n = C / 8;
-  const long long total = (long long)H2 * (W2 + 1) * c8n;
+  const long long total = (long long)H2 * p_out * c8n;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int c8 = (int)(idx % c8n);
     const long long px = idx / c8n;
-    const int ox = (int)(px % (W2 + 1));
-    const long long oy = px / (W2 + 1);
+    const int ox = (int)(px % p_out);
+    const long long oy = px / p_out;
     uint4 o = make_uint4(0, 0, 0, 0);
     if (ox < W2) {
-      const float* p00 = x + ((size_t)(2 * oy) * (2 * W2 + 1) + 2 * ox) * ldx + c8 * 8;
-      const float* p10 = p00 + (size_t)(2 * W2 + 1) * ldx;
+      const float* p00 = x + ((size_t)(2 * oy) * p_in + 2 * ox) * ldx + c8 * 8;
+      const float* p10 = p00 + (size_t)p_in * ldx;
       float v[8];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -122,8 +123,11 @@ __global__ void rmvpe_pool_kernel(const float* __restrict__ x, int ldx, __half* 
   }
 }
 
-// g fp16 [H][W + 1][4][Co] (phase = py * 2 + px) -> out fp16 [2 H][2 W + 1][ld] channels [0, Co): out[2y+py][2x+px] = g[y][x][phase]
-__global__ void rmvpe_shuffle_kernel(const __half* __restrict__ g, __half* __restrict__ out, int H, int W, int Co, int ld) {
+// g fp16 [H][p_in pixels][4][Co] (phase = py * 2 + px) -> the up-sampled half of the decoder's concat buffer: output pixel
+// (2y + py, 2x + px) lives in row (2y + py) * fp_out + (2x + px) / pack of `out` (row stride ld), columns ((2x + px) % pack) * Co ..
+// (pack = pixels per 64-channel row of the wide levels, 1 elsewhere)
+__global__ void rmvpe_shuffle_kernel(const __half* __restrict__ g, __half* __restrict__ out, int H, int W, int Co, int ld, int p_in,
+                                     int fp_out, int pack) {
   const int c8n = Co / 8;
   const long long total = (long long)H * W * 4 * c8n;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -132,20 +136,21 @@ __global__ void rmvpe_shuffle_kernel(const __half* __restrict__ g, __half* __res
     const int ph = (int)(r & 3); r >>= 2;
     const int x = (int)(r % W);
     const long long y = r / W;
-    const uint4 v = *reinterpret_cast<const uint4*>(g + (((size_t)y * (W + 1) + x) * 4 + ph) * Co + c8 * 8);
-    const size_t orow = (size_t)(2 * y + (ph >> 1)) * (2 * W + 1) + 2 * x + (ph & 1);
-    *reinterpret_cast<uint4*>(out + orow * ld + c8 * 8) = v;
+    const uint4 v = *reinterpret_cast<const uint4*>(g + (((size_t)y * p_in + x) * 4 + ph) * Co + c8 * 8);
+    const int ox = 2 * x + (ph & 1);
+    const size_t orow = (size_t)(2 * y + (ph >> 1)) * fp_out + ox / pack;
+    *reinterpret_cast<uint4*>(out + orow * ld + (size_t)(ox % pack) * Co + c8 * 8) = v;
   }
 }
 
-// cnn output fp32 [T][W + 1][ldc] (channels 0..2) -> GRU operand fp16 [T][3 W], column c * W + w (rmvpe.py:468 transpose + flatten)
-__global__ void rmvpe_gru_pack_kernel(const float* __restrict__ y, int ldc, __half* __restrict__ x16, long long T, int W) {
+// cnn output fp32 [T][pitch pixels][ldc] (channels 0..2) -> GRU operand fp16 [T][3 W], column c * W + w (rmvpe.py:468 transpose + flatten)
+__global__ void rmvpe_gru_pack_kernel(const float* __restrict__ y, int ldc, __half* __restrict__ x16, long long T, int W, int pitch) {
   const long long total = T * 3 * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int w = (int)(idx % W);
     const int c = (int)((idx / W) % 3);
     const long long t = idx / (3 * W);
-    x16[idx] = __float2half_rn(y[((size_t)t * (W + 1) + w) * ldc + c]);
+    x16[idx] = __float2half_rn(y[((size_t)t * pitch + w) * ldc + c]);
   }
 }
 
@@ -333,37 +338,40 @@ inline unsigned blocks_for(long long total, int threads, int cap = 148 * 16) {
 
 cudaError_t launch_rmvpe_logmel(const float* audio, long long n, const float* window, const void* twiddle, const float* mel_basis,
                                 const void* mel_range, float bn_scale, float bn_shift, float* mel_out, void* img, int n_frames,
-                                int frames_out, cudaStream_t st) {
+                                int frames_out, int img_pitch, int img_c, cudaStream_t st) {
   if (!audio || !window || !twiddle || !mel_basis || !mel_range || n <= kNfft / 2 || n_frames != (int)(n / kHop) + 1 ||
-      frames_out < n_frames || frames_out > 2 * n_frames - 1 || (!mel_out && !img))
+      frames_out < n_frames || frames_out > 2 * n_frames - 1 || (!mel_out && !img) || (img && (img_pitch < kMels || img_c < 1)))
     return cudaErrorInvalidValue;
   rmvpe_logmel_kernel<<<frames_out, 256, 0, st>>>(audio, n, window, reinterpret_cast<const float2*>(twiddle), mel_basis,
                                                   reinterpret_cast<const int2*>(mel_range), bn_scale, bn_shift, mel_out,
-                                                  reinterpret_cast<__half*>(img), n_frames);
+                                                  reinterpret_cast<__half*>(img), n_frames, img_pitch, img_c);
   launch_counter().n++;
   return cudaGetLastError();
 }
 
-cudaError_t launch_rmvpe_pool(const float* x, int ldx, void* y16, int H2, int W2, int C, cudaStream_t st) {
-  if (!x || !y16 || H2 < 1 || W2 < 1 || C % 8 != 0 || ldx % 4 != 0 || ldx < C) return cudaErrorInvalidValue;
-  const long long total = (long long)H2 * (W2 + 1) * (C / 8);
-  rmvpe_pool_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, reinterpret_cast<__half*>(y16), H2, W2, C);
+cudaError_t launch_rmvpe_pool(const float* x, int ldx, void* y16, int H2, int W2, int C, int p_in, int p_out, cudaStream_t st) {
+  if (!x || !y16 || H2 < 1 || W2 < 1 || C % 8 != 0 || ldx % 4 != 0 || ldx < C || p_in < 2 * W2 || p_out < W2) return cudaErrorInvalidValue;
+  const long long total = (long long)H2 * p_out * (C / 8);
+  rmvpe_pool_kernel<<<blocks_for(total, 256), 256, 0, st>>>(x, ldx, reinterpret_cast<__half*>(y16), H2, W2, C, p_in, p_out);
   launch_counter().n++;
   return cudaGetLastError();
 }
 
-cudaError_t launch_rmvpe_shuffle(const void* g16, void* out16, int H, int W, int Co, int ld, cudaStream_t st) {
-  if (!g16 || !out16 || H < 1 || W < 1 || Co % 8 != 0 || ld % 8 != 0 || ld < Co) return cudaErrorInvalidValue;
+cudaError_t launch_rmvpe_shuffle(const void* g16, void* out16, int H, int W, int Co, int ld, int p_in, int fp_out, int pack,
+                                 cudaStream_t st) {
+  if (!g16 || !out16 || H < 1 || W < 1 || Co % 8 != 0 || ld % 8 != 0 || pack < 1 || ld < pack * Co || p_in < W || (2 * W) % pack != 0 ||
+      fp_out < 2 * W / pack)
+    return cudaErrorInvalidValue;
   const long long total = (long long)H * W * 4 * (Co / 8);
   rmvpe_shuffle_kernel<<<blocks_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __half*>(g16), reinterpret_cast<__half*>(out16),
-                                                               H, W, Co, ld);
+                                                               H, W, Co, ld, p_in, fp_out, pack);
   launch_counter().n++;
   return cudaGetLastError();
 }
 
-cudaError_t launch_rmvpe_gru_pack(const float* y, int ldc, void* x16, long long T, int W, cudaStream_t st) {
-  if (!y || !x16 || T < 1 || W < 1 || ldc < 3) return cudaErrorInvalidValue;
-  rmvpe_gru_pack_kernel<<<blocks_for(T * 3 * W, 256), 256, 0, st>>>(y, ldc, reinterpret_cast<__half*>(x16), T, W);
+cudaError_t launch_rmvpe_gru_pack(const float* y, int ldc, void* x16, long long T, int W, int pitch, cudaStream_t st) {
+  if (!y || !x16 || T < 1 || W < 1 || ldc < 3 || pitch < W) return cudaErrorInvalidValue;
+  rmvpe_gru_pack_kernel<<<blocks_for(T * 3 * W, 256), 256, 0, st>>>(y, ldc, reinterpret_cast<__half*>(x16), T, W, pitch);
   launch_counter().n++;
   return cudaGetLastError();
 }
@@ -377,10 +385,11 @@ cudaError_t launch_rmvpe_gru(const float* gi, const float* w_hh, const float* b_
 }
 
 cudaError_t launch_rmvpe_mel_to_img(const float* mel, void* img, int n_frames, int frames_out, float bn_scale, float bn_shift,
-                                    cudaStream_t st) {
-  if (!mel || !img || n_frames < 1 || frames_out < n_frames || frames_out > 2 * n_frames - 1) return cudaErrorInvalidValue;
+                                    int img_pitch, int img_c, cudaStream_t st) {
+  if (!mel || !img || n_frames < 1 || frames_out < n_frames || frames_out > 2 * n_frames - 1 || img_pitch < kMels || img_c < 1)
+    return cudaErrorInvalidValue;
   rmvpe_mel_to_img_kernel<<<blocks_for((long long)frames_out * kMels, 256), 256, 0, st>>>(mel, reinterpret_cast<__half*>(img), n_frames,
-                                                                                         frames_out, bn_scale, bn_shift);
+                                                                                         frames_out, bn_scale, bn_shift, img_pitch, img_c);
   launch_counter().n++;
   return cudaGetLastError();
 }

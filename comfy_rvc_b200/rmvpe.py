@@ -9,8 +9,11 @@ Drop-in for the reference's `RMVPE` class (/root/reference/lib/rmvpe.py:559-684)
 Host code is Python like the reference's; every FLOP runs in librvcb200.so through the C ABI (include/rvcb200.h):
   * log-mel (`MelSpectrogram`, rmvpe.py:476-556) + the model's input BatchNorm + `mel2hidden`'s reflect padding of the frame
     axis: `rvcb200_op_rmvpe_logmel` (one FFT per frame in shared memory) -> fp16 image;
-  * DeepUnet (rmvpe.py:232-428): images are channels-last fp16, a line = W + 1 pixels (the last one zero), so a 3 x 3 convolution
-    is a 9-tap row-offset contraction on the generic tcgen05 implicit-GEMM kernel (`rvcb200_op_conv_tc`, `tap_w` / `dil2`); the
+  * DeepUnet (rmvpe.py:232-428): images are channels-last fp16, a line = W pixels + zero padding, so a 3 x 3 convolution
+    is a 9-tap row-offset contraction on the generic tcgen05 implicit-GEMM kernel (`rvcb200_op_conv_tc`, `tap_w` / `dil2`).  On the
+    two wide levels (16 / 32 channels) `pack` = 4 / 2 neighbouring pixels form ONE 64-channel GEMM row and the weights become
+    block-Toeplitz (out pixel j of a row reads in pixel i of the rows left / same / right with kernel column 4 fdx + i - j): a TMA box
+    row then carries 128 useful bytes instead of 32 and a tile covers 512 instead of 128 pixels (L0 convolutions 97 -> ~35 us).  The
     eval-mode BatchNorms are folded into the convolution weights and biases at load, ReLU and the residual add sit in the epilogue,
     the residual stream stays fp32, `torch.cat` is a channel offset into one buffer, ConvTranspose2d(stride 2) is a 2 x 2-tap GEMM
     over (phase, channel) columns + `rvcb200_op_rmvpe_shuffle`, AvgPool2d is `rvcb200_op_rmvpe_pool`;
@@ -37,7 +40,7 @@ PADF = 32
 N_FFT, HOP, N_MELS, N_BINS, SR, FMIN, FMAX = 1024, 160, 128, 513, 16000, 30.0, 8000.0
 N_CLASS, N_CLASS_PAD = 360, 384
 BN_EPS = 1e-5
-IMG_C = 8                     # channels of the input image (1 real + zero padding: TMA rows are multiples of 16 bytes)
+ROW_C = 64                    # channels of a GEMM row on the wide levels: `pack` = ROW_C / C pixels per row
 
 
 def mel_filterbank(sr=SR, n_fft=N_FFT, n_mels=N_MELS, fmin=FMIN, fmax=FMAX) -> np.ndarray:
@@ -111,40 +114,77 @@ class RMVPE:
             self._build_host()
         self._w = {k: v.to(self.device).contiguous() for k, v in self._host.items()}
 
+    # ---- image geometry ----------------------------------------------------------------------------------------------------
+    def _pack(self, level: int) -> int:
+        """Pixels per GEMM row at a level (levels 0.. = encoder / decoder, n_levels = intermediate)."""
+        c = self.c0 << level
+        return ROW_C // c if c < ROW_C else 1
+
+    @property
+    def _img_c(self) -> int:
+        """Channels of the input image (1 real + zeros): one GEMM row of level 0 has ROW_C of them (>= 8: 16-byte TMA rows)."""
+        return max(8, ROW_C // self._pack(0)) if self._pack(0) > 1 else 8
+
+    def _geom(self, level: int, Tp: int):
+        """(C, lines H, pixels per line W, pack, pixel pitch P = W + pack, rows per line FP = W / pack + 1, rows)."""
+        c, Wd, H, pk = self.c0 << level, N_MELS >> level, Tp >> level, self._pack(level)
+        return c, H, Wd, pk, Wd + pk, Wd // pk + 1, H * (Wd // pk + 1)
+
     def _build_host(self):
         """Weight-norm-free model: fold the BatchNorms, re-lay the kernels as tap matrices (CPU tensors; `_materialize` uploads)."""
         sd = self._sd
         W: Dict[str, torch.Tensor] = {}
         f32 = lambda t: t.to(torch.float32).contiguous()
 
-        def conv3(name, w, b):                                    # [Co][Ci][3][3] -> taps [9][Ci][Co] (tap = ky * 3 + kx)
+        def krows(i, ci, pack, cat_c):
+            """GEMM-row channel indices of pixel i's ci input channels.  Plain images: pixel-major.  The decoder's concat buffer
+            keeps the up-sampled and the skip half of a row side by side ([pack x C up | pack x C skip]) so that the encoder's
+            epilogue can write its half as one column range."""
+            if cat_c is None:
+                return i * ci + torch.arange(ci)
+            c = torch.arange(ci)
+            return (c // cat_c) * pack * cat_c + i * cat_c + (c % cat_c)
+
+        def conv3(name, w, b, pack=1, cat_c=None):                # [Co][Ci][3][3] -> taps [9][pack Ci][pack Co]
             co, ci = w.shape[:2]
-            t = w.permute(2, 3, 1, 0).reshape(9, ci, co)
-            if ci % 8:                                            # the 1-channel input image is stored with 8 channels
-                t = torch.cat([t, t.new_zeros(9, 8 - ci % 8, co)], dim=1)
+            if ci == 1:                                           # the 1-channel input image is stored with _img_c channels
+                w = torch.cat([w, w.new_zeros(co, self._img_c - 1, 3, 3)], dim=1)
+                ci = self._img_c
             if co % 16:                                           # cnn: 3 output channels -> 16 columns
-                t = torch.cat([t, t.new_zeros(9, t.shape[1], 16 - co % 16)], dim=2)
+                w = torch.cat([w, w.new_zeros(16 - co % 16, ci, 3, 3)], dim=0)
                 b = torch.cat([b, b.new_zeros(16 - co % 16)])
-            self._src[name + ".w"], W[name + ".b"] = t.contiguous(), f32(b)
+                co = w.shape[0]
+            t = torch.zeros(9, pack * ci, pack * co)
+            for ky in range(3):
+                for fdx in (-1, 0, 1):                            # GEMM row to the left / same / right
+                    for i in range(pack):                         # input pixel inside that row
+                        for j in range(pack):                     # output pixel inside this row
+                            dx = pack * fdx + i - j
+                            if -1 <= dx <= 1:
+                                t[ky * 3 + fdx + 1, krows(i, ci, pack, cat_c), j * co:(j + 1) * co] = w[:, :, ky, dx + 1].t()
+            self._src[name + ".w"], W[name + ".b"] = t.contiguous(), f32(b.repeat(pack))
 
-        def conv1(name, w, b):                                    # 1 x 1 shortcut: [Co][Ci][1][1] -> [1][Ci][Co]
+        def conv1(name, w, b, pack=1, cat_c=None):                # 1 x 1 shortcut: [Co][Ci][1][1] -> [1][pack Ci][pack Co]
             co, ci = w.shape[:2]
-            t = w[:, :, 0, 0].t()[None]
-            if ci % 8:
-                t = torch.cat([t, t.new_zeros(1, 8 - ci % 8, co)], dim=1)
-            self._src[name + ".w"], W[name + ".b"] = t.contiguous(), f32(b)
+            if ci == 1:
+                w = torch.cat([w, w.new_zeros(co, self._img_c - 1, 1, 1)], dim=1)
+                ci = self._img_c
+            t = torch.zeros(1, pack * ci, pack * co)
+            for i in range(pack):
+                t[0, krows(i, ci, pack, cat_c), i * co:(i + 1) * co] = w[:, :, 0, 0].t()
+            self._src[name + ".w"], W[name + ".b"] = t.contiguous(), f32(b.repeat(pack))
 
-        def block(p):                                             # ConvBlockRes, rmvpe.py:232-267
+        def block(p, pack=1, cat_c=None):                         # ConvBlockRes, rmvpe.py:232-267
             w1, b1 = self._fold_bn(sd[p + "conv.0.weight"], p + "conv.1.")
             w2, b2 = self._fold_bn(sd[p + "conv.3.weight"], p + "conv.4.")
-            conv3(p + "c1", w1, b1)
-            conv3(p + "c2", w2, b2)
+            conv3(p + "c1", w1, b1, pack, cat_c)
+            conv3(p + "c2", w2, b2, pack)
             if p + "shortcut.weight" in sd:
-                conv1(p + "sc", sd[p + "shortcut.weight"], sd[p + "shortcut.bias"])
+                conv1(p + "sc", sd[p + "shortcut.weight"], sd[p + "shortcut.bias"], pack, cat_c)
 
         for i in range(self.n_levels):
             for j in range(self.n_blocks):
-                block(f"unet.encoder.layers.{i}.conv.{j}.")
+                block(f"unet.encoder.layers.{i}.conv.{j}.", self._pack(i))
         for i in range(self.n_inter):
             for j in range(self.n_blocks):
                 block(f"unet.intermediate.layers.{i}.conv.{j}.")
@@ -162,9 +202,10 @@ class RMVPE:
                             if 0 <= ky <= 2 and 0 <= kx <= 2:
                                 t[dy * 2 + dx, :, (py * 2 + px) * co:(py * 2 + px + 1) * co] = wt[:, :, ky, kx]
             self._src[p + "up.w"], W[p + "up.b"] = t, f32(bt.repeat(4))
+            lvl = self.n_levels - 1 - i
             for j in range(self.n_blocks):
-                block(p + f"conv2.{j}.")
-        conv3("cnn", sd["cnn.weight"], sd["cnn.bias"])
+                block(p + f"conv2.{j}.", self._pack(lvl), cat_c=co if j == 0 else None)
+        conv3("cnn", sd["cnn.weight"], sd["cnn.bias"], self._pack(0))
         g = "fc.0.gru."
         self._src["gru.ih.w"] = torch.cat([sd[g + "weight_ih_l0"].t(), sd[g + "weight_ih_l0_reverse"].t()], dim=1)[None].contiguous()
         W["gru.ih.b"] = f32(torch.cat([sd[g + "bias_ih_l0"], sd[g + "bias_ih_l0_reverse"]]))
@@ -289,57 +330,62 @@ class RMVPE:
 
     # ---- the model -------------------------------------------------------------------------------------------------------
     def _hidden_from_img(self, img: torch.Tensor, Tp: int, taps: Optional[dict] = None):
-        """img fp16 [Tp][129][8] -> (logits fp32 [Tp][384] on the device).  Tp a multiple of 32."""
+        """img fp16 [Tp][P0][img_c] -> (logits fp32 [Tp][384] on the device).  Tp a multiple of 32.
+        Every image is [H][P pixels][C] in memory; the convolutions see it as [H][FP rows][pack C] (see _geom)."""
         lib, Wt, dev = _lib.load(), self._w, self.device
         cats = []
         own = img                               # owner of the memory behind x16 (see _block)
-        x16, ldx, cin, x32 = img.data_ptr(), IMG_C, IMG_C, None
-        H, Wd = Tp, N_MELS
+        x16, x32 = img.data_ptr(), None
+        cin_pix = self._img_c                   # channels per pixel of the tensor behind x16
         for i in range(self.n_levels):                                        # Encoder, rmvpe.py:296-305
-            c = self.c0 << i
-            rows = H * (Wd + 1)
-            cat = torch.zeros(rows, 2 * c, dtype=torch.float16, device=dev)  # [0, c): decoder's up-sampled half; [c, 2c): skip
+            c, H, Wd, pk, P, FP, rows = self._geom(i, Tp)
+            cf = pk * c
+            cat = torch.zeros(rows, 2 * cf, dtype=torch.float16, device=dev)  # per row: [pk x c up-sampled | pk x c skip]
             cats.append(cat)
             for j in range(self.n_blocks):
                 last = j == self.n_blocks - 1
-                x32, x16, ldx, own = self._block(f"unet.encoder.layers.{i}.conv.{j}.", x16, ldx, cin, x32, c, H, Wd,
-                                                 out16=cat.data_ptr() + 2 * c if last else 0, ld_out16=2 * c if last else 0)
-                cin = c
-            pooled = torch.empty((H // 2) * (Wd // 2 + 1), c, dtype=torch.float16, device=dev)
-            self._check(lib.rvcb200_op_rmvpe_pool(C.c_void_p(x32.data_ptr()), c, C.c_void_p(pooled.data_ptr()), H // 2, Wd // 2, c,
+                x32, x16, ldx, own = self._block(f"unet.encoder.layers.{i}.conv.{j}.", x16, pk * cin_pix, pk * cin_pix, x32, cf, H, FP - 1,
+                                                 out16=cat.data_ptr() + 2 * cf if last else 0, ld_out16=2 * cf if last else 0)
+                cin_pix = c
+            _, H2, W2, _, P2, _, _ = self._geom(i + 1, Tp)
+            pooled = torch.empty(H2 * P2, c, dtype=torch.float16, device=dev)
+            self._check(lib.rvcb200_op_rmvpe_pool(C.c_void_p(x32.data_ptr()), c, C.c_void_p(pooled.data_ptr()), H2, W2, c, P, P2,
                                                   self._stream), "rvcb200_op_rmvpe_pool")
-            x16, ldx, x32, own = pooled.data_ptr(), c, None, pooled
-            H, Wd = H // 2, Wd // 2
-        c = self.c0 << self.n_levels
+            x16, x32, own = pooled.data_ptr(), None, pooled
+        c, H, Wd, pk, P, FP, rows = self._geom(self.n_levels, Tp)
         if taps is not None:
             taps["enc16"] = pooled
         for i in range(self.n_inter):                                         # Intermediate, rmvpe.py:343-347
             for j in range(self.n_blocks):
-                x32, x16, ldx, own = self._block(f"unet.intermediate.layers.{i}.conv.{j}.", x16, ldx, cin, x32, c, H, Wd)
-                cin = c
+                x32, x16, ldx, own = self._block(f"unet.intermediate.layers.{i}.conv.{j}.", x16, cin_pix, cin_pix, x32, c, H, FP - 1)
+                cin_pix = c
         if taps is not None:
             taps["inter32"] = x32
         for i in range(self.n_levels):                                        # Decoder, rmvpe.py:389-392, 371-377
             p = f"unet.decoder.layers.{i}."
-            co = cin // 2
-            rows_in = H * (Wd + 1)
-            g16 = torch.empty(rows_in, 4 * co, dtype=torch.float16, device=dev)
-            self._conv(x16, rows_in, cin, ldx, p + "up", 4 * co, Wd, taps=4, relu=True, y16=g16.data_ptr(), ldy16=4 * co, mask=False)
+            _, Hi, Wi, _, Pi, _, _ = self._geom(self.n_levels - i, Tp)        # the level the input lives on (pixel rows here)
+            c, H, Wd, pk, P, FP, rows = self._geom(self.n_levels - 1 - i, Tp)
+            cf = pk * c
+            rows_in = Hi * Pi
+            g16 = torch.empty(rows_in, 4 * c, dtype=torch.float16, device=dev)
+            self._conv(x16, rows_in, cin_pix, cin_pix, p + "up", 4 * c, Pi - 1, taps=4, relu=True, y16=g16.data_ptr(), ldy16=4 * c,
+                       mask=False)
             cat = cats[self.n_levels - 1 - i]
-            self._check(lib.rvcb200_op_rmvpe_shuffle(C.c_void_p(g16.data_ptr()), C.c_void_p(cat.data_ptr()), H, Wd, co, 2 * co,
+            self._check(lib.rvcb200_op_rmvpe_shuffle(C.c_void_p(g16.data_ptr()), C.c_void_p(cat.data_ptr()), Hi, Wi, c, 2 * cf, Pi, FP, pk,
                                                      self._stream), "rvcb200_op_rmvpe_shuffle")
-            H, Wd = H * 2, Wd * 2
-            x16, ldx, cin, x32, own = cat.data_ptr(), 2 * co, 2 * co, None, cat
+            x16, x32, own = cat.data_ptr(), None, cat
+            cin_f = 2 * cf
             for j in range(self.n_blocks):
-                x32, x16, ldx, own = self._block(p + f"conv2.{j}.", x16, ldx, cin, x32, co, H, Wd)
-                cin = co
+                x32, x16, ldx, own = self._block(p + f"conv2.{j}.", x16, cin_f, cin_f, x32, cf, H, FP - 1)
+                cin_f = cf
+            cin_pix = c
         if taps is not None:
             taps["unet32"] = x32
-        rows = H * (Wd + 1)
-        cnn32 = torch.empty(rows, 16, dtype=torch.float32, device=dev)       # cnn, rmvpe.py:450, 468
-        self._conv(x16, rows, cin, ldx, "cnn", 16, Wd, taps=9, relu=False, y32=cnn32.data_ptr(), ldy32=16)
+        c, H, Wd, pk, P, FP, rows = self._geom(0, Tp)
+        cnn32 = torch.empty(rows, pk * 16, dtype=torch.float32, device=dev)  # cnn, rmvpe.py:450, 468: [H][P][16], channels 0..2
+        self._conv(x16, rows, pk * c, pk * c, "cnn", pk * 16, FP - 1, taps=9, relu=False, y32=cnn32.data_ptr(), ldy32=pk * 16)
         gx16 = torch.empty(Tp, 3 * N_MELS, dtype=torch.float16, device=dev)
-        self._check(lib.rvcb200_op_rmvpe_gru_pack(C.c_void_p(cnn32.data_ptr()), 16, C.c_void_p(gx16.data_ptr()), Tp, N_MELS,
+        self._check(lib.rvcb200_op_rmvpe_gru_pack(C.c_void_p(cnn32.data_ptr()), 16, C.c_void_p(gx16.data_ptr()), Tp, N_MELS, P,
                                                   self._stream), "rvcb200_op_rmvpe_gru_pack")
         if taps is not None:
             taps["gru_in16"] = gx16
@@ -395,7 +441,7 @@ class RMVPE:
         self._stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _logmel(self, audio: torch.Tensor, want_mel: bool, want_img: bool):
-        """audio fp32 [n] on the device -> (mel fp32 [128][n_frames] | None, img fp16 [Tp][129][8] | None, n_frames, Tp)."""
+        """audio fp32 [n] on the device -> (mel fp32 [128][n_frames] | None, img fp16 [Tp][P0][img_c] | None, n_frames, Tp)."""
         lib, Wt, dev = _lib.load(), self._w, self.device
         n = int(audio.shape[0])
         if n <= N_FFT // 2:
@@ -403,12 +449,14 @@ class RMVPE:
         n_frames = n // HOP + 1
         Tp = self._padded_frames(n_frames) if want_img else n_frames
         mel = torch.empty(N_MELS, n_frames, dtype=torch.float32, device=dev) if want_mel else None
-        img = torch.zeros(Tp, N_MELS + 1, IMG_C, dtype=torch.float16, device=dev) if want_img else None
+        P0 = N_MELS + self._pack(0)
+        img = torch.zeros(Tp, P0, self._img_c, dtype=torch.float16, device=dev) if want_img else None
         self._check(lib.rvcb200_op_rmvpe_logmel(C.c_void_p(audio.data_ptr()), n, C.c_void_p(Wt["mel.window"].data_ptr()),
                                                 C.c_void_p(Wt["mel.twiddle"].data_ptr()), C.c_void_p(Wt["mel.basis"].data_ptr()),
                                                 C.c_void_p(Wt["mel.range"].data_ptr()), self._bn_scale, self._bn_shift,
                                                 C.c_void_p(mel.data_ptr()) if want_mel else None,
-                                                C.c_void_p(img.data_ptr()) if want_img else None, n_frames, Tp, self._stream),
+                                                C.c_void_p(img.data_ptr()) if want_img else None, n_frames, Tp, P0, self._img_c,
+                                                self._stream),
                     "rvcb200_op_rmvpe_logmel")
         return mel, img, n_frames, Tp
 
@@ -438,9 +486,11 @@ class RMVPE:
             m = mel[0].to(dev, torch.float32).contiguous()
             n_frames = int(m.shape[1])
             Tp = self._padded_frames(n_frames)
-            img = torch.zeros(Tp, N_MELS + 1, IMG_C, dtype=torch.float16, device=dev)
+            P0 = N_MELS + self._pack(0)
+            img = torch.zeros(Tp, P0, self._img_c, dtype=torch.float16, device=dev)
             self._check(lib.rvcb200_op_rmvpe_mel_to_img(C.c_void_p(m.data_ptr()), C.c_void_p(img.data_ptr()), n_frames, Tp,
-                                                        self._bn_scale, self._bn_shift, self._stream), "rvcb200_op_rmvpe_mel_to_img")
+                                                        self._bn_scale, self._bn_shift, P0, self._img_c, self._stream),
+                        "rvcb200_op_rmvpe_mel_to_img")
             logits = self._hidden_from_img(img, Tp, taps)
             hidden = torch.empty(n_frames, N_CLASS, dtype=torch.float32, device=dev)
             f0 = torch.empty(n_frames, dtype=torch.float64, device=dev)

@@ -318,26 +318,31 @@ int rvcb200_op_quiet_point(const double* audio_pad, int64_t lo, int64_t hi, int3
 /* ---- RMVPE f0 estimator (host orchestration in comfy_rvc_b200/rmvpe.py) ----
  * Replaces the torch modules of /root/reference/lib/rmvpe.py as reached from pitch_extraction.py:191-201.  The DeepUnet's
  * convolutions, the GRU input projection and the output Linear run through rvcb200_op_conv_tc (2-D taps); these entries are
- * what is left.  Images are fp16 channels-last, stored as lines of W + 1 pixels whose last pixel is zero. */
+ * what is left.  Images are fp16 channels-last, stored as lines of `pitch` >= W + 1 pixels; pixels [W, pitch) of a line are zero
+ * (they are the left / right border of the 3 x 3 convolutions).  On the wide levels (C < 64) the host views `pack` = 64 / C pixels
+ * as ONE 64-channel row (pitch = W + pack) and runs the convolutions with block-Toeplitz weights: 4x / 2x fewer TMA box rows. */
 
 /* `MelSpectrogram.forward` (rmvpe.py:489-556; n_fft 1024, hop 160, 128 HTK mel filters 30-8000 Hz, log(clamp 1e-5)) of
  * audio[n] (16 kHz, n > 512), n_frames = n / 160 + 1.  window[1024]: periodic Hann; twiddle[512][2]: (cos, -sin)(2 pi i / 1024);
  * mel_basis[128][513]; mel_range[128][2]: first / one-past-last non-zero bin of each filter.  Outputs (either may be NULL):
- * mel_out fp32 [128][n_frames]; img16 fp16 [frames_out][129][8], channel 0 = mel * bn_scale + bn_shift (`Encoder.bn`,
+ * mel_out fp32 [128][n_frames]; img16 fp16 [frames_out][img_pitch][img_c], channel 0 = mel * bn_scale + bn_shift (`Encoder.bn`,
  * rmvpe.py:299), frames n_frames.. = the reflect padding of `mel2hidden` (rmvpe.py:594-595); img16 must be zero-initialised. */
 int rvcb200_op_rmvpe_logmel(const float* audio, int64_t n, const float* window, const float* twiddle, const float* mel_basis,
                             const int32_t* mel_range, float bn_scale, float bn_shift, float* mel_out, void* img16, int32_t n_frames,
-                            int32_t frames_out, void* stream);
+                            int32_t frames_out, int32_t img_pitch, int32_t img_c, void* stream);
 
-/* AvgPool2d((2, 2)) (rmvpe.py:318): x32 fp32 [2 H2][2 W2 + 1][ldx] -> y16 fp16 [H2][W2 + 1][C] (pad pixel zero). */
-int rvcb200_op_rmvpe_pool(const float* x32, int32_t ldx, void* y16, int32_t H2, int32_t W2, int32_t C, void* stream);
+/* AvgPool2d((2, 2)) (rmvpe.py:318): x32 fp32 [2 H2][p_in][ldx] -> y16 fp16 [H2][p_out][C] (pixels [W2, p_out) zero). */
+int rvcb200_op_rmvpe_pool(const float* x32, int32_t ldx, void* y16, int32_t H2, int32_t W2, int32_t C, int32_t p_in, int32_t p_out,
+                          void* stream);
 
 /* Scatter behind ConvTranspose2d(3 x 3, stride 2, padding 1, output_padding 1) (rmvpe.py:355-366) computed as a 2 x 2-tap GEMM
- * with (phase, channel) columns: g16 fp16 [H][W + 1][4][Co] -> out16 fp16 [2 H][2 W + 1][ld], channels [0, Co). */
-int rvcb200_op_rmvpe_shuffle(const void* g16, void* out16, int32_t H, int32_t W, int32_t Co, int32_t ld, void* stream);
+ * with (phase, channel) columns: g16 fp16 [H][p_in][4][Co] -> output pixel (oy, ox) = (2y + py, 2x + px) at row
+ * oy * fp_out + ox / pack of out16 (row stride ld), columns (ox % pack) * Co .. + Co (the up-sampled half of the concat buffer). */
+int rvcb200_op_rmvpe_shuffle(const void* g16, void* out16, int32_t H, int32_t W, int32_t Co, int32_t ld, int32_t p_in, int32_t fp_out,
+                             int32_t pack, void* stream);
 
-/* `x.transpose(1, 2).flatten(-2)` (rmvpe.py:468): y32 fp32 [T][W + 1][ldc] (channels 0..2) -> x16 fp16 [T][3 W], column c W + w. */
-int rvcb200_op_rmvpe_gru_pack(const float* y32, int32_t ldc, void* x16, int64_t T, int32_t W, void* stream);
+/* `x.transpose(1, 2).flatten(-2)` (rmvpe.py:468): y32 fp32 [T][pitch][ldc] (channels 0..2) -> x16 fp16 [T][3 W], column c W + w. */
+int rvcb200_op_rmvpe_gru_pack(const float* y32, int32_t ldc, void* x16, int64_t T, int32_t W, int32_t pitch, void* stream);
 
 /* Recurrence of nn.GRU(384, 256, bidirectional=True) (rmvpe.py:217-229): gi fp32 [T][2][3][256] = W_ih x + b_ih (gates r|z|n),
  * w_hh fp32 [2][768][256], b_hh fp32 [2][768] -> out16 fp16 [T][512] (forward | reverse), out32 the same in fp32 or NULL. */
@@ -351,7 +356,7 @@ int rvcb200_op_rmvpe_decode(const float* in, int32_t ld, int32_t from_hidden, fl
 
 /* `mel2hidden` called with a caller-supplied log-mel: mel fp32 [128][n_frames] -> the img16 of rvcb200_op_rmvpe_logmel. */
 int rvcb200_op_rmvpe_mel_to_img(const float* mel, void* img16, int32_t n_frames, int32_t frames_out, float bn_scale, float bn_shift,
-                                void* stream);
+                                int32_t img_pitch, int32_t img_c, void* stream);
 
 /* ---- host (CPU) side of the song-level driver (csrc/host_plan.cu) ---- */
 

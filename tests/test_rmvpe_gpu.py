@@ -234,10 +234,21 @@ def test_rmvpe_image_convolution_matches_torch(H, W, cin, cout, taps, a_mode):
         err = (up - want).abs().max().item()
         # the shuffle kernel scatters the same values into the decoder's concat buffer
         cat = torch.zeros(2 * H * (2 * W + 1), 2 * co, dtype=torch.float16, device="cuda")
-        assert lib.rvcb200_op_rmvpe_shuffle(C.c_void_p(y16.data_ptr()), C.c_void_p(cat.data_ptr()), H, W, co, 2 * co, stream()) == 0
+        assert lib.rvcb200_op_rmvpe_shuffle(C.c_void_p(y16.data_ptr()), C.c_void_p(cat.data_ptr()), H, W, co, 2 * co, Wp, 2 * W + 1, 1,
+                                            stream()) == 0
         torch.cuda.synchronize()
         c = cat.float().cpu().reshape(2 * H, 2 * W + 1, 2 * co)
         assert (c[:, :2 * W, :co] - up.half().float()).abs().max().item() == 0 and c[:, 2 * W].abs().max() == 0 and c[:, :, co:].abs().max() == 0
+        # ... and with `pack` pixels per row (the wide levels): row = [pack x co up-sampled | pack x co skip], W / pack + 1 rows per line
+        for pack in (2, 4):
+            fp = 2 * W // pack + 1
+            catp = torch.zeros(2 * H * fp, 2 * pack * co, dtype=torch.float16, device="cuda")
+            assert lib.rvcb200_op_rmvpe_shuffle(C.c_void_p(y16.data_ptr()), C.c_void_p(catp.data_ptr()), H, W, co, 2 * pack * co, Wp, fp,
+                                                pack, stream()) == 0
+            torch.cuda.synchronize()
+            cp = catp.float().cpu().reshape(2 * H, fp, 2 * pack * co)
+            got_up = cp[:, :2 * W // pack, :pack * co].reshape(2 * H, 2 * W, co)
+            assert (got_up - up.half().float()).abs().max().item() == 0 and cp[:, -1].abs().max() == 0 and cp[:, :, pack * co:].abs().max() == 0
     else:
         want = ref[0].permute(1, 2, 0) + res.reshape(H, Wp, cout)[:, :W]
         err = (got[:, :W] - want).abs().max().item()
@@ -253,12 +264,14 @@ def test_rmvpe_pool_matches_torch():
     g = torch.Generator().manual_seed(9)
     x = torch.randn(H, W + 1, Cn, generator=g)
     xd = x.cuda().contiguous()
-    y = torch.full((H // 2, W // 2 + 1, Cn), 5.0, dtype=torch.float16, device="cuda")
-    assert lib.rvcb200_op_rmvpe_pool(C.c_void_p(xd.data_ptr()), Cn, C.c_void_p(y.data_ptr()), H // 2, W // 2, Cn, stream()) == 0
-    torch.cuda.synchronize()
     want = F.avg_pool2d(x[:, :W].permute(2, 0, 1)[None], 2)[0].permute(1, 2, 0)
-    got = y.float().cpu()
-    assert (got[:, :W // 2] - want.half().float()).abs().max().item() <= 1e-3 and got[:, W // 2].abs().max().item() == 0
+    for p_out in (W // 2 + 1, W // 2 + 2, W // 2 + 4):                    # output line pitch: 1, 2 or 4 zero pixels behind the data
+        y = torch.full((H // 2, p_out, Cn), 5.0, dtype=torch.float16, device="cuda")
+        assert lib.rvcb200_op_rmvpe_pool(C.c_void_p(xd.data_ptr()), Cn, C.c_void_p(y.data_ptr()), H // 2, W // 2, Cn, W + 1, p_out,
+                                         stream()) == 0
+        torch.cuda.synchronize()
+        got = y.float().cpu()
+        assert (got[:, :W // 2] - want.half().float()).abs().max().item() <= 1e-3 and got[:, W // 2:].abs().max().item() == 0
 
 
 def test_rmvpe_feeds_the_pitch_pipeline():

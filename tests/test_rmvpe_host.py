@@ -31,8 +31,10 @@ def test_rmvpe_host_layout_reproduces_reference_fixture():
     n_frames = mel.shape[1]
     Tp = m._padded_frames(n_frames)
     src = [j if j < n_frames else 2 * n_frames - 2 - j for j in range(Tp)]
-    img = torch.zeros(Tp, 129, 8)
+    img = torch.zeros(Tp, 128 + m._pack(0), m._img_c)
     img[:, :128, 0] = (mel[:, src] * m._bn_scale + m._bn_shift).t()
+    assert m._pack(0) == 4 and m._pack(1) == 2 and m._pack(2) == 1 and m._img_c == 16
+    assert m._geom(0, 64) == (16, 64, 128, 4, 132, 33, 64 * 33) and m._geom(1, 64) == (32, 32, 64, 2, 66, 33, 32 * 33)
     hidden = torch.sigmoid(hidden_logits(m, img, Tp)[:n_frames, :360]).numpy()
     err = np.abs(hidden - gold["hidden"]).max()
     print(f"emulated device path vs reference: max |err| {err:.2e}")
