@@ -73,7 +73,7 @@ class TcConvDesc(C.Structure):
         ("inj_har", C.c_void_p), ("inj_w", C.c_void_p), ("inj_b", C.c_void_p),
         ("inj_k", C.c_int32), ("inj_s", C.c_int32), ("inj_pad", C.c_int32), ("inj_cn", C.c_int32), ("inj_Lhar", C.c_int64),
         ("gelu", C.c_int32), ("tap_w", C.c_int32), ("dil2", C.c_int32), ("pad_period", C.c_int32), ("pad_valid", C.c_int32),
-        ("b_group", C.c_int32),
+        ("b_group", C.c_int32), ("a_nt_stride", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 

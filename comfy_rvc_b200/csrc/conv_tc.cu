@@ -287,6 +287,9 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
         int mt, nt, g, b;
         decode((long long)blockIdx.x + (long long)t * gridDim.x, mt, nt, g, b);
         const int row0 = mt * BM + p.g_off[g];
+        // grouped convolutions (HuBERT's positional convolution: 16 groups of 48 channels): N tile nt reads its own input channels
+        // [nt * a_nt_stride, + Cin); what a 64-channel box reads beyond them meets the zero K padding of the weight image
+        const int ch0 = nt * p.a_nt_stride;
         int wrow = w_row(g, nt, 0, 0);
         if (SG > 1) {                     // grouped ring stages (slab modes, weights not resident)
           if (p.ntaps == 1) {             // a stage = SG consecutive k-blocks; their activation boxes first
@@ -295,7 +298,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
               for (int kk = 0; kk < cnt; ++kk) {
                 mbar_wait(&a_empty[sa], pa);
                 mbar_expect_tx(&a_full[sa], a_bytes);
-                tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, (kbg + kk) * KBLK, row0, b, &a_full[sa]);
+                tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, (kbg + kk) * KBLK + ch0, row0, b, &a_full[sa]);
                 if (++sa == NA) { sa = 0; pa ^= 1; }
               }
               mbar_wait(&b_empty[sb], pb);
@@ -309,7 +312,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
               for (int kh = 0; kh < KH; ++kh) {
                 mbar_wait(&a_empty[sa], pa);
                 mbar_expect_tx(&a_full[sa], a_bytes);
-                tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0 + kh * p.dil2, b, &a_full[sa]);
+                tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK + ch0, row0 + kh * p.dil2, b, &a_full[sa]);
                 if (++sa == NA) { sa = 0; pa ^= 1; }
                 for (int tg = 0; tg < TW; tg += SG) {
                   const int cnt = TW - tg < SG ? TW - tg : SG;
@@ -329,14 +332,14 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
           if (slab) {
             mbar_wait(&a_empty[sa], pa);
             mbar_expect_tx(&a_full[sa], a_bytes);
-            tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0 + kh * p.dil2, b, &a_full[sa]);
+            tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK + ch0, row0 + kh * p.dil2, b, &a_full[sa]);
             if (++sa == NA) { sa = 0; pa ^= 1; }
           }
           for (int tap = kh * TW; tap < kh * TW + TW; ++tap) {
             if (!slab) {
               mbar_wait(&a_empty[sa], pa);
               mbar_expect_tx(&a_full[sa], a_bytes);
-              tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK, row0 + tap_row_off(p, tap), b, &a_full[sa]);
+              tma_load_3d(slabA + (size_t)sa * a_stride, &tmA, kb * KBLK + ch0, row0 + tap_row_off(p, tap), b, &a_full[sa]);
               if (++sa == NA) { sa = 0; pa ^= 1; }
             }
             if (!stat) {
@@ -979,7 +982,7 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   TcConvDesc d = d_in;
   if (d.N < 16 || d.N > 256 || d.N % 16 != 0 || d.Cin % 8 != 0 || d.Cout_total % d.N != 0 || d.G < 1 || d.G > 16 ||
       d.Lj <= 0 || d.L_in <= 0 || (d.a_mode != 1 && slab_rows_halo(d) > 127) || tap_halo(d) < 0 || d.tap_w < 0 ||
-      d.a_mode < 0 || d.a_mode > 2 || (d.a_mode == 2 && d.tap_w <= 0) ||
+      d.a_mode < 0 || d.a_mode > 2 || (d.a_mode == 2 && d.tap_w <= 0) || d.a_nt_stride < 0 || (d.a_nt_stride > 0 && (!d.generic || d.G != 1)) ||
       (d.tap_w > 0 && (d.ntaps % d.tap_w != 0 || d.dil2 < (d.tap_w - 1) * d.dil)) || d.pad_period < 0 || (d.pad_period > 0 && !d.generic) || (d.accum && !d.y32) || B <= 0 || !d.x16 || !d.w16 ||
       d.a_fp16 || (d.res16 && d.res32) || (d.acc_f16 && (d.generic || d.Cout_total % 8)))
     return cudaErrorInvalidValue;
@@ -1056,7 +1059,9 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
   const CUtensorMapDataType dt = d.in_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
     const int R = d.a_mode != 1 ? ((BM + halo + 7) & ~7) : BM;
-    cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)d.L_in, (cuuint64_t)B};
+    // (grouped: the channel axis spans every N tile's input channels)
+    cuuint64_t dims[3] = {(cuuint64_t)(d.a_nt_stride > 0 ? (long long)d.a_nt_stride * (n_nt - 1) + d.Cin : (long long)d.Cin),
+                          (cuuint64_t)d.L_in, (cuuint64_t)B};
     const cuuint64_t ldx = (cuuint64_t)(d.generic && d.ldx16 ? d.ldx16 : d.Cin);
     cuuint64_t strides[2] = {ldx * 2, ldx * 2 * (cuuint64_t)d.L_in};
     cuuint32_t box[3] = {(cuuint32_t)KBLK, (cuuint32_t)R, 1};

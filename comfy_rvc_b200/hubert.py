@@ -16,8 +16,8 @@ Host code is Python like the reference's; every FLOP runs in librvcb200.so throu
     same memory viewed as [L/2][1024] -- two taps for k = 3 (the second tap's upper half is zero), one for k = 2 -- so they
     run on the generic tcgen05 implicit-GEMM kernel (`rvcb200_op_conv_tc`, GELU in the epilogue);
   * LayerNorms: `rvcb200_op_layernorm16`; projections / feed-forward / q|k|v / out: `rvcb200_op_conv_tc` (1 tap);
-  * positional convolution (k 128, 16 groups of 48 channels): one 128-tap launch per group (K = 48 zero-filled to 64 by
-    the tensor map), GELU + residual in the epilogue;
+  * positional convolution (k 128, 16 groups of 48 channels): one 128-tap launch, an N tile per group that reads its own 48
+    input channels (`a_nt_stride`; K = 48 meets the zero K padding of the weight image), GELU + residual in the epilogue;
   * attention: `rvcb200_op_attention_tc` (flash-style tcgen05 kernel of the text encoder) with 12 heads of 64 channels
     laid out in its 128-channel-per-head operand format, relative-position tables zero.
 There is no PyTorch or CPU fallback: without the extension or a CUDA device `extract_features` raises.
@@ -144,8 +144,9 @@ class HubertB200:
         else:
             wpos = sd[p + "weight"]
         cg = H // self.gpos
-        for gi in range(self.gpos):                                                                    # [cg out][cg in][128]
-            W[f"pos.{gi}.w"] = img(wpos[gi * cg:(gi + 1) * cg].permute(2, 1, 0).contiguous(), cg)
+        # grouped convolution as ONE launch: N tile gi = group gi (its cg output channels), which reads input channels
+        # [gi * cg, + cg) (`a_nt_stride`): the image is [128 taps][cg in][H out] with N = cg
+        W["pos.w"] = img(wpos.permute(2, 1, 0).contiguous(), cg)
         W["pos.b"] = f32(sd[p + "bias"])
         W["enc.ln_w"], W["enc.ln_b"] = f32(sd["encoder.layer_norm.weight"]), f32(sd["encoder.layer_norm.bias"])
         nh, dk = self.n_heads, H // self.n_heads
@@ -180,7 +181,7 @@ class HubertB200:
 
     # ---- one generic tcgen05 contraction -----------------------------------------------------------------------------
     def _gemm(self, x16, L_in, Cin, w16, bias, Cout, Lj, *, ntaps=1, g_off=0, n_tile=64, ldx16=0, gelu=False, y16=None,
-              ldy16=0, y32=None, ldy32=0, res32=None, ldr32=0):
+              ldy16=0, y32=None, ldy32=0, res32=None, ldr32=0, a_nt_stride=0):
         d = _lib.TcConvDesc()
         d.x16, d.L_in, d.padf = x16, L_in, PADF
         d.w16, d.bias = w16.data_ptr(), bias.data_ptr()
@@ -191,6 +192,7 @@ class HubertB200:
         d.div, d.out_slope, d.alpha, d.pre_slope = 1.0, 1.0, 1.0, 1.0
         d.generic, d.f32_cl, d.ldx16 = 1, 1, ldx16
         d.gelu = 1 if gelu else 0
+        d.a_nt_stride = a_nt_stride
         if y16 is not None:
             d.y16, d.ldy16 = y16, ldy16
         if y32 is not None:
@@ -290,14 +292,12 @@ class HubertB200:
             h16 = torch.empty(T, H, dtype=torch.float16, device=dev)
             w16, nt_ = self._tiled("fp.w", T, H)
             self._gemm(ln16.data_ptr(), T, C0, w16, W["fp.b"], H, T, n_tile=nt_, y32=h32.data_ptr(), ldy32=H, y16=h16.data_ptr(), ldy16=H)
-            # positional convolution: h + GELU(conv_k128_groups16(h) + b), one launch per group
+            # positional convolution: h + GELU(conv_k128_groups16(h) + b): one launch, an N tile per group (16 launches of 24 CTAs
+            # each before: 528 of the 5 100 us of a 60 s utterance, profiles/r2_hubert_launches_60s_v1.csv)
             t32 = torch.empty(T, H, dtype=torch.float32, device=dev)
             cg = H // self.gpos
-            for gi in range(self.gpos):
-                o = gi * cg
-                self._gemm(h16.data_ptr() + o * 2, T, cg, W[f"pos.{gi}.w"], W["pos.b"][o:o + cg], cg, T, ntaps=self.kpos,
-                           g_off=-(self.kpos // 2), n_tile=cg, ldx16=H, gelu=True, y32=t32.data_ptr() + o * 4, ldy32=H,
-                           res32=h32.data_ptr() + o * 4, ldr32=H)
+            self._gemm(h16.data_ptr(), T, cg, W["pos.w"], W["pos.b"], H, T, ntaps=self.kpos, g_off=-(self.kpos // 2), n_tile=cg,
+                       ldx16=H, gelu=True, y32=t32.data_ptr(), ldy32=H, res32=h32.data_ptr(), ldr32=H, a_nt_stride=cg)
             self._ln(t32, W["enc.ln_w"], W["enc.ln_b"], h32, h16, T, H)
             # encoder layers (post-norm)
             nh = self.n_heads
