@@ -11,6 +11,10 @@ for o in *.o; do
       $(echo "$s" | grep -c LDTM) $(echo "$s" | grep -c UTCBAR)
 done
 echo
+echo "# rmvpe_kernels.o (GRU recurrence over a thread-block cluster): STAS = st.async (DSMEM store + mbarrier complete_tx), SYNCS = mbarrier ops, UCGABAR = barrier.cluster, MAPA"
+s=$(cuobjdump -sass rmvpe_kernels.o 2>/dev/null)
+printf "%-22s STAS %d  SYNCS %d  UCGABAR %d  MAPA %d\n" rmvpe_kernels.o $(echo "$s" | grep -c "STAS") $(echo "$s" | grep -c "SYNCS") $(echo "$s" | grep -c "UCGABAR") $(echo "$s" | grep -c "MAPA")
+echo
 echo "# per kernel (objects with tcgen05 code): function, UTCHMMA, UTMALDG, UTMASTG, LDTM"
 for o in rbconv_tc.o rbpair_tc.o conv_tc.o attention_tc.o; do
   cuobjdump -sass "$o" 2>/dev/null | awk -v obj="$o" '
