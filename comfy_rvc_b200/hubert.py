@@ -75,6 +75,7 @@ class HubertB200:
             raise RuntimeError(f"missing keys in state_dict: {missing}")
         self._w: Optional[Dict[str, torch.Tensor]] = None
         self.last_launches = 0
+        self.rng_draws_per_call = self.n_layers       # global-generator draws of one reference forward (see extract_features)
 
     # ---- reference loader protocol (loaders.py:21-32) ------------------------------------------------------------
     @staticmethod
@@ -239,6 +240,12 @@ class HubertB200:
             raise ValueError("HubertB200.extract_features handles one utterance per call ([1, n]), like the reference pipeline")
         self._materialize()
         lib, W, dev, H = _lib.load(), self._w, self.device, self.hidden
+        # Side effect of the reference kept on purpose: HuggingFace's HubertEncoder draws `torch.rand([])` from the GLOBAL CPU generator
+        # once per encoder layer on every forward, training or not (its LayerDrop test).  `VC.vc` draws the synthesizer's noise from
+        # the same generator right afterwards (models.py:801), so a drop-in that skipped these draws would produce a different --
+        # equally valid, but not the reference's -- noise stream after `torch.manual_seed` (tests/test_pipeline_gpu.py, fixture p4).
+        for _ in range(self.rng_draws_per_call):
+            torch.rand([])
         n = int(source.shape[1])
         if n < self.conv_kernel[0]:
             raise RuntimeError(f"input of {n} samples is shorter than the feature encoder's first kernel")

@@ -330,6 +330,8 @@ class VC(FeatureExtractor):
         padding_mask = torch.zeros(feats.shape, dtype=torch.bool, device=dev)
         inputs = {"source": feats, "padding_mask": padding_mask, "output_layer": 9 if version == "v1" else 12}
         feats = model.extract_features(version=version, **inputs)                              # :48-55
+        if callable(noise):      # "reference" noise: drawn AFTER the feature extractor, like models.py:801 after :48-55 -- HuggingFace's
+            noise = noise()      # HuBERT consumes the global generator itself (one torch.rand([]) per encoder layer and forward)
         use_f0 = pitch is not None and pitchf is not None
         feats0 = feats if (protect < 0.5 and use_f0) else None                                 # :57-58 (no clone needed)
         if index is not None and big_npy is not None and index_rate > 0:                       # :59-75, host like the reference
@@ -477,7 +479,14 @@ class VC(FeatureExtractor):
             T_formula = min(s.n_samples // self.window, 2 * hubert_frames(s.n_samples))
             run = s.index in mine
             noise = None
-            if self.noise_mode == "reference" or run:   # "reference": every rank advances the global stream past every segment
+            if self.noise_mode == "reference":          # every rank advances the global stream past every segment, in the
+                if run:                                 # reference's order: the front end's own draws, then the synthesizer's
+                    noise = (lambda s=s, T=T_formula: self._segment_noise(net_g, s.index, T, staged))
+                else:
+                    for _ in range(int(getattr(model, "rng_draws_per_call", 0))):
+                        torch.rand([])
+                    self._segment_noise(net_g, s.index, T_formula, staged)
+            elif run:
                 noise = self._segment_noise(net_g, s.index, T_formula, staged)
             if run:
                 parts.append((s.index, self._convert(staged, model, net_g, s, T_formula, index, big_npy, index_rate,

@@ -38,6 +38,8 @@ def fold_pos_conv_weight(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
 def extract_features(sd: Dict[str, torch.Tensor], hcfg, source: torch.Tensor, version: str = "v2") -> torch.Tensor:
     """source [B, n] (16 kHz) -> features [B, frames, 768] (v2) or [B, frames, 256] (v1), frames = (n - 400) // 320 + 1."""
     w = {k: v.float() for k, v in sd.items()}
+    for _ in range(hcfg.num_hidden_layers):      # HubertEncoder's LayerDrop test draws torch.rand([]) per layer, in eval mode too
+        torch.rand([])
     x = source.float()[:, None, :]
     # HubertFeatureEncoder: layer 0 = conv -> GroupNorm(C groups) -> GELU, layers 1.. = conv -> GELU (no bias)
     for i, (k, s) in enumerate(zip(hcfg.conv_kernel, hcfg.conv_stride)):

@@ -194,3 +194,65 @@ def test_device_planning_equals_host_planning(secs, tier, seed):
     assert np.array_equal(ap2, ap) and np.array_equal(staged.cpu().numpy(), ap)
     assert [(s.start, s.end) for s in segs2] == [(s.start, s.end) for s in segs]
     assert vc.last_plan is None
+
+
+def test_pipeline_with_both_real_front_ends_matches_reference():
+    """The whole reference pipeline with nothing stubbed in front of the synthesizer (tests/golden/make_pipeline_real_golden.py):
+    `f0_method="rmvpe"` through the reference's own RMVPE class and the reference's own HuBERT, against `comfy_rvc_b200.RMVPE` +
+    `HubertB200` + the fp32 synthesis path.  The front ends run on fp16 operands (65-69 dB each), so the gate is not +-1 LSB:
+      * f0: >= 97 % of the frames within 5 cents of the reference's f0 (arg-max flips of the seeded random model would be the rest);
+      * coarse pitch (the 1..255 quantisation the synthesizer's embedding sees): identical on >= 97 % of the frames;
+      * song, same length and peak normalisation: SNR >= 60 dB with the f0 pinned to the reference's own estimate (run B: HuBERT on
+        the B200 kernels -> fp32 synthesis; measured 76.7 dB), and >= 40 dB with our own RMVPE f0 (run A; measured 58.2 dB -- the NSF
+        source integrates f0 into a phase (models.py:361-411), so sub-cent f0 differences drift the phase over a segment, and a
+        flipped frame would decorrelate everything behind it; the second gate therefore only applies when no frame flipped).
+    The fixture also pins a side effect: HuggingFace's HubertEncoder draws `torch.rand([])` per layer from the global generator on
+    every forward, which shifts the synthesizer's noise stream; `HubertB200` reproduces the draws and `VC` draws the synthesizer's
+    noise after the front end like the reference (4 dB instead of 77 dB without)."""
+    import ast
+    import os
+    from comfy_rvc_b200.config import NAMED_CONFIGS
+    from comfy_rvc_b200.hubert import HubertB200
+    from comfy_rvc_b200.rmvpe import RMVPE
+    from tests._util import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "p4_48k_v2_real_front_ends.npz"), allow_pickle=True)
+    cfg_name, secs, tiers, protect, f0_up_key, aseed, rseed = [str(x) for x in z["meta"][:7]]
+    cfg = NAMED_CONFIGS[cfg_name]
+    net = build_net(cfg, synthetic.make_state_dict(cfg, seed=0), "fp32")
+    hubert = HubertB200(synthetic.HUBERT_BASE, synthetic.make_hubert_state_dict(0), "cuda:0")
+    rmvpe = RMVPE(synthetic.make_rmvpe_state_dict(0), is_half=False, device="cuda:0")
+    audio = synthetic.make_song(float(secs), seed=int(aseed))
+
+    def run(f0_method):
+        vc = pl.VC(cfg.sr, pl.PipelineConfig(*ast.literal_eval(tiers), is_half=False, device="cuda:0"), noise="reference")
+        vc.model_rmvpe = rmvpe
+        vc.f0_method_dict["reference_f0"] = lambda **k: z["f0"].copy()
+        seen = {}
+        orig = vc.get_f0
+
+        def spy(*a, **k):
+            coarse, f0 = orig(*a, **k)
+            seen["coarse"], seen["f0"] = np.array(coarse), np.array(f0)
+            return coarse, f0
+
+        vc.get_f0 = spy
+        torch.manual_seed(int(rseed))
+        out = vc.pipeline(hubert, net, 0, audio.copy(), [0, 0, 0], int(f0_up_key), f0_method, "median", "", 0.0, 1, 3, cfg.sr, 0, 1.0,
+                          "v2", float(protect), 160, False, False, None, 50, 1100)
+        assert out.dtype == np.int16 and out.shape == z["out_i16"].shape and np.abs(out).max() == 32440
+        return out, seen, len(vc.last_plan["segments"])
+
+    out_a, seen, nseg = run("rmvpe")
+    assert seen["f0"].shape == z["f0"].shape
+    cents = 1200 * np.abs(np.log2(np.maximum(seen["f0"], 1e-3) / np.maximum(z["f0"], 1e-3)))
+    f0_ok = float(np.mean(cents < 5.0))
+    coarse_ok = float(np.mean(seen["coarse"] == z["coarse"]))
+    snr_a = synthetic.snr_db(z["out_i16"].astype(np.float64), out_a.astype(np.float64))
+    out_b, seen_b, _ = run("reference_f0")
+    assert np.array_equal(seen_b["coarse"], z["coarse"])
+    snr_b = synthetic.snr_db(z["out_i16"].astype(np.float64), out_b.astype(np.float64))
+    print(f"real front ends, {nseg} segments: f0 within 5 cents {100 * f0_ok:.1f} %, coarse pitch equal {100 * coarse_ok:.1f} %, "
+          f"song SNR {snr_a:.1f} dB (own f0) / {snr_b:.1f} dB (f0 pinned to the reference's)")
+    assert f0_ok >= 0.97 and coarse_ok >= 0.97
+    assert snr_b >= 60.0
+    assert snr_a >= 40.0 or f0_ok < 1.0
