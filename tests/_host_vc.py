@@ -28,7 +28,8 @@ class HostVC(VC):
 
         def infer_fn(feats, p_len_t, pitch_s, pitchf_s, sid_s):
             assert feats.shape[1] == T_formula
-            return rvc_oracle.infer(net_g.w, net_g.cfg, feats, p_len_t, pitch_s, pitchf_s, sid_s, *noise)[0][0, 0].numpy()
+            nz = noise() if callable(noise) else noise          # "reference" mode: drawn after the front end, like the reference
+            return rvc_oracle.infer(net_g.w, net_g.cfg, feats, p_len_t, pitch_s, pitchf_s, sid_s, *nz)[0][0, 0].numpy()
 
         out = pipeline_oracle.vc_segment(infer_fn, model, net_g.cfg, staged["audio"][s.start:s.end],
                                          staged["pitch"][:, s.f0_start:s.f0_end], staged["pitchf"][:, s.f0_start:s.f0_end],
