@@ -14,9 +14,13 @@
 //
 // Operands (all K-major, TMA + SWIZZLE_128B): qk16 [B][T][512] = q(h0|h1) k(h0|h1), 128 channels per head
 // (96 + zero pad); vt16 [B*heads][128][Tp] = V transposed (keys contiguous); ek16 [32][128]; evt16 [128][64].
-// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax: thread = query row = TMEM lane, two warps per lane quadrant,
-// each owning 32 of a key tile's 64 columns (the per-tile softmax chain is what bounds the kernel; row max and row sum
-// are exchanged through shared memory once per pass).
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax: thread = query row = TMEM lane, two GROUPS of four warps (one
+// per lane quadrant).  Group g owns S buffer g and P buffer g and takes every second key tile whole (64 columns per
+// thread), so the two groups' per-tile chains (S landed -> tcgen05.ld -> exp -> P in smem -> P V) overlap instead of
+// running in lockstep.  Three MMA-issuing warps: warp 1 / warp 10 issue Q K^T for group 0 / 1 (S buffer g, K stages g and
+// g + 2), warp 11 issues P V and the final Pband Ev -- with one issuer the kernel was bound by that single thread's
+// instruction stream (~145 SASS instructions, ~1200 cycles per key tile; the softmax warps sat in their S-landed wait,
+// `profiles/r2_ncu_attention.md`).  Row max and row sum are exchanged between the two groups through shared memory once per pass.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -26,9 +30,8 @@
 namespace rvc {
 namespace {
 
-constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 3, MAXREL = 21;
-constexpr int kThreadsAtt = 64 + 256;
-constexpr int HC = BKV / 2;           // key columns of a tile per softmax warp
+constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 4, NSTV = 3, MAXREL = 21;   // K ring / V ring depths
+constexpr int kThreadsAtt = 64 + 256 + 64;   // producer, Q K^T issuer 0, 8 softmax warps, Q K^T issuer 1, P V issuer
 // TMEM columns
 // two S buffers: Q K^T of key tile t+1 is issued while the softmax warps still work on tile t
 constexpr uint32_t TM_S = 0, TM_O = 64, TM_R = 160, TM_S2 = 192, TM_COLS = 256;
@@ -112,16 +115,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// 64 accumulator columns of this thread's lane: both loads in flight before the one wait
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
+  uint32_t r[64];
+  tmem_ld32_nowait(taddr, r);
+  tmem_ld32_nowait(taddr + 32, r + 32);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 struct AttSmem {                        // 1024-byte aligned tiles, all [rows][128 B] swizzled
   unsigned char q[2][BQ * 128];         // 2 k-blocks of 64 channels
   unsigned char k[NSTG][2][BKV * 128];
-  unsigned char v[NSTG][DKP * 128];     // V^T tile: 128 d-rows x 64 keys
+  unsigned char v[NSTV][DKV * 128];     // V^T tile: 96 d-rows x 64 keys
   unsigned char p[2][BQ * 128];         // probabilities, 64 keys per row; two tiles: P(t+1) is written while P V(t) runs
   unsigned char pband[BQ * 128];        // P[i][i+r-w], r < 21 (columns >= 21 stay zero)
   unsigned char ek[2][32 * 128];
-  unsigned char evt[DKP * 128];
+  unsigned char evt[DKV * 128];
   float rtab[BQ * 24];                  // relative-key logits per query row (dynamic indexing)
-  float xch[2][2][BQ];                  // [max | sum][column half][row]: exchanged between the two warps of a row
+  float xch[2][2][BQ];                  // [max | sum][group][row]: exchanged between the two warps of a row
   uint64_t bars[32];
   uint32_t tmem_slot;
 };
@@ -159,22 +182,23 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
 
   uint64_t* q_full = &sm.bars[0];
   uint64_t* k_full = &sm.bars[1];        // [NSTG]
-  uint64_t* k_empty = &sm.bars[4];       // [NSTG]
-  uint64_t* v_full = &sm.bars[7];        // [NSTG]
-  uint64_t* v_empty = &sm.bars[10];      // [NSTG]
-  uint64_t* r_full = &sm.bars[13];
+  uint64_t* k_empty = &sm.bars[5];       // [NSTG]
+  uint64_t* v_full = &sm.bars[9];        // [NSTV]
+  uint64_t* v_empty = &sm.bars[12];      // [NSTV]
+  uint64_t* r_full = &sm.bars[15];
   uint64_t* s_full = &sm.bars[20];       // [2]
-  uint64_t* s_empty = &sm.bars[22];      // [2], 8 softmax warps each
-  uint64_t* p_full = &sm.bars[24];       // [2], 8 softmax warps each
+  uint64_t* s_empty = &sm.bars[22];      // [2], the 4 warps of the buffer's group
+  uint64_t* p_full = &sm.bars[24];       // [2], the 4 warps of the buffer's group
   uint64_t* p_empty = &sm.bars[26];      // [2]
   uint64_t* pb_full = &sm.bars[18];      // 8 softmax warps
   uint64_t* o_full = &sm.bars[19];
 
   if (threadIdx.x == 0) {
     bar_init(q_full, 1);
-    for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); bar_init(&v_full[i], 1); bar_init(&v_empty[i], 1); }
+    for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); }
+    for (int i = 0; i < NSTV; ++i) { bar_init(&v_full[i], 1); bar_init(&v_empty[i], 1); }
     bar_init(r_full, 1);
-    for (int i = 0; i < 2; ++i) { bar_init(&s_full[i], 1); bar_init(&s_empty[i], 8); bar_init(&p_full[i], 8); bar_init(&p_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { bar_init(&s_full[i], 1); bar_init(&s_empty[i], 4); bar_init(&p_full[i], 4); bar_init(&p_empty[i], 1); }
     bar_init(pb_full, 8); bar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -193,89 +217,102 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
 
   if (warp == 0) {
     // ======================================= TMA producer =======================================
+    // lane 0 streams Q, the relative tables and the K tiles of both passes, lane 1 the V tiles of pass 1: two independent
+    // rings, so that a full V ring never holds back the K tile the next Q K^T is waiting for
     if (lane == 0) {
-      bar_expect(q_full, 2 * BQ * 128 + 2 * 32 * 128 + DKP * 128);
+      bar_expect(q_full, 2 * BQ * 128 + 2 * 32 * 128 + DKV * 128);
       for (int kb = 0; kb < 2; ++kb) tma3(sm.q[kb], &tmQ, h * DKP + kb * 64, q0, b, q_full);
       for (int kb = 0; kb < 2; ++kb) tma2(sm.ek[kb], &tmEk, kb * 64, 0, q_full);
       tma2(sm.evt, &tmEv, 0, 0, q_full);
-      int ks = 0, vs = 0;
-      uint32_t kp = 1, vp = 1;
-      for (int pass = 0; pass < 2; ++pass)
-        for (int t = 0; t < ntiles; ++t) {
-          const int j0 = t * BKV;
-          bar_wait(&k_empty[ks], kp);
-          bar_expect(&k_full[ks], 2 * BKV * 128);
-          for (int kb = 0; kb < 2; ++kb) tma3(sm.k[ks][kb], &tmK, a.n_heads * DKP + h * DKP + kb * 64, j0, b, &k_full[ks]);
-          if (++ks == NSTG) { ks = 0; kp ^= 1; }
-          if (pass == 1) {
-            bar_wait(&v_empty[vs], vp);
-            bar_expect(&v_full[vs], DKP * 128);
-            tma3(sm.v[vs], &tmV, j0, 0, b * a.n_heads + h, &v_full[vs]);
-            if (++vs == NSTG) { vs = 0; vp ^= 1; }
-          }
-        }
+      int ks = 0;
+      uint32_t kp = 1;
+      for (int it = 0; it < 2 * ntiles; ++it) {
+        const int j0 = (it < ntiles ? it : it - ntiles) * BKV;
+        bar_wait(&k_empty[ks], kp);
+        bar_expect(&k_full[ks], 2 * BKV * 128);
+        for (int kb = 0; kb < 2; ++kb) tma3(sm.k[ks][kb], &tmK, a.n_heads * DKP + h * DKP + kb * 64, j0, b, &k_full[ks]);
+        if (++ks == NSTG) { ks = 0; kp ^= 1; }
+      }
+    } else if (lane == 1) {
+      int vs = 0;
+      uint32_t vp = 1;
+      for (int t = 0; t < ntiles; ++t) {
+        bar_wait(&v_empty[vs], vp);
+        bar_expect(&v_full[vs], DKV * 128);
+        tma3(sm.v[vs], &tmV, t * BKV, 0, b * a.n_heads + h, &v_full[vs]);
+        if (++vs == NSTV) { vs = 0; vp ^= 1; }
+      }
     }
-  } else if (warp == 1) {
-    // ======================================= MMA issuer =========================================
-    const uint32_t id_s = idesc_f16(BKV), id_o = idesc_f16(DKV), id_r = idesc_f16(32);
+  } else if (warp == 1 || warp == 10) {
+    // ============================ Q K^T issuer of softmax group g (warp 1: also R = Q Ek^T) ============================
+    const int g = warp == 1 ? 0 : 1;
+    const uint32_t id_s = idesc_f16(BKV), id_r = idesc_f16(32);
     const uint32_t q_lo0 = desc_lo(s_u32(sm.q[0])), q_lo1 = desc_lo(s_u32(sm.q[1]));
     bar_wait(q_full, 0);
     fence_after();
-    if (elect1()) {   // R = Q Ek^T : K = 96 = 4 + 2 MMAs
-      uint32_t acc = 0;
-      for (int ks = 0; ks < 6; ++ks) {
-        const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
-        const uint32_t b_lo = desc_lo(s_u32(sm.ek[ks >> 2])) + 2u * (ks & 3);
-        mma_f16(tmem + TM_R, a_lo, b_lo, kDescHi, id_r, acc);
-        acc = 1;
-      }
-      commit(r_full);
-    }
-    __syncwarp();
-    int ks_ = 0, vs_ = 0;
-    uint32_t kp = 0, vp = 0;
-    uint32_t o_acc = 0;
-    const int total = 2 * ntiles;                       // pass 0 (row max) then pass 1 (probabilities, P V)
-    auto issue_qk = [&](int it) {                       // S[it & 1] = Q K^T of key tile it % ntiles
-      const int buf = it & 1;
-      bar_wait(&k_full[ks_], kp);
-      bar_wait(&s_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u);   // softmax has read this buffer's previous tile out of TMEM
-      fence_after();
-      if (elect1()) {
+    if (g == 0) {
+      if (elect1()) {   // R = Q Ek^T : K = 96 = 4 + 2 MMAs
         uint32_t acc = 0;
         for (int ks = 0; ks < 6; ++ks) {
           const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
-          const uint32_t b_lo = desc_lo(s_u32(sm.k[ks_][ks >> 2])) + 2u * (ks & 3);
-          mma_f16(tmem + (buf ? TM_S2 : TM_S), a_lo, b_lo, kDescHi, id_s, acc);
+          const uint32_t b_lo = desc_lo(s_u32(sm.ek[ks >> 2])) + 2u * (ks & 3);
+          mma_f16(tmem + TM_R, a_lo, b_lo, kDescHi, id_r, acc);
           acc = 1;
         }
-        commit(&s_full[buf]);
-        commit(&k_empty[ks_]);
+        commit(r_full);
       }
       __syncwarp();
-      if (++ks_ == NSTG) { ks_ = 0; kp ^= 1; }
-    };
-    issue_qk(0);
-    for (int it = 0; it < total; ++it) {
-      if (it + 1 < total) issue_qk(it + 1);             // one tile ahead of the softmax warps
-      if (it >= ntiles) {
-        const int j = it - ntiles, pb = j & 1;          // P buffer of this key tile
-        bar_wait(&p_full[pb], ((uint32_t)j >> 1) & 1u); // probabilities of this tile are in smem
-        bar_wait(&v_full[vs_], vp);
-        fence_after();
-        if (elect1()) {
-          const uint32_t p_lo = desc_lo(s_u32(sm.p[pb])), v_lo = desc_lo(s_u32(sm.v[vs_]));
-          for (int ks = 0; ks < BKV / 16; ++ks) {
-            mma_f16(tmem + TM_O, p_lo + 2u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
-            o_acc = 1;
-          }
-          commit(&p_empty[pb]);
-          commit(&v_empty[vs_]);
+    }
+    // tile it = g + 2 n of the 2 ntiles (pass 0 then pass 1) lands in K stage g + 2 (n & 1) and in S buffer g
+    const uint32_t s_tm = tmem + (g ? TM_S2 : TM_S);
+    const uint32_t k_lo[2] = {desc_lo(s_u32(sm.k[g][0])), desc_lo(s_u32(sm.k[g + 2][0]))};
+    constexpr uint32_t kKb = (BKV * 128) >> 4;            // second k-block of a stage, in descriptor units
+    const int mine = (2 * ntiles - g + 1) / 2;
+    auto issue_qk = [&](int n, int odd) {
+      const int st = g + 2 * odd;
+      bar_wait(&k_full[st], ((uint32_t)n >> 1) & 1u);
+      bar_wait(&s_empty[g], ((uint32_t)n & 1u) ^ 1u);    // the group has read this buffer's previous tile out of TMEM
+      fence_after();
+      if (elect1()) {
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) {
+          const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
+          const uint32_t b_lo = k_lo[odd] + (ks < 4 ? 0u : kKb) + 2u * (ks & 3);
+          mma_f16(s_tm, a_lo, b_lo, kDescHi, id_s, ks ? 1u : 0u);
         }
-        __syncwarp();
-        o_acc = 1;
-        if (++vs_ == NSTG) { vs_ = 0; vp ^= 1; }
+        commit(&s_full[g]);
+        commit(&k_empty[st]);
       }
+      __syncwarp();
+    };
+    int n = 0;
+    for (; n + 1 < mine; n += 2) { issue_qk(n, 0); issue_qk(n + 1, 1); }
+    if (n < mine) issue_qk(n, 0);
+  } else if (warp == 11) {
+    // ======================================= P V issuer =========================================
+    const uint32_t id_o = idesc_f16(DKV);
+    bar_wait(q_full, 0);                                 // Ev^T landed with Q
+    int vs_ = 0;
+    uint32_t vp = 0, pf0 = 0, pf1 = 0, o_acc = 0;
+    for (int it = ntiles; it < 2 * ntiles; ++it) {
+      const int pb = it & 1;                            // P buffer = S buffer = softmax group of this tile
+      bar_wait(&p_full[pb], pb ? pf1 : pf0);            // probabilities of this tile are in smem
+      if (pb) pf1 ^= 1u; else pf0 ^= 1u;
+      bar_wait(&v_full[vs_], vp);
+      fence_after();
+      if (elect1()) {
+        const uint32_t p_lo = desc_lo(s_u32(sm.p[pb])), v_lo = desc_lo(s_u32(sm.v[vs_]));
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks) {
+          mma_f16(tmem + TM_O, p_lo + 2u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
+          o_acc = 1;
+        }
+        commit(&p_empty[pb]);
+        commit(&v_empty[vs_]);
+      }
+      __syncwarp();
+      o_acc = 1;
+      if (++vs_ == NSTV) { vs_ = 0; vp ^= 1; }
     }
     // O += Pband Ev  (K = 32: two MMAs)
     bar_wait(pb_full, 0);
@@ -289,14 +326,15 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   } else {
     // ======================================= softmax warps ======================================
     const int qd = warp & 3;
-    const int half = (warp - 2) >> 2;                   // which 32 of a key tile's 64 columns this warp owns
+    const int grp = (warp - 2) >> 2;                    // softmax group: S / P buffer grp, every second key tile
     const int row = qd * 32 + lane;                     // TMEM lane = query row in the tile
     const int qi = q0 + row;
     const uint32_t lane_base = ((uint32_t)(qd * 32) << 16);
+    const uint32_t s_addr = tmem + lane_base + (grp ? TM_S2 : TM_S);
     // relative-key logits of this row -> smem (dynamic indexing by key offset); written by the row's first warp
     bar_wait(r_full, 0);
     fence_after();
-    if (half == 0) {
+    if (grp == 0) {
       float rv[32];
       tmem_ld32(tmem + lane_base + TM_R, rv);
 #pragma unroll
@@ -304,88 +342,106 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 softmax warps
     float mx = -INFINITY, lsum = 0.f;
-    int it = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 1) {                                  // row max over both column halves
-        sm.xch[0][half][row] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mx = fmaxf(mx, sm.xch[0][half ^ 1][row]);
-      }
-      for (int t = 0; t < ntiles; ++t, ++it) {
-        const int j0 = t * BKV + half * HC;             // first key of this warp's columns
-        const int buf = it & 1;
-        bar_wait(&s_full[buf], ((uint32_t)it >> 1) & 1u);
-        fence_after();
-        float s[HC];
-        tmem_ld32(tmem + lane_base + (buf ? TM_S2 : TM_S) + half * HC, s);
-        fence_before();
-        __syncwarp();
-        if (lane == 0) bar_arrive(&s_empty[buf]);       // S is in registers: a later Q K^T may overwrite this buffer
-        const bool band = j0 <= q0 + BQ - 1 + a.window && j0 + HC - 1 >= q0 - a.window;
-        if (band) {
+    const int total = 2 * ntiles;
+    int it = grp;
+    // ---- pass 0: row max over this group's key tiles ----
+    for (; it < ntiles; it += 2) {
+      const int j0 = it * BKV;
+      bar_wait(&s_full[grp], ((uint32_t)it >> 1) & 1u);
+      fence_after();
+      float s[BKV];
+      tmem_ld64(s_addr, s);
+      fence_before();
+      __syncwarp();
+      if (lane == 0) bar_arrive(&s_empty[grp]);         // S is in registers: a later Q K^T may overwrite this buffer
+      if (j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window) {
 #pragma unroll
-          for (int c = 0; c < HC; ++c) {
-            const int r = j0 + c - qi + a.window;
-            if ((unsigned)r < (unsigned)nrel) s[c] += sm.rtab[row * 24 + r];
-          }
-        }
-        if (j0 + HC > L) {
-#pragma unroll
-          for (int c = 0; c < HC; ++c)
-            if (j0 + c >= L) s[c] = -INFINITY;
-        }
-        if (pass == 0) {
-#pragma unroll
-          for (int c = 0; c < HC; ++c) mx = fmaxf(mx, s[c]);
-        } else {
-          // probabilities (fp16) -> swizzled K-major smem tile; also harvest the band for the Ev term
-          uint32_t pk[HC / 2];
-#pragma unroll
-          for (int c = 0; c < HC; c += 2) {
-            const float p0 = __expf(s[c] - mx), p1 = __expf(s[c + 1] - mx);
-            lsum += p0 + p1;
-            __half2 hp = __floats2half2_rn(p0, p1);
-            pk[c / 2] = *reinterpret_cast<uint32_t*>(&hp);
-          }
-          if (band) {
-#pragma unroll
-            for (int c = 0; c < HC; ++c) {
-              const int r = j0 + c - qi + a.window;
-              if ((unsigned)r < (unsigned)nrel) {
-                const uint32_t w = pk[c / 2];
-                const unsigned short hv = (c & 1) ? (unsigned short)(w >> 16) : (unsigned short)(w & 0xffffu);
-                *reinterpret_cast<unsigned short*>(sm.pband + row * 128 + (((r >> 3) ^ (row & 7)) << 4) + (r & 7) * 2) = hv;
-              }
-            }
-          }
-          const int pb = t & 1;                         // P buffer of this key tile
-          bar_wait(&p_empty[pb], (((uint32_t)t >> 1) & 1u) ^ 1u);   // the P V MMA that last read this buffer has finished
-#pragma unroll
-          for (int cc = 0; cc < HC / 8; ++cc)
-            *reinterpret_cast<uint4*>(sm.p[pb] + row * 128 + (((half * (HC / 8) + cc) ^ (row & 7)) << 4)) =
-                make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) bar_arrive(&p_full[pb]);
+        for (int c = 0; c < BKV; ++c) {
+          const int r = j0 + c - qi + a.window;
+          if ((unsigned)r < (unsigned)nrel) s[c] += sm.rtab[row * 24 + r];
         }
       }
+      if (j0 + BKV > L) {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c)
+          if (j0 + c >= L) s[c] = -INFINITY;
+      }
+#pragma unroll
+      for (int c = 0; c < BKV; ++c) mx = fmaxf(mx, s[c]);
+    }
+    sm.xch[0][grp][row] = mx;                           // row max over both groups' tiles
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(mx, sm.xch[0][grp ^ 1][row]);
+    // ---- pass 1: probabilities of this group's key tiles -> P buffer grp ----
+    uint32_t pe = 1;                                    // phase of p_empty[grp] to wait for (first use passes)
+    for (; it < total; it += 2) {
+      const int j0 = (it - ntiles) * BKV;
+      bar_wait(&s_full[grp], ((uint32_t)it >> 1) & 1u);
+      fence_after();
+      float s[BKV];
+      tmem_ld64(s_addr, s);
+      fence_before();
+      __syncwarp();
+      if (lane == 0) bar_arrive(&s_empty[grp]);
+      const bool band = j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window;
+      if (band) {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c) {
+          const int r = j0 + c - qi + a.window;
+          if ((unsigned)r < (unsigned)nrel) s[c] += sm.rtab[row * 24 + r];
+        }
+      }
+      if (j0 + BKV > L) {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c)
+          if (j0 + c >= L) s[c] = -INFINITY;
+      }
+      // probabilities (fp16) -> swizzled K-major smem tile; also harvest the band for the Ev term
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 2) {
+        const float p0 = __expf(s[c] - mx), p1 = __expf(s[c + 1] - mx);
+        lsum += p0 + p1;
+        __half2 hp = __floats2half2_rn(p0, p1);
+        pk[c / 2] = *reinterpret_cast<uint32_t*>(&hp);
+      }
+      if (band) {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c) {
+          const int r = j0 + c - qi + a.window;
+          if ((unsigned)r < (unsigned)nrel) {
+            const uint32_t w = pk[c / 2];
+            const unsigned short hv = (c & 1) ? (unsigned short)(w >> 16) : (unsigned short)(w & 0xffffu);
+            *reinterpret_cast<unsigned short*>(sm.pband + row * 128 + (((r >> 3) ^ (row & 7)) << 4) + (r & 7) * 2) = hv;
+          }
+        }
+      }
+      bar_wait(&p_empty[grp], pe);                      // the P V MMA that last read this buffer has finished
+      pe ^= 1u;
+#pragma unroll
+      for (int cc = 0; cc < BKV / 8; ++cc)
+        *reinterpret_cast<uint4*>(sm.p[grp] + row * 128 + ((cc ^ (row & 7)) << 4)) =
+            make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) bar_arrive(&p_full[grp]);
     }
     // band tile complete -> final MMA, then normalise and store
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) bar_arrive(pb_full);
-    sm.xch[1][half][row] = lsum;                        // row sum over both column halves
+    sm.xch[1][grp][row] = lsum;                         // row sum over both groups' tiles
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    lsum += sm.xch[1][half ^ 1][row];
+    lsum += sm.xch[1][grp ^ 1][row];
     bar_wait(o_full, 0);
     fence_after();
     const bool valid = qi < L;
     const float inv = valid ? 1.f / lsum : 0.f;
     __half* orow = a.out + ((size_t)b * a.T + qi) * a.H + h * DKV;
-    // output columns: the row's first warp stores [0, 64), the second [64, 96)
+    // output columns: the row's warp of group 0 stores [0, 64), that of group 1 [64, 96)
 #pragma unroll
     for (int c0 = 0; c0 < DKV; c0 += 32) {
-      if ((c0 < 64) != (half == 0)) continue;
+      if ((c0 < 64) != (grp == 0)) continue;
       float o[32];
       tmem_ld32(tmem + lane_base + TM_O + c0, o);
       if (qi < a.T) {
@@ -475,13 +531,13 @@ cudaError_t launch_attention_tc(const void* qkv16, void* vt, const void* ek16, c
     if (!make_map(&tmQ, qkv16, 3, dims, strides, boxq) || !make_map(&tmK, qkv16, 3, dims, strides, boxk)) return cudaErrorInvalidValue;
     cuuint64_t vd[3] = {(cuuint64_t)T, (cuuint64_t)DKP, (cuuint64_t)(B * n_heads)};          // keys >= T read as zero
     cuuint64_t vs[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)Tp * 2 * DKP};
-    cuuint32_t boxv[3] = {BKV, DKP, 1};
+    cuuint32_t boxv[3] = {BKV, DKV, 1};                                                     // the 96 real d-rows of a head
     if (!make_map(&tmV, vt, 3, vd, vs, boxv)) return cudaErrorInvalidValue;
     cuuint64_t ekd[2] = {DKP, 32}, eks[1] = {DKP * 2};
     cuuint32_t boxek[2] = {64, 32};
     if (!make_map(&tmEk, ek16, 2, ekd, eks, boxek)) return cudaErrorInvalidValue;
     cuuint64_t evd[2] = {64, DKP}, evs[1] = {64 * 2};
-    cuuint32_t boxev[2] = {64, DKP};
+    cuuint32_t boxev[2] = {64, DKV};
     if (!make_map(&tmEv, evt16, 2, evd, evs, boxev)) return cudaErrorInvalidValue;
   }
   const size_t smem = sizeof(AttSmem) + 1024;

@@ -256,3 +256,9 @@ def test_pipeline_with_both_real_front_ends_matches_reference():
     assert f0_ok >= 0.97 and coarse_ok >= 0.97
     assert snr_b >= 60.0
     assert snr_a >= 40.0 or f0_ok < 1.0
+    # ... and what `get_vc(is_half=True)` runs: both front ends + the tcgen05 synthesis path (fp16 operands), gate 45 dB
+    net = build_net(cfg, synthetic.make_state_dict(cfg, seed=0), "fp16")
+    out_c, _, _ = run("reference_f0")
+    snr_c = synthetic.snr_db(z["out_i16"].astype(np.float64), out_c.astype(np.float64))
+    print(f"real front ends + fp16 tensor-core synthesis, f0 pinned: song SNR {snr_c:.1f} dB")
+    assert snr_c >= 45.0
