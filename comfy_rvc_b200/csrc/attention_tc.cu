@@ -30,11 +30,11 @@
 namespace rvc {
 namespace {
 
-constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 4, NSTV = 3, MAXREL = 21;   // K ring / V ring depths
+constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 4, NSTV = 4, MAXREL = 21;   // K ring / V ring depths
 constexpr int kThreadsAtt = 64 + 256 + 64;   // producer, Q K^T issuer 0, 8 softmax warps, Q K^T issuer 1, P V issuer
-// TMEM columns
-// two S buffers: Q K^T of key tile t+1 is issued while the softmax warps still work on tile t
-constexpr uint32_t TM_S = 0, TM_O = 64, TM_R = 160, TM_S2 = 192, TM_COLS = 256;
+// TMEM columns (512 allocated).  O accumulator, relative-key logits R, the Q tile as an MMA A operand (96 fp16 per lane
+// = 48 columns), one P tile per softmax group as an MMA A operand (64 fp16 = 32 columns), four S buffers (slot = K stage)
+constexpr uint32_t TM_O = 0, TM_R = 96, TM_Q = 128, TM_P = 176, TM_S = 256, TM_COLS = 512;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
@@ -94,6 +94,31 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
       "}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc) : "memory");
 }
+// A operand in tensor memory (lane = row, 32-bit column c = elements 2c | 2c+1 of the row's K range), B through a descriptor
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+      "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // SWIZZLE_128B K-major descriptor halves: lo = start>>4 | LBO(1)<<16 ; hi = SBO(1024>>4) | version 1<<14 | SW128 (2)<<29
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -136,29 +161,27 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
 }
 
 struct AttSmem {                        // 1024-byte aligned tiles, all [rows][128 B] swizzled
-  unsigned char q[2][BQ * 128];         // 2 k-blocks of 64 channels
-  unsigned char k[NSTG][2][BKV * 128];
+  unsigned char k[NSTG][2][BKV * 128];  // 2 k-blocks of 64 channels
   unsigned char v[NSTV][DKV * 128];     // V^T tile: 96 d-rows x 64 keys
-  unsigned char p[2][BQ * 128];         // probabilities, 64 keys per row; two tiles: P(t+1) is written while P V(t) runs
   unsigned char pband[BQ * 128];        // P[i][i+r-w], r < 21 (columns >= 21 stay zero)
   unsigned char ek[2][32 * 128];
   unsigned char evt[DKV * 128];
   float rtab[BQ * 24];                  // relative-key logits per query row (dynamic indexing)
   float xch[2][2][BQ];                  // [max | sum][group][row]: exchanged between the two warps of a row
-  uint64_t bars[32];
+  uint64_t bars[40];
   uint32_t tmem_slot;
 };
 
 struct AttArgs {
   const int* len;
+  const __half* qkv;    // [B][T][ld]: q | k | v, 128 channels per head
   __half* out;          // [B][T][H]
-  int T, n_heads, window, H;
+  int T, n_heads, window, H, ld;
 };
 
 __global__ void __launch_bounds__(kThreadsAtt, 1)
-attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmEk,
-                    const __grid_constant__ CUtensorMap tmEv) {
+attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmEk, const __grid_constant__ CUtensorMap tmEv) {
   extern __shared__ unsigned char smem_raw[];
   // aligned by pointer arithmetic on the __shared__ array: keeps the shared address space (LDS/STS, not generic LD/ST)
   AttSmem& sm = *reinterpret_cast<AttSmem*>(smem_raw + ((1024u - (s_u32(smem_raw) & 1023u)) & 1023u));
@@ -180,26 +203,25 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   }
   const int ntiles = (L + BKV - 1) / BKV;
 
-  uint64_t* q_full = &sm.bars[0];
-  uint64_t* k_full = &sm.bars[1];        // [NSTG]
-  uint64_t* k_empty = &sm.bars[5];       // [NSTG]
-  uint64_t* v_full = &sm.bars[9];        // [NSTV]
-  uint64_t* v_empty = &sm.bars[12];      // [NSTV]
-  uint64_t* r_full = &sm.bars[15];
-  uint64_t* s_full = &sm.bars[20];       // [2]
-  uint64_t* s_empty = &sm.bars[22];      // [2], the 4 warps of the buffer's group
-  uint64_t* p_full = &sm.bars[24];       // [2], the 4 warps of the buffer's group
-  uint64_t* p_empty = &sm.bars[26];      // [2]
-  uint64_t* pb_full = &sm.bars[18];      // 8 softmax warps
-  uint64_t* o_full = &sm.bars[19];
+  uint64_t* e_full = &sm.bars[0];        // Ek | Ev^T landed
+  uint64_t* q_ready = &sm.bars[1];       // Q tile stored to tensor memory by the 8 softmax warps
+  uint64_t* r_full = &sm.bars[2];
+  uint64_t* pb_full = &sm.bars[3];       // 8 softmax warps
+  uint64_t* o_full = &sm.bars[4];
+  uint64_t* k_full = &sm.bars[8];        // [NSTG]
+  uint64_t* k_empty = &sm.bars[12];      // [NSTG]
+  uint64_t* v_full = &sm.bars[16];       // [NSTV]
+  uint64_t* v_empty = &sm.bars[20];      // [NSTV]
+  uint64_t* s_full = &sm.bars[24];       // [4]: S buffer = K stage = slot g + 2 (n & 1) of group g's n-th tile
+  uint64_t* s_empty = &sm.bars[28];      // [4], the 4 warps of the slot's group
+  uint64_t* p_full = &sm.bars[32];       // [2], the 4 warps of the group
+  uint64_t* p_empty = &sm.bars[34];      // [2]
 
   if (threadIdx.x == 0) {
-    bar_init(q_full, 1);
-    for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); }
+    bar_init(e_full, 1); bar_init(q_ready, 8); bar_init(r_full, 1); bar_init(pb_full, 8); bar_init(o_full, 1);
+    for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); bar_init(&s_full[i], 1); bar_init(&s_empty[i], 4); }
     for (int i = 0; i < NSTV; ++i) { bar_init(&v_full[i], 1); bar_init(&v_empty[i], 1); }
-    bar_init(r_full, 1);
-    for (int i = 0; i < 2; ++i) { bar_init(&s_full[i], 1); bar_init(&s_empty[i], 4); bar_init(&p_full[i], 4); bar_init(&p_empty[i], 1); }
-    bar_init(pb_full, 8); bar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) { bar_init(&p_full[i], 4); bar_init(&p_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -217,13 +239,12 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
 
   if (warp == 0) {
     // ======================================= TMA producer =======================================
-    // lane 0 streams Q, the relative tables and the K tiles of both passes, lane 1 the V tiles of pass 1: two independent
+    // lane 0 streams the relative tables and the K tiles of both passes, lane 1 the V tiles of pass 1: two independent
     // rings, so that a full V ring never holds back the K tile the next Q K^T is waiting for
     if (lane == 0) {
-      bar_expect(q_full, 2 * BQ * 128 + 2 * 32 * 128 + DKV * 128);
-      for (int kb = 0; kb < 2; ++kb) tma3(sm.q[kb], &tmQ, h * DKP + kb * 64, q0, b, q_full);
-      for (int kb = 0; kb < 2; ++kb) tma2(sm.ek[kb], &tmEk, kb * 64, 0, q_full);
-      tma2(sm.evt, &tmEv, 0, 0, q_full);
+      bar_expect(e_full, 2 * 32 * 128 + DKV * 128);
+      for (int kb = 0; kb < 2; ++kb) tma2(sm.ek[kb], &tmEk, kb * 64, 0, e_full);
+      tma2(sm.evt, &tmEv, 0, 0, e_full);
       int ks = 0;
       uint32_t kp = 1;
       for (int it = 0; it < 2 * ntiles; ++it) {
@@ -247,41 +268,34 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
     // ============================ Q K^T issuer of softmax group g (warp 1: also R = Q Ek^T) ============================
     const int g = warp == 1 ? 0 : 1;
     const uint32_t id_s = idesc_f16(BKV), id_r = idesc_f16(32);
-    const uint32_t q_lo0 = desc_lo(s_u32(sm.q[0])), q_lo1 = desc_lo(s_u32(sm.q[1]));
-    bar_wait(q_full, 0);
+    const uint32_t q_tm = tmem + TM_Q;                   // A operand: 8 columns per K = 16 step
+    bar_wait(q_ready, 0);
     fence_after();
     if (g == 0) {
+      bar_wait(e_full, 0);
       if (elect1()) {   // R = Q Ek^T : K = 96 = 4 + 2 MMAs
-        uint32_t acc = 0;
-        for (int ks = 0; ks < 6; ++ks) {
-          const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
-          const uint32_t b_lo = desc_lo(s_u32(sm.ek[ks >> 2])) + 2u * (ks & 3);
-          mma_f16(tmem + TM_R, a_lo, b_lo, kDescHi, id_r, acc);
-          acc = 1;
-        }
+        for (int ks = 0; ks < 6; ++ks)
+          mma_f16_ts(tmem + TM_R, q_tm + 8u * ks, desc_lo(s_u32(sm.ek[ks >> 2])) + 2u * (ks & 3), kDescHi, id_r, ks ? 1u : 0u);
         commit(r_full);
       }
       __syncwarp();
     }
-    // tile it = g + 2 n of the 2 ntiles (pass 0 then pass 1) lands in K stage g + 2 (n & 1) and in S buffer g
-    const uint32_t s_tm = tmem + (g ? TM_S2 : TM_S);
+    // tile it = g + 2 n of the 2 ntiles (pass 0 then pass 1) lands in slot g + 2 (n & 1): K stage and S buffer
     const uint32_t k_lo[2] = {desc_lo(s_u32(sm.k[g][0])), desc_lo(s_u32(sm.k[g + 2][0]))};
     constexpr uint32_t kKb = (BKV * 128) >> 4;            // second k-block of a stage, in descriptor units
-    const int mine = (2 * ntiles - g + 1) / 2;
+    const int mine = ntiles;                             // of the 2 ntiles, every second one
     auto issue_qk = [&](int n, int odd) {
-      const int st = g + 2 * odd;
-      bar_wait(&k_full[st], ((uint32_t)n >> 1) & 1u);
-      bar_wait(&s_empty[g], ((uint32_t)n & 1u) ^ 1u);    // the group has read this buffer's previous tile out of TMEM
+      const int slot = g + 2 * odd;
+      bar_wait(&k_full[slot], ((uint32_t)n >> 1) & 1u);
+      bar_wait(&s_empty[slot], (((uint32_t)n >> 1) & 1u) ^ 1u);   // the group has read this buffer's previous tile out of TMEM
       fence_after();
       if (elect1()) {
 #pragma unroll
-        for (int ks = 0; ks < 6; ++ks) {
-          const uint32_t a_lo = (ks < 4 ? q_lo0 : q_lo1) + 2u * (ks & 3);
-          const uint32_t b_lo = k_lo[odd] + (ks < 4 ? 0u : kKb) + 2u * (ks & 3);
-          mma_f16(s_tm, a_lo, b_lo, kDescHi, id_s, ks ? 1u : 0u);
-        }
-        commit(&s_full[g]);
-        commit(&k_empty[st]);
+        for (int ks = 0; ks < 6; ++ks)
+          mma_f16_ts(tmem + TM_S + 64u * slot, q_tm + 8u * ks, k_lo[odd] + (ks < 4 ? 0u : kKb) + 2u * (ks & 3), kDescHi, id_s,
+                     ks ? 1u : 0u);
+        commit(&s_full[slot]);
+        commit(&k_empty[slot]);
       }
       __syncwarp();
     };
@@ -291,20 +305,20 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   } else if (warp == 11) {
     // ======================================= P V issuer =========================================
     const uint32_t id_o = idesc_f16(DKV);
-    bar_wait(q_full, 0);                                 // Ev^T landed with Q
+    bar_wait(e_full, 0);                                 // Ev^T
     int vs_ = 0;
     uint32_t vp = 0, pf0 = 0, pf1 = 0, o_acc = 0;
     for (int it = ntiles; it < 2 * ntiles; ++it) {
-      const int pb = it & 1;                            // P buffer = S buffer = softmax group of this tile
-      bar_wait(&p_full[pb], pb ? pf1 : pf0);            // probabilities of this tile are in smem
+      const int pb = it & 1;                            // softmax group of this tile
+      bar_wait(&p_full[pb], pb ? pf1 : pf0);            // probabilities of this tile are in tensor memory
       if (pb) pf1 ^= 1u; else pf0 ^= 1u;
       bar_wait(&v_full[vs_], vp);
       fence_after();
       if (elect1()) {
-        const uint32_t p_lo = desc_lo(s_u32(sm.p[pb])), v_lo = desc_lo(s_u32(sm.v[vs_]));
+        const uint32_t p_tm = tmem + TM_P + 32u * pb, v_lo = desc_lo(s_u32(sm.v[vs_]));
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks) {
-          mma_f16(tmem + TM_O, p_lo + 2u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
+          mma_f16_ts(tmem + TM_O, p_tm + 8u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
           o_acc = 1;
         }
         commit(&p_empty[pb]);
@@ -314,7 +328,7 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
       o_acc = 1;
       if (++vs_ == NSTV) { vs_ = 0; vp ^= 1; }
     }
-    // O += Pband Ev  (K = 32: two MMAs)
+    // O += Pband Ev  (K = 32: two MMAs, both operands in shared memory)
     bar_wait(pb_full, 0);
     fence_after();
     if (elect1()) {
@@ -326,11 +340,30 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
   } else {
     // ======================================= softmax warps ======================================
     const int qd = warp & 3;
-    const int grp = (warp - 2) >> 2;                    // softmax group: S / P buffer grp, every second key tile
+    const int grp = (warp - 2) >> 2;                    // softmax group: every second key tile, P buffer grp
     const int row = qd * 32 + lane;                     // TMEM lane = query row in the tile
     const int qi = q0 + row;
     const uint32_t lane_base = ((uint32_t)(qd * 32) << 16);
-    const uint32_t s_addr = tmem + lane_base + (grp ? TM_S2 : TM_S);
+    {  // this row's q (pre-scaled, fp16) -> tensor memory: group 0 channels [0, 48), group 1 [48, 96)
+      uint32_t qv[24];
+      if (qi < a.T) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.qkv + ((size_t)b * a.T + qi) * a.ld + h * DKP + grp * 48);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          const uint4 w = __ldg(src + c);
+          qv[c * 4 + 0] = w.x; qv[c * 4 + 1] = w.y; qv[c * 4 + 2] = w.z; qv[c * 4 + 3] = w.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 24; ++c) qv[c] = 0u;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tmem_st8(tmem + lane_base + TM_Q + grp * 24 + c * 8, qv + c * 8);
+      tmem_st_wait();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) bar_arrive(q_ready);
+    }
     // relative-key logits of this row -> smem (dynamic indexing by key offset); written by the row's first warp
     bar_wait(r_full, 0);
     fence_after();
@@ -343,17 +376,18 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
     asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 softmax warps
     float mx = -INFINITY, lsum = 0.f;
     const int total = 2 * ntiles;
-    int it = grp;
+    int it = grp, n = 0;                                // n-th tile of this group -> slot grp + 2 (n & 1)
     // ---- pass 0: row max over this group's key tiles ----
-    for (; it < ntiles; it += 2) {
+    for (; it < ntiles; it += 2, ++n) {
       const int j0 = it * BKV;
-      bar_wait(&s_full[grp], ((uint32_t)it >> 1) & 1u);
+      const int slot = grp + 2 * (n & 1);
+      bar_wait(&s_full[slot], ((uint32_t)n >> 1) & 1u);
       fence_after();
       float s[BKV];
-      tmem_ld64(s_addr, s);
+      tmem_ld64(tmem + lane_base + TM_S + 64u * slot, s);
       fence_before();
       __syncwarp();
-      if (lane == 0) bar_arrive(&s_empty[grp]);         // S is in registers: a later Q K^T may overwrite this buffer
+      if (lane == 0) bar_arrive(&s_empty[slot]);        // S is in registers: a later Q K^T may overwrite this buffer
       if (j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window) {
 #pragma unroll
         for (int c = 0; c < BKV; ++c) {
@@ -372,17 +406,18 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
     sm.xch[0][grp][row] = mx;                           // row max over both groups' tiles
     asm volatile("bar.sync 1, 256;" ::: "memory");
     mx = fmaxf(mx, sm.xch[0][grp ^ 1][row]);
-    // ---- pass 1: probabilities of this group's key tiles -> P buffer grp ----
+    // ---- pass 1: probabilities of this group's key tiles -> P buffer grp (tensor memory) ----
     uint32_t pe = 1;                                    // phase of p_empty[grp] to wait for (first use passes)
-    for (; it < total; it += 2) {
+    for (; it < total; it += 2, ++n) {
       const int j0 = (it - ntiles) * BKV;
-      bar_wait(&s_full[grp], ((uint32_t)it >> 1) & 1u);
+      const int slot = grp + 2 * (n & 1);
+      bar_wait(&s_full[slot], ((uint32_t)n >> 1) & 1u);
       fence_after();
       float s[BKV];
-      tmem_ld64(s_addr, s);
+      tmem_ld64(tmem + lane_base + TM_S + 64u * slot, s);
       fence_before();
       __syncwarp();
-      if (lane == 0) bar_arrive(&s_empty[grp]);
+      if (lane == 0) bar_arrive(&s_empty[slot]);
       const bool band = j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window;
       if (band) {
 #pragma unroll
@@ -396,7 +431,7 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
         for (int c = 0; c < BKV; ++c)
           if (j0 + c >= L) s[c] = -INFINITY;
       }
-      // probabilities (fp16) -> swizzled K-major smem tile; also harvest the band for the Ev term
+      // probabilities (fp16, two keys per 32-bit column); also harvest the band for the Ev term
       uint32_t pk[BKV / 2];
 #pragma unroll
       for (int c = 0; c < BKV; c += 2) {
@@ -418,11 +453,10 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmQ, co
       }
       bar_wait(&p_empty[grp], pe);                      // the P V MMA that last read this buffer has finished
       pe ^= 1u;
-#pragma unroll
-      for (int cc = 0; cc < BKV / 8; ++cc)
-        *reinterpret_cast<uint4*>(sm.p[grp] + row * 128 + ((cc ^ (row & 7)) << 4)) =
-            make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fence_after();
+      tmem_st32(tmem + lane_base + TM_P + 32u * grp, pk);
+      tmem_st_wait();
+      fence_before();
       __syncwarp();
       if (lane == 0) bar_arrive(&p_full[grp]);
     }
@@ -523,12 +557,12 @@ cudaError_t launch_attention_tc(const void* qkv16, void* vt, const void* ek16, c
                                                      ld, 2 * n_heads * DKP, n_heads);
     launch_counter().n++;
   }
-  CUtensorMap tmQ, tmK, tmV, tmEk, tmEv;
+  CUtensorMap tmK, tmV, tmEk, tmEv;
   {
     cuuint64_t dims[3] = {(cuuint64_t)(2 * n_heads * DKP), (cuuint64_t)T, (cuuint64_t)B};   // only the q|k columns are visible
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)T};
-    cuuint32_t boxq[3] = {64, BQ, 1}, boxk[3] = {64, BKV, 1};
-    if (!make_map(&tmQ, qkv16, 3, dims, strides, boxq) || !make_map(&tmK, qkv16, 3, dims, strides, boxk)) return cudaErrorInvalidValue;
+    cuuint32_t boxk[3] = {64, BKV, 1};
+    if (!make_map(&tmK, qkv16, 3, dims, strides, boxk)) return cudaErrorInvalidValue;
     cuuint64_t vd[3] = {(cuuint64_t)T, (cuuint64_t)DKP, (cuuint64_t)(B * n_heads)};          // keys >= T read as zero
     cuuint64_t vs[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)Tp * 2 * DKP};
     cuuint32_t boxv[3] = {BKV, DKV, 1};                                                     // the 96 real d-rows of a head
@@ -544,9 +578,9 @@ cudaError_t launch_attention_tc(const void* qkv16, void* vt, const void* ek16, c
   static SmemOptIn opt;
   if (cudaError_t e = opt_in_smem(attention_tc_kernel, smem, opt)) return e;
   AttArgs a;
-  a.len = len; a.out = reinterpret_cast<__half*>(out); a.T = T; a.n_heads = n_heads; a.window = window; a.H = n_heads * DKV;
+  a.len = len; a.qkv = reinterpret_cast<const __half*>(qkv16); a.ld = ld; a.out = reinterpret_cast<__half*>(out); a.T = T; a.n_heads = n_heads; a.window = window; a.H = n_heads * DKV;
   dim3 grid((T + BQ - 1) / BQ, n_heads, B);
-  cudaError_t le = launch_pdl(attention_tc_kernel, grid, dim3(kThreadsAtt), smem, st, a, tmQ, tmK, tmV, tmEk, tmEv);
+  cudaError_t le = launch_pdl(attention_tc_kernel, grid, dim3(kThreadsAtt), smem, st, a, tmK, tmV, tmEk, tmEv);
   if (le != cudaSuccess) return le;
   launch_counter().n++;
   return cudaGetLastError();
