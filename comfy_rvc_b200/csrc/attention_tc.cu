@@ -6,21 +6,28 @@
 //
 // One CTA = 128 queries of one (batch, head).  All four contractions run on the tensor core:
 //     R  = Q Ek^T           [128 x 32]   once          (the 21 relative-key logits of every query)
-//     S  = Q K^T            [128 x 64]   per key tile, twice (pass 1: row max, pass 2: probabilities)
-//     O += P V              [128 x 96]   per key tile (pass 2)
-//     O += Pband Ev         [128 x 96]   once          (Pband[i][r] = P[i][i+r-w], gathered by the softmax warps)
-// Two passes over the keys avoid rescaling the TMEM accumulator (the extra Q K^T costs 37 % more MMA work on
-// a kernel that is bound by the exp/TMEM traffic of the softmax warps anyway).
+//     S  = Q K^T            [128 x 64]   per key tile
+//     O += P V              [128 x 96]   per key tile
+//     O += Pband Ev         [128 x 96]   once          (Pband[i][r] = P[i][i+r-w])
+// ONE pass over the keys with an online softmax (round 2; the first version made two passes to avoid rescaling the TMEM
+// accumulator, and its extra Q K^T was 38 % of the tensor-pipe time of a kernel that ncu showed to be bound by exactly that
+// -- an M = 128, N = 64, K = 16 MMA keeps the pipe busy ~63 cycles, twice its math time, from shared memory and from tensor
+// memory alike, `profiles/r2_ncu_attention.md`).  A row's running max is raised only when a tile exceeds it by more than
+// kTau (probabilities stay <= e^kTau in fp16), so the rescale of O -- tcgen05.ld / multiply / tcgen05.st by the row's own
+// softmax thread, after the group's previous P V has completed -- happens in the first tiles only.
 //
-// Operands (all K-major, TMA + SWIZZLE_128B): qk16 [B][T][512] = q(h0|h1) k(h0|h1), 128 channels per head
-// (96 + zero pad); vt16 [B*heads][128][Tp] = V transposed (keys contiguous); ek16 [32][128]; evt16 [128][64].
-// Warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = softmax: thread = query row = TMEM lane, two GROUPS of four warps (one
-// per lane quadrant).  Group g owns S buffer g and P buffer g and takes every second key tile whole (64 columns per
-// thread), so the two groups' per-tile chains (S landed -> tcgen05.ld -> exp -> P in smem -> P V) overlap instead of
-// running in lockstep.  Three MMA-issuing warps: warp 1 / warp 10 issue Q K^T for group 0 / 1 (S buffer g, K stages g and
-// g + 2), warp 11 issues P V and the final Pband Ev -- with one issuer the kernel was bound by that single thread's
-// instruction stream (~145 SASS instructions, ~1200 cycles per key tile; the softmax warps sat in their S-landed wait,
-// `profiles/r2_ncu_attention.md`).  Row max and row sum are exchanged between the two groups through shared memory once per pass.
+// Operands: qkv16 [B][T][3*heads*128] = q | k | v, 128 channels per head (96 + zero pad), q pre-scaled; K tiles by TMA
+// (K-major, SWIZZLE_128B); vt16 [B*heads][128][Tp] = V transposed (keys contiguous), 96-row tiles by TMA; ek16 [32][128];
+// evt16 [128][64].  Q and P are MMA A operands in TENSOR MEMORY (tcgen05.mma TS form: lane = row, a 32-bit column holds two
+// fp16 of the row): the softmax threads store their q row once and each tile's probabilities over the head of the tile's own
+// S slot, so neither needs shared memory, a swizzle or a proxy fence.
+// Warps: 0 = TMA producer (lane 0: K ring, lane 1: V ring), 2..9 = softmax, thread = query row = TMEM lane, in two GROUPS of
+// four warps (one per lane quadrant).  Group g takes every second key tile whole (64 columns per thread) and has its OWN
+// accumulator O_g, running max and running sum, so the two groups never synchronise inside the key loop; they are combined
+// at the end (O_0 is brought to the final scale in tensor memory, the band probabilities are formed from the kept band
+// logits at that scale, Pband Ev is accumulated into O_0, O_1 is added in registers).  Three MMA-issuing warps: warp 1 /
+// warp 10 issue Q K^T for group 0 / 1, warp 11 issues P V and Pband Ev -- with ONE issuer the kernel was bound by that
+// thread's instruction stream (~145 SASS instructions, ~1200 cycles per key tile).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -30,11 +37,14 @@
 namespace rvc {
 namespace {
 
-constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 4, NSTV = 4, MAXREL = 21;   // K ring / V ring depths
+constexpr int BQ = 128, BKV = 64, DKP = 128, DKV = 96, NSTG = 4, NSTV = 4, MAXREL = 21;   // K ring (= S slots) / V ring depths
 constexpr int kThreadsAtt = 64 + 256 + 64;   // producer, Q K^T issuer 0, 8 softmax warps, Q K^T issuer 1, P V issuer
-// TMEM columns (512 allocated).  O accumulator, relative-key logits R, the Q tile as an MMA A operand (96 fp16 per lane
-// = 48 columns), one P tile per softmax group as an MMA A operand (64 fp16 = 32 columns), four S buffers (slot = K stage)
-constexpr uint32_t TM_O = 0, TM_R = 96, TM_Q = 128, TM_P = 176, TM_S = 256, TM_COLS = 512;
+// TMEM columns (512 allocated): one O accumulator per softmax group, the relative-key logits R (aliases the head of O_1,
+// dead before the first P V), the Q tile as an MMA A operand (96 fp16 per lane = 48 columns), four S slots; the P tile
+// of a key tile (64 fp16 = 32 columns, MMA A operand) overwrites the head of its own S slot.
+constexpr uint32_t TM_O = 0, TM_R = 96, TM_Q = 192, TM_S = 256, TM_COLS = 512;
+constexpr float kTau = 4.f;                  // a row's running max is raised (and O rescaled) only when exceeded by more than this
+constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
@@ -117,6 +127,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
         "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // SWIZZLE_128B K-major descriptor halves: lo = start>>4 | LBO(1)<<16 ; hi = SBO(1024>>4) | version 1<<14 | SW128 (2)<<29
@@ -206,22 +221,23 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
   uint64_t* e_full = &sm.bars[0];        // Ek | Ev^T landed
   uint64_t* q_ready = &sm.bars[1];       // Q tile stored to tensor memory by the 8 softmax warps
   uint64_t* r_full = &sm.bars[2];
-  uint64_t* pb_full = &sm.bars[3];       // 8 softmax warps
+  uint64_t* pb_full = &sm.bars[3];       // the 4 warps of group 0: O_0 at the final scale, Pband tile written
   uint64_t* o_full = &sm.bars[4];
-  uint64_t* k_full = &sm.bars[8];        // [NSTG]
+  uint64_t* pv_all = &sm.bars[5];        // every P V MMA has completed
+  uint64_t* k_full = &sm.bars[8];        // [NSTG]   key tile it -> slot it & 3: K stage, S buffer, P buffer
   uint64_t* k_empty = &sm.bars[12];      // [NSTG]
   uint64_t* v_full = &sm.bars[16];       // [NSTV]
   uint64_t* v_empty = &sm.bars[20];      // [NSTV]
-  uint64_t* s_full = &sm.bars[24];       // [4]: S buffer = K stage = slot g + 2 (n & 1) of group g's n-th tile
-  uint64_t* s_empty = &sm.bars[28];      // [4], the 4 warps of the slot's group
-  uint64_t* p_full = &sm.bars[32];       // [2], the 4 warps of the group
-  uint64_t* p_empty = &sm.bars[34];      // [2]
+  uint64_t* s_full = &sm.bars[24];       // [4]
+  uint64_t* pv_done = &sm.bars[28];      // [4]  the P V MMA of the slot's tile has completed: slot (S and P) free, O settled
+  uint64_t* p_full = &sm.bars[32];       // [4], the 4 warps of the slot's group
 
   if (threadIdx.x == 0) {
-    bar_init(e_full, 1); bar_init(q_ready, 8); bar_init(r_full, 1); bar_init(pb_full, 8); bar_init(o_full, 1);
-    for (int i = 0; i < NSTG; ++i) { bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); bar_init(&s_full[i], 1); bar_init(&s_empty[i], 4); }
+    bar_init(e_full, 1); bar_init(q_ready, 8); bar_init(r_full, 1); bar_init(pb_full, 4); bar_init(o_full, 1); bar_init(pv_all, 1);
+    for (int i = 0; i < NSTG; ++i) {
+      bar_init(&k_full[i], 1); bar_init(&k_empty[i], 1); bar_init(&s_full[i], 1); bar_init(&pv_done[i], 1); bar_init(&p_full[i], 4);
+    }
     for (int i = 0; i < NSTV; ++i) { bar_init(&v_full[i], 1); bar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { bar_init(&p_full[i], 4); bar_init(&p_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -239,19 +255,18 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
 
   if (warp == 0) {
     // ======================================= TMA producer =======================================
-    // lane 0 streams the relative tables and the K tiles of both passes, lane 1 the V tiles of pass 1: two independent
-    // rings, so that a full V ring never holds back the K tile the next Q K^T is waiting for
+    // lane 0 streams the relative tables and the K tiles, lane 1 the V tiles: two independent rings, so that a full V ring
+    // never holds back the K tile the next Q K^T is waiting for
     if (lane == 0) {
       bar_expect(e_full, 2 * 32 * 128 + DKV * 128);
       for (int kb = 0; kb < 2; ++kb) tma2(sm.ek[kb], &tmEk, kb * 64, 0, e_full);
       tma2(sm.evt, &tmEv, 0, 0, e_full);
       int ks = 0;
       uint32_t kp = 1;
-      for (int it = 0; it < 2 * ntiles; ++it) {
-        const int j0 = (it < ntiles ? it : it - ntiles) * BKV;
+      for (int it = 0; it < ntiles; ++it) {
         bar_wait(&k_empty[ks], kp);
         bar_expect(&k_full[ks], 2 * BKV * 128);
-        for (int kb = 0; kb < 2; ++kb) tma3(sm.k[ks][kb], &tmK, a.n_heads * DKP + h * DKP + kb * 64, j0, b, &k_full[ks]);
+        for (int kb = 0; kb < 2; ++kb) tma3(sm.k[ks][kb], &tmK, a.n_heads * DKP + h * DKP + kb * 64, it * BKV, b, &k_full[ks]);
         if (++ks == NSTG) { ks = 0; kp ^= 1; }
       }
     } else if (lane == 1) {
@@ -280,14 +295,14 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
       }
       __syncwarp();
     }
-    // tile it = g + 2 n of the 2 ntiles (pass 0 then pass 1) lands in slot g + 2 (n & 1): K stage and S buffer
+    // key tile it = g + 2 n lands in slot g + 2 (n & 1)
     const uint32_t k_lo[2] = {desc_lo(s_u32(sm.k[g][0])), desc_lo(s_u32(sm.k[g + 2][0]))};
     constexpr uint32_t kKb = (BKV * 128) >> 4;            // second k-block of a stage, in descriptor units
-    const int mine = ntiles;                             // of the 2 ntiles, every second one
+    const int mine = (ntiles - g + 1) / 2;
     auto issue_qk = [&](int n, int odd) {
       const int slot = g + 2 * odd;
       bar_wait(&k_full[slot], ((uint32_t)n >> 1) & 1u);
-      bar_wait(&s_empty[slot], (((uint32_t)n >> 1) & 1u) ^ 1u);   // the group has read this buffer's previous tile out of TMEM
+      bar_wait(&pv_done[slot], (((uint32_t)n >> 1) & 1u) ^ 1u);   // P V of the slot's previous tile has read its P
       fence_after();
       if (elect1()) {
 #pragma unroll
@@ -307,28 +322,27 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
     const uint32_t id_o = idesc_f16(DKV);
     bar_wait(e_full, 0);                                 // Ev^T
     int vs_ = 0;
-    uint32_t vp = 0, pf0 = 0, pf1 = 0, o_acc = 0;
-    for (int it = ntiles; it < 2 * ntiles; ++it) {
-      const int pb = it & 1;                            // softmax group of this tile
-      bar_wait(&p_full[pb], pb ? pf1 : pf0);            // probabilities of this tile are in tensor memory
-      if (pb) pf1 ^= 1u; else pf0 ^= 1u;
+    uint32_t vp = 0;
+    for (int it = 0; it < ntiles; ++it) {
+      const int slot = it & 3;
+      bar_wait(&p_full[slot], ((uint32_t)it >> 2) & 1u); // probabilities of this tile are in tensor memory
       bar_wait(&v_full[vs_], vp);
       fence_after();
       if (elect1()) {
-        const uint32_t p_tm = tmem + TM_P + 32u * pb, v_lo = desc_lo(s_u32(sm.v[vs_]));
+        const uint32_t p_tm = tmem + TM_S + 64u * slot, v_lo = desc_lo(s_u32(sm.v[vs_]));
+        const uint32_t o_tm = tmem + TM_O + 96u * (it & 1);      // the group's own accumulator
 #pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks) {
-          mma_f16_ts(tmem + TM_O, p_tm + 8u * ks, v_lo + 2u * ks, kDescHi, id_o, o_acc);
-          o_acc = 1;
-        }
-        commit(&p_empty[pb]);
+        for (int ks = 0; ks < BKV / 16; ++ks)
+          mma_f16_ts(o_tm, p_tm + 8u * ks, v_lo + 2u * ks, kDescHi, id_o, (it > 1 || ks) ? 1u : 0u);
+        commit(&pv_done[slot]);
         commit(&v_empty[vs_]);
       }
       __syncwarp();
-      o_acc = 1;
       if (++vs_ == NSTV) { vs_ = 0; vp ^= 1; }
     }
-    // O += Pband Ev  (K = 32: two MMAs, both operands in shared memory)
+    if (elect1()) commit(pv_all);
+    __syncwarp();
+    // O_0 += Pband Ev  (K = 32: two MMAs, both operands in shared memory; O_0 and Pband are at the final scale)
     bar_wait(pb_full, 0);
     fence_after();
     if (elect1()) {
@@ -340,7 +354,7 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
   } else {
     // ======================================= softmax warps ======================================
     const int qd = warp & 3;
-    const int grp = (warp - 2) >> 2;                    // softmax group: every second key tile, P buffer grp
+    const int grp = (warp - 2) >> 2;                    // softmax group: every second key tile, accumulator O_grp
     const int row = qd * 32 + lane;                     // TMEM lane = query row in the tile
     const int qi = q0 + row;
     const uint32_t lane_base = ((uint32_t)(qd * 32) << 16);
@@ -373,104 +387,116 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
 #pragma unroll
       for (int r = 0; r < 24; ++r) sm.rtab[row * 24 + r] = rv[r];
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 softmax warps
-    float mx = -INFINITY, lsum = 0.f;
-    const int total = 2 * ntiles;
-    int it = grp, n = 0;                                // n-th tile of this group -> slot grp + 2 (n & 1)
-    // ---- pass 0: row max over this group's key tiles ----
-    for (; it < ntiles; it += 2, ++n) {
+    fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 softmax warps; R (= head of O_1) is dead from here on
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t o_addr = tmem + lane_base + TM_O + 96u * grp;
+    int n = 0;                                          // n-th tile of this group -> slot grp + 2 (n & 1)
+    for (int it = grp; it < ntiles; it += 2, ++n) {
       const int j0 = it * BKV;
       const int slot = grp + 2 * (n & 1);
+      const uint32_t s_addr = tmem + lane_base + TM_S + 64u * slot;
       bar_wait(&s_full[slot], ((uint32_t)n >> 1) & 1u);
       fence_after();
       float s[BKV];
-      tmem_ld64(tmem + lane_base + TM_S + 64u * slot, s);
-      fence_before();
-      __syncwarp();
-      if (lane == 0) bar_arrive(&s_empty[slot]);        // S is in registers: a later Q K^T may overwrite this buffer
+      tmem_ld64(s_addr, s);
       if (j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window) {
-#pragma unroll
-        for (int c = 0; c < BKV; ++c) {
-          const int r = j0 + c - qi + a.window;
-          if ((unsigned)r < (unsigned)nrel) s[c] += sm.rtab[row * 24 + r];
-        }
-      }
-      if (j0 + BKV > L) {
-#pragma unroll
-        for (int c = 0; c < BKV; ++c)
-          if (j0 + c >= L) s[c] = -INFINITY;
-      }
-#pragma unroll
-      for (int c = 0; c < BKV; ++c) mx = fmaxf(mx, s[c]);
-    }
-    sm.xch[0][grp][row] = mx;                           // row max over both groups' tiles
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    mx = fmaxf(mx, sm.xch[0][grp ^ 1][row]);
-    // ---- pass 1: probabilities of this group's key tiles -> P buffer grp (tensor memory) ----
-    uint32_t pe = 1;                                    // phase of p_empty[grp] to wait for (first use passes)
-    for (; it < total; it += 2, ++n) {
-      const int j0 = (it - ntiles) * BKV;
-      const int slot = grp + 2 * (n & 1);
-      bar_wait(&s_full[slot], ((uint32_t)n >> 1) & 1u);
-      fence_after();
-      float s[BKV];
-      tmem_ld64(tmem + lane_base + TM_S + 64u * slot, s);
-      fence_before();
-      __syncwarp();
-      if (lane == 0) bar_arrive(&s_empty[slot]);
-      const bool band = j0 <= q0 + BQ - 1 + a.window && j0 + BKV - 1 >= q0 - a.window;
-      if (band) {
-#pragma unroll
-        for (int c = 0; c < BKV; ++c) {
-          const int r = j0 + c - qi + a.window;
-          if ((unsigned)r < (unsigned)nrel) s[c] += sm.rtab[row * 24 + r];
-        }
-      }
-      if (j0 + BKV > L) {
-#pragma unroll
-        for (int c = 0; c < BKV; ++c)
-          if (j0 + c >= L) s[c] = -INFINITY;
-      }
-      // probabilities (fp16, two keys per 32-bit column); also harvest the band for the Ev term
-      uint32_t pk[BKV / 2];
-#pragma unroll
-      for (int c = 0; c < BKV; c += 2) {
-        const float p0 = __expf(s[c] - mx), p1 = __expf(s[c + 1] - mx);
-        lsum += p0 + p1;
-        __half2 hp = __floats2half2_rn(p0, p1);
-        pk[c / 2] = *reinterpret_cast<uint32_t*>(&hp);
-      }
-      if (band) {
+        // band: add the relative-key logit and keep the full logit (each band key belongs to exactly one tile): the
+        // probabilities of the Ev term are formed from it at the end, at the final scale
 #pragma unroll
         for (int c = 0; c < BKV; ++c) {
           const int r = j0 + c - qi + a.window;
           if ((unsigned)r < (unsigned)nrel) {
-            const uint32_t w = pk[c / 2];
-            const unsigned short hv = (c & 1) ? (unsigned short)(w >> 16) : (unsigned short)(w & 0xffffu);
-            *reinterpret_cast<unsigned short*>(sm.pband + row * 128 + (((r >> 3) ^ (row & 7)) << 4) + (r & 7) * 2) = hv;
+            s[c] += sm.rtab[row * 24 + r];
+            sm.rtab[row * 24 + r] = s[c];
           }
         }
       }
-      bar_wait(&p_empty[grp], pe);                      // the P V MMA that last read this buffer has finished
-      pe ^= 1u;
-      fence_after();
-      tmem_st32(tmem + lane_base + TM_P + 32u * grp, pk);
+      if (j0 + BKV > L) {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c)
+          if (j0 + c >= L) s[c] = -INFINITY;
+      }
+      float m_t = s[0];
+#pragma unroll
+      for (int c = 1; c < BKV; ++c) m_t = fmaxf(m_t, s[c]);
+      if (__any_sync(0xffffffffu, m_t > m_run + kTau)) {
+        // raise the running max of the warp's rows; O_grp (settled once the group's previous P V has completed) follows
+        const float m_new = fmaxf(m_run, m_t);
+        if (n > 0) {
+          bar_wait(&pv_done[grp + 2 * ((n - 1) & 1)], ((uint32_t)(n - 1) >> 1) & 1u);
+          fence_after();
+          const float sc = ex2f((m_run - m_new) * kLog2e);
+          l_run *= sc;
+#pragma unroll
+          for (int c0 = 0; c0 < DKV; c0 += 32) {
+            float o[32];
+            tmem_ld32(o_addr + c0, o);
+            uint32_t ob[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) ob[c] = __float_as_uint(o[c] * sc);
+            tmem_st32(o_addr + c0, ob);
+          }
+          tmem_st_wait();
+        }
+        m_run = m_new;
+      }
+      // probabilities (fp16, two keys per 32-bit column) -> head of this tile's S slot
+      const float mb = m_run * kLog2e;
+      uint32_t pk[BKV / 2];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 2) {
+        const float p0 = ex2f(fmaf(s[c], kLog2e, -mb)), p1 = ex2f(fmaf(s[c + 1], kLog2e, -mb));
+        l_run += p0 + p1;
+        __half2 hp = __floats2half2_rn(p0, p1);
+        pk[c / 2] = *reinterpret_cast<uint32_t*>(&hp);
+      }
+      tmem_st32(s_addr, pk);
       tmem_st_wait();
       fence_before();
       __syncwarp();
-      if (lane == 0) bar_arrive(&p_full[grp]);
+      if (lane == 0) bar_arrive(&p_full[slot]);
     }
-    // band tile complete -> final MMA, then normalise and store
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) bar_arrive(pb_full);
-    sm.xch[1][grp][row] = lsum;                         // row sum over both groups' tiles
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    lsum += sm.xch[1][grp ^ 1][row];
+    // ---- combine the two groups: final row max / row sum, O_0 and the band probabilities at the final scale ----
+    sm.xch[0][grp][row] = m_run;
+    sm.xch[1][grp][row] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // also: every band logit is in rtab
+    const float m_o = sm.xch[0][grp ^ 1][row], l_o = sm.xch[1][grp ^ 1][row];
+    const int n_o = grp ? (ntiles + 1) / 2 : ntiles / 2;  // tiles of the other group
+    const float m_fin = fmaxf(m_run, m_o);
+    const float f_me = n > 0 ? ex2f((m_run - m_fin) * kLog2e) : 0.f;
+    const float f_o = n_o > 0 ? ex2f((m_o - m_fin) * kLog2e) : 0.f;
+    const float lsum = l_run * f_me + l_o * f_o;
+    if (grp == 0) {
+      bar_wait(pv_all, 0);
+      fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < DKV; c0 += 32) {
+        float o[32];
+        tmem_ld32(o_addr + c0, o);
+        uint32_t ob[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) ob[c] = __float_as_uint(o[c] * f_me);
+        tmem_st32(o_addr + c0, ob);
+      }
+      tmem_st_wait();
+      const float mb = m_fin * kLog2e;
+      for (int r = 0; r < nrel; ++r) {
+        const int j = qi + r - a.window;
+        const float pv = (j >= 0 && j < L) ? ex2f(fmaf(sm.rtab[row * 24 + r], kLog2e, -mb)) : 0.f;
+        *reinterpret_cast<__half*>(sm.pband + row * 128 + (((r >> 3) ^ (row & 7)) << 4) + (r & 7) * 2) = __float2half_rn(pv);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fence_before();
+      __syncwarp();
+      if (lane == 0) bar_arrive(pb_full);
+    }
     bar_wait(o_full, 0);
     fence_after();
     const bool valid = qi < L;
     const float inv = valid ? 1.f / lsum : 0.f;
+    const float f1 = grp ? f_me : f_o;                  // scale of O_1 (O_0 is at the final scale already)
+    const bool has1 = (grp ? n : n_o) > 0;
     __half* orow = a.out + ((size_t)b * a.T + qi) * a.H + h * DKV;
     // output columns: the row's warp of group 0 stores [0, 64), that of group 1 [64, 96)
 #pragma unroll
@@ -478,6 +504,12 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
       if ((c0 < 64) != (grp == 0)) continue;
       float o[32];
       tmem_ld32(tmem + lane_base + TM_O + c0, o);
+      if (has1) {
+        float o1[32];
+        tmem_ld32(tmem + lane_base + TM_O + 96 + c0, o1);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c] = fmaf(o1[c], f1, o[c]);
+      }
       if (qi < a.T) {
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
