@@ -432,9 +432,11 @@ def main():
     # per-class kernel times: a second pass of the same K steps with a CUDA-event pair around every launch (the event
     # records sit between kernels and serialise their programmatic dependent launches, so they stay out of `value`)
     lib.rvcb200_profile_enable(net._ctx, 1)
+    keep_graph, net.graph_max_frames = net.graph_max_frames, 0     # a replayed graph has no per-launch events
     for _ in range(args.steps):
         step_resident()
     torch.cuda.synchronize()
+    net.graph_max_frames = keep_graph
     cls_ms = (C.c_double * 8)()
     cls_n = (C.c_int64 * 8)()
     lib.rvcb200_profile_collect(net._ctx, cls_ms, cls_n)
