@@ -100,7 +100,13 @@ __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t
   int nout = 16, oc = co;
   if (p.gate) {   // commons.py:211-218 on interleaved (tanh, sigmoid) pairs
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = tanhf(v[2 * i]) * sigmoidf_(v[2 * i + 1]);
+    for (int i = 0; i < 8; ++i) {
+      // sigma(x) = 1 / (1 + 2^(-x log2 e)) on the MUFU pipe (ex2 + rcp, ~1e-6), tanh(a) = 2 sigma(2a) - 1: the result is
+      // rounded to fp16 (2.4e-4) right below; the libm forms were ~45 instructions per gate and made this epilogue the
+      // longest phase of the flow.in launches (profiles/r2_trace_generic.md)
+      const float sa = __fdividef(1.f, 1.f + __expf(-2.f * v[2 * i])), sb_ = __fdividef(1.f, 1.f + __expf(-v[2 * i + 1]));
+      v[i] = fmaf(2.f, sa, -1.f) * sb_;
+    }
     nout = 8; oc = co >> 1;
   }
   if (p.pre_slope != 1.f) {
@@ -789,22 +795,31 @@ noise_add_tile_kernel(const float* __restrict__ har, const float* __restrict__ w
 // contiguous; 2 B read + 2 B written per element.  Tiles of TR rows per block; taps, bias and the harmonic-source
 // segment of the tile sit in shared memory; one item = 4 rows (TR/4 apart) x 8 channels so that the 4 loads are in
 // flight together and every weight vector feeds 32 FMAs.
-__global__ void __launch_bounds__(256)
+// ROWS rows per item: 4 for the many-tap stages (every weight vector feeds 32 FMAs), 2 for the few-tap ones, which are
+// bound by HBM and want the occupancy instead (121 registers per thread held the 8-tap stage at 16 warps per SM and
+// 2.6 TB/s, ncu `gpurun_out/prof_noise.ncu-rep`).  Taps sit in shared memory as [k][2][C/8][4]: the two float4 halves of a
+// lane's 8 channels in separate planes, so that a warp's LDS.128 is contiguous (the [k][C] order made every weight load a
+// two-way bank conflict: 40 % of the kernel's shared-memory wavefronts).
+template <int ROWS>
+__global__ void __launch_bounds__(256, ROWS == 4 ? 2 : 4)
 noise_add16_kernel(const float* __restrict__ har, const float* __restrict__ wn, const float* __restrict__ nb,
                    unsigned char* __restrict__ x16, long long L_har, long long L, int C, int k, int s, int pad, float slope,
                    int TR) {
   extern __shared__ __align__(16) unsigned char nsm[];
   const int hs = s + 1;
   const int n_hrows = TR + (k + s - 1) / s;
-  float* sw = reinterpret_cast<float*>(nsm);                       // [k][C] + [C]
+  float* sw = reinterpret_cast<float*>(nsm);                       // [k + 1][2][C/8][4]  (plane k = bias)
   float* sh = sw + (size_t)k * C + C;                              // [n_hrows][hs]
   if (threadIdx.x == 0) pdl_trigger();
-  for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = wn[i];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sw[k * C + i] = nb[i];
+  const int pieces = C / 8, RQ = TR / ROWS;
+  for (int i = threadIdx.x; i < (k + 1) * (C / 4); i += blockDim.x) {   // one float4 = half of a piece
+    const int kk = i / (C / 4), r = i % (C / 4), pc = r >> 1, hf = r & 1;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(kk < k ? wn + (size_t)kk * C : nb) + r);
+    *reinterpret_cast<float4*>(sw + (size_t)kk * C + (size_t)hf * (C / 2) + pc * 4) = w;
+  }
   pdl_wait();
   const int b = blockIdx.y;
   const float* hb = har + (long long)b * L_har;
-  const int pieces = C / 8, RQ = TR / 4;
   const long long n_tiles = (L + TR - 1) / TR;
   for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
     const long long t0 = tl * TR;
@@ -819,32 +834,38 @@ noise_add16_kernel(const float* __restrict__ har, const float* __restrict__ wn, 
       const int pc = idx % pieces, rq = idx / pieces;
       uint4* px0 = reinterpret_cast<uint4*>(x16 + (((long long)b * L + t0 + rq) * C + pc * 8) * 2);
       const long long rstep = (long long)RQ * pieces;              // uint4 elements between the item's rows
-      uint4 xv[4];
+      uint4 xv[ROWS];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xv[j] = (t0 + rq + j * RQ < L) ? px0[j * rstep] : make_uint4(0, 0, 0, 0);
-      float a[4][8];
+      for (int j = 0; j < ROWS; ++j) xv[j] = (t0 + rq + j * RQ < L) ? px0[j * rstep] : make_uint4(0, 0, 0, 0);
+      float a[ROWS][8];
+      const float* wp = sw + pc * 4;
       {
-        const float4 b0 = *reinterpret_cast<const float4*>(sw + k * C + pc * 8), b1 = *reinterpret_cast<const float4*>(sw + k * C + pc * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(wp + (size_t)k * C), b1 = *reinterpret_cast<const float4*>(wp + (size_t)k * C + C / 2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < ROWS; ++j) {
           a[j][0] = b0.x; a[j][1] = b0.y; a[j][2] = b0.z; a[j][3] = b0.w; a[j][4] = b1.x; a[j][5] = b1.y; a[j][6] = b1.z; a[j][7] = b1.w;
         }
       }
       const float* hp = sh + rq * hs;
       const int hstep = RQ * hs;
-      for (int kk = 0, j = 0; kk < k; ++kk) {
-        const float4 w0 = *reinterpret_cast<const float4*>(sw + kk * C + pc * 8), w1 = *reinterpret_cast<const float4*>(sw + kk * C + pc * 8 + 4);
+      // taps in runs of one source row (s taps), the run unrolled by four
+      for (int k0 = 0; k0 < k; k0 += s, hp += hs) {
+        const int run = min(s, k - k0);
+#pragma unroll 4
+        for (int j = 0; j < run; ++j) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wp + (size_t)(k0 + j) * C),
+                       w1 = *reinterpret_cast<const float4*>(wp + (size_t)(k0 + j) * C + C / 2);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float hv = hp[q * hstep + j];
-          a[q][0] = fmaf(hv, w0.x, a[q][0]); a[q][1] = fmaf(hv, w0.y, a[q][1]); a[q][2] = fmaf(hv, w0.z, a[q][2]);
-          a[q][3] = fmaf(hv, w0.w, a[q][3]); a[q][4] = fmaf(hv, w1.x, a[q][4]); a[q][5] = fmaf(hv, w1.y, a[q][5]);
-          a[q][6] = fmaf(hv, w1.z, a[q][6]); a[q][7] = fmaf(hv, w1.w, a[q][7]);
+          for (int q = 0; q < ROWS; ++q) {
+            const float hv = hp[q * hstep + j];
+            a[q][0] = fmaf(hv, w0.x, a[q][0]); a[q][1] = fmaf(hv, w0.y, a[q][1]); a[q][2] = fmaf(hv, w0.z, a[q][2]);
+            a[q][3] = fmaf(hv, w0.w, a[q][3]); a[q][4] = fmaf(hv, w1.x, a[q][4]); a[q][5] = fmaf(hv, w1.y, a[q][5]);
+            a[q][6] = fmaf(hv, w1.z, a[q][6]); a[q][7] = fmaf(hv, w1.w, a[q][7]);
+          }
         }
-        if (++j == s) { j = 0; hp += hs; }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < ROWS; ++q) {
         if (t0 + rq + q * RQ >= L) continue;
         float f[8];
         unpack8(xv[q], f);
@@ -1150,13 +1171,15 @@ cudaError_t launch_noise_add16(const float* har, const float* wn, const float* n
   auto smem_for = [&](int tr) { return sizeof(float) * ((size_t)k * C + C + (size_t)(tr + (k + s - 1) / s) * (s + 1)); };
   while (TR > 8 && smem_for(TR) > 100 * 1024) TR >>= 1;
   const size_t smem = smem_for(TR);
-  static SmemOptIn opt;
-  if (cudaError_t e = opt_in_smem(noise_add16_kernel, smem, opt)) return e;
+  const bool many = k >= 16;                   // 4 rows per item (FMA-bound stages) or 2 (HBM-bound ones, higher occupancy)
+  static SmemOptIn opt4, opt2;
+  if (cudaError_t e = many ? opt_in_smem(noise_add16_kernel<4>, smem, opt4) : opt_in_smem(noise_add16_kernel<2>, smem, opt2)) return e;
   const long long n_tiles = (L + TR - 1) / TR;
   const long long per = smem > 56 * 1024 ? 2 : (smem > 24 * 1024 ? 4 : 8);
   dim3 grid((unsigned)(n_tiles < 148 * per ? n_tiles : 148 * per), B);
-  cudaError_t le = launch_pdl(noise_add16_kernel, grid, dim3(256), smem, st, har, wn, nb, reinterpret_cast<unsigned char*>(x16), L_har,
-                              L, C, k, s, pad, slope, TR);
+  unsigned char* xp = reinterpret_cast<unsigned char*>(x16);
+  cudaError_t le = many ? launch_pdl(noise_add16_kernel<4>, grid, dim3(256), smem, st, har, wn, nb, xp, L_har, L, C, k, s, pad, slope, TR)
+                        : launch_pdl(noise_add16_kernel<2>, grid, dim3(256), smem, st, har, wn, nb, xp, L_har, L, C, k, s, pad, slope, TR);
   launch_counter().n++;
   return le != cudaSuccess ? le : cudaGetLastError();
 }
