@@ -190,6 +190,123 @@ __device__ __forceinline__ void epilogue_generic16(const TcConvDesc& p, uint32_t
   }
 }
 
+// Lean form of the generic epilogue for one whole 128 x 64 tile (the N tile of every text-encoder / flow / HuBERT
+// contraction): the four tcgen05.ld of the row are in flight together, every mode flag is tested once per tile instead of
+// once per 16-column pass, the row's output addresses are formed once.  The pass-by-pass form above costs ~1700 cycles per
+// pass with ONE warp per scheduler running it (a dependent chain of flag tests and 64-bit address arithmetic per pass,
+// 3.6 us per tile, profiles/r2_trace_generic.md); it stays for the other N and the modes not listed in `lean_ok`.
+__device__ __forceinline__ bool lean_ok(const TcConvDesc& p) {
+  return p.N == 64 && p.f32_cl && !p.gather && p.alpha == 1.f && p.pre_slope == 1.f && p.div == 1.f && !p.out_bf16 &&
+         p.out_slope == 1.f && !(p.res32 && p.accum) && !(p.gate && (p.res32 || p.accum || p.y32 || p.relu || p.gelu));
+}
+__device__ __forceinline__ void epilogue_lean64(const TcConvDesc& p, uint32_t taddr, bool row_ok, bool valid, int b, long long orow,
+                                                int co, const float* sb, const float4* pre, bool have_pre) {
+  uint32_t r[64];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[q * 16 + 0]), "=r"(r[q * 16 + 1]), "=r"(r[q * 16 + 2]), "=r"(r[q * 16 + 3]), "=r"(r[q * 16 + 4]),
+          "=r"(r[q * 16 + 5]), "=r"(r[q * 16 + 6]), "=r"(r[q * 16 + 7]), "=r"(r[q * 16 + 8]), "=r"(r[q * 16 + 9]),
+          "=r"(r[q * 16 + 10]), "=r"(r[q * 16 + 11]), "=r"(r[q * 16 + 12]), "=r"(r[q * 16 + 13]), "=r"(r[q * 16 + 14]),
+          "=r"(r[q * 16 + 15])
+        : "r"(taddr + 16u * q));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (!row_ok) return;
+  const long long Lout = (long long)p.Lj * p.out_stride;
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 64; i += 4) {
+    const float4 bq = *reinterpret_cast<const float4*>(sb + i);
+    v[i] = __uint_as_float(r[i]) + bq.x; v[i + 1] = __uint_as_float(r[i + 1]) + bq.y;
+    v[i + 2] = __uint_as_float(r[i + 2]) + bq.z; v[i + 3] = __uint_as_float(r[i + 3]) + bq.w;
+  }
+  const size_t rowi = (size_t)b * Lout + orow;
+  if (p.gate) {   // 32 gated channels -> 16-bit only (lean_ok)
+    uint4 o[4];
+    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float g2[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float sa = __fdividef(1.f, 1.f + __expf(-2.f * v[2 * (i + e)])), sg = __fdividef(1.f, 1.f + __expf(-v[2 * (i + e) + 1]));
+        g2[e] = fmaf(2.f, sa, -1.f) * sg;
+      }
+      if (p.mask_pre && !valid) { g2[0] = 0.f; g2[1] = 0.f; }
+      ow[i >> 1] = pack2(false, g2[0], g2[1]);
+    }
+    if ((p.mask16 || p.mask_post) && !valid) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = make_uint4(0, 0, 0, 0);
+    }
+    if (p.y16) {
+      const int ctot = p.Cout_total / 2, ld16 = p.ldy16 ? p.ldy16 : ctot;
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.y16) + (rowi * ld16 + (co >> 1)) * 2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = o[q];
+    }
+    return;
+  }
+  if (p.gelu) {   // exact GELU (torch.nn.functional.gelu default)
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+  }
+  if (p.mask_pre && !valid) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+  }
+  if (p.res32) {
+    const float4* rp = reinterpret_cast<const float4*>(p.res32 + rowi * p.ldr32 + co);
+    if (p.res_mode == 2) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 q = have_pre ? pre[k] : rp[k];
+        v[4 * k] = q.x - v[4 * k]; v[4 * k + 1] = q.y - v[4 * k + 1]; v[4 * k + 2] = q.z - v[4 * k + 2]; v[4 * k + 3] = q.w - v[4 * k + 3];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 q = have_pre ? pre[k] : rp[k];
+        v[4 * k] += q.x; v[4 * k + 1] += q.y; v[4 * k + 2] += q.z; v[4 * k + 3] += q.w;
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  float4* yp = p.y32 ? reinterpret_cast<float4*>(p.y32 + rowi * p.ldy32 + co) : nullptr;
+  if (p.accum) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 q = have_pre ? pre[k] : yp[k];
+      v[4 * k] += q.x; v[4 * k + 1] += q.y; v[4 * k + 2] += q.z; v[4 * k + 3] += q.w;
+    }
+  }
+  if (p.mask_post && !valid) {
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = 0.f;
+  }
+  if (yp) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) yp[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  }
+  if (p.y16) {
+    const int ld16 = p.ldy16 ? p.ldy16 : p.Cout_total;
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(p.y16) + (rowi * ld16 + co) * 2);
+    const bool z16 = p.mask16 && !valid;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint4 o;
+      o.x = pack2(false, v[8 * k], v[8 * k + 1]); o.y = pack2(false, v[8 * k + 2], v[8 * k + 3]);
+      o.z = pack2(false, v[8 * k + 4], v[8 * k + 5]); o.w = pack2(false, v[8 * k + 6], v[8 * k + 7]);
+      if (z16) o = make_uint4(0, 0, 0, 0);
+      dst[k] = o;
+    }
+  }
+}
+
 template <bool GENERIC>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -538,6 +655,7 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
     const bool simple = n_nt == 1 && p.G == 1;      // resblock convs: tile -> (batch, m-tile) with one division
     const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(eg * p.N);
     uint32_t ocnt = 0;                              // staged output boxes so far (tma_out)
+    const bool lean = GENERIC && !p.reserved1 && lean_ok(p);   // reserved1: launcher's RVCB200_LEAN_EPI=0 (A/B switch)
     for (int t = eg; t < my_tiles; t += 2) {
       int mt, nt = 0, g = 0, b = 0;
       const unsigned tile = blockIdx.x + (unsigned)t * gridDim.x;
@@ -579,7 +697,9 @@ conv_tc_kernel(const TcConvDesc p, const __grid_constant__ CUtensorMap tmA, cons
       mbar_wait(&acc_full[eg], (t >> 1) & 1);
       tc_fence_after();
       if (t == 0 && warp == 2 && lane == 0) trace_mark(5);                  // first tile: accumulator complete
-      if (GENERIC) {
+      if (GENERIC && lean) {
+        epilogue_lean64(p, tbase, row_ok, valid, b, orow, nt * p.N, sb, pre, have_pre);
+      } else if (GENERIC) {
 #pragma unroll 1
         for (int c0 = 0; c0 < p.N; c0 += 16) {
           float4 pq[4];                                  // this pass's 16 prefetched words (static indices: registers)
@@ -1009,6 +1129,10 @@ cudaError_t launch_conv_tc(const TcConvDesc& d_in, int B, cudaStream_t st) {
     return cudaErrorInvalidValue;
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return cudaErrorNotSupported;
+  {
+    static const int lean_on = [] { const char* e = getenv("RVCB200_LEAN_EPI"); return e ? atoi(e) : 1; }();
+    d.reserved1 = lean_on ? 0 : 1;
+  }
   d.batch = B;
   int cols = 32;
   while (cols < 2 * d.N) cols <<= 1;          // two accumulator buffers

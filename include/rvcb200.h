@@ -237,7 +237,7 @@ typedef struct rvcb200_tc_conv_desc {
   int32_t b_group;             /* filled in by the launcher: weight tiles per ring stage (non-resident weights) */
   int32_t a_nt_stride;         /* grouped convolution (generic, G = 1): N tile nt reads input channels [nt * a_nt_stride, + Cin) of
                                 * x16 (row stride ldx16); 0 = every N tile reads channels [0, Cin) */
-  int32_t reserved1;
+  int32_t reserved1;           /* set by the launcher: 1 = pass-by-pass generic epilogue only (RVCB200_LEAN_EPI=0) */
 } rvcb200_tc_conv_desc;
 int rvcb200_op_conv_tc(const rvcb200_tc_conv_desc* d, int32_t B, void* stream);
 
