@@ -17,8 +17,8 @@
 // softmax thread, after the group's previous P V has completed -- happens in the first tiles only.
 //
 // Operands: qkv16 [B][T][3*heads*128] = q | k | v, 128 channels per head (96 + zero pad), q pre-scaled; K tiles by TMA
-// (K-major, SWIZZLE_128B); vt16 [B*heads][128][Tp] = V transposed (keys contiguous), 96-row tiles by TMA; ek16 [32][128];
-// evt16 [128][64].  Q and P are MMA A operands in TENSOR MEMORY (tcgen05.mma TS form: lane = row, a 32-bit column holds two
+// (K-major, SWIZZLE_128B); V tiles by TMA from the same rows, keys x channels as the projection wrote them, consumed as an
+// MN-major B operand (no transposed copy; the `vt` scratch argument of the launcher is unused); ek16 [32][128]; evt16 [128][64].  Q and P are MMA A operands in TENSOR MEMORY (tcgen05.mma TS form: lane = row, a 32-bit column holds two
 // fp16 of the row): the softmax threads store their q row once and each tile's probabilities over the head of the tile's own
 // S slot, so neither needs shared memory, a swizzle or a proxy fence.
 // Warps: 0 = TMA producer (lane 0: K ring, lane 1: V ring), 2..9 = softmax, thread = query row = TMEM lane, in two GROUPS of
@@ -177,7 +177,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
 
 struct AttSmem {                        // 1024-byte aligned tiles, all [rows][128 B] swizzled
   unsigned char k[NSTG][2][BKV * 128];  // 2 k-blocks of 64 channels
-  unsigned char v[NSTV][DKV * 128];     // V^T tile: 96 d-rows x 64 keys
+  unsigned char v[NSTV][2][BKV * 128];  // V tile as it lies in q|k|v: 64 keys x (2 blocks of 64 channels), MN-major B operand
   unsigned char pband[BQ * 128];        // P[i][i+r-w], r < 21 (columns >= 21 stay zero)
   unsigned char ek[2][32 * 128];
   unsigned char evt[DKV * 128];
@@ -274,8 +274,8 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
       uint32_t vp = 1;
       for (int t = 0; t < ntiles; ++t) {
         bar_wait(&v_empty[vs], vp);
-        bar_expect(&v_full[vs], DKV * 128);
-        tma3(sm.v[vs], &tmV, t * BKV, 0, b * a.n_heads + h, &v_full[vs]);
+        bar_expect(&v_full[vs], 2 * BKV * 128);
+        for (int db = 0; db < 2; ++db) tma3(sm.v[vs][db], &tmV, 2 * a.n_heads * DKP + h * DKP + db * 64, t * BKV, b, &v_full[vs]);
         if (++vs == NSTV) { vs = 0; vp ^= 1; }
       }
     }
@@ -319,7 +319,11 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
     if (n < mine) issue_qk(n, 0);
   } else if (warp == 11) {
     // ======================================= P V issuer =========================================
-    const uint32_t id_o = idesc_f16(DKV);
+    // V is read where the q|k|v projection wrote it, keys x channels: an MN-major B operand (idesc bit 16; canonical
+    // SWIZZLE_128B layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: 64 channels contiguous, key rows 128 B apart,
+    // SBO = 1024 B between groups of 8 keys, LBO = 8192 B between the two 64-channel blocks); N = 96 takes the first
+    // block and half of the second.  No transposed copy of V.
+    const uint32_t id_o = idesc_f16(DKV), id_ov = id_o | (1u << 16);
     bar_wait(e_full, 0);                                 // Ev^T
     int vs_ = 0;
     uint32_t vp = 0;
@@ -329,11 +333,12 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
       bar_wait(&v_full[vs_], vp);
       fence_after();
       if (elect1()) {
-        const uint32_t p_tm = tmem + TM_S + 64u * slot, v_lo = desc_lo(s_u32(sm.v[vs_]));
+        const uint32_t p_tm = tmem + TM_S + 64u * slot;
+        const uint32_t v_lo = ((s_u32(sm.v[vs_][0]) >> 4) & 0x3FFFu) | ((uint32_t)((BKV * 128) >> 4) << 16);
         const uint32_t o_tm = tmem + TM_O + 96u * (it & 1);      // the group's own accumulator
 #pragma unroll
         for (int ks = 0; ks < BKV / 16; ++ks)
-          mma_f16_ts(o_tm, p_tm + 8u * ks, v_lo + 2u * ks, kDescHi, id_o, (it > 1 || ks) ? 1u : 0u);
+          mma_f16_ts(o_tm, p_tm + 8u * ks, v_lo + 128u * ks, kDescHi, id_ov, (it > 1 || ks) ? 1u : 0u);   // 16 keys = 2048 B
         commit(&pv_done[slot]);
         commit(&v_empty[vs_]);
       }
@@ -532,24 +537,6 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
   }
 }
 
-// V part of the fused q|k|v projection -> V^T per (batch, head): vt[b*heads+h][d][t], keys contiguous
-__global__ void transpose_v_kernel(const __half* __restrict__ qkv16, __half* __restrict__ vt, int T, int Tp, int ld, int voff,
-                                   int n_heads) {
-  __shared__ __half tile[32][34];
-  const int bh = blockIdx.z, b = bh / n_heads, h = bh % n_heads;
-  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-  const int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
-  for (int r = ty; r < 32; r += 8) {
-    const int t = t0 + r;
-    tile[r][tx] = t < T ? qkv16[((size_t)b * T + t) * ld + voff + h * DKP + d0 + tx] : __float2half(0.f);
-  }
-  __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int t = t0 + tx;
-    if (t < Tp) vt[((size_t)bh * DKP + d0 + r) * Tp + t] = tile[tx][r];
-  }
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -575,30 +562,22 @@ bool make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dim
 
 }  // namespace
 
-// qkv16: [B][T][3*heads*128] fp16 (q | k | v, 128 channels per head, q pre-scaled); vt: scratch [B*heads][128][Tp];
+// qkv16: [B][T][3*heads*128] fp16 (q | k | v, 128 channels per head, q pre-scaled); vt: unused (was the V^T scratch);
 // ek16 [32][128], evt16 [128][64]; out: [B][T][heads*96] fp16.
 cudaError_t launch_attention_tc(const void* qkv16, void* vt, const void* ek16, const void* evt16, const int* len, void* out,
                                 int B, int T, int n_heads, int dk, int window, cudaStream_t st) {
   if (dk != DKV || 2 * window + 1 > MAXREL || B <= 0 || T <= 0 || n_heads < 1) return cudaErrorInvalidValue;
   if (!att_encode_tiled()) return cudaErrorNotSupported;
   const int ld = 3 * n_heads * DKP;
-  const int Tp = (T + 7) & ~7;
-  {
-    dim3 grid((Tp + 31) / 32, DKP / 32, B * n_heads);
-    transpose_v_kernel<<<grid, dim3(32, 8), 0, st>>>(reinterpret_cast<const __half*>(qkv16), reinterpret_cast<__half*>(vt), T, Tp,
-                                                     ld, 2 * n_heads * DKP, n_heads);
-    launch_counter().n++;
-  }
+  (void)vt;   // the transposed copy of V is no longer made (the scratch argument stays in the ABI)
   CUtensorMap tmK, tmV, tmEk, tmEv;
   {
     cuuint64_t dims[3] = {(cuuint64_t)(2 * n_heads * DKP), (cuuint64_t)T, (cuuint64_t)B};   // only the q|k columns are visible
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)T};
     cuuint32_t boxk[3] = {64, BKV, 1};
     if (!make_map(&tmK, qkv16, 3, dims, strides, boxk)) return cudaErrorInvalidValue;
-    cuuint64_t vd[3] = {(cuuint64_t)T, (cuuint64_t)DKP, (cuuint64_t)(B * n_heads)};          // keys >= T read as zero
-    cuuint64_t vs[2] = {(cuuint64_t)Tp * 2, (cuuint64_t)Tp * 2 * DKP};
-    cuuint32_t boxv[3] = {BKV, DKV, 1};                                                     // the 96 real d-rows of a head
-    if (!make_map(&tmV, vt, 3, vd, vs, boxv)) return cudaErrorInvalidValue;
+    cuuint64_t vd[3] = {(cuuint64_t)ld, (cuuint64_t)T, (cuuint64_t)B};                        // the whole q|k|v row; keys >= T read as zero
+    if (!make_map(&tmV, qkv16, 3, vd, strides, boxk)) return cudaErrorInvalidValue;
     cuuint64_t ekd[2] = {DKP, 32}, eks[1] = {DKP * 2};
     cuuint32_t boxek[2] = {64, 32};
     if (!make_map(&tmEk, ek16, 2, ekd, eks, boxek)) return cudaErrorInvalidValue;

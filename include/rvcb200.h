@@ -265,7 +265,7 @@ int rvcb200_op_attention_f32(const float* qkv, const float* rel_k, const float* 
                              void* stream);
 
 /* tcgen05 attention (csrc/attention_tc.cu): qkv16 [B][T][3*heads*128] fp16 (q|k|v, 128 channels per head = dk + zero
- * pad, q pre-scaled by 1/sqrt(dk)), vt scratch [B*heads][128][roundup(T,8)] fp16, ek16 [32][128], evt16 [128][64] fp16
+ * pad, q pre-scaled by 1/sqrt(dk)), vt: unused since V is read in place as an MN-major operand (may be NULL), ek16 [32][128], evt16 [128][64] fp16
  * relative tables, out [B][T][heads*dk] fp16. */
 int rvcb200_op_attention_tc(const void* qkv16, void* vt, const void* ek16, const void* evt16, const int32_t* len, void* out,
                             int32_t B, int32_t T, int32_t n_heads, int32_t dk, int32_t window, void* stream);
