@@ -201,7 +201,7 @@ Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws, int precision = RVC
     p.att16 = bp.take<unsigned short>(BT * H);
     p.ffh16 = bp.take<unsigned short>(BT * cf.filter_channels);
     p.h16 = bp.take<unsigned short>(BT * H);
-    p.acts16 = bp.take<unsigned short>(BT * H);
+    p.acts16 = bp.take<unsigned short>(BT * H * (cf.flow_wn_layers > 0 ? cf.flow_wn_layers : 1));   // [BT][n H]: every layer's gate output
     p.skip16 = bp.take<unsigned short>(BT * H);
     p.qkv16 = bp.take<unsigned short>(BT * 3 * cf.n_heads * 128);
     p.vt16 = bp.take<unsigned short>((size_t)B * cf.n_heads * 128 * ((T + 7) & ~7));
@@ -752,32 +752,31 @@ static int infer_impl(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone
           d.ldx16 = C; d.mask_post = 1; d.y32 = pl.h; d.ldy32 = H; d.y16 = pl.h16;
           TCG(5, d, "flow.pre(tc)");
         }
+        // every layer's gate output stays in its own H columns of acts [BT][n H]: the skip sums and `post` are one
+        // contraction over all of them at the end (folded weights, weights.py `flow.%d.sp.w`)
+        const int AH = f.flow_wn_layers * H;
+        unsigned short* acts = reinterpret_cast<unsigned short*>(pl.acts16);
         for (int j = 0; j < f.flow_wn_layers; ++j) {
-          {  // acts = gate(in_layer(h) + cond)
+          {  // acts_j = gate(in_layer(h) + cond)
             TcConvDesc d = gen(pl.h16, H, S("flow.%d.in.%d.w", i, j), S("flow.%d.in.%d.b", i, j), 2 * H);
             d.ntaps = f.flow_kernel; d.g_off[0] = -(f.flow_kernel - 1) / 2;
             d.cond = pl.cond + f.up_init_channels + (i * f.flow_wn_layers + j) * 2 * H; d.cond_bstride = ctx->n_cond;
-            d.gate = 1; d.y16 = pl.acts16;
+            d.gate = 1; d.y16 = acts + j * H; d.ldy16 = AH;
             TCG(5, d, "flow.in(tc)");
           }
           if (j < f.flow_wn_layers - 1) {  // h = (h + res)*mask
-            TcConvDesc d = gen(pl.acts16, H, S("flow.%d.rs.%d.res.w", i, j), S("flow.%d.rs.%d.res.b", i, j), H);
+            TcConvDesc d = gen(acts + j * H, H, S("flow.%d.rs.%d.res.w", i, j), S("flow.%d.rs.%d.res.b", i, j), H);
+            d.ldx16 = AH;
             d.res32 = pl.h; d.ldr32 = H; d.res_mode = 1; d.mask_post = 1; d.y32 = pl.h; d.ldy32 = H; d.y16 = pl.h16;
             TCG(5, d, "flow.res(tc)");
           }
-          {  // output += skip; the last layer also emits the masked fp16 copy that feeds `post`
-            TcConvDesc d = gen(pl.acts16, H, S("flow.%d.rs.%d.skip.w", i, j), S("flow.%d.rs.%d.skip.b", i, j), H);
-            d.y32 = pl.skip; d.ldy32 = H; d.accum = j > 0;
-            if (j == f.flow_wn_layers - 1) { d.y16 = pl.skip16; d.mask16 = 1; }
-            TCG(5, d, "flow.skip(tc)");
-          }
         }
-        {  // x1 = (x1 - post(out*mask)*mask)*mask, fp32 in place + fp16 copy into the z operand
-          TcConvDesc d = gen(pl.skip16, H, S("flow.%d.post.w", i), S("flow.%d.post.b", i), half);
+        {  // x1 = (x1 - post(sum_j skip_j(acts_j))*mask)*mask, fp32 in place + fp16 copy into the z operand
+          TcConvDesc d = gen(acts, AH, S("flow.%d.sp.w", i), S("flow.%d.sp.b", i), half);
           d.mask_pre = 1; d.mask_post = 1;
           d.res32 = z + out_off; d.ldr32 = C; d.res_mode = 2; d.y32 = z + out_off; d.ldy32 = C;
           d.y16 = const_cast<unsigned short*>(z16) + out_off; d.ldy16 = C;
-          TCG(5, d, "flow.post(tc)");
+          TCG(5, d, "flow.skip+post(tc)");
         }
       }
     }

@@ -203,6 +203,15 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
             else:
                 P[f"flow.{i}.rs.{j}.skip.w"] = rs_w.t().contiguous()
                 P[f"flow.{i}.rs.{j}.skip.b"] = rs_b.contiguous()
+        # Tensor path: `post(sum_j skip_j(acts_j))` (modules.py:196-209 then :497-505) is a chain of 1x1 convolutions with
+        # nothing non-linear between them, so the n skip launches and the post launch of a flow are ONE contraction of
+        # the concatenated gate outputs [acts_0 | acts_1 | ...] (K = n H) with the folded weights W_skip_j W_post
+        # (products in float64); masked frames are zeroed by the output mask either way.
+        wp64 = P[f"flow.{i}.post.w"].double()
+        P[f"flow.{i}.sp.w"] = torch.cat([P[f"flow.{i}.rs.{j}.skip.w"].double() @ wp64 for j in range(cfg.flow_wn_layers)],
+                                        dim=0).float().contiguous()            # [n H][half]
+        P[f"flow.{i}.sp.b"] = (sum(P[f"flow.{i}.rs.{j}.skip.b"].double() for j in range(cfg.flow_wn_layers)) @ wp64
+                               + P[f"flow.{i}.post.b"].double()).float().contiguous()
     P["cond.w"] = torch.cat(cond_w, dim=0).contiguous()
     P["cond.b"] = torch.cat(cond_b, dim=0).contiguous()
     # ---- GeneratorNSF ----
@@ -289,9 +298,9 @@ def tc_weight_names(cfg: SynthConfig):
     for l in range(cfg.n_layers):
         names += [f"enc.{l}.qkv.w", f"enc.{l}.qkvp.w", f"enc.{l}.o.w", f"enc.{l}.ffn1.w", f"enc.{l}.ffn2.w"]
     for i in range(cfg.n_flows):
-        names += [f"flow.{i}.pre.w", f"flow.{i}.post.w"]
+        names += [f"flow.{i}.pre.w", f"flow.{i}.sp.w"]
         for j in range(cfg.flow_wn_layers):
-            names += [f"flow.{i}.in.{j}.w", f"flow.{i}.rs.{j}.skip.w"]
+            names.append(f"flow.{i}.in.{j}.w")
             if j < cfg.flow_wn_layers - 1:
                 names.append(f"flow.{i}.rs.{j}.res.w")
     nk = cfg.num_kernels

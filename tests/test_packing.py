@@ -62,7 +62,12 @@ def test_flow_packing_matches_oracle(cfg_name):
                 h = (h + conv_cl(acts, P[f"flow.{i}.rs.{j}.res.w"][None, None], P[f"flow.{i}.rs.{j}.res.b"])) * m3
             sk = conv_cl(acts, P[f"flow.{i}.rs.{j}.skip.w"][None, None], P[f"flow.{i}.rs.{j}.skip.b"])
             skip = sk if skip is None else skip + sk
+            acts_all = acts if j == 0 else torch.cat([acts_all, acts], dim=-1)
         m = conv_cl(skip, P[f"flow.{i}.post.w"][None, None], P[f"flow.{i}.post.b"], in_len=lens) * m3
+        # the tensor path's folded form (engine.cu "flow.skip+post"): one contraction of [acts_0 | acts_1 | ...] with W_skip_j W_post
+        m_fold = conv_cl(acts_all, P[f"flow.{i}.sp.w"][None, None], P[f"flow.{i}.sp.b"], in_len=lens) * m3
+        assert P[f"flow.{i}.sp.w"].shape == (cfg.flow_wn_layers * H, half)
+        torch.testing.assert_close(m_fold, m, rtol=0, atol=2e-7)          # the folded weights are stored in float32
         z[:, :, out_off:out_off + half] = (z[:, :, out_off:out_off + half] - m) * m3
     torch.testing.assert_close(z.transpose(1, 2), ref, rtol=1e-10, atol=1e-10)
     # dec.cond is the first block of the stacked conditioning matrix
