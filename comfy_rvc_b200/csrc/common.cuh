@@ -105,6 +105,8 @@ cudaError_t launch_cond_gemv(const float* emb_g, const long long* sid, const flo
                              int B, int gin, int n_out, int n_spk, cudaStream_t st);
 
 // z_p[b][t][c] = (m + exp(logs) * noise[b][c][t] * 0.66666) masked   (models.py:685/801)
+cudaError_t launch_flow_x0_init(const void* z16, const int* len, void* abuf, int B, int T, int C, int in_off, int half, int xb, int aw,
+                                cudaStream_t st);
 cudaError_t launch_zp_sample(const float* stats, const float* noise_cf, const int* len, float* zp, int B, int T, int C,
                              cudaStream_t st, float* z = nullptr, void* z16 = nullptr);
 

@@ -201,7 +201,8 @@ Plan make_plan(const rvcb200_ctx* c, int B, int T, void* ws, int precision = RVC
     p.att16 = bp.take<unsigned short>(BT * H);
     p.ffh16 = bp.take<unsigned short>(BT * cf.filter_channels);
     p.h16 = bp.take<unsigned short>(BT * H);
-    p.acts16 = bp.take<unsigned short>(BT * H * (cf.flow_wn_layers > 0 ? cf.flow_wn_layers : 1));   // [BT][n H]: every layer's gate output
+    // flow activation buffer [BT][xb + n H]: [x0 | mask | zeros] (xb columns) then every layer's gate output
+    p.acts16 = bp.take<unsigned short>(BT * ((size_t)((C / 2 + 1 + 63) / 64 * 64) + (size_t)H * (cf.flow_wn_layers > 0 ? cf.flow_wn_layers : 1)));
     p.skip16 = bp.take<unsigned short>(BT * H);
     p.qkv16 = bp.take<unsigned short>(BT * 3 * cf.n_heads * 128);
     p.vt16 = bp.take<unsigned short>((size_t)B * cf.n_heads * 128 * ((T + 7) & ~7));
@@ -742,43 +743,40 @@ static int infer_impl(rvcb200_ctx* ctx, int32_t B, int32_t T, const float* phone
     CK(tp.emit("z_p", zp, sizeof(float) * BT * C), "tap");
     }
     {
+      // Reverse coupling layers on folded weights (weights.py): per flow n in_layer launches + ONE skip/post launch, no h.
+      // Activation buffer `acts` [BT][AW]: columns [0, xb) = [x0 | mask | zeros], then the n gate outputs (H columns each).
+      // in_layer j reads columns [0, xb + j H) (x0, mask, acts_0..j-1: `pre` and the res convolutions are in its weights)
+      // and writes acts_j (masked: its neighbours read it through a 5-tap window); the last launch contracts all gate
+      // outputs with W_skip_j W_post, updates the other half of z in fp32 and writes its fp16 copy into columns [0, half):
+      // after the Flip it is the next flow's x0.
       bool flipped = false;
-      const unsigned short* z16 = reinterpret_cast<const unsigned short*>(pl.z16);
+      const int n_wn = f.flow_wn_layers;
+      const int xb = (half + 1 + 63) / 64 * 64, AW = xb + n_wn * H;
+      unsigned short* acts = reinterpret_cast<unsigned short*>(pl.acts16);
+      CKC(3, launch_flow_x0_init(pl.z16, pl.len32, acts, B, T, C, /*in_off of the first flow*/ half, half, xb, AW, st), "flow.x0");
       for (int i = f.n_flows - 1; i >= 0; --i) {
         flipped = !flipped;
         const int in_off = flipped ? half : 0, out_off = half - in_off;
-        {  // h = pre(x0)*mask
-          TcConvDesc d = gen(z16 + in_off, half, S("flow.%d.pre.w", i), S("flow.%d.pre.b", i), H);
-          d.ldx16 = C; d.mask_post = 1; d.y32 = pl.h; d.ldy32 = H; d.y16 = pl.h16;
-          TCG(5, d, "flow.pre(tc)");
+        (void)in_off;
+        for (int j = 0; j < n_wn; ++j) {  // acts_j = gate(in_layer(h_j) + cond) * mask
+          TcConvDesc d = gen(acts, xb + j * H, S("flow.%d.inf.%d.w", i, j), S("flow.%d.in.%d.b", i, j), 2 * H);
+          d.ldx16 = AW;
+          d.ntaps = f.flow_kernel; d.g_off[0] = -(f.flow_kernel - 1) / 2;
+          d.cond = pl.cond + f.up_init_channels + (i * n_wn + j) * 2 * H; d.cond_bstride = ctx->n_cond;
+          d.gate = 1; d.mask16 = 1; d.y16 = acts + xb + j * H; d.ldy16 = AW;
+          TCG(5, d, "flow.in(tc)");
         }
-        // every layer's gate output stays in its own H columns of acts [BT][n H]: the skip sums and `post` are one
-        // contraction over all of them at the end (folded weights, weights.py `flow.%d.sp.w`)
-        const int AH = f.flow_wn_layers * H;
-        unsigned short* acts = reinterpret_cast<unsigned short*>(pl.acts16);
-        for (int j = 0; j < f.flow_wn_layers; ++j) {
-          {  // acts_j = gate(in_layer(h) + cond)
-            TcConvDesc d = gen(pl.h16, H, S("flow.%d.in.%d.w", i, j), S("flow.%d.in.%d.b", i, j), 2 * H);
-            d.ntaps = f.flow_kernel; d.g_off[0] = -(f.flow_kernel - 1) / 2;
-            d.cond = pl.cond + f.up_init_channels + (i * f.flow_wn_layers + j) * 2 * H; d.cond_bstride = ctx->n_cond;
-            d.gate = 1; d.y16 = acts + j * H; d.ldy16 = AH;
-            TCG(5, d, "flow.in(tc)");
-          }
-          if (j < f.flow_wn_layers - 1) {  // h = (h + res)*mask
-            TcConvDesc d = gen(acts + j * H, H, S("flow.%d.rs.%d.res.w", i, j), S("flow.%d.rs.%d.res.b", i, j), H);
-            d.ldx16 = AH;
-            d.res32 = pl.h; d.ldr32 = H; d.res_mode = 1; d.mask_post = 1; d.y32 = pl.h; d.ldy32 = H; d.y16 = pl.h16;
-            TCG(5, d, "flow.res(tc)");
-          }
-        }
-        {  // x1 = (x1 - post(sum_j skip_j(acts_j))*mask)*mask, fp32 in place + fp16 copy into the z operand
-          TcConvDesc d = gen(acts, AH, S("flow.%d.sp.w", i), S("flow.%d.sp.b", i), half);
+        {  // x1 = (x1 - post(sum_j skip_j(acts_j))*mask)*mask, fp32 in place; fp16 copy = the next flow's x0
+          TcConvDesc d = gen(acts + xb, n_wn * H, S("flow.%d.sp.w", i), S("flow.%d.sp.b", i), half);
+          d.ldx16 = AW;
           d.mask_pre = 1; d.mask_post = 1;
           d.res32 = z + out_off; d.ldr32 = C; d.res_mode = 2; d.y32 = z + out_off; d.ldy32 = C;
-          d.y16 = const_cast<unsigned short*>(z16) + out_off; d.ldy16 = C;
+          d.y16 = acts; d.ldy16 = AW;
           TCG(5, d, "flow.skip+post(tc)");
         }
       }
+      // the decoder's fp16 operand: both halves of z as the flows left them
+      CKC(3, launch_cl32_to_cl16(z, pl.z16, (long long)BT * C, 1.f, false, st), "z->fp16");
     }
     CK(tp.emit("z", z, sizeof(float) * BT * C), "tap");
 #undef TCG

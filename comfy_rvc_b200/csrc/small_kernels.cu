@@ -246,6 +246,30 @@ cudaError_t launch_cond_gemv(const float* emb_g, const long long* sid, const flo
   return cudaGetLastError();
 }
 
+// Flow, tensor path: the [x0 | mask | zeros] block in front of the gate outputs of the flow's activation buffer
+// (weights.py `flow.%d.inf.%d.w`): x0 = channels [in_off, in_off + half) of z16, the mask channel is 1 on frames < len.
+__global__ void flow_x0_init_kernel(const __half* __restrict__ z16, const int* __restrict__ len, __half* __restrict__ abuf, int T,
+                                    int C, int in_off, int half, int xb, int aw) {
+  const long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y;   // b * T + t
+  const int b = blockIdx.y;
+  const long long t = row;
+  if (t >= T) return;
+  const bool valid = t < len[b];
+  const __half* src = z16 + ((long long)b * T + t) * C + in_off;
+  __half* dst = abuf + ((long long)b * T + t) * aw;
+  for (int c = threadIdx.x; c < xb; c += blockDim.x)
+    dst[c] = c < half ? src[c] : (c == half && valid ? __float2half(1.f) : __float2half(0.f));
+}
+
+cudaError_t launch_flow_x0_init(const void* z16, const int* len, void* abuf, int B, int T, int C, int in_off, int half, int xb, int aw,
+                                cudaStream_t st) {
+  dim3 block(32, 8), grid((T + 7) / 8, B);
+  flow_x0_init_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const __half*>(z16), len, reinterpret_cast<__half*>(abuf), T, C, in_off,
+                                              half, xb, aw);
+  launch_counter().n++;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_zp_sample(const float* stats, const float* noise_cf, const int* len, float* zp, int B, int T, int C,
                              cudaStream_t st, float* z, void* z16) {
   dim3 grid((T + 31) / 32, (C + 31) / 32, B);

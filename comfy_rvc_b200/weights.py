@@ -207,6 +207,23 @@ def pack(cfg: SynthConfig, sd: Dict[str, torch.Tensor]) -> Tuple[Dict[str, torch
         # nothing non-linear between them, so the n skip launches and the post launch of a flow are ONE contraction of
         # the concatenated gate outputs [acts_0 | acts_1 | ...] (K = n H) with the folded weights W_skip_j W_post
         # (products in float64); masked frames are zeroed by the output mask either way.
+        # ... and `pre` and the res 1x1 convolutions fold into the NEXT in_layer: with m the frame mask,
+        #     h_j = (W_pre x0 + b_pre) m + sum_{l<j} (W_res_l acts_l + b_res_l) m        (modules.py:497, :199-205)
+        # so in_layer_j(h_j) is ONE k-tap convolution over the channels [x0 | m | 0.. | acts_0 | .. | acts_{j-1}] (x0 and acts
+        # arrive masked, m is a channel of its own that carries the bias terms through the zero padding and the mask edge
+        # exactly) with weights W_in_j[tap] applied after W_pre / (b_pre + sum b_res_l) / W_res_l.  The x0 block is padded
+        # to a multiple of 64 channels (one MMA k-block granule).  h is never materialised on the tensor path.
+        xb = flow_x0_block(cfg)
+        pre64, preb64 = P[f"flow.{i}.pre.w"].double(), P[f"flow.{i}.pre.b"].double()
+        for j in range(cfg.flow_wn_layers):
+            win = P[f"flow.{i}.in.{j}.w"].double()                               # [k][H][2H], gate-interleaved columns
+            rows = torch.zeros(win.shape[0], xb + j * H, 2 * H, dtype=torch.float64)
+            rows[:, :half] = torch.einsum("ch,khn->kcn", pre64, win)
+            bsum = preb64 + sum(P[f"flow.{i}.rs.{l}.res.b"].double() for l in range(j))
+            rows[:, half] = torch.einsum("h,khn->kn", bsum, win)
+            for l in range(j):
+                rows[:, xb + l * H: xb + (l + 1) * H] = torch.einsum("ah,khn->kan", P[f"flow.{i}.rs.{l}.res.w"].double(), win)
+            P[f"flow.{i}.inf.{j}.w"] = rows.float().contiguous()
         wp64 = P[f"flow.{i}.post.w"].double()
         P[f"flow.{i}.sp.w"] = torch.cat([P[f"flow.{i}.rs.{j}.skip.w"].double() @ wp64 for j in range(cfg.flow_wn_layers)],
                                         dim=0).float().contiguous()            # [n H][half]
@@ -258,6 +275,12 @@ TC_KB, TC_N_MAX = 64, 256
 TC_N_MAX_SMALL_M = 64   # text encoder / flow: few 128-row tiles per launch (T/128), so split C_out over more CTAs
 
 
+def flow_x0_block(cfg: SynthConfig) -> int:
+    """Columns of the [x0 | mask | zeros] block in front of the gate outputs in the flow's activation buffer (engine.cu)."""
+    half = cfg.inter_channels // 2
+    return (half + 1 + TC_KB - 1) // TC_KB * TC_KB
+
+
 def tc_n_max_for_name(name: str) -> int:
     """N-tile cap per packed tensor (same rule as csrc/engine.cu): the decoder's long time axis fills the GPU with
     M tiles and wants wide N; the text encoder and flow have T/128 (~47) M tiles per launch, so C_out is split into
@@ -298,11 +321,9 @@ def tc_weight_names(cfg: SynthConfig):
     for l in range(cfg.n_layers):
         names += [f"enc.{l}.qkv.w", f"enc.{l}.qkvp.w", f"enc.{l}.o.w", f"enc.{l}.ffn1.w", f"enc.{l}.ffn2.w"]
     for i in range(cfg.n_flows):
-        names += [f"flow.{i}.pre.w", f"flow.{i}.sp.w"]
+        names.append(f"flow.{i}.sp.w")
         for j in range(cfg.flow_wn_layers):
-            names.append(f"flow.{i}.in.{j}.w")
-            if j < cfg.flow_wn_layers - 1:
-                names.append(f"flow.{i}.rs.{j}.res.w")
+            names.append(f"flow.{i}.inf.{j}.w")
     nk = cfg.num_kernels
     for i in range(cfg.num_upsamples):
         names.append(f"dec.ups.{i}.w")

@@ -55,6 +55,15 @@ def test_flow_packing_matches_oracle(cfg_name):
         for j in range(cfg.flow_wn_layers):
             kf = cfg.flow_kernel
             xin = conv_cl(h, P[f"flow.{i}.in.{j}.w"][None], P[f"flow.{i}.in.{j}.b"], g_off=[-(kf - 1) // 2])
+            # the tensor path's folded form (engine.cu): the same in_layer over [x0 m | m | 0.. | acts_0 m | ..] -- `pre` and the res
+            # convolutions live in the weights, h is never formed
+            xb = weights.flow_x0_block(cfg)
+            if j == 0:
+                x0 = z[:, :, in_off:in_off + half] * m3
+                fold_in = torch.cat([x0, m3.expand(-1, -1, 1), x0.new_zeros(B, T, xb - half - 1)], dim=-1)
+            assert P[f"flow.{i}.inf.{j}.w"].shape == (kf, xb + j * H, 2 * H)
+            xin_fold = conv_cl(fold_in, P[f"flow.{i}.inf.{j}.w"][None], P[f"flow.{i}.in.{j}.b"], g_off=[-(kf - 1) // 2])
+            torch.testing.assert_close(xin_fold, xin, rtol=0, atol=5e-6)      # folded weights are stored in float32
             off = cfg.upsample_initial_channel + (i * cfg.flow_wn_layers + j) * 2 * H
             xin = xin + cond[:, None, off:off + 2 * H]
             acts = torch.tanh(xin[..., 0::2]) * torch.sigmoid(xin[..., 1::2])
@@ -63,6 +72,7 @@ def test_flow_packing_matches_oracle(cfg_name):
             sk = conv_cl(acts, P[f"flow.{i}.rs.{j}.skip.w"][None, None], P[f"flow.{i}.rs.{j}.skip.b"])
             skip = sk if skip is None else skip + sk
             acts_all = acts if j == 0 else torch.cat([acts_all, acts], dim=-1)
+            fold_in = torch.cat([fold_in, acts * m3], dim=-1)
         m = conv_cl(skip, P[f"flow.{i}.post.w"][None, None], P[f"flow.{i}.post.b"], in_len=lens) * m3
         # the tensor path's folded form (engine.cu "flow.skip+post"): one contraction of [acts_0 | acts_1 | ...] with W_skip_j W_post
         m_fold = conv_cl(acts_all, P[f"flow.{i}.sp.w"][None, None], P[f"flow.{i}.sp.b"], in_len=lens) * m3
