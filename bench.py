@@ -483,7 +483,10 @@ def main():
         cur.wait_stream(s_in)
         read_done[0] = read_done[1] = None
 
-    run_e2e(max(3, args.warmup) + 3)         # warm-up: lets the caching allocator reach its steady set of blocks
+    # warm-up: lets the caching allocator reach its steady set of blocks.  At least as many iterations as the timed region: since the
+    # step replays from a CUDA graph the host runs the whole region ahead of the GPU, every step's output tensors are live at once
+    # (record_stream), and a shorter warm-up left cudaMalloc calls inside the timed region (seen as one ~50 ms stall in 2 of 12 runs)
+    run_e2e(max(max(3, args.warmup) + 3, args.steps + 2))
     barrier()
     f0_, f1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0_.record()
