@@ -465,15 +465,17 @@ def main():
             ev.record(s_in)
         return dev_in[k], ev
 
-    def run_e2e(n):
+    def run_e2e(n, stamps=None):
         nxt = fetch(0)
         for i in range(n):
             ins, ev = nxt
             cur.wait_event(ev)
             nxt = fetch(i + 1)                         # H2D of the next step's inputs overlaps this step's kernels
             o = net.infer(*ins)[0]
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=stamps is not None)
             done.record(cur)
+            if stamps is not None:
+                stamps.append(done)
             read_done[i % 2] = done
             s_out.wait_event(done)
             with torch.cuda.stream(s_out):
@@ -490,10 +492,13 @@ def main():
     barrier()
     f0_, f1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0_.record()
-    run_e2e(args.steps)
+    e2e_stamps = []
+    run_e2e(args.steps, e2e_stamps)
     f1_.record()
     barrier()
     ms_e2e = f0_.elapsed_time(f1_)
+    # per-step completion times of the same K steps (diagnostic: a single stalled step shows up as max >> median)
+    e2e_step_ms = [f0_.elapsed_time(e2e_stamps[0])] + [e2e_stamps[i - 1].elapsed_time(e2e_stamps[i]) for i in range(1, len(e2e_stamps))]
     clocks = sampler.stop() if sampler else None
 
     if dist is not None:
@@ -526,7 +531,8 @@ def main():
         "config": config, "precision": args.precision,
         "roofline_pass": "per-launch CUDA events in a second pass of the same K steps (kept out of `value`)",
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": T * cfg.upp * 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "step_ms_median": sorted(e2e_step_ms)[len(e2e_step_ms) // 2], "step_ms_max": max(e2e_step_ms)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "decoder resblock convolutions (rbconv_tc_kernel + fused-pair rbpair_tc_kernel on tcgen05; conv_f32_kernel in fp32 mode)",
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],

@@ -204,7 +204,7 @@ attention_tc_kernel(const AttArgs a, const __grid_constant__ CUtensorMap tmK, co
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
   if (threadIdx.x == 0) pdl_trigger();
-  pdl_wait();                            // q|k|v (and V^T) come from the kernels just before
+  pdl_wait();                            // q|k|v come from the kernel just before
   const int L = min(a.len ? a.len[b] : a.T, a.T);
   const int nrel = 2 * a.window + 1;
 

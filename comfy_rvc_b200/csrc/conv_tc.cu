@@ -1291,7 +1291,7 @@ cudaError_t launch_noise_add16(const float* har, const float* wn, const float* n
   if (C % 8 != 0 || s < 1 || k < 1 || !har || !wn || !nb || !x16) return cudaErrorInvalidValue;
   // tile rows: ~32 KB of stream per tile (two block-wide barriers per tile), shrunk until taps + source segment fit
   int TR = 512;
-  while (TR > 32 && (long long)TR * C > 16384) TR >>= 1;
+  while (TR > 32 && (long long)TR * C > 16384) TR >>= 1;      // (8 K - 64 K elements per tile measured: no difference)
   auto smem_for = [&](int tr) { return sizeof(float) * ((size_t)k * C + C + (size_t)(tr + (k + s - 1) / s) * (s + 1)); };
   while (TR > 8 && smem_for(TR) > 100 * 1024) TR >>= 1;
   const size_t smem = smem_for(TR);

@@ -309,19 +309,18 @@ class HubertB200:
             # encoder layers (post-norm)
             nh = self.n_heads
             qkv16 = torch.empty(T, 3 * nh * HEAD_PAD, dtype=torch.float16, device=dev)
-            vt16 = torch.empty(nh * HEAD_PAD * ((T + 7) // 8 * 8), dtype=torch.float16, device=dev)
             att16 = torch.empty(T, nh * HEAD_OUT, dtype=torch.float16, device=dev)
             ff16 = torch.empty(T, self.inter, dtype=torch.float16, device=dev)
             for l in range(n_layers):
                 w16, nt_ = self._tiled(f"l{l}.qkv.w", T, 3 * nh * HEAD_PAD)
                 self._gemm(h16.data_ptr(), T, H, w16, W[f"l{l}.qkv.b"], 3 * nh * HEAD_PAD, T, n_tile=nt_, y16=qkv16.data_ptr(),
                            ldy16=3 * nh * HEAD_PAD)
-                st = lib.rvcb200_op_attention_tc(C.c_void_p(qkv16.data_ptr()), C.c_void_p(vt16.data_ptr()),
+                st = lib.rvcb200_op_attention_tc(C.c_void_p(qkv16.data_ptr()), None,      # V is read in place: no V^T scratch
                                                  C.c_void_p(W["ek0"].data_ptr()), C.c_void_p(W["evt0"].data_ptr()), None,
                                                  C.c_void_p(att16.data_ptr()), 1, T, nh, HEAD_OUT, 0, self._stream)
                 if st != 0:
                     raise RuntimeError(f"rvcb200_op_attention_tc failed with status {st}")
-                self.last_launches += 2
+                self.last_launches += 1
                 w16, nt_ = self._tiled(f"l{l}.o.w", T, H)
                 self._gemm(att16.data_ptr(), T, nh * HEAD_OUT, w16, W[f"l{l}.o.b"], H, T, n_tile=nt_, y32=t32.data_ptr(), ldy32=H,
                            res32=h32.data_ptr(), ldr32=H)
