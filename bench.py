@@ -429,6 +429,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = net.last_launches * args.steps
+    graph_replay = bool(getattr(net, "last_graph_replay", False))   # the timed steps ran as replays of the captured step
     # per-class kernel times: a second pass of the same K steps with a CUDA-event pair around every launch (the event
     # records sit between kernels and serialise their programmatic dependent launches, so they stay out of `value`)
     lib.rvcb200_profile_enable(net._ctx, 1)
@@ -534,6 +535,8 @@ def main():
                 "ms_per_step": ms_e2e / args.steps,
                 "step_ms_median": sorted(e2e_step_ms)[len(e2e_step_ms) // 2], "step_ms_max": max(e2e_step_ms)},
         "gpu_launches": int(launches),
+        "launch_mode": ("CUDA graph replay of the step captured during warm-up (synthesizer.py: shapes seen before); gpu_launches = its kernel nodes"
+                        if graph_replay else "stream launches"),
         "roofline": {"bound": "tensor", "kernel": "decoder resblock convolutions (rbconv_tc_kernel + fused-pair rbpair_tc_kernel on tcgen05; conv_f32_kernel in fp32 mode)",
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                      "traffic": (tr["bytes_per_step"] / tr["launches_per_step"]) if tr else None,
