@@ -37,6 +37,21 @@ class _IncompatibleKeys:
         return f"<missing={self.missing_keys} unexpected={self.unexpected_keys}>"
 
 
+def graph_policy(key, frames: int, max_frames: int, repeat: bool, seen: "OrderedDict", graphs) -> bool:
+    """Should this infer() call go through a CUDA graph?  Launch-bound sizes (`frames <= max_frames`) always do; larger calls
+    do from the second time their key (B, T, precision) occurs (`repeat`), so a length that occurs once never pays for a
+    capture; a key that already has a graph keeps using it.  `max_frames == 0` switches the mechanism off.  Records the key in
+    `seen` (bounded, least recently used first out).  Host logic only: tested on the CPU (tests/test_pipeline_host.py)."""
+    if max_frames <= 0:
+        return False
+    use = frames <= max_frames or (repeat and key in seen) or key in graphs
+    seen[key] = None
+    seen.move_to_end(key)
+    while len(seen) > 256:
+        seen.popitem(last=False)
+    return use
+
+
 class SynthesizerB200(nn.Module):
     """Common implementation; subclasses fix `feat_dim` (TextEncoder256 vs TextEncoder768)."""
 
@@ -302,14 +317,8 @@ class SynthesizerB200(nn.Module):
             if self.f0:
                 ins.update(pitch=pitch_d, f0=f0_d, ns=ns)
             self.last_graph_replay = False
-            use_graph = False
-            if taps is None and self.graph_max_frames > 0:
-                key = (B, T, prec)
-                use_graph = B * T <= self.graph_max_frames or (self.graph_repeat and key in self._seen_keys) or key in self._graphs
-                self._seen_keys[key] = None
-                self._seen_keys.move_to_end(key)
-                while len(self._seen_keys) > 256:
-                    self._seen_keys.popitem(last=False)
+            use_graph = taps is None and graph_policy((B, T, prec), B * T, self.graph_max_frames, self.graph_repeat, self._seen_keys,
+                                                       self._graphs)
             if use_graph:
                 o, stats, z_p, z = self._infer_graphed(B, T, prec, ins)
             else:
